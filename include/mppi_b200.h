@@ -1,0 +1,171 @@
+/*
+ * mppi_b200.h — C ABI of libmppi_b200.so, the Blackwell (sm_100a) MPPI rollout-and-reduce engine.
+ *
+ * This is the drop-in boundary for the reference's hot path. The reference has no ABI: its
+ * controllers call the templated launchers of include/mppi/core/mppi_common.cuh:206-247 plus the sampler methods of
+ * include/mppi/sampling_distributions/sampling_distribution.cuh:367-401 directly. Templates cannot cross a C ABI, so
+ * each entry point below names the reference interface it replaces; the header-only host layer
+ * (the .hpp files under include/mppi_b200/, same class / method names as the reference) and the ctypes mirror
+ * (mppi-generic_b200/host.py) are the only callers. INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions: every function returns 0 on success or a negative mppib_status; nothing exit()s or throws across the
+ * boundary (the reference's HANDLE_ERROR -> exit behaviour, include/mppi/utils/gpu_err_chk.cuh:32-40, is restored by
+ * the host layer). Host arrays are caller-owned, plain float/int pointers; device memory, the cuRAND generator, streams
+ * and the NCCL communicator are owned by the opaque engine. One engine = one caller thread at a time (same rule as
+ * the reference: include/mppi/core/base_plant.hpp:464-468 serialises access with a mutex).
+ *
+ * Layouts (identical to the reference):
+ *   samples  [D][N][T][C]  ((N*d + n)*T + t)*C + c        sampling_distribution.cu:175-177
+ *   costs    [D][N]        n + N*d                        mppi_common.cu:850
+ *   means/U  [D][T][C]     (T*d + t)*C + c  == Eigen C x T column-major   gaussian.cu:494
+ *   x0       [D][S]        S*d + i                        mppi_common.cu:781
+ */
+#ifndef MPPI_B200_H_
+#define MPPI_B200_H_
+
+#include <stddef.h>
+#include "mppi_b200/params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mppib_engine mppib_engine; /* opaque */
+
+enum mppib_status
+{
+  MPPIB_OK = 0,
+  MPPIB_ERR_INVALID_ARG = -1,
+  MPPIB_ERR_UNSUPPORTED = -2, /* no kernel registered for (dynamics, cost, sampler, D) */
+  MPPIB_ERR_CUDA = -3,        /* a CUDA runtime call failed; mppib_last_error() has the text */
+  MPPIB_ERR_CURAND = -4,
+  MPPIB_ERR_NO_DEVICE = -5, /* no CUDA device / driver: the engine never falls back to the CPU */
+  MPPIB_ERR_NCCL = -6,
+  MPPIB_ERR_SMEM = -7, /* horizon tile does not fit in shared memory (mirrors mppi_controller.cu:64-76 runtime_error) */
+  MPPIB_ERR_CUFFT = -8,
+  MPPIB_ERR_STATE = -9 /* call order violated (e.g. solve before blobs were set) */
+};
+
+enum mppib_blob
+{
+  MPPIB_BLOB_DYN_PARAMS = 0,  /* Dynamics::setParams + control ranges   dynamics.cuh:147-175 */
+  MPPIB_BLOB_COST_PARAMS = 1, /* Cost::setParams                         cost.cuh:97-105      */
+  MPPIB_BLOB_SAMPLER_PARAMS = 2, /* SamplingDistribution::setParams      sampling_distribution.cuh */
+  MPPIB_BLOB_NN_WEIGHTS = 3,  /* NeuralNetModel::updateModel             ar_nn_model.cu:40-45 (packed W,b per layer) */
+  MPPIB_BLOB_COSTMAP = 4,     /* ARStandardCost::costmapToTexture        ar_standard_cost.cu:145-184 (float4 texels) */
+  MPPIB_BLOB_LSTM_WEIGHTS = 5 /* LSTMHelper weights                      lstm_helper.cu:72-88 */
+};
+
+/* Flags for mppib_desc.flags */
+#define MPPIB_FLAG_WRITEBACK_CONTROLS 1u /* keep the constrained sampled controls in HBM like the reference does    \
+                                            (mppi_common.cu:117); needed by mppib_get_samples */
+#define MPPIB_FLAG_NO_TMA 2u             /* stage noise tiles with plain loads instead of cp.async.bulk.tensor */
+#define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
+                                            bit-identical XORWOW kernel */
+
+typedef struct mppib_desc
+{
+  int dynamics_id;       /* enum mppib_dynamics_id */
+  int cost_id;           /* enum mppib_cost_id */
+  int sampler_id;        /* enum mppib_sampler_id */
+  int num_rollouts;      /* N  (template NUM_ROLLOUTS in the reference) — GLOBAL count across all ranks */
+  int num_timesteps;     /* T  (<= MAX_TIMESTEPS in the reference) */
+  int num_distributions; /* D: 1 = VanillaMPPI, 2 = Tube-MPPI / RMPPI (blockDim.z in the reference) */
+  int device;            /* CUDA device ordinal (the reference hard-codes 0, mppi_controller.cu:48) */
+  unsigned flags;
+  void* stream; /* cudaStream_t to run on (Controller::setCUDAStream, controller.cuh:901); NULL = engine-owned */
+  /* rollout sharding across GPUs. rank r owns samples [r*N/W, (r+1)*N/W). */
+  int rank;
+  int world_size;
+} mppib_desc;
+
+/* Per-solve statistics for one distribution (getBaselineCost / getNormalizerCost, controller.cuh:510-517, and the
+ * inputs of computeFreeEnergy, mppi_common.cu:1065-1081). */
+typedef struct mppib_solve_stats
+{
+  float baseline;   /* beta = min_n cost */
+  float normalizer; /* eta  = sum_n w_n */
+  float sum_w2;     /* sum_n w_n^2 */
+  float pad;
+} mppib_solve_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+/* Replaces Controller::Controller + allocateCUDAMemoryHelper + createAndSeedCUDARandomNumberGen
+ * (controller.cuh:111-152, controller.cu:192-236) and the plugins' GPUSetup() (managed.cuh:121-131). */
+int mppib_create(mppib_engine** out, const mppib_desc* desc);
+/* Replaces Controller::~Controller / freeCudaMem (controller.cuh:194-216). */
+int mppib_destroy(mppib_engine* e);
+
+/* ---- configuration ----------------------------------------------------------------------------- */
+/* Replaces <plugin>::setParams -> paramsToDevice (dynamics.cu:36-58, cost.cu:5-13, sampling_distribution.cu:52-70). */
+int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes);
+/* Replaces Controller::setParams for the fields the device path uses (dt_, lambda_, alpha_; controller.cuh:46-68). */
+int mppib_set_solver(mppib_engine* e, float dt, float lambda, float alpha);
+/* Replaces Controller::setSeedCUDARandomNumberGen: seed and absolute offset (controller.cu:200-207 resets offset to 0). */
+int mppib_seed(mppib_engine* e, unsigned long long seed, unsigned long long offset);
+/* Consume n_generate_calls noise draws without using them — mirrors the draw made by
+ * VanillaMPPIController::chooseAppropriateKernel (mppi_controller.cu:95) so RNG offsets stay in lock-step. */
+int mppib_burn_draws(mppib_engine* e, int n_generate_calls);
+/* Current absolute RNG offset in normals (checkpoint/resume: SURVEY §5). */
+int mppib_get_rng_offset(mppib_engine* e, unsigned long long* offset);
+/* Join an NCCL communicator for world_size > 1. unique_id = the 128-byte ncclUniqueId created on rank 0 and
+ * distributed by the caller (torch.distributed / MPI / a file). No reference counterpart (single GPU only). */
+int mppib_comm_unique_id(void* unique_id_128);
+int mppib_comm_init(mppib_engine* e, const void* unique_id_128);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* One optimisation iteration of Controller::computeControl up to the new mean — replaces, in one call:
+ *   cudaMemcpyAsync(initial_state_d_), copyNominalControlToDevice      mppi_controller.cu:157-165
+ *   SAMPLING_T::generateSamples                                        gaussian.cu:375-431
+ *   launchRolloutKernel / launchSplitRolloutKernel                     mppi_common.cu:1259-1325
+ *   D2H costs, computeBaselineCost, launchNormExpKernel, computeNormalizer   mppi_controller.cu:187-208
+ *   updateDistributionParamsFromDevice -> launchWeightedReductionKernel      gaussian.cu:434-457
+ *   setHostOptimalControlSequence                                      gaussian.cu:460-478
+ * x0 [D][S], U_in [D][T][C], U_out [D][T][C], stats [D] are host arrays. iteration_num scales std_dev by
+ * std_dev_decay^iteration_num (gaussian.cu:423). Blocks until U_out is valid. */
+int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num,
+                float* U_out, mppib_solve_stats* stats);
+
+/* Kernel-level parity hooks (the reference tests kernels in isolation: tests/mppi_core/rollout_kernel_tests.cu). */
+/* mppib_set_noise: overwrite the raw N(0,1) buffer [N_local][T][C] from the host (tests with hand-made noise).
+ * mppib_draw_noise: one generateSamples-equivalent draw into the buffer, advancing the RNG offset.
+ * mppib_rollout_only: launchRolloutKernel on the current buffer; no draw. costs -> mppib_get_costs. */
+int mppib_set_noise(mppib_engine* e, const float* host_eps, size_t count);
+int mppib_draw_noise(mppib_engine* e);
+int mppib_rollout_only(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride,
+                       int iteration_num);
+/* mppib_reduce_only: baseline / weights / weighted average over the costs and samples of the last rollout. */
+int mppib_reduce_only(mppib_engine* e, float* U_out, mppib_solve_stats* stats);
+
+/* ---- read-backs (getSampledCostSeq controller.cuh:431-436, getSampledNoise :778) ---------------- */
+int mppib_get_costs(mppib_engine* e, float* host_costs /*[D][N_local]*/);
+int mppib_get_noise(mppib_engine* e, float* host_eps /*[N_local][T][C] raw N(0,1)*/);
+int mppib_get_samples(mppib_engine* e, float* host_samples /*[D][N_local][T][C]; needs WRITEBACK_CONTROLS*/);
+/* importance-sampling weights w_n = exp(-(c_n - beta)/lambda) of the last solve (trajectory_costs_d_ after
+ * launchNormExpKernel in the reference). */
+int mppib_get_weights(mppib_engine* e, float* host_weights /*[D][N_local]*/);
+
+/* ---- introspection / timing -------------------------------------------------------------------- */
+typedef struct mppib_timing
+{
+  float noise_ms;   /* K0 draw */
+  float rollout_ms; /* K1 fused rollout */
+  float reduce_ms;  /* K2 combine (+ collective) */
+  float total_ms;   /* first launch to last kernel end, device time */
+} mppib_timing;
+/* Enable CUDA-event timestamps around each stage of subsequent solves (adds ~us; off by default). */
+int mppib_enable_timing(mppib_engine* e, int enable);
+int mppib_get_timing(mppib_engine* e, mppib_timing* out);
+/* Launch geometry actually used by K1 (for bench.py / DESIGN.md). */
+int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_bytes, int* uses_tma,
+                          int* kernels_per_solve);
+int mppib_local_rollouts(mppib_engine* e, int* n_local, int* n_offset);
+
+const char* mppib_strerror(int status);
+const char* mppib_last_error(void); /* thread-local text of the last failure */
+int mppib_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H_ */

@@ -1,0 +1,30 @@
+/*
+ * mppi_b200/host_twins.h — CPU twins of the plugins and the controller's host tail, exported by libmppi_b200.so
+ * (mppi-generic_b200/csrc/host_twins.cpp). Each replaces a host method of the reference's templated classes:
+ *   mppib_host_enforce_constraints  Dynamics::enforceConstraints          include/mppi/dynamics/dynamics.cuh:250-264
+ *   mppib_host_step                 Dynamics::step (host)                 dynamics.cuh:283-290
+ *   mppib_host_smooth_controls      Controller::smoothControlTrajectoryHelper   controllers/controller.cuh:557-586
+ *   mppib_host_slide_controls       Controller::slideControlSequenceHelper      controller.cuh:588-600
+ *   mppib_host_output_trajectory    Controller::computeOutputTrajectoryHelper   controller.cuh:643-663
+ *   mppib_host_free_energy          mppi::kernels::computeFreeEnergy      include/mppi/core/mppi_common.cu:1065-1081
+ * Arrays: u / history are [T][C] / [2][C] (== Eigen C x T / C x 2 column-major), states [T][S], outputs [T][O].
+ */
+#ifndef MPPI_B200_HOST_TWINS_H_
+#define MPPI_B200_HOST_TWINS_H_
+#include "../mppi_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+int mppib_host_dims(int dyn_id, int* S, int* C, int* O);
+int mppib_host_enforce_constraints(int dyn_id, const void* dyn_params, float* u);
+int mppib_host_step(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x, const float* u,
+                    float dt, float* x_next, float* xdot, float* y);
+void mppib_host_smooth_controls(float* u, const float* history, int T, int C);
+void mppib_host_slide_controls(float* u, int steps, int T, int C, const float* zero_control, const float* scale);
+int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x0,
+                                 const float* u, int T, float dt, float* states, float* outputs);
+void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float lambda, float* out3);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1008 @@
+/*
+ * engine.cu — the C-ABI (include/mppi_b200.h) and the host-side orchestration of one MPPI solve on one B200:
+ *   K0 noise draw (cuRAND XORWOW, same generator / seed / offset / count as controllers/controller.cu:192-207 and
+ *      sampling_distributions/gaussian/gaussian.cu:380-381, so sample indexing is bit-identical to the reference)
+ *   K1 fused rollout                (rollout_kernel.cuh)
+ *   K2 baseline / weights / average (combine_kernel.cuh)  [+ one NCCL all-gather and a second K2 when world_size > 1]
+ * One stream, no host round trip between the kernels (the reference synchronises three times per iteration,
+ * controllers/MPPI/mppi_controller.cu:187-218); x0 and the nominal controls travel in the kernel parameter bank and
+ * the result record is written by K2 straight into mapped pinned host memory, so a solve issues no cudaMemcpy.
+ *
+ * The engine never computes on the CPU: without a CUDA device mppib_create fails with MPPIB_ERR_NO_DEVICE.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <curand.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mppi_b200.h"
+#include "combine_kernel.cuh"
+#include "plugins/costs.cuh"
+#include "plugins/dynamics.cuh"
+#include "rollout_kernel.cuh"
+
+namespace
+{
+thread_local std::string g_last_error;
+
+int fail(int status, const char* fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return status;
+}
+
+#define CUDA_TRY(expr)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess)                                                                                             \
+    {                                                                                                                  \
+      cudaGetLastError();                                                                                              \
+      return fail(MPPIB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);         \
+    }                                                                                                                  \
+  } while (0)
+
+#define CURAND_TRY(expr)                                                                                               \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    curandStatus_t _s = (expr);                                                                                        \
+    if (_s != CURAND_STATUS_SUCCESS)                                                                                   \
+      return fail(MPPIB_ERR_CURAND, "%s failed: curandStatus %d (%s:%d)", #expr, (int)_s, __FILE__, __LINE__);         \
+  } while (0)
+
+// ---- minimal NCCL binding, resolved lazily with dlopen so single-GPU users need no NCCL at all --------------------
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId
+{
+  char internal[128];
+};
+struct NcclApi
+{
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load()
+  {
+    if (handle)
+      return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names)
+    {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle)
+        break;
+    }
+    if (!handle)
+      return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat = 7;  // ncclFloat32
+
+}  // namespace
+
+using namespace mppib;
+
+// ---- engine state -----------------------------------------------------------------------------------------------
+struct mppib_engine
+{
+  mppib_desc desc{};
+  int S = 0, C = 0, O = 0, D = 1;
+  int N = 0, T = 0, TC = 0;
+  int n_local = 0, n_offset = 0;
+  int pstride = 0, nchunks = 0;
+  int bx = 64, grid = 0;
+  uint32_t smem_bytes = 0;
+  bool use_tma = false;
+  bool writeback = false;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  // solver scalars
+  float dt = 0.01f, lambda = 1.0f, alpha = 0.0f;
+
+  // parameter blobs (host copies)
+  std::vector<unsigned char> dyn_blob, cost_blob;
+  mppib_gaussian_params sampler{};
+  bool have_dyn = false, have_cost = false, have_sampler = false;
+
+  // aux device resources
+  float* nn_theta_d = nullptr;
+  cudaArray_t costmap_array = nullptr;
+  cudaTextureObject_t costmap_tex = 0;
+
+  // RNG
+  curandGenerator_t gen = nullptr;
+  unsigned long long seed = 0;
+  unsigned long long rng_offset = 0;  // absolute position (in normals) of the next GLOBAL draw
+  bool rng_positioned = false;        // generator's internal position == what the next local draw needs
+
+  // device buffers
+  float* noise_alloc = nullptr;  // allocation incl. lead-in space for offset alignment
+  float* eps_d = nullptr;        // [n_local][T][C]
+  float* costs_d = nullptr;      // [D][n_local]
+  float* partials_d = nullptr;   // [grid][D][pstride]
+  float* controls_d = nullptr;   // optional [D][n_local][T][C]
+  float* rank_rec_d = nullptr;   // [D][pstride] this rank's record (world > 1)
+  float* gather_d = nullptr;     // [world][D][pstride]
+  float* result_d = nullptr;     // [D][pstride] final record (device copy)
+  float* result_h = nullptr;     // mapped pinned host copy K2 writes directly
+  float* result_h_dev = nullptr; // device alias of result_h
+  float* weights_d = nullptr;    // lazily allocated for mppib_get_weights
+
+  CUtensorMap tmap{};
+
+  // comm
+  ncclComm_t comm = nullptr;
+
+  // timing
+  bool timing = false;
+  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+  bool timing_valid = false;
+
+  // registry hook
+  int (*launch_rollout)(mppib_engine&, const float* x0, const float* U_in, int opt_stride, int iter) = nullptr;
+  size_t dyn_param_bytes = 0, cost_param_bytes = 0;
+  int dyn_shared_floats = 0;
+  int (*prepare)(mppib_engine&) = nullptr;  // sets func attributes
+  bool solved_once = false;
+};
+
+// ---- registry of (dynamics, cost) pairs compiled into this library ---------------------------------------------
+template <class AUX>
+struct AuxFill
+{
+  static void fill(AUX&, const mppib_engine&)
+  {
+  }
+};
+template <>
+struct AuxFill<plugins::AutorallyNNDynamics::Aux>
+{
+  static void fill(plugins::AutorallyNNDynamics::Aux& a, const mppib_engine& e)
+  {
+    a.theta_d = e.nn_theta_d;
+  }
+};
+template <>
+struct AuxFill<plugins::ARStandardCost::Aux>
+{
+  static void fill(plugins::ARStandardCost::Aux& a, const mppib_engine& e)
+  {
+    a.costmap_tex = e.costmap_tex;
+  }
+};
+
+template <class DYN, class COST>
+struct Pair
+{
+  using Args = RolloutArgs<DYN, COST>;
+
+  static int prepare(mppib_engine& e)
+  {
+    if (e.D == 1)
+      CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)e.smem_bytes));
+    else
+      CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)e.smem_bytes));
+    return MPPIB_OK;
+  }
+
+  static int launch(mppib_engine& e, const float* x0, const float* U_in, int opt_stride, int iter)
+  {
+    static_assert(sizeof(Args) < 30000, "kernel parameter block too large");
+    Args a;
+    memcpy(&a.dyn, e.dyn_blob.data(), sizeof(a.dyn));
+    memcpy(&a.cost, e.cost_blob.data(), sizeof(a.cost));
+    AuxFill<typename DYN::Aux>::fill(a.dyn_aux, e);
+    AuxFill<typename COST::Aux>::fill(a.cost_aux, e);
+    const float decay = powf(e.sampler.std_dev_decay, (float)iter);  // gaussian.cu:423
+    for (int d = 0; d < MPPIB_MAX_DISTRIBUTIONS; d++)
+      for (int c = 0; c < MPPIB_MAX_CONTROL_DIM; c++)
+      {
+        const float sd = (c < e.C) ? e.sampler.std_dev[d * e.C + c] : 1.0f;
+        a.samp.std_dev[d][c] = sd;
+        a.samp.std_dev_decayed[d][c] = decay * sd;  // gaussian.cu:86-90
+      }
+    for (int c = 0; c < MPPIB_MAX_CONTROL_DIM; c++)
+      a.samp.control_cost_coeff[c] = e.sampler.control_cost_coeff[c];
+    a.samp.pure_noise_threshold = (1.0f - e.sampler.pure_noise_trajectories_percentage) * e.N;  // gaussian.cu:108
+    a.eps = e.eps_d;
+    a.costs = e.costs_d;
+    a.partials = e.partials_d;
+    a.controls_out = e.writeback ? e.controls_d : nullptr;
+    a.n_local = e.n_local;
+    a.n_offset = e.n_offset;
+    a.T = e.T;
+    a.nchunks = e.nchunks;
+    a.pstride = e.pstride;
+    a.opt_stride = opt_stride;
+    a.use_tma = e.use_tma ? 1 : 0;
+    a.dt = e.dt;
+    a.lambda = e.lambda;
+    a.alpha = e.alpha;
+    a.lambda_inv = (float)(1.0 / e.lambda);  // mppi_controller.cu:201-202: 1.0 / lambda in double, narrowed
+    memcpy(a.x0, x0, sizeof(float) * e.D * e.S);
+    memcpy(a.means, U_in, sizeof(float) * e.D * e.TC);
+    if (e.D == 1)
+      rollout_kernel<DYN, COST, 1><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+    else
+      rollout_kernel<DYN, COST, 2><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+    CUDA_TRY(cudaGetLastError());
+    return MPPIB_OK;
+  }
+};
+
+struct PairEntry
+{
+  int dyn_id, cost_id;
+  int S, C, O;
+  size_t dyn_bytes, cost_bytes;
+  int dyn_shared_floats;
+  int (*launch)(mppib_engine&, const float*, const float*, int, int);
+  int (*prepare)(mppib_engine&);
+};
+template <class DYN, class COST>
+constexpr PairEntry make_entry(int dyn_id, int cost_id)
+{
+  return PairEntry{ dyn_id,
+                    cost_id,
+                    DYN::STATE_DIM,
+                    DYN::CONTROL_DIM,
+                    DYN::OUTPUT_DIM,
+                    sizeof(typename DYN::Params),
+                    sizeof(typename COST::Params),
+                    DYN::SHARED_FLOATS,
+                    &Pair<DYN, COST>::launch,
+                    &Pair<DYN, COST>::prepare };
+}
+static const PairEntry kPairs[] = {
+  make_entry<plugins::CartpoleDynamics, plugins::CartpoleQuadraticCost>(MPPIB_DYN_CARTPOLE,
+                                                                        MPPIB_COST_CARTPOLE_QUADRATIC),
+  make_entry<plugins::DoubleIntegratorDynamics, plugins::DoubleIntegratorCircleCost>(MPPIB_DYN_DOUBLE_INTEGRATOR,
+                                                                                     MPPIB_COST_DI_CIRCLE),
+  make_entry<plugins::AutorallyNNDynamics, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
+};
+
+// ---- helpers ----------------------------------------------------------------------------------------------------
+static int make_tensor_map(mppib_engine& e)
+{
+  // 2-D view of the noise buffer: rows = local rollouts, cols = T*C floats (row pitch T*C*4 B, must be 16-B multiple)
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fail(MPPIB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = { (cuuint64_t)e.TC, (cuuint64_t)e.n_local };
+  cuuint64_t gstride[1] = { (cuuint64_t)e.TC * sizeof(float) };
+  cuuint32_t box[2] = { (cuuint32_t)kChunkFloats, (cuuint32_t)e.bx };
+  cuuint32_t estride[2] = { 1, 1 };
+  CUresult r = ((EncodeFn)fn)(&e.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e.eps_d, gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MPPIB_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+  return MPPIB_OK;
+}
+
+static int draw_noise(mppib_engine& e)
+{
+  // One generateSamples-equivalent draw (gaussian.cu:378-394): N*T*C normals of the single global XORWOW stream;
+  // this rank keeps elements [n_offset*T*C, (n_offset+n_local)*T*C) of it.
+  const unsigned long long global_count = (unsigned long long)e.N * e.TC;
+  const unsigned long long start = e.rng_offset + (unsigned long long)e.n_offset * e.TC;
+  const size_t count = (size_t)e.n_local * e.TC;
+  if (e.desc.world_size == 1 && e.rng_positioned)
+  {
+    // generator already sits at `start`: plain continuation, exactly what the reference does call after call
+    CURAND_TRY(curandGenerateNormal(e.gen, e.eps_d, count, 0.0f, 1.0f));
+  }
+  else
+  {
+    // XORWOW default ordering interleaves 4096 streams x 2 normals: absolute offsets are honoured at multiples of
+    // 8192 (probed on B200, tools/curand_probe.cu), so start from the aligned position below and discard the lead-in.
+    const unsigned long long aligned = (start / 8192ULL) * 8192ULL;
+    const size_t lead = (size_t)(start - aligned);
+    if (((lead + count) & 1) != 0)
+      return fail(MPPIB_ERR_UNSUPPORTED, "cuRAND normal draws need an even count (lead %zu + count %zu)", lead, count);
+    CURAND_TRY(curandSetGeneratorOffset(e.gen, aligned));
+    CURAND_TRY(curandGenerateNormal(e.gen, e.eps_d - lead, lead + count, 0.0f, 1.0f));
+  }
+  e.rng_offset += global_count;
+  e.rng_positioned = (e.desc.world_size == 1);
+  return MPPIB_OK;
+}
+
+static int launch_combine(mppib_engine& e)
+{
+  const dim3 grid((e.TC + kCombineCols - 1) / kCombineCols, e.D);
+  const float lambda_inv = (float)(1.0 / e.lambda);
+  if (e.desc.world_size == 1 || !e.comm)
+  {
+    combine_kernel<<<grid, kCombineCols * kCombineGroups, 0, e.stream>>>(e.partials_d, e.grid, e.D, e.TC, e.pstride,
+                                                                        lambda_inv, 1, e.result_d, e.result_h_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MPPIB_OK;
+  }
+  // rank record (un-normalised) -> all-gather -> merge of the world_size records (normalised)
+  combine_kernel<<<grid, kCombineCols * kCombineGroups, 0, e.stream>>>(e.partials_d, e.grid, e.D, e.TC, e.pstride,
+                                                                      lambda_inv, 0, e.rank_rec_d, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  const size_t rec_floats = (size_t)e.D * e.pstride;
+  int rc = g_nccl.AllGather(e.rank_rec_d, e.gather_d, rec_floats, kNcclFloat, e.comm, e.stream);
+  if (rc != 0)
+    return fail(MPPIB_ERR_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  combine_kernel<<<grid, kCombineCols * kCombineGroups, 0, e.stream>>>(e.gather_d, e.desc.world_size, e.D, e.TC,
+                                                                      e.pstride, lambda_inv, 1, e.result_d,
+                                                                      e.result_h_dev);
+  CUDA_TRY(cudaGetLastError());
+  return MPPIB_OK;
+}
+
+static int check_ready(mppib_engine* e)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (!e->have_dyn || !e->have_cost || !e->have_sampler)
+    return fail(MPPIB_ERR_STATE, "dynamics / cost / sampler parameter blobs must be set before solving");
+  if (e->desc.dynamics_id == MPPIB_DYN_AUTORALLY_NN && !e->nn_theta_d)
+    return fail(MPPIB_ERR_STATE, "MPPIB_BLOB_NN_WEIGHTS not set");
+  if (e->desc.cost_id == MPPIB_COST_AR_STANDARD && !e->costmap_tex)
+    return fail(MPPIB_ERR_STATE, "MPPIB_BLOB_COSTMAP not set");
+  if (e->desc.world_size > 1 && !e->comm)
+    return fail(MPPIB_ERR_STATE, "world_size > 1 but mppib_comm_init was not called");
+  return MPPIB_OK;
+}
+
+static void read_result(mppib_engine& e, float* U_out, mppib_solve_stats* stats)
+{
+  for (int d = 0; d < e.D; d++)
+  {
+    const float* r = e.result_h + (size_t)d * e.pstride;
+    if (stats)
+    {
+      stats[d].baseline = r[0];
+      stats[d].normalizer = r[1];
+      stats[d].sum_w2 = r[2];
+      stats[d].pad = 0.0f;
+    }
+    if (U_out)
+      memcpy(U_out + (size_t)d * e.TC, r + kPartialHeader, sizeof(float) * e.TC);
+  }
+}
+
+// =================================================================================================================
+extern "C" {
+
+int mppib_version(void)
+{
+  return 100;
+}
+
+const char* mppib_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+const char* mppib_strerror(int status)
+{
+  switch (status)
+  {
+    case MPPIB_OK:
+      return "ok";
+    case MPPIB_ERR_INVALID_ARG:
+      return "invalid argument";
+    case MPPIB_ERR_UNSUPPORTED:
+      return "unsupported plugin combination or size";
+    case MPPIB_ERR_CUDA:
+      return "CUDA runtime error";
+    case MPPIB_ERR_CURAND:
+      return "cuRAND error";
+    case MPPIB_ERR_NO_DEVICE:
+      return "no CUDA device (the engine has no CPU fallback)";
+    case MPPIB_ERR_NCCL:
+      return "NCCL error";
+    case MPPIB_ERR_SMEM:
+      return "rollout tile does not fit in shared memory";
+    case MPPIB_ERR_CUFFT:
+      return "cuFFT error";
+    case MPPIB_ERR_STATE:
+      return "call order violated";
+  }
+  return "unknown status";
+}
+
+int mppib_create(mppib_engine** out, const mppib_desc* desc)
+{
+  if (!out || !desc)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (desc->num_rollouts <= 0 || desc->num_timesteps <= 0)
+    return fail(MPPIB_ERR_INVALID_ARG, "num_rollouts and num_timesteps must be positive");
+  if (desc->num_distributions < 1 || desc->num_distributions > MPPIB_MAX_DISTRIBUTIONS)
+    return fail(MPPIB_ERR_INVALID_ARG, "num_distributions must be 1 or 2");
+  const int world = desc->world_size <= 0 ? 1 : desc->world_size;
+  if (desc->rank < 0 || desc->rank >= world)
+    return fail(MPPIB_ERR_INVALID_ARG, "rank out of range");
+  if (desc->sampler_id != MPPIB_SAMPLER_GAUSSIAN)
+    return fail(MPPIB_ERR_UNSUPPORTED, "sampler %d is not built into this library yet", desc->sampler_id);
+
+  const PairEntry* entry = nullptr;
+  for (const auto& p : kPairs)
+    if (p.dyn_id == desc->dynamics_id && p.cost_id == desc->cost_id)
+      entry = &p;
+  if (!entry)
+    return fail(MPPIB_ERR_UNSUPPORTED, "no kernel registered for dynamics %d + cost %d", desc->dynamics_id,
+                desc->cost_id);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+  {
+    cudaGetLastError();
+    return fail(MPPIB_ERR_NO_DEVICE, "no CUDA device visible; libmppi_b200 has no CPU path");
+  }
+  if (desc->device < 0 || desc->device >= ndev)
+    return fail(MPPIB_ERR_INVALID_ARG, "device %d out of range (%d devices)", desc->device, ndev);
+  CUDA_TRY(cudaSetDevice(desc->device));
+
+  mppib_engine* e = new mppib_engine();
+  e->desc = *desc;
+  e->desc.world_size = world;
+  e->S = entry->S;
+  e->C = entry->C;
+  e->O = entry->O;
+  e->D = desc->num_distributions;
+  e->N = desc->num_rollouts;
+  e->T = desc->num_timesteps;
+  e->TC = e->T * e->C;
+  e->launch_rollout = entry->launch;
+  e->prepare = entry->prepare;
+  e->dyn_param_bytes = entry->dyn_bytes;
+  e->cost_param_bytes = entry->cost_bytes;
+  e->dyn_shared_floats = entry->dyn_shared_floats;
+  e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
+
+  auto bail = [&](int rc) {
+    mppib_destroy(e);
+    return rc;
+  };
+
+  if (e->D * e->TC > kMaxMeanFloats)
+    return bail(fail(MPPIB_ERR_UNSUPPORTED, "D*T*C = %d exceeds %d", e->D * e->TC, kMaxMeanFloats));
+  e->nchunks = (e->TC + kChunkFloats - 1) / kChunkFloats;
+  if (e->nchunks > kMaxChunks)
+    return bail(fail(MPPIB_ERR_UNSUPPORTED, "T*C = %d exceeds %d", e->TC, kMaxChunks * kChunkFloats));
+
+  // rollout sharding: contiguous slices, remainder to the last rank
+  const int per = e->N / world;
+  e->n_offset = per * desc->rank;
+  e->n_local = (desc->rank == world - 1) ? (e->N - e->n_offset) : per;
+  if (e->n_local <= 0)
+    return bail(fail(MPPIB_ERR_INVALID_ARG, "rank %d of %d has no rollouts (N=%d)", desc->rank, world, e->N));
+
+  // launch geometry: one thread per sample; BX samples per CTA, whole-horizon noise tile resident in shared memory
+  int bx = 64;
+  if (const char* s = getenv("MPPIB_BX"))
+    bx = atoi(s);
+  if (bx < 32 || bx > 256 || (bx % 32) != 0)
+    bx = 64;
+  int max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
+  for (;;)
+  {
+    e->smem_bytes = rollout_smem_layout(bx, e->nchunks, e->D, e->TC, e->dyn_shared_floats).total;
+    if ((int)e->smem_bytes <= max_smem || bx == 32)
+      break;
+    bx /= 2;
+  }
+  if ((int)e->smem_bytes > max_smem)
+    return bail(fail(MPPIB_ERR_SMEM, "noise tile needs %u B of shared memory, device allows %d", e->smem_bytes,
+                     max_smem));
+  e->bx = bx;
+  e->grid = (e->n_local + bx - 1) / bx;
+  e->pstride = ((kPartialHeader + e->TC + 3) / 4) * 4;
+  e->use_tma = !(desc->flags & MPPIB_FLAG_NO_TMA) && (e->TC % 4 == 0) && !getenv("MPPIB_NO_TMA");
+
+  if (desc->stream)
+    e->stream = (cudaStream_t)desc->stream;
+  else
+  {
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+      return bail(fail(MPPIB_ERR_CUDA, "cudaStreamCreate failed"));
+    e->own_stream = true;
+  }
+
+#define CUDA_TRY_B(expr)                                                                                               \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess)                                                                                             \
+    {                                                                                                                  \
+      cudaGetLastError();                                                                                              \
+      return bail(fail(MPPIB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)));                               \
+    }                                                                                                                  \
+  } while (0)
+
+  const size_t noise_floats = (size_t)e->n_local * e->TC;
+  const size_t lead_floats = 8192;  // room for the offset-alignment lead-in (see draw_noise)
+  CUDA_TRY_B(cudaMalloc(&e->noise_alloc, (lead_floats + noise_floats + 8) * sizeof(float)));
+  e->eps_d = e->noise_alloc + lead_floats;  // cudaMalloc is 256-B aligned and 8192*4 keeps that
+  CUDA_TRY_B(cudaMemsetAsync(e->noise_alloc, 0, (lead_floats + noise_floats + 8) * sizeof(float), e->stream));
+  CUDA_TRY_B(cudaMalloc(&e->costs_d, (size_t)e->D * e->n_local * sizeof(float)));
+  CUDA_TRY_B(cudaMalloc(&e->partials_d, (size_t)e->grid * e->D * e->pstride * sizeof(float)));
+  CUDA_TRY_B(cudaMalloc(&e->result_d, (size_t)e->D * e->pstride * sizeof(float)));
+  CUDA_TRY_B(cudaHostAlloc(&e->result_h, (size_t)e->D * e->pstride * sizeof(float), cudaHostAllocMapped));
+  memset(e->result_h, 0, (size_t)e->D * e->pstride * sizeof(float));
+  CUDA_TRY_B(cudaHostGetDevicePointer(&e->result_h_dev, e->result_h, 0));
+  if (e->writeback)
+    CUDA_TRY_B(cudaMalloc(&e->controls_d, (size_t)e->D * noise_floats * sizeof(float)));
+  if (world > 1)
+  {
+    CUDA_TRY_B(cudaMalloc(&e->rank_rec_d, (size_t)e->D * e->pstride * sizeof(float)));
+    CUDA_TRY_B(cudaMalloc(&e->gather_d, (size_t)world * e->D * e->pstride * sizeof(float)));
+  }
+  for (int i = 0; i < 4; i++)
+    CUDA_TRY_B(cudaEventCreate(&e->ev[i]));
+
+  if (e->use_tma)
+  {
+    int rc = make_tensor_map(*e);
+    if (rc != MPPIB_OK)
+      return bail(rc);
+  }
+  {
+    int rc = e->prepare(*e);
+    if (rc != MPPIB_OK)
+      return bail(rc);
+  }
+
+  // Controller::createAndSeedCUDARandomNumberGen (controller.cu:192-207): XORWOW, seed, offset 0
+  if (curandCreateGenerator(&e->gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS)
+    return bail(fail(MPPIB_ERR_CURAND, "curandCreateGenerator failed"));
+  if (curandSetStream(e->gen, e->stream) != CURAND_STATUS_SUCCESS)
+    return bail(fail(MPPIB_ERR_CURAND, "curandSetStream failed"));
+  {
+    int rc = mppib_seed(e, 0ULL, 0ULL);
+    if (rc != MPPIB_OK)
+      return bail(rc);
+  }
+  CUDA_TRY_B(cudaStreamSynchronize(e->stream));
+#undef CUDA_TRY_B
+  *out = e;
+  return MPPIB_OK;
+}
+
+int mppib_destroy(mppib_engine* e)
+{
+  if (!e)
+    return MPPIB_OK;
+  cudaSetDevice(e->desc.device);
+  if (e->stream)
+    cudaStreamSynchronize(e->stream);
+  if (e->comm && g_nccl.CommDestroy)
+    g_nccl.CommDestroy(e->comm);
+  if (e->gen)
+    curandDestroyGenerator(e->gen);
+  if (e->costmap_tex)
+    cudaDestroyTextureObject(e->costmap_tex);
+  if (e->costmap_array)
+    cudaFreeArray(e->costmap_array);
+  cudaFree(e->nn_theta_d);
+  cudaFree(e->noise_alloc);
+  cudaFree(e->costs_d);
+  cudaFree(e->partials_d);
+  cudaFree(e->controls_d);
+  cudaFree(e->rank_rec_d);
+  cudaFree(e->gather_d);
+  cudaFree(e->result_d);
+  cudaFree(e->weights_d);
+  if (e->result_h)
+    cudaFreeHost(e->result_h);
+  for (int i = 0; i < 4; i++)
+    if (e->ev[i])
+      cudaEventDestroy(e->ev[i]);
+  if (e->own_stream && e->stream)
+    cudaStreamDestroy(e->stream);
+  cudaGetLastError();
+  delete e;
+  return MPPIB_OK;
+}
+
+int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
+{
+  if (!e || !host)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  switch (which)
+  {
+    case MPPIB_BLOB_DYN_PARAMS:
+      if (nbytes != e->dyn_param_bytes)
+        return fail(MPPIB_ERR_INVALID_ARG, "dynamics params: got %zu bytes, expected %zu", nbytes,
+                    e->dyn_param_bytes);
+      e->dyn_blob.assign((const unsigned char*)host, (const unsigned char*)host + nbytes);
+      e->have_dyn = true;
+      return MPPIB_OK;
+    case MPPIB_BLOB_COST_PARAMS:
+      if (nbytes != e->cost_param_bytes)
+        return fail(MPPIB_ERR_INVALID_ARG, "cost params: got %zu bytes, expected %zu", nbytes, e->cost_param_bytes);
+      e->cost_blob.assign((const unsigned char*)host, (const unsigned char*)host + nbytes);
+      e->have_cost = true;
+      return MPPIB_OK;
+    case MPPIB_BLOB_SAMPLER_PARAMS:
+    {
+      if (nbytes != sizeof(mppib_gaussian_params))
+        return fail(MPPIB_ERR_INVALID_ARG, "sampler params: got %zu bytes, expected %zu", nbytes,
+                    sizeof(mppib_gaussian_params));
+      mppib_gaussian_params sp;
+      memcpy(&sp, host, sizeof(sp));
+      if (e->D > 1 && !sp.use_same_noise_for_all_distributions)
+        return fail(MPPIB_ERR_UNSUPPORTED,
+                    "use_same_noise_for_all_distributions = false is not supported (Tube-MPPI default is true, "
+                    "sampling_distribution.cuh:20)");
+      for (int i = 0; i < e->D * e->C; i++)
+        if (!(sp.std_dev[i] > 0.0f))
+          return fail(MPPIB_ERR_INVALID_ARG, "std_dev[%d] must be positive", i);
+      e->sampler = sp;
+      e->have_sampler = true;
+      return MPPIB_OK;
+    }
+    case MPPIB_BLOB_NN_WEIGHTS:
+    {
+      if (e->desc.dynamics_id != MPPIB_DYN_AUTORALLY_NN)
+        return fail(MPPIB_ERR_INVALID_ARG, "NN weights given to a non-NN dynamics");
+      if (nbytes != MPPIB_AR_NN_NUM_PARAMS * sizeof(float))
+        return fail(MPPIB_ERR_INVALID_ARG, "NN weights: got %zu bytes, expected %zu", nbytes,
+                    MPPIB_AR_NN_NUM_PARAMS * sizeof(float));
+      const float* w = (const float*)host;
+      for (int i = 0; i < MPPIB_AR_NN_NUM_PARAMS; i++)
+        if (!std::isfinite(w[i]))  // fnn_helper.cu:244-247 asserts finiteness
+          return fail(MPPIB_ERR_INVALID_ARG, "NN weight %d is not finite", i);
+      if (!e->nn_theta_d)
+        CUDA_TRY(cudaMalloc(&e->nn_theta_d, nbytes));
+      CUDA_TRY(cudaMemcpyAsync(e->nn_theta_d, host, nbytes, cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      return MPPIB_OK;
+    }
+    case MPPIB_BLOB_COSTMAP:
+    {
+      if (e->desc.cost_id != MPPIB_COST_AR_STANDARD)
+        return fail(MPPIB_ERR_INVALID_ARG, "costmap given to a cost without a map");
+      if (!e->have_cost)
+        return fail(MPPIB_ERR_STATE, "set MPPIB_BLOB_COST_PARAMS (map_width/map_height) before the costmap");
+      mppib_ar_standard_cost_params cp;
+      memcpy(&cp, e->cost_blob.data(), sizeof(cp));
+      const size_t expect = (size_t)cp.map_width * cp.map_height * 4 * sizeof(float);
+      if (cp.map_width <= 0 || cp.map_height <= 0 || nbytes != expect)
+        return fail(MPPIB_ERR_INVALID_ARG, "costmap: got %zu bytes, expected %zu (%d x %d float4)", nbytes, expect,
+                    cp.map_width, cp.map_height);
+      if (e->costmap_tex)
+      {
+        cudaDestroyTextureObject(e->costmap_tex);
+        e->costmap_tex = 0;
+      }
+      if (e->costmap_array)
+      {
+        cudaFreeArray(e->costmap_array);
+        e->costmap_array = nullptr;
+      }
+      // ar_standard_cost.cu:101-176: float4 array, clamp, point filter, element read, normalised coordinates
+      cudaChannelFormatDesc ch = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+      CUDA_TRY(cudaMallocArray(&e->costmap_array, &ch, cp.map_width, cp.map_height));
+      CUDA_TRY(cudaMemcpy2DToArrayAsync(e->costmap_array, 0, 0, host, (size_t)cp.map_width * 16,
+                                        (size_t)cp.map_width * 16, cp.map_height, cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      cudaResourceDesc res;
+      memset(&res, 0, sizeof(res));
+      res.resType = cudaResourceTypeArray;
+      res.res.array.array = e->costmap_array;
+      cudaTextureDesc tex;
+      memset(&tex, 0, sizeof(tex));
+      tex.addressMode[0] = cudaAddressModeClamp;
+      tex.addressMode[1] = cudaAddressModeClamp;
+      tex.filterMode = cudaFilterModePoint;
+      tex.readMode = cudaReadModeElementType;
+      tex.normalizedCoords = 1;
+      CUDA_TRY(cudaCreateTextureObject(&e->costmap_tex, &res, &tex, nullptr));
+      return MPPIB_OK;
+    }
+    default:
+      return fail(MPPIB_ERR_INVALID_ARG, "unknown blob kind %d", which);
+  }
+}
+
+int mppib_set_solver(mppib_engine* e, float dt, float lambda, float alpha)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (!(dt > 0.0f) || !(lambda > 0.0f))
+    return fail(MPPIB_ERR_INVALID_ARG, "dt and lambda must be positive");
+  e->dt = dt;
+  e->lambda = lambda;
+  e->alpha = alpha;
+  return MPPIB_OK;
+}
+
+int mppib_seed(mppib_engine* e, unsigned long long seed, unsigned long long offset)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  CURAND_TRY(curandSetPseudoRandomGeneratorSeed(e->gen, seed));
+  CURAND_TRY(curandSetGeneratorOffset(e->gen, 0ULL));
+  e->seed = seed;
+  e->rng_offset = offset;
+  // the generator sits at element 0; it is "positioned" only if that is where the next local draw starts
+  e->rng_positioned = (offset == 0 && e->desc.world_size == 1);
+  return MPPIB_OK;
+}
+
+int mppib_get_rng_offset(mppib_engine* e, unsigned long long* offset)
+{
+  if (!e || !offset)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  *offset = e->rng_offset;
+  return MPPIB_OK;
+}
+
+int mppib_burn_draws(mppib_engine* e, int n)
+{
+  if (!e || n < 0)
+    return fail(MPPIB_ERR_INVALID_ARG, "bad argument");
+  // skipping is free for a counter-positioned stream: just move the absolute offset
+  e->rng_offset += (unsigned long long)n * e->N * e->TC;
+  e->rng_positioned = false;
+  return MPPIB_OK;
+}
+
+int mppib_comm_unique_id(void* unique_id_128)
+{
+  if (!unique_id_128)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (!g_nccl.load())
+    return fail(MPPIB_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  NcclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0)
+    return fail(MPPIB_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  memcpy(unique_id_128, &id, sizeof(id));
+  return MPPIB_OK;
+}
+
+int mppib_comm_init(mppib_engine* e, const void* unique_id_128)
+{
+  if (!e || !unique_id_128)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (e->desc.world_size <= 1)
+    return MPPIB_OK;
+  if (!g_nccl.load())
+    return fail(MPPIB_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror());
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  NcclUniqueId id;
+  memcpy(&id, unique_id_128, sizeof(id));
+  int rc = g_nccl.CommInitRank(&e->comm, e->desc.world_size, id, e->desc.rank);
+  if (rc != 0)
+    return fail(MPPIB_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return MPPIB_OK;
+}
+
+int mppib_set_noise(mppib_engine* e, const float* host_eps, size_t count)
+{
+  if (!e || !host_eps)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (count != (size_t)e->n_local * e->TC)
+    return fail(MPPIB_ERR_INVALID_ARG, "noise count %zu != n_local*T*C = %zu", count, (size_t)e->n_local * e->TC);
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  CUDA_TRY(cudaMemcpyAsync(e->eps_d, host_eps, count * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_draw_noise(mppib_engine* e)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  int rc = draw_noise(*e);
+  if (rc != MPPIB_OK)
+    return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_rollout_only(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !U_in)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  rc = e->launch_rollout(*e, x0, U_in, optimization_stride, iteration_num);
+  if (rc != MPPIB_OK)
+    return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->solved_once = true;
+  return MPPIB_OK;
+}
+
+int mppib_reduce_only(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!e->solved_once)
+    return fail(MPPIB_ERR_STATE, "no rollout has been run yet");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  rc = launch_combine(*e);
+  if (rc != MPPIB_OK)
+    return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  read_result(*e, U_out, stats);
+  return MPPIB_OK;
+}
+
+int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num,
+                float* U_out, mppib_solve_stats* stats)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !U_in || !U_out)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  if (e->timing)
+    CUDA_TRY(cudaEventRecord(e->ev[0], e->stream));
+  rc = draw_noise(*e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (e->timing)
+    CUDA_TRY(cudaEventRecord(e->ev[1], e->stream));
+  rc = e->launch_rollout(*e, x0, U_in, optimization_stride, iteration_num);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (e->timing)
+    CUDA_TRY(cudaEventRecord(e->ev[2], e->stream));
+  rc = launch_combine(*e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (e->timing)
+    CUDA_TRY(cudaEventRecord(e->ev[3], e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->timing_valid = e->timing;
+  e->solved_once = true;
+  read_result(*e, U_out, stats);
+  return MPPIB_OK;
+}
+
+int mppib_get_costs(mppib_engine* e, float* host_costs)
+{
+  if (!e || !host_costs)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  CUDA_TRY(cudaMemcpyAsync(host_costs, e->costs_d, (size_t)e->D * e->n_local * sizeof(float), cudaMemcpyDeviceToHost,
+                           e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_get_noise(mppib_engine* e, float* host_eps)
+{
+  if (!e || !host_eps)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  CUDA_TRY(cudaMemcpyAsync(host_eps, e->eps_d, (size_t)e->n_local * e->TC * sizeof(float), cudaMemcpyDeviceToHost,
+                           e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_get_samples(mppib_engine* e, float* host_samples)
+{
+  if (!e || !host_samples)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (!e->writeback)
+    return fail(MPPIB_ERR_STATE, "engine was created without MPPIB_FLAG_WRITEBACK_CONTROLS");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  CUDA_TRY(cudaMemcpyAsync(host_samples, e->controls_d, (size_t)e->D * e->n_local * e->TC * sizeof(float),
+                           cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_get_weights(mppib_engine* e, float* host_weights)
+{
+  if (!e || !host_weights)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (!e->solved_once)
+    return fail(MPPIB_ERR_STATE, "no solve has been run yet");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  const size_t n = (size_t)e->D * e->n_local;
+  if (!e->weights_d)
+    CUDA_TRY(cudaMalloc(&e->weights_d, n * sizeof(float)));
+  const dim3 grid((e->n_local + 255) / 256 > 1024 ? 1024 : (e->n_local + 255) / 256, e->D);
+  weights_kernel<<<grid, 256, 0, e->stream>>>(e->costs_d, e->result_d, e->n_local, e->pstride,
+                                              (float)(1.0 / e->lambda), e->weights_d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(host_weights, e->weights_d, n * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_enable_timing(mppib_engine* e, int enable)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  e->timing = enable != 0;
+  e->timing_valid = false;
+  return MPPIB_OK;
+}
+
+int mppib_get_timing(mppib_engine* e, mppib_timing* out)
+{
+  if (!e || !out)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (!e->timing_valid)
+    return fail(MPPIB_ERR_STATE, "timing not enabled or no solve since it was enabled");
+  CUDA_TRY(cudaEventElapsedTime(&out->noise_ms, e->ev[0], e->ev[1]));
+  CUDA_TRY(cudaEventElapsedTime(&out->rollout_ms, e->ev[1], e->ev[2]));
+  CUDA_TRY(cudaEventElapsedTime(&out->reduce_ms, e->ev[2], e->ev[3]));
+  CUDA_TRY(cudaEventElapsedTime(&out->total_ms, e->ev[0], e->ev[3]));
+  return MPPIB_OK;
+}
+
+int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_bytes, int* uses_tma,
+                          int* kernels_per_solve)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (grid)
+    *grid = e->grid;
+  if (block)
+    *block = e->bx;
+  if (smem_bytes)
+    *smem_bytes = (int)e->smem_bytes;
+  if (uses_tma)
+    *uses_tma = e->use_tma ? 1 : 0;
+  if (kernels_per_solve)
+    *kernels_per_solve = (e->desc.world_size > 1) ? 3 : 2;  // K1 + K2 (+ second K2); cuRAND's own launches not counted
+  return MPPIB_OK;
+}
+
+int mppib_local_rollouts(mppib_engine* e, int* n_local, int* n_offset)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (n_local)
+    *n_local = e->n_local;
+  if (n_offset)
+    *n_offset = e->n_offset;
+  return MPPIB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+/*
+ * plugins/costs.cuh — device twins of the reference's Cost plugins (include/mppi/cost_functions/cost.cuh:34-35 contract:
+ * initializeCosts, computeStateCost, computeControlCost (== 0, cost.cuh:205-208), computeRunningCost, terminalCost).
+ * One thread owns one sample, so `crash_status` is a thread-private int that is sticky across the horizon exactly as
+ * in the reference's single-kernel path (mppi_common.cu:77-78).
+ */
+#pragma once
+#include "../device_utils.cuh"
+#include "../../../include/mppi_b200/params.h"
+
+namespace mppib
+{
+namespace plugins
+{
+template <class CLASS_T, class PARAMS_T>
+struct Cost
+{
+  using Params = PARAMS_T;
+  struct Aux
+  {
+  };
+  __device__ static __forceinline__ void initializeCosts(const Params&, const Aux&, const float* /*y*/, const float* /*u*/)
+  {
+  }
+  __device__ static __forceinline__ float computeControlCost(const Params&, const float* /*u*/, int /*t*/)
+  {
+    return 0.0f;  // cost.cuh:205-208
+  }
+  // cost.cu:40-53
+  template <class AUX>
+  __device__ static __forceinline__ float computeRunningCost(const Params& p, const AUX& aux, const float* y,
+                                                             const float* u, int t, int* crash)
+  {
+    return CLASS_T::computeStateCost(p, aux, y, t, crash) + CLASS_T::computeControlCost(p, u, t);
+  }
+};
+
+// cost_functions/cartpole/cartpole_quadratic_cost.cu:20-43
+struct CartpoleQuadraticCost : public Cost<CartpoleQuadraticCost, mppib_cartpole_cost_params>
+{
+  __device__ static __forceinline__ float computeStateCost(const Params& params_, const Aux&, const float* state, int,
+                                                           int*)
+  {
+    return (state[0] - params_.desired_terminal_state[0]) * (state[0] - params_.desired_terminal_state[0]) *
+               params_.cart_position_coeff +
+           (state[1] - params_.desired_terminal_state[1]) * (state[1] - params_.desired_terminal_state[1]) *
+               params_.cart_velocity_coeff +
+           (state[2] - params_.desired_terminal_state[2]) * (state[2] - params_.desired_terminal_state[2]) *
+               params_.pole_angle_coeff +
+           (state[3] - params_.desired_terminal_state[3]) * (state[3] - params_.desired_terminal_state[3]) *
+               params_.pole_angular_velocity_coeff;
+  }
+  __device__ static __forceinline__ float terminalCost(const Params& params_, const Aux& a, const float* state)
+  {
+    return computeStateCost(params_, a, state, 0, nullptr) * params_.terminal_cost_coeff;
+  }
+};
+
+// cost_functions/double_integrator/double_integrator_circle_cost.cu:8-32
+struct DoubleIntegratorCircleCost : public Cost<DoubleIntegratorCircleCost, mppib_di_circle_cost_params>
+{
+  __device__ static __forceinline__ float computeStateCost(const Params& params_, const Aux&, const float* s,
+                                                           int timestep, int*)
+  {
+    float radial_position = s[0] * s[0] + s[1] * s[1];
+    float current_velocity = sqrtf(s[2] * s[2] + s[3] * s[3]);
+    float current_angular_momentum = s[0] * s[3] - s[1] * s[2];
+    float cost = 0;
+    if ((radial_position < params_.inner_path_radius2) || (radial_position > params_.outer_path_radius2))
+    {
+      cost += powf(params_.discount, timestep) * params_.crash_cost;
+    }
+    cost += params_.velocity_cost * fabsf(current_velocity - params_.velocity_desired);
+    cost += params_.velocity_cost * fabsf(current_angular_momentum - params_.angular_momentum_desired);
+    return cost;
+  }
+  __device__ static __forceinline__ float terminalCost(const Params&, const Aux&, const float*)
+  {
+    return 0.0f;
+  }
+};
+
+// cost_functions/autorally/ar_standard_cost.cu:284-413 (device branches)
+struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_params>
+{
+  static constexpr float MAX_COST_VALUE = 1e16f;
+  struct Aux
+  {
+    cudaTextureObject_t costmap_tex;  // float4 texels, point filter, clamp, normalised coords (ar_standard_cost.cu:160-171)
+  };
+  __device__ static __forceinline__ void initializeCosts(const Params&, const Aux&, const float*, const float*)
+  {
+  }
+  // ar_standard_cost.cu:206-243 (device branch)
+  __device__ static __forceinline__ float4 queryTextureTransformed(const Params& p, const Aux& aux, float x, float y)
+  {
+    float u = p.r_c1[0] * x + p.r_c2[0] * y + p.trs[0];
+    float v = p.r_c1[1] * x + p.r_c2[1] * y + p.trs[1];
+    float w = p.r_c1[2] * x + p.r_c2[2] * y + p.trs[2];
+    return tex2D<float4>(aux.costmap_tex, u / w, v / w);
+  }
+  __device__ static __forceinline__ float getSpeedCost(const Params& p, const float* s)
+  {
+    float cost = 0;
+    float error = s[4] - p.desired_speed;
+    if (p.l1_cost)
+      cost = fabsf(error);
+    else
+      cost = error * error;
+    return (p.speed_coeff * cost);
+  }
+  __device__ static __forceinline__ float getStabilizingCost(const Params& p, const float* s, int* crash_status)
+  {
+    float stabilizing_cost = 0;
+    // reference compares against the double literal 0.001 (ar_standard_cost.cu:304); float(0.001) is the smallest float
+    // above it, so `>=` on floats is the identical predicate
+    if (fabsf(s[4]) >= 0.001f)
+    {
+      float slip = -atanf(s[5] / fabsf(s[4]));
+      stabilizing_cost = p.slip_coeff * powf(slip, 2);
+      if (fabsf(slip) > p.max_slip_ang)
+      {
+        stabilizing_cost += p.crash_coeff;
+      }
+    }
+    // fabs(s[3]) > M_PI_2 in double (ar_standard_cost.cu:315); float(pi/2) is the smallest float above pi/2
+    if (fabsf(s[3]) >= 1.57079632679489661923f)
+    {
+      crash_status[0] = 1;
+    }
+    return stabilizing_cost;
+  }
+  __device__ static __forceinline__ float getCrashCost(const Params& p, const int* crash)
+  {
+    return crash[0] > 0 ? p.crash_coeff : 0.0f;
+  }
+  __device__ static __forceinline__ float getTrackCost(const Params& p, const Aux& aux, const float* s, int* crash)
+  {
+    float track_cost = 0;
+    float sn, cs;
+    __sincosf(s[2], &sn, &cs);  // __cosf / __sinf in the reference (ar_standard_cost.cu:342-346)
+    float x_front = s[0] + p.front_d * cs;
+    float y_front = s[1] + p.front_d * sn;
+    float x_back = s[0] + p.back_d * cs;
+    float y_back = s[1] + p.back_d * sn;
+    float track_cost_front = queryTextureTransformed(p, aux, x_front, y_front).x;
+    float track_cost_back = queryTextureTransformed(p, aux, x_back, y_back).x;
+    track_cost = (fabsf(track_cost_front) + fabsf(track_cost_back)) / 2.0f;
+    if (fabsf(track_cost) < p.track_slop)
+      track_cost = 0;
+    else
+      track_cost = p.track_coeff * track_cost;
+    if (track_cost_front >= p.boundary_threshold || track_cost_back >= p.boundary_threshold)
+      crash[0] = 1;
+    return track_cost;
+  }
+  __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux& aux, const float* s,
+                                                           int timestep, int* crash_status)
+  {
+    float track_cost = getTrackCost(p, aux, s, crash_status);
+    float speed_cost = getSpeedCost(p, s);
+    float stabilizing_cost = getStabilizingCost(p, s, crash_status);
+    float crash_cost = powf(p.discount, timestep) * getCrashCost(p, crash_status);
+    float cost = speed_cost + crash_cost + track_cost + stabilizing_cost;
+    if (cost > MAX_COST_VALUE || isnan(cost))
+      cost = MAX_COST_VALUE;
+    return cost;
+  }
+  __device__ static __forceinline__ float terminalCost(const Params&, const Aux&, const float*)
+  {
+    return 0.0f;
+  }
+};
+
+}  // namespace plugins
+}  // namespace mppib

@@ -1,0 +1,363 @@
+/*
+ * rollout_kernel.cuh — K1, the fused per-sample rollout of the MPPI hot path, written for sm_100a.
+ *
+ * Replaces, in ONE kernel and one pass over the noise buffer:
+ *   setGaussianControls           sampling_distributions/gaussian/gaussian.cu:17-277   (mean / sigma / special cases)
+ *   rolloutKernel                 core/mppi_common.cu:28-146                           (read sample, constrain, step,
+ *                                                                                       running cost + LR cost)
+ *   rolloutDynamicsKernel + rolloutCostKernel   core/mppi_common.cu:148-362            (split variant; no y_d round trip)
+ *   costArrayReduction / computeAndSaveCost     core/mppi_common.cu:843-853,1191-1254
+ * and the per-block half of
+ *   computeBaselineCost / normExpKernel / computeNormalizer / weightedReductionKernel
+ *                                 core/mppi_common.cu:686-737,858-900,1055-1063,1115-1160
+ * (each block emits its own min-cost baseline, exp-weights sum and exp-weighted control sum; K2 — combine_kernel.cuh —
+ *  merges the block partials with the usual log-sum-exp rescale, exactly like the cross-GPU merge).
+ *
+ * B200 design:
+ *   - one thread owns one sample (and all D systems of it: Tube-MPPI's actual + nominal share the noise draw,
+ *     gaussian.cu:378-389, which gives every thread D independent dependency chains); state, output, control and the
+ *     running cost live in registers. No blockDim.y lane cooperation => no barriers inside the T-step loop (the
+ *     reference pays 4 barrier waits + 2 __syncthreads per step, mppi_common.cu:98-137).
+ *   - the block's noise rows [BX samples][T*C floats] — one contiguous HBM range — are staged to shared memory by
+ *     TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, one mbarrier per 32-column slab so the first time steps can
+ *     start while later slabs are still in flight). Threads read their row with conflict-free LDS.128.
+ *   - the raw N(0,1) buffer is read exactly once from HBM and never rewritten: mean/sigma/special cases and the
+ *     control constraints are applied on the fly, and the exp-weighted control sum is taken from the SAME shared
+ *     tile in the epilogue. Algorithmic HBM traffic = N*T*C*4 bytes.
+ */
+#pragma once
+#include "device_utils.cuh"
+#include "../../include/mppi_b200/params.h"
+
+namespace mppib
+{
+constexpr int kMaxStateDim = 32;
+constexpr int kMaxMeanFloats = 2048;  // D*T*C carried in the kernel parameter bank
+constexpr int kMaxChunks = 32;        // T*C <= 1024
+
+// sampler quantities the kernel needs (gaussian.cuh:21-61), prepared on the host once per solve
+struct SamplerArgs
+{
+  float std_dev[MPPIB_MAX_DISTRIBUTIONS][MPPIB_MAX_CONTROL_DIM];  // un-decayed (LR cost, gaussian.cu:489)
+  float std_dev_decayed[MPPIB_MAX_DISTRIBUTIONS][MPPIB_MAX_CONTROL_DIM];  // * std_dev_decay^iter (gaussian.cu:423)
+  float control_cost_coeff[MPPIB_MAX_CONTROL_DIM];
+  float pure_noise_threshold;  // (1.0f - pure_noise_trajectories_percentage) * num_rollouts   (gaussian.cu:108)
+};
+
+template <class DYN, class COST>
+struct RolloutArgs
+{
+  typename DYN::Params dyn;
+  typename COST::Params cost;
+  typename DYN::Aux dyn_aux;
+  typename COST::Aux cost_aux;
+  SamplerArgs samp;
+  const float* eps;     // raw N(0,1) [n_local][T][C]
+  float* costs;         // [D][n_local]
+  float* partials;      // [gridDim.x][D][pstride]
+  float* controls_out;  // optional [D][n_local][T][C] (MPPIB_FLAG_WRITEBACK_CONTROLS), else nullptr
+  int n_local;          // rollouts on this rank
+  int n_offset;         // global index of local rollout 0 (rank * N / world)
+  int T;
+  int nchunks;  // ceil(T*C / 32)
+  int pstride;  // floats per (block, distribution) partial record
+  int opt_stride;
+  int use_tma;
+  float dt, lambda, alpha, lambda_inv;
+  float x0[MPPIB_MAX_DISTRIBUTIONS * kMaxStateDim];  // [D][S]
+  float means[kMaxMeanFloats];                       // [D][T][C] importance-sampler mean == nominal control
+};
+
+// gaussian.cu:101-121: the three cases of setGaussianControls for one element
+__device__ __forceinline__ float sample_control(float mean, float sd, float eps, bool use_mean, bool pure_noise)
+{
+  if (use_mean)
+    return mean;
+  if (pure_noise)
+    return sd * eps;
+  return fmaf(sd, eps, mean);  // nvcc contracts the reference's `mean + std_dev * eps` to the same FFMA
+}
+
+// gaussian.cu:481-569 (device formula)
+template <int C>
+__device__ __forceinline__ float likelihood_ratio_cost(const SamplerArgs& sp, int d, const float* mean_t, const float* u,
+                                                       bool pure_noise, float lambda, float alpha)
+{
+  float cost = 0.0f;
+#pragma unroll
+  for (int i = 0; i < C; i++)
+  {
+    const float mean_i = pure_noise ? 0.0f : mean_t[i];
+    const float sd = sp.std_dev[d][i];
+    cost += sp.control_cost_coeff[i] * mean_i * (mean_i - 2.0f * u[i]) / (sd * sd);
+  }
+  return 0.5f * lambda * (1.0f - alpha) * cost;
+}
+
+// shared-memory carve-up (bytes); the tile base is rounded up to 1024 B inside the kernel (SWIZZLE_128B atom)
+struct RolloutSmem
+{
+  uint32_t tile, means, theta, weights, scratch, bars, total;
+};
+__host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, int D, int TC, int dyn_shared_floats)
+{
+  RolloutSmem s;
+  uint32_t off = 0;
+  s.tile = off;
+  off += (uint32_t)nchunks * bx * kChunkBytes;
+  s.means = off;
+  off += ((uint32_t)(D * TC + 3) / 4) * 16;
+  s.theta = off;
+  off += ((uint32_t)(dyn_shared_floats + 3) / 4) * 16;
+  s.weights = off;
+  off += ((uint32_t)(D * bx + 3) / 4) * 16;
+  s.scratch = off;
+  off += 3 * 32 * 4;  // per-warp partials for (min | sum w | sum w^2)
+  s.bars = off;
+  off += (uint32_t)kMaxChunks * 8;
+  s.total = off + 1024;  // slack for the 1024-B round-up of the base
+  return s;
+}
+
+template <class DYN, class COST, int D>
+__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
+                                                      const __grid_constant__ CUtensorMap tmap)
+{
+  constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
+  static_assert(C == 1 || C == 2 || C == 4, "CONTROL_DIM must divide a 16-byte group");
+  constexpr int STEPS_PER_GROUP = 4 / C;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int bx = blockDim.x;
+  const int tid = threadIdx.x;
+  const int T = args.T;
+  const int TC = T * C;
+  const int nchunks = args.nchunks;
+  const RolloutSmem L = rollout_smem_layout(bx, nchunks, D, TC, DYN::SHARED_FLOATS);
+  unsigned char* tile = smem + L.tile;
+  float* means_s = reinterpret_cast<float*>(smem + L.means);
+  float* theta_s = reinterpret_cast<float*>(smem + L.theta);
+  float* w_s = reinterpret_cast<float*>(smem + L.weights);
+  float* red_s = reinterpret_cast<float*>(smem + L.scratch);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+
+  const int row0 = blockIdx.x * bx;  // first local rollout of this block
+  const int n_loc = row0 + tid;
+  const bool valid = n_loc < args.n_local;
+  const int n_glob = args.n_offset + n_loc;
+
+  // ---- stage the block's noise rows -------------------------------------------------------------------------------
+  if (args.use_tma)
+  {
+    if (tid == 0)
+    {
+      tma_prefetch_desc(&tmap);
+      for (int k = 0; k < nchunks; k++)
+        mbar_init(&bars[k], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+      for (int k = 0; k < nchunks; k++)
+      {
+        mbar_arrive_expect_tx(&bars[k], (uint32_t)bx * kChunkBytes);
+        tma_load_2d(tile + (size_t)k * bx * kChunkBytes, &tmap, k * kChunkFloats, row0, &bars[k]);
+      }
+    }
+  }
+  else
+  {
+    // plain-load fallback (T*C not a multiple of 4, or MPPIB_FLAG_NO_TMA): coalesced LDG of the contiguous block
+    // range, scattered into the same swizzled layout; out-of-range elements are zero like TMA's OOB fill.
+    const float* src = args.eps + (size_t)row0 * TC;
+    const int rows_here = min(bx, args.n_local - row0);
+    const int total = bx * nchunks * kChunkFloats;
+    for (int i = tid; i < total; i += bx)
+    {
+      const int r = i / (nchunks * kChunkFloats);
+      const int col = i - r * (nchunks * kChunkFloats);
+      float v = 0.0f;
+      if (r < rows_here && col < TC)
+        v = __ldg(src + (size_t)r * TC + col);
+      const int chunk = col >> 5, within = col & 31;
+      *reinterpret_cast<float*>(tile + tile_offset_bytes(bx, chunk, r, within >> 2) + ((within & 3) << 2)) = v;
+    }
+  }
+
+  // ---- block-shared read-only data --------------------------------------------------------------------------------
+  for (int i = tid; i < D * TC; i += bx)
+    means_s[i] = args.means[i];
+
+  // ---- per-sample state in registers ------------------------------------------------------------------------------
+  float x[D][S], y[D][O], running_cost[D];
+  int crash_status[D];
+#pragma unroll
+  for (int d = 0; d < D; d++)
+  {
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      x[d][i] = args.x0[d * S + i];
+#pragma unroll
+    for (int i = 0; i < O; i++)
+      y[d][i] = 0.0f;
+    running_cost[d] = 0.0f;
+    crash_status[d] = 0;
+  }
+  // initializeDynamics fills theta_s cooperatively (FNNHelper::initialize) and seeds y; initializeCosts is a no-op
+  // for every in-tree cost (mppi_common.cu:94-96)
+#pragma unroll
+  for (int d = 0; d < D; d++)
+  {
+    DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, x[d], y[d]);
+  }
+  __syncthreads();
+
+  const bool pure_noise = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
+  const bool zero_noise_sample = (n_glob == 0);                             // gaussian.cu:101
+
+  // ---- the horizon ----------------------------------------------------------------------------------------------
+  for (int k = 0; k < nchunks; k++)
+  {
+    if (args.use_tma)
+      mbar_wait(&bars[k], 0);
+#pragma unroll 1
+    for (int g = 0; g < 8; g++)
+    {
+      const int col0 = k * kChunkFloats + g * 4;
+      if (col0 >= TC)
+        break;
+      const float4 e4 = lds128(tile, tile_offset_bytes(bx, k, tid, g));
+      const float e[4] = { e4.x, e4.y, e4.z, e4.w };
+#pragma unroll
+      for (int s = 0; s < STEPS_PER_GROUP; s++)
+      {
+        const int t = col0 / C + s;
+        if (t >= T)
+          break;
+        const bool use_mean = zero_noise_sample || (t < args.opt_stride);
+#pragma unroll
+        for (int d = 0; d < D; d++)
+        {
+          float u[C], x_next[S], xdot[S];
+          const float* mean_t = means_s + (d * T + t) * C;
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], e[s * C + c], use_mean, pure_noise);
+          DYN::enforceConstraints(args.dyn, x[d], u);  // mppi_common.cu:108-111
+          if (args.controls_out != nullptr && valid)
+          {  // mppi_common.cu:117 writeControlSample (compat / debug path only)
+            float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc) * T + t) * C;
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              dst[c] = u[c];
+          }
+#pragma unroll
+          for (int i = 0; i < S; i++)
+            xdot[i] = 0.0f;
+          DYN::step(args.dyn, theta_s, x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
+          running_cost[d] +=
+              COST::computeRunningCost(args.cost, args.cost_aux, y[d], u, t, &crash_status[d]) +
+              likelihood_ratio_cost<C>(args.samp, d, mean_t, u, pure_noise, args.lambda, args.alpha);  // :126-128
+#pragma unroll
+          for (int i = 0; i < S; i++)
+            x[d][i] = x_next[i];
+        }
+      }
+    }
+  }
+
+  // ---- per-sample cost (computeAndSaveCost, mppi_common.cu:843-853) ------------------------------------------------
+  float cost[D];
+#pragma unroll
+  for (int d = 0; d < D; d++)
+  {
+    cost[d] = running_cost[d] / (float)T + COST::terminalCost(args.cost, args.cost_aux, y[d]) / (float)T;
+    if (valid)
+      args.costs[(size_t)d * args.n_local + n_loc] = cost[d];
+  }
+
+  // ---- block partial of the softmin-weighted control average ------------------------------------------------------
+  const int lane = tid & 31, warp = tid >> 5, nwarps = (bx + 31) >> 5;
+#pragma unroll
+  for (int d = 0; d < D; d++)
+  {
+    // block baseline
+    float m = warp_min(valid ? cost[d] : INFINITY);
+    if (lane == 0)
+      red_s[warp] = m;
+    __syncthreads();
+    float beta_b = red_s[0];
+    for (int i = 1; i < nwarps; i++)
+      beta_b = fminf(beta_b, red_s[i]);
+    // normExpTransform (mppi_common.cu:958-966) against the block baseline
+    const float w = valid ? expf(-args.lambda_inv * (cost[d] - beta_b)) : 0.0f;
+    w_s[d * bx + tid] = w;
+    const float sw = warp_sum(w), sw2 = warp_sum(w * w);
+    if (lane == 0)
+    {
+      red_s[32 + warp] = sw;
+      red_s[64 + warp] = sw2;
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+      float eta_b = 0.0f, w2_b = 0.0f;
+      for (int i = 0; i < nwarps; i++)
+      {
+        eta_b += red_s[32 + i];
+        w2_b += red_s[64 + i];
+      }
+      float* hdr = args.partials + ((size_t)blockIdx.x * D + d) * args.pstride;
+      hdr[0] = beta_b;
+      hdr[1] = eta_b;
+      hdr[2] = w2_b;
+      hdr[3] = 0.0f;
+    }
+    __syncthreads();  // red_s reused by the next distribution
+  }
+
+  // exp-weighted sum of the CONSTRAINED sampled controls (weightedReductionKernel, mppi_common.cu:710-737), taken
+  // from the shared noise tile: thread j owns time step j (all C components so enforceConstraints sees the full u).
+  const int rows_here = min(bx, args.n_local - row0);
+#pragma unroll
+  for (int d = 0; d < D; d++)
+  {
+    float* out = args.partials + ((size_t)blockIdx.x * D + d) * args.pstride + kPartialHeader;
+    for (int t = tid; t < T; t += bx)
+    {
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        acc[c] = 0.0f;
+      const float* mean_t = means_s + (d * T + t) * C;
+      const int col = t * C;
+      const int chunk = col >> 5, within = col & 31;
+      const bool t_uses_mean = t < args.opt_stride;
+#pragma unroll 4
+      for (int r = 0; r < rows_here; r++)
+      {
+        const unsigned char* p = tile + tile_offset_bytes(bx, chunk, r, within >> 2) + ((within & 3) << 2);
+        float u[C];
+        const int ng = args.n_offset + row0 + r;
+        const bool pn = (float)ng >= args.samp.pure_noise_threshold;
+        const bool um = t_uses_mean || (ng == 0);
+#pragma unroll
+        for (int c = 0; c < C; c++)
+          u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], reinterpret_cast<const float*>(p)[c], um, pn);
+        DYN::enforceConstraints(args.dyn, nullptr, u);
+        const float w = w_s[d * bx + r];
+#pragma unroll
+        for (int c = 0; c < C; c++)
+          acc[c] = fmaf(w, u[c], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        out[col + c] = acc[c];
+    }
+  }
+}
+
+}  // namespace mppib

@@ -1,0 +1,752 @@
+"""ctypes mirror of the reference's host-side plugin / controller interface over libmppi_b200.so.
+
+The reference is header-only C++ (Eigen); its C++ twin here is ``include/mppi_b200/*.hpp``. This module is the same
+surface for Python callers (tests, bench.py): identical class names, constructor arguments, method names and argument
+meaning as the reference classes cited in each docstring. It contains NO numerics of its own: every number comes from
+the C-ABI (``include/mppi_b200.h``) — the CUDA engine for the rollout-and-reduce path, and the exported host twins
+(``include/mppi_b200/host_twins.h``) for the controller's CPU tail. If the library is missing, import fails loudly;
+there is no Python / CPU fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmppi_b200.so")
+
+MAX_C = 4  # MPPIB_MAX_CONTROL_DIM
+MAX_D = 2  # MPPIB_MAX_DISTRIBUTIONS
+FLT_MAX = 3.4028234663852886e38
+
+# plugin ids (include/mppi_b200/params.h)
+DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM = 0, 1, 2, 3
+COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC = 0, 1, 2, 3
+SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
+BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
+FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API = 1, 2, 4
+AR_NN_NUM_PARAMS = 1412
+
+
+class MppibError(RuntimeError):
+    """Raised for any negative mppib_status (the reference would print and exit(): utils/gpu_err_chk.cuh:32-40)."""
+
+    def __init__(self, status: int, what: str):
+        super().__init__(f"libmppi_b200: status {status}: {what}")
+        self.status = status
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# POD blobs (field-for-field with include/mppi_b200/params.h)
+class ControlLimits(C.Structure):
+    _fields_ = [("rng_lo", C.c_float * MAX_C), ("rng_hi", C.c_float * MAX_C), ("deadband", C.c_float * MAX_C),
+                ("zero_control", C.c_float * MAX_C)]
+
+    def __init__(self):
+        super().__init__()
+        for i in range(MAX_C):  # dynamics.cuh:99-106 defaults
+            self.rng_lo[i] = -FLT_MAX
+            self.rng_hi[i] = FLT_MAX
+
+
+class CartpoleDynParams(C.Structure):
+    _fields_ = [("lim", ControlLimits), ("cart_mass", C.c_float), ("pole_mass", C.c_float),
+                ("pole_length", C.c_float), ("gravity", C.c_float)]
+
+
+class DIDynParams(C.Structure):
+    _fields_ = [("lim", ControlLimits), ("system_noise", C.c_float)]
+
+
+class ARNNDynParams(C.Structure):
+    _fields_ = [("lim", ControlLimits)]
+
+
+class CartpoleCostParams(C.Structure):
+    _fields_ = [("control_cost_coeff", C.c_float * MAX_C), ("discount", C.c_float),
+                ("cart_position_coeff", C.c_float), ("cart_velocity_coeff", C.c_float),
+                ("pole_angle_coeff", C.c_float), ("pole_angular_velocity_coeff", C.c_float),
+                ("terminal_cost_coeff", C.c_float), ("desired_terminal_state", C.c_float * 4)]
+
+
+class DICircleCostParams(C.Structure):
+    _fields_ = [("control_cost_coeff", C.c_float * MAX_C), ("discount", C.c_float), ("velocity_cost", C.c_float),
+                ("crash_cost", C.c_float), ("velocity_desired", C.c_float), ("inner_path_radius2", C.c_float),
+                ("outer_path_radius2", C.c_float), ("angular_momentum_desired", C.c_float)]
+
+
+class ARStandardCostParams(C.Structure):
+    _fields_ = [("control_cost_coeff", C.c_float * MAX_C), ("discount", C.c_float), ("desired_speed", C.c_float),
+                ("speed_coeff", C.c_float), ("track_coeff", C.c_float), ("max_slip_ang", C.c_float),
+                ("slip_coeff", C.c_float), ("track_slop", C.c_float), ("crash_coeff", C.c_float),
+                ("boundary_threshold", C.c_float), ("grid_res", C.c_int), ("r_c1", C.c_float * 3),
+                ("r_c2", C.c_float * 3), ("trs", C.c_float * 3), ("l1_cost", C.c_int), ("front_d", C.c_float),
+                ("back_d", C.c_float), ("map_width", C.c_int), ("map_height", C.c_int)]
+
+
+class GaussianParams(C.Structure):
+    _fields_ = [("std_dev", C.c_float * (MAX_C * MAX_D)), ("control_cost_coeff", C.c_float * MAX_C),
+                ("pure_noise_trajectories_percentage", C.c_float), ("std_dev_decay", C.c_float),
+                ("sum_strides", C.c_int), ("use_same_noise_for_all_distributions", C.c_int),
+                ("exponents", C.c_float * (MAX_C * MAX_D)), ("offset_decay_rate", C.c_float), ("fmin", C.c_float)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("dynamics_id", C.c_int), ("cost_id", C.c_int), ("sampler_id", C.c_int), ("num_rollouts", C.c_int),
+                ("num_timesteps", C.c_int), ("num_distributions", C.c_int), ("device", C.c_int),
+                ("flags", C.c_uint), ("stream", C.c_void_p), ("rank", C.c_int), ("world_size", C.c_int)]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("baseline", C.c_float), ("normalizer", C.c_float), ("sum_w2", C.c_float), ("pad", C.c_float)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("noise_ms", C.c_float), ("rollout_ms", C.c_float), ("reduce_ms", C.c_float),
+                ("total_ms", C.c_float)]
+
+
+# every symbol include/mppi_b200.h and include/mppi_b200/host_twins.h declare (tests check the .so exports them all)
+ABI_SYMBOLS = [
+    "mppib_create", "mppib_destroy", "mppib_set_blob", "mppib_set_solver", "mppib_seed", "mppib_burn_draws",
+    "mppib_get_rng_offset", "mppib_comm_unique_id", "mppib_comm_init", "mppib_solve", "mppib_set_noise",
+    "mppib_draw_noise", "mppib_rollout_only", "mppib_reduce_only", "mppib_get_costs", "mppib_get_noise",
+    "mppib_get_samples", "mppib_get_weights", "mppib_enable_timing", "mppib_get_timing", "mppib_get_launch_info",
+    "mppib_local_rollouts", "mppib_strerror", "mppib_last_error", "mppib_version",
+    "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
+    "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libmppi_b200.so (built by ``__graft_entry__.build()`` / ``mppi-generic_b200/build.sh``). No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "— the MPPI engine has no Python/CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    fp, vp, ip = C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int)
+    L.mppib_create.argtypes = [C.POINTER(vp), C.POINTER(Desc)]
+    L.mppib_destroy.argtypes = [vp]
+    L.mppib_set_blob.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.mppib_set_solver.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    L.mppib_seed.argtypes = [vp, C.c_ulonglong, C.c_ulonglong]
+    L.mppib_burn_draws.argtypes = [vp, C.c_int]
+    L.mppib_get_rng_offset.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.mppib_comm_unique_id.argtypes = [vp]
+    L.mppib_comm_init.argtypes = [vp, vp]
+    L.mppib_solve.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(SolveStats)]
+    L.mppib_set_noise.argtypes = [vp, vp, C.c_size_t]
+    L.mppib_draw_noise.argtypes = [vp]
+    L.mppib_rollout_only.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    L.mppib_reduce_only.argtypes = [vp, vp, C.POINTER(SolveStats)]
+    for f in ("mppib_get_costs", "mppib_get_noise", "mppib_get_samples", "mppib_get_weights"):
+        getattr(L, f).argtypes = [vp, vp]
+    L.mppib_enable_timing.argtypes = [vp, C.c_int]
+    L.mppib_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.mppib_get_launch_info.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.mppib_local_rollouts.argtypes = [vp, ip, ip]
+    L.mppib_strerror.argtypes = [C.c_int]
+    L.mppib_strerror.restype = C.c_char_p
+    L.mppib_last_error.restype = C.c_char_p
+    L.mppib_host_dims.argtypes = [C.c_int, ip, ip, ip]
+    L.mppib_host_enforce_constraints.argtypes = [C.c_int, vp, vp]
+    L.mppib_host_step.argtypes = [C.c_int, vp, vp, vp, vp, C.c_float, vp, vp, vp]
+    L.mppib_host_smooth_controls.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.mppib_host_smooth_controls.restype = None
+    L.mppib_host_slide_controls.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.mppib_host_slide_controls.restype = None
+    L.mppib_host_output_trajectory.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp]
+    L.mppib_host_free_energy.argtypes = [C.POINTER(SolveStats), C.c_int, C.c_float, vp]
+    L.mppib_host_free_energy.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        L = lib()
+        msg = (L.mppib_last_error() or b"").decode() or (L.mppib_strerror(rc) or b"").decode()
+        raise MppibError(rc, msg)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Plugins — host objects that own the POD parameters, like the reference's host classes do
+class _Dynamics:
+    """Base of the dynamics plugins (include/mppi/dynamics/dynamics.cuh:67-68). Subclasses set DYN_ID / dims / params."""
+    DYN_ID = -1
+    STATE_DIM = CONTROL_DIM = OUTPUT_DIM = 0
+
+    def __init__(self):
+        self.params = None
+        self.nn_theta: Optional[np.ndarray] = None
+
+    # dynamics.cuh:163-175
+    def setControlRanges(self, control_rngs: Sequence[Sequence[float]]):
+        for i, (lo, hi) in enumerate(control_rngs):
+            self.params.lim.rng_lo[i] = lo
+            self.params.lim.rng_hi[i] = hi
+
+    def setControlDeadbands(self, deadband: Sequence[float]):
+        for i, v in enumerate(deadband):
+            self.params.lim.deadband[i] = v
+
+    @property
+    def zero_control_(self) -> np.ndarray:
+        return np.array([self.params.lim.zero_control[i] for i in range(self.CONTROL_DIM)], dtype=np.float32)
+
+    def getZeroState(self) -> np.ndarray:
+        return np.zeros(self.STATE_DIM, dtype=np.float32)
+
+    def blob(self) -> bytes:
+        return bytes(self.params)
+
+    # host twins (dynamics.cuh:250-300)
+    def enforceConstraints(self, state: np.ndarray, control: np.ndarray) -> None:
+        u = _f32(control)
+        _check(lib().mppib_host_enforce_constraints(self.DYN_ID, C.byref(self.params), _ptr(u)))
+        control[...] = u
+
+    def step(self, state, control, dt: float):
+        """Returns (next_state, state_der, output) — Dynamics::step host twin (dynamics.cuh:283-290)."""
+        x, u = _f32(state), _f32(control)
+        xn = np.zeros(self.STATE_DIM, np.float32)
+        xd = np.zeros(self.STATE_DIM, np.float32)
+        y = np.zeros(self.OUTPUT_DIM, np.float32)
+        _check(lib().mppib_host_step(self.DYN_ID, C.byref(self.params), _ptr(self.nn_theta), _ptr(x), _ptr(u),
+                                     C.c_float(dt), _ptr(xn), _ptr(xd), _ptr(y)))
+        return xn, xd, y
+
+
+class CartpoleDynamics(_Dynamics):
+    """dynamics/cartpole/cartpole_dynamics.cuh:44-52 — CartpoleDynamics(cart_mass, pole_mass, pole_length)."""
+    DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_CARTPOLE, 4, 1, 4
+
+    def __init__(self, cart_mass: float = 1.0, pole_mass: float = 1.0, pole_length: float = 1.0):
+        super().__init__()
+        self.params = CartpoleDynParams()
+        self.params.cart_mass, self.params.pole_mass, self.params.pole_length = cart_mass, pole_mass, pole_length
+        self.params.gravity = 9.81  # cartpole_dynamics.cuh:101
+
+
+class DoubleIntegratorDynamics(_Dynamics):
+    """dynamics/double_integrator/di_dynamics.cuh — DoubleIntegratorDynamics(system_noise)."""
+    DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_DOUBLE_INTEGRATOR, 4, 2, 4
+
+    def __init__(self, system_noise: float = 1.0):
+        super().__init__()
+        self.params = DIDynParams()
+        self.params.system_noise = system_noise
+
+
+class NeuralNetModel(_Dynamics):
+    """dynamics/autorally/ar_nn_model.cuh — NeuralNetModel<7,2,3>(control_rngs); 6-32-32-4 tanh network."""
+    DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_AUTORALLY_NN, 7, 2, 8
+    LAYERS = (6, 32, 32, 4)
+
+    def __init__(self, control_rngs: Optional[Sequence[Sequence[float]]] = None):
+        super().__init__()
+        self.params = ARNNDynParams()
+        if control_rngs is not None:
+            self.setControlRanges(control_rngs)
+        self.nn_theta = np.zeros(AR_NN_NUM_PARAMS, np.float32)
+
+    def updateModel(self, description: Sequence[int], data) -> None:
+        """ar_nn_model.cu:40-45 -> FNNHelper::updateModel (fnn_helper.cu:218-257): packed W (row-major out x in), b per layer."""
+        if tuple(description) != self.LAYERS:
+            raise ValueError("Invalid model trying to to be set for NN")  # fnn_helper.cu:224-227
+        data = _f32(data).ravel()
+        if data.size != AR_NN_NUM_PARAMS or not np.all(np.isfinite(data)):
+            raise ValueError("NN parameter vector must hold 1412 finite floats")
+        self.nn_theta = data.copy()
+
+
+class _Cost:
+    COST_ID = -1
+
+    def __init__(self):
+        self.params = None
+        self.costmap: Optional[np.ndarray] = None
+
+    def blob(self) -> bytes:
+        return bytes(self.params)
+
+
+class CartpoleQuadraticCost(_Cost):
+    """cost_functions/cartpole/cartpole_quadratic_cost.cuh:10-23 (defaults reproduced)."""
+    COST_ID = COST_CARTPOLE_QUADRATIC
+
+    def __init__(self):
+        super().__init__()
+        p = CartpoleCostParams()
+        for i in range(MAX_C):
+            p.control_cost_coeff[i] = 1.0
+        p.control_cost_coeff[0] = 10.0
+        p.discount = 1.0
+        p.cart_position_coeff, p.cart_velocity_coeff = 1000.0, 100.0
+        p.pole_angle_coeff, p.pole_angular_velocity_coeff = 2000.0, 100.0
+        p.terminal_cost_coeff = 0.0
+        p.desired_terminal_state[:] = [0.0, 0.0, math.pi, 0.0]
+        self.params = p
+
+
+class DoubleIntegratorCircleCost(_Cost):
+    """cost_functions/double_integrator/double_integrator_circle_cost.cuh:8-23 (defaults reproduced)."""
+    COST_ID = COST_DI_CIRCLE
+
+    def __init__(self):
+        super().__init__()
+        p = DICircleCostParams()
+        for i in range(MAX_C):
+            p.control_cost_coeff[i] = 1.0
+        p.control_cost_coeff[0] = p.control_cost_coeff[1] = 0.01
+        p.discount = 1.0
+        p.velocity_cost, p.crash_cost, p.velocity_desired = 1.0, 1000.0, 2.0
+        p.inner_path_radius2, p.outer_path_radius2 = 1.875 * 1.875, 2.125 * 2.125
+        p.angular_momentum_desired = 2.0 * 2.0
+        self.params = p
+
+
+class ARStandardCost(_Cost):
+    """cost_functions/autorally/ar_standard_cost.cuh:14-41 (defaults reproduced); map set with the methods below."""
+    COST_ID = COST_AR_STANDARD
+
+    def __init__(self):
+        super().__init__()
+        p = ARStandardCostParams()
+        for i in range(MAX_C):
+            p.control_cost_coeff[i] = 1.0
+        p.control_cost_coeff[0] = p.control_cost_coeff[1] = 0.0
+        p.discount = 1.0
+        p.desired_speed, p.speed_coeff, p.track_coeff = 6.0, 4.25, 200.0
+        p.max_slip_ang, p.slip_coeff, p.track_slop = 1.25, 10.0, 0.0
+        p.crash_coeff, p.boundary_threshold, p.grid_res = 10000.0, 0.65, 10
+        p.l1_cost, p.front_d, p.back_d = 0, 0.5, -0.5
+        self.params = p
+
+    def setCostmap(self, texels_float4: np.ndarray, width: int, height: int) -> None:
+        """track_costs_ as float4 per texel, row-major [height][width][4] (ar_standard_cost.cu:101-143)."""
+        t = _f32(texels_float4).reshape(height, width, 4)
+        self.costmap = t
+        self.params.map_width, self.params.map_height = width, height
+
+    def updateTransform(self, m: np.ndarray, trs: Sequence[float]) -> None:
+        """ar_standard_cost.cu:188-204: columns 0/1 of the 3x3 rotation and the translation."""
+        for i in range(3):
+            self.params.r_c1[i] = float(m[i][0])
+            self.params.r_c2[i] = float(m[i][1])
+            self.params.trs[i] = float(trs[i])
+
+    def loadTrackData(self, channel0: np.ndarray, x_min: float, x_max: float, y_min: float, y_max: float,
+                      ppm: float) -> None:
+        """In-memory equivalent of ARStandardCostImpl::loadTrackData (ar_standard_cost.cu:416-474) for a map given as
+        its channel-0 array [height][width]; channels 1-3 are zero; the world->texture transform is the reference's:
+        R = diag(1/(x_max-x_min), 1/(y_max-y_min), 1), trs = (-x_min/(x_max-x_min), -y_min/(y_max-y_min), 1)."""
+        h, w = channel0.shape
+        tex = np.zeros((h, w, 4), np.float32)
+        tex[..., 0] = channel0
+        self.setCostmap(tex, w, h)
+        R = np.zeros((3, 3), np.float32)
+        R[0, 0] = 1.0 / (x_max - x_min)
+        R[1, 1] = 1.0 / (y_max - y_min)
+        R[2, 2] = 1.0
+        trs = [-x_min / (x_max - x_min), -y_min / (y_max - y_min), 1.0]
+        self.updateTransform(R, trs)
+
+
+class GaussianDistribution:
+    """sampling_distributions/gaussian/gaussian.cuh:63-… — owns the sampling parameters (GaussianParamsImpl :21-61)."""
+    SAMPLER_ID = SAMPLER_GAUSSIAN
+
+    def __init__(self, control_dim: int, std_dev: Optional[Sequence[float]] = None):
+        self.control_dim = control_dim
+        p = GaussianParams()
+        for i in range(MAX_C * MAX_D):
+            p.std_dev[i] = 1.0
+        p.pure_noise_trajectories_percentage = 0.01
+        p.std_dev_decay = 1.0
+        p.sum_strides = 32
+        p.use_same_noise_for_all_distributions = 1
+        p.offset_decay_rate = 0.97
+        self.params = p
+        if std_dev is not None:
+            self.setStdDev(std_dev)
+
+    def setStdDev(self, std_dev: Sequence[float], distribution: Optional[int] = None) -> None:
+        ds = range(MAX_D) if distribution is None else [distribution]
+        for d in ds:
+            for c, v in enumerate(std_dev):
+                self.params.std_dev[d * self.control_dim + c] = v
+
+    def setControlCostCoeff(self, coeff: Sequence[float]) -> None:
+        for c, v in enumerate(coeff):
+            self.params.control_cost_coeff[c] = v
+
+    def blob(self) -> bytes:
+        return bytes(self.params)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Engine:
+    """Thin RAII wrapper of the opaque mppib_engine (one per controller)."""
+
+    def __init__(self, dyn: _Dynamics, cost: _Cost, sampler: GaussianDistribution, num_rollouts: int,
+                 num_timesteps: int, num_distributions: int = 1, device: int = 0, flags: int = 0,
+                 stream: Optional[int] = None, rank: int = 0, world_size: int = 1):
+        self._h = C.c_void_p()
+        self.dyn, self.cost, self.sampler = dyn, cost, sampler
+        self.N, self.T, self.D = num_rollouts, num_timesteps, num_distributions
+        self.S, self.Cdim, self.O = dyn.STATE_DIM, dyn.CONTROL_DIM, dyn.OUTPUT_DIM
+        d = Desc(dyn.DYN_ID, cost.COST_ID, sampler.SAMPLER_ID, num_rollouts, num_timesteps, num_distributions, device,
+                 flags, stream, rank, world_size)
+        _check(lib().mppib_create(C.byref(self._h), C.byref(d)))
+        self.push_params()
+        nl, no = C.c_int(), C.c_int()
+        _check(lib().mppib_local_rollouts(self._h, C.byref(nl), C.byref(no)))
+        self.n_local, self.n_offset = nl.value, no.value
+
+    def push_params(self) -> None:
+        L = lib()
+        b = self.dyn.blob()
+        _check(L.mppib_set_blob(self._h, BLOB_DYN, b, len(b)))
+        b = self.cost.blob()
+        _check(L.mppib_set_blob(self._h, BLOB_COST, b, len(b)))
+        b = self.sampler.blob()
+        _check(L.mppib_set_blob(self._h, BLOB_SAMPLER, b, len(b)))
+        if self.dyn.DYN_ID == DYN_AUTORALLY_NN:
+            w = _f32(self.dyn.nn_theta)
+            _check(L.mppib_set_blob(self._h, BLOB_NN_WEIGHTS, _ptr(w), w.nbytes))
+        if self.cost.COST_ID == COST_AR_STANDARD:
+            if self.cost.costmap is None:
+                raise MppibError(-9, "ARStandardCost has no costmap (call loadTrackData / setCostmap)")
+            m = _f32(self.cost.costmap)
+            _check(L.mppib_set_blob(self._h, BLOB_COSTMAP, _ptr(m), m.nbytes))
+
+    def close(self) -> None:
+        if self._h:
+            lib().mppib_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # configuration
+    def set_solver(self, dt: float, lambda_: float, alpha: float) -> None:
+        _check(lib().mppib_set_solver(self._h, dt, lambda_, alpha))
+
+    def seed(self, seed: int, offset: int = 0) -> None:
+        _check(lib().mppib_seed(self._h, seed, offset))
+
+    def burn_draws(self, n: int) -> None:
+        _check(lib().mppib_burn_draws(self._h, n))
+
+    def rng_offset(self) -> int:
+        v = C.c_ulonglong()
+        _check(lib().mppib_get_rng_offset(self._h, C.byref(v)))
+        return v.value
+
+    def comm_init(self, unique_id: bytes) -> None:
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(lib().mppib_comm_init(self._h, buf))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().mppib_comm_unique_id(buf))
+        return buf.raw
+
+    # hot path
+    def solve(self, x0, U_in, optimization_stride: int = 1, iteration_num: int = 0):
+        x0, U_in = _f32(x0), _f32(U_in)
+        assert x0.size == self.D * self.S and U_in.size == self.D * self.T * self.Cdim
+        U_out = np.empty((self.D, self.T, self.Cdim), np.float32)
+        stats = (SolveStats * self.D)()
+        _check(lib().mppib_solve(self._h, _ptr(x0), _ptr(U_in), optimization_stride, iteration_num, _ptr(U_out), stats))
+        return U_out, [(s.baseline, s.normalizer, s.sum_w2) for s in stats]
+
+    def solve_into(self, x0: np.ndarray, U_in: np.ndarray, U_out: np.ndarray, stats, optimization_stride: int = 1,
+                   iteration_num: int = 0) -> None:
+        """Allocation-free variant for timing loops: all arrays are caller-owned float32 C-contiguous."""
+        _check(lib().mppib_solve(self._h, x0.ctypes.data, U_in.ctypes.data, optimization_stride, iteration_num,
+                                 U_out.ctypes.data, stats))
+
+    def set_noise(self, eps) -> None:
+        eps = _f32(eps)
+        _check(lib().mppib_set_noise(self._h, _ptr(eps), eps.size))
+
+    def draw_noise(self) -> None:
+        _check(lib().mppib_draw_noise(self._h))
+
+    def rollout_only(self, x0, U_in, optimization_stride: int = 1, iteration_num: int = 0) -> None:
+        x0, U_in = _f32(x0), _f32(U_in)
+        _check(lib().mppib_rollout_only(self._h, _ptr(x0), _ptr(U_in), optimization_stride, iteration_num))
+
+    def reduce_only(self):
+        U_out = np.empty((self.D, self.T, self.Cdim), np.float32)
+        stats = (SolveStats * self.D)()
+        _check(lib().mppib_reduce_only(self._h, _ptr(U_out), stats))
+        return U_out, [(s.baseline, s.normalizer, s.sum_w2) for s in stats]
+
+    # read-backs
+    def get_costs(self) -> np.ndarray:
+        a = np.empty((self.D, self.n_local), np.float32)
+        _check(lib().mppib_get_costs(self._h, _ptr(a)))
+        return a
+
+    def get_noise(self) -> np.ndarray:
+        a = np.empty((self.n_local, self.T, self.Cdim), np.float32)
+        _check(lib().mppib_get_noise(self._h, _ptr(a)))
+        return a
+
+    def get_samples(self) -> np.ndarray:
+        a = np.empty((self.D, self.n_local, self.T, self.Cdim), np.float32)
+        _check(lib().mppib_get_samples(self._h, _ptr(a)))
+        return a
+
+    def get_weights(self) -> np.ndarray:
+        a = np.empty((self.D, self.n_local), np.float32)
+        _check(lib().mppib_get_weights(self._h, _ptr(a)))
+        return a
+
+    def enable_timing(self, on: bool = True) -> None:
+        _check(lib().mppib_enable_timing(self._h, int(on)))
+
+    def timing(self) -> dict:
+        t = Timing()
+        _check(lib().mppib_get_timing(self._h, C.byref(t)))
+        return {"noise_ms": t.noise_ms, "rollout_ms": t.rollout_ms, "reduce_ms": t.reduce_ms, "total_ms": t.total_ms}
+
+    def launch_info(self) -> dict:
+        g, b, s, t, k = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().mppib_get_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(t), C.byref(k)))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "uses_tma": bool(t.value),
+                "kernels_per_solve": k.value}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class _Controller:
+    """Shared part of the controllers (include/mppi/controllers/controller.cuh:71-…). Trajectories are numpy arrays
+    shaped like the reference's Eigen matrices transposed: control [T][C] (Eigen C x T column-major is the same
+    memory), state [T][S], output [T][O]."""
+    NUM_DISTRIBUTIONS = 1
+
+    def __init__(self, model: _Dynamics, cost: _Cost, fb_controller, sampler: GaussianDistribution, dt: float,
+                 max_iter: int, lambda_: float, alpha: float, num_timesteps: int, num_rollouts: int,
+                 init_control_traj: Optional[np.ndarray] = None, seed: Optional[int] = None, device: int = 0,
+                 flags: int = 0, stream: Optional[int] = None, rank: int = 0, world_size: int = 1,
+                 lockstep_with_reference_ctor: bool = True):
+        self.model_, self.cost_, self.fb_controller_, self.sampler_ = model, cost, fb_controller, sampler
+        self.dt_, self.num_iters_, self.lambda_, self.alpha_ = dt, max_iter, lambda_, alpha
+        self.num_timesteps_, self.num_rollouts_ = num_timesteps, num_rollouts
+        T, Cd, S, O = num_timesteps, model.CONTROL_DIM, model.STATE_DIM, model.OUTPUT_DIM
+        self.control_ = np.zeros((T, Cd), np.float32) if init_control_traj is None else _f32(init_control_traj).copy()
+        self.control_history_ = np.zeros((2, Cd), np.float32)  # controller.cuh:968
+        self.state_ = np.zeros((T, S), np.float32)
+        self.output_ = np.zeros((T, O), np.float32)
+        self.slide_control_scale_ = np.zeros(Cd, np.float32)  # controller.cuh:67
+        self.baseline_ = [0.0] * self.NUM_DISTRIBUTIONS
+        self.normalizer_ = [0.0] * self.NUM_DISTRIBUTIONS
+        self.free_energy_statistics_ = {}
+        self.engine = Engine(model, cost, sampler, num_rollouts, num_timesteps, self.NUM_DISTRIBUTIONS, device, flags,
+                             stream, rank, world_size)
+        self.engine.set_solver(dt, lambda_, alpha)
+        # controller.cuh:59 seeds from the wall clock; tests pass an explicit seed (ControllerParams::seed_ is unsigned)
+        self.seed_ = (int.from_bytes(os.urandom(4), "little") if seed is None else seed) & 0xFFFFFFFF
+        self.engine.seed(self.seed_, 0)
+        if lockstep_with_reference_ctor:
+            # chooseAppropriateKernel draws one full noise buffer in the constructor (mppi_controller.cu:95)
+            self.engine.burn_draws(1)
+
+    # getters (controller.cuh:409-436,510-517)
+    def getControlSeq(self) -> np.ndarray:
+        return self.control_
+
+    def getTargetStateSeq(self) -> np.ndarray:
+        return self.state_
+
+    def getTargetOutputSeq(self) -> np.ndarray:
+        return self.output_
+
+    def getBaselineCost(self, ind: int = 0) -> float:
+        return self.baseline_[ind]
+
+    def getNormalizerCost(self, ind: int = 0) -> float:
+        return self.normalizer_[ind]
+
+    def getFreeEnergyStatistics(self) -> dict:
+        return self.free_energy_statistics_
+
+    def getSampledCostSeq(self) -> np.ndarray:
+        return self.engine.get_costs()
+
+    def getNumTimesteps(self) -> int:
+        return self.num_timesteps_
+
+    def getDt(self) -> float:
+        return self.dt_
+
+    def setSeedCUDARandomNumberGen(self, seed: int) -> None:  # controller.cu:200-207
+        self.seed_ = seed & 0xFFFFFFFF
+        self.engine.seed(self.seed_, 0)
+
+    def setParams(self) -> None:
+        """Push (possibly edited) plugin / solver parameters to the engine (Controller::setParams, controller.cuh:821-850)."""
+        self.engine.push_params()
+        self.engine.set_solver(self.dt_, self.lambda_, self.alpha_)
+
+    # host tail helpers — CPU, in the C library (controller.cuh:557-663)
+    def _smooth(self, u: np.ndarray) -> None:
+        lib().mppib_host_smooth_controls(_ptr(u), _ptr(self.control_history_), self.num_timesteps_,
+                                         self.model_.CONTROL_DIM)
+
+    def _slide(self, u: np.ndarray, steps: int) -> None:
+        z = self.model_.zero_control_
+        lib().mppib_host_slide_controls(_ptr(u), steps, self.num_timesteps_, self.model_.CONTROL_DIM, _ptr(z),
+                                        _ptr(self.slide_control_scale_))
+
+    def _output_trajectory(self, x0: np.ndarray, u: np.ndarray, states: np.ndarray, outputs: np.ndarray) -> None:
+        _check(lib().mppib_host_output_trajectory(self.model_.DYN_ID, C.byref(self.model_.params),
+                                                  _ptr(self.model_.nn_theta), _ptr(_f32(x0)), _ptr(u),
+                                                  self.num_timesteps_, C.c_float(self.dt_), _ptr(states),
+                                                  _ptr(outputs)))
+
+    def _save_control_history(self, steps: int, u: np.ndarray) -> None:  # controller.cuh:602-616
+        if steps == 1:
+            self.control_history_[0] = self.control_history_[1]
+            self.control_history_[1] = u[0]
+        elif steps >= 2:
+            self.control_history_[0] = u[steps - 2]
+            self.control_history_[1] = u[steps - 1]
+
+    def _free_energy(self, stats) -> dict:
+        out = np.zeros(3, np.float32)
+        st = SolveStats(*stats, 0.0)
+        lib().mppib_host_free_energy(C.byref(st), self.num_rollouts_, C.c_float(self.lambda_), _ptr(out))
+        return {"freeEnergyMean": float(out[0]), "freeEnergyVariance": float(out[1]),
+                "freeEnergyModifiedVariance": float(out[2])}
+
+
+class VanillaMPPIController(_Controller):
+    """controllers/MPPI/mppi_controller.cuh:14-17 — same constructor arguments; NUM_ROLLOUTS / MAX_TIMESTEPS are runtime."""
+    NUM_DISTRIBUTIONS = 1
+
+    def computeControl(self, state, optimization_stride: int = 1) -> None:
+        """controllers/MPPI/mppi_controller.cu:151-241."""
+        state = _f32(state)
+        prev_baseline = self.baseline_[0]
+        for opt_iter in range(self.num_iters_):
+            U, stats = self.engine.solve(state, self.control_, optimization_stride, opt_iter)
+            self.control_ = U[0].copy()
+            self.baseline_[0], self.normalizer_[0] = stats[0][0], stats[0][1]
+            fe = self._free_energy(stats[0])
+        fe["normalizerPercent"] = self.normalizer_[0] / self.num_rollouts_
+        fe["increase"] = self.baseline_[0] - prev_baseline
+        fe["previousBaseline"] = prev_baseline
+        self.free_energy_statistics_ = {"real_sys": fe}
+        self._smooth(self.control_)  # smoothControlTrajectory
+        self._output_trajectory(state, self.control_, self.state_, self.output_)  # computeStateTrajectory
+        for i in range(self.num_timesteps_):  # mppi_controller.cu:227-231
+            self.model_.enforceConstraints(None, self.control_[i])
+
+    def slideControlSequence(self, steps: int) -> None:
+        """controllers/MPPI/mppi_controller.cu (slideControlSequence): save history, then slide."""
+        self._save_control_history(steps, self.control_)
+        self._slide(self.control_, steps)
+
+
+class TubeMPPIController(_Controller):
+    """controllers/Tube-MPPI/tube_mppi_controller.cuh — actual + nominal system sharing one noise draw."""
+    NUM_DISTRIBUTIONS = 2
+
+    def __init__(self, *args, nominal_threshold: float = 20.0, **kwargs):
+        super().__init__(*args, **kwargs)
+        T = self.num_timesteps_
+        self.nominal_control_trajectory_ = self.control_.copy()
+        self.nominal_state_trajectory_ = np.zeros((T, self.model_.STATE_DIM), np.float32)
+        self.nominal_output_trajectory_ = np.zeros((T, self.model_.OUTPUT_DIM), np.float32)
+        self.nominalStateInit_ = False
+        self.nominal_threshold_ = nominal_threshold
+        self.nominal_state_used_ = 0
+
+    def setNominalThreshold(self, v: float) -> None:
+        self.nominal_threshold_ = v
+
+    def getNominalThreshold(self) -> float:
+        return self.nominal_threshold_
+
+    def getNominalControlSeq(self) -> np.ndarray:
+        return self.nominal_control_trajectory_
+
+    def getNominalStateSeq(self) -> np.ndarray:
+        return self.nominal_state_trajectory_
+
+    def _compute_state_trajectories(self, state: np.ndarray) -> None:
+        # tube_mppi_controller.cu:345-350: actual from `state`, nominal from nominal_state_trajectory_.col(0)
+        self._output_trajectory(state, self.control_, self.state_, self.output_)
+        x0n = self.nominal_state_trajectory_[0].copy()
+        self._output_trajectory(x0n, self.nominal_control_trajectory_, self.nominal_state_trajectory_,
+                                self.nominal_output_trajectory_)
+
+    def computeControl(self, state, optimization_stride: int = 1) -> None:
+        """controllers/Tube-MPPI/tube_mppi_controller.cu:157-299."""
+        state = _f32(state)
+        if not self.nominalStateInit_:
+            self.nominal_state_trajectory_[0] = state
+            self.nominalStateInit_ = True
+        prev = list(self.baseline_)
+        for opt_iter in range(self.num_iters_):
+            x0 = np.stack([state, self.nominal_state_trajectory_[0]])
+            U_in = np.stack([self.control_, self.nominal_control_trajectory_])
+            U, stats = self.engine.solve(x0, U_in, optimization_stride, opt_iter)
+            self.control_ = U[0].copy()
+            self.nominal_control_trajectory_ = U[1].copy()
+            for d in range(2):
+                self.baseline_[d], self.normalizer_[d] = stats[d][0], stats[d][1]
+            fe = [self._free_energy(stats[0]), self._free_energy(stats[1])]
+            self._compute_state_trajectories(state)
+            if self.baseline_[0] < self.baseline_[1] + self.nominal_threshold_:  # :268-280
+                self.nominal_state_used_ = 0
+                self.nominal_state_trajectory_ = self.state_.copy()
+                self.nominal_control_trajectory_ = self.control_.copy()
+            else:
+                self.nominal_state_used_ = 1
+        # smoothControlTrajectory (tube_mppi_controller.cu:327-331) smooths the NOMINAL sequence
+        self._smooth(self.nominal_control_trajectory_)
+        self._compute_state_trajectories(state)
+        for d, key in enumerate(("real_sys", "nominal_sys")):
+            fe[d]["normalizerPercent"] = self.normalizer_[d] / self.num_rollouts_
+            fe[d]["increase"] = self.baseline_[d] - prev[d]
+            fe[d]["previousBaseline"] = prev[d]
+            self.free_energy_statistics_[key] = fe[d]
+        self.free_energy_statistics_["nominal_state_used"] = self.nominal_state_used_
+
+    def updateNominalState(self, u) -> None:
+        """tube_mppi_controller.cu:333-343: propagate the nominal state one step with control u."""
+        xn, _, _ = self.model_.step(self.nominal_state_trajectory_[0], _f32(u), self.dt_)
+        self.nominal_state_trajectory_[0] = xn
+
+    def slideControlSequence(self, steps: int) -> None:
+        """tube_mppi_controller.cu:314-325."""
+        self.updateNominalState(self.nominal_control_trajectory_[0])
+        self._save_control_history(steps, self.nominal_control_trajectory_)
+        self._slide(self.nominal_control_trajectory_, steps)
+        self._slide(self.control_, steps)

@@ -1,0 +1,185 @@
+"""ctypes binding of oracle/libmppi_oracle.so (the CPU restatement of the reference path). Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmppi_oracle.so")
+_lib = None
+
+
+def build() -> None:
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_baseline.restype = C.c_float
+        _lib.orc_normalizer.restype = C.c_float
+        _lib.orc_ar_query_texture.restype = C.c_float
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def curand_normal(seed: int, offset: int, n: int) -> np.ndarray:
+    """Host XORWOW normals (same generator type/seed/offset semantics as controller.cu:192-207 + gaussian.cu:380)."""
+    out = np.empty(n, np.float32)
+    rc = lib().orc_curand_normal(C.c_ulonglong(seed), C.c_ulonglong(offset), C.c_size_t(n), _p(out))
+    if rc:
+        raise RuntimeError(f"orc_curand_normal failed: {rc}")
+    return out
+
+
+def set_gaussian_controls(means, sp, samples, C_, T, N, D, optimization_stride=1, iteration_num=0):
+    lib().orc_set_gaussian_controls(_p(_f32(means)), C.byref(sp), _p(samples), C_, T, N, D, optimization_stride,
+                                    iteration_num)
+
+
+def rollout(dyn_id, cost_id, dyn_params, cost_params, sp, nn_theta, costmap, N, T, D, dt, lam, alpha, x0, means,
+            samples, nthreads=1):
+    """samples [D][N][T][C] (controls, constrained in place). Returns costs [D][N]."""
+    costs = np.empty((D, N), np.float32)
+    rc = lib().orc_rollout(dyn_id, cost_id, C.byref(dyn_params), C.byref(cost_params), C.byref(sp), _p(nn_theta),
+                           _p(costmap), N, T, D, C.c_float(dt), C.c_float(lam), C.c_float(alpha), _p(_f32(x0)),
+                           _p(_f32(means)), _p(samples), _p(costs), nthreads)
+    if rc:
+        raise RuntimeError(f"orc_rollout failed: {rc}")
+    return costs
+
+
+def solve(dyn_id, cost_id, dyn_params, cost_params, sp, nn_theta, costmap, N, T, D, C_, dt, lam, alpha, x0, U_in, eps,
+          optimization_stride=1, iteration_num=0, sum_stride=32, nthreads=1, want_samples=False):
+    """One optimisation iteration (see orc_solve). Returns dict(U, baseline, normalizer, free_energy, costs[, samples])."""
+    U = np.empty((D, T, C_), np.float32)
+    base = np.empty(D, np.float32)
+    norm = np.empty(D, np.float32)
+    fe = np.empty((D, 3), np.float32)
+    costs = np.empty((D, N), np.float32)
+    samples = np.empty((D, N, T, C_), np.float32) if want_samples else None
+    rc = lib().orc_solve(dyn_id, cost_id, C.byref(dyn_params), C.byref(cost_params), C.byref(sp), _p(nn_theta),
+                         _p(costmap), N, T, D, C.c_float(dt), C.c_float(lam), C.c_float(alpha), _p(_f32(x0)),
+                         _p(_f32(U_in)), _p(_f32(eps)), optimization_stride, iteration_num, sum_stride, nthreads,
+                         _p(U), _p(base), _p(norm), _p(fe), _p(costs), _p(samples))
+    if rc:
+        raise RuntimeError(f"orc_solve failed: {rc}")
+    out = {"U": U, "baseline": base, "normalizer": norm, "free_energy": fe, "costs": costs}
+    if want_samples:
+        out["samples"] = samples
+    return out
+
+
+def baseline(costs) -> float:
+    c = _f32(costs)
+    return float(lib().orc_baseline(_p(c), c.size))
+
+
+def norm_exp(costs, lambda_inv, base) -> np.ndarray:
+    c = _f32(costs).copy()
+    lib().orc_norm_exp(_p(c), c.size, C.c_float(lambda_inv), C.c_float(base))
+    return c
+
+
+def normalizer(w) -> float:
+    w = _f32(w)
+    return float(lib().orc_normalizer(_p(w), w.size))
+
+
+def free_energy(w, base, lam) -> np.ndarray:
+    w = _f32(w)
+    out = np.empty(3, np.float32)
+    lib().orc_free_energy(_p(w), w.size, C.c_float(base), C.c_float(lam), _p(out))
+    return out
+
+
+def weighted_reduction(w, du, normalizer_, T, N, C_, sum_stride=32) -> np.ndarray:
+    out = np.empty((T, C_), np.float32)
+    lib().orc_weighted_reduction(_p(_f32(w)), _p(_f32(du)), _p(out), C.c_float(normalizer_), T, N, C_, sum_stride)
+    return out
+
+
+def smooth(u, history) -> np.ndarray:
+    u = _f32(u).copy()
+    T, C_ = u.shape
+    lib().orc_smooth(_p(u), _p(_f32(history)), T, C_)
+    return u
+
+
+def slide(u, steps, zero_control, scale) -> np.ndarray:
+    u = _f32(u).copy()
+    T, C_ = u.shape
+    lib().orc_slide(_p(u), steps, T, C_, _p(_f32(zero_control)), _p(_f32(scale)))
+    return u
+
+
+def enforce_constraints(lim, u) -> np.ndarray:
+    u = _f32(u).copy()
+    lib().orc_enforce_constraints(C.byref(lim), _p(u), u.size)
+    return u
+
+
+def dyn_step(dyn_id, dyn_params, nn_theta, x, u, dt):
+    S, C_, O = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_dims(dyn_id, C.byref(S), C.byref(C_), C.byref(O))
+    xn, xd, y = np.zeros(S.value, np.float32), np.zeros(S.value, np.float32), np.zeros(O.value, np.float32)
+    rc = lib().orc_dyn_step(dyn_id, C.byref(dyn_params), _p(nn_theta), _p(_f32(x)), _p(_f32(u)), C.c_float(dt), _p(xn),
+                            _p(xd), _p(y))
+    if rc:
+        raise RuntimeError("orc_dyn_step failed")
+    return xn, xd, y
+
+
+def state_cost(cost_id, cost_params, costmap, y, t=0, crash=0):
+    cr = C.c_int(crash)
+    c, term = C.c_float(), C.c_float()
+    rc = lib().orc_state_cost(cost_id, C.byref(cost_params), _p(costmap), _p(_f32(y)), t, C.byref(cr), C.byref(c),
+                              C.byref(term))
+    if rc:
+        raise RuntimeError("orc_state_cost failed")
+    return c.value, term.value, cr.value
+
+
+def ar_cost_terms(cost_params, costmap, s, crash=0):
+    cr = C.c_int(crash)
+    sp, st, tr, cc = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+    lib().orc_ar_cost_terms(C.byref(cost_params), _p(costmap), _p(_f32(s)), C.byref(cr), C.byref(sp), C.byref(st),
+                            C.byref(tr), C.byref(cc))
+    return {"speed": sp.value, "stabilizing": st.value, "track": tr.value, "crash": cc.value, "crash_status": cr.value}
+
+
+def ar_query_texture(cost_params, costmap, x, y) -> float:
+    return float(lib().orc_ar_query_texture(C.byref(cost_params), _p(costmap), C.c_float(x), C.c_float(y)))
+
+
+def fnn_forward(theta, layers, inp) -> np.ndarray:
+    layers = np.ascontiguousarray(layers, dtype=np.int32)
+    out = np.zeros(int(layers[-1]), np.float32)
+    lib().orc_fnn_forward(_p(_f32(theta)), layers.ctypes.data_as(C.c_void_p), len(layers), _p(_f32(inp)), _p(out))
+    return out
+
+
+def output_trajectory(dyn_id, dyn_params, nn_theta, x0, u, dt):
+    S, C_, O = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_dims(dyn_id, C.byref(S), C.byref(C_), C.byref(O))
+    u = _f32(u)
+    T = u.shape[0]
+    states, outputs = np.zeros((T, S.value), np.float32), np.zeros((T, O.value), np.float32)
+    rc = lib().orc_output_trajectory(dyn_id, C.byref(dyn_params), _p(nn_theta), _p(_f32(x0)), _p(u), T, C.c_float(dt),
+                                     _p(states), _p(outputs))
+    if rc:
+        raise RuntimeError("orc_output_trajectory failed")
+    return states, outputs

@@ -1,0 +1,427 @@
+"""GPU parity tests: the sm_100a path, called THROUGH THE C-ABI (mppi_generic_b200.host -> libmppi_b200.so), against the
+CPU oracle on the same seeded inputs. Tolerances are the reference's own:
+  per-sample trajectory cost  1e-4 relative   tests/mppi_core/rollout_kernel_tests.cu:258
+  weighted control average    1e-5 relative to the control scale (tree-order vs serial FP32 summation)
+  baseline / normaliser       FLOAT_EQ-class (4e-7 / 2e-6 relative)
+The raw N(0,1) buffer is read back from the device (mppib_get_noise) and handed to the oracle, so both sides consume
+bit-identical noise; the device stream itself is checked against the host cuRAND generator separately."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import mppi_generic_b200 as m
+from mppi_generic_b200 import workloads as W
+
+H = m.host
+pytestmark = pytest.mark.gpu
+
+COST_RTOL = 1e-4
+
+
+def _oracle_solve(w, eps, stride=1, it=0, want_samples=False):
+    return oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, w.dyn.nn_theta,
+                        w.cost.costmap, w.N, w.T, w.D, w.dyn.CONTROL_DIM, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps,
+                        optimization_stride=stride, iteration_num=it, nthreads=8, want_samples=want_samples)
+
+
+def _check_solve(w, e, stride=1, cost_rtol=COST_RTOL, u_tol=1e-5):
+    U, stats = e.solve(w.x0, w.U0, stride, 0)
+    eps = e.get_noise()
+    ref = _oracle_solve(w, eps, stride)
+    costs = e.get_costs()
+    np.testing.assert_allclose(costs, ref["costs"], rtol=cost_rtol, atol=1e-5)
+    scale = max(1.0, float(np.abs(ref["U"]).max()))
+    for d in range(w.D):
+        assert stats[d][0] == pytest.approx(float(ref["baseline"][d]), rel=cost_rtol)
+        # the normaliser inherits the per-sample cost differences through exp(-(c-beta)/lambda)
+        assert stats[d][1] == pytest.approx(float(ref["normalizer"][d]), rel=5e-3)
+    # U compared against the oracle run on the oracle's own costs: dominated by cost parity, so use a looser bound
+    np.testing.assert_allclose(U, ref["U"], atol=2e-3 * scale)
+    # tight check of the reduction itself: recompute the reference average from the DEVICE costs (float64)
+    samples = _oracle_solve(w, eps, stride, want_samples=True)["samples"]
+    lam_inv = np.float32(1.0 / w.lambda_)
+    for d in range(w.D):
+        c = costs[d].astype(np.float64)
+        wts = np.exp(-float(lam_inv) * (c - c.min()))
+        Uref = np.einsum("n,ntc->tc", wts / wts.sum(), samples[d].astype(np.float64))
+        np.testing.assert_allclose(U[d], Uref, atol=u_tol * scale, rtol=u_tol)
+        assert stats[d][0] == np.float32(c.min())
+        assert stats[d][1] == pytest.approx(wts.sum(), rel=2e-6)
+        assert stats[d][2] == pytest.approx((wts ** 2).sum(), rel=2e-6)
+    return U, stats, costs
+
+
+# ---- K0: noise stream ----------------------------------------------------------------------------------------------
+def test_device_noise_stream_matches_host_curand_indexing():
+    """Same XORWOW stream, seed and [n][t][c] layout as the host generator (values agree to the last ulp or two — the
+    device Box-Muller uses different intrinsics; SURVEY §8c: third-party arithmetic, 'parity unpinned' at that boundary)."""
+    w = W.cartpole(2048, 100)
+    e = w.make_engine()
+    e.seed(42, 0)
+    e.draw_noise()
+    a = e.get_noise().ravel()
+    ref = oracle.curand_normal(42, 0, a.size)
+    np.testing.assert_allclose(a, ref, rtol=0, atol=2e-6)
+    assert e.rng_offset() == a.size
+    e.draw_noise()  # continuation == elements [n, 2n) of the stream
+    b = e.get_noise().ravel()
+    np.testing.assert_allclose(b, oracle.curand_normal(42, a.size, a.size), rtol=0, atol=2e-6)
+    # burn_draws skips exactly one generateSamples worth of normals (mppi_controller.cu:95 lock-step)
+    e.seed(42, 0)
+    e.burn_draws(1)
+    e.draw_noise()
+    np.testing.assert_array_equal(e.get_noise().ravel(), b)
+    # re-seeding resets the offset to 0 (controller.cu:200-207)
+    e.seed(42, 0)
+    e.draw_noise()
+    np.testing.assert_array_equal(e.get_noise().ravel(), a)
+    e.close()
+
+
+def test_rank_slices_tile_the_global_stream():
+    """rank r of W draws elements [r*N/W*T*C, (r+1)*N/W*T*C) of the single global stream."""
+    w = W.cartpole(2048, 100)
+    full = w.make_engine()
+    full.draw_noise()
+    ref = full.get_noise()
+    full.close()
+    for world in (2, 4):
+        parts = []
+        for r in range(world):
+            e = H.Engine(w.dyn, w.cost, w.sampler, w.N, w.T, 1, rank=r, world_size=world)
+            e.seed(w.seed, 0)
+            e.draw_noise()
+            parts.append(e.get_noise())
+            assert e.n_offset == r * (w.N // world)
+            e.close()
+        np.testing.assert_array_equal(np.concatenate(parts), ref)
+    # a slice start that is NOT a multiple of 8192 normals (lead-in path)
+    w2 = W.cartpole(1000, 50)
+    f = w2.make_engine()
+    f.draw_noise()
+    ref2 = f.get_noise()
+    f.close()
+    e = H.Engine(w2.dyn, w2.cost, w2.sampler, w2.N, w2.T, 1, rank=1, world_size=2)
+    e.seed(w2.seed, 0)
+    e.draw_noise()
+    np.testing.assert_array_equal(e.get_noise(), ref2[500:])
+    e.close()
+
+
+# ---- K1: rollout kernel vs launchCPURolloutKernel -----------------------------------------------------------------
+def _rollout_kernel_test_workload(N=2048, T=100):
+    # tests/mppi_core/rollout_kernel_tests.cu:114-167: dt 0.01, lambda 0.5, alpha 0.001, sigma 0.4, cost (100,10,200,20)
+    w = W.cartpole(N, T)
+    w.dyn.setControlRanges([(-H.FLT_MAX, H.FLT_MAX)])
+    w.sampler.setStdDev([0.4])
+    w.lambda_, w.alpha = 0.5, 0.001
+    rng = np.random.RandomState(0)
+    w.x0 = rng.uniform(-1, 1, (1, 4)).astype(np.float32)
+    w.U0 = rng.uniform(-1, 1, (1, T, 1)).astype(np.float32)
+    return w
+
+
+@pytest.mark.parametrize("flags", [0, H.FLAG_NO_TMA])
+@pytest.mark.parametrize("bx", [32, 64, 128, 256])
+def test_cartpole_rollout_costs_match_cpu_oracle(flags, bx, monkeypatch):
+    monkeypatch.setenv("MPPIB_BX", str(bx))
+    w = _rollout_kernel_test_workload()
+    e = w.make_engine(flags=flags)
+    info = e.launch_info()
+    assert info["block"] == bx and info["uses_tma"] == (flags == 0)
+    _check_solve(w, e)
+    e.close()
+
+
+def test_rollout_only_and_reduce_only_hooks_with_handmade_noise():
+    w = _rollout_kernel_test_workload(512, 40)
+    e = w.make_engine()
+    eps = np.random.RandomState(3).randn(w.N, w.T, 1).astype(np.float32)
+    e.set_noise(eps)
+    e.rollout_only(w.x0, w.U0, 1, 0)
+    ref = _oracle_solve(w, eps)
+    np.testing.assert_allclose(e.get_costs(), ref["costs"], rtol=COST_RTOL)
+    U, stats = e.reduce_only()
+    np.testing.assert_allclose(U, ref["U"], atol=2e-3)
+    assert stats[0][0] == pytest.approx(float(ref["baseline"][0]), rel=COST_RTOL)
+    # zero noise: every rollout equals the nominal one => all costs equal, weights 1, U == clamp(mean)
+    e.set_noise(np.zeros_like(eps))
+    e.rollout_only(w.x0, w.U0, 1, 0)
+    c = e.get_costs()
+    assert np.all(c == c[0, 0])
+    U, stats = e.reduce_only()
+    np.testing.assert_allclose(U[0], w.U0[0], rtol=1e-6, atol=1e-7)
+    assert stats[0][1] == pytest.approx(w.N, rel=1e-6)
+    e.close()
+
+
+@pytest.mark.parametrize("N,T", [(33, 7), (1000, 50), (64, 1), (1, 16), (257, 100), (4096, 13)])
+def test_ragged_and_edge_sizes(N, T):
+    """N not a multiple of the block, T*C not a multiple of 4 (plain-load staging), single step, single rollout."""
+    w = _rollout_kernel_test_workload(N, T)
+    if N * T % 2:
+        with pytest.raises(m.MppibError):  # cuRAND needs an even count, as it would in the reference
+            e = w.make_engine()
+            e.solve(w.x0, w.U0)
+        return
+    e = w.make_engine()
+    assert e.launch_info()["uses_tma"] == ((T * 1) % 4 == 0)
+    _check_solve(w, e)
+    e.close()
+
+
+def test_optimization_stride_and_std_dev_decay_semantics():
+    w = _rollout_kernel_test_workload(1024, 32)
+    w.sampler.params.std_dev_decay = 0.9
+    e = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    U, stats = e.solve(w.x0, w.U0, 5, 3)  # stride 5, iteration 3 -> sigma * 0.9^3
+    eps = e.get_noise()
+    ref = _oracle_solve(w, eps, stride=5, it=3, want_samples=True)
+    np.testing.assert_allclose(e.get_costs(), ref["costs"], rtol=COST_RTOL)
+    s = e.get_samples()
+    np.testing.assert_allclose(s, ref["samples"], rtol=2e-7, atol=1e-7)  # FMA vs mul+add: <= 1 ulp
+    np.testing.assert_array_equal(s[0, :, :5, :], np.broadcast_to(w.U0[0, :5], (w.N, 5, 1)))  # t < stride -> mean
+    np.testing.assert_array_equal(s[0, 0], w.U0[0])  # sample 0 noise-free
+    first_pure = int(math.ceil((1.0 - 0.01) * w.N))
+    np.testing.assert_allclose(s[0, first_pure:, 5:], np.float32(0.4 * 0.9 ** 3) * eps[first_pure:, 5:], rtol=3e-7)
+    e.close()
+
+
+def test_control_constraints_are_applied_before_dynamics_cost_and_average():
+    w = _rollout_kernel_test_workload(1024, 40)
+    w.dyn.setControlRanges([(-0.25, 0.5)])
+    w.sampler.setStdDev([2.0])
+    e = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    U, stats, _ = _check_solve(w, e)
+    s = e.get_samples()
+    assert s.min() >= -0.25 and s.max() <= 0.5 and (s == 0.5).any() and (s == -0.25).any()
+    assert U.min() >= -0.25 - 1e-6 and U.max() <= 0.5 + 1e-6
+    e.close()
+
+
+def test_likelihood_ratio_cost_term():
+    """gaussian.cu:481-569 device formula; the reference's tests leave it unpinned (control_cost_coeff = 0 there)."""
+    w = _rollout_kernel_test_workload(512, 30)
+    w.sampler.setControlCostCoeff([0.7])
+    w.alpha = 0.3
+    e = w.make_engine()
+    _check_solve(w, e)
+    c1 = e.get_costs().copy()
+    w.sampler.setControlCostCoeff([0.0])
+    e2 = w.make_engine()
+    e2.solve(w.x0, w.U0)
+    assert np.abs(c1 - e2.get_costs()).max() > 1e-3  # the term really contributes
+    e.close()
+    e2.close()
+
+
+# ---- Tube-MPPI: two systems, one noise draw ------------------------------------------------------------------------
+def test_double_integrator_tube_two_systems():
+    w = W.double_integrator_tube(4096, 64)
+    rng = np.random.RandomState(1)
+    w.x0 = np.stack([[2.0, 0.0, 0.0, 1.0], [1.9, 0.1, 0.05, 1.1]]).astype(np.float32)
+    w.U0 = rng.uniform(-0.5, 0.5, (2, w.T, 2)).astype(np.float32)
+    w.sampler.setStdDev([1.0, 0.7], 0)
+    w.sampler.setStdDev([0.8, 1.2], 1)
+    w.sampler.setControlCostCoeff([0.3, 0.2])
+    w.alpha = 0.1
+    e = w.make_engine()
+    _check_solve(w, e)
+    e.close()
+
+
+def test_tube_actual_equals_nominal_when_inputs_equal():
+    # tests/mppi_core/rollout_kernel_tests.cu:169-198 (runRolloutKernelOnMultipleSystems): bit-equal costs
+    w = W.double_integrator_tube(2048, 100)
+    w.U0[:] = np.random.RandomState(4).uniform(-1, 1, (1, w.T, 2)).astype(np.float32)
+    e = w.make_engine()
+    U, stats = e.solve(w.x0, w.U0)
+    c = e.get_costs()
+    np.testing.assert_array_equal(c[0], c[1])
+    np.testing.assert_array_equal(U[0], U[1])
+    assert stats[0] == stats[1]
+    e.close()
+
+
+def test_double_integrator_vanilla():
+    w = W.double_integrator_vanilla(2000, 50)
+    e = w.make_engine()
+    _check_solve(w, e)
+    e.close()
+
+
+# ---- Autorally: NN dynamics + texture cost --------------------------------------------------------------------------
+def test_autorally_nn_all_ones_known_answer_on_device():
+    """tests/dynamics/ar_dynamics_nn_test.cu:483-529 (computeDynamicsGPU): theta = 1, s = 0, u = (1,-1) => s_der[3..6] = 33.
+    Observed through the rollout: one step of dt from x0 = 0 gives y = (0,0,0,33dt,33dt,33dt,33dt); the speed cost
+    4.25*(33dt-6)^2 is the only non-constant term we read back."""
+    w = W.autorally(64, 1)
+    w.dyn.updateModel([6, 32, 32, 4], np.ones(1412, np.float32))
+    w.dyn.setControlRanges([(-H.FLT_MAX, H.FLT_MAX)] * 2)
+    w.x0[:] = 0
+    w.U0[0, 0] = [1.0, -1.0]
+    w.dt = 0.01
+    p = w.cost.params
+    p.track_coeff, p.slip_coeff, p.crash_coeff = 0.0, 0.0, 0.0
+    e = w.make_engine()
+    e.set_noise(np.zeros((64, 1, 2), np.float32))
+    e.rollout_only(w.x0, w.U0)
+    c = e.get_costs()
+    assert c[0, 0] == pytest.approx(4.25 * (33 * 0.01 - 6.0) ** 2, rel=1e-6)
+    assert np.all(c == c[0, 0])
+    e.close()
+
+
+def test_autorally_cost_golden_values_on_device():
+    """tests/cost_functions/autorally_standard_cost_test.cu:897-982 — the reference's DEVICE known answers on
+    track_map_standard: speed 68.0, slip 10*atan(0.5)^2, track 1116.3333, crash 9000 at t=1 (discount 0.9).
+    The state is held in place with a zero network and dt -> 0, so cost_n = (c(t=0) + c(t=1)) / 2."""
+    w = W.autorally(32, 2)
+    w.dyn.updateModel([6, 32, 32, 4], np.zeros(1412, np.float32))
+    w.x0[0] = [3.0, 0.0, math.pi / 2, 0.0, 2.0, 1.0, 0.0]  # yaw rate 0 so the state does not move
+    w.dt = 1e-12
+    p = w.cost.params
+    p.discount = 0.9
+    e = w.make_engine()
+    e.set_noise(np.zeros((32, 2, 2), np.float32))
+
+    def run(**kw):
+        for k in ("track_coeff", "speed_coeff", "crash_coeff", "slip_coeff"):
+            setattr(p, k, kw.get(k, 0.0))
+        e.push_params()
+        e.rollout_only(w.x0, w.U0)
+        return float(e.get_costs()[0, 0])
+
+    assert run() == 0.0
+    assert run(speed_coeff=4.25) == pytest.approx(68.0, rel=4e-7)
+    assert run(slip_coeff=10.0) == pytest.approx(math.atan(0.5) ** 2 * 10, rel=1e-6)
+    track = run(track_coeff=200.0)
+    crash = run(crash_coeff=10000.0)
+    assert crash == pytest.approx((10000.0 + 9000.0) / 2, rel=1e-6)  # crash flag set by the map at t=0, sticky at t=1
+    # exact-texel-boundary lookups: device golden 1116.3333 (texels 319/209/189); see tests/test_oracle_golden.py
+    assert track == pytest.approx(1116.3333, rel=1e-6)
+    e.close()
+
+
+def test_autorally_rollout_matches_cpu_oracle():
+    w = W.autorally(2048, 100)
+    e = w.make_engine()
+    U, stats = e.solve(w.x0, w.U0)
+    eps = e.get_noise()
+    ref = _oracle_solve(w, eps)
+    c = e.get_costs()
+    rel = np.abs(c - ref["costs"]) / np.maximum(np.abs(ref["costs"]), 1.0)
+    # FNN tolerance in the reference is 1e-4 absolute per forward pass (fnn_helper_test.cu:497-546); over a 100-step
+    # recurrence with a point-sampled map, a texel flip near a cell boundary moves a sample's cost by a visible amount.
+    # Bar: 99% of samples within 1e-3, median within 1e-5.
+    assert np.median(rel) < 1e-5, np.median(rel)
+    assert np.quantile(rel, 0.99) < 1e-3, np.quantile(rel, 0.99)
+    assert stats[0][0] == pytest.approx(float(ref["baseline"][0]), rel=1e-3)
+    np.testing.assert_allclose(U, ref["U"], atol=5e-3)
+    e.close()
+
+
+# ---- K2 + whole solve properties at BASELINE sizes -----------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cartpole", "double_integrator_tube", "autorally"])
+def test_full_size_size_independent_properties(name):
+    """At BASELINE.json's full sizes the oracle is too slow for every test run; check the properties the domain offers:
+    determinism, weights in (0,1] with max 1 at the arg-min, eta = sum w, U a convex combination inside the control
+    box, sample 0 == nominal rollout, tube systems bit-equal for equal inputs."""
+    w = W.by_name(name)
+    e = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    U1, s1 = e.solve(w.x0, w.U0)
+    c1 = e.get_costs()
+    wts = e.get_weights()
+    e.seed(w.seed, 0)
+    U2, s2 = e.solve(w.x0, w.U0)
+    np.testing.assert_array_equal(U1, U2)  # same seed -> bit-identical solve
+    assert s1 == s2
+    assert np.isfinite(c1).all() and np.isfinite(U1).all()
+    for d in range(w.D):
+        assert s1[d][0] == c1[d].min()
+        assert wts[d].max() == 1.0 and wts[d].min() >= 0.0
+        assert int(np.argmax(wts[d])) == int(np.argmin(c1[d]))
+        assert s1[d][1] == pytest.approx(float(wts[d].astype(np.float64).sum()), rel=2e-6)
+        assert s1[d][2] == pytest.approx(float((wts[d].astype(np.float64) ** 2).sum()), rel=2e-6)
+        samples = e.get_samples()[d].astype(np.float64)
+        Uref = np.einsum("n,ntc->tc", wts[d].astype(np.float64) / wts[d].astype(np.float64).sum(), samples)
+        np.testing.assert_allclose(U1[d], Uref, atol=2e-5 * max(1.0, np.abs(Uref).max()))
+        lo = np.array([w.dyn.params.lim.rng_lo[i] for i in range(w.dyn.CONTROL_DIM)])
+        hi = np.array([w.dyn.params.lim.rng_hi[i] for i in range(w.dyn.CONTROL_DIM)])
+        assert (U1[d] >= lo - 1e-5).all() and (U1[d] <= hi + 1e-5).all()
+    if w.D == 2:
+        np.testing.assert_array_equal(c1[0], c1[1])
+    # sample 0 is the noise-free nominal rollout: compare with the oracle on that one sample
+    eps0 = e.get_noise()[:1]
+    w1 = W.by_name(name, N=1)
+    ref = oracle.rollout(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, w.dyn.nn_theta,
+                         w.cost.costmap, 1, w.T, w.D, w.dt, w.lambda_, w.alpha, w.x0, w.U0,
+                         np.ascontiguousarray(np.broadcast_to(w.U0[:, None], (w.D, 1, w.T, w.dyn.CONTROL_DIM))).copy())
+    # LR term of sample 0 uses N for the pure-noise test; with N=1 the oracle would treat it as pure noise, so only
+    # compare when the sampler's control cost coefficient is zero or U0 is zero (true for all three workloads)
+    np.testing.assert_allclose(c1[:, 0], ref[:, 0], rtol=1e-4)
+    e.close()
+
+
+# ---- controller level (behavioural, like the reference's integration tests) -----------------------------------------
+def test_vanilla_controller_one_computeControl_matches_oracle_pipeline():
+    """Whole Controller::computeControl (mppi_controller.cu:151-241) through the ctypes mirror vs the oracle pipeline:
+    solve -> Savitzky-Golay smoothing -> nominal roll-forward -> clamp."""
+    w = _rollout_kernel_test_workload(2048, 100)
+    w.dyn.setControlRanges([(-5.0, 5.0)])
+    ctrl = m.VanillaMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N,
+                                   init_control_traj=w.U0[0], seed=123)
+    assert ctrl.engine.rng_offset() == w.N * w.T  # the constructor's lock-step draw (mppi_controller.cu:95)
+    ctrl.computeControl(w.x0[0], 1)
+    eps = ctrl.engine.get_noise()
+    np.testing.assert_allclose(eps.ravel(), oracle.curand_normal(123, w.N * w.T, w.N * w.T), atol=2e-6)
+    ref = _oracle_solve(w, eps)
+    U = oracle.smooth(ref["U"][0], np.zeros((2, 1), np.float32))
+    states, outputs = oracle.output_trajectory(w.dyn.DYN_ID, w.dyn.params, None, w.x0[0], U, w.dt)
+    U = np.clip(U, -5.0, 5.0)
+    np.testing.assert_allclose(ctrl.getControlSeq(), U, atol=2e-3)
+    np.testing.assert_allclose(ctrl.getTargetStateSeq(), states, atol=5e-3, rtol=1e-3)
+    assert ctrl.getBaselineCost() == pytest.approx(float(ref["baseline"][0]), rel=1e-4)
+    fe = ctrl.getFreeEnergyStatistics()["real_sys"]
+    assert fe["freeEnergyMean"] == pytest.approx(float(ref["free_energy"][0, 0]), rel=1e-3)
+    assert fe["normalizerPercent"] == pytest.approx(ctrl.getNormalizerCost() / w.N)
+
+
+def test_cartpole_swing_up_behaviour():
+    """tests/controllers/vanilla_mppi_test.cu:79-136: N=2048, T=100, 1000 control steps from rest, baseline < 1.0."""
+    w = W.cartpole(2048, 100)
+    w.dyn.setControlRanges([(-H.FLT_MAX, H.FLT_MAX)])
+    ctrl = m.VanillaMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N, seed=42)
+    ctrl.slide_control_scale_[0] = 1.0
+    x = np.zeros(4, np.float32)
+    for i in range(1000):
+        ctrl.computeControl(x, 1)
+        u = ctrl.getControlSeq()[0].copy()
+        x, _, _ = w.dyn.step(x, u, w.dt)
+        ctrl.slideControlSequence(1)
+    assert ctrl.getBaselineCost() < 1.0
+    assert abs(abs(float(x[2])) - math.pi) < 0.3  # pole up
+
+
+def test_tube_controller_runs_and_tracks_the_circle():
+    """tests/controllers/tube_mppi_test.cu: DoubleIntegrator on the circular track under disturbance; the actual system
+    must stay on the track (no crash cost in the baseline) for 300 steps."""
+    w = W.double_integrator_tube(2048, 50)
+    ctrl = m.TubeMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N, seed=7,
+                                nominal_threshold=20.0)
+    x = w.x0[0].copy()
+    rng = np.random.RandomState(0)
+    inside = 0
+    for i in range(300):
+        ctrl.computeControl(x, 1)
+        u = ctrl.getControlSeq()[0].copy()
+        x, _, _ = w.dyn.step(x, u, w.dt)
+        x[2:] += rng.randn(2).astype(np.float32) * 0.1 * math.sqrt(w.dt)
+        ctrl.slideControlSequence(1)
+        r2 = float(x[0] ** 2 + x[1] ** 2)
+        inside += (1.875 ** 2 <= r2 <= 2.125 ** 2)
+    assert inside >= 290
+    assert ctrl.getFreeEnergyStatistics()["nominal_state_used"] in (0, 1)

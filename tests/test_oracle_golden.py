@@ -1,0 +1,282 @@
+"""Pins the CPU oracle (oracle/mppi_oracle.cpp) against the known-answer values the reference's own tests hold for the
+hot path. No GPU, no product code: if these fail the oracle is wrong and no parity claim stands."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+import mppi_generic_b200 as m
+from mppi_generic_b200 import workloads as W
+
+H = m.host
+
+
+def test_fnn_all_ones_gives_33():
+    # tests/dynamics/ar_dynamics_nn_test.cu:445-481: theta = 1, s = 0, u = (1,-1)  =>  s_der[3..6] = 33, kinematics 0
+    dyn = H.NeuralNetModel()
+    theta = np.ones(1412, np.float32)
+    x = np.zeros(7, np.float32)
+    u = np.array([1.0, -1.0], np.float32)
+    xn, xd, y = oracle.dyn_step(H.DYN_AUTORALLY_NN, dyn.params, theta, x, u, 0.1)
+    np.testing.assert_array_equal(xd[:3], 0.0)
+    np.testing.assert_allclose(xd[3:], 33.0, rtol=4e-7)  # EXPECT_FLOAT_EQ == 4 ULP
+    out = oracle.fnn_forward(theta, [6, 32, 32, 4], [0, 0, 0, 0, 1, -1])
+    np.testing.assert_allclose(out, 33.0, rtol=4e-7)
+    # product host twin agrees (Dynamics::step host method)
+    dyn.updateModel([6, 32, 32, 4], theta)
+    xn2, xd2, _ = dyn.step(x, u, 0.1)
+    np.testing.assert_allclose(xd2, xd, rtol=4e-7)
+
+
+def test_fnn_weight_layout_matches_reference_packing():
+    # tests/nn_helpers/fnn_helper_test.cu:199-253 / fnn_helper.cu:176-183: W (row-major out x in) then b, layer by layer
+    rng = np.random.RandomState(0)
+    theta = rng.randn(1412).astype(np.float32)
+    W1, b1 = theta[:192].reshape(32, 6), theta[192:224]
+    W2, b2 = theta[224:1248].reshape(32, 32), theta[1248:1280]
+    W3, b3 = theta[1280:1408].reshape(4, 32), theta[1408:]
+    x = rng.randn(6).astype(np.float32)
+    ref = W3.astype(np.float64) @ np.tanh(W2.astype(np.float64) @ np.tanh(W1.astype(np.float64) @ x + b1) + b2) + b3
+    out = oracle.fnn_forward(theta, [6, 32, 32, 4], x)
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)  # fnn_helper_test.cu:497-546 tolerance 1e-4
+
+
+def _ar_cost():
+    cost = H.ARStandardCost()
+    ch0, xb, yb, ppm = W.track_map_standard()
+    cost.loadTrackData(ch0, xb[0], xb[1], yb[0], yb[1], ppm)
+    return cost
+
+
+def test_ar_standard_cost_individual_terms():
+    # tests/cost_functions/autorally_standard_cost_test.cu:897-982 on track_map_standard
+    cost = _ar_cost()
+    p = cost.params
+    p.discount = 0.9
+    s = np.array([3.0, 0.0, math.pi / 2, 0.0, 2.0, 1.0, 0.1, 0.0], np.float32)
+    terms = oracle.ar_cost_terms(p, cost.costmap, s, crash=0)
+    assert terms["speed"] == pytest.approx(4.0 ** 2 * 4.25, rel=4e-7)           # 68.0
+    assert terms["stabilizing"] == pytest.approx(math.atan(0.5) ** 2 * 10, rel=1e-6)
+    # Track term: the state puts both lookups EXACTLY on texel boundaries (u*600 = 320.00002, v*600 = 210.00001 and
+    # 189.99999). The reference's GPU texture unit resolves them to texels (319,209)/(319,189) => 1116.3333, the value
+    # its test hard-codes for the DEVICE path (autorally_standard_cost_test.cu:958-960); the reference's HOST branch
+    # (ar_standard_cost.cu:236-242: float v*600 rounds to 190.0, then -0.5, clamp, std::round) lands on (320,210)/(320,190)
+    # => 1106.6666. The oracle
+    # restates the host branch; the device value is pinned on the GPU in tests/test_gpu_parity.py.
+    host_track = 200.0 * ((4.5 + 320 / 600.0) + (5.5 + 320 / 600.0)) / 2.0
+    assert terms["track"] == pytest.approx(host_track, rel=1e-6)
+    assert abs(terms["track"] - 1116.3333) < 200 * 0.05  # within one texel of the device golden value
+    assert terms["crash_status"] == 1 and terms["crash"] == pytest.approx(10000.0)
+    total, _, crash = oracle.state_cost(H.COST_AR_STANDARD, p, cost.costmap, s, t=1, crash=0)
+    expect = 68.0 + math.atan(0.5) ** 2 * 10 + host_track + 9000.0
+    assert total == pytest.approx(expect, rel=1e-6) and crash == 1
+    total4, _, _ = oracle.state_cost(H.COST_AR_STANDARD, p, cost.costmap, s, t=4, crash=0)
+    assert total4 == pytest.approx(68.0 + math.atan(0.5) ** 2 * 10 + host_track + 0.9 ** 4 * 10000, rel=1e-6)
+
+
+def test_ar_cost_texture_lookup_is_point_sampled_and_clamped():
+    # texture emulation of ar_standard_cost.cu:225-243: normalised coords, -0.5, clamp, round
+    cost = _ar_cost()
+    p = cost.params
+    ch0 = cost.costmap[..., 0]
+    # world (x,y) -> texel (j,i): j = (x+13)*20 - 0.5, i = (y+10)*20 - 0.5
+    for (x, y) in [(0.0, 0.0), (3.0, 0.5), (-12.98, 19.9), (16.99, -9.99)]:
+        j = int(round(min(max((x + 13) * 20 - 0.5, 0), 599)))
+        i = int(round(min(max((y + 10) * 20 - 0.5, 0), 599)))
+        assert oracle.ar_query_texture(p, cost.costmap, x, y) == pytest.approx(float(ch0[i, j]), rel=1e-6)
+    # out of bounds clamps to the edge texel
+    assert oracle.ar_query_texture(p, cost.costmap, -100.0, -100.0) == pytest.approx(float(ch0[0, 0]))
+    assert oracle.ar_query_texture(p, cost.costmap, 100.0, 100.0) == pytest.approx(float(ch0[599, 599]))
+
+
+def test_enforce_constraints_known_answers():
+    # tests/dynamics/dynamics_generic_tests.cu:259-283 and :285-357
+    lim = H.ControlLimits()
+    lim.rng_lo[0], lim.rng_hi[0] = -2, 5
+    for u, expect in [(100, 5), (-42178, -2), (2, 2), (-1.5, -1.5)]:
+        assert oracle.enforce_constraints(lim, [u])[0] == expect
+    lim.rng_lo[1], lim.rng_hi[1] = -6, 8
+    lim.rng_lo[2], lim.rng_hi[2] = -11, 16
+    np.testing.assert_array_equal(oracle.enforce_constraints(lim, [48, 48, 48]), [5, 8, 16])
+    np.testing.assert_array_equal(oracle.enforce_constraints(lim, [-51, -51, -51]), [-2, -6, -11])
+    np.testing.assert_array_equal(oracle.enforce_constraints(lim, [-1.5, -1.5, -1.5]), [-1.5, -1.5, -1.5])
+    # deadband semantics (dynamics.cuh:254-261)
+    lim = H.ControlLimits()
+    lim.deadband[0] = 0.5
+    assert oracle.enforce_constraints(lim, [0.3])[0] == 0.0
+    assert oracle.enforce_constraints(lim, [1.0])[0] == 0.5
+    assert oracle.enforce_constraints(lim, [-1.0])[0] == -0.5
+
+
+def test_update_state_euler():
+    # tests/dynamics/dynamics_generic_tests.cu:359-417: s=(0,1,2,3), s_der=(0,1,2,3), dt=0.1 -> (0,1.1,2.2,3.3)
+    dyn = H.DoubleIntegratorDynamics()
+    x = np.array([0, 1, 2, 3], np.float32)
+    u = np.array([2, 3], np.float32)  # xdot = (x2, x3, u0, u1) = (2,3,2,3)
+    xn, xd, y = oracle.dyn_step(H.DYN_DOUBLE_INTEGRATOR, dyn.params, None, x, u, 0.1)
+    np.testing.assert_allclose(xd, [2, 3, 2, 3])
+    np.testing.assert_allclose(xn, [0.2, 1.3, 2.2, 3.3], rtol=4e-7)
+    np.testing.assert_array_equal(y, xn)
+
+
+def test_cartpole_dynamics_formula():
+    # dynamics/cartpole/cartpole_dynamics.cu:48-69 evaluated in float64 (tests/dynamics/cartpole_dynamics_tests.cu:153-199
+    # only compares CPU with GPU; the formula itself is the known answer)
+    dyn = H.CartpoleDynamics(2.0, 3.0, 4.0)
+    x = np.array([0.1, 0.3, 0.23, 0.334], np.float32)
+    u = np.array([0.654], np.float32)
+    _, xd, _ = oracle.dyn_step(H.DYN_CARTPOLE, dyn.params, None, x, u, 0.01)
+    th, thd, f, mc, mp_, lp, g = 0.23, 0.334, 0.654, 2.0, 3.0, 4.0, 9.81
+    s, c = math.sin(th), math.cos(th)
+    ref1 = 1.0 / (mc + mp_ * s * s) * (f + mp_ * s * (lp * thd * thd + g * c))
+    ref3 = 1.0 / (lp * (mc + mp_ * s * s)) * (-f * c - mp_ * lp * thd * thd * c * s - (mc + mp_) * g * s)
+    np.testing.assert_allclose(xd, [0.3, ref1, 0.334, ref3], rtol=2e-6)
+
+
+def test_cartpole_quadratic_cost_known_answer():
+    # tests/cost_functions/cartpole_quadratic_cost_test.cu:109-177 (defaults 1000,100,2000,100; goal (0,0,pi,0))
+    cost = H.CartpoleQuadraticCost()
+    s = np.array([1, 2, 3, 4], np.float32)
+    c, term, _ = oracle.state_cost(H.COST_CARTPOLE_QUADRATIC, cost.params, None, s)
+    ref = 1 * 1000 + 4 * 100 + (3 - math.pi) ** 2 * 2000 + 16 * 100
+    assert c == pytest.approx(ref, rel=1e-6) and term == 0.0
+    cost.params.terminal_cost_coeff = 2.5
+    _, term, _ = oracle.state_cost(H.COST_CARTPOLE_QUADRATIC, cost.params, None, s)
+    assert term == pytest.approx(2.5 * ref, rel=1e-6)
+
+
+def test_double_integrator_circle_cost():
+    # cost_functions/double_integrator/double_integrator_circle_cost.cu:34-59
+    cost = H.DoubleIntegratorCircleCost()
+    c, _, _ = oracle.state_cost(H.COST_DI_CIRCLE, cost.params, None, np.array([2, 0, 0, 2], np.float32))
+    assert c == pytest.approx(0.0, abs=1e-6)  # on the circle, |v| = 2, L = 4
+    c, _, _ = oracle.state_cost(H.COST_DI_CIRCLE, cost.params, None, np.array([3, 0, 0, 1], np.float32), t=5)
+    assert c == pytest.approx(1000.0 + 1.0 + 1.0, rel=1e-6)  # crash + |1-2| + |3-4|
+
+
+def test_savitzky_golay_smoothing_known_answers():
+    # tests/controllers/controller_generic_tests.cu:214-239
+    hist = np.zeros((2, 3), np.float32)
+    u = np.ones((1, 3), np.float32)
+    out = oracle.smooth(u, hist)
+    np.testing.assert_allclose(out[0], (17 + 12 - 3) / 35.0, rtol=4e-7)
+    u = np.array([[1, 1, 1], [2, 2, 2]], np.float32)
+    out = oracle.smooth(u, hist)
+    np.testing.assert_allclose(out[0], (1 * 17 + 2 * 12 + 2 * -3) / 35.0, rtol=4e-7)
+    np.testing.assert_allclose(out[1], (1 * 12 + 2 * 17 + 2 * 12 + 2 * -3) / 35.0, rtol=4e-7)
+    # product host twin == oracle
+    L = H.lib()
+    v = u.copy()
+    L.mppib_host_smooth_controls(v.ctypes.data, hist.ctypes.data, 2, 3)
+    np.testing.assert_array_equal(v, out)
+
+
+def test_slide_control_sequence_known_answers():
+    # tests/controllers/controller_generic_tests.cu:241-282 (T=100, scale 0 -> tail becomes zero_control)
+    T = 100
+    u = np.repeat(np.arange(T, dtype=np.float32)[:, None], 2, axis=1)
+    z, sc = np.zeros(2, np.float32), np.zeros(2, np.float32)
+    s1 = oracle.slide(u, 1, z, sc)
+    for i in range(T):
+        assert s1[i, 0] == (0 if i + 1 > T - 1 else min(i + 1, T - 1))
+    s2 = oracle.slide(s1, 10, z, sc)
+    for i in range(T):
+        assert s2[i, 0] == (0 if i + 10 > T - 2 else min(i + 11, T - 1))
+    v = u.copy()
+    H.lib().mppib_host_slide_controls(v.ctypes.data, 1, T, 2, z.ctypes.data, sc.ctypes.data)
+    np.testing.assert_array_equal(v, s1)
+
+
+def test_norm_exp_baseline_normalizer_identities():
+    # tests/mppi_core/normexp_kernel_tests.cu:79-178: N=555 / 28754 / 6048, gamma = 0.3, costs ~ N(100, 2)
+    rng = np.random.RandomState(7)
+    for n in (555, 6048, 28754):
+        costs = (100 + 2 * rng.randn(n)).astype(np.float32)
+        base = oracle.baseline(costs)
+        assert base == costs.min()
+        w = oracle.norm_exp(costs, 0.3, base)
+        ref = np.exp(np.float32(-0.3) * (costs - np.float32(base))).astype(np.float32)
+        np.testing.assert_allclose(w, ref, rtol=4e-7)
+        assert oracle.normalizer(w) == pytest.approx(float(w.astype(np.float64).sum()), rel=1e-7)
+    # first minimum wins; value identical either way (mppi_common.cu:885-900)
+    assert oracle.baseline(np.array([3, 1, 2, 1], np.float32)) == 1.0
+
+
+def test_free_energy_formula():
+    # core/mppi_common.cu:1065-1081
+    rng = np.random.RandomState(3)
+    w = rng.rand(1000).astype(np.float32)
+    fe = oracle.free_energy(w, 5.0, 2.0)
+    norm = w.astype(np.float64).sum() / 1000
+    var = (w.astype(np.float64) ** 2).sum()
+    assert fe[0] == pytest.approx(-2.0 * math.log(norm) + 5.0, rel=1e-5)
+    assert fe[1] == pytest.approx(2.0 * (var / 1000 - norm ** 2), rel=1e-4)
+
+
+def test_weighted_reduction_matches_triple_loop():
+    # tests/mppi_core/weightedreduction_kernel_tests.cu:20-133: N=1024, C=6, T=100, stride 64
+    rng = np.random.RandomState(11)
+    N, T, Cd = 1024, 100, 6
+    w = rng.rand(N).astype(np.float32)
+    du = rng.randn(N, T, Cd).astype(np.float32)
+    eta = float(w.astype(np.float64).sum())
+    out = oracle.weighted_reduction(w, du, eta, T, N, Cd, 64)
+    ref = np.einsum("n,ntc->tc", w.astype(np.float64) / eta, du.astype(np.float64))
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-6)
+
+
+def test_set_gaussian_controls_three_cases():
+    # sampling_distributions/gaussian/gaussian.cu:101-121
+    N, T, Cd = 200, 6, 2
+    sp = H.GaussianDistribution(2, [0.5, 2.0]).params
+    eps = np.random.RandomState(5).randn(1, N, T, Cd).astype(np.float32)
+    mean = np.arange(T * Cd, dtype=np.float32).reshape(1, T, Cd)
+    s = eps.copy()
+    oracle.set_gaussian_controls(mean, sp, s, Cd, T, N, 1, optimization_stride=2)
+    np.testing.assert_array_equal(s[0, 0], mean[0])                    # sample 0 == mean
+    np.testing.assert_array_equal(s[0, :, :2], np.broadcast_to(mean[0, :2], (N, 2, Cd)))  # t < stride == mean
+    sd = np.array([0.5, 2.0], np.float32)
+    first_pure = int(math.ceil((1.0 - 0.01) * N))  # n >= 0.99*N  -> 198
+    np.testing.assert_array_equal(s[0, first_pure:, 2:], sd * eps[0, first_pure:, 2:])
+    np.testing.assert_allclose(s[0, 1:first_pure, 2:], mean[0, 2:] + sd * eps[0, 1:first_pure, 2:], rtol=1e-6)
+
+
+def test_curand_host_stream_properties():
+    # same generator type / seed / offset semantics as controllers/controller.cu:192-207. Values are third-party
+    # (libcurand): pinned here only structurally — determinism, continuation, offsets honoured at multiples of 8192.
+    a = oracle.curand_normal(42, 0, 32768)
+    b = oracle.curand_normal(42, 0, 32768)
+    np.testing.assert_array_equal(a, b)
+    c = oracle.curand_normal(42, 16384, 16384)
+    np.testing.assert_array_equal(a[16384:], c)
+    assert abs(float(a.mean())) < 0.03 and abs(float(a.std()) - 1.0) < 0.03
+    assert not np.array_equal(a, oracle.curand_normal(43, 0, 32768))
+
+
+def test_rollout_actual_equals_nominal_when_inputs_equal():
+    # tests/mppi_core/rollout_kernel_tests.cu:181-198: same x0 / mean for both systems -> identical costs
+    w = W.double_integrator_tube(N=256, T=20)
+    eps = oracle.curand_normal(7, 0, 256 * 20 * 2).reshape(256, 20, 2)
+    r = oracle.solve(H.DYN_DOUBLE_INTEGRATOR, H.COST_DI_CIRCLE, w.dyn.params, w.cost.params, w.sampler.params, None,
+                     None, 256, 20, 2, 2, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps)
+    np.testing.assert_array_equal(r["costs"][0], r["costs"][1])
+    np.testing.assert_array_equal(r["U"][0], r["U"][1])
+
+
+def test_output_trajectory_host_twin_matches_oracle():
+    # controllers/controller.cuh:643-663 — product host twin (libmppi_b200) vs oracle restatement
+    for w in (W.cartpole(64, 30), W.autorally(64, 30)):
+        rng = np.random.RandomState(2)
+        u = rng.randn(w.T, w.dyn.CONTROL_DIM).astype(np.float32)
+        st, out = oracle.output_trajectory(w.dyn.DYN_ID, w.dyn.params, w.dyn.nn_theta, w.x0[0], u, w.dt)
+        st2 = np.zeros_like(st)
+        out2 = np.zeros_like(out)
+        rc = H.lib().mppib_host_output_trajectory(w.dyn.DYN_ID, C.byref(w.dyn.params),
+                                                  None if w.dyn.nn_theta is None else w.dyn.nn_theta.ctypes.data,
+                                                  w.x0[0].ctypes.data, u.ctypes.data, w.T, C.c_float(w.dt),
+                                                  st2.ctypes.data, out2.ctypes.data)
+        assert rc == 0
+        np.testing.assert_allclose(st2, st, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out2, out, rtol=1e-5, atol=1e-6)
