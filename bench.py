@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — computeControl Hz of the B200 MPPI engine (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus N --steps K --warmup W [--workload autorally|cartpole|double_integrator_tube]
+    python bench.py --impl reference ...      # the reference's CPU step() loop (oracle port) on the host cores
+
+A "step" is one optimisation iteration of Controller::computeControl (noise draw -> N x T rollout -> baseline /
+exp-weights -> weighted control average) on synthetic inputs. Default workload = the configuration the
+north-star target is quoted on: Autorally NN dynamics + map cost, N=32768, T=100 (BASELINE.json configs[3]); rollouts
+are sharded over the N GPUs with ONE NCCL all-gather per solve (strong scaling: total work fixed).
+
+Reported numbers
+  value     solves/s with the inputs resident: K solves enqueued back to back (x0 / U travel in the kernel parameter
+            bank), one sync at the end, CUDA events on the launching stream, max over ranks.
+  e2e       solves/s through the public C-ABI call mppib_solve with HOST buffers, one blocking call per solve: host
+            inputs -> device, result -> host every step (what Controller::computeControl does).
+  roofline  K1 (fused rollout kernel): algorithmic bytes (N_local*T*C*4, one read of the noise buffer) / its average
+            duration from CUDA events in a separate pass of the same process with L2 flushed between K0 and K1.
+  cpu_baseline  the oracle (CPU port of the reference's launchCPURolloutKernel + host weight code) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "computeControl_hz"
+UNIT = "solves/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, device_index: int):
+        super().__init__(daemon=True)
+        self.idx, self.stop_flag, self.samples, self.reasons, self.max_mhz = device_index, False, [], set(), None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _workload(args):
+    from mppi_generic_b200 import workloads as W
+    return W.by_name(args.workload, args.rollouts, args.timesteps)
+
+
+def _cpu_solve_hz(w, nthreads, repeats, sample_N=None):
+    """Times the oracle's full solve (setGaussianControls + CPU rollout + min/exp/sum + weighted reduction) on the host
+    cores. Noise is pre-generated outside the timed region, as in the reference's CPU path, which reads the samples the
+    GPU drew (tests/include/kernel_tests/core/rollout_kernel_test.cu:504-541). Returns (Hz of a FULL-size solve, text)."""
+    import oracle
+    N = w.N if sample_N is None else min(sample_N, w.N)
+    Cd = w.dyn.CONTROL_DIM
+    eps = oracle.curand_normal(w.seed, 0, N * w.T * Cd).reshape(N, w.T, Cd)
+    sp = w.sampler.params
+
+    def once():
+        return oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, sp, w.dyn.nn_theta,
+                            w.cost.costmap, N, w.T, w.D, Cd, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps,
+                            nthreads=nthreads)
+    once()
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        once()
+    dt = (time.perf_counter() - t0) / repeats
+    full = dt * (w.N / N)
+    return 1.0 / full, f"{repeats} solves of {N}/{w.N} rollouts x {w.T} steps, {nthreads} threads, scaled to N={w.N}", dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path. The reference cannot be compiled here (all
+    its host headers need Eigen, absent from this image), so this arm runs the oracle port of
+    launchCPURolloutKernel + the host weight functions with all host threads, on the same workload/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = _workload(args)
+    ncores = os.cpu_count() or 1
+    # bound each step to roughly <= 1 s of CPU work: sample the rollouts if the full solve is longer
+    hz_probe, _, dt_probe = _cpu_solve_hz(w, ncores, 1, sample_N=min(w.N, 2048))
+    est_full = dt_probe * w.N / min(w.N, 2048)
+    sample_N = w.N if est_full <= 1.5 else max(2048, int(w.N * 1.5 / est_full) // 64 * 64)
+    import oracle
+    N = min(sample_N, w.N)
+    Cd = w.dyn.CONTROL_DIM
+    eps = oracle.curand_normal(w.seed, 0, N * w.T * Cd).reshape(N, w.T, Cd)
+
+    def once():
+        oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, w.dyn.nn_theta,
+                     w.cost.costmap, N, w.T, w.D, Cd, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps, nthreads=ncores)
+    for _ in range(args.warmup):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        once()
+    per = (time.perf_counter() - t0) / args.steps * (w.N / N)
+    value = 1.0 / per
+    sample = f"each step = CPU solve of {N}/{w.N} rollouts x {w.T} steps on {ncores} threads, scaled to N={w.N}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "num_rollouts": w.N, "num_timesteps": w.T, "controller": w.controller},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_engine(args):
+    import torch
+    import mppi_generic_b200 as m
+    H = m.host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = _workload(args)
+    stream = torch.cuda.current_stream()
+    flags = 0
+    e = H.Engine(w.dyn, w.cost, w.sampler, w.N, w.T, w.D, device=local_rank, flags=flags,
+                 stream=stream.cuda_stream, rank=rank, world_size=world)
+    e.set_solver(w.dt, w.lambda_, w.alpha)
+    e.seed(w.seed, 0)
+    if world > 1:
+        ids = [H.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        e.comm_init(ids[0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x0 = np.ascontiguousarray(w.x0, np.float32)
+    U = np.ascontiguousarray(w.U0, np.float32).copy()
+    U_out = np.empty_like(U)
+    stats = (H.SolveStats * w.D)()
+
+    # ---- warm-up ---------------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- value: K solves enqueued back to back, inputs resident (kernel parameter bank), device-timed -----------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        e.solve_async(x0, U, w.optimization_stride, 0)
+    ev1.record(stream)
+    e.solve_wait()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+
+    # ---- e2e: one blocking C-ABI call per solve with host buffers (closed loop: U feeds back) -------------------------
+    barrier()
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
+        U[...] = U_out
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max(e2e_wall_ms, ev0.elapsed_time(ev1))
+
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    clocks = sampler.result()
+
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- roofline pass: K1 duration from CUDA events, L2 flushed between K0 and K1, same process ----------------------
+    U[...] = w.U0
+    e.set_option(H.OPT_L2_FLUSH_BYTES, 256 << 20)
+    e.enable_timing(True)
+    for _ in range(max(10, min(args.steps, 50))):
+        e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
+    t_cold = e.timing()
+    e.set_option(H.OPT_L2_FLUSH_BYTES, 0)
+    e.enable_timing(True)
+    for _ in range(max(10, min(args.steps, 50))):
+        e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
+    t_warm = e.timing()
+    e.enable_timing(False)
+    info = e.launch_info()
+    peak, peak_src = _peaks()
+    bytes_per_launch = e.n_local * w.T * w.dyn.CONTROL_DIM * 4
+    achieved = bytes_per_launch / (t_cold["rollout_ms"] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "rollout_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_l2_flushed": t_cold["rollout_ms"],
+        "kernel_ms_l2_warm": t_warm["rollout_ms"],
+        "stage_ms_l2_warm": {k: t_warm[k] for k in ("noise_ms", "rollout_ms", "reduce_ms", "total_ms")},
+        "note": "K1 is bound by the T-step dependency chain (and FP32/MUFU work for NN dynamics), not by HBM: see DESIGN.md",
+    }
+
+    if rank == 0:
+        value = args.steps / (dev_ms * 1e-3)
+        e2e_value = args.steps / (e2e_ms * 1e-3)
+        h2d = (x0.nbytes + U.nbytes)
+        d2h = w.D * (w.T * w.dyn.CONTROL_DIM + 4) * 4
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ncores = os.cpu_count() or 1
+            hz, sample, _ = _cpu_solve_hz(w, ncores, 3, sample_N=None if w.N * w.T <= 4_000_000 else 8192)
+            cpu = {"value": hz, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "num_rollouts": w.N, "num_timesteps": w.T, "controller": w.controller,
+                       "parallelism": f"rollout-sharded dp{world}", "rollouts_per_gpu": e.n_local,
+                       "k1_launch": info,
+                       "l2": "noise buffer is regenerated on the device every step (K0 -> K1 through L2/HBM); no data "
+                             "is reused across steps; the roofline pass flushes L2 (256 MiB memset) between K0 and K1"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": args.steps * info["kernels_per_solve"],
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    e.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="autorally")
+    ap.add_argument("--rollouts", type=int, default=None)
+    ap.add_argument("--timesteps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

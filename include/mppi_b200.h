@@ -126,6 +126,12 @@ int mppib_comm_init(mppib_engine* e, const void* unique_id_128);
 int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num,
                 float* U_out, mppib_solve_stats* stats);
 
+/* Pipelined variant: mppib_solve_async enqueues the same work (x0 / U_in are captured into the kernel parameter bank at
+ * call time, so the host arrays may be reused immediately) and returns without waiting; mppib_solve_wait blocks until
+ * everything enqueued so far is done and returns the result of the LAST solve. mppib_solve == async + wait. */
+int mppib_solve_async(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num);
+int mppib_solve_wait(mppib_engine* e, float* U_out, mppib_solve_stats* stats);
+
 /* Kernel-level parity hooks (the reference tests kernels in isolation: tests/mppi_core/rollout_kernel_tests.cu). */
 /* mppib_set_noise: overwrite the raw N(0,1) buffer [N_local][T][C] from the host (tests with hand-made noise).
  * mppib_draw_noise: one generateSamples-equivalent draw into the buffer, advancing the RNG offset.
@@ -152,14 +158,24 @@ typedef struct mppib_timing
   float rollout_ms; /* K1 fused rollout */
   float reduce_ms;  /* K2 combine (+ collective) */
   float total_ms;   /* first launch to last kernel end, device time */
+  int samples;      /* synchronous solves averaged */
 } mppib_timing;
-/* Enable CUDA-event timestamps around each stage of subsequent solves (adds ~us; off by default). */
+/* Enable CUDA-event timestamps around each stage of subsequent solves (adds ~us; off by default); mppib_get_timing
+ * returns the averages over the synchronous solves since the last enable call. */
 int mppib_enable_timing(mppib_engine* e, int enable);
 int mppib_get_timing(mppib_engine* e, mppib_timing* out);
 /* Launch geometry actually used by K1 (for bench.py / DESIGN.md). */
 int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_bytes, int* uses_tma,
                           int* kernels_per_solve);
 int mppib_local_rollouts(mppib_engine* e, int* n_local, int* n_offset);
+
+/* Measurement options. MPPIB_OPT_L2_FLUSH_BYTES: if > 0, a buffer of that many bytes is overwritten between the noise
+ * draw and the rollout so K1 reads its tile from HBM instead of the L2 lines K0 just wrote (roofline measurements). */
+enum mppib_option
+{
+  MPPIB_OPT_L2_FLUSH_BYTES = 1
+};
+int mppib_set_option(mppib_engine* e, int option, long long value);
 
 const char* mppib_strerror(int status);
 const char* mppib_last_error(void); /* thread-local text of the last failure */

@@ -151,6 +151,12 @@ struct mppib_engine
   float* result_h = nullptr;     // mapped pinned host copy K2 writes directly
   float* result_h_dev = nullptr; // device alias of result_h
   float* weights_d = nullptr;    // lazily allocated for mppib_get_weights
+  unsigned char* l2_flush_d = nullptr;  // optional: buffer written between K0 and K1 to evict the noise from L2
+  size_t l2_flush_bytes = 0;
+  int pending = 0;               // solves enqueued and not yet waited for
+  // accumulated stage timings (timing mode)
+  double acc_ms[4] = { 0, 0, 0, 0 };
+  long acc_n = 0;
 
   CUtensorMap tmap{};
 
@@ -622,6 +628,7 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->gather_d);
   cudaFree(e->result_d);
   cudaFree(e->weights_d);
+  cudaFree(e->l2_flush_d);
   if (e->result_h)
     cudaFreeHost(e->result_h);
   for (int i = 0; i < 4; i++)
@@ -867,20 +874,16 @@ int mppib_reduce_only(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
   return MPPIB_OK;
 }
 
-int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num,
-                float* U_out, mppib_solve_stats* stats)
+static int enqueue_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride,
+                         int iteration_num)
 {
-  int rc = check_ready(e);
-  if (rc != MPPIB_OK)
-    return rc;
-  if (!x0 || !U_in || !U_out)
-    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
-  CUDA_TRY(cudaSetDevice(e->desc.device));
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[0], e->stream));
-  rc = draw_noise(*e);
+  int rc = draw_noise(*e);
   if (rc != MPPIB_OK)
     return rc;
+  if (e->l2_flush_d)
+    CUDA_TRY(cudaMemsetAsync(e->l2_flush_d, 0, e->l2_flush_bytes, e->stream));
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[1], e->stream));
   rc = e->launch_rollout(*e, x0, U_in, optimization_stride, iteration_num);
@@ -893,11 +896,92 @@ int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimiz
     return rc;
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[3], e->stream));
+  e->pending++;
+  return MPPIB_OK;
+}
+
+static int wait_solve(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
+{
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->pending = 0;
   e->timing_valid = e->timing;
+  if (e->timing)
+  {
+    float ms[4];
+    if (cudaEventElapsedTime(&ms[0], e->ev[0], e->ev[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms[1], e->ev[1], e->ev[2]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms[2], e->ev[2], e->ev[3]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms[3], e->ev[0], e->ev[3]) == cudaSuccess)
+    {
+      for (int i = 0; i < 4; i++)
+        e->acc_ms[i] += ms[i];
+      e->acc_n++;
+    }
+  }
   e->solved_once = true;
   read_result(*e, U_out, stats);
   return MPPIB_OK;
+}
+
+int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num,
+                float* U_out, mppib_solve_stats* stats)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !U_in || !U_out)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  rc = enqueue_solve(e, x0, U_in, optimization_stride, iteration_num);
+  if (rc != MPPIB_OK)
+    return rc;
+  return wait_solve(e, U_out, stats);
+}
+
+int mppib_solve_async(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !U_in)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  return enqueue_solve(e, x0, U_in, optimization_stride, iteration_num);
+}
+
+int mppib_solve_wait(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (e->pending == 0)
+    return fail(MPPIB_ERR_STATE, "no solve in flight");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  return wait_solve(e, U_out, stats);
+}
+
+int mppib_set_option(mppib_engine* e, int option, long long value)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  switch (option)
+  {
+    case MPPIB_OPT_L2_FLUSH_BYTES:
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      if (e->l2_flush_d)
+      {
+        cudaFree(e->l2_flush_d);
+        e->l2_flush_d = nullptr;
+        e->l2_flush_bytes = 0;
+      }
+      if (value > 0)
+      {
+        CUDA_TRY(cudaMalloc(&e->l2_flush_d, (size_t)value));
+        e->l2_flush_bytes = (size_t)value;
+      }
+      return MPPIB_OK;
+  }
+  return fail(MPPIB_ERR_INVALID_ARG, "unknown option %d", option);
 }
 
 int mppib_get_costs(mppib_engine* e, float* host_costs)
@@ -960,6 +1044,9 @@ int mppib_enable_timing(mppib_engine* e, int enable)
     return fail(MPPIB_ERR_INVALID_ARG, "null engine");
   e->timing = enable != 0;
   e->timing_valid = false;
+  for (int i = 0; i < 4; i++)
+    e->acc_ms[i] = 0.0;
+  e->acc_n = 0;
   return MPPIB_OK;
 }
 
@@ -967,12 +1054,14 @@ int mppib_get_timing(mppib_engine* e, mppib_timing* out)
 {
   if (!e || !out)
     return fail(MPPIB_ERR_INVALID_ARG, "null argument");
-  if (!e->timing_valid)
-    return fail(MPPIB_ERR_STATE, "timing not enabled or no solve since it was enabled");
-  CUDA_TRY(cudaEventElapsedTime(&out->noise_ms, e->ev[0], e->ev[1]));
-  CUDA_TRY(cudaEventElapsedTime(&out->rollout_ms, e->ev[1], e->ev[2]));
-  CUDA_TRY(cudaEventElapsedTime(&out->reduce_ms, e->ev[2], e->ev[3]));
-  CUDA_TRY(cudaEventElapsedTime(&out->total_ms, e->ev[0], e->ev[3]));
+  if (e->acc_n == 0)
+    return fail(MPPIB_ERR_STATE, "timing not enabled or no synchronous solve since it was enabled");
+  // averages over the synchronous solves since mppib_enable_timing(e, 1)
+  out->noise_ms = (float)(e->acc_ms[0] / e->acc_n);
+  out->rollout_ms = (float)(e->acc_ms[1] / e->acc_n);
+  out->reduce_ms = (float)(e->acc_ms[2] / e->acc_n);
+  out->total_ms = (float)(e->acc_ms[3] / e->acc_n);
+  out->samples = (int)e->acc_n;
   return MPPIB_OK;
 }
 

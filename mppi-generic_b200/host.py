@@ -29,6 +29,7 @@ COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC 
 SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
 BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API = 1, 2, 4
+OPT_L2_FLUSH_BYTES = 1
 AR_NN_NUM_PARAMS = 1412
 
 
@@ -107,13 +108,14 @@ class SolveStats(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("noise_ms", C.c_float), ("rollout_ms", C.c_float), ("reduce_ms", C.c_float),
-                ("total_ms", C.c_float)]
+                ("total_ms", C.c_float), ("samples", C.c_int)]
 
 
 # every symbol include/mppi_b200.h and include/mppi_b200/host_twins.h declare (tests check the .so exports them all)
 ABI_SYMBOLS = [
     "mppib_create", "mppib_destroy", "mppib_set_blob", "mppib_set_solver", "mppib_seed", "mppib_burn_draws",
-    "mppib_get_rng_offset", "mppib_comm_unique_id", "mppib_comm_init", "mppib_solve", "mppib_set_noise",
+    "mppib_get_rng_offset", "mppib_comm_unique_id", "mppib_comm_init", "mppib_solve", "mppib_solve_async",
+    "mppib_solve_wait", "mppib_set_option", "mppib_set_noise",
     "mppib_draw_noise", "mppib_rollout_only", "mppib_reduce_only", "mppib_get_costs", "mppib_get_noise",
     "mppib_get_samples", "mppib_get_weights", "mppib_enable_timing", "mppib_get_timing", "mppib_get_launch_info",
     "mppib_local_rollouts", "mppib_strerror", "mppib_last_error", "mppib_version",
@@ -144,6 +146,9 @@ def lib() -> C.CDLL:
     L.mppib_comm_unique_id.argtypes = [vp]
     L.mppib_comm_init.argtypes = [vp, vp]
     L.mppib_solve.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(SolveStats)]
+    L.mppib_solve_async.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    L.mppib_solve_wait.argtypes = [vp, vp, C.POINTER(SolveStats)]
+    L.mppib_set_option.argtypes = [vp, C.c_int, C.c_longlong]
     L.mppib_set_noise.argtypes = [vp, vp, C.c_size_t]
     L.mppib_draw_noise.argtypes = [vp]
     L.mppib_rollout_only.argtypes = [vp, vp, vp, C.c_int, C.c_int]
@@ -489,6 +494,18 @@ class Engine:
         _check(lib().mppib_solve(self._h, x0.ctypes.data, U_in.ctypes.data, optimization_stride, iteration_num,
                                  U_out.ctypes.data, stats))
 
+    def solve_async(self, x0: np.ndarray, U_in: np.ndarray, optimization_stride: int = 1, iteration_num: int = 0):
+        _check(lib().mppib_solve_async(self._h, x0.ctypes.data, U_in.ctypes.data, optimization_stride, iteration_num))
+
+    def solve_wait(self):
+        U_out = np.empty((self.D, self.T, self.Cdim), np.float32)
+        stats = (SolveStats * self.D)()
+        _check(lib().mppib_solve_wait(self._h, _ptr(U_out), stats))
+        return U_out, [(s.baseline, s.normalizer, s.sum_w2) for s in stats]
+
+    def set_option(self, option: int, value: int) -> None:
+        _check(lib().mppib_set_option(self._h, option, value))
+
     def set_noise(self, eps) -> None:
         eps = _f32(eps)
         _check(lib().mppib_set_noise(self._h, _ptr(eps), eps.size))
@@ -533,7 +550,8 @@ class Engine:
     def timing(self) -> dict:
         t = Timing()
         _check(lib().mppib_get_timing(self._h, C.byref(t)))
-        return {"noise_ms": t.noise_ms, "rollout_ms": t.rollout_ms, "reduce_ms": t.reduce_ms, "total_ms": t.total_ms}
+        return {"noise_ms": t.noise_ms, "rollout_ms": t.rollout_ms, "reduce_ms": t.reduce_ms, "total_ms": t.total_ms,
+                "samples": t.samples}
 
     def launch_info(self) -> dict:
         g, b, s, t, k = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
