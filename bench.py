@@ -184,7 +184,10 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = _workload(args)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the legacy default stream has handle 0, which the C-ABI reads as "engine-owned", and
+    # torch events would then not see the engine's work
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     flags = 0
     e = H.Engine(w.dyn, w.cost, w.sampler, w.N, w.T, w.D, device=local_rank, flags=flags,
                  stream=stream.cuda_stream, rank=rank, world_size=world)

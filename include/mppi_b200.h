@@ -167,6 +167,8 @@ int mppib_get_timing(mppib_engine* e, mppib_timing* out);
 /* Launch geometry actually used by K1 (for bench.py / DESIGN.md). */
 int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_bytes, int* uses_tma,
                           int* kernels_per_solve);
+/* 1 if the engine's own XORWOW kernel draws the noise, 0 if curandGenerateNormal does (sizes / flag); chunks = K. */
+int mppib_get_rng_info(mppib_engine* e, int* own_kernel, int* chunks, int* rounds_per_chunk);
 int mppib_local_rollouts(mppib_engine* e, int* n_local, int* n_offset);
 
 /* Measurement options. MPPIB_OPT_L2_FLUSH_BYTES: if > 0, a buffer of that many bytes is overwritten between the noise

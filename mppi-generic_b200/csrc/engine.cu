@@ -25,6 +25,7 @@
 
 #include "../../include/mppi_b200.h"
 #include "combine_kernel.cuh"
+#include "noise_xorwow.cuh"
 #include "plugins/costs.cuh"
 #include "plugins/dynamics.cuh"
 #include "rollout_kernel.cuh"
@@ -138,6 +139,13 @@ struct mppib_engine
   unsigned long long seed = 0;
   unsigned long long rng_offset = 0;  // absolute position (in normals) of the next GLOBAL draw
   bool rng_positioned = false;        // generator's internal position == what the next local draw needs
+  // own XORWOW draw (noise_xorwow.cuh): 4096 * xw_chunks persistent states
+  bool xw_enabled = false;  // sizes allow it and MPPIB_FLAG_CURAND_HOST_API not set
+  bool xw_dirty = true;     // states must be (re)initialised from (seed, rng_offset)
+  int xw_chunks = 0, xw_rounds_per_chunk = 0;
+  uint32_t xw_jump_d = 0;
+  uint32_t* xw_states_d = nullptr;
+  uint32_t* xw_tables_d = nullptr;
 
   // device buffers
   float* noise_alloc = nullptr;  // allocation incl. lead-in space for offset alignment
@@ -324,6 +332,25 @@ static int draw_noise(mppib_engine& e)
   const unsigned long long global_count = (unsigned long long)e.N * e.TC;
   const unsigned long long start = e.rng_offset + (unsigned long long)e.n_offset * e.TC;
   const size_t count = (size_t)e.n_local * e.TC;
+  if (e.xw_enabled && (e.rng_offset % 8192ULL) == 0)
+  {
+    const int nstates = e.xw_chunks * kXorwowStreams;
+    if (e.xw_dirty)
+    {
+      xorwow_init_kernel<<<(nstates + 127) / 128, 128, 0, e.stream>>>(e.seed, start / 8192ULL, e.xw_rounds_per_chunk,
+                                                                    e.xw_chunks, e.xw_states_d);
+      CUDA_TRY(cudaGetLastError());
+      e.xw_dirty = false;
+    }
+    xorwow_normal_kernel<<<(nstates + 255) / 256, 256, 0, e.stream>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
+                                                                     e.xw_rounds_per_chunk, e.xw_chunks,
+                                                                     reinterpret_cast<float2*>(e.eps_d));
+    CUDA_TRY(cudaGetLastError());
+    e.rng_offset += global_count;
+    e.rng_positioned = false;  // the library generator was not advanced
+    return MPPIB_OK;
+  }
+  e.xw_dirty = true;  // library path taken: our states no longer track the stream position
   if (e.desc.world_size == 1 && e.rng_positioned)
   {
     // generator already sits at `start`: plain continuation, exactly what the reference does call after call
@@ -576,6 +603,32 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   for (int i = 0; i < 4; i++)
     CUDA_TRY_B(cudaEventCreate(&e->ev[i]));
 
+  // own XORWOW draw: possible when this rank's slice is a whole number of 8192-normal rounds
+  if (!(desc->flags & MPPIB_FLAG_CURAND_HOST_API) && !getenv("MPPIB_CURAND_HOST_API") &&
+      (noise_floats % 8192) == 0 && (((size_t)e->n_offset * e->TC) % 8192) == 0 && (((size_t)e->N * e->TC) % 8192) == 0)
+  {
+    const int rounds_local = (int)(noise_floats / 8192);
+    const unsigned long long rounds_global = (unsigned long long)e->N * e->TC / 8192ULL;
+    int K = 1;
+    for (int cand = 1; cand <= 64 && cand <= rounds_local; cand++)
+      if (rounds_local % cand == 0 && (rounds_local / cand >= 4 || cand == 1))
+        K = cand;
+    e->xw_chunks = K;
+    e->xw_rounds_per_chunk = rounds_local / K;
+    const unsigned long long jump_draws = 2ULL * (rounds_global - (unsigned long long)e->xw_rounds_per_chunk);
+    std::vector<uint32_t> tables;
+    xorwow_nibble_tables(XorwowMatrix::power(jump_draws), tables);
+    e->xw_jump_d = (uint32_t)(kXorwowWeyl * (uint32_t)(jump_draws & 0xffffffffULL));
+    const size_t nstates = (size_t)K * kXorwowStreams;
+    CUDA_TRY_B(cudaMalloc(&e->xw_states_d, nstates * 6 * sizeof(uint32_t)));
+    CUDA_TRY_B(cudaMalloc(&e->xw_tables_d, tables.size() * sizeof(uint32_t)));
+    CUDA_TRY_B(cudaMemcpyAsync(e->xw_tables_d, tables.data(), tables.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               e->stream));
+    CUDA_TRY_B(cudaStreamSynchronize(e->stream));
+    e->xw_enabled = true;
+    e->xw_dirty = true;
+  }
+
   if (e->use_tma)
   {
     int rc = make_tensor_map(*e);
@@ -629,6 +682,8 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->result_d);
   cudaFree(e->weights_d);
   cudaFree(e->l2_flush_d);
+  cudaFree(e->xw_states_d);
+  cudaFree(e->xw_tables_d);
   if (e->result_h)
     cudaFreeHost(e->result_h);
   for (int i = 0; i < 4; i++)
@@ -764,6 +819,7 @@ int mppib_seed(mppib_engine* e, unsigned long long seed, unsigned long long offs
   CURAND_TRY(curandSetGeneratorOffset(e->gen, 0ULL));
   e->seed = seed;
   e->rng_offset = offset;
+  e->xw_dirty = true;
   // the generator sits at element 0; it is "positioned" only if that is where the next local draw starts
   e->rng_positioned = (offset == 0 && e->desc.world_size == 1);
   return MPPIB_OK;
@@ -784,6 +840,7 @@ int mppib_burn_draws(mppib_engine* e, int n)
   // skipping is free for a counter-positioned stream: just move the absolute offset
   e->rng_offset += (unsigned long long)n * e->N * e->TC;
   e->rng_positioned = false;
+  e->xw_dirty = true;
   return MPPIB_OK;
 }
 
@@ -971,6 +1028,8 @@ int mppib_set_option(mppib_engine* e, int option, long long value)
       if (e->l2_flush_d)
       {
         cudaFree(e->l2_flush_d);
+  cudaFree(e->xw_states_d);
+  cudaFree(e->xw_tables_d);
         e->l2_flush_d = nullptr;
         e->l2_flush_bytes = 0;
       }
@@ -1079,7 +1138,21 @@ int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_byte
   if (uses_tma)
     *uses_tma = e->use_tma ? 1 : 0;
   if (kernels_per_solve)
-    *kernels_per_solve = (e->desc.world_size > 1) ? 3 : 2;  // K1 + K2 (+ second K2); cuRAND's own launches not counted
+    *kernels_per_solve = ((e->desc.world_size > 1) ? 3 : 2) + (e->xw_enabled ? 1 : 0);  // [K0] + K1 + K2 (+ K2'); cuRAND's
+                                                                                         // own launches are not counted
+  return MPPIB_OK;
+}
+
+int mppib_get_rng_info(mppib_engine* e, int* own_kernel, int* chunks, int* rounds_per_chunk)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (own_kernel)
+    *own_kernel = e->xw_enabled ? 1 : 0;
+  if (chunks)
+    *chunks = e->xw_chunks;
+  if (rounds_per_chunk)
+    *rounds_per_chunk = e->xw_rounds_per_chunk;
   return MPPIB_OK;
 }
 

@@ -118,6 +118,7 @@ ABI_SYMBOLS = [
     "mppib_solve_wait", "mppib_set_option", "mppib_set_noise",
     "mppib_draw_noise", "mppib_rollout_only", "mppib_reduce_only", "mppib_get_costs", "mppib_get_noise",
     "mppib_get_samples", "mppib_get_weights", "mppib_enable_timing", "mppib_get_timing", "mppib_get_launch_info",
+    "mppib_get_rng_info",
     "mppib_local_rollouts", "mppib_strerror", "mppib_last_error", "mppib_version",
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
@@ -158,6 +159,7 @@ def lib() -> C.CDLL:
     L.mppib_enable_timing.argtypes = [vp, C.c_int]
     L.mppib_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.mppib_get_launch_info.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.mppib_get_rng_info.argtypes = [vp, ip, ip, ip]
     L.mppib_local_rollouts.argtypes = [vp, ip, ip]
     L.mppib_strerror.argtypes = [C.c_int]
     L.mppib_strerror.restype = C.c_char_p
@@ -553,6 +555,11 @@ class Engine:
         return {"noise_ms": t.noise_ms, "rollout_ms": t.rollout_ms, "reduce_ms": t.reduce_ms, "total_ms": t.total_ms,
                 "samples": t.samples}
 
+    def rng_info(self) -> dict:
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().mppib_get_rng_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"own_kernel": bool(a.value), "chunks": b.value, "rounds_per_chunk": c.value}
+
     def launch_info(self) -> dict:
         g, b, s, t, k = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(lib().mppib_get_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(t), C.byref(k)))
@@ -711,11 +718,18 @@ class TubeMPPIController(_Controller):
     def getNominalThreshold(self) -> float:
         return self.nominal_threshold_
 
-    def getNominalControlSeq(self) -> np.ndarray:
+    # tube_mppi_controller.cuh:49-63: the controller's "solution" is the NOMINAL system; the actual one has its own getters
+    def getControlSeq(self) -> np.ndarray:
         return self.nominal_control_trajectory_
 
-    def getNominalStateSeq(self) -> np.ndarray:
+    def getTargetStateSeq(self) -> np.ndarray:
         return self.nominal_state_trajectory_
+
+    def getActualControlSeq(self) -> np.ndarray:
+        return self.control_
+
+    def getActualStateSeq(self) -> np.ndarray:
+        return self.state_
 
     def _compute_state_trajectories(self, state: np.ndarray) -> None:
         # tube_mppi_controller.cu:345-350: actual from `state`, nominal from nominal_state_trajectory_.col(0)
