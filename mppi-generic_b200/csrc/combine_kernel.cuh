@@ -12,7 +12,8 @@
  * which is algebraically the reference's two-pass formula (w_n = expf(-(c_n-beta_b)/lambda) * s_b). The same kernel
  * merges the per-GPU records after the NCCL all-gather (records = ranks, normalize = 1).
  *
- * Launch: grid (ceil(TC/64), D), block 256 = 4 record-groups x 64 columns; block-wide warp-shuffle reductions.
+ * Launch: grid (ceil(TC/32), D), block 512 = 16 warps x 32 columns; block-wide warp-shuffle reductions, the rescale
+ * factors s_b staged once in shared memory, four record loads in flight per thread.
  * Output record layout == input record layout: [beta, eta, sum_w2, pad, V or U (TC floats)].
  */
 #pragma once
@@ -20,32 +21,38 @@
 
 namespace mppib
 {
-constexpr int kCombineCols = 64;
-constexpr int kCombineGroups = 4;
+constexpr int kCombineCols = 32;     // one warp-width of columns per block: 128-byte coalesced record reads
+constexpr int kCombineGroups = 16;   // 16 warps split the records
+constexpr int kCombineMaxRecords = 4096;
 
 __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
     combine_kernel(const float* __restrict__ records,  // [nrec][D][pstride]
                    int nrec, int D, int TC, int pstride, float lambda_inv, int normalize,
-                   float* __restrict__ out,    // [D][pstride] (device or mapped host)
+                   float* __restrict__ out,    // [D][pstride] (device)
                    float* __restrict__ out2)   // optional second copy (mapped host result), may be nullptr
 {
-  __shared__ float red_f[8];
-  __shared__ float beta_sh;
-  __shared__ double eta_sh[kCombineGroups], w2_sh[kCombineGroups];
+  __shared__ float scale_sh[kCombineMaxRecords];  // s_b = expf(-(beta_b - beta)/lambda)
+  __shared__ float red_f[kCombineGroups];
+  __shared__ double red_d[2][kCombineGroups];
   __shared__ float acc_sh[kCombineGroups][kCombineCols];
+  __shared__ float beta_sh, eta_sh;
+  __shared__ double w2_sh;
 
   const int d = blockIdx.y;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int group = tid / kCombineCols, cl = tid % kCombineCols;
-  const int col = blockIdx.x * kCombineCols + cl;
+  const int col = blockIdx.x * kCombineCols + lane;
   const float* rec = records + (size_t)d * pstride;
   const size_t rstride = (size_t)D * pstride;
 
-  // global baseline: first-minimum value == plain min (mppi_common.cu:858-900)
+  // 1. global baseline: first-minimum VALUE == plain min (mppi_common.cu:858-900)
   float m = INFINITY;
   for (int b = tid; b < nrec; b += blockDim.x)
-    m = fminf(m, rec[b * rstride + 0]);
+  {
+    const float bb = rec[b * rstride];
+    scale_sh[b] = bb;  // stash beta_b
+    m = fminf(m, bb);
+  }
   m = warp_min(m);
   if (lane == 0)
     red_f[warp] = m;
@@ -53,43 +60,72 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
   if (tid == 0)
   {
     float v = red_f[0];
-    for (int i = 1; i < (int)(blockDim.x >> 5); i++)
+    for (int i = 1; i < kCombineGroups; i++)
       v = fminf(v, red_f[i]);
     beta_sh = v;
   }
   __syncthreads();
   const float beta = beta_sh;
 
-  float acc = 0.0f;
+  // 2. per-record rescale factors, normaliser (double accumulate, mppi_common.cu:1055-1063) and sum of squares
   double eta = 0.0, w2 = 0.0;
-  for (int b = group; b < nrec; b += kCombineGroups)
+  for (int b = tid; b < nrec; b += blockDim.x)
   {
-    const float* r = rec + b * rstride;
-    const float s = expf(-lambda_inv * (r[0] - beta));
-    eta += (double)s * (double)r[1];
-    w2 += (double)s * (double)s * (double)r[2];
-    if (col < TC)
-      acc = fmaf(s, r[kPartialHeader + col], acc);
+    const float s = expf(-lambda_inv * (scale_sh[b] - beta));
+    scale_sh[b] = s;
+    eta += (double)s * (double)rec[b * rstride + 1];
+    w2 += (double)s * (double)s * (double)rec[b * rstride + 2];
   }
-  acc_sh[group][cl] = acc;
-  if (cl == 0)
+  eta = warp_sum(eta);
+  w2 = warp_sum(w2);
+  if (lane == 0)
   {
-    eta_sh[group] = eta;
-    w2_sh[group] = w2;
+    red_d[0][warp] = eta;
+    red_d[1][warp] = w2;
   }
   __syncthreads();
-  if (group == 0)
+  if (tid == 0)
   {
     double e = 0.0, q = 0.0;
+    for (int i = 0; i < kCombineGroups; i++)
+    {
+      e += red_d[0][i];
+      q += red_d[1][i];
+    }
+    eta_sh = (float)e;  // narrowed to float like the reference's return value
+    w2_sh = q;
+  }
+  __syncthreads();
+
+  // 3. column sums: warp g takes records g, g+16, ... ; 4 independent loads in flight per thread
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  if (col < TC)
+  {
+    const float* colp = rec + kPartialHeader + col;
+    int b = warp;
+    for (; b + 3 * kCombineGroups < nrec; b += 4 * kCombineGroups)
+    {
+      const float v0 = colp[(size_t)b * rstride];
+      const float v1 = colp[(size_t)(b + kCombineGroups) * rstride];
+      const float v2 = colp[(size_t)(b + 2 * kCombineGroups) * rstride];
+      const float v3 = colp[(size_t)(b + 3 * kCombineGroups) * rstride];
+      a0 = fmaf(scale_sh[b], v0, a0);
+      a1 = fmaf(scale_sh[b + kCombineGroups], v1, a1);
+      a2 = fmaf(scale_sh[b + 2 * kCombineGroups], v2, a2);
+      a3 = fmaf(scale_sh[b + 3 * kCombineGroups], v3, a3);
+    }
+    for (; b < nrec; b += kCombineGroups)
+      a0 = fmaf(scale_sh[b], colp[(size_t)b * rstride], a0);
+  }
+  acc_sh[warp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0)
+  {
     float a = 0.0f;
 #pragma unroll
     for (int gq = 0; gq < kCombineGroups; gq++)
-    {
-      e += eta_sh[gq];
-      q += w2_sh[gq];
-      a += acc_sh[gq][cl];
-    }
-    const float eta_f = (float)e;  // mppi_common.cu:1055-1063: double accumulate, narrowed to float
+      a += acc_sh[gq][lane];
+    const float eta_f = eta_sh;
     float* o = out + (size_t)d * pstride;
     float* o2 = out2 ? out2 + (size_t)d * pstride : nullptr;
     if (col < TC)
@@ -99,17 +135,17 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
       if (o2)
         o2[kPartialHeader + col] = v;
     }
-    if (blockIdx.x == 0 && cl == 0)
+    if (blockIdx.x == 0 && lane == 0)
     {
       o[0] = beta;
       o[1] = eta_f;
-      o[2] = (float)q;
+      o[2] = (float)w2_sh;
       o[3] = 0.0f;
       if (o2)
       {
         o2[0] = beta;
         o2[1] = eta_f;
-        o2[2] = (float)q;
+        o2[2] = (float)w2_sh;
         o2[3] = 0.0f;
       }
     }

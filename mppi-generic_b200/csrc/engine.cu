@@ -180,6 +180,7 @@ struct mppib_engine
   int (*launch_rollout)(mppib_engine&, const float* x0, const float* U_in, int opt_stride, int iter) = nullptr;
   size_t dyn_param_bytes = 0, cost_param_bytes = 0;
   int dyn_shared_floats = 0;
+  int (*cost_shared_floats)(int) = nullptr;
   int (*prepare)(mppib_engine&) = nullptr;  // sets func attributes
   bool solved_once = false;
 };
@@ -214,15 +215,23 @@ struct Pair
 {
   using Args = RolloutArgs<DYN, COST>;
 
+  static int cost_shared(int T)
+  {
+    return COST::sharedFloats(T);
+  }
+
+  template <int DD, bool WB>
+  static int prepare_one(mppib_engine& e)
+  {
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, DD, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)e.smem_bytes));
+    return MPPIB_OK;
+  }
   static int prepare(mppib_engine& e)
   {
     if (e.D == 1)
-      CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)e.smem_bytes));
-    else
-      CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)e.smem_bytes));
-    return MPPIB_OK;
+      return e.writeback ? prepare_one<1, true>(e) : prepare_one<1, false>(e);
+    return e.writeback ? prepare_one<2, true>(e) : prepare_one<2, false>(e);
   }
 
   static int launch(mppib_engine& e, const float* x0, const float* U_in, int opt_stride, int iter)
@@ -262,9 +271,19 @@ struct Pair
     memcpy(a.x0, x0, sizeof(float) * e.D * e.S);
     memcpy(a.means, U_in, sizeof(float) * e.D * e.TC);
     if (e.D == 1)
-      rollout_kernel<DYN, COST, 1><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+    {
+      if (e.writeback)
+        rollout_kernel<DYN, COST, 1, true><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+      else
+        rollout_kernel<DYN, COST, 1, false><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+    }
     else
-      rollout_kernel<DYN, COST, 2><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+    {
+      if (e.writeback)
+        rollout_kernel<DYN, COST, 2, true><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+      else
+        rollout_kernel<DYN, COST, 2, false><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+    }
     CUDA_TRY(cudaGetLastError());
     return MPPIB_OK;
   }
@@ -276,6 +295,8 @@ struct PairEntry
   int S, C, O;
   size_t dyn_bytes, cost_bytes;
   int dyn_shared_floats;
+  int max_block_threads;
+  int (*cost_shared_floats)(int);
   int (*launch)(mppib_engine&, const float*, const float*, int, int);
   int (*prepare)(mppib_engine&);
 };
@@ -290,6 +311,8 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     sizeof(typename DYN::Params),
                     sizeof(typename COST::Params),
                     DYN::SHARED_FLOATS,
+                    DYN::MAX_BLOCK_THREADS,
+                    &Pair<DYN, COST>::cost_shared,
                     &Pair<DYN, COST>::launch,
                     &Pair<DYN, COST>::prepare };
 }
@@ -519,6 +542,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->dyn_param_bytes = entry->dyn_bytes;
   e->cost_param_bytes = entry->cost_bytes;
   e->dyn_shared_floats = entry->dyn_shared_floats;
+  e->cost_shared_floats = entry->cost_shared_floats;
   e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
 
   auto bail = [&](int rc) {
@@ -545,11 +569,14 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     bx = atoi(s);
   if (bx < 32 || bx > 256 || (bx % 32) != 0)
     bx = 64;
+  if (bx > entry->max_block_threads)
+    bx = entry->max_block_threads;
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
   for (;;)
   {
-    e->smem_bytes = rollout_smem_layout(bx, e->nchunks, e->D, e->TC, e->dyn_shared_floats).total;
+    e->smem_bytes =
+        rollout_smem_layout(bx, e->nchunks, e->D, e->TC, e->dyn_shared_floats, e->cost_shared_floats(e->T)).total;
     if ((int)e->smem_bytes <= max_smem || bx == 32)
       break;
     bx /= 2;
@@ -559,6 +586,9 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
                      max_smem));
   e->bx = bx;
   e->grid = (e->n_local + bx - 1) / bx;
+  if (e->grid > kCombineMaxRecords)
+    return bail(fail(MPPIB_ERR_UNSUPPORTED, "%d rollout blocks exceed the combine kernel's %d records; raise MPPIB_BX",
+                     e->grid, kCombineMaxRecords));
   e->pstride = ((kPartialHeader + e->TC + 3) / 4) * 4;
   e->use_tma = !(desc->flags & MPPIB_FLAG_NO_TMA) && (e->TC % 4 == 0) && !getenv("MPPIB_NO_TMA");
 

@@ -19,7 +19,13 @@ struct Cost
   struct Aux
   {
   };
-  __device__ static __forceinline__ void initializeCosts(const Params&, const Aux&, const float* /*y*/, const float* /*u*/)
+  // per-block shared scratch ("theta_c" in the reference, cost.cuh:186-189) as a function of the horizon
+  __host__ __device__ static constexpr int sharedFloats(int /*T*/)
+  {
+    return 0;
+  }
+  // block-cooperative setup of theta_c (Cost::initializeCosts, cost.cuh:186-189)
+  __device__ static __forceinline__ void initializeCosts(const Params&, const Aux&, float* /*theta_c*/, int /*T*/)
   {
   }
   __device__ static __forceinline__ float computeControlCost(const Params&, const float* /*u*/, int /*t*/)
@@ -28,18 +34,27 @@ struct Cost
   }
   // cost.cu:40-53
   template <class AUX>
-  __device__ static __forceinline__ float computeRunningCost(const Params& p, const AUX& aux, const float* y,
-                                                             const float* u, int t, int* crash)
+  __device__ static __forceinline__ float computeRunningCost(const Params& p, const AUX& aux, const float* theta_c,
+                                                             const float* y, const float* u, int t, int* crash)
   {
-    return CLASS_T::computeStateCost(p, aux, y, t, crash) + CLASS_T::computeControlCost(p, u, t);
+    return CLASS_T::computeStateCost(p, aux, theta_c, y, t, crash) + CLASS_T::computeControlCost(p, u, t);
   }
 };
+
+// powf(discount, t) is the same number for every sample of a block: it is evaluated once per time step into theta_c
+// (identical function, identical arguments => identical bits to the reference's per-sample powf call).
+template <class PARAMS_T>
+__device__ __forceinline__ void fill_discount_table(const PARAMS_T& p, float* theta_c, int T)
+{
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    theta_c[t] = powf(p.discount, t);
+}
 
 // cost_functions/cartpole/cartpole_quadratic_cost.cu:20-43
 struct CartpoleQuadraticCost : public Cost<CartpoleQuadraticCost, mppib_cartpole_cost_params>
 {
-  __device__ static __forceinline__ float computeStateCost(const Params& params_, const Aux&, const float* state, int,
-                                                           int*)
+  __device__ static __forceinline__ float computeStateCost(const Params& params_, const Aux&, const float*,
+                                                           const float* state, int, int*)
   {
     return (state[0] - params_.desired_terminal_state[0]) * (state[0] - params_.desired_terminal_state[0]) *
                params_.cart_position_coeff +
@@ -52,15 +67,23 @@ struct CartpoleQuadraticCost : public Cost<CartpoleQuadraticCost, mppib_cartpole
   }
   __device__ static __forceinline__ float terminalCost(const Params& params_, const Aux& a, const float* state)
   {
-    return computeStateCost(params_, a, state, 0, nullptr) * params_.terminal_cost_coeff;
+    return computeStateCost(params_, a, nullptr, state, 0, nullptr) * params_.terminal_cost_coeff;
   }
 };
 
 // cost_functions/double_integrator/double_integrator_circle_cost.cu:8-32
 struct DoubleIntegratorCircleCost : public Cost<DoubleIntegratorCircleCost, mppib_di_circle_cost_params>
 {
-  __device__ static __forceinline__ float computeStateCost(const Params& params_, const Aux&, const float* s,
-                                                           int timestep, int*)
+  __host__ __device__ static constexpr int sharedFloats(int T)
+  {
+    return T;
+  }
+  __device__ static __forceinline__ void initializeCosts(const Params& p, const Aux&, float* theta_c, int T)
+  {
+    fill_discount_table(p, theta_c, T);
+  }
+  __device__ static __forceinline__ float computeStateCost(const Params& params_, const Aux&, const float* theta_c,
+                                                           const float* s, int timestep, int*)
   {
     float radial_position = s[0] * s[0] + s[1] * s[1];
     float current_velocity = sqrtf(s[2] * s[2] + s[3] * s[3]);
@@ -68,7 +91,7 @@ struct DoubleIntegratorCircleCost : public Cost<DoubleIntegratorCircleCost, mppi
     float cost = 0;
     if ((radial_position < params_.inner_path_radius2) || (radial_position > params_.outer_path_radius2))
     {
-      cost += powf(params_.discount, timestep) * params_.crash_cost;
+      cost += theta_c[timestep] * params_.crash_cost;  // powf(discount, timestep)
     }
     cost += params_.velocity_cost * fabsf(current_velocity - params_.velocity_desired);
     cost += params_.velocity_cost * fabsf(current_angular_momentum - params_.angular_momentum_desired);
@@ -88,8 +111,13 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
   {
     cudaTextureObject_t costmap_tex;  // float4 texels, point filter, clamp, normalised coords (ar_standard_cost.cu:160-171)
   };
-  __device__ static __forceinline__ void initializeCosts(const Params&, const Aux&, const float*, const float*)
+  __host__ __device__ static constexpr int sharedFloats(int T)
   {
+    return T;
+  }
+  __device__ static __forceinline__ void initializeCosts(const Params& p, const Aux&, float* theta_c, int T)
+  {
+    fill_discount_table(p, theta_c, T);
   }
   // ar_standard_cost.cu:206-243 (device branch)
   __device__ static __forceinline__ float4 queryTextureTransformed(const Params& p, const Aux& aux, float x, float y)
@@ -117,7 +145,7 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
     if (fabsf(s[4]) >= 0.001f)
     {
       float slip = -atanf(s[5] / fabsf(s[4]));
-      stabilizing_cost = p.slip_coeff * powf(slip, 2);
+      stabilizing_cost = p.slip_coeff * (slip * slip);  // powf(slip, 2) in the reference: <= 2 ulp apart
       if (fabsf(slip) > p.max_slip_ang)
       {
         stabilizing_cost += p.crash_coeff;
@@ -154,13 +182,13 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
       crash[0] = 1;
     return track_cost;
   }
-  __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux& aux, const float* s,
-                                                           int timestep, int* crash_status)
+  __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux& aux, const float* theta_c,
+                                                           const float* s, int timestep, int* crash_status)
   {
     float track_cost = getTrackCost(p, aux, s, crash_status);
     float speed_cost = getSpeedCost(p, s);
     float stabilizing_cost = getStabilizingCost(p, s, crash_status);
-    float crash_cost = powf(p.discount, timestep) * getCrashCost(p, crash_status);
+    float crash_cost = theta_c[timestep] * getCrashCost(p, crash_status);  // powf(discount, timestep)
     float cost = speed_cost + crash_cost + track_cost + stabilizing_cost;
     if (cost > MAX_COST_VALUE || isnan(cost))
       cost = MAX_COST_VALUE;

@@ -49,6 +49,8 @@ struct Dynamics
   static constexpr int CONTROL_DIM = C;
   static constexpr int OUTPUT_DIM = O;
   static constexpr int SHARED_FLOATS = 0;  // SHARED_MEM_REQUEST_GRD_BYTES / 4
+  static constexpr int MAX_BLOCK_THREADS = 256;  // __launch_bounds__ of the rollout kernel for this model
+  static constexpr bool UNROLL_STEPS = true;     // unroll the 4/C steps that share one 16-byte noise group
   struct Aux
   {
   };
@@ -115,13 +117,13 @@ struct CartpoleDynamics : public Dynamics<CartpoleDynamics, mppib_cartpole_dyn_p
     float l_p = p.pole_length;
     const float gravity_ = p.gravity;
 
+    // cartpole_dynamics.cu:100-106 with the two reciprocals taken by rcp_nr (denominators >= m_c > 0)
+    const float denom = m_c + m_p * MPPIB_SQ(sin_theta);
     state_der[0] = state[1];
-    state_der[1] = 1.0f / (m_c + m_p * MPPIB_SQ(sin_theta)) *
-                   (force + m_p * sin_theta * (l_p * MPPIB_SQ(theta_dot) + gravity_ * cos_theta));
+    state_der[1] = rcp_nr(denom) * (force + m_p * sin_theta * (l_p * MPPIB_SQ(theta_dot) + gravity_ * cos_theta));
     state_der[2] = theta_dot;
-    state_der[3] = 1.0f / (l_p * (m_c + m_p * MPPIB_SQ(sin_theta))) *
-                   (-force * cos_theta - m_p * l_p * MPPIB_SQ(theta_dot) * cos_theta * sin_theta -
-                    (m_c + m_p) * gravity_ * sin_theta);
+    state_der[3] = rcp_nr(l_p * denom) * (-force * cos_theta - m_p * l_p * MPPIB_SQ(theta_dot) * cos_theta * sin_theta -
+                                          (m_c + m_p) * gravity_ * sin_theta);
   }
 };
 
@@ -140,21 +142,36 @@ struct DoubleIntegratorDynamics : public Dynamics<DoubleIntegratorDynamics, mppi
 
 // ---- Autorally NeuralNetModel<7,2,3>: dynamics/autorally/ar_nn_model.cu:123-160 + FNNHelper::forward
 //      (utils/nn_helpers/fnn_helper.cu:419-484) -------------------------------------------------------------------
-// theta_s layout (ours): each layer's W rows padded to a multiple of 4 inputs so a row is read with broadcast LDS.128
-// (all 32 lanes of a warp read the same weight at the same time — one wavefront), then the layer's biases:
-//   L1: W[32][8] (cols 6,7 zero) | b[32]   L2: W[32][32] | b[32]   L3: W[4][32] | b[4]
+// One thread = one sample; the 6-32-32-4 forward pass is 1344 FMAs per step, issued as packed FP32x2 FMAs (FFMA2,
+// sm_100's full-rate FP32 path): the two halves of every FFMA2 are two adjacent OUTPUT neurons, so the accumulation over
+// the inputs k runs in the reference's order (k ascending, bias added last, fnn_helper.cu:463-472) and each neuron's sum
+// is bit-identical to a scalar FFMA chain. Weights sit in shared memory TRANSPOSED ([in][out]) so one broadcast LDS.128
+// (all lanes read the same address: one wavefront) feeds two FFMA2.
+//   theta_s: WT1[6][32] | b1[32] | WT2[32][32] | b2[32] | WT3[32][4] | b3[4]      (1412 floats, like the reference)
+__device__ __forceinline__ float tanh_fast(float x)
+{
+  // tanh(x) = 1 - 2 / (exp(2x) + 1) with ex2.approx / rcp.approx: |abs error| < 2e-7 over the whole range (the
+  // reference's tanhf, activation_functions.cuh:15-26, is ~1 ulp; its own FNN test bound is 1e-4, fnn_helper_test.cu:546)
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
 struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>
 {
   static constexpr int DYNAMICS_DIM = 4;  // S_DIM - K_DIM
-  static constexpr int L1_W = 0, L1_B = L1_W + 32 * 8, L2_W = L1_B + 32, L2_B = L2_W + 32 * 32, L3_W = L2_B + 32,
-                       L3_B = L3_W + 4 * 32;
-  static constexpr int SHARED_FLOATS = L3_B + 4;  // 1476
+  static constexpr int L1_W = 0, L1_B = L1_W + 6 * 32, L2_W = L1_B + 32, L2_B = L2_W + 32 * 32, L3_W = L2_B + 32,
+                       L3_B = L3_W + 32 * 4;
+  static constexpr int SHARED_FLOATS = L3_B + 4;  // 1412
+  static constexpr int MAX_BLOCK_THREADS = 128;   // lets ptxas use up to 255 registers: the forward pass is register-tiled
+  static constexpr bool UNROLL_STEPS = false;     // one copy of the 1344-FMA step body
   struct Aux
   {
     const float* theta_d;  // reference packed layout, MPPIB_AR_NN_NUM_PARAMS floats (fnn_helper.cu:176-183)
   };
 
-  // FNNHelper::initialize (fnn_helper.cu:385-416): block-cooperative global -> shared copy of the weights.
+  // FNNHelper::initialize (fnn_helper.cu:385-416): block-cooperative global -> shared copy, transposing W on the way.
   __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s,
                                                             const float* x, float* y)
   {
@@ -163,20 +180,26 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
     {
       float v;
       if (i < L1_B)
-      {  // W1[j][k], k padded 6 -> 8
-        const int j = i >> 3, k = i & 7;
-        v = k < 6 ? g[j * 6 + k] : 0.0f;
+      {  // WT1[k][j] = W1[j][k]
+        const int k = i >> 5, j = i & 31;
+        v = g[j * 6 + k];
       }
       else if (i < L2_W)
         v = g[192 + (i - L1_B)];
       else if (i < L2_B)
-        v = g[224 + (i - L2_W)];
+      {
+        const int q = i - L2_W, k = q >> 5, j = q & 31;
+        v = g[224 + j * 32 + k];
+      }
       else if (i < L3_W)
-        v = g[224 + 1024 + (i - L2_B)];
+        v = g[1248 + (i - L2_B)];
       else if (i < L3_B)
-        v = g[224 + 1024 + 32 + (i - L3_W)];
+      {
+        const int q = i - L3_W, k = q >> 2, j = q & 3;
+        v = g[1280 + j * 32 + k];
+      }
       else
-        v = g[224 + 1024 + 32 + 128 + (i - L3_B)];
+        v = g[1408 + (i - L3_B)];
       theta_s[i] = v;
     }
 #pragma unroll
@@ -184,51 +207,61 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
       y[i] = x[i];
   }
 
-  // ar_nn_model.cu:123-128
+  // ar_nn_model.cu:123-128 (cosf / sinf, not the fast intrinsics, in the reference's device code)
   __device__ static __forceinline__ void computeKinematics(const Params&, const float* state, float* state_der)
   {
-    state_der[0] = cosf(state[2]) * state[4] - sinf(state[2]) * state[5];
-    state_der[1] = sinf(state[2]) * state[4] + cosf(state[2]) * state[5];
+    float sn, cs;
+    sincosf(state[2], &sn, &cs);
+    state_der[0] = cs * state[4] - sn * state[5];
+    state_der[1] = sn * state[4] + cs * state[5];
     state_der[2] = -state[6];
   }
 
-  template <int IN4 /*inputs/4*/, int OUT, bool TANH>
-  __device__ static __forceinline__ void layer(const float* __restrict__ W, const float* __restrict__ b,
+  template <int IN, int OUT, bool TANH>
+  __device__ static __forceinline__ void layer(const float* __restrict__ WT, const float* __restrict__ b,
                                                const float* in, float* out)
   {
+    float2 acc[OUT / 2];
 #pragma unroll
-    for (int j = 0; j < OUT; j++)
+    for (int j = 0; j < OUT / 2; j++)
+      acc[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < IN; k++)
     {
-      float tmp = 0.0f;
+      const float2 xk = make_float2(in[k], in[k]);
 #pragma unroll
-      for (int k4 = 0; k4 < IN4; k4++)
+      for (int j4 = 0; j4 < OUT / 4; j4++)
       {
-        const float4 w = *reinterpret_cast<const float4*>(W + j * IN4 * 4 + k4 * 4);
-        // same k order as the reference's inner loop (fnn_helper.cu:466-470)
-        tmp += w.x * in[k4 * 4 + 0];
-        tmp += w.y * in[k4 * 4 + 1];
-        tmp += w.z * in[k4 * 4 + 2];
-        tmp += w.w * in[k4 * 4 + 3];
+        const float4 w = *reinterpret_cast<const float4*>(WT + k * OUT + 4 * j4);
+        acc[2 * j4] = __ffma2_rn(make_float2(w.x, w.y), xk, acc[2 * j4]);
+        acc[2 * j4 + 1] = __ffma2_rn(make_float2(w.z, w.w), xk, acc[2 * j4 + 1]);
       }
-      tmp += b[j];
-      out[j] = TANH ? tanhf(tmp) : tmp;
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < OUT / 4; j4++)
+    {
+      const float4 bb = *reinterpret_cast<const float4*>(b + 4 * j4);
+      const float t0 = acc[2 * j4].x + bb.x, t1 = acc[2 * j4].y + bb.y, t2 = acc[2 * j4 + 1].x + bb.z,
+                  t3 = acc[2 * j4 + 1].y + bb.w;
+      out[4 * j4 + 0] = TANH ? tanh_fast(t0) : t0;
+      out[4 * j4 + 1] = TANH ? tanh_fast(t1) : t1;
+      out[4 * j4 + 2] = TANH ? tanh_fast(t2) : t2;
+      out[4 * j4 + 3] = TANH ? tanh_fast(t3) : t3;
     }
   }
 
   __device__ static __forceinline__ void computeDynamics(const Params&, const float* theta_s, const float* state,
                                                          const float* control, float* state_der)
   {
-    float a0[8], a1[32], a2[32], a3[4];
+    float a0[6], a1[32], a2[32], a3[4];
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       a0[i] = state[i + (7 - DYNAMICS_DIM)];
     a0[4] = control[0];
     a0[5] = control[1];
-    a0[6] = 0.0f;
-    a0[7] = 0.0f;
-    layer<2, 32, true>(theta_s + L1_W, theta_s + L1_B, a0, a1);
-    layer<8, 32, true>(theta_s + L2_W, theta_s + L2_B, a1, a2);
-    layer<8, 4, false>(theta_s + L3_W, theta_s + L3_B, a2, a3);
+    layer<6, 32, true>(theta_s + L1_W, theta_s + L1_B, a0, a1);
+    layer<32, 32, true>(theta_s + L2_W, theta_s + L2_B, a1, a2);
+    layer<32, 4, false>(theta_s + L3_W, theta_s + L3_B, a2, a3);
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       state_der[i + (7 - DYNAMICS_DIM)] = a3[i];

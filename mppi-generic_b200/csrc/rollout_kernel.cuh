@@ -78,28 +78,35 @@ __device__ __forceinline__ float sample_control(float mean, float sd, float eps,
   return fmaf(sd, eps, mean);  // nvcc contracts the reference's `mean + std_dev * eps` to the same FFMA
 }
 
-// gaussian.cu:481-569 (device formula)
+// element i (0..3) of a 16-byte group without forcing it into local memory when i is not a compile-time constant
+__device__ __forceinline__ float group_elem(const float4& v, int i)
+{
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// gaussian.cu:481-569 (device formula): 0.5*lambda*(1-alpha) * sum_i k_i * mean_i * (mean_i - 2 u_i) / sigma_i^2, mean = 0
+// for the pure-noise tail. k_i / sigma_i^2 is loop-invariant and hoisted (lr_scale), which moves one rounding.
 template <int C>
-__device__ __forceinline__ float likelihood_ratio_cost(const SamplerArgs& sp, int d, const float* mean_t, const float* u,
-                                                       bool pure_noise, float lambda, float alpha)
+__device__ __forceinline__ float likelihood_ratio_cost(const float* lr_scale, const float* mean_t, const float* u,
+                                                       bool pure_noise, float half_lambda_1ma)
 {
   float cost = 0.0f;
 #pragma unroll
   for (int i = 0; i < C; i++)
   {
     const float mean_i = pure_noise ? 0.0f : mean_t[i];
-    const float sd = sp.std_dev[d][i];
-    cost += sp.control_cost_coeff[i] * mean_i * (mean_i - 2.0f * u[i]) / (sd * sd);
+    cost += lr_scale[i] * mean_i * (mean_i - 2.0f * u[i]);
   }
-  return 0.5f * lambda * (1.0f - alpha) * cost;
+  return half_lambda_1ma * cost;
 }
 
 // shared-memory carve-up (bytes); the tile base is rounded up to 1024 B inside the kernel (SWIZZLE_128B atom)
 struct RolloutSmem
 {
-  uint32_t tile, means, theta, weights, scratch, bars, total;
+  uint32_t tile, means, theta, theta_c, weights, scratch, bars, total;
 };
-__host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, int D, int TC, int dyn_shared_floats)
+__host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, int D, int TC, int dyn_shared_floats,
+                                                           int cost_shared_floats)
 {
   RolloutSmem s;
   uint32_t off = 0;
@@ -109,6 +116,8 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, 
   off += ((uint32_t)(D * TC + 3) / 4) * 16;
   s.theta = off;
   off += ((uint32_t)(dyn_shared_floats + 3) / 4) * 16;
+  s.theta_c = off;
+  off += ((uint32_t)(cost_shared_floats + 3) / 4) * 16;
   s.weights = off;
   off += ((uint32_t)(D * bx + 3) / 4) * 16;
   s.scratch = off;
@@ -119,8 +128,8 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, 
   return s;
 }
 
-template <class DYN, class COST, int D>
-__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
+template <class DYN, class COST, int D, bool WRITEBACK>
+__global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
                                                       const __grid_constant__ CUtensorMap tmap)
 {
   constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
@@ -135,10 +144,11 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   const int T = args.T;
   const int TC = T * C;
   const int nchunks = args.nchunks;
-  const RolloutSmem L = rollout_smem_layout(bx, nchunks, D, TC, DYN::SHARED_FLOATS);
+  const RolloutSmem L = rollout_smem_layout(bx, nchunks, D, TC, DYN::SHARED_FLOATS, COST::sharedFloats(T));
   unsigned char* tile = smem + L.tile;
   float* means_s = reinterpret_cast<float*>(smem + L.means);
   float* theta_s = reinterpret_cast<float*>(smem + L.theta);
+  float* theta_c = reinterpret_cast<float*>(smem + L.theta_c);
   float* w_s = reinterpret_cast<float*>(smem + L.weights);
   float* red_s = reinterpret_cast<float*>(smem + L.scratch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -206,17 +216,31 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     running_cost[d] = 0.0f;
     crash_status[d] = 0;
   }
-  // initializeDynamics fills theta_s cooperatively (FNNHelper::initialize) and seeds y; initializeCosts is a no-op
-  // for every in-tree cost (mppi_common.cu:94-96)
+  // initializeDynamics fills theta_s cooperatively (FNNHelper::initialize) and seeds y; initializeCosts fills theta_c
+  // (mppi_common.cu:94-96)
 #pragma unroll
   for (int d = 0; d < D; d++)
   {
     DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, x[d], y[d]);
   }
+  COST::initializeCosts(args.cost, args.cost_aux, theta_c, T);
   __syncthreads();
 
   const bool pure_noise = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
   const bool zero_noise_sample = (n_glob == 0);                             // gaussian.cu:101
+
+  // likelihood-ratio term: skipped altogether when every control_cost_coeff is zero (the sampler's default)
+  float lr_scale[D][C];
+  bool lr_on = false;
+#pragma unroll
+  for (int d = 0; d < D; d++)
+#pragma unroll
+    for (int c = 0; c < C; c++)
+    {
+      lr_scale[d][c] = args.samp.control_cost_coeff[c] / (args.samp.std_dev[d][c] * args.samp.std_dev[d][c]);
+      lr_on = lr_on || (args.samp.control_cost_coeff[c] != 0.0f);
+    }
+  const float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
 
   // ---- the horizon ----------------------------------------------------------------------------------------------
   for (int k = 0; k < nchunks; k++)
@@ -229,9 +253,10 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       const int col0 = k * kChunkFloats + g * 4;
       if (col0 >= TC)
         break;
-      const float4 e4 = lds128(tile, tile_offset_bytes(bx, k, tid, g));
-      const float e[4] = { e4.x, e4.y, e4.z, e4.w };
-#pragma unroll
+      unsigned char* gp = tile + tile_offset_bytes(bx, k, tid, g);
+      const float4 e4 = *reinterpret_cast<const float4*>(gp);
+      // light models: the 4/C steps of a 16-byte group are unrolled; heavy ones (NN) keep one copy of the step body
+#pragma unroll(DYN::UNROLL_STEPS ? STEPS_PER_GROUP : 1)
       for (int s = 0; s < STEPS_PER_GROUP; s++)
       {
         const int t = col0 / C + s;
@@ -245,22 +270,35 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
           const float* mean_t = means_s + (d * T + t) * C;
 #pragma unroll
           for (int c = 0; c < C; c++)
-            u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], e[s * C + c], use_mean, pure_noise);
+            u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], group_elem(e4, s * C + c), use_mean,
+                                  pure_noise);
           DYN::enforceConstraints(args.dyn, x[d], u);  // mppi_common.cu:108-111
-          if (args.controls_out != nullptr && valid)
-          {  // mppi_common.cu:117 writeControlSample (compat / debug path only)
-            float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc) * T + t) * C;
+          if (D == 1)
+          {
+            // single system: the constrained control replaces the noise in the shared tile (what writeControlSample does
+            // in HBM, mppi_common.cu:117), so the epilogue's weighted sum reads it back instead of recomputing it
 #pragma unroll
             for (int c = 0; c < C; c++)
-              dst[c] = u[c];
+              reinterpret_cast<float*>(gp)[s * C + c] = u[c];
+          }
+          if (WRITEBACK)
+          {  // compat / debug path: keep the constrained samples in HBM like the reference
+            if (valid)
+            {
+              float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc) * T + t) * C;
+#pragma unroll
+              for (int c = 0; c < C; c++)
+                dst[c] = u[c];
+            }
           }
 #pragma unroll
           for (int i = 0; i < S; i++)
             xdot[i] = 0.0f;
           DYN::step(args.dyn, theta_s, x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
-          running_cost[d] +=
-              COST::computeRunningCost(args.cost, args.cost_aux, y[d], u, t, &crash_status[d]) +
-              likelihood_ratio_cost<C>(args.samp, d, mean_t, u, pure_noise, args.lambda, args.alpha);  // :126-128
+          float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[d], u, t, &crash_status[d]);
+          if (lr_on)
+            step_cost += likelihood_ratio_cost<C>(lr_scale[d], mean_t, u, pure_noise, half_lambda_1ma);  // :126-128
+          running_cost[d] += step_cost;
 #pragma unroll
           for (int i = 0; i < S; i++)
             x[d][i] = x_next[i];
@@ -320,7 +358,9 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   }
 
   // exp-weighted sum of the CONSTRAINED sampled controls (weightedReductionKernel, mppi_common.cu:710-737), taken
-  // from the shared noise tile: thread j owns time step j (all C components so enforceConstraints sees the full u).
+  // from the shared tile: thread j owns time step j (all C components so enforceConstraints sees the full u).
+  // D == 1: the tile already holds the constrained controls. D == 2: the tile still holds the shared noise and each
+  // system's control is recomputed from it.
   const int rows_here = min(bx, args.n_local - row0);
 #pragma unroll
   for (int d = 0; d < D; d++)
@@ -334,24 +374,43 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
         acc[c] = 0.0f;
       const float* mean_t = means_s + (d * T + t) * C;
       const int col = t * C;
-      const int chunk = col >> 5, within = col & 31;
+      const int chunk = col >> 5, within = col & 31, grp = within >> 2;
       const bool t_uses_mean = t < args.opt_stride;
-#pragma unroll 4
-      for (int r = 0; r < rows_here; r++)
+      const unsigned char* slab = tile + (size_t)chunk * bx * kChunkBytes + ((within & 3) << 2);
+      const float* wrow = w_s + d * bx;
+      // rows in blocks of 8: the swizzle term (grp ^ (r & 7)) << 4 is then a per-lane constant of the unrolled body
+      for (int r8 = 0; r8 < rows_here; r8 += 8)
       {
-        const unsigned char* p = tile + tile_offset_bytes(bx, chunk, r, within >> 2) + ((within & 3) << 2);
-        float u[C];
-        const int ng = args.n_offset + row0 + r;
-        const bool pn = (float)ng >= args.samp.pure_noise_threshold;
-        const bool um = t_uses_mean || (ng == 0);
 #pragma unroll
-        for (int c = 0; c < C; c++)
-          u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], reinterpret_cast<const float*>(p)[c], um, pn);
-        DYN::enforceConstraints(args.dyn, nullptr, u);
-        const float w = w_s[d * bx + r];
+        for (int i = 0; i < 8; i++)
+        {
+          const int r = r8 + i;
+          if (r < rows_here)
+          {
+            const float* p = reinterpret_cast<const float*>(slab + r * kChunkBytes + ((grp ^ i) << 4));
+            float u[C];
+            if (D == 1)
+            {
 #pragma unroll
-        for (int c = 0; c < C; c++)
-          acc[c] = fmaf(w, u[c], acc[c]);
+              for (int c = 0; c < C; c++)
+                u[c] = p[c];
+            }
+            else
+            {
+              const int ng = args.n_offset + row0 + r;
+              const bool pn = (float)ng >= args.samp.pure_noise_threshold;
+              const bool um = t_uses_mean || (ng == 0);
+#pragma unroll
+              for (int c = 0; c < C; c++)
+                u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], p[c], um, pn);
+              DYN::enforceConstraints(args.dyn, nullptr, u);
+            }
+            const float w = wrow[r];
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              acc[c] = fmaf(w, u[c], acc[c]);
+          }
+        }
       }
 #pragma unroll
       for (int c = 0; c < C; c++)

@@ -49,9 +49,16 @@ class ControlLimits(C.Structure):
 
     def __init__(self):
         super().__init__()
-        for i in range(MAX_C):  # dynamics.cuh:99-106 defaults
+        self.set_defaults()
+
+    def set_defaults(self) -> None:
+        """dynamics.cuh:99-106: unbounded ranges, zero deadband / zero control. NOTE: ctypes does not run __init__ for
+        a struct nested inside another struct, so every dynamics blob calls this explicitly."""
+        for i in range(MAX_C):
             self.rng_lo[i] = -FLT_MAX
             self.rng_hi[i] = FLT_MAX
+            self.deadband[i] = 0.0
+            self.zero_control[i] = 0.0
 
 
 class CartpoleDynParams(C.Structure):
@@ -248,6 +255,7 @@ class CartpoleDynamics(_Dynamics):
     def __init__(self, cart_mass: float = 1.0, pole_mass: float = 1.0, pole_length: float = 1.0):
         super().__init__()
         self.params = CartpoleDynParams()
+        self.params.lim.set_defaults()
         self.params.cart_mass, self.params.pole_mass, self.params.pole_length = cart_mass, pole_mass, pole_length
         self.params.gravity = 9.81  # cartpole_dynamics.cuh:101
 
@@ -259,6 +267,7 @@ class DoubleIntegratorDynamics(_Dynamics):
     def __init__(self, system_noise: float = 1.0):
         super().__init__()
         self.params = DIDynParams()
+        self.params.lim.set_defaults()
         self.params.system_noise = system_noise
 
 
@@ -270,6 +279,7 @@ class NeuralNetModel(_Dynamics):
     def __init__(self, control_rngs: Optional[Sequence[Sequence[float]]] = None):
         super().__init__()
         self.params = ARNNDynParams()
+        self.params.lim.set_defaults()
         if control_rngs is not None:
             self.setControlRanges(control_rngs)
         self.nn_theta = np.zeros(AR_NN_NUM_PARAMS, np.float32)
