@@ -1,0 +1,68 @@
+/* NeuralNetModel<S_DIM, C_DIM, K_DIM> — host class of include/mppi/dynamics/autorally/ar_nn_model.cuh. Only the
+ * <7,2,3> instance (6-32-32-4 network) has a device twin in libmppi_b200.so. */
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <vector>
+
+#include "../dynamics.hpp"
+
+struct NNDynamicsParams
+{
+};
+
+template <int S_DIM, int C_DIM, int K_DIM>
+class NeuralNetModel
+  : public MPPI_internal::Dynamics<NeuralNetModel<S_DIM, C_DIM, K_DIM>, mppib_ar_nn_dyn_params, MPPIB_DYN_AUTORALLY_NN,
+                                   S_DIM, C_DIM, 8>
+{
+  static_assert(S_DIM == 7 && C_DIM == 2 && K_DIM == 3, "libmppi_b200 ships NeuralNetModel<7,2,3> only");
+
+public:
+  typedef NNDynamicsParams DYN_PARAMS_T;
+  using PARENT = MPPI_internal::Dynamics<NeuralNetModel<S_DIM, C_DIM, K_DIM>, mppib_ar_nn_dyn_params,
+                                         MPPIB_DYN_AUTORALLY_NN, S_DIM, C_DIM, 8>;
+  static const int DYNAMICS_DIM = S_DIM - K_DIM;
+  NeuralNetModel(cudaStream_t stream = 0) : theta_(MPPIB_AR_NN_NUM_PARAMS, 0.0f)
+  {
+  }
+  NeuralNetModel(std::array<float2, C_DIM> control_rngs, cudaStream_t stream = 0) : NeuralNetModel()
+  {
+    this->setControlRanges(control_rngs);
+  }
+  // ar_nn_model.cu:40-45 -> FNNHelper::updateModel (fnn_helper.cu:218-257)
+  void updateModel(const std::vector<int>& description, const std::vector<float>& data)
+  {
+    const int expect[4] = { 6, 32, 32, 4 };
+    if (description.size() != 4)
+      throw std::invalid_argument("Invalid model trying to to be set for NN");
+    for (int i = 0; i < 4; i++)
+      if (description[i] != expect[i])
+        throw std::invalid_argument("Invalid model trying to to be set for NN");
+    if (data.size() != (size_t)MPPIB_AR_NN_NUM_PARAMS)
+      throw std::invalid_argument("NN parameter vector must hold 1412 floats");
+    for (float v : data)
+      if (!std::isfinite(v))
+        throw std::invalid_argument("NN parameters must be finite");
+    theta_ = data;
+  }
+  const float* nnWeights() const
+  {
+    return theta_.data();
+  }
+  const std::vector<float>& getTheta() const
+  {
+    return theta_;
+  }
+  std::string getDynamicsModelName() const override
+  {
+    return "FCN Autorally Model";
+  }
+  mppib_ar_nn_dyn_params modelBlob() const
+  {
+    return mppib_ar_nn_dyn_params{};
+  }
+
+private:
+  std::vector<float> theta_;
+};

@@ -365,6 +365,10 @@ static int draw_noise(mppib_engine& e)
       CUDA_TRY(cudaGetLastError());
       e.xw_dirty = false;
     }
+    if (getenv("MPPIB_DEBUG"))
+      fprintf(stderr, "[mppib] draw: engine %p states %p tables %p chunks %d rounds %d eps %p stream %p\n", (void*)&e,
+              (void*)e.xw_states_d, (void*)e.xw_tables_d, e.xw_chunks, e.xw_rounds_per_chunk, (void*)e.eps_d,
+              (void*)e.stream);
     xorwow_normal_kernel<<<(nstates + 255) / 256, 256, 0, e.stream>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
                                                                      e.xw_rounds_per_chunk, e.xw_chunks,
                                                                      reinterpret_cast<float2*>(e.eps_d));
@@ -657,6 +661,9 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     CUDA_TRY_B(cudaStreamSynchronize(e->stream));
     e->xw_enabled = true;
     e->xw_dirty = true;
+    if (getenv("MPPIB_DEBUG"))
+      fprintf(stderr, "[mppib] create: engine %p states %p tables %p (%zu B)\n", (void*)e, (void*)e->xw_states_d,
+              (void*)e->xw_tables_d, tables.size() * sizeof(uint32_t));
   }
 
   if (e->use_tma)
@@ -691,6 +698,8 @@ int mppib_destroy(mppib_engine* e)
 {
   if (!e)
     return MPPIB_OK;
+  if (getenv("MPPIB_DEBUG"))
+    fprintf(stderr, "[mppib] destroy: engine %p\n", (void*)e);
   cudaSetDevice(e->desc.device);
   if (e->stream)
     cudaStreamSynchronize(e->stream);
@@ -1058,8 +1067,6 @@ int mppib_set_option(mppib_engine* e, int option, long long value)
       if (e->l2_flush_d)
       {
         cudaFree(e->l2_flush_d);
-  cudaFree(e->xw_states_d);
-  cudaFree(e->xw_tables_d);
         e->l2_flush_d = nullptr;
         e->l2_flush_bytes = 0;
       }
