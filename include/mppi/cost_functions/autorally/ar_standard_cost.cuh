@@ -1,0 +1,3 @@
+// Source-compatibility forwarder: the reference's include path, served by the B200 host layer.
+#pragma once
+#include <mppi_b200/cost_functions/autorally/ar_standard_cost.hpp>

@@ -1,0 +1,5 @@
+// Source-compatibility forwarder: the reference's include path, served by the B200 host layer.
+#pragma once
+#include <mppi_b200/controllers/MPPI/mppi_controller.hpp>
+#include <mppi_b200/dynamics/cartpole/cartpole_dynamics.hpp>
+#include <mppi_b200/cost_functions/cartpole/cartpole_quadratic_cost.hpp>

@@ -1,0 +1,387 @@
+/*
+ * mppi_b200/controllers/controller.hpp — host-side Controller base, mirroring include/mppi/controllers/controller.cuh:
+ * same template parameters and order, same constructor arguments, same public methods for the hot path
+ * (computeControl, getControlSeq, getTargetStateSeq, getTargetOutputSeq, getBaselineCost, getNormalizerCost,
+ *  getFreeEnergyStatistics, slideControlSequence, setParams/getParams, setSeedCUDARandomNumberGen, getSampledCostSeq).
+ * Everything device-side goes through the C-ABI engine (include/mppi_b200.h); the host tail — Savitzky-Golay smoothing,
+ * nominal roll-forward, clamping (controller.cuh:557-663) — stays on the host like in the reference.
+ *
+ * Not carried over (SURVEY.md §8 out of scope): DDP feedback computation, visualisation kernels, kernel-choice timing
+ * (chooseAppropriateKernel keeps its RNG side effect only: one burnt noise draw, mppi_controller.cu:95).
+ */
+#pragma once
+#include <chrono>
+#include <memory>
+#include <vector>
+
+#include "../utils/common.hpp"
+
+// controller.cuh:22-38
+struct freeEnergyEstimate
+{
+  float increase = -1;
+  float previousBaseline = -1;
+  float freeEnergyMean = -1;
+  float freeEnergyVariance = -1;
+  float freeEnergyModifiedVariance = -1;
+  float normalizerPercent = -1;
+};
+struct MPPIFreeEnergyStatistics
+{
+  int nominal_state_used = 0;
+  freeEnergyEstimate nominal_sys;
+  freeEnergyEstimate real_sys;
+};
+
+enum class kernelType : int
+{
+  USE_SINGLE_KERNEL = 0,
+  USE_SPLIT_KERNELS,
+};
+
+// controller.cuh:46-68
+template <int S_DIM, int C_DIM, int MAX_TIMESTEPS>
+struct ControllerParams
+{
+  static const int TEMPLATED_STATE_DIM = S_DIM;
+  static const int TEMPLATED_CONTROL_DIM = C_DIM;
+  static const int TEMPLATED_MAX_TIMESTEPS = MAX_TIMESTEPS;
+  float dt_ = 0.01f;
+  float lambda_ = 1.0;
+  float alpha_ = 0.0;
+  int num_timesteps_ = MAX_TIMESTEPS;
+  int num_iters_ = 1;
+  unsigned seed_ = (unsigned)std::chrono::system_clock::now().time_since_epoch().count();
+  dim3 dynamics_rollout_dim_;  // accepted for source compatibility; the B200 kernel picks its own geometry
+  dim3 cost_rollout_dim_;
+  dim3 visualize_dim_ = dim3(32, 1, 1);
+  int norm_exp_kernel_parallelization_ = 64;
+  Eigen::Matrix<float, C_DIM, MAX_TIMESTEPS> init_control_traj_ = Eigen::Matrix<float, C_DIM, MAX_TIMESTEPS>::Zero();
+  Eigen::Matrix<float, C_DIM, 1> slide_control_scale_ = Eigen::Matrix<float, C_DIM, 1>::Zero();
+};
+
+template <class DYN_T, class COST_T, class FB_T, class SAMPLING_T, int MAX_TIMESTEPS, int NUM_ROLLOUTS,
+          class PARAMS_T = ControllerParams<DYN_T::STATE_DIM, DYN_T::CONTROL_DIM, MAX_TIMESTEPS>, int NUM_DISTRIBUTIONS = 1>
+class Controller
+{
+public:
+  typedef DYN_T TEMPLATED_DYNAMICS;
+  typedef COST_T TEMPLATED_COSTS;
+  typedef FB_T TEMPLATED_FEEDBACK;
+  typedef PARAMS_T TEMPLATED_PARAMS;
+  typedef SAMPLING_T TEMPLATED_SAMPLING;
+  static const int TEMPLATED_DYNAMICS_STATE_DIM = DYN_T::STATE_DIM;
+  using control_array = typename DYN_T::control_array;
+  using state_array = typename DYN_T::state_array;
+  using output_array = typename DYN_T::output_array;
+  typedef Eigen::Matrix<float, DYN_T::CONTROL_DIM, MAX_TIMESTEPS> control_trajectory;
+  typedef Eigen::Matrix<float, DYN_T::STATE_DIM, MAX_TIMESTEPS> state_trajectory;
+  typedef Eigen::Matrix<float, DYN_T::OUTPUT_DIM, MAX_TIMESTEPS> output_trajectory;
+  typedef Eigen::Matrix<float, NUM_ROLLOUTS, 1> sampled_cost_traj;
+
+  Controller(DYN_T* model, COST_T* cost, FB_T* fb_controller, SAMPLING_T* sampler, float dt, int max_iter, float lambda,
+             float alpha, int num_timesteps = MAX_TIMESTEPS,
+             const Eigen::Ref<const control_trajectory>& init_control_traj = control_trajectory::Zero(),
+             cudaStream_t stream = nullptr)
+    : model_(model), cost_(cost), fb_controller_(fb_controller), sampler_(sampler)
+  {
+    params_.dt_ = dt;
+    params_.num_iters_ = max_iter;
+    params_.lambda_ = lambda;
+    params_.alpha_ = alpha;
+    params_.num_timesteps_ = (num_timesteps > 0 && num_timesteps <= MAX_TIMESTEPS) ? num_timesteps : MAX_TIMESTEPS;
+    params_.init_control_traj_ = init_control_traj;
+    control_ = init_control_traj;
+    construct(stream);
+  }
+  Controller(DYN_T* model, COST_T* cost, FB_T* fb_controller, SAMPLING_T* sampler, PARAMS_T& params,
+             cudaStream_t stream = nullptr)
+    : model_(model), cost_(cost), fb_controller_(fb_controller), sampler_(sampler), params_(params)
+  {
+    control_ = params_.init_control_traj_;
+    construct(stream);
+  }
+  virtual ~Controller()
+  {  // controller.cuh:194-216: the controller frees the device side, not the plugin objects
+    if (engine_)
+      mppib_destroy(engine_);
+  }
+  Controller(const Controller&) = delete;
+  Controller& operator=(const Controller&) = delete;
+
+  virtual void computeControl(const Eigen::Ref<const state_array>& state, int optimization_stride) = 0;
+  virtual void slideControlSequence(int steps) = 0;
+  virtual std::string getControllerName()
+  {
+    return "name not set";
+  }
+
+  // ---- getters (controller.cuh:409-436,510-517,773-776) ----------------------------------------------------------
+  virtual control_trajectory getControlSeq() const
+  {
+    return control_;
+  }
+  virtual state_trajectory getTargetStateSeq() const
+  {
+    return state_;
+  }
+  virtual output_trajectory getTargetOutputSeq() const
+  {
+    return output_;
+  }
+  float getBaselineCost(int ind = 0) const
+  {
+    return baseline_[ind];
+  }
+  float getNormalizerCost(int ind = 0) const
+  {
+    return normalizer_[ind];
+  }
+  float getNormalizerPercent() const
+  {
+    return normalizer_[0] / NUM_ROLLOUTS;
+  }
+  MPPIFreeEnergyStatistics getFreeEnergyStatistics() const
+  {
+    return free_energy_statistics_;
+  }
+  sampled_cost_traj getSampledCostSeq()
+  {  // trajectory costs of distribution 0 (raw costs; weights via mppib_get_weights)
+    std::vector<float> c((size_t)NUM_DISTRIBUTIONS * NUM_ROLLOUTS);
+    MPPIB_HANDLE(mppib_get_costs(engine_, c.data()));
+    sampled_cost_traj r;
+    for (int i = 0; i < NUM_ROLLOUTS; i++)
+      r(i) = c[i];
+    return r;
+  }
+  int getNumTimesteps() const
+  {
+    return params_.num_timesteps_;
+  }
+  float getDt() const
+  {
+    return params_.dt_;
+  }
+  float getLambda() const
+  {
+    return params_.lambda_;
+  }
+  float getAlpha() const
+  {
+    return params_.alpha_;
+  }
+  int getNumIters() const
+  {
+    return params_.num_iters_;
+  }
+  PARAMS_T getParams() const
+  {
+    return params_;
+  }
+  // controller.cuh:821-850
+  virtual void setParams(const PARAMS_T& p)
+  {
+    const bool reseed = p.seed_ != params_.seed_;
+    const bool retime = p.num_timesteps_ != params_.num_timesteps_;
+    params_ = p;
+    if (retime)
+    {  // the horizon is baked into the engine's buffers
+      createEngine();
+    }
+    else
+    {
+      pushParams();
+      if (reseed)
+        setSeedCUDARandomNumberGen(params_.seed_);
+    }
+  }
+  void setDt(float dt)
+  {
+    params_.dt_ = dt;
+    pushParams();
+  }
+  void setLambda(float lambda)
+  {
+    params_.lambda_ = lambda;
+    pushParams();
+  }
+  void setAlpha(float alpha)
+  {
+    params_.alpha_ = alpha;
+    pushParams();
+  }
+  void setNumIters(int n)
+  {
+    params_.num_iters_ = n;
+  }
+  void setNumTimesteps(int num_timesteps)
+  {  // controller.cuh:665-676
+    if (num_timesteps <= MAX_TIMESTEPS && num_timesteps > 0 && num_timesteps != params_.num_timesteps_)
+    {
+      params_.num_timesteps_ = num_timesteps;
+      createEngine();
+    }
+  }
+  // controller.cu:200-207: new seed, offset back to 0
+  void setSeedCUDARandomNumberGen(unsigned seed)
+  {
+    params_.seed_ = seed;
+    MPPIB_HANDLE(mppib_seed(engine_, seed, 0ULL));
+  }
+  void setCUDAStream(cudaStream_t stream)
+  {  // controller.cuh:901: re-create the engine on the new stream
+    stream_ = stream;
+    createEngine();
+  }
+  // plugin parameters were edited through model_/cost_/sampler_: send them to the device (setParams -> paramsToDevice)
+  void pushParams()
+  {
+    auto db = model_->blob();
+    MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_DYN_PARAMS, &db, sizeof(db)));
+    auto cb = cost_->blob();
+    MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_COST_PARAMS, &cb, sizeof(cb)));
+    auto sb = sampler_->blob();
+    MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_SAMPLER_PARAMS, &sb, sizeof(sb)));
+    if (model_->nnWeights())
+      MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_NN_WEIGHTS, model_->nnWeights(),
+                                  MPPIB_AR_NN_NUM_PARAMS * sizeof(float)));
+    pushCostmap(cost_);
+    MPPIB_HANDLE(mppib_set_solver(engine_, params_.dt_, params_.lambda_, params_.alpha_));
+  }
+  // kept for source compatibility (controller.cuh:299-302,886-894); the engine has a single fused kernel
+  void setKernelChoice(kernelType)
+  {
+  }
+  kernelType getKernelChoiceAsEnum() const
+  {
+    return kernelType::USE_SINGLE_KERNEL;
+  }
+  virtual void chooseAppropriateKernel()
+  {  // mppi_controller.cu:44-143 draws one full noise buffer: keep the RNG in lock-step
+    MPPIB_HANDLE(mppib_burn_draws(engine_, 1));
+  }
+  mppib_engine* engine()
+  {
+    return engine_;
+  }
+
+  // ---- host tail helpers (controller.cuh:557-663) -----------------------------------------------------------------
+  void smoothControlTrajectoryHelper(Eigen::Ref<control_trajectory> u,
+                                     const Eigen::Ref<const Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2>>& control_history)
+  {
+    control_trajectory tmp = u;
+    Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2> h = control_history;
+    mppib_host_smooth_controls(tmp.data(), h.data(), getNumTimesteps(), DYN_T::CONTROL_DIM);
+    u = tmp;
+  }
+  virtual void slideControlSequenceHelper(int steps, Eigen::Ref<control_trajectory> u)
+  {
+    control_trajectory tmp = u;
+    mppib_host_slide_controls(tmp.data(), steps, getNumTimesteps(), DYN_T::CONTROL_DIM, model_->zero_control_.data(),
+                              params_.slide_control_scale_.data());
+    u = tmp;
+  }
+  virtual void saveControlHistoryHelper(int steps, const Eigen::Ref<const control_trajectory>& u_trajectory,
+                                        Eigen::Ref<Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2>> u_history)
+  {  // controller.cuh:602-616
+    if (steps == 1)
+    {
+      u_history.col(0) = u_history.col(1);
+      u_history.col(1) = u_trajectory.col(0);
+    }
+    else if (steps >= 2)
+    {
+      u_history.col(0) = u_trajectory.col(steps - 2);
+      u_history.col(1) = u_trajectory.col(steps - 1);
+    }
+  }
+  virtual void computeOutputTrajectoryHelper(Eigen::Ref<output_trajectory> output_result,
+                                             Eigen::Ref<state_trajectory> state_result,
+                                             const Eigen::Ref<const state_array>& x0,
+                                             const Eigen::Ref<const control_trajectory>& u)
+  {
+    state_array x = x0;
+    control_trajectory uu = u;
+    state_trajectory st = state_trajectory::Zero();
+    output_trajectory out = output_trajectory::Zero();
+    auto db = model_->blob();
+    MPPIB_HANDLE(mppib_host_output_trajectory(DYN_T::DYN_ID, &db, model_->nnWeights(), x.data(), uu.data(),
+                                              getNumTimesteps(), getDt(), st.data(), out.data()));
+    state_result = st;
+    output_result = out;
+  }
+
+protected:
+  void construct(cudaStream_t stream)
+  {
+    stream_ = stream;
+    for (int d = 0; d < NUM_DISTRIBUTIONS; d++)
+      baseline_[d] = normalizer_[d] = 0.0f;
+    createEngine();
+  }
+  void createEngine()
+  {
+    if (engine_)
+    {
+      mppib_destroy(engine_);
+      engine_ = nullptr;
+    }
+    mppib_desc d{};
+    d.dynamics_id = DYN_T::DYN_ID;
+    d.cost_id = COST_T::COST_ID;
+    d.sampler_id = SAMPLING_T::SAMPLER_ID;
+    d.num_rollouts = NUM_ROLLOUTS;
+    d.num_timesteps = params_.num_timesteps_;
+    d.num_distributions = NUM_DISTRIBUTIONS;
+    d.device = 0;  // mppi_controller.cu:48
+    d.flags = 0;
+    d.stream = (void*)stream_;
+    d.rank = 0;
+    d.world_size = 1;
+    MPPIB_HANDLE(mppib_create(&engine_, &d));
+    pushParams();
+    MPPIB_HANDLE(mppib_seed(engine_, params_.seed_, 0ULL));  // createAndSeedCUDARandomNumberGen (controller.cu:192-198)
+  }
+  template <class C>
+  auto pushCostmap(C* c) -> decltype(c->costmapBytes(), void())
+  {
+    if (c->costmap())
+      MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_COSTMAP, c->costmap(), c->costmapBytes()));
+  }
+  void pushCostmap(...)
+  {
+  }
+  // one engine solve for all distributions; x0s [D][S], Us [D][T][C] in the engine's layout
+  void solve(const float* x0s, const float* Us_in, int optimization_stride, int iter, float* Us_out)
+  {
+    mppib_solve_stats st[NUM_DISTRIBUTIONS];
+    MPPIB_HANDLE(mppib_solve(engine_, x0s, Us_in, optimization_stride, iter, Us_out, st));
+    for (int d = 0; d < NUM_DISTRIBUTIONS; d++)
+    {
+      baseline_[d] = st[d].baseline;
+      normalizer_[d] = st[d].normalizer;
+      float fe[3];
+      mppib_host_free_energy(&st[d], NUM_ROLLOUTS, params_.lambda_, fe);
+      freeEnergyEstimate& e = (d == 0) ? free_energy_statistics_.real_sys : free_energy_statistics_.nominal_sys;
+      e.freeEnergyMean = fe[0];
+      e.freeEnergyVariance = fe[1];
+      e.freeEnergyModifiedVariance = fe[2];
+    }
+  }
+
+  DYN_T* model_;
+  COST_T* cost_;
+  FB_T* fb_controller_;
+  SAMPLING_T* sampler_;
+  PARAMS_T params_;
+  cudaStream_t stream_ = nullptr;
+  mppib_engine* engine_ = nullptr;
+
+  control_trajectory control_ = control_trajectory::Zero();
+  Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2> control_history_ = Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2>::Zero();
+  state_trajectory state_ = state_trajectory::Zero();
+  output_trajectory output_ = output_trajectory::Zero();
+  float baseline_[NUM_DISTRIBUTIONS];
+  float normalizer_[NUM_DISTRIBUTIONS];
+  MPPIFreeEnergyStatistics free_energy_statistics_;
+};

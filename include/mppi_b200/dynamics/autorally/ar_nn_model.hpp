@@ -8,7 +8,10 @@
 #include "../dynamics.hpp"
 
 struct NNDynamicsParams
-{
+{  // ar_nn_model.cuh:18-51
+  enum class StateIndex : int { POS_X = 0, POS_Y, YAW, ROLL, BODY_VEL_X, BODY_VEL_Y, YAW_RATE, NUM_STATES };
+  enum class ControlIndex : int { STEERING = 0, THROTTLE, NUM_CONTROLS };
+  enum class OutputIndex : int { POS_X = 0, POS_Y, YAW, ROLL, BODY_VEL_X, BODY_VEL_Y, YAW_RATE, FILLER_1, NUM_OUTPUTS };
 };
 
 template <int S_DIM, int C_DIM, int K_DIM>

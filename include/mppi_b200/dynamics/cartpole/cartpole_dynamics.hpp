@@ -5,6 +5,9 @@
 
 struct CartpoleDynamicsParams
 {  // cartpole_dynamics.cuh:8-37
+  enum class StateIndex : int { POS_X = 0, VEL_X, THETA, THETA_DOT, NUM_STATES };
+  enum class ControlIndex : int { FORCE = 0, NUM_CONTROLS };
+  enum class OutputIndex : int { POS_X = 0, VEL_X, THETA, THETA_DOT, NUM_OUTPUTS };
   float cart_mass = 1.0f;
   float pole_mass = 1.0f;
   float pole_length = 1.0f;

@@ -6,7 +6,10 @@
 #include "../dynamics.hpp"
 
 struct DoubleIntegratorParams
-{
+{  // di_dynamics.cuh:9-37
+  enum class StateIndex : int { POS_X = 0, POS_Y, VEL_X, VEL_Y, NUM_STATES };
+  enum class ControlIndex : int { ACCEL_X = 0, ACCEL_Y, NUM_CONTROLS };
+  enum class OutputIndex : int { POS_X = 0, POS_Y, VEL_X, VEL_Y, NUM_OUTPUTS };
   float system_noise = 1;
   DoubleIntegratorParams() = default;
   DoubleIntegratorParams(float noise) : system_noise(noise){};

@@ -87,9 +87,9 @@ protected:
   SAMPLING_PARAMS_T params_;
 };
 
-// GaussianDistribution<DYN_PARAMS_T>: the reference deduces CONTROL_DIM from the dynamics params' ControlIndex enum;
-// here the controller re-binds the sampler to its dynamics' CONTROL_DIM through SamplerFor<>.
-template <int C_DIM>
-using GaussianDistributionC = GaussianDistributionImpl<void, C_DIM>;
+// GaussianDistribution<DYN_PARAMS_T>: CONTROL_DIM comes from the dynamics params' ControlIndex enum, as in the reference
+// (sampling_distribution.cuh:36-40).
+template <class DYN_PARAMS_T>
+using GaussianDistribution = GaussianDistributionImpl<DYN_PARAMS_T, (int)DYN_PARAMS_T::ControlIndex::NUM_CONTROLS>;
 }  // namespace sampling_distributions
 }  // namespace mppi

@@ -1,0 +1,34 @@
+"""The header-only C++ host layer (include/mppi_b200/): builds with plain g++ against the Eigen shim, links to the C-ABI
+library, and runs the reference's cartpole example flow (tests/cpp/cartpole_example.cpp). On a box without a GPU the
+binary must stop at the C-ABI's NO_DEVICE error (exit code 5) — never a CPU fallback; on the B200 it must swing up."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "cartpole_example.bin")
+
+
+def _build():
+    lib_dir = os.path.join(ROOT, "mppi-generic_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-variable", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "cartpole_example.cpp"), "-o", EXE, "-L", lib_dir,
+                           "-lmppi_b200", "-Wl,-rpath," + lib_dir])
+
+
+def test_host_layer_compiles_and_fails_loudly_without_a_device():
+    _build()
+    p = subprocess.run([EXE], capture_output=True, text=True, timeout=600)
+    if p.returncode == 5:
+        assert "no CUDA device" in p.stdout
+    else:  # a GPU is present: the example must succeed
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_host_layer_cartpole_example_swings_up_on_the_gpu():
+    _build()
+    p = subprocess.run([EXE], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "final pole angle error" in p.stdout
