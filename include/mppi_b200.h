@@ -60,6 +60,7 @@ enum mppib_blob
 #define MPPIB_FLAG_WRITEBACK_CONTROLS 1u /* keep the constrained sampled controls in HBM like the reference does    \
                                             (mppi_common.cu:117); needed by mppib_get_samples */
 #define MPPIB_FLAG_NO_TMA 2u             /* stage noise tiles with plain loads instead of cp.async.bulk.tensor */
+#define MPPIB_FLAG_NO_PREFETCH 8u         /* draw each solve's noise inline instead of one solve ahead on a side stream */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
 

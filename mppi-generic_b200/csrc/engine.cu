@@ -137,11 +137,28 @@ struct mppib_engine
   // RNG
   curandGenerator_t gen = nullptr;
   unsigned long long seed = 0;
-  unsigned long long rng_offset = 0;  // absolute position (in normals) of the next GLOBAL draw
-  bool rng_positioned = false;        // generator's internal position == what the next local draw needs
+  unsigned long long rng_offset = 0;  // absolute position (in normals) of the next GLOBAL draw to be CONSUMED
+  static constexpr unsigned long long kNoPos = ~0ULL;
+  unsigned long long curand_pos = kNoPos;  // global draw position the library generator sits at (world_size == 1 only)
   // own XORWOW draw (noise_xorwow.cuh): 4096 * xw_chunks persistent states
-  bool xw_enabled = false;  // sizes allow it and MPPIB_FLAG_CURAND_HOST_API not set
-  bool xw_dirty = true;     // states must be (re)initialised from (seed, rng_offset)
+  bool xw_enabled = false;             // sizes allow it and MPPIB_FLAG_CURAND_HOST_API not set
+  unsigned long long xw_pos = kNoPos;  // global draw position the states sit at (kNoPos = must be initialised)
+  // double-buffered noise: the draw for solve s+1 runs on a side stream while K1/K2 of solve s run (it depends on
+  // nothing but the RNG position)
+  bool prefetch_enabled = false;
+  float* noise_alloc2 = nullptr;
+  float* eps_buf[2] = { nullptr, nullptr };
+  CUtensorMap tmap_buf[2];
+  int cur_buf = 0;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_k1_done[2] = { nullptr, nullptr };   // K1 that read eps_buf[i] has finished
+  cudaEvent_t ev_gen_done[2] = { nullptr, nullptr };  // the draw into eps_buf[i] has finished
+  cudaEvent_t ev_last_gen = nullptr;                   // last draw on either stream (generator state ordering)
+  bool k1_recorded[2] = { false, false };
+  bool any_gen = false;
+  bool prefetch_valid = false;
+  unsigned long long prefetch_pos = 0;
+  int prefetch_buf = 0;
   int xw_chunks = 0, xw_rounds_per_chunk = 0;
   uint32_t xw_jump_d = 0;
   uint32_t* xw_states_d = nullptr;
@@ -325,7 +342,7 @@ static const PairEntry kPairs[] = {
 };
 
 // ---- helpers ----------------------------------------------------------------------------------------------------
-static int make_tensor_map(mppib_engine& e)
+static int make_tensor_map(mppib_engine& e, float* base, CUtensorMap* out)
 {
   // 2-D view of the noise buffer: rows = local rollouts, cols = T*C floats (row pitch T*C*4 B, must be 16-B multiple)
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -340,7 +357,7 @@ static int make_tensor_map(mppib_engine& e)
   cuuint64_t gstride[1] = { (cuuint64_t)e.TC * sizeof(float) };
   cuuint32_t box[2] = { (cuuint32_t)kChunkFloats, (cuuint32_t)e.bx };
   cuuint32_t estride[2] = { 1, 1 };
-  CUresult r = ((EncodeFn)fn)(&e.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, e.eps_d, gdim, gstride, box, estride,
+  CUresult r = ((EncodeFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estride,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -348,54 +365,99 @@ static int make_tensor_map(mppib_engine& e)
   return MPPIB_OK;
 }
 
-static int draw_noise(mppib_engine& e)
+// One generateSamples-equivalent draw (gaussian.cu:378-394) of the block of the global XORWOW stream that starts at
+// global position `pos` (N*T*C normals per block; this rank keeps elements [n_offset*T*C, (n_offset+n_local)*T*C) of it)
+// into eps_buf[buf], on `st`. Draws are totally ordered through ev_last_gen because they share the generator state.
+static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long long pos)
 {
-  // One generateSamples-equivalent draw (gaussian.cu:378-394): N*T*C normals of the single global XORWOW stream;
-  // this rank keeps elements [n_offset*T*C, (n_offset+n_local)*T*C) of it.
   const unsigned long long global_count = (unsigned long long)e.N * e.TC;
-  const unsigned long long start = e.rng_offset + (unsigned long long)e.n_offset * e.TC;
+  const unsigned long long start = pos + (unsigned long long)e.n_offset * e.TC;
   const size_t count = (size_t)e.n_local * e.TC;
-  if (e.xw_enabled && (e.rng_offset % 8192ULL) == 0)
+  float* dst = e.eps_buf[buf];
+  if (e.any_gen)
+    CUDA_TRY(cudaStreamWaitEvent(st, e.ev_last_gen, 0));
+  if (e.xw_enabled && (pos % 8192ULL) == 0)
   {
     const int nstates = e.xw_chunks * kXorwowStreams;
-    if (e.xw_dirty)
+    if (e.xw_pos != pos)
     {
-      xorwow_init_kernel<<<(nstates + 127) / 128, 128, 0, e.stream>>>(e.seed, start / 8192ULL, e.xw_rounds_per_chunk,
-                                                                    e.xw_chunks, e.xw_states_d);
+      xorwow_init_kernel<<<(nstates + 127) / 128, 128, 0, st>>>(e.seed, start / 8192ULL, e.xw_rounds_per_chunk,
+                                                             e.xw_chunks, e.xw_states_d);
       CUDA_TRY(cudaGetLastError());
-      e.xw_dirty = false;
     }
-    if (getenv("MPPIB_DEBUG"))
-      fprintf(stderr, "[mppib] draw: engine %p states %p tables %p chunks %d rounds %d eps %p stream %p\n", (void*)&e,
-              (void*)e.xw_states_d, (void*)e.xw_tables_d, e.xw_chunks, e.xw_rounds_per_chunk, (void*)e.eps_d,
-              (void*)e.stream);
-    xorwow_normal_kernel<<<(nstates + 255) / 256, 256, 0, e.stream>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
-                                                                     e.xw_rounds_per_chunk, e.xw_chunks,
-                                                                     reinterpret_cast<float2*>(e.eps_d));
+    xorwow_normal_kernel<<<(nstates + 255) / 256, 256, 0, st>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
+                                                               e.xw_rounds_per_chunk, e.xw_chunks,
+                                                               reinterpret_cast<float2*>(dst));
     CUDA_TRY(cudaGetLastError());
-    e.rng_offset += global_count;
-    e.rng_positioned = false;  // the library generator was not advanced
-    return MPPIB_OK;
-  }
-  e.xw_dirty = true;  // library path taken: our states no longer track the stream position
-  if (e.desc.world_size == 1 && e.rng_positioned)
-  {
-    // generator already sits at `start`: plain continuation, exactly what the reference does call after call
-    CURAND_TRY(curandGenerateNormal(e.gen, e.eps_d, count, 0.0f, 1.0f));
+    e.xw_pos = pos + global_count;
   }
   else
   {
-    // XORWOW default ordering interleaves 4096 streams x 2 normals: absolute offsets are honoured at multiples of
-    // 8192 (probed on B200, tools/curand_probe.cu), so start from the aligned position below and discard the lead-in.
-    const unsigned long long aligned = (start / 8192ULL) * 8192ULL;
-    const size_t lead = (size_t)(start - aligned);
-    if (((lead + count) & 1) != 0)
-      return fail(MPPIB_ERR_UNSUPPORTED, "cuRAND normal draws need an even count (lead %zu + count %zu)", lead, count);
-    CURAND_TRY(curandSetGeneratorOffset(e.gen, aligned));
-    CURAND_TRY(curandGenerateNormal(e.gen, e.eps_d - lead, lead + count, 0.0f, 1.0f));
+    CURAND_TRY(curandSetStream(e.gen, st));
+    if (e.desc.world_size == 1 && e.curand_pos == pos)
+    {
+      // generator already sits at `start`: plain continuation, exactly what the reference does call after call
+      CURAND_TRY(curandGenerateNormal(e.gen, dst, count, 0.0f, 1.0f));
+    }
+    else
+    {
+      // XORWOW default ordering interleaves 4096 streams x 2 normals: absolute offsets are honoured at multiples of
+      // 8192 (probed on B200, tools/curand_probe.cu), so start from the aligned position below and discard the lead-in.
+      const unsigned long long aligned = (start / 8192ULL) * 8192ULL;
+      const size_t lead = (size_t)(start - aligned);
+      if (((lead + count) & 1) != 0)
+        return fail(MPPIB_ERR_UNSUPPORTED, "cuRAND normal draws need an even count (lead %zu + count %zu)", lead, count);
+      CURAND_TRY(curandSetGeneratorOffset(e.gen, aligned));
+      CURAND_TRY(curandGenerateNormal(e.gen, dst - lead, lead + count, 0.0f, 1.0f));
+    }
+    e.curand_pos = (e.desc.world_size == 1) ? pos + global_count : mppib_engine::kNoPos;
   }
-  e.rng_offset += global_count;
-  e.rng_positioned = (e.desc.world_size == 1);
+  CUDA_TRY(cudaEventRecord(e.ev_last_gen, st));
+  e.any_gen = true;
+  return MPPIB_OK;
+}
+
+// Makes eps_buf[cur_buf] hold the block at rng_offset (taking the prefetched buffer if it is the right one) and
+// advances rng_offset. Everything is ordered on the main stream when this returns.
+static int draw_noise(mppib_engine& e)
+{
+  if (e.prefetch_valid && e.prefetch_pos == e.rng_offset)
+  {
+    CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_gen_done[e.prefetch_buf], 0));
+    e.cur_buf = e.prefetch_buf;
+  }
+  else
+  {
+    // the main stream orders this draw after every earlier K1 that read eps_buf[cur_buf]
+    int rc = gen_draw(e, e.cur_buf, e.stream, e.rng_offset);
+    if (rc != MPPIB_OK)
+      return rc;
+  }
+  e.prefetch_valid = false;
+  e.eps_d = e.eps_buf[e.cur_buf];
+  e.tmap = e.tmap_buf[e.cur_buf];
+  e.rng_offset += (unsigned long long)e.N * e.TC;
+  return MPPIB_OK;
+}
+
+// After K1 of the current solve has been enqueued: start the draw of the NEXT block into the other buffer on the side
+// stream. It only has to wait for the K1 that last read that buffer.
+static int prefetch_next(mppib_engine& e)
+{
+  if (!e.prefetch_enabled)
+    return MPPIB_OK;
+  CUDA_TRY(cudaEventRecord(e.ev_k1_done[e.cur_buf], e.stream));
+  e.k1_recorded[e.cur_buf] = true;
+  const int nb = e.cur_buf ^ 1;
+  if (e.k1_recorded[nb])
+    CUDA_TRY(cudaStreamWaitEvent(e.side_stream, e.ev_k1_done[nb], 0));
+  int rc = gen_draw(e, nb, e.side_stream, e.rng_offset);
+  if (rc != MPPIB_OK)
+    return rc;
+  CUDA_TRY(cudaEventRecord(e.ev_gen_done[nb], e.side_stream));
+  e.prefetch_valid = true;
+  e.prefetch_pos = e.rng_offset;
+  e.prefetch_buf = nb;
   return MPPIB_OK;
 }
 
@@ -621,6 +683,21 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   CUDA_TRY_B(cudaMalloc(&e->noise_alloc, (lead_floats + noise_floats + 8) * sizeof(float)));
   e->eps_d = e->noise_alloc + lead_floats;  // cudaMalloc is 256-B aligned and 8192*4 keeps that
   CUDA_TRY_B(cudaMemsetAsync(e->noise_alloc, 0, (lead_floats + noise_floats + 8) * sizeof(float), e->stream));
+  e->eps_buf[0] = e->eps_buf[1] = e->eps_d;
+  e->prefetch_enabled = !(desc->flags & MPPIB_FLAG_NO_PREFETCH) && !getenv("MPPIB_NO_PREFETCH");
+  CUDA_TRY_B(cudaEventCreateWithFlags(&e->ev_last_gen, cudaEventDisableTiming));
+  if (e->prefetch_enabled)
+  {
+    CUDA_TRY_B(cudaMalloc(&e->noise_alloc2, (lead_floats + noise_floats + 8) * sizeof(float)));
+    CUDA_TRY_B(cudaMemsetAsync(e->noise_alloc2, 0, (lead_floats + noise_floats + 8) * sizeof(float), e->stream));
+    e->eps_buf[1] = e->noise_alloc2 + lead_floats;
+    CUDA_TRY_B(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++)
+    {
+      CUDA_TRY_B(cudaEventCreateWithFlags(&e->ev_k1_done[i], cudaEventDisableTiming));
+      CUDA_TRY_B(cudaEventCreateWithFlags(&e->ev_gen_done[i], cudaEventDisableTiming));
+    }
+  }
   CUDA_TRY_B(cudaMalloc(&e->costs_d, (size_t)e->D * e->n_local * sizeof(float)));
   CUDA_TRY_B(cudaMalloc(&e->partials_d, (size_t)e->grid * e->D * e->pstride * sizeof(float)));
   CUDA_TRY_B(cudaMalloc(&e->result_d, (size_t)e->D * e->pstride * sizeof(float)));
@@ -660,7 +737,6 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
                                e->stream));
     CUDA_TRY_B(cudaStreamSynchronize(e->stream));
     e->xw_enabled = true;
-    e->xw_dirty = true;
     if (getenv("MPPIB_DEBUG"))
       fprintf(stderr, "[mppib] create: engine %p states %p tables %p (%zu B)\n", (void*)e, (void*)e->xw_states_d,
               (void*)e->xw_tables_d, tables.size() * sizeof(uint32_t));
@@ -668,9 +744,13 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
 
   if (e->use_tma)
   {
-    int rc = make_tensor_map(*e);
-    if (rc != MPPIB_OK)
-      return bail(rc);
+    for (int i = 0; i < 2; i++)
+    {
+      int rc = make_tensor_map(*e, e->eps_buf[i], &e->tmap_buf[i]);
+      if (rc != MPPIB_OK)
+        return bail(rc);
+    }
+    e->tmap = e->tmap_buf[0];
   }
   {
     int rc = e->prepare(*e);
@@ -701,6 +781,8 @@ int mppib_destroy(mppib_engine* e)
   if (getenv("MPPIB_DEBUG"))
     fprintf(stderr, "[mppib] destroy: engine %p\n", (void*)e);
   cudaSetDevice(e->desc.device);
+  if (e->side_stream)
+    cudaStreamSynchronize(e->side_stream);
   if (e->stream)
     cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy)
@@ -713,6 +795,7 @@ int mppib_destroy(mppib_engine* e)
     cudaFreeArray(e->costmap_array);
   cudaFree(e->nn_theta_d);
   cudaFree(e->noise_alloc);
+  cudaFree(e->noise_alloc2);
   cudaFree(e->costs_d);
   cudaFree(e->partials_d);
   cudaFree(e->controls_d);
@@ -728,6 +811,17 @@ int mppib_destroy(mppib_engine* e)
   for (int i = 0; i < 4; i++)
     if (e->ev[i])
       cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 2; i++)
+  {
+    if (e->ev_k1_done[i])
+      cudaEventDestroy(e->ev_k1_done[i]);
+    if (e->ev_gen_done[i])
+      cudaEventDestroy(e->ev_gen_done[i]);
+  }
+  if (e->ev_last_gen)
+    cudaEventDestroy(e->ev_last_gen);
+  if (e->side_stream)
+    cudaStreamDestroy(e->side_stream);
   if (e->own_stream && e->stream)
     cudaStreamDestroy(e->stream);
   cudaGetLastError();
@@ -854,13 +948,16 @@ int mppib_seed(mppib_engine* e, unsigned long long seed, unsigned long long offs
   if (!e)
     return fail(MPPIB_ERR_INVALID_ARG, "null engine");
   CUDA_TRY(cudaSetDevice(e->desc.device));
+  if (e->side_stream)
+    CUDA_TRY(cudaStreamSynchronize(e->side_stream));  // a prefetch may still be using the generator
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
   CURAND_TRY(curandSetPseudoRandomGeneratorSeed(e->gen, seed));
   CURAND_TRY(curandSetGeneratorOffset(e->gen, 0ULL));
   e->seed = seed;
   e->rng_offset = offset;
-  e->xw_dirty = true;
-  // the generator sits at element 0; it is "positioned" only if that is where the next local draw starts
-  e->rng_positioned = (offset == 0 && e->desc.world_size == 1);
+  e->xw_pos = mppib_engine::kNoPos;
+  e->curand_pos = 0;  // the library generator sits at element 0 of the new stream
+  e->prefetch_valid = false;
   return MPPIB_OK;
 }
 
@@ -877,9 +974,8 @@ int mppib_burn_draws(mppib_engine* e, int n)
   if (!e || n < 0)
     return fail(MPPIB_ERR_INVALID_ARG, "bad argument");
   // skipping is free for a counter-positioned stream: just move the absolute offset
-  e->rng_offset += (unsigned long long)n * e->N * e->TC;
-  e->rng_positioned = false;
-  e->xw_dirty = true;
+  e->rng_offset += (unsigned long long)n * e->N * e->TC;  // generators are re-positioned lazily by gen_draw
+  e->prefetch_valid = false;
   return MPPIB_OK;
 }
 
@@ -983,6 +1079,9 @@ static int enqueue_solve(mppib_engine* e, const float* x0, const float* U_in, in
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[1], e->stream));
   rc = e->launch_rollout(*e, x0, U_in, optimization_stride, iteration_num);
+  if (rc != MPPIB_OK)
+    return rc;
+  rc = prefetch_next(*e);
   if (rc != MPPIB_OK)
     return rc;
   if (e->timing)

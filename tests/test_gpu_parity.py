@@ -155,6 +155,38 @@ def test_rank_slices_tile_the_global_stream():
     e.close()
 
 
+def test_noise_prefetch_is_transparent():
+    """The draw for solve s+1 runs one solve ahead on a side stream; results must be bit-identical to drawing inline,
+    through sequences of solves, async pipelines, re-seeding, burn_draws and interleaved hook calls."""
+    w = W.cartpole(8192, 100)
+    a = w.make_engine()
+    b = w.make_engine(flags=H.FLAG_NO_PREFETCH)
+    U = [w.U0.copy(), w.U0.copy()]
+    for it in range(6):
+        for i, e in enumerate((a, b)):
+            U[i], _ = e.solve(w.x0, U[i])
+        np.testing.assert_array_equal(U[0], U[1], err_msg=f"solve {it}")
+        np.testing.assert_array_equal(a.get_noise(), b.get_noise())
+    assert a.rng_offset() == b.rng_offset()
+    for e in (a, b):
+        e.burn_draws(2)
+    ra, rb = a.solve(w.x0, U[0]), b.solve(w.x0, U[1])
+    np.testing.assert_array_equal(ra[0], rb[0])
+    for e in (a, b):
+        e.seed(99, 0)
+        e.draw_noise()  # hook call in between
+    np.testing.assert_array_equal(a.get_noise(), b.get_noise())
+    x0, U0 = np.ascontiguousarray(w.x0), np.ascontiguousarray(w.U0)
+    for e in (a, b):
+        for _ in range(5):
+            e.solve_async(x0, U0)
+    ra, rb = a.solve_wait(), b.solve_wait()
+    np.testing.assert_array_equal(ra[0], rb[0])
+    assert ra[1] == rb[1] and a.rng_offset() == b.rng_offset()
+    a.close()
+    b.close()
+
+
 # ---- K1: rollout kernel vs launchCPURolloutKernel -----------------------------------------------------------------
 def _rollout_kernel_test_workload(N=2048, T=100):
     # tests/mppi_core/rollout_kernel_tests.cu:114-167: dt 0.01, lambda 0.5, alpha 0.001, sigma 0.4, cost (100,10,200,20)
