@@ -7,6 +7,7 @@
  *   mppib_host_slide_controls       Controller::slideControlSequenceHelper      controller.cuh:588-600
  *   mppib_host_output_trajectory    Controller::computeOutputTrajectoryHelper   controller.cuh:643-663
  *   mppib_host_free_energy          mppi::kernels::computeFreeEnergy      include/mppi/core/mppi_common.cu:1065-1081
+ *   mppib_host_merge_records        (no reference counterpart: the log-sum-exp merge of rollout shards)
  * Arrays: u / history are [T][C] / [2][C] (== Eigen C x T / C x 2 column-major), states [T][S], outputs [T][O].
  */
 #ifndef MPPI_B200_HOST_TWINS_H_
@@ -24,6 +25,9 @@ void mppib_host_slide_controls(float* u, int steps, int T, int C, const float* z
 int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x0,
                                  const float* u, int T, float dt, float* states, float* outputs);
 void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float lambda, float* out3);
+/* CPU twin of the K2 merge (csrc/combine_kernel.cuh): records [nrec][D][pstride] = (beta, eta, sum w^2, -, V[TC]). */
+int mppib_host_merge_records(const float* records, int nrec, int D, int TC, int pstride, float lambda, int normalize,
+                             float* out);
 #ifdef __cplusplus
 }
 #endif

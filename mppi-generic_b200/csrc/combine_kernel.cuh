@@ -26,7 +26,8 @@ constexpr int kCombineGroups = 16;   // 16 warps split the records
 constexpr int kCombineMaxRecords = 4096;
 
 __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
-    combine_kernel(const float* __restrict__ records,  // [nrec][D][pstride]
+    combine_kernel(const float* __restrict__ records,   // [nrec][D][pstride]  (V at [kPartialHeader..))
+                   const float4* __restrict__ headers,  // [nrec][D] (beta_b, eta_b, sum w^2_b, -)
                    int nrec, int D, int TC, int pstride, float lambda_inv, int normalize,
                    float* __restrict__ out,    // [D][pstride] (device)
                    float* __restrict__ out2)   // optional second copy (mapped host result), may be nullptr
@@ -45,13 +46,17 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
   const float* rec = records + (size_t)d * pstride;
   const size_t rstride = (size_t)D * pstride;
 
-  // 1. global baseline: first-minimum VALUE == plain min (mppi_common.cu:858-900)
+  pdl_wait_prerequisites();  // launched with programmatic stream serialisation: K1's results are complete from here on
+
+  // 1. global baseline: first-minimum VALUE == plain min (mppi_common.cu:858-900). Headers are a compact float4 array.
   float m = INFINITY;
-  for (int b = tid; b < nrec; b += blockDim.x)
+  float4 h[(kCombineMaxRecords + kCombineCols * kCombineGroups - 1) / (kCombineCols * kCombineGroups)];
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(h) / sizeof(h[0])); i++)
   {
-    const float bb = rec[b * rstride];
-    scale_sh[b] = bb;  // stash beta_b
-    m = fminf(m, bb);
+    const int b = tid + i * (int)blockDim.x;
+    h[i] = (b < nrec) ? headers[(size_t)b * D + d] : make_float4(INFINITY, 0.0f, 0.0f, 0.0f);
+    m = fminf(m, h[i].x);
   }
   m = warp_min(m);
   if (lane == 0)
@@ -69,12 +74,17 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
 
   // 2. per-record rescale factors, normaliser (double accumulate, mppi_common.cu:1055-1063) and sum of squares
   double eta = 0.0, w2 = 0.0;
-  for (int b = tid; b < nrec; b += blockDim.x)
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(h) / sizeof(h[0])); i++)
   {
-    const float s = expf(-lambda_inv * (scale_sh[b] - beta));
-    scale_sh[b] = s;
-    eta += (double)s * (double)rec[b * rstride + 1];
-    w2 += (double)s * (double)s * (double)rec[b * rstride + 2];
+    const int b = tid + i * (int)blockDim.x;
+    if (b < nrec)
+    {
+      const float s = expf(-lambda_inv * (h[i].x - beta));
+      scale_sh[b] = s;
+      eta += (double)s * (double)h[i].y;
+      w2 += (double)s * (double)s * (double)h[i].z;
+    }
   }
   eta = warp_sum(eta);
   w2 = warp_sum(w2);
@@ -149,6 +159,18 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
         o2[3] = 0.0f;
       }
     }
+  }
+}
+
+// rank record (output of a non-normalising combine) -> compact header, for the cross-rank merge after the all-gather
+__global__ void record_headers_kernel(const float* __restrict__ records, int nrec, int D, int pstride,
+                                      float4* __restrict__ headers)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrec * D)
+  {
+    const float* r = records + (size_t)i * pstride;
+    headers[i] = make_float4(r[0], r[1], r[2], 0.0f);
   }
 }
 

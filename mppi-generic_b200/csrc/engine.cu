@@ -117,6 +117,7 @@ struct mppib_engine
   int bx = 64, grid = 0;
   uint32_t smem_bytes = 0;
   bool use_tma = false;
+  bool use_pdl = true;
   bool writeback = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -169,6 +170,8 @@ struct mppib_engine
   float* eps_d = nullptr;        // [n_local][T][C]
   float* costs_d = nullptr;      // [D][n_local]
   float* partials_d = nullptr;   // [grid][D][pstride]
+  float4* headers_d = nullptr;   // [grid][D] compact (beta, eta, sum w^2)
+  float4* gather_hdr_d = nullptr;  // [world][D]
   float* controls_d = nullptr;   // optional [D][n_local][T][C]
   float* rank_rec_d = nullptr;   // [D][pstride] this rank's record (world > 1)
   float* gather_d = nullptr;     // [world][D][pstride]
@@ -273,6 +276,7 @@ struct Pair
     a.eps = e.eps_d;
     a.costs = e.costs_d;
     a.partials = e.partials_d;
+    a.headers = e.headers_d;
     a.controls_out = e.writeback ? e.controls_d : nullptr;
     a.n_local = e.n_local;
     a.n_offset = e.n_offset;
@@ -446,8 +450,6 @@ static int prefetch_next(mppib_engine& e)
 {
   if (!e.prefetch_enabled)
     return MPPIB_OK;
-  CUDA_TRY(cudaEventRecord(e.ev_k1_done[e.cur_buf], e.stream));
-  e.k1_recorded[e.cur_buf] = true;
   const int nb = e.cur_buf ^ 1;
   if (e.k1_recorded[nb])
     CUDA_TRY(cudaStreamWaitEvent(e.side_stream, e.ev_k1_done[nb], 0));
@@ -461,30 +463,46 @@ static int prefetch_next(mppib_engine& e)
   return MPPIB_OK;
 }
 
-static int launch_combine(mppib_engine& e)
+// K2 launch. `pdl` = programmatic dependent launch: the grid may start while the preceding kernel on the stream (K1) is
+// still running and blocks at griddepcontrol.wait until that kernel has completed — hides K2's launch latency.
+static int launch_combine_one(mppib_engine& e, const float* records, const float4* headers, int nrec, int normalize,
+                              float* out, float* out2, bool pdl)
 {
-  const dim3 grid((e.TC + kCombineCols - 1) / kCombineCols, e.D);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((e.TC + kCombineCols - 1) / kCombineCols, e.D, 1);
+  cfg.blockDim = dim3(kCombineCols * kCombineGroups, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = e.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   const float lambda_inv = (float)(1.0 / e.lambda);
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, combine_kernel, records, headers, nrec, e.D, e.TC, e.pstride, lambda_inv, normalize,
+                              out, out2));
+  return MPPIB_OK;
+}
+
+static int launch_combine(mppib_engine& e, bool after_k1)
+{
+  const bool pdl = after_k1 && e.use_pdl;
   if (e.desc.world_size == 1 || !e.comm)
-  {
-    combine_kernel<<<grid, kCombineCols * kCombineGroups, 0, e.stream>>>(e.partials_d, e.grid, e.D, e.TC, e.pstride,
-                                                                        lambda_inv, 1, e.result_d, e.result_h_dev);
-    CUDA_TRY(cudaGetLastError());
-    return MPPIB_OK;
-  }
+    return launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, e.result_h_dev, pdl);
   // rank record (un-normalised) -> all-gather -> merge of the world_size records (normalised)
-  combine_kernel<<<grid, kCombineCols * kCombineGroups, 0, e.stream>>>(e.partials_d, e.grid, e.D, e.TC, e.pstride,
-                                                                      lambda_inv, 0, e.rank_rec_d, nullptr);
-  CUDA_TRY(cudaGetLastError());
+  int rc = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 0, e.rank_rec_d, nullptr, pdl);
+  if (rc != MPPIB_OK)
+    return rc;
   const size_t rec_floats = (size_t)e.D * e.pstride;
-  int rc = g_nccl.AllGather(e.rank_rec_d, e.gather_d, rec_floats, kNcclFloat, e.comm, e.stream);
+  rc = g_nccl.AllGather(e.rank_rec_d, e.gather_d, rec_floats, kNcclFloat, e.comm, e.stream);
   if (rc != 0)
     return fail(MPPIB_ERR_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-  combine_kernel<<<grid, kCombineCols * kCombineGroups, 0, e.stream>>>(e.gather_d, e.desc.world_size, e.D, e.TC,
-                                                                      e.pstride, lambda_inv, 1, e.result_d,
-                                                                      e.result_h_dev);
+  const int nh = e.desc.world_size * e.D;
+  record_headers_kernel<<<(nh + 63) / 64, 64, 0, e.stream>>>(e.gather_d, e.desc.world_size, e.D, e.pstride,
+                                                            e.gather_hdr_d);
   CUDA_TRY(cudaGetLastError());
-  return MPPIB_OK;
+  return launch_combine_one(e, e.gather_d, e.gather_hdr_d, e.desc.world_size, 1, e.result_d, e.result_h_dev, false);
 }
 
 static int check_ready(mppib_engine* e)
@@ -610,6 +628,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->dyn_shared_floats = entry->dyn_shared_floats;
   e->cost_shared_floats = entry->cost_shared_floats;
   e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
+  e->use_pdl = !getenv("MPPIB_NO_PDL");
 
   auto bail = [&](int rc) {
     mppib_destroy(e);
@@ -700,6 +719,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   }
   CUDA_TRY_B(cudaMalloc(&e->costs_d, (size_t)e->D * e->n_local * sizeof(float)));
   CUDA_TRY_B(cudaMalloc(&e->partials_d, (size_t)e->grid * e->D * e->pstride * sizeof(float)));
+  CUDA_TRY_B(cudaMalloc(&e->headers_d, (size_t)e->grid * e->D * sizeof(float4)));
   CUDA_TRY_B(cudaMalloc(&e->result_d, (size_t)e->D * e->pstride * sizeof(float)));
   CUDA_TRY_B(cudaHostAlloc(&e->result_h, (size_t)e->D * e->pstride * sizeof(float), cudaHostAllocMapped));
   memset(e->result_h, 0, (size_t)e->D * e->pstride * sizeof(float));
@@ -710,6 +730,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   {
     CUDA_TRY_B(cudaMalloc(&e->rank_rec_d, (size_t)e->D * e->pstride * sizeof(float)));
     CUDA_TRY_B(cudaMalloc(&e->gather_d, (size_t)world * e->D * e->pstride * sizeof(float)));
+    CUDA_TRY_B(cudaMalloc(&e->gather_hdr_d, (size_t)world * e->D * sizeof(float4)));
   }
   for (int i = 0; i < 4; i++)
     CUDA_TRY_B(cudaEventCreate(&e->ev[i]));
@@ -798,6 +819,8 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->noise_alloc2);
   cudaFree(e->costs_d);
   cudaFree(e->partials_d);
+  cudaFree(e->headers_d);
+  cudaFree(e->gather_hdr_d);
   cudaFree(e->controls_d);
   cudaFree(e->rank_rec_d);
   cudaFree(e->gather_d);
@@ -1058,7 +1081,7 @@ int mppib_reduce_only(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
   if (!e->solved_once)
     return fail(MPPIB_ERR_STATE, "no rollout has been run yet");
   CUDA_TRY(cudaSetDevice(e->desc.device));
-  rc = launch_combine(*e);
+  rc = launch_combine(*e, false);
   if (rc != MPPIB_OK)
     return rc;
   CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -1086,9 +1109,14 @@ static int enqueue_solve(mppib_engine* e, const float* x0, const float* U_in, in
     return rc;
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[2], e->stream));
-  rc = launch_combine(*e);
+  rc = launch_combine(*e, /*after_k1=*/!e->timing);  // timing mode records an event between K1 and K2: no PDL then
   if (rc != MPPIB_OK)
     return rc;
+  if (e->prefetch_enabled)
+  {  // "the K1 that read eps_buf[cur_buf] is done" — recorded after K2 so nothing sits between K1 and its PDL dependent
+    CUDA_TRY(cudaEventRecord(e->ev_k1_done[e->cur_buf], e->stream));
+    e->k1_recorded[e->cur_buf] = true;
+  }
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[3], e->stream));
   e->pending++;

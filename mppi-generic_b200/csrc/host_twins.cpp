@@ -253,4 +253,43 @@ void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float
   out3[2] = lambda * (weird_term + 0.5f * weird_term * weird_term);
 }
 
+
+int mppib_host_merge_records(const float* records, int nrec, int D, int TC, int pstride, float lambda, int normalize,
+                             float* out)
+{
+  // CPU twin of combine_kernel (csrc/combine_kernel.cuh): merges per-block or per-rank records
+  // [beta_b, eta_b, sum w^2_b, -, V_b[TC]] with s_b = expf(-(beta_b - beta)/lambda). Used by launchers and tests that
+  // reason about rollout sharding without a GPU; the engine itself always merges on the device.
+  if (!records || !out || nrec <= 0 || D <= 0 || TC <= 0 || pstride < 4 + TC || !(lambda > 0.0f))
+    return MPPIB_ERR_INVALID_ARG;
+  const float lambda_inv = (float)(1.0 / lambda);
+  for (int d = 0; d < D; d++)
+  {
+    const float* rec = records + (size_t)d * pstride;
+    const size_t rstride = (size_t)D * pstride;
+    float beta = rec[0];
+    for (int b = 1; b < nrec; b++)
+      beta = fminf(beta, rec[b * rstride]);
+    double eta = 0.0, w2 = 0.0;
+    std::vector<float> acc(TC, 0.0f);
+    for (int b = 0; b < nrec; b++)
+    {
+      const float* r = rec + b * rstride;
+      const float s = expf(-lambda_inv * (r[0] - beta));
+      eta += (double)s * (double)r[1];
+      w2 += (double)s * (double)s * (double)r[2];
+      for (int c = 0; c < TC; c++)
+        acc[c] = fmaf(s, r[4 + c], acc[c]);
+    }
+    float* o = out + (size_t)d * pstride;
+    o[0] = beta;
+    o[1] = (float)eta;
+    o[2] = (float)w2;
+    o[3] = 0.0f;
+    for (int c = 0; c < TC; c++)
+      o[4 + c] = normalize ? acc[c] / (float)eta : acc[c];
+  }
+  return MPPIB_OK;
+}
+
 }  // extern "C"

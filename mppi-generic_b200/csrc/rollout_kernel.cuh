@@ -54,7 +54,8 @@ struct RolloutArgs
   SamplerArgs samp;
   const float* eps;     // raw N(0,1) [n_local][T][C]
   float* costs;         // [D][n_local]
-  float* partials;      // [gridDim.x][D][pstride]
+  float* partials;      // [gridDim.x][D][pstride]   V_b at [kPartialHeader..)
+  float4* headers;      // [gridDim.x][D]  (beta_b, eta_b, sum w^2_b, 0): compact copy for K2's first pass
   float* controls_out;  // optional [D][n_local][T][C] (MPPIB_FLAG_WRITEBACK_CONTROLS), else nullptr
   int n_local;          // rollouts on this rank
   int n_offset;         // global index of local rollout 0 (rank * N / world)
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   float* red_s = reinterpret_cast<float*>(smem + L.scratch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
+  pdl_launch_dependents();           // K2 may be scheduled now; it waits for this grid to finish before reading
   const int row0 = blockIdx.x * bx;  // first local rollout of this block
   const int n_loc = row0 + tid;
   const bool valid = n_loc < args.n_local;
@@ -348,11 +350,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         eta_b += red_s[32 + i];
         w2_b += red_s[64 + i];
       }
-      float* hdr = args.partials + ((size_t)blockIdx.x * D + d) * args.pstride;
-      hdr[0] = beta_b;
-      hdr[1] = eta_b;
-      hdr[2] = w2_b;
-      hdr[3] = 0.0f;
+      args.headers[(size_t)blockIdx.x * D + d] = make_float4(beta_b, eta_b, w2_b, 0.0f);
     }
     __syncthreads();  // red_s reused by the next distribution
   }

@@ -129,6 +129,7 @@ ABI_SYMBOLS = [
     "mppib_local_rollouts", "mppib_strerror", "mppib_last_error", "mppib_version",
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
+    "mppib_host_merge_records",
 ]
 
 _lib = None
@@ -181,6 +182,7 @@ def lib() -> C.CDLL:
     L.mppib_host_output_trajectory.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp]
     L.mppib_host_free_energy.argtypes = [C.POINTER(SolveStats), C.c_int, C.c_float, vp]
     L.mppib_host_free_energy.restype = None
+    L.mppib_host_merge_records.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]
     _lib = L
     return L
 
@@ -678,6 +680,16 @@ class _Controller:
         lib().mppib_host_free_energy(C.byref(st), self.num_rollouts_, C.c_float(self.lambda_), _ptr(out))
         return {"freeEnergyMean": float(out[0]), "freeEnergyVariance": float(out[1]),
                 "freeEnergyModifiedVariance": float(out[2])}
+
+
+def merge_records(records: np.ndarray, lambda_: float, normalize: bool = True) -> np.ndarray:
+    """records [nrec][D][pstride] -> merged [D][pstride] with the engine's K2 arithmetic (CPU twin, host_twins.h)."""
+    r = _f32(records)
+    nrec, D, pstride = r.shape
+    out = np.zeros((D, pstride), np.float32)
+    _check(lib().mppib_host_merge_records(_ptr(r), nrec, D, pstride - 4, pstride, C.c_float(lambda_), int(normalize),
+                                          _ptr(out)))
+    return out
 
 
 class VanillaMPPIController(_Controller):
