@@ -15,6 +15,7 @@
 #include <curand.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -118,6 +119,7 @@ struct mppib_engine
   uint32_t smem_bytes = 0;
   bool use_tma = false;
   bool use_pdl = true;
+  bool mapped_result = true;  // K2 writes the result record straight into mapped pinned host memory
   bool writeback = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -488,8 +490,15 @@ static int launch_combine_one(mppib_engine& e, const float* records, const float
 static int launch_combine(mppib_engine& e, bool after_k1)
 {
   const bool pdl = after_k1 && e.use_pdl;
+  float* host_copy = e.mapped_result ? e.result_h_dev : nullptr;
   if (e.desc.world_size == 1 || !e.comm)
-    return launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, e.result_h_dev, pdl);
+  {
+    int rc1 = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, host_copy, pdl);
+    if (rc1 == MPPIB_OK && !e.mapped_result)
+      CUDA_TRY(cudaMemcpyAsync(e.result_h, e.result_d, (size_t)e.D * e.pstride * sizeof(float), cudaMemcpyDeviceToHost,
+                               e.stream));
+    return rc1;
+  }
   // rank record (un-normalised) -> all-gather -> merge of the world_size records (normalised)
   int rc = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 0, e.rank_rec_d, nullptr, pdl);
   if (rc != MPPIB_OK)
@@ -502,7 +511,11 @@ static int launch_combine(mppib_engine& e, bool after_k1)
   record_headers_kernel<<<(nh + 63) / 64, 64, 0, e.stream>>>(e.gather_d, e.desc.world_size, e.D, e.pstride,
                                                             e.gather_hdr_d);
   CUDA_TRY(cudaGetLastError());
-  return launch_combine_one(e, e.gather_d, e.gather_hdr_d, e.desc.world_size, 1, e.result_d, e.result_h_dev, false);
+  rc = launch_combine_one(e, e.gather_d, e.gather_hdr_d, e.desc.world_size, 1, e.result_d, host_copy, false);
+  if (rc == MPPIB_OK && !e.mapped_result)
+    CUDA_TRY(cudaMemcpyAsync(e.result_h, e.result_d, (size_t)e.D * e.pstride * sizeof(float), cudaMemcpyDeviceToHost,
+                             e.stream));
+  return rc;
 }
 
 static int check_ready(mppib_engine* e)
@@ -629,6 +642,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->cost_shared_floats = entry->cost_shared_floats;
   e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
   e->use_pdl = !getenv("MPPIB_NO_PDL");
+  e->mapped_result = !getenv("MPPIB_NO_MAPPED_RESULT");
 
   auto bail = [&](int rc) {
     mppib_destroy(e);
@@ -648,24 +662,52 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   if (e->n_local <= 0)
     return bail(fail(MPPIB_ERR_INVALID_ARG, "rank %d of %d has no rollouts (N=%d)", desc->rank, world, e->N));
 
-  // launch geometry: one thread per sample; BX samples per CTA, whole-horizon noise tile resident in shared memory
-  int bx = 64;
+  // launch geometry: one thread per sample; BX samples per CTA, whole-horizon noise tile resident in shared memory.
+  // The rollout is bound by the T-step dependency chain, so a CTA takes the same time whatever its width: the block
+  // width is chosen to put every CTA in ONE wave (no tail wave running at a fraction of the chip), preferring the
+  // narrowest such width (more SMs busy, fewer warps contending per scheduler); 64 if several waves are unavoidable.
+  int max_smem = 0, num_sms = 0, smem_per_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, desc->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, desc->device));
+  auto smem_for = [&](int b) {
+    return (int)rollout_smem_layout(b, e->nchunks, e->D, e->TC, e->dyn_shared_floats, e->cost_shared_floats(e->T)).total;
+  };
+  int bx = 0;
   if (const char* s = getenv("MPPIB_BX"))
+  {
     bx = atoi(s);
-  if (bx < 32 || bx > 256 || (bx % 32) != 0)
-    bx = 64;
+    if (bx < 32 || bx > 256 || (bx % 32) != 0)
+      bx = 0;
+  }
+  if (bx == 0)
+  {
+    int best = 0;
+    long best_waves = 1L << 40;
+    for (int cand = 64; cand <= entry->max_block_threads; cand += 32)
+    {
+      const int sm = smem_for(cand);
+      if (sm > max_smem)
+        break;
+      // +1 KB per CTA is what the hardware reserves out of the SM's shared memory
+      const int per_sm = std::min(std::min(smem_per_sm / (sm + 1024), 2048 / cand), 32);
+      if (per_sm < 1)
+        break;
+      const long blocks = (e->n_local + cand - 1) / cand;
+      const long waves = (blocks + (long)per_sm * num_sms - 1) / ((long)per_sm * num_sms);
+      if (waves < best_waves)
+      {
+        best_waves = waves;
+        best = cand;
+      }
+    }
+    bx = best ? best : 32;
+  }
   if (bx > entry->max_block_threads)
     bx = entry->max_block_threads;
-  int max_smem = 0;
-  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
-  for (;;)
-  {
-    e->smem_bytes =
-        rollout_smem_layout(bx, e->nchunks, e->D, e->TC, e->dyn_shared_floats, e->cost_shared_floats(e->T)).total;
-    if ((int)e->smem_bytes <= max_smem || bx == 32)
-      break;
-    bx /= 2;
-  }
+  while (smem_for(bx) > max_smem && bx > 32)
+    bx -= 32;
+  e->smem_bytes = (uint32_t)smem_for(bx);
   if ((int)e->smem_bytes > max_smem)
     return bail(fail(MPPIB_ERR_SMEM, "noise tile needs %u B of shared memory, device allows %d", e->smem_bytes,
                      max_smem));

@@ -164,7 +164,7 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
   static constexpr int L1_W = 0, L1_B = L1_W + 6 * 32, L2_W = L1_B + 32, L2_B = L2_W + 32 * 32, L3_W = L2_B + 32,
                        L3_B = L3_W + 32 * 4;
   static constexpr int SHARED_FLOATS = L3_B + 4;  // 1412
-  static constexpr int MAX_BLOCK_THREADS = 128;   // lets ptxas use up to 255 registers: the forward pass is register-tiled
+  static constexpr int MAX_BLOCK_THREADS = 256;   // 86 registers/thread: up to 7 warps of samples share one SM's tile
   static constexpr bool UNROLL_STEPS = false;     // one copy of the 1344-FMA step body
   struct Aux
   {
