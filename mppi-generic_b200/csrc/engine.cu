@@ -120,6 +120,11 @@ struct mppib_engine
   bool use_tma = false;
   bool use_pdl = true;
   bool mapped_result = true;  // K2 writes the result record straight into mapped pinned host memory
+  bool spin_wait = true;      // the host waits for the solve by polling a mapped flag K2's last block sets
+  unsigned* k2_counter_d = nullptr;
+  volatile unsigned* done_flag_h = nullptr;
+  unsigned* done_flag_dev = nullptr;
+  unsigned solve_seq = 0;
   bool writeback = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -468,8 +473,16 @@ static int prefetch_next(mppib_engine& e)
 // K2 launch. `pdl` = programmatic dependent launch: the grid may start while the preceding kernel on the stream (K1) is
 // still running and blocks at griddepcontrol.wait until that kernel has completed — hides K2's launch latency.
 static int launch_combine_one(mppib_engine& e, const float* records, const float4* headers, int nrec, int normalize,
-                              float* out, float* out2, bool pdl)
+                              float* out, float* out2, bool pdl, bool final_stage = false)
 {
+  unsigned* counter = e.k2_counter_d;
+  volatile unsigned* flag = nullptr;
+  unsigned seq = 0;
+  if (final_stage && e.spin_wait && out2 != nullptr)
+  {
+    flag = e.done_flag_dev;
+    seq = ++e.solve_seq;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((e.TC + kCombineCols - 1) / kCombineCols, e.D, 1);
@@ -483,7 +496,7 @@ static int launch_combine_one(mppib_engine& e, const float* records, const float
   cfg.numAttrs = pdl ? 1 : 0;
   const float lambda_inv = (float)(1.0 / e.lambda);
   CUDA_TRY(cudaLaunchKernelEx(&cfg, combine_kernel, records, headers, nrec, e.D, e.TC, e.pstride, lambda_inv, normalize,
-                              out, out2));
+                              out, out2, counter, flag, seq));
   return MPPIB_OK;
 }
 
@@ -493,7 +506,7 @@ static int launch_combine(mppib_engine& e, bool after_k1)
   float* host_copy = e.mapped_result ? e.result_h_dev : nullptr;
   if (e.desc.world_size == 1 || !e.comm)
   {
-    int rc1 = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, host_copy, pdl);
+    int rc1 = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, host_copy, pdl, true);
     if (rc1 == MPPIB_OK && !e.mapped_result)
       CUDA_TRY(cudaMemcpyAsync(e.result_h, e.result_d, (size_t)e.D * e.pstride * sizeof(float), cudaMemcpyDeviceToHost,
                                e.stream));
@@ -511,7 +524,7 @@ static int launch_combine(mppib_engine& e, bool after_k1)
   record_headers_kernel<<<(nh + 63) / 64, 64, 0, e.stream>>>(e.gather_d, e.desc.world_size, e.D, e.pstride,
                                                             e.gather_hdr_d);
   CUDA_TRY(cudaGetLastError());
-  rc = launch_combine_one(e, e.gather_d, e.gather_hdr_d, e.desc.world_size, 1, e.result_d, host_copy, false);
+  rc = launch_combine_one(e, e.gather_d, e.gather_hdr_d, e.desc.world_size, 1, e.result_d, host_copy, false, true);
   if (rc == MPPIB_OK && !e.mapped_result)
     CUDA_TRY(cudaMemcpyAsync(e.result_h, e.result_d, (size_t)e.D * e.pstride * sizeof(float), cudaMemcpyDeviceToHost,
                              e.stream));
@@ -643,6 +656,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
   e->use_pdl = !getenv("MPPIB_NO_PDL");
   e->mapped_result = !getenv("MPPIB_NO_MAPPED_RESULT");
+  e->spin_wait = e->mapped_result && !getenv("MPPIB_NO_SPIN_WAIT");
 
   auto bail = [&](int rc) {
     mppib_destroy(e);
@@ -766,6 +780,15 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   CUDA_TRY_B(cudaHostAlloc(&e->result_h, (size_t)e->D * e->pstride * sizeof(float), cudaHostAllocMapped));
   memset(e->result_h, 0, (size_t)e->D * e->pstride * sizeof(float));
   CUDA_TRY_B(cudaHostGetDevicePointer(&e->result_h_dev, e->result_h, 0));
+  CUDA_TRY_B(cudaMalloc(&e->k2_counter_d, sizeof(unsigned)));
+  CUDA_TRY_B(cudaMemsetAsync(e->k2_counter_d, 0, sizeof(unsigned), e->stream));
+  {
+    unsigned* f = nullptr;
+    CUDA_TRY_B(cudaHostAlloc(&f, 64, cudaHostAllocMapped));
+    *f = 0u;
+    e->done_flag_h = f;
+    CUDA_TRY_B(cudaHostGetDevicePointer(&e->done_flag_dev, f, 0));
+  }
   if (e->writeback)
     CUDA_TRY_B(cudaMalloc(&e->controls_d, (size_t)e->D * noise_floats * sizeof(float)));
   if (world > 1)
@@ -873,6 +896,9 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->xw_tables_d);
   if (e->result_h)
     cudaFreeHost(e->result_h);
+  if (e->done_flag_h)
+    cudaFreeHost((void*)e->done_flag_h);
+  cudaFree(e->k2_counter_d);
   for (int i = 0; i < 4; i++)
     if (e->ev[i])
       cudaEventDestroy(e->ev[i]);
@@ -1165,9 +1191,43 @@ static int enqueue_solve(mppib_engine* e, const float* x0, const float* U_in, in
   return MPPIB_OK;
 }
 
+// Blocks until the last enqueued solve is complete. Fast path: poll the mapped word K2's last block writes after the
+// result record (the record travels the same way, so it is visible when the flag is); every few thousand polls the
+// stream is queried so that a failed launch cannot spin forever, and timing mode uses a full synchronize (events).
+static int wait_for_stream(mppib_engine* e)
+{
+  if (e->spin_wait && !e->timing && e->solve_seq != 0)
+  {
+    const unsigned want = e->solve_seq;
+    for (unsigned spins = 1;; spins++)
+    {
+      if (*e->done_flag_h == want)
+        return MPPIB_OK;
+      if ((spins & 0x3fff) == 0)
+      {
+        cudaError_t q = cudaStreamQuery(e->stream);
+        if (q == cudaSuccess)
+          break;  // stream drained (the flag write is then visible as well)
+        if (q != cudaErrorNotReady)
+        {
+          cudaGetLastError();
+          return fail(MPPIB_ERR_CUDA, "solve failed: %s", cudaGetErrorString(q));
+        }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
 static int wait_solve(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
 {
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  int rcw = wait_for_stream(e);
+  if (rcw != MPPIB_OK)
+    return rcw;
   e->pending = 0;
   e->timing_valid = e->timing;
   if (e->timing)

@@ -217,6 +217,21 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
     state_der[2] = -state[6];
   }
 
+  // One weight row (all OUT outputs of input k) as OUT/4 broadcast LDS.128. `volatile` keeps the loads in program
+  // order, which is how the software pipeline below is expressed: row k+1 is requested BEFORE the FFMA2s of row k, so the
+  // ~30-cycle shared-memory latency is covered by arithmetic even when a scheduler holds a single warp (ptxas otherwise
+  // funnels every load through one register quad and stalls on each: profiles/r01_autorally_k1_notes.md).
+  template <int OUT>
+  __device__ static __forceinline__ void load_row(float4 (&w)[OUT / 4], const float* row)
+  {
+    const uint32_t a = smem_u32(row);
+#pragma unroll
+    for (int j4 = 0; j4 < OUT / 4; j4++)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(w[j4].x), "=f"(w[j4].y), "=f"(w[j4].z), "=f"(w[j4].w)
+                   : "r"(a + 16u * j4));
+  }
+
   template <int IN, int OUT, bool TANH>
   __device__ static __forceinline__ void layer(const float* __restrict__ WT, const float* __restrict__ b,
                                                const float* in, float* out)
@@ -225,24 +240,32 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
 #pragma unroll
     for (int j = 0; j < OUT / 2; j++)
       acc[j] = make_float2(0.0f, 0.0f);
+    float4 w[OUT / 4], wn[OUT / 4];
+    load_row<OUT>(w, WT);
 #pragma unroll
     for (int k = 0; k < IN; k++)
     {
+      if (k + 1 < IN)
+        load_row<OUT>(wn, WT + (k + 1) * OUT);
+      else
+        load_row<OUT>(wn, b);  // the bias row rides the same pipeline
       const float2 xk = make_float2(in[k], in[k]);
 #pragma unroll
       for (int j4 = 0; j4 < OUT / 4; j4++)
       {
-        const float4 w = *reinterpret_cast<const float4*>(WT + k * OUT + 4 * j4);
-        acc[2 * j4] = __ffma2_rn(make_float2(w.x, w.y), xk, acc[2 * j4]);
-        acc[2 * j4 + 1] = __ffma2_rn(make_float2(w.z, w.w), xk, acc[2 * j4 + 1]);
+        acc[2 * j4] = __ffma2_rn(make_float2(w[j4].x, w[j4].y), xk, acc[2 * j4]);
+        acc[2 * j4 + 1] = __ffma2_rn(make_float2(w[j4].z, w[j4].w), xk, acc[2 * j4 + 1]);
       }
+#pragma unroll
+      for (int j4 = 0; j4 < OUT / 4; j4++)
+        w[j4] = wn[j4];
     }
+    // w now holds the bias row
 #pragma unroll
     for (int j4 = 0; j4 < OUT / 4; j4++)
     {
-      const float4 bb = *reinterpret_cast<const float4*>(b + 4 * j4);
-      const float t0 = acc[2 * j4].x + bb.x, t1 = acc[2 * j4].y + bb.y, t2 = acc[2 * j4 + 1].x + bb.z,
-                  t3 = acc[2 * j4 + 1].y + bb.w;
+      const float t0 = acc[2 * j4].x + w[j4].x, t1 = acc[2 * j4].y + w[j4].y, t2 = acc[2 * j4 + 1].x + w[j4].z,
+                  t3 = acc[2 * j4 + 1].y + w[j4].w;
       out[4 * j4 + 0] = TANH ? tanh_fast(t0) : t0;
       out[4 * j4 + 1] = TANH ? tanh_fast(t1) : t1;
       out[4 * j4 + 2] = TANH ? tanh_fast(t2) : t2;
