@@ -162,21 +162,22 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
         o2[3] = 0.0f;
       }
     }
-  }
-  // completion flag for the host's spin-wait: the last block to finish publishes `seq` after every block's host writes
-  if (done_flag != nullptr)
-  {
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0)
+    // completion flag for the host's spin-wait. Only this warp wrote output; its lane 0 publishes after a system fence
+    // (cumulative over the warp's writes through __syncwarp), and the last block to arrive sets the host word.
+    if (done_flag != nullptr)
     {
-      const unsigned total = gridDim.x * gridDim.y;
-      const unsigned prev = atomicAdd(block_counter, 1u);
-      if (prev == total - 1)
+      __syncwarp();
+      if (lane == 0)
       {
-        *block_counter = 0u;
         __threadfence_system();
-        *done_flag = seq;
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(block_counter, 1u);
+        if (prev == total - 1)
+        {
+          *block_counter = 0u;
+          __threadfence_system();
+          *done_flag = seq;
+        }
       }
     }
   }
