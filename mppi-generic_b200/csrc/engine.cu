@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/mppi_b200.h"
@@ -30,6 +31,7 @@
 #include "plugins/costs.cuh"
 #include "plugins/dynamics.cuh"
 #include "rollout_kernel.cuh"
+#include "rollout_kernel_nn_tc.cuh"
 
 namespace
 {
@@ -119,6 +121,7 @@ struct mppib_engine
   uint32_t smem_bytes = 0;
   bool use_tma = false;
   bool use_pdl = true;
+  bool nn_tc = false;  // Autorally pair: NN forward pass on tcgen05 tensor cores (rollout_kernel_nn_tc.cuh)
   bool mapped_result = true;  // K2 writes the result record straight into mapped pinned host memory
   bool spin_wait = true;      // the host waits for the solve by polling a mapped flag K2's last block sets
   unsigned* k2_counter_d = nullptr;
@@ -254,8 +257,23 @@ struct Pair
                                   (int)e.smem_bytes));
     return MPPIB_OK;
   }
+  static constexpr bool kHasTensorCoreVariant = std::is_same<DYN, plugins::AutorallyNNDynamics>::value &&
+                                                std::is_same<COST, plugins::ARStandardCost>::value;
   static int prepare(mppib_engine& e)
   {
+    if constexpr (kHasTensorCoreVariant)
+    {
+      if (e.nn_tc)
+      {
+        if (e.writeback)
+          CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)e.smem_bytes));
+        else
+          CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)e.smem_bytes));
+        return MPPIB_OK;
+      }
+    }
     if (e.D == 1)
       return e.writeback ? prepare_one<1, true>(e) : prepare_one<1, false>(e);
     return e.writeback ? prepare_one<2, true>(e) : prepare_one<2, false>(e);
@@ -298,7 +316,22 @@ struct Pair
     a.lambda_inv = (float)(1.0 / e.lambda);  // mppi_controller.cu:201-202: 1.0 / lambda in double, narrowed
     memcpy(a.x0, x0, sizeof(float) * e.D * e.S);
     memcpy(a.means, U_in, sizeof(float) * e.D * e.TC);
-    if (e.D == 1)
+    bool launched = false;
+    if constexpr (kHasTensorCoreVariant)
+    {
+      if (e.nn_tc)
+      {
+        if (e.writeback)
+          rollout_kernel_ar_tc<true><<<e.grid, nn_tc::kRows, e.smem_bytes, e.stream>>>(a, e.tmap);
+        else
+          rollout_kernel_ar_tc<false><<<e.grid, nn_tc::kRows, e.smem_bytes, e.stream>>>(a, e.tmap);
+        launched = true;
+      }
+    }
+    if (launched)
+    {
+    }
+    else if (e.D == 1)
     {
       if (e.writeback)
         rollout_kernel<DYN, COST, 1, true><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
@@ -656,7 +689,9 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
   e->use_pdl = !getenv("MPPIB_NO_PDL");
   e->mapped_result = !getenv("MPPIB_NO_MAPPED_RESULT");
-  e->spin_wait = e->mapped_result && !getenv("MPPIB_NO_SPIN_WAIT");
+  // measured on B200: polling a mapped flag is not faster than cudaStreamSynchronize (39.99 vs 40.33 us per cartpole
+  // solve) and costs K2 two system fences; off unless MPPIB_SPIN_WAIT is set
+  e->spin_wait = e->mapped_result && getenv("MPPIB_SPIN_WAIT") != nullptr;
 
   auto bail = [&](int rc) {
     mppib_destroy(e);
@@ -725,6 +760,18 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   if ((int)e->smem_bytes > max_smem)
     return bail(fail(MPPIB_ERR_SMEM, "noise tile needs %u B of shared memory, device allows %d", e->smem_bytes,
                      max_smem));
+  // tensor-core variant of the Autorally pair: fixed 128-sample CTAs (one UMMA tile), streaming noise ring
+  if (desc->dynamics_id == MPPIB_DYN_AUTORALLY_NN && desc->cost_id == MPPIB_COST_AR_STANDARD && e->D == 1 &&
+      (e->TC % 4) == 0 && !(desc->flags & (MPPIB_FLAG_NN_SIMT | MPPIB_FLAG_NO_TMA)) && !getenv("MPPIB_NN_SIMT") &&
+      !getenv("MPPIB_NO_TMA"))
+  {
+    e->nn_tc = true;
+    bx = nn_tc::kRows;
+    e->smem_bytes = nn_tc::layout(e->TC, e->T).total;
+    if ((int)e->smem_bytes > max_smem)
+      return bail(fail(MPPIB_ERR_SMEM, "tensor-core rollout needs %u B of shared memory, device allows %d",
+                       e->smem_bytes, max_smem));
+  }
   e->bx = bx;
   e->grid = (e->n_local + bx - 1) / bx;
   if (e->grid > kCombineMaxRecords)
