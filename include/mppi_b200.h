@@ -61,7 +61,7 @@ enum mppib_blob
                                             (mppi_common.cu:117); needed by mppib_get_samples */
 #define MPPIB_FLAG_NO_TMA 2u             /* stage noise tiles with plain loads instead of cp.async.bulk.tensor */
 #define MPPIB_FLAG_NO_PREFETCH 8u         /* draw each solve's noise inline instead of one solve ahead on a side stream */
-#define MPPIB_FLAG_NN_SIMT 16u           /* Autorally NN: FP32 FFMA2 forward pass instead of the tcgen05 tensor-core one */
+#define MPPIB_FLAG_NN_TENSOR 16u         /* Autorally NN: forward pass on tcgen05 tensor cores (3xTF32) instead of FP32 FFMA2 */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
 

@@ -760,10 +760,12 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   if ((int)e->smem_bytes > max_smem)
     return bail(fail(MPPIB_ERR_SMEM, "noise tile needs %u B of shared memory, device allows %d", e->smem_bytes,
                      max_smem));
-  // tensor-core variant of the Autorally pair: fixed 128-sample CTAs (one UMMA tile), streaming noise ring
+  // tensor-core variant of the Autorally pair: fixed 128-sample CTAs (one UMMA tile), streaming noise ring. Opt-in:
+  // measured on B200 it does not beat the FFMA2 kernel yet (378 vs 353 us at N=32768, T=100 — three exposed MMA round
+  // trips per step with only ~7 warps per SM to cover them; profiles/r01_autorally_k1_notes.md)
   if (desc->dynamics_id == MPPIB_DYN_AUTORALLY_NN && desc->cost_id == MPPIB_COST_AR_STANDARD && e->D == 1 &&
-      (e->TC % 4) == 0 && !(desc->flags & (MPPIB_FLAG_NN_SIMT | MPPIB_FLAG_NO_TMA)) && !getenv("MPPIB_NN_SIMT") &&
-      !getenv("MPPIB_NO_TMA"))
+      (e->TC % 4) == 0 && !(desc->flags & MPPIB_FLAG_NO_TMA) && !getenv("MPPIB_NO_TMA") &&
+      ((desc->flags & MPPIB_FLAG_NN_TENSOR) || getenv("MPPIB_NN_TENSOR")))
   {
     e->nn_tc = true;
     bx = nn_tc::kRows;

@@ -28,7 +28,7 @@ DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM = 0, 1, 2,
 COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC = 0, 1, 2, 3
 SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
 BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
-FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_SIMT = 1, 2, 4, 8, 16
+FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR = 1, 2, 4, 8, 16
 OPT_L2_FLUSH_BYTES = 1
 AR_NN_NUM_PARAMS = 1412
 
