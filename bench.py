@@ -101,11 +101,19 @@ def _workload(args):
     return W.by_name(args.workload, args.rollouts, args.timesteps)
 
 
+def _oracle_prepare(w):
+    """The LSTM model's weights / architecture are handed to the oracle once (oracle/binding.py: set_lstm)."""
+    import oracle
+    if hasattr(w.dyn, "lstm_theta"):
+        oracle.set_lstm(w.dyn.lstm_theta, w.dyn.hidden_dim, w.dyn.head_hidden)
+
+
 def _cpu_solve_hz(w, nthreads, repeats, sample_N=None):
     """Times the oracle's full solve (setGaussianControls + CPU rollout + min/exp/sum + weighted reduction) on the host
     cores. Noise is pre-generated outside the timed region, as in the reference's CPU path, which reads the samples the
     GPU drew (tests/include/kernel_tests/core/rollout_kernel_test.cu:504-541). Returns (Hz of a FULL-size solve, text)."""
     import oracle
+    _oracle_prepare(w)
     N = w.N if sample_N is None else min(sample_N, w.N)
     Cd = w.dyn.CONTROL_DIM
     eps = oracle.curand_normal(w.seed, 0, N * w.T * Cd).reshape(N, w.T, Cd)
@@ -113,7 +121,7 @@ def _cpu_solve_hz(w, nthreads, repeats, sample_N=None):
 
     def once():
         return oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, sp, w.dyn.nn_theta,
-                            w.cost.costmap, N, w.T, w.D, Cd, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps,
+                            getattr(w.cost, "costmap", None), N, w.T, w.D, Cd, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps,
                             nthreads=nthreads)
     once()
     t0 = time.perf_counter()
@@ -144,7 +152,7 @@ def run_reference(args):
 
     def once():
         oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, w.dyn.nn_theta,
-                     w.cost.costmap, N, w.T, w.D, Cd, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps, nthreads=ncores)
+                     getattr(w.cost, "costmap", None), N, w.T, w.D, Cd, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps, nthreads=ncores)
     for _ in range(args.warmup):
         once()
     t0 = time.perf_counter()

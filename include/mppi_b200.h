@@ -79,6 +79,9 @@ typedef struct mppib_desc
   /* rollout sharding across GPUs. rank r owns samples [r*N/W, (r+1)*N/W). */
   int rank;
   int world_size;
+  /* architecture arguments of the dynamics' constructor (not parameters): MPPIB_DYN_RACER_LSTM = { hidden_dim H,
+   * head hidden width L1 } (racer_dubins_elevation_lstm_steering.cu:11-22); all zero for the other models. */
+  int model_dims[8];
 } mppib_desc;
 
 /* Per-solve statistics for one distribution (getBaselineCost / getNormalizerCost, controller.cuh:510-517, and the
@@ -177,7 +180,10 @@ int mppib_local_rollouts(mppib_engine* e, int* n_local, int* n_offset);
  * draw and the rollout so K1 reads its tile from HBM instead of the L2 lines K0 just wrote (roofline measurements). */
 enum mppib_option
 {
-  MPPIB_OPT_L2_FLUSH_BYTES = 1
+  MPPIB_OPT_L2_FLUSH_BYTES = 1,
+  /* ColoredNoise: the optimization_stride (rearrangeNoise's offset_t, colored_noise.cu:39-56) assumed by draws that
+   * are issued before a solve names its own: mppib_draw_noise and the one-solve-ahead prefetch. Default 1. */
+  MPPIB_OPT_COLORED_OFFSET_T = 2
 };
 int mppib_set_option(mppib_engine* e, int option, long long value);
 

@@ -6,6 +6,7 @@
  *   mppib_host_smooth_controls      Controller::smoothControlTrajectoryHelper   controllers/controller.cuh:557-586
  *   mppib_host_slide_controls       Controller::slideControlSequenceHelper      controller.cuh:588-600
  *   mppib_host_output_trajectory    Controller::computeOutputTrajectoryHelper   controller.cuh:643-663
+ *   mppib_host_step_lstm / mppib_host_output_trajectory_lstm   the same two for RacerDubinsElevationLSTMSteering
  *   mppib_host_free_energy          mppi::kernels::computeFreeEnergy      include/mppi/core/mppi_common.cu:1065-1081
  *   mppib_host_merge_records        (no reference counterpart: the log-sum-exp merge of rollout shards)
  * Arrays: u / history are [T][C] / [2][C] (== Eigen C x T / C x 2 column-major), states [T][S], outputs [T][O].
@@ -24,6 +25,21 @@ void mppib_host_smooth_controls(float* u, const float* history, int T, int C);
 void mppib_host_slide_controls(float* u, int steps, int T, int C, const float* zero_control, const float* scale);
 int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x0,
                                  const float* u, int T, float dt, float* states, float* outputs);
+/* RacerDubinsElevationLSTMSteering (racer_dubins_elevation_lstm_steering.cu:90-118): the model carries its LSTM's
+ * hidden / cell vectors from step to step, so its host twin takes them explicitly (updated in place by _step_lstm;
+ * _output_trajectory_lstm starts from the initial state stored in the weight blob and leaves `net` untouched). */
+typedef struct mppib_host_lstm
+{
+  const float* theta; /* MPPIB_BLOB_LSTM_WEIGHTS layout (params.h) */
+  int hidden_dim;     /* H */
+  int head_hidden;    /* L1 */
+  float* hidden;      /* [H] */
+  float* cell;        /* [H] */
+} mppib_host_lstm;
+int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x, const float* u, float dt,
+                         float* x_next, float* xdot, float* y);
+int mppib_host_output_trajectory_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x0,
+                                      const float* u, int T, float dt, float* states, float* outputs);
 void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float lambda, float* out3);
 /* CPU twin of the K2 merge (csrc/combine_kernel.cuh): records [nrec][D][pstride] = (beta, eta, sum w^2, -, V[TC]). */
 int mppib_host_merge_records(const float* records, int nrec, int D, int TC, int pstride, float lambda, int normalize,

@@ -76,6 +76,48 @@ typedef struct mppib_ar_nn_dyn_params
   mppib_control_limits lim;
 } mppib_ar_nn_dyn_params;
 
+/* RacerDubinsElevationLSTMSteering (dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cuh): the parametric
+ * fields of RacerDubinsParams (racer_dubins.cuh:78-104) + RacerDubinsElevationParams (racer_dubins_elevation.cuh:47-59).
+ * The LSTM architecture is a constructor argument in the reference (lstm_steering.cu:11-22) and therefore travels in
+ * mppib_desc.model_dims = { hidden_dim H, head hidden width L1 } (LSTM input dim is 4, head layers {H+4, L1, 1});
+ * the weights travel as MPPIB_BLOB_LSTM_WEIGHTS in the reference's packed layouts:
+ *   LSTM  W_im W_fm W_om W_cm (H x H row-major each) | W_ii W_fi W_oi W_ci (H x 4) | b_i b_f b_o b_c (H) |
+ *         initial_hidden (H) | initial_cell (H)                               (utils/nn_helpers/lstm_helper.cu:72-88)
+ *   head  per layer W (row-major out x in) then b                              (utils/nn_helpers/fnn_helper.cu:176-183)
+ * Elevation map: not built yet (flat terrain == TwoDTextureHelper::checkTextureUse(0) false, racer_dubins.cu:427-432). */
+#define MPPIB_RACER_LSTM_INPUT_DIM 4
+#define MPPIB_RACER_LSTM_NUM_PARAMS(H, L1) \
+  (4 * (H) * (H) + 4 * (H) * 4 + 6 * (H) + ((H) + 4) * (L1) + (L1) + (L1) + 1)
+typedef struct mppib_racer_lstm_dyn_params
+{
+  mppib_control_limits lim;
+  float c_t[3];                    /* 1.3, 2.6, 3.9 */
+  float c_b[3];                    /* 2.5, 3.5, 4.5 */
+  float c_v[3];                    /* 3.7, 4.7, 5.7 */
+  float c_0;                       /* 4.9 */
+  float steering_constant;         /* 0.6 */
+  float steer_command_angle_scale; /* 5 */
+  float steer_angle_scale;         /* -9.1 */
+  float max_steer_angle;           /* 0.5 */
+  float max_steer_rate;            /* 5 */
+  float steer_accel_constant;      /* 12.1 */
+  float steer_accel_drag_constant; /* 1.0 */
+  float brake_delay_constant;      /* 6.6 */
+  float brake_delay_constant_neg;  /* 8.2 */
+  float max_brake_rate_neg;        /* 0.9 */
+  float max_brake_rate_pos;        /* 0.33 */
+  float wheel_base;                /* 0.3 */
+  float low_min_throttle;          /* 0.13 */
+  float gravity;                   /* -9.81 */
+  int gear_sign;                   /* 1 */
+  float clamp_ax;                  /* 5.5 */
+  float K_x, K_y, K_yaw, K_vel_x;  /* 1 */
+  float Q_x_acc;                   /* 1 */
+  float Q_x_v[3];                  /* 41.74219, -0.8187027, -2.2131343 */
+  float Q_y_f;                     /* 0.1 */
+  float Q_omega_v;                 /* 0.001 */
+  float Q_omega_steering;          /* 0 */
+} mppib_racer_lstm_dyn_params;
 /* ---- Cost parameter blobs ----------------------------------------------------------------------- */
 typedef struct mppib_cartpole_cost_params /* cost_functions/cartpole/cartpole_quadratic_cost.cuh:10-23 */
 {
@@ -124,6 +166,22 @@ typedef struct mppib_ar_standard_cost_params /* cost_functions/autorally/ar_stan
   int map_height;           /* texture height */
 } mppib_ar_standard_cost_params;
 
+/* Quadratic tracking cost on the RACER output vector (ours: the RACER cost classes are not in the reference tree,
+ * SURVEY §8d C5). cost = speed_coeff (y[VEL_B_X] - desired_speed)^2 + yaw_coeff angdist(y[YAW], desired_yaw)^2
+ *                      + lateral_coeff (y[POS_I_Y] - desired_y)^2 + steer_coeff y[STEER_ANGLE]^2, times discount^t;
+ * terminal cost 0. */
+typedef struct mppib_racer_quadratic_cost_params
+{
+  float control_cost_coeff[MPPIB_MAX_CONTROL_DIM];
+  float discount;      /* 1.0 */
+  float desired_speed; /* 5.0 */
+  float speed_coeff;   /* 4.0 */
+  float desired_yaw;   /* 0.0 */
+  float yaw_coeff;     /* 20.0 */
+  float desired_y;     /* 0.0 */
+  float lateral_coeff; /* 2.0 */
+  float steer_coeff;   /* 1.0 */
+} mppib_racer_quadratic_cost_params;
 /* ---- Sampler parameter blob (sampling_distribution.cuh:14-29, gaussian.cuh:21-61) --------------- */
 typedef struct mppib_gaussian_params
 {

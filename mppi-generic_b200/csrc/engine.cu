@@ -12,6 +12,7 @@
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cufft.h>
 #include <curand.h>
 #include <dlfcn.h>
 
@@ -27,6 +28,7 @@
 
 #include "../../include/mppi_b200.h"
 #include "combine_kernel.cuh"
+#include "noise_colored.cuh"
 #include "noise_xorwow.cuh"
 #include "plugins/costs.cuh"
 #include "plugins/dynamics.cuh"
@@ -142,6 +144,8 @@ struct mppib_engine
 
   // aux device resources
   float* nn_theta_d = nullptr;
+  float* lstm_theta_d = nullptr;  // MPPIB_BLOB_LSTM_WEIGHTS
+  bool have_lstm = false;
   cudaArray_t costmap_array = nullptr;
   cudaTextureObject_t costmap_tex = 0;
 
@@ -172,6 +176,24 @@ struct mppib_engine
   int prefetch_buf = 0;
   int xw_chunks = 0, xw_rounds_per_chunk = 0;
   uint32_t xw_jump_d = 0;
+  // normals per generateSamples call: Gaussian N*T*C (gaussian.cu:380-381), ColoredNoise 2*N*C*(T+1) (colored_noise.cu:343)
+  unsigned long long draw_global = 0;  // whole job
+  unsigned long long draw_start = 0;   // this rank's first normal inside the call's block
+  size_t draw_local = 0;               // this rank's normals
+  // ColoredNoise sampler (noise_colored.cuh)
+  bool colored = false;
+  int F = 0;                     // T + 1 frequencies
+  float2* spec_d = nullptr;      // [n_local*C][F] complex spectrum == the raw draw
+  float* spec_alloc = nullptr;   // allocation incl. the offset-alignment lead-in
+  float* time_d = nullptr;       // [n_local*C][2T] cuFFT output, kept until the next draw
+  float* coeffs_d = nullptr;     // [C][F]
+  float* sigma_d = nullptr;      // [C]
+  cufftHandle fft_plan = 0;
+  bool have_plan = false;
+  int colored_offset_t = 1;      // optimization_stride assumed by draws issued before a solve names its own
+  int buf_offset_t[2] = { 1, 1 };  // stride the colored block in eps_buf[i] was rearranged with
+  cudaEvent_t ev_rearr = nullptr;  // last re-rearrange on the main stream (time_d must outlive it)
+  bool rearr_recorded = false;
   uint32_t* xw_states_d = nullptr;
   uint32_t* xw_tables_d = nullptr;
 
@@ -210,6 +232,7 @@ struct mppib_engine
   int (*launch_rollout)(mppib_engine&, const float* x0, const float* U_in, int opt_stride, int iter) = nullptr;
   size_t dyn_param_bytes = 0, cost_param_bytes = 0;
   int dyn_shared_floats = 0;
+  int (*dyn_shared_floats_fn)(const int*, int) = nullptr;
   int (*cost_shared_floats)(int) = nullptr;
   int (*prepare)(mppib_engine&) = nullptr;  // sets func attributes
   bool solved_once = false;
@@ -229,6 +252,16 @@ struct AuxFill<plugins::AutorallyNNDynamics::Aux>
   static void fill(plugins::AutorallyNNDynamics::Aux& a, const mppib_engine& e)
   {
     a.theta_d = e.nn_theta_d;
+  }
+};
+template <>
+struct AuxFill<plugins::RacerLSTMDynamics::Aux>
+{
+  static void fill(plugins::RacerLSTMDynamics::Aux& a, const mppib_engine& e)
+  {
+    a.theta_d = e.lstm_theta_d;
+    a.H = e.desc.model_dims[0];
+    a.L1 = e.desc.model_dims[1];
   }
 };
 template <>
@@ -276,7 +309,9 @@ struct Pair
     }
     if (e.D == 1)
       return e.writeback ? prepare_one<1, true>(e) : prepare_one<1, false>(e);
-    return e.writeback ? prepare_one<2, true>(e) : prepare_one<2, false>(e);
+    if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
+      return e.writeback ? prepare_one<2, true>(e) : prepare_one<2, false>(e);
+    return fail(MPPIB_ERR_UNSUPPORTED, "this dynamics model is built for num_distributions == 1 only");
   }
 
   static int launch(mppib_engine& e, const float* x0, const float* U_in, int opt_stride, int iter)
@@ -310,6 +345,7 @@ struct Pair
     a.pstride = e.pstride;
     a.opt_stride = opt_stride;
     a.use_tma = e.use_tma ? 1 : 0;
+    a.dyn_shared_floats = e.dyn_shared_floats;
     a.dt = e.dt;
     a.lambda = e.lambda;
     a.alpha = e.alpha;
@@ -338,7 +374,7 @@ struct Pair
       else
         rollout_kernel<DYN, COST, 1, false><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
     }
-    else
+    else if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
     {
       if (e.writeback)
         rollout_kernel<DYN, COST, 2, true><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
@@ -355,7 +391,7 @@ struct PairEntry
   int dyn_id, cost_id;
   int S, C, O;
   size_t dyn_bytes, cost_bytes;
-  int dyn_shared_floats;
+  int (*dyn_shared_floats)(const int*, int);
   int max_block_threads;
   int (*cost_shared_floats)(int);
   int (*launch)(mppib_engine&, const float*, const float*, int, int);
@@ -371,7 +407,7 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     DYN::OUTPUT_DIM,
                     sizeof(typename DYN::Params),
                     sizeof(typename COST::Params),
-                    DYN::SHARED_FLOATS,
+                    &DYN::sharedFloats,
                     DYN::MAX_BLOCK_THREADS,
                     &Pair<DYN, COST>::cost_shared,
                     &Pair<DYN, COST>::launch,
@@ -383,6 +419,7 @@ static const PairEntry kPairs[] = {
   make_entry<plugins::DoubleIntegratorDynamics, plugins::DoubleIntegratorCircleCost>(MPPIB_DYN_DOUBLE_INTEGRATOR,
                                                                                      MPPIB_COST_DI_CIRCLE),
   make_entry<plugins::AutorallyNNDynamics, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
+  make_entry<plugins::RacerLSTMDynamics, plugins::RacerQuadraticCost>(MPPIB_DYN_RACER_LSTM, MPPIB_COST_RACER_QUADRATIC),
 };
 
 // ---- helpers ----------------------------------------------------------------------------------------------------
@@ -409,17 +446,48 @@ static int make_tensor_map(mppib_engine& e, float* base, CUtensorMap* out)
   return MPPIB_OK;
 }
 
-// One generateSamples-equivalent draw (gaussian.cu:378-394) of the block of the global XORWOW stream that starts at
-// global position `pos` (N*T*C normals per block; this rank keeps elements [n_offset*T*C, (n_offset+n_local)*T*C) of it)
-// into eps_buf[buf], on `st`. Draws are totally ordered through ev_last_gen because they share the generator state.
-static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long long pos)
+// ColoredNoise: rearrangeNoise (colored_noise.cu:39-56) from the retained time-domain buffer into eps_buf[buf] on `st`.
+static int colored_rearrange(mppib_engine& e, int buf, cudaStream_t st, int offset_t)
 {
-  const unsigned long long global_count = (unsigned long long)e.N * e.TC;
-  const unsigned long long start = pos + (unsigned long long)e.n_offset * e.TC;
-  const size_t count = (size_t)e.n_local * e.TC;
+  if (offset_t < 0 || offset_t >= 2 * e.T)
+    return fail(MPPIB_ERR_INVALID_ARG, "optimization_stride %d outside the 2T = %d colored-noise samples", offset_t,
+                2 * e.T);
+  const dim3 block(128), grid((unsigned)e.n_local, (unsigned)((e.T + 127) / 128));
   float* dst = e.eps_buf[buf];
+  const float decay = e.sampler.offset_decay_rate;
+  switch (e.C)
+  {
+    case 1:
+      colored_rearrange_kernel<1><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.n_local, e.T, offset_t, decay);
+      break;
+    case 2:
+      colored_rearrange_kernel<2><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.n_local, e.T, offset_t, decay);
+      break;
+    case 4:
+      colored_rearrange_kernel<4><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.n_local, e.T, offset_t, decay);
+      break;
+    default:
+      return fail(MPPIB_ERR_UNSUPPORTED, "ColoredNoise: CONTROL_DIM %d", e.C);
+  }
+  CUDA_TRY(cudaGetLastError());
+  e.buf_offset_t[buf] = offset_t;
+  return MPPIB_OK;
+}
+
+// One generateSamples-equivalent draw (gaussian.cu:378-394 / colored_noise.cu:343-372) of the block of the global
+// XORWOW stream that starts at global position `pos` (draw_global normals per block; this rank keeps elements
+// [draw_start, draw_start + draw_local) of it) into eps_buf[buf], on `st`. Draws are totally ordered through
+// ev_last_gen because they share the generator state (and, for ColoredNoise, the spectrum / time buffers).
+static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long long pos, int offset_t)
+{
+  const unsigned long long global_count = e.draw_global;
+  const unsigned long long start = pos + e.draw_start;
+  const size_t count = e.draw_local;
+  float* dst = e.colored ? reinterpret_cast<float*>(e.spec_d) : e.eps_buf[buf];
   if (e.any_gen)
     CUDA_TRY(cudaStreamWaitEvent(st, e.ev_last_gen, 0));
+  if (e.colored && e.rearr_recorded)
+    CUDA_TRY(cudaStreamWaitEvent(st, e.ev_rearr, 0));  // a re-rearrange may still be reading time_d
   if (e.xw_enabled && (pos % 8192ULL) == 0)
   {
     const int nstates = e.xw_chunks * kXorwowStreams;
@@ -456,6 +524,21 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
     }
     e.curand_pos = (e.desc.world_size == 1) ? pos + global_count : mppib_engine::kNoPos;
   }
+  if (e.colored)
+  {
+    const size_t ncomplex = count / 2;
+    const int blocks = (int)std::min<size_t>((ncomplex + 255) / 256, 148 * 16);
+    colored_scale_kernel<<<blocks, 256, 0, st>>>(e.spec_d, e.coeffs_d, ncomplex, e.C, e.F);
+    CUDA_TRY(cudaGetLastError());
+    if (cufftSetStream(e.fft_plan, st) != CUFFT_SUCCESS)
+      return fail(MPPIB_ERR_CUDA, "cufftSetStream failed");
+    const cufftResult fr = cufftExecC2R(e.fft_plan, reinterpret_cast<cufftComplex*>(e.spec_d), e.time_d);
+    if (fr != CUFFT_SUCCESS)
+      return fail(MPPIB_ERR_CUDA, "cufftExecC2R failed: %d", (int)fr);
+    int rc = colored_rearrange(e, buf, st, offset_t);
+    if (rc != MPPIB_OK)
+      return rc;
+  }
   CUDA_TRY(cudaEventRecord(e.ev_last_gen, st));
   e.any_gen = true;
   return MPPIB_OK;
@@ -463,24 +546,36 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
 
 // Makes eps_buf[cur_buf] hold the block at rng_offset (taking the prefetched buffer if it is the right one) and
 // advances rng_offset. Everything is ordered on the main stream when this returns.
-static int draw_noise(mppib_engine& e)
+static int draw_noise(mppib_engine& e, int offset_t)
 {
   if (e.prefetch_valid && e.prefetch_pos == e.rng_offset)
   {
     CUDA_TRY(cudaStreamWaitEvent(e.stream, e.ev_gen_done[e.prefetch_buf], 0));
     e.cur_buf = e.prefetch_buf;
+    if (e.colored && e.buf_offset_t[e.cur_buf] != offset_t)
+    {
+      // the prefetch assumed another optimization_stride: redo the (cheap) rearrange from the time-domain buffer,
+      // which still holds this block (no later draw has been issued)
+      int rc = colored_rearrange(e, e.cur_buf, e.stream, offset_t);
+      if (rc != MPPIB_OK)
+        return rc;
+      CUDA_TRY(cudaEventRecord(e.ev_rearr, e.stream));
+      e.rearr_recorded = true;
+    }
   }
   else
   {
     // the main stream orders this draw after every earlier K1 that read eps_buf[cur_buf]
-    int rc = gen_draw(e, e.cur_buf, e.stream, e.rng_offset);
+    int rc = gen_draw(e, e.cur_buf, e.stream, e.rng_offset, offset_t);
     if (rc != MPPIB_OK)
       return rc;
   }
   e.prefetch_valid = false;
   e.eps_d = e.eps_buf[e.cur_buf];
   e.tmap = e.tmap_buf[e.cur_buf];
-  e.rng_offset += (unsigned long long)e.N * e.TC;
+  e.rng_offset += e.draw_global;
+  if (e.colored)
+    e.colored_offset_t = offset_t;  // what the next prefetch assumes
   return MPPIB_OK;
 }
 
@@ -493,7 +588,7 @@ static int prefetch_next(mppib_engine& e)
   const int nb = e.cur_buf ^ 1;
   if (e.k1_recorded[nb])
     CUDA_TRY(cudaStreamWaitEvent(e.side_stream, e.ev_k1_done[nb], 0));
-  int rc = gen_draw(e, nb, e.side_stream, e.rng_offset);
+  int rc = gen_draw(e, nb, e.side_stream, e.rng_offset, e.colored_offset_t);
   if (rc != MPPIB_OK)
     return rc;
   CUDA_TRY(cudaEventRecord(e.ev_gen_done[nb], e.side_stream));
@@ -574,6 +669,8 @@ static int check_ready(mppib_engine* e)
     return fail(MPPIB_ERR_STATE, "MPPIB_BLOB_NN_WEIGHTS not set");
   if (e->desc.cost_id == MPPIB_COST_AR_STANDARD && !e->costmap_tex)
     return fail(MPPIB_ERR_STATE, "MPPIB_BLOB_COSTMAP not set");
+  if (e->desc.dynamics_id == MPPIB_DYN_RACER_LSTM && !e->have_lstm)
+    return fail(MPPIB_ERR_STATE, "MPPIB_BLOB_LSTM_WEIGHTS not set");
   if (e->desc.world_size > 1 && !e->comm)
     return fail(MPPIB_ERR_STATE, "world_size > 1 but mppib_comm_init was not called");
   return MPPIB_OK;
@@ -649,9 +746,23 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   const int world = desc->world_size <= 0 ? 1 : desc->world_size;
   if (desc->rank < 0 || desc->rank >= world)
     return fail(MPPIB_ERR_INVALID_ARG, "rank out of range");
-  if (desc->sampler_id != MPPIB_SAMPLER_GAUSSIAN)
-    return fail(MPPIB_ERR_UNSUPPORTED, "sampler %d is not built into this library yet", desc->sampler_id);
+  if (desc->sampler_id != MPPIB_SAMPLER_GAUSSIAN && desc->sampler_id != MPPIB_SAMPLER_COLORED_NOISE)
+    return fail(MPPIB_ERR_UNSUPPORTED, "sampler %d is not built into this library", desc->sampler_id);
+  if (desc->sampler_id == MPPIB_SAMPLER_COLORED_NOISE && desc->num_distributions != 1)
+    return fail(MPPIB_ERR_UNSUPPORTED,
+                "ColoredNoise draws independent noise per distribution (colored_noise.cu:291); only "
+                "num_distributions == 1 is built");
 
+  if (desc->dynamics_id == MPPIB_DYN_RACER_LSTM)
+  {
+    const int H = desc->model_dims[0], L1 = desc->model_dims[1];
+    if (H < 1 || H > plugins::RacerLSTMDynamics::MAX_HIDDEN || L1 < 1 || L1 > plugins::RacerLSTMDynamics::MAX_HEAD)
+      return fail(MPPIB_ERR_INVALID_ARG, "RacerDubinsElevationLSTMSteering: model_dims = {hidden_dim %d, head width %d} "
+                                         "outside [1, %d] x [1, %d]",
+                  H, L1, plugins::RacerLSTMDynamics::MAX_HIDDEN, plugins::RacerLSTMDynamics::MAX_HEAD);
+    if (desc->num_distributions != 1)
+      return fail(MPPIB_ERR_UNSUPPORTED, "RacerDubinsElevationLSTMSteering is built for num_distributions == 1 only");
+  }
   const PairEntry* entry = nullptr;
   for (const auto& p : kPairs)
     if (p.dyn_id == desc->dynamics_id && p.cost_id == desc->cost_id)
@@ -684,7 +795,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->prepare = entry->prepare;
   e->dyn_param_bytes = entry->dyn_bytes;
   e->cost_param_bytes = entry->cost_bytes;
-  e->dyn_shared_floats = entry->dyn_shared_floats;
+  e->dyn_shared_floats_fn = entry->dyn_shared_floats;
   e->cost_shared_floats = entry->cost_shared_floats;
   e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
   e->use_pdl = !getenv("MPPIB_NO_PDL");
@@ -720,7 +831,9 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, desc->device));
   CUDA_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, desc->device));
   auto smem_for = [&](int b) {
-    return (int)rollout_smem_layout(b, e->nchunks, e->D, e->TC, e->dyn_shared_floats, e->cost_shared_floats(e->T)).total;
+    return (int)rollout_smem_layout(b, e->nchunks, e->D, e->TC, e->dyn_shared_floats_fn(e->desc.model_dims, b),
+                                    e->cost_shared_floats(e->T))
+        .total;
   };
   int bx = 0;
   if (const char* s = getenv("MPPIB_BX"))
@@ -775,6 +888,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
                        e->smem_bytes, max_smem));
   }
   e->bx = bx;
+  e->dyn_shared_floats = e->dyn_shared_floats_fn(e->desc.model_dims, bx);
   e->grid = (e->n_local + bx - 1) / bx;
   if (e->grid > kCombineMaxRecords)
     return bail(fail(MPPIB_ERR_UNSUPPORTED, "%d rollout blocks exceed the combine kernel's %d records; raise MPPIB_BX",
@@ -804,6 +918,16 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
 
   const size_t noise_floats = (size_t)e->n_local * e->TC;
   const size_t lead_floats = 8192;  // room for the offset-alignment lead-in (see draw_noise)
+  e->colored = desc->sampler_id == MPPIB_SAMPLER_COLORED_NOISE;
+  e->F = e->T + 1;
+  {
+    // normals per generateSamples call and this rank's slice of them
+    const unsigned long long per_rollout =
+        e->colored ? 2ULL * e->C * e->F : (unsigned long long)e->TC;  // colored_noise.cu:341-343 / gaussian.cu:380
+    e->draw_global = per_rollout * (unsigned long long)e->N;
+    e->draw_start = per_rollout * (unsigned long long)e->n_offset;
+    e->draw_local = (size_t)(per_rollout * (unsigned long long)e->n_local);
+  }
   CUDA_TRY_B(cudaMalloc(&e->noise_alloc, (lead_floats + noise_floats + 8) * sizeof(float)));
   e->eps_d = e->noise_alloc + lead_floats;  // cudaMalloc is 256-B aligned and 8192*4 keeps that
   CUDA_TRY_B(cudaMemsetAsync(e->noise_alloc, 0, (lead_floats + noise_floats + 8) * sizeof(float), e->stream));
@@ -849,12 +973,29 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   for (int i = 0; i < 4; i++)
     CUDA_TRY_B(cudaEventCreate(&e->ev[i]));
 
+  if (e->colored)
+  {
+    // spectrum (the raw draw), time-domain buffer, tables and the reference's plan (colored_noise.cu:236-282)
+    const size_t batch = (size_t)e->n_local * e->C;
+    CUDA_TRY_B(cudaMalloc(&e->spec_alloc, (lead_floats + e->draw_local + 8) * sizeof(float)));
+    CUDA_TRY_B(cudaMemsetAsync(e->spec_alloc, 0, (lead_floats + e->draw_local + 8) * sizeof(float), e->stream));
+    e->spec_d = reinterpret_cast<float2*>(e->spec_alloc + lead_floats);
+    CUDA_TRY_B(cudaMalloc(&e->time_d, batch * 2 * e->T * sizeof(float)));
+    CUDA_TRY_B(cudaMalloc(&e->coeffs_d, (size_t)e->C * e->F * sizeof(float)));
+    CUDA_TRY_B(cudaMalloc(&e->sigma_d, (size_t)e->C * sizeof(float)));
+    CUDA_TRY_B(cudaEventCreateWithFlags(&e->ev_rearr, cudaEventDisableTiming));
+    const cufftResult fr = cufftPlan1d(&e->fft_plan, 2 * e->T, CUFFT_C2R, (int)batch);
+    if (fr != CUFFT_SUCCESS)
+      return bail(fail(MPPIB_ERR_CUDA, "cufftPlan1d(%d, C2R, %zu) failed: %d", 2 * e->T, batch, (int)fr));
+    e->have_plan = true;
+  }
+
   // own XORWOW draw: possible when this rank's slice is a whole number of 8192-normal rounds
   if (!(desc->flags & MPPIB_FLAG_CURAND_HOST_API) && !getenv("MPPIB_CURAND_HOST_API") &&
-      (noise_floats % 8192) == 0 && (((size_t)e->n_offset * e->TC) % 8192) == 0 && (((size_t)e->N * e->TC) % 8192) == 0)
+      (e->draw_local % 8192) == 0 && (e->draw_start % 8192ULL) == 0 && (e->draw_global % 8192ULL) == 0)
   {
-    const int rounds_local = (int)(noise_floats / 8192);
-    const unsigned long long rounds_global = (unsigned long long)e->N * e->TC / 8192ULL;
+    const int rounds_local = (int)(e->draw_local / 8192);
+    const unsigned long long rounds_global = e->draw_global / 8192ULL;
     int K = 1;
     for (int cand = 1; cand <= 64 && cand <= rounds_local; cand++)
       if (rounds_local % cand == 0 && (rounds_local / cand >= 4 || cand == 1))
@@ -929,6 +1070,7 @@ int mppib_destroy(mppib_engine* e)
   if (e->costmap_array)
     cudaFreeArray(e->costmap_array);
   cudaFree(e->nn_theta_d);
+  cudaFree(e->lstm_theta_d);
   cudaFree(e->noise_alloc);
   cudaFree(e->noise_alloc2);
   cudaFree(e->costs_d);
@@ -943,6 +1085,14 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->l2_flush_d);
   cudaFree(e->xw_states_d);
   cudaFree(e->xw_tables_d);
+  if (e->have_plan)
+    cufftDestroy(e->fft_plan);
+  cudaFree(e->spec_alloc);
+  cudaFree(e->time_d);
+  cudaFree(e->coeffs_d);
+  cudaFree(e->sigma_d);
+  if (e->ev_rearr)
+    cudaEventDestroy(e->ev_rearr);
   if (e->result_h)
     cudaFreeHost(e->result_h);
   if (e->done_flag_h)
@@ -1003,6 +1153,49 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
       for (int i = 0; i < e->D * e->C; i++)
         if (!(sp.std_dev[i] > 0.0f))
           return fail(MPPIB_ERR_INVALID_ARG, "std_dev[%d] must be positive", i);
+      if (e->colored)
+      {
+        // frequency weights and sigma, computed like ColoredNoiseDistribution::generateSamples does on the host every
+        // call (colored_noise.cu:294-338): fftfreq(2T), low-frequency cutoff, f^(-beta_c/2), theoretical std dev
+        const int n2 = 2 * e->T, F = e->F, Cn = e->C;
+        std::vector<float> sample_freq(F);
+        for (int i = 0; i < F; i++)
+          sample_freq[i] = i / (1.0f * n2);  // colored_noise.cuh:24-34
+        const float cutoff_freq = fmaxf(sp.fmin, 1.0f / n2);
+        std::vector<float> coeffs((size_t)Cn * F, 0.0f);  // Eigen MatrixXf(F, C) is column-major: [c][f]
+        int smaller_index = 0;
+        for (int i = 0; i < F; i++)
+        {
+          if (sample_freq[i] < cutoff_freq)
+            smaller_index++;
+          else if (smaller_index < F)
+            for (int j = 0; j < smaller_index; j++)
+            {
+              sample_freq[j] = sample_freq[smaller_index];
+              for (int k = 0; k < Cn; k++)
+                coeffs[(size_t)k * F + j] = powf(sample_freq[smaller_index], -sp.exponents[k] / 2.0f);
+            }
+          for (int j = 0; j < Cn; j++)
+            coeffs[(size_t)j * F + i] = powf(sample_freq[i], -sp.exponents[j] / 2.0f);
+        }
+        float sigma[MPPIB_MAX_CONTROL_DIM] = { 0 };
+        for (int i = 0; i < Cn; i++)
+        {
+          for (int j = 1; j < F - 1; j++)
+            sigma[i] += coeffs[(size_t)i * F + j] * coeffs[(size_t)i * F + j];
+          const float last = coeffs[(size_t)i * F + F - 1] * ((1.0f + (n2 % 2)) / 2.0f);
+          sigma[i] += last * last;
+          sigma[i] = 2.0f * sqrtf(sigma[i]) / n2;
+          if (!(sigma[i] > 0.0f) || !std::isfinite(sigma[i]))
+            return fail(MPPIB_ERR_INVALID_ARG, "ColoredNoise: exponent %g gives a non-finite spectrum", sp.exponents[i]);
+        }
+        if (e->side_stream)
+          CUDA_TRY(cudaStreamSynchronize(e->side_stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(cudaMemcpy(e->coeffs_d, coeffs.data(), coeffs.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->sigma_d, sigma, Cn * sizeof(float), cudaMemcpyHostToDevice));
+        e->prefetch_valid = false;  // a prefetched block was shaped with the old table
+      }
       e->sampler = sp;
       e->have_sampler = true;
       return MPPIB_OK;
@@ -1022,6 +1215,26 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
         CUDA_TRY(cudaMalloc(&e->nn_theta_d, nbytes));
       CUDA_TRY(cudaMemcpyAsync(e->nn_theta_d, host, nbytes, cudaMemcpyHostToDevice, e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
+      return MPPIB_OK;
+    }
+    case MPPIB_BLOB_LSTM_WEIGHTS:
+    {
+      if (e->desc.dynamics_id != MPPIB_DYN_RACER_LSTM)
+        return fail(MPPIB_ERR_INVALID_ARG, "LSTM weights given to a dynamics without an LSTM");
+      const int H = e->desc.model_dims[0], L1 = e->desc.model_dims[1];
+      const size_t expect = (size_t)MPPIB_RACER_LSTM_NUM_PARAMS(H, L1) * sizeof(float);
+      if (nbytes != expect)
+        return fail(MPPIB_ERR_INVALID_ARG, "LSTM weights: got %zu bytes, expected %zu (H = %d, head width %d)", nbytes,
+                    expect, H, L1);
+      const float* w = (const float*)host;
+      for (size_t i = 0; i < nbytes / sizeof(float); i++)
+        if (!std::isfinite(w[i]))
+          return fail(MPPIB_ERR_INVALID_ARG, "LSTM weight %zu is not finite", i);
+      if (!e->lstm_theta_d)
+        CUDA_TRY(cudaMalloc(&e->lstm_theta_d, nbytes));
+      CUDA_TRY(cudaMemcpyAsync(e->lstm_theta_d, host, nbytes, cudaMemcpyHostToDevice, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      e->have_lstm = true;
       return MPPIB_OK;
     }
     case MPPIB_BLOB_COSTMAP:
@@ -1114,7 +1327,7 @@ int mppib_burn_draws(mppib_engine* e, int n)
   if (!e || n < 0)
     return fail(MPPIB_ERR_INVALID_ARG, "bad argument");
   // skipping is free for a counter-positioned stream: just move the absolute offset
-  e->rng_offset += (unsigned long long)n * e->N * e->TC;  // generators are re-positioned lazily by gen_draw
+  e->rng_offset += (unsigned long long)n * e->draw_global;  // generators are re-positioned lazily by gen_draw
   e->prefetch_valid = false;
   return MPPIB_OK;
 }
@@ -1167,7 +1380,7 @@ int mppib_draw_noise(mppib_engine* e)
   if (!e)
     return fail(MPPIB_ERR_INVALID_ARG, "null engine");
   CUDA_TRY(cudaSetDevice(e->desc.device));
-  int rc = draw_noise(*e);
+  int rc = draw_noise(*e, e->colored_offset_t);
   if (rc != MPPIB_OK)
     return rc;
   CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -1211,7 +1424,7 @@ static int enqueue_solve(mppib_engine* e, const float* x0, const float* U_in, in
 {
   if (e->timing)
     CUDA_TRY(cudaEventRecord(e->ev[0], e->stream));
-  int rc = draw_noise(*e);
+  int rc = draw_noise(*e, optimization_stride);
   if (rc != MPPIB_OK)
     return rc;
   if (e->l2_flush_d)
@@ -1335,6 +1548,13 @@ int mppib_solve_wait(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
 
 int mppib_set_option(mppib_engine* e, int option, long long value)
 {
+  if (e && option == MPPIB_OPT_COLORED_OFFSET_T)
+  {
+    if (value < 0 || value >= 2 * e->T)
+      return fail(MPPIB_ERR_INVALID_ARG, "offset_t out of range");
+    e->colored_offset_t = (int)value;
+    return MPPIB_OK;
+  }
   if (!e)
     return fail(MPPIB_ERR_INVALID_ARG, "null engine");
   CUDA_TRY(cudaSetDevice(e->desc.device));

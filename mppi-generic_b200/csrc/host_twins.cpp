@@ -47,6 +47,8 @@ const mppib_control_limits* limits_of(int dyn_id, const void* p)
       return &((const mppib_di_dyn_params*)p)->lim;
     case MPPIB_DYN_AUTORALLY_NN:
       return &((const mppib_ar_nn_dyn_params*)p)->lim;
+    case MPPIB_DYN_RACER_LSTM:
+      return &((const mppib_racer_lstm_dyn_params*)p)->lim;
   }
   return nullptr;
 }
@@ -120,6 +122,177 @@ int state_deriv(int dyn_id, const void* p, const float* nn_theta, const float* x
   }
   return MPPIB_ERR_UNSUPPORTED;
 }
+
+// ---- RacerDubinsElevationLSTMSteering host twin ------------------------------------------------------------------
+// State / output indices: racer_dubins_elevation.cuh:18-39, racer_dubins.cuh:35-76
+enum
+{
+  R_VEL_X = 0, R_YAW, R_POS_X, R_POS_Y, R_STEER_ANGLE, R_BRAKE_STATE, R_ROLL, R_PITCH, R_STEER_ANGLE_RATE, R_UNC0
+};
+inline float normalize_angle(float a)  // utils/angle_utils.cuh
+{
+  const float two_pi = 6.283185307179586f, pi = 3.14159265358979f;
+  float r = fmodf(a + pi, two_pi);
+  return r <= 0.0f ? r + pi : r - pi;
+}
+
+// LSTMHelper::forward (host), utils/nn_helpers/lstm_helper.cu:267-339: gates from W_*m h + W_*i x + b, FNN head on [h; x]
+float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
+{
+  const int H = net->hidden_dim, I = MPPIB_RACER_LSTM_INPUT_DIM, L1 = net->head_hidden;
+  const int HH = H * H, IH = H * I;
+  const float* w = net->theta;
+  const float* bias = w + 4 * HH + 4 * IH;
+  std::vector<float> hn(H), cn(H);
+  for (int i = 0; i < H; i++)
+  {
+    float g[4];
+    for (int k = 0; k < 4; k++)  // k: input, forget, output, cell-update
+    {
+      const float* Wm = w + k * HH + i * H;
+      const float* Wi = w + 4 * HH + k * IH + i * I;
+      float hm = 0.0f, im = 0.0f;
+      for (int j = 0; j < H; j++)
+        hm += Wm[j] * net->hidden[j];
+      for (int j = 0; j < I; j++)
+        im += Wi[j] * in4[j];
+      g[k] = (hm + im) + bias[k * H + i];
+    }
+    const float gi = 1.0f / (1.0f + expf(-g[0])), gf = 1.0f / (1.0f + expf(-g[1])), go = 1.0f / (1.0f + expf(-g[2]));
+    cn[i] = gi * tanhf(g[3]) + gf * net->cell[i];
+    hn[i] = go * tanhf(cn[i]);
+  }
+  memcpy(net->hidden, hn.data(), sizeof(float) * H);
+  memcpy(net->cell, cn.data(), sizeof(float) * H);
+  const float* hd = w + 4 * HH + 4 * IH + 6 * H;  // head {H+I, L1, 1}: W1 | b1 | W2 | b2 (fnn_helper.cu:176-183)
+  const int IN = H + I;
+  float out = 0.0f;
+  for (int k = 0; k < L1; k++)
+  {
+    float a = 0.0f;
+    for (int j = 0; j < H; j++)
+      a += hd[k * IN + j] * hn[j];
+    for (int j = 0; j < I; j++)
+      a += hd[k * IN + H + j] * in4[j];
+    out += hd[L1 * IN + L1 + k] * tanhf(a + hd[L1 * IN + k]);
+  }
+  return out + hd[L1 * IN + 2 * L1];
+}
+
+// racer_dubins_elevation_lstm_steering.cu:90-118 (host step) and the host methods it calls
+void racer_step(const mppib_racer_lstm_dyn_params& p, const mppib_host_lstm* net, const float* x, const float* u,
+                float dt, float* xn, float* xd, float* y)
+{
+  const float vx = x[R_VEL_X];
+  const int index = (fabsf(vx) > 0.2f && fabsf(vx) <= 3.0f) + (fabsf(vx) > 3.0f) * 2;
+  const bool enable_brake = u[0] < 0.0f;
+  const float brake_error = (enable_brake * -u[0] - x[R_BRAKE_STATE]);  // racer_dubins.cu:306-319
+  xd[R_BRAKE_STATE] = fminf(fmaxf((brake_error > 0) * brake_error * p.brake_delay_constant +
+                                      (brake_error < 0) * brake_error * p.brake_delay_constant_neg,
+                                  -p.max_brake_rate_neg),
+                            p.max_brake_rate_pos);
+  const float brake_state = fminf(fmaxf(x[R_BRAKE_STATE], 0.0f), 0.25f);  // racer_dubins_elevation.cu:32-67
+  float throttle = p.c_t[index] * u[0];
+  float brake = p.c_b[index] * brake_state * (vx >= 0.0f ? -1.0f : 1.0f);
+  if (fabsf(vx) <= 0.2f)
+  {
+    throttle = p.c_t[index] * fmaxf(u[0] - p.low_min_throttle, 0.0f);
+    brake = p.c_b[index] * brake_state * -vx;
+  }
+  xd[R_VEL_X] = (!enable_brake) * throttle * p.gear_sign + brake - p.c_v[index] * vx + p.c_0;
+  xd[R_VEL_X] = fminf(fmaxf(xd[R_VEL_X], -p.clamp_ax), p.clamp_ax);
+  if (fabsf(x[R_PITCH]) < 1.57079632679489661923f)
+    xd[R_VEL_X] -= p.gravity * sinf(x[R_PITCH]);
+  const float delta = x[R_STEER_ANGLE] / p.steer_angle_scale;
+  const float tan_delta = tanf(delta);
+  xd[R_YAW] = (vx / p.wheel_base) * tan_delta;
+  const float sy = sinf(x[R_YAW]), cy = cosf(x[R_YAW]);
+  xd[R_POS_X] = vx * cy;
+  xd[R_POS_Y] = vx * sy;
+  {  // computeLSTMSteering, lstm_steering.cu:66-88
+    const float parametric_accel = (u[1] * p.steer_command_angle_scale - x[R_STEER_ANGLE]) * p.steering_constant;
+    xd[R_STEER_ANGLE_RATE] = fmaxf(fminf((parametric_accel - x[R_STEER_ANGLE_RATE]) * p.steer_accel_constant -
+                                             x[R_STEER_ANGLE_RATE] * p.steer_accel_drag_constant,
+                                         p.max_steer_rate),
+                                   -p.max_steer_rate);
+    const float in4[4] = { x[R_STEER_ANGLE] * 0.2f, x[R_STEER_ANGLE_RATE] * 0.2f, u[1], xd[R_STEER_ANGLE_RATE] * 0.2f };
+    xd[R_STEER_ANGLE_RATE] += lstm_head_forward(net, in4) * 5.0f;
+    xd[R_STEER_ANGLE] = x[R_STEER_ANGLE_RATE];
+  }
+  for (int i = 0; i < 6; i++)  // updateState, lstm_steering.cu:267-285
+    xn[i] = x[i] + xd[i] * dt;
+  xn[R_YAW] = normalize_angle(xn[R_YAW]);
+  xn[R_STEER_ANGLE] = fmaxf(fminf(xn[R_STEER_ANGLE], p.max_steer_angle), -p.max_steer_angle);
+  xn[R_STEER_ANGLE_RATE] = x[R_STEER_ANGLE_RATE] + xd[R_STEER_ANGLE_RATE] * dt;
+  xn[R_BRAKE_STATE] = fminf(fmaxf(xn[R_BRAKE_STATE], 0.0f), -p.lim.rng_lo[0]);
+  {  // computeUncertaintyPropagation, racer_dubins_elevation.cu:662-741; matrices column-major 4x4 over
+     // (VEL_X, YAW, POS_X, POS_Y); state order of the 10 covariance entries: racer_dubins_elevation.cuh:29-38
+    float A[4][4] = {}, Sg[4][4], Tm[4][4], Q[4][4] = {};  // [row][col]
+    const float c2 = cosf(delta) * cosf(delta);
+    A[0][0] = -p.c_v[index] - p.K_vel_x - (index == 0 ? 1.0f : 0.0f) * p.c_b[0] * brake_state;
+    A[0][2] = -p.K_x * cy;
+    A[0][3] = -p.K_x * sy;
+    A[1][0] = tan_delta / p.wheel_base;
+    A[1][1] = -fabsf(vx) * p.K_yaw / (p.wheel_base * c2);
+    A[1][2] = vx * p.K_y * sy / (p.wheel_base * c2);
+    A[1][3] = -vx * p.K_y * cy / (p.wheel_base * c2);
+    A[2][0] = cy;
+    A[2][1] = -sy * vx;
+    A[3][0] = sy;
+    A[3][1] = cy * vx;
+    const float* s = x + R_UNC0;  // POS_X, POS_Y, YAW, VEL_X, POS_X_Y, POS_X_YAW, POS_X_VEL_X, POS_Y_YAW, POS_Y_VEL_X, YAW_VEL_X
+    Sg[0][0] = s[3], Sg[1][1] = s[2], Sg[2][2] = s[0], Sg[3][3] = s[1];
+    Sg[1][0] = Sg[0][1] = s[9];
+    Sg[2][0] = Sg[0][2] = s[6];
+    Sg[3][0] = Sg[0][3] = s[8];
+    Sg[2][1] = Sg[1][2] = s[5];
+    Sg[3][1] = Sg[1][3] = s[7];
+    Sg[3][2] = Sg[2][3] = s[4];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++)
+        A[r][c] = (r == c) + A[r][c] * dt;
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++)
+      {
+        float acc = 0.0f;
+        for (int k = 0; k < 4; k++)
+          acc += A[r][k] * Sg[k][c];
+        Tm[r][c] = acc;
+      }
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++)
+      {
+        float acc = 0.0f;
+        for (int k = 0; k < 4; k++)
+          acc += Tm[r][k] * A[c][k];
+        Sg[r][c] = acc;
+      }
+    const float abs_vx = fabsf(vx);
+    const float side_force = abs_vx * abs_vx * tan_delta / p.wheel_base + p.gravity * sinf(x[R_ROLL]);
+    const float Q_11 = fabsf(p.Q_y_f * fabsf(side_force) * fmaxf(abs_vx - 2, 0.0f));
+    Q[0][0] = p.Q_x_acc * fabsf(xd[R_VEL_X]) + p.Q_x_v[index] * abs_vx;
+    Q[1][1] = abs_vx * (p.Q_omega_steering * fabsf(delta) + p.Q_omega_v);
+    Q[2][2] = Q_11 * sy * sy;
+    Q[2][3] = Q[3][2] = -Q_11 * sy * cy;
+    Q[3][3] = Q_11 * cy * cy;
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++)
+        Sg[r][c] += Q[r][c] * dt;
+    float* o = xn + R_UNC0;
+    o[0] = Sg[2][2], o[1] = Sg[3][3], o[2] = Sg[1][1], o[3] = Sg[0][0], o[4] = Sg[3][2], o[5] = Sg[2][1], o[6] = Sg[2][0],
+    o[7] = Sg[3][1], o[8] = Sg[3][0], o[9] = Sg[1][0];
+  }
+  xn[R_ROLL] = 0.0f;  // computeStaticSettling without an elevation map, racer_dubins.cu:427-432
+  xn[R_PITCH] = 0.0f;
+  // setOutputs, racer_dubins_elevation.cu:69-227 (output order racer_dubins.cuh:35-76)
+  y[0] = xn[R_VEL_X], y[1] = 0.0f, y[2] = xn[R_POS_X], y[3] = xn[R_POS_Y], y[4] = 0.0f, y[5] = xn[R_YAW];
+  y[6] = xn[R_ROLL], y[7] = xn[R_PITCH], y[8] = xn[R_STEER_ANGLE], y[9] = xn[R_STEER_ANGLE_RATE];
+  y[10] = y[11] = y[12] = NAN;
+  y[13] = xd[R_VEL_X], y[14] = 0.0f, y[15] = xd[R_YAW], y[16] = fabsf(xn[R_VEL_X]);
+  for (int i = 0; i < 10; i++)
+    y[17 + i] = xn[R_UNC0 + i];
+  y[27] = 0.0f;
+}
 }  // namespace
 
 extern "C" {
@@ -137,6 +310,9 @@ int mppib_host_dims(int dyn_id, int* S, int* C, int* O)
       break;
     case MPPIB_DYN_AUTORALLY_NN:
       s = 7, c = 2, o = 8;
+      break;
+    case MPPIB_DYN_RACER_LSTM:
+      s = 19, c = 2, o = 28;
       break;
     default:
       return MPPIB_ERR_UNSUPPORTED;
@@ -237,6 +413,50 @@ int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float
                              y.data());
     if (rc)
       return rc;
+    memcpy(states + (size_t)(t + 1) * S, xn.data(), sizeof(float) * S);
+    memcpy(outputs + (size_t)(t + 1) * O, y.data(), sizeof(float) * O);
+  }
+  return MPPIB_OK;
+}
+
+int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x, const float* u, float dt,
+                         float* x_next, float* xdot, float* y)
+{
+  if (!dyn_params || !net || !net->theta || !net->hidden || !net->cell || !x || !u || !x_next || !xdot || !y)
+    return MPPIB_ERR_INVALID_ARG;
+  for (int i = 0; i < 19; i++)
+    xdot[i] = 0.0f;
+  racer_step(*(const mppib_racer_lstm_dyn_params*)dyn_params, net, x, u, dt, x_next, xdot, y);
+  return MPPIB_OK;
+}
+
+int mppib_host_output_trajectory_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x0,
+                                      const float* u, int T, float dt, float* states, float* outputs)
+{
+  // controller.cuh:643-663; initializeDynamics resets the LSTM to its initial hidden / cell state
+  // (lstm_steering.cu:230-237), which the weight blob carries after the biases (lstm_helper.cu:86-87)
+  if (!dyn_params || !net || !net->theta || !x0 || !u || !states || !outputs || T <= 0)
+    return MPPIB_ERR_INVALID_ARG;
+  const int S = 19, C = 2, O = 28, H = net->hidden_dim;
+  std::vector<float> h(H), c(H), xn(S), xd(S), y(O, 0.0f);
+  const float* init = net->theta + 4 * H * H + 4 * H * MPPIB_RACER_LSTM_INPUT_DIM + 4 * H;
+  memcpy(h.data(), init, sizeof(float) * H);
+  memcpy(c.data(), init + H, sizeof(float) * H);
+  mppib_host_lstm local = *net;
+  local.hidden = h.data();
+  local.cell = c.data();
+  memcpy(states, x0, sizeof(float) * S);
+  for (int i = 0; i < O && i < S; i++)
+    y[i] = x0[i];
+  memcpy(outputs, y.data(), sizeof(float) * O);
+  const auto& p = *(const mppib_racer_lstm_dyn_params*)dyn_params;
+  for (int t = 0; t < T - 1; t++)
+  {
+    float ui[2] = { u[(size_t)t * C], u[(size_t)t * C + 1] };
+    enforce(p.lim, ui, C);
+    for (int i = 0; i < S; i++)
+      xd[i] = 0.0f;
+    racer_step(p, &local, states + (size_t)t * S, ui, dt, xn.data(), xd.data(), y.data());
     memcpy(states + (size_t)(t + 1) * S, xn.data(), sizeof(float) * S);
     memcpy(outputs + (size_t)(t + 1) * O, y.data(), sizeof(float) * O);
   }

@@ -200,5 +200,34 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
   }
 };
 
+// Quadratic tracking cost on the RACER output vector (ours, params.h: mppib_racer_quadratic_cost_params; the RACER cost
+// classes are not in the reference tree). Output indices: racer_dubins.cuh:35-76.
+struct RacerQuadraticCost : public Cost<RacerQuadraticCost, mppib_racer_quadratic_cost_params>
+{
+  __host__ __device__ static constexpr int sharedFloats(int T)
+  {
+    return T;
+  }
+  __device__ static __forceinline__ void initializeCosts(const Params& p, const Aux&, float* theta_c, int T)
+  {
+    fill_discount_table(p, theta_c, T);
+  }
+  __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux&, const float* theta_c,
+                                                           const float* y, int t, int*)
+  {
+    const float dv = y[0] - p.desired_speed;                   // BASELINK_VEL_B_X
+    const float dyaw = normalizeAngle(y[5] - p.desired_yaw);   // YAW
+    const float dy = y[3] - p.desired_y;                       // BASELINK_POS_I_Y
+    const float st = y[8];                                     // STEER_ANGLE
+    const float cost =
+        p.speed_coeff * dv * dv + p.yaw_coeff * dyaw * dyaw + p.lateral_coeff * dy * dy + p.steer_coeff * st * st;
+    return cost * theta_c[t];
+  }
+  __device__ static __forceinline__ float terminalCost(const Params&, const Aux&, const float*)
+  {
+    return 0.0f;
+  }
+};
+
 }  // namespace plugins
 }  // namespace mppib

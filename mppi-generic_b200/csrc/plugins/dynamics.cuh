@@ -49,6 +49,13 @@ struct Dynamics
   static constexpr int CONTROL_DIM = C;
   static constexpr int OUTPUT_DIM = O;
   static constexpr int SHARED_FLOATS = 0;  // SHARED_MEM_REQUEST_GRD_BYTES / 4
+  // theta_s size for models whose request depends on constructor arguments (mppib_desc.model_dims) and, for the
+  // per-sample part (SHARED_MEM_REQUEST_BLK_BYTES), on the block width
+  static int sharedFloats(const int* /*model_dims*/, int /*bx*/)
+  {
+    return CLASS_T::SHARED_FLOATS;
+  }
+  static constexpr int MAX_DISTRIBUTIONS = 2;  // systems one thread may roll out side by side (Tube / RMPPI)
   static constexpr int MAX_BLOCK_THREADS = 256;  // __launch_bounds__ of the rollout kernel for this model
   static constexpr bool UNROLL_STEPS = true;     // unroll the 4/C steps that share one 16-byte noise group
   struct Aux
@@ -92,8 +99,9 @@ struct Dynamics
       y[i] = x[i];
   }
   // dynamics.cu:131-142
-  __device__ static __forceinline__ void step(const Params& p, const float* theta_s, const float* x, float* x_next,
-                                              float* xdot, const float* u, float* y, int /*t*/, float dt)
+  template <class AUX>
+  __device__ static __forceinline__ void step(const Params& p, const AUX&, float* theta_s, const float* x,
+                                              float* x_next, float* xdot, const float* u, float* y, int /*t*/, float dt)
   {
     CLASS_T::computeStateDeriv(p, theta_s, x, u, xdot);
     CLASS_T::updateState(x, x_next, xdot, dt);
@@ -288,6 +296,406 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       state_der[i + (7 - DYNAMICS_DIM)] = a3[i];
+  }
+};
+
+
+// ---- RacerDubinsElevationLSTMSteering: dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cu:131-213,240-262
+//      (device step / computeLSTMSteering / updateState), racer_dubins.cu:281-293 (brake delay),
+//      racer_dubins_elevation.cu:767-806 (parametric acceleration, device), :336-515,662-741 (uncertainty propagation),
+//      LSTMHelper::forward utils/nn_helpers/lstm_helper.cu:341-463 + FNN head (fnn_helper.cu:419-484) -----------------
+// One thread = one sample. The parametric model and the 4x4 covariance propagation live in registers (fully unrolled);
+// the LSTM has constructor-time dimensions (Aux::H, Aux::L1 from mppib_desc.model_dims), so its weights and the
+// per-sample hidden / cell vectors live in shared memory:
+//   theta_s: gate rows  [i < H][ j < 4 : (W_ii,W_fi,W_oi,W_ci)[i][j] | j < H : (W_im,W_fm,W_om,W_cm)[i][j] | bias ] float4
+//            head       W1T[j < H+4][k < L1p] | b1[L1p] | w2[L1p] | b2 (4)                (L1p = L1 rounded up to 4)
+//            per sample hA[H][bx] | hB[H][bx] | c[H][bx]   (element [j][tid]: conflict-free, h double-buffered by step parity)
+// so one broadcast LDS.128 brings the four gate weights of a (row, input) pair and every accumulation runs in the
+// reference's order (inputs, then hidden, then bias; lstm_helper.cu:411-431). The elevation map is not built: flat
+// terrain (TwoDTextureHelper::checkTextureUse false => roll = pitch = height = 0, racer_dubins.cu:427-432).
+struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_dyn_params, 19, 2, 28>
+{
+  static constexpr int I = MPPIB_RACER_LSTM_INPUT_DIM;
+  static constexpr int MAX_BLOCK_THREADS = 128;
+  static constexpr int MAX_DISTRIBUTIONS = 1;  // the per-sample LSTM state is keyed by thread only
+  static constexpr bool UNROLL_STEPS = false;
+  static constexpr int MAX_HIDDEN = 64, MAX_HEAD = 64;
+  enum
+  {
+    VEL_X = 0, YAW, POS_X, POS_Y, STEER_ANGLE, BRAKE_STATE, ROLL, PITCH, STEER_ANGLE_RATE, UNC_POS_X, UNC_POS_Y, UNC_YAW,
+    UNC_VEL_X, UNC_POS_X_Y, UNC_POS_X_YAW, UNC_POS_X_VEL_X, UNC_POS_Y_YAW, UNC_POS_Y_VEL_X, UNC_YAW_VEL_X
+  };
+  enum
+  {
+    O_VEL_B_X = 0, O_VEL_B_Y, O_POS_I_X, O_POS_I_Y, O_POS_I_Z, O_YAW, O_ROLL, O_PITCH, O_STEER_ANGLE, O_STEER_ANGLE_RATE,
+    O_WF_UP, O_WF_FWD, O_WF_SIDE, O_ACCEL_X, O_ACCEL_Y, O_OMEGA_Z, O_TOTAL_VELOCITY, O_UNC_POS_X, O_UNC_POS_Y, O_UNC_YAW,
+    O_UNC_VEL_X, O_UNC_POS_X_Y, O_UNC_POS_X_YAW, O_UNC_POS_X_VEL_X, O_UNC_POS_Y_YAW, O_UNC_POS_Y_VEL_X, O_UNC_YAW_VEL_X
+  };
+  enum
+  {
+    U_VEL_X = 0, U_YAW, U_POS_X, U_POS_Y
+  };
+  struct Aux
+  {
+    const float* theta_d;  // MPPIB_BLOB_LSTM_WEIGHTS: LSTM block then head block (params.h)
+    int H, L1;
+  };
+  struct Layout
+  {
+    int gate, w1t, b1, w2, b2, per_thread, L1p, total;
+  };
+  __host__ __device__ static Layout layout(int H, int L1, int bx)
+  {
+    Layout l;
+    l.L1p = (L1 + 3) & ~3;
+    l.gate = 0;
+    l.w1t = l.gate + 4 * H * (I + H + 1);
+    l.b1 = l.w1t + (H + I) * l.L1p;
+    l.w2 = l.b1 + l.L1p;
+    l.b2 = l.w2 + l.L1p;
+    l.per_thread = l.b2 + 4;
+    l.total = l.per_thread + 3 * H * bx;
+    return l;
+  }
+  static int sharedFloats(const int* model_dims, int bx)
+  {
+    return layout(model_dims[0], model_dims[1], bx).total;
+  }
+  __host__ __device__ static constexpr int cm(int row, int col)
+  {
+    return col * 4 + row;  // mm::columnMajorIndex(row, col, 4)
+  }
+
+  // setOutputs, racer_dubins_elevation.cu:69-227
+  __device__ static __forceinline__ void setOutputs(const float* state_der, const float* next_state, float* output)
+  {
+    output[O_VEL_B_X] = next_state[VEL_X];
+    output[O_VEL_B_Y] = 0.0f;
+    output[O_POS_I_X] = next_state[POS_X];
+    output[O_POS_I_Y] = next_state[POS_Y];
+    output[O_PITCH] = next_state[PITCH];
+    output[O_ROLL] = next_state[ROLL];
+    output[O_YAW] = next_state[YAW];
+    output[O_STEER_ANGLE] = next_state[STEER_ANGLE];
+    output[O_STEER_ANGLE_RATE] = next_state[STEER_ANGLE_RATE];
+    output[O_WF_UP] = NAN;
+    output[O_WF_FWD] = NAN;
+    output[O_WF_SIDE] = NAN;
+    output[O_ACCEL_X] = state_der[VEL_X];
+    output[O_ACCEL_Y] = 0.0f;
+    output[O_OMEGA_Z] = state_der[YAW];
+    output[O_UNC_VEL_X] = next_state[UNC_VEL_X];
+    output[O_UNC_YAW_VEL_X] = next_state[UNC_YAW_VEL_X];
+    output[O_UNC_POS_X_VEL_X] = next_state[UNC_POS_X_VEL_X];
+    output[O_UNC_POS_Y_VEL_X] = next_state[UNC_POS_Y_VEL_X];
+    output[O_UNC_YAW] = next_state[UNC_YAW];
+    output[O_UNC_POS_X_YAW] = next_state[UNC_POS_X_YAW];
+    output[O_UNC_POS_Y_YAW] = next_state[UNC_POS_Y_YAW];
+    output[O_UNC_POS_X] = next_state[UNC_POS_X];
+    output[O_UNC_POS_X_Y] = next_state[UNC_POS_X_Y];
+    output[O_UNC_POS_Y] = next_state[UNC_POS_Y];
+    output[O_TOTAL_VELOCITY] = fabsf(next_state[VEL_X]);
+  }
+
+  // lstm_steering.cu:115-128 (initializeDynamics: LSTMHelper::initialize copies the weights to shared memory and the
+  // initial hidden / cell state into the sample's slice; outputs from the initial state)
+  __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s,
+                                                            const float* x, float* y)
+  {
+    const int H = aux.H, L1 = aux.L1, bx = blockDim.x, tid = threadIdx.x;
+    const Layout l = layout(H, L1, bx);
+    const float* g = aux.theta_d;
+    const int HH = H * H, IH = H * I;
+    const float* gb = g + 4 * HH + 4 * IH;  // b_i b_f b_o b_c
+    // gate rows
+    const int row_f4 = I + H + 1;
+    for (int q = tid; q < H * row_f4; q += bx)
+    {
+      const int i = q / row_f4, j = q - i * row_f4;
+      float4 v;
+      if (j < I)
+      {  // (W_ii, W_fi, W_oi, W_ci)[i][j]
+        const float* w = g + 4 * HH + i * I + j;
+        v = make_float4(w[0], w[IH], w[2 * IH], w[3 * IH]);
+      }
+      else if (j < I + H)
+      {  // (W_im, W_fm, W_om, W_cm)[i][j - I]
+        const float* w = g + i * H + (j - I);
+        v = make_float4(w[0], w[HH], w[2 * HH], w[3 * HH]);
+      }
+      else
+        v = make_float4(gb[i], gb[H + i], gb[2 * H + i], gb[3 * H + i]);
+      reinterpret_cast<float4*>(theta_s + l.gate)[q] = v;
+    }
+    // head {H+I, L1, 1}: W1 (L1 x (H+I) row-major) | b1 | W2 (1 x L1) | b2   (fnn_helper.cu:176-183)
+    const float* hd = g + 4 * HH + 4 * IH + 6 * H;
+    const int IN = H + I;
+    for (int q = tid; q < IN * l.L1p; q += bx)
+    {
+      const int j = q / l.L1p, k = q - j * l.L1p;
+      theta_s[l.w1t + q] = (k < L1) ? hd[k * IN + j] : 0.0f;
+    }
+    for (int k = tid; k < l.L1p; k += bx)
+    {
+      theta_s[l.b1 + k] = (k < L1) ? hd[L1 * IN + k] : 0.0f;
+      theta_s[l.w2 + k] = (k < L1) ? hd[L1 * IN + L1 + k] : 0.0f;
+    }
+    if (tid == 0)
+      theta_s[l.b2] = hd[L1 * IN + L1 + L1];
+    // per-sample hidden / cell state <- initial_hidden_, initial_cell_ (lstm_helper.cu:86-87)
+    const float* init = gb + 4 * H;
+    float* pt = theta_s + l.per_thread;
+    for (int j = 0; j < H; j++)
+    {
+      pt[j * bx + tid] = init[j];               // hA
+      pt[(2 * H + j) * bx + tid] = init[H + j];  // c
+    }
+    setOutputs(x, x, y);  // lstm_steering.cu:128
+  }
+
+  __device__ static __forceinline__ float sigmoid_dev(float v)
+  {
+    return (1.0f + tanh_fast(v * 0.5f)) * 0.5f;  // activation_functions.cuh:49-59, device branch
+  }
+
+  // LSTMHelper::forward (device) + head; returns the head's single output. h is read from the buffer of parity
+  // (t & 1) and written to the other one.
+  __device__ static __forceinline__ float lstm_forward(const Aux& aux, float* theta_s, const float (&in)[I], int t)
+  {
+    const int H = aux.H, bx = blockDim.x, tid = threadIdx.x;
+    const Layout l = layout(H, aux.L1, bx);
+    float* pt = theta_s + l.per_thread + tid;
+    const float* h_old = pt + ((t & 1) ? H * bx : 0);
+    float* h_new = pt + ((t & 1) ? 0 : H * bx);
+    float* cell = pt + 2 * H * bx;
+    const int row_f4 = I + H + 1;
+    const float4* G = reinterpret_cast<const float4*>(theta_s + l.gate);
+    for (int i = 0; i < H; i++)
+    {
+      const float4* row = G + i * row_f4;
+      float gi = 0.0f, gf = 0.0f, go = 0.0f, gc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < I; j++)
+      {
+        const float4 w = row[j];
+        gi = fmaf(w.x, in[j], gi);
+        gf = fmaf(w.y, in[j], gf);
+        go = fmaf(w.z, in[j], go);
+        gc = fmaf(w.w, in[j], gc);
+      }
+#pragma unroll 4
+      for (int j = 0; j < H; j++)
+      {
+        const float4 w = row[I + j];
+        const float hj = h_old[j * bx];
+        gi = fmaf(w.x, hj, gi);
+        gf = fmaf(w.y, hj, gf);
+        go = fmaf(w.z, hj, go);
+        gc = fmaf(w.w, hj, gc);
+      }
+      const float4 b = row[I + H];
+      gi = sigmoid_dev(gi + b.x);
+      gf = sigmoid_dev(gf + b.y);
+      go = sigmoid_dev(go + b.z);
+      gc = tanh_fast(gc + b.w);
+      const float c_next = gi * gc + gf * cell[i * bx];
+      cell[i * bx] = c_next;
+      h_new[i * bx] = tanh_fast(c_next) * go;
+    }
+    // head on [h_new ; input]: layer 1 (tanh) four neurons at a time, layer 2 (linear, one output) folded in
+    const int L1p = l.L1p;
+    const float* W1T = theta_s + l.w1t;
+    float out = 0.0f;
+    for (int k4 = 0; k4 < L1p; k4 += 4)
+    {
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll 4
+      for (int j = 0; j < H; j++)
+      {
+        const float4 w = *reinterpret_cast<const float4*>(W1T + j * L1p + k4);
+        const float a = h_new[j * bx];
+        acc.x = fmaf(w.x, a, acc.x);
+        acc.y = fmaf(w.y, a, acc.y);
+        acc.z = fmaf(w.z, a, acc.z);
+        acc.w = fmaf(w.w, a, acc.w);
+      }
+#pragma unroll
+      for (int j = 0; j < I; j++)
+      {
+        const float4 w = *reinterpret_cast<const float4*>(W1T + (H + j) * L1p + k4);
+        acc.x = fmaf(w.x, in[j], acc.x);
+        acc.y = fmaf(w.y, in[j], acc.y);
+        acc.z = fmaf(w.z, in[j], acc.z);
+        acc.w = fmaf(w.w, in[j], acc.w);
+      }
+      const float4 b = *reinterpret_cast<const float4*>(theta_s + l.b1 + k4);
+      const float4 w2 = *reinterpret_cast<const float4*>(theta_s + l.w2 + k4);  // zero for the padding neurons
+      out = fmaf(w2.x, tanh_fast(acc.x + b.x), out);
+      out = fmaf(w2.y, tanh_fast(acc.y + b.y), out);
+      out = fmaf(w2.z, tanh_fast(acc.z + b.z), out);
+      out = fmaf(w2.w, tanh_fast(acc.w + b.w), out);
+    }
+    return out + theta_s[l.b2];
+  }
+
+  __device__ static __forceinline__ float pick3(const float (&a)[3], int index)
+  {
+    return index == 0 ? a[0] : (index == 1 ? a[1] : a[2]);
+  }
+
+  __device__ static __forceinline__ void step(const Params& p, const Aux& aux, float* theta_s, const float* state,
+                                              float* next_state, float* state_der, const float* control,
+                                              float* output, int t, float dt)
+  {
+    const float vx = state[VEL_X];
+    const float linear_brake_slope = 0.2f;
+    const int index = (fabsf(vx) > linear_brake_slope && fabsf(vx) <= 3.0f) + (fabsf(vx) > 3.0f) * 2;
+    const bool enable_brake = control[0] < 0.0f;
+    // computeParametricDelayDeriv, racer_dubins.cu:281-293
+    {
+      const float brake_error = (enable_brake * -control[0] - state[BRAKE_STATE]);
+      state_der[BRAKE_STATE] = fminf(fmaxf((brake_error > 0) * brake_error * p.brake_delay_constant +
+                                               (brake_error < 0) * brake_error * p.brake_delay_constant_neg,
+                                           -p.max_brake_rate_neg),
+                                     p.max_brake_rate_pos);
+    }
+    const float brake_state = fminf(fmaxf(state[BRAKE_STATE], 0.0f), 0.25f);
+    const float c_t = pick3(p.c_t, index), c_b = pick3(p.c_b, index), c_v = pick3(p.c_v, index);
+    // computeParametricAccelDeriv (device), racer_dubins_elevation.cu:767-806
+    {
+      float throttle = c_t * control[0];
+      float brake = c_b * brake_state * (vx >= 0.0f ? -1.0f : 1.0f);
+      if (fabsf(vx) <= linear_brake_slope)
+      {
+        throttle = c_t * fmaxf(control[0] - p.low_min_throttle, 0.0f);
+        brake = c_b * brake_state * -vx;
+      }
+      state_der[VEL_X] = (!enable_brake) * throttle * p.gear_sign + brake - c_v * vx + p.c_0;
+      state_der[VEL_X] = fminf(fmaxf(state_der[VEL_X], -p.clamp_ax), p.clamp_ax);
+      if (fabsf(state[PITCH]) < 1.57079632679489661923f)
+        state_der[VEL_X] -= p.gravity * __sinf(normalizeAngle(state[PITCH]));
+      state_der[YAW] = (vx / p.wheel_base) * __tanf(normalizeAngle(state[STEER_ANGLE] / p.steer_angle_scale));
+    }
+    const float yaw_norm = normalizeAngle(state[YAW]);
+    float sin_yaw, cos_yaw;
+    __sincosf(yaw_norm, &sin_yaw, &cos_yaw);
+    state_der[POS_X] = vx * cos_yaw;
+    state_der[POS_Y] = vx * sin_yaw;
+    // computeLSTMSteering (device), lstm_steering.cu:131-166
+    {
+      const float parametric_accel =
+          (control[1] * p.steer_command_angle_scale - state[STEER_ANGLE]) * p.steering_constant;
+      state_der[STEER_ANGLE_RATE] =
+          fmaxf(fminf((parametric_accel - state[STEER_ANGLE_RATE]) * p.steer_accel_constant -
+                          state[STEER_ANGLE_RATE] * p.steer_accel_drag_constant,
+                      p.max_steer_rate),
+                -p.max_steer_rate);
+      float in[I];
+      in[0] = state[STEER_ANGLE] * 0.2f;
+      in[1] = state[STEER_ANGLE_RATE] * 0.2f;
+      in[2] = control[1];
+      in[3] = state_der[STEER_ANGLE_RATE] * 0.2f;
+      const float nn_output = lstm_forward(aux, theta_s, in, t);
+      state_der[STEER_ANGLE_RATE] += nn_output * 5.0f;
+      state_der[STEER_ANGLE] = state[STEER_ANGLE_RATE];
+    }
+    // updateState (device), lstm_steering.cu:240-262
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+      next_state[i] = state[i] + state_der[i] * dt;
+    next_state[YAW] = normalizeAngle(next_state[YAW]);
+    next_state[STEER_ANGLE] = fmaxf(fminf(next_state[STEER_ANGLE], p.max_steer_angle), -p.max_steer_angle);
+    next_state[STEER_ANGLE_RATE] = state[STEER_ANGLE_RATE] + state_der[STEER_ANGLE_RATE] * dt;
+    next_state[BRAKE_STATE] = fminf(fmaxf(next_state[BRAKE_STATE], 0.0f), 1.0f);
+    // computeUncertaintyPropagation (device), racer_dubins_elevation.cu:662-741
+    {
+      float A[16], Sa[16], Sb[16];
+      const float delta = state[STEER_ANGLE] / p.steer_angle_scale;
+      const float tan_steer_angle = __tanf(delta);
+      const float cos_2_delta = MPPIB_SQ(__cosf(delta));
+      // computeUncertaintyJacobian :336-425
+      A[cm(U_VEL_X, U_VEL_X)] = -c_v - p.K_vel_x - (index == 0 ? 1.0f : 0.0f) * p.c_b[0] * brake_state;
+      A[cm(U_VEL_X, U_YAW)] = 0.0f;
+      A[cm(U_VEL_X, U_POS_X)] = -p.K_x * cos_yaw;
+      A[cm(U_VEL_X, U_POS_Y)] = -p.K_x * sin_yaw;
+      A[cm(U_YAW, U_VEL_X)] = tan_steer_angle / (p.wheel_base);
+      A[cm(U_YAW, U_YAW)] = -fabsf(vx) * p.K_yaw / (p.wheel_base * cos_2_delta);
+      A[cm(U_YAW, U_POS_X)] = vx * p.K_y * sin_yaw / (p.wheel_base * cos_2_delta);
+      A[cm(U_YAW, U_POS_Y)] = -vx * p.K_y * cos_yaw / (p.wheel_base * cos_2_delta);
+      A[cm(U_POS_X, U_VEL_X)] = cos_yaw;
+      A[cm(U_POS_X, U_YAW)] = -sin_yaw * vx;
+      A[cm(U_POS_X, U_POS_X)] = 0.0f;
+      A[cm(U_POS_X, U_POS_Y)] = 0.0f;
+      A[cm(U_POS_Y, U_VEL_X)] = sin_yaw;
+      A[cm(U_POS_Y, U_YAW)] = cos_yaw * vx;
+      A[cm(U_POS_Y, U_POS_Y)] = 0.0f;
+      A[cm(U_POS_Y, U_POS_X)] = 0.0f;
+      // uncertaintyStateToMatrix :517-577
+      Sa[cm(U_VEL_X, U_VEL_X)] = state[UNC_VEL_X];
+      Sa[cm(U_YAW, U_VEL_X)] = Sa[cm(U_VEL_X, U_YAW)] = state[UNC_YAW_VEL_X];
+      Sa[cm(U_POS_X, U_VEL_X)] = Sa[cm(U_VEL_X, U_POS_X)] = state[UNC_POS_X_VEL_X];
+      Sa[cm(U_POS_Y, U_VEL_X)] = Sa[cm(U_VEL_X, U_POS_Y)] = state[UNC_POS_Y_VEL_X];
+      Sa[cm(U_YAW, U_YAW)] = state[UNC_YAW];
+      Sa[cm(U_POS_X, U_YAW)] = Sa[cm(U_YAW, U_POS_X)] = state[UNC_POS_X_YAW];
+      Sa[cm(U_POS_Y, U_YAW)] = Sa[cm(U_YAW, U_POS_Y)] = state[UNC_POS_Y_YAW];
+      Sa[cm(U_POS_X, U_POS_X)] = state[UNC_POS_X];
+      Sa[cm(U_POS_Y, U_POS_X)] = Sa[cm(U_POS_X, U_POS_Y)] = state[UNC_POS_X_Y];
+      Sa[cm(U_POS_Y, U_POS_Y)] = state[UNC_POS_Y];
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        A[i] = (i % 5 == 0) + A[i] * dt;  // I + A dt
+      // Sigma_b = A Sigma_a ; Sigma_a = Sigma_b A^T   (mm::gemm1, k ascending)
+#pragma unroll
+      for (int col = 0; col < 4; col++)
+#pragma unroll
+        for (int row = 0; row < 4; row++)
+        {
+          float acc = 0.0f;
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            acc += A[cm(row, q)] * Sa[cm(q, col)];
+          Sb[cm(row, col)] = acc;
+        }
+#pragma unroll
+      for (int col = 0; col < 4; col++)
+#pragma unroll
+        for (int row = 0; row < 4; row++)
+        {
+          float acc = 0.0f;
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            acc += Sb[cm(row, q)] * A[cm(col, q)];
+          Sa[cm(row, col)] = acc;
+        }
+      // computeQ :427-515 (device branch), added as Q dt
+      const float abs_vx = fabsf(vx);
+      const float abs_acc_x = fabsf(state_der[VEL_X]);
+      const float sin_roll = __sinf(normalizeAngle(state[ROLL]));
+      const float side_force = MPPIB_SQ(abs_vx) * tan_steer_angle / p.wheel_base + p.gravity * sin_roll;
+      const float Q_11 = fabsf(p.Q_y_f * fabsf(side_force) * fmaxf(abs_vx - 2, 0.0f));
+      Sa[cm(U_VEL_X, U_VEL_X)] += (p.Q_x_acc * abs_acc_x + pick3(p.Q_x_v, index) * abs_vx) * dt;
+      Sa[cm(U_YAW, U_YAW)] += (abs_vx * (p.Q_omega_steering * fabsf(delta) + p.Q_omega_v)) * dt;
+      Sa[cm(U_POS_X, U_POS_X)] += (Q_11 * sin_yaw * sin_yaw) * dt;
+      Sa[cm(U_POS_X, U_POS_Y)] += (-Q_11 * sin_yaw * cos_yaw) * dt;
+      Sa[cm(U_POS_Y, U_POS_Y)] += (Q_11 * cos_yaw * cos_yaw) * dt;
+      Sa[cm(U_POS_Y, U_POS_X)] += (-Q_11 * sin_yaw * cos_yaw) * dt;
+      // uncertaintyMatrixToState :579-621
+      next_state[UNC_VEL_X] = Sa[cm(U_VEL_X, U_VEL_X)];
+      next_state[UNC_YAW_VEL_X] = Sa[cm(U_YAW, U_VEL_X)];
+      next_state[UNC_POS_X_VEL_X] = Sa[cm(U_POS_X, U_VEL_X)];
+      next_state[UNC_POS_Y_VEL_X] = Sa[cm(U_POS_Y, U_VEL_X)];
+      next_state[UNC_YAW] = Sa[cm(U_YAW, U_YAW)];
+      next_state[UNC_POS_X_YAW] = Sa[cm(U_POS_X, U_YAW)];
+      next_state[UNC_POS_Y_YAW] = Sa[cm(U_POS_Y, U_YAW)];
+      next_state[UNC_POS_X] = Sa[cm(U_POS_X, U_POS_X)];
+      next_state[UNC_POS_X_Y] = Sa[cm(U_POS_Y, U_POS_X)];
+      next_state[UNC_POS_Y] = Sa[cm(U_POS_Y, U_POS_Y)];
+    }
+    // static settling without an elevation map (racer_dubins.cu:427-432)
+    output[O_POS_I_Z] = 0.0f;
+    next_state[PITCH] = 0.0f;
+    next_state[ROLL] = 0.0f;
+    setOutputs(state_der, next_state, output);
   }
 };
 

@@ -64,6 +64,7 @@ struct RolloutArgs
   int pstride;  // floats per (block, distribution) partial record
   int opt_stride;
   int use_tma;
+  int dyn_shared_floats;  // DYN::sharedFloats(model_dims, blockDim.x): theta_s size (run-time for the LSTM model)
   float dt, lambda, alpha, lambda_inv;
   float x0[MPPIB_MAX_DISTRIBUTIONS * kMaxStateDim];  // [D][S]
   float means[kMaxMeanFloats];                       // [D][T][C] importance-sampler mean == nominal control
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
 {
   constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
   static_assert(C == 1 || C == 2 || C == 4, "CONTROL_DIM must divide a 16-byte group");
+  static_assert(D <= MPPIB_MAX_DISTRIBUTIONS, "too many distributions");
   constexpr int STEPS_PER_GROUP = 4 / C;
 
   extern __shared__ unsigned char smem_raw[];
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   const int T = args.T;
   const int TC = T * C;
   const int nchunks = args.nchunks;
-  const RolloutSmem L = rollout_smem_layout(bx, nchunks, D, TC, DYN::SHARED_FLOATS, COST::sharedFloats(T));
+  const RolloutSmem L = rollout_smem_layout(bx, nchunks, D, TC, args.dyn_shared_floats, COST::sharedFloats(T));
   unsigned char* tile = smem + L.tile;
   float* means_s = reinterpret_cast<float*>(smem + L.means);
   float* theta_s = reinterpret_cast<float*>(smem + L.theta);
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
 #pragma unroll
           for (int i = 0; i < S; i++)
             xdot[i] = 0.0f;
-          DYN::step(args.dyn, theta_s, x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
+          DYN::step(args.dyn, args.dyn_aux, theta_s, x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
           float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[d], u, t, &crash_status[d]);
           if (lr_on)
             step_cost += likelihood_ratio_cost<C>(lr_scale[d], mean_t, u, pure_noise, half_lambda_1ma);  // :126-128

@@ -30,6 +30,14 @@ SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
 BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR = 1, 2, 4, 8, 16
 OPT_L2_FLUSH_BYTES = 1
+OPT_COLORED_OFFSET_T = 2
+RACER_LSTM_INPUT_DIM = 4
+
+
+def racer_lstm_num_params(hidden_dim: int, head_hidden: int) -> int:
+    """MPPIB_RACER_LSTM_NUM_PARAMS (params.h): LSTM block (lstm_helper.cu:72-88) + head {H+4, L1, 1} (fnn_helper.cu:176-183)."""
+    H, L1 = hidden_dim, head_hidden
+    return 4 * H * H + 4 * H * 4 + 6 * H + (H + 4) * L1 + L1 + L1 + 1
 AR_NN_NUM_PARAMS = 1412
 
 
@@ -74,6 +82,30 @@ class ARNNDynParams(C.Structure):
     _fields_ = [("lim", ControlLimits)]
 
 
+class RacerLSTMDynParams(C.Structure):
+    _fields_ = [("lim", ControlLimits), ("c_t", C.c_float * 3), ("c_b", C.c_float * 3), ("c_v", C.c_float * 3),
+                ("c_0", C.c_float), ("steering_constant", C.c_float), ("steer_command_angle_scale", C.c_float),
+                ("steer_angle_scale", C.c_float), ("max_steer_angle", C.c_float), ("max_steer_rate", C.c_float),
+                ("steer_accel_constant", C.c_float), ("steer_accel_drag_constant", C.c_float),
+                ("brake_delay_constant", C.c_float), ("brake_delay_constant_neg", C.c_float),
+                ("max_brake_rate_neg", C.c_float), ("max_brake_rate_pos", C.c_float), ("wheel_base", C.c_float),
+                ("low_min_throttle", C.c_float), ("gravity", C.c_float), ("gear_sign", C.c_int),
+                ("clamp_ax", C.c_float), ("K_x", C.c_float), ("K_y", C.c_float), ("K_yaw", C.c_float),
+                ("K_vel_x", C.c_float), ("Q_x_acc", C.c_float), ("Q_x_v", C.c_float * 3), ("Q_y_f", C.c_float),
+                ("Q_omega_v", C.c_float), ("Q_omega_steering", C.c_float)]
+
+
+class RacerQuadraticCostParams(C.Structure):
+    _fields_ = [("control_cost_coeff", C.c_float * MAX_C), ("discount", C.c_float), ("desired_speed", C.c_float),
+                ("speed_coeff", C.c_float), ("desired_yaw", C.c_float), ("yaw_coeff", C.c_float),
+                ("desired_y", C.c_float), ("lateral_coeff", C.c_float), ("steer_coeff", C.c_float)]
+
+
+class HostLSTM(C.Structure):
+    _fields_ = [("theta", C.c_void_p), ("hidden_dim", C.c_int), ("head_hidden", C.c_int), ("hidden", C.c_void_p),
+                ("cell", C.c_void_p)]
+
+
 class CartpoleCostParams(C.Structure):
     _fields_ = [("control_cost_coeff", C.c_float * MAX_C), ("discount", C.c_float),
                 ("cart_position_coeff", C.c_float), ("cart_velocity_coeff", C.c_float),
@@ -106,7 +138,8 @@ class GaussianParams(C.Structure):
 class Desc(C.Structure):
     _fields_ = [("dynamics_id", C.c_int), ("cost_id", C.c_int), ("sampler_id", C.c_int), ("num_rollouts", C.c_int),
                 ("num_timesteps", C.c_int), ("num_distributions", C.c_int), ("device", C.c_int),
-                ("flags", C.c_uint), ("stream", C.c_void_p), ("rank", C.c_int), ("world_size", C.c_int)]
+                ("flags", C.c_uint), ("stream", C.c_void_p), ("rank", C.c_int), ("world_size", C.c_int),
+                ("model_dims", C.c_int * 8)]
 
 
 class SolveStats(C.Structure):
@@ -129,7 +162,7 @@ ABI_SYMBOLS = [
     "mppib_local_rollouts", "mppib_strerror", "mppib_last_error", "mppib_version",
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
-    "mppib_host_merge_records",
+    "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
 ]
 
 _lib = None
@@ -180,6 +213,8 @@ def lib() -> C.CDLL:
     L.mppib_host_slide_controls.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.mppib_host_slide_controls.restype = None
     L.mppib_host_output_trajectory.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp]
+    L.mppib_host_step_lstm.argtypes = [vp, C.POINTER(HostLSTM), vp, vp, C.c_float, vp, vp, vp]
+    L.mppib_host_output_trajectory_lstm.argtypes = [vp, C.POINTER(HostLSTM), vp, vp, C.c_int, C.c_float, vp, vp]
     L.mppib_host_free_energy.argtypes = [C.POINTER(SolveStats), C.c_int, C.c_float, vp]
     L.mppib_host_free_energy.restype = None
     L.mppib_host_merge_records.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]
@@ -212,6 +247,16 @@ class _Dynamics:
     def __init__(self):
         self.params = None
         self.nn_theta: Optional[np.ndarray] = None
+
+    def model_dims(self) -> Sequence[int]:
+        """Constructor-time architecture arguments that size the kernel (mppib_desc.model_dims)."""
+        return ()
+
+    def output_trajectory(self, x0, u, T: int, dt: float, states: np.ndarray, outputs: np.ndarray) -> None:
+        """Controller::computeOutputTrajectoryHelper (controller.cuh:643-663) with this model's host step."""
+        _check(lib().mppib_host_output_trajectory(self.DYN_ID, C.byref(self.params), _ptr(self.nn_theta),
+                                                  _ptr(_f32(x0)), _ptr(u), T, C.c_float(dt), _ptr(states),
+                                                  _ptr(outputs)))
 
     # dynamics.cuh:163-175
     def setControlRanges(self, control_rngs: Sequence[Sequence[float]]):
@@ -294,6 +339,101 @@ class NeuralNetModel(_Dynamics):
         if data.size != AR_NN_NUM_PARAMS or not np.all(np.isfinite(data)):
             raise ValueError("NN parameter vector must hold 1412 finite floats")
         self.nn_theta = data.copy()
+
+
+class RacerDubinsElevationLSTMSteering(_Dynamics):
+    """dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cuh:34-49 —
+    RacerDubinsElevationLSTMSteering(init_input_dim, init_hidden_dim, init_output_layers, input_dim, hidden_dim,
+    output_layers, init_len). The prediction LSTM (input_dim must be 4, output_layers = [hidden_dim + 4, L1, 1]) runs
+    inside the rollout; the init network (LSTMLSTMHelper) only produces the initial hidden / cell state from a history
+    buffer on the host (updateFromBuffer, :215-232) and is represented here by that state itself
+    (``setInitialHiddenCell``). No elevation map: flat terrain."""
+    DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_RACER_LSTM, 19, 2, 28
+
+    def __init__(self, init_input_dim: int = 3, init_hidden_dim: int = 20, init_output_layers: Sequence[int] = (23, 100, 8),
+                 input_dim: int = 4, hidden_dim: int = 4, output_layers: Sequence[int] = (8, 20, 1), init_len: int = 11):
+        super().__init__()
+        output_layers = tuple(output_layers)
+        if input_dim != RACER_LSTM_INPUT_DIM:
+            raise ValueError("the steering LSTM takes 4 inputs (lstm_steering.cu:148-151)")
+        if len(output_layers) != 3 or output_layers[0] != hidden_dim + input_dim or output_layers[2] != 1:
+            raise ValueError("output_layers must be [hidden_dim + 4, L1, 1] (lstm_helper.cu:41)")
+        if tuple(init_output_layers)[-1] != 2 * hidden_dim:
+            raise ValueError("init network must output 2 * hidden_dim values (lstm_lstm_helper.cu:11)")
+        self.hidden_dim, self.head_hidden = hidden_dim, output_layers[1]
+        p = RacerLSTMDynParams()
+        p.lim.set_defaults()
+        # racer_dubins.cuh:78-104, racer_dubins_elevation.cuh:47-59
+        for i, v in enumerate((1.3, 2.6, 3.9)):
+            p.c_t[i] = v
+        for i, v in enumerate((2.5, 3.5, 4.5)):
+            p.c_b[i] = v
+        for i, v in enumerate((3.7, 4.7, 5.7)):
+            p.c_v[i] = v
+        p.c_0 = 4.9
+        p.steering_constant, p.steer_command_angle_scale, p.steer_angle_scale = 0.6, 5.0, -9.1
+        p.max_steer_angle, p.max_steer_rate = 0.5, 5.0
+        p.steer_accel_constant, p.steer_accel_drag_constant = 12.1, 1.0
+        p.brake_delay_constant, p.brake_delay_constant_neg = 6.6, 8.2
+        p.max_brake_rate_neg, p.max_brake_rate_pos = 0.9, 0.33
+        p.wheel_base, p.low_min_throttle, p.gravity, p.gear_sign = 0.3, 0.13, -9.81, 1
+        p.clamp_ax = 5.5
+        p.K_x = p.K_y = p.K_yaw = p.K_vel_x = 1.0
+        p.Q_x_acc = 1.0
+        for i, v in enumerate((41.74219, -0.8187027, -2.2131343)):
+            p.Q_x_v[i] = v
+        p.Q_y_f, p.Q_omega_v, p.Q_omega_steering = 0.1, 0.001, 0.0
+        self.params = p
+        self.lstm_theta = np.zeros(racer_lstm_num_params(self.hidden_dim, self.head_hidden), np.float32)
+
+    def model_dims(self) -> Sequence[int]:
+        return (self.hidden_dim, self.head_hidden)
+
+    def _lstm_block(self) -> int:
+        H = self.hidden_dim
+        return 4 * H * H + 4 * H * RACER_LSTM_INPUT_DIM + 6 * H
+
+    def setAllValues(self, lstm, output) -> None:
+        """LSTMHelper::setAllValues(lstm, output) (lstm_helper.cuh:65-72): packed LSTM weights incl. the initial hidden /
+        cell vectors, then the packed head."""
+        lstm, output = _f32(lstm).ravel(), _f32(output).ravel()
+        if lstm.size != self._lstm_block() or lstm.size + output.size != self.lstm_theta.size:
+            raise ValueError("wrong number of LSTM / head parameters")
+        if not (np.all(np.isfinite(lstm)) and np.all(np.isfinite(output))):
+            raise ValueError("LSTM parameters must be finite")
+        self.lstm_theta = np.concatenate([lstm, output]).astype(np.float32)
+
+    def setInitialHiddenCell(self, hidden, cell) -> None:
+        """LSTMHelper::updateLSTMInitialStates (lstm_helper.cu:98-110)."""
+        H, base = self.hidden_dim, self._lstm_block() - 2 * self.hidden_dim
+        self.lstm_theta[base:base + H] = _f32(hidden)
+        self.lstm_theta[base + H:base + 2 * H] = _f32(cell)
+
+    def _host_net(self, hidden: np.ndarray, cell: np.ndarray) -> HostLSTM:
+        return HostLSTM(self.lstm_theta.ctypes.data, self.hidden_dim, self.head_hidden, hidden.ctypes.data,
+                        cell.ctypes.data)
+
+    def initial_hidden_cell(self):
+        H, base = self.hidden_dim, self._lstm_block() - 2 * self.hidden_dim
+        return self.lstm_theta[base:base + H].copy(), self.lstm_theta[base + H:base + 2 * H].copy()
+
+    def step(self, state, control, dt: float, hidden=None, cell=None):
+        """Host step; returns (next_state, state_der, output, hidden, cell)."""
+        h0, c0 = self.initial_hidden_cell()
+        h = h0 if hidden is None else _f32(hidden).copy()
+        c = c0 if cell is None else _f32(cell).copy()
+        x, u = _f32(state), _f32(control)
+        xn, xd, y = np.zeros(19, np.float32), np.zeros(19, np.float32), np.zeros(28, np.float32)
+        net = self._host_net(h, c)
+        _check(lib().mppib_host_step_lstm(C.byref(self.params), C.byref(net), _ptr(x), _ptr(u), C.c_float(dt),
+                                          _ptr(xn), _ptr(xd), _ptr(y)))
+        return xn, xd, y, h, c
+
+    def output_trajectory(self, x0, u, T: int, dt: float, states: np.ndarray, outputs: np.ndarray) -> None:
+        h, c = self.initial_hidden_cell()
+        net = self._host_net(h, c)
+        _check(lib().mppib_host_output_trajectory_lstm(C.byref(self.params), C.byref(net), _ptr(_f32(x0)), _ptr(u), T,
+                                                       C.c_float(dt), _ptr(states), _ptr(outputs)))
 
 
 class _Cost:
@@ -389,6 +529,21 @@ class ARStandardCost(_Cost):
         self.updateTransform(R, trs)
 
 
+class RacerQuadraticCost(_Cost):
+    """Quadratic tracking cost on the RACER output vector (ours; params.h: mppib_racer_quadratic_cost_params)."""
+    COST_ID = COST_RACER_QUADRATIC
+
+    def __init__(self):
+        super().__init__()
+        p = RacerQuadraticCostParams()
+        p.discount = 1.0
+        p.desired_speed, p.speed_coeff = 5.0, 4.0
+        p.desired_yaw, p.yaw_coeff = 0.0, 20.0
+        p.desired_y, p.lateral_coeff = 0.0, 2.0
+        p.steer_coeff = 1.0
+        self.params = p
+
+
 class GaussianDistribution:
     """sampling_distributions/gaussian/gaussian.cuh:63-… — owns the sampling parameters (GaussianParamsImpl :21-61)."""
     SAMPLER_ID = SAMPLER_GAUSSIAN
@@ -421,6 +576,25 @@ class GaussianDistribution:
         return bytes(self.params)
 
 
+class ColoredNoiseDistribution(GaussianDistribution):
+    """sampling_distributions/colored_noise/colored_noise.cuh:41-… — Gaussian parameters + exponents per control
+    (0 white, 1 pink, 2 brown), offset_decay_rate (0.97) and fmin."""
+    SAMPLER_ID = SAMPLER_COLORED_NOISE
+
+    def __init__(self, control_dim: int, std_dev: Optional[Sequence[float]] = None,
+                 exponents: Optional[Sequence[float]] = None):
+        super().__init__(control_dim, std_dev)
+        if exponents is not None:
+            self.setExponents(exponents)
+
+    def setExponents(self, exponents: Sequence[float]) -> None:
+        for c, v in enumerate(exponents):
+            self.params.exponents[c] = v
+
+    def setOffsetDecayRate(self, v: float) -> None:  # colored_noise.cuh setOffsetDecayRate
+        self.params.offset_decay_rate = v
+
+
 # ---------------------------------------------------------------------------------------------------------------
 class Engine:
     """Thin RAII wrapper of the opaque mppib_engine (one per controller)."""
@@ -434,6 +608,8 @@ class Engine:
         self.S, self.Cdim, self.O = dyn.STATE_DIM, dyn.CONTROL_DIM, dyn.OUTPUT_DIM
         d = Desc(dyn.DYN_ID, cost.COST_ID, sampler.SAMPLER_ID, num_rollouts, num_timesteps, num_distributions, device,
                  flags, stream, rank, world_size)
+        for i, v in enumerate(dyn.model_dims()):
+            d.model_dims[i] = v
         _check(lib().mppib_create(C.byref(self._h), C.byref(d)))
         self.push_params()
         nl, no = C.c_int(), C.c_int()
@@ -451,6 +627,9 @@ class Engine:
         if self.dyn.DYN_ID == DYN_AUTORALLY_NN:
             w = _f32(self.dyn.nn_theta)
             _check(L.mppib_set_blob(self._h, BLOB_NN_WEIGHTS, _ptr(w), w.nbytes))
+        if self.dyn.DYN_ID == DYN_RACER_LSTM:
+            w = _f32(self.dyn.lstm_theta)
+            _check(L.mppib_set_blob(self._h, BLOB_LSTM_WEIGHTS, _ptr(w), w.nbytes))
         if self.cost.COST_ID == COST_AR_STANDARD:
             if self.cost.costmap is None:
                 raise MppibError(-9, "ARStandardCost has no costmap (call loadTrackData / setCostmap)")
@@ -661,10 +840,7 @@ class _Controller:
                                         _ptr(self.slide_control_scale_))
 
     def _output_trajectory(self, x0: np.ndarray, u: np.ndarray, states: np.ndarray, outputs: np.ndarray) -> None:
-        _check(lib().mppib_host_output_trajectory(self.model_.DYN_ID, C.byref(self.model_.params),
-                                                  _ptr(self.model_.nn_theta), _ptr(_f32(x0)), _ptr(u),
-                                                  self.num_timesteps_, C.c_float(self.dt_), _ptr(states),
-                                                  _ptr(outputs)))
+        self.model_.output_trajectory(x0, u, self.num_timesteps_, self.dt_, states, outputs)
 
     def _save_control_history(self, steps: int, u: np.ndarray) -> None:  # controller.cuh:602-616
         if steps == 1:

@@ -124,7 +124,51 @@ def autorally(N: int = 32768, T: int = 100) -> Workload:
     return Workload(f"autorally_nn_N{N}_T{T}", "vanilla", dyn, cost, sampler, N, T, 1, 0.02, 6.67, 0.0, x0, U0)
 
 
+def synthetic_lstm_weights(hidden_dim: int = 4, head_hidden: int = 20, seed: int = 2) -> tuple:
+    """(lstm, head) ~ U(-1,1)/sqrt(fan_in) in the reference's packed layouts (lstm_helper.cu:72-88, fnn_helper.cu:176-183),
+    initial hidden / cell state zero. The RACER networks are not in the reference tree."""
+    rng = np.random.RandomState(seed)
+    Hd, I = hidden_dim, H.RACER_LSTM_INPUT_DIM
+    parts = [rng.uniform(-1, 1, 4 * Hd * Hd) / math.sqrt(Hd + I), rng.uniform(-1, 1, 4 * Hd * I) / math.sqrt(Hd + I),
+             rng.uniform(-1, 1, 4 * Hd) / math.sqrt(Hd + I), np.zeros(2 * Hd)]
+    lstm = np.concatenate(parts).astype(np.float32)
+    IN = Hd + I
+    head = np.concatenate([rng.uniform(-1, 1, head_hidden * IN) / math.sqrt(IN), rng.uniform(-1, 1, head_hidden) / math.sqrt(IN),
+                           rng.uniform(-1, 1, head_hidden) / math.sqrt(head_hidden),
+                           rng.uniform(-1, 1, 1) / math.sqrt(head_hidden)]).astype(np.float32)
+    return lstm, head
+
+
+def racer_lstm(N: int = 65536, T: int = 150, hidden_dim: int = 4, head_hidden: int = 20, colored: bool = True) -> Workload:
+    """C5: RacerDubinsElevationLSTMSteering (the in-tree LSTM vehicle model, S19 C2 O28; constructor
+    (3, 20, {23, 100, 2H}, 4, H, {H+4, 20, 1}, 11), tests/dynamics/racer_dubins_elevation_lstm_steering_model_test.cu:26-32)
+    on flat terrain + ColoredNoise sampler (exponents (1, 1), offset_decay_rate 0.97, colored_noise.cuh:47-49) + our quadratic
+    tracking cost."""
+    dyn = H.RacerDubinsElevationLSTMSteering(3, 20, (23, 100, 2 * hidden_dim), 4, hidden_dim,
+                                             (hidden_dim + 4, head_hidden, 1), 11)
+    dyn.setControlRanges([(-1.0, 1.0), (-1.0, 1.0)])  # throttle/brake, steering command
+    dyn.setAllValues(*synthetic_lstm_weights(hidden_dim, head_hidden, 2))
+    cost = H.RacerQuadraticCost()
+    if colored:
+        sampler = H.ColoredNoiseDistribution(2, [0.3, 0.3], [1.0, 1.0])
+    else:
+        sampler = H.GaussianDistribution(2, [0.3, 0.3])
+    x0 = np.zeros((1, 19), np.float32)
+    x0[0, 0] = 3.0  # VEL_X
+    x0[0, 9:13] = 1e-6  # covariance diagonal floor (racer_dubins_elevation.cu stateFromMap)
+    U0 = np.zeros((1, T, 2), np.float32)
+    tag = "colored" if colored else "gaussian"
+    return Workload(f"racer_lstm_H{hidden_dim}_{tag}_N{N}_T{T}", "vanilla", dyn, cost, sampler, N, T, 1, 0.02, 1.0, 0.0,
+                    x0, U0)
+
+
+def racer_lstm_gaussian(N: int = 4096, T: int = 100) -> Workload:
+    return racer_lstm(N, T, colored=False)
+
+
 BUILDERS = {
+    "racer_lstm": racer_lstm,
+    "racer_lstm_gaussian": racer_lstm_gaussian,
     "cartpole": cartpole,
     "double_integrator_tube": double_integrator_tube,
     "double_integrator_vanilla": double_integrator_vanilla,

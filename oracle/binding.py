@@ -183,3 +183,50 @@ def output_trajectory(dyn_id, dyn_params, nn_theta, x0, u, dt):
     if rc:
         raise RuntimeError("orc_output_trajectory failed")
     return states, outputs
+
+
+_lstm_keepalive = None
+
+
+def set_lstm(theta, hidden_dim: int, head_hidden: int) -> None:
+    """LSTM weights/architecture for MPPIB_DYN_RACER_LSTM (kept by pointer inside the oracle)."""
+    global _lstm_keepalive
+    _lstm_keepalive = _f32(theta).copy()
+    lib().orc_set_lstm(_p(_lstm_keepalive), hidden_dim, head_hidden)
+
+
+def lstm_forward(lstm_w, input_dim, hidden_dim, head_theta, head_layers, inp, h, c):
+    """LSTMHelper::forward(input, output), host path. Returns (output, h_next, c_next)."""
+    head_layers = np.ascontiguousarray(head_layers, dtype=np.int32)
+    h, c = _f32(h).copy(), _f32(c).copy()
+    out = np.zeros(int(head_layers[-1]), np.float32)
+    lib().orc_lstm_forward(_p(_f32(lstm_w)), input_dim, hidden_dim, _p(_f32(head_theta)),
+                           head_layers.ctypes.data_as(C.c_void_p), len(head_layers), _p(_f32(inp)), _p(h), _p(c), _p(out))
+    return out, h, c
+
+
+def racer_step(dyn_params, x, u, dt, h, c):
+    """One host step of RacerDubinsElevationLSTMSteering. Returns (x_next, xdot, y, h_next, c_next)."""
+    h, c = _f32(h).copy(), _f32(c).copy()
+    xn, xd, y = np.zeros(19, np.float32), np.zeros(19, np.float32), np.zeros(28, np.float32)
+    rc = lib().orc_racer_step(C.byref(dyn_params), _p(_f32(x)), _p(_f32(u)), C.c_float(dt), _p(h), _p(c), _p(xn), _p(xd),
+                              _p(y))
+    if rc:
+        raise RuntimeError("orc_racer_step failed (set_lstm not called?)")
+    return xn, xd, y, h, c
+
+
+def colored_noise(normals, sp, N, C_, T, offset_t=1, nthreads=1) -> np.ndarray:
+    """ColoredNoise block [N][T][C] (before setGaussianControls) from the 2*N*C*(T+1) raw normals of one draw."""
+    normals = _f32(normals)
+    assert normals.size == 2 * N * C_ * (T + 1)
+    eps = np.empty((N, T, C_), np.float32)
+    lib().orc_colored_noise(_p(normals), C.byref(sp), N, C_, T, offset_t, _p(eps), nthreads)
+    return eps
+
+
+def colored_tables(sp, C_, T):
+    coeffs = np.empty((C_, T + 1), np.float32)
+    sigma = np.empty(C_, np.float32)
+    lib().orc_colored_tables(C.byref(sp), C_, T, _p(coeffs), _p(sigma))
+    return coeffs, sigma

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include <curand.h>
@@ -81,10 +82,22 @@ struct Aux
 {
   const float* nn_theta = nullptr;   // packed W,b per layer (fnn_helper.cu:176-183)
   const float* costmap = nullptr;    // float4 per texel, row-major [h][w]
+  const float* lstm_theta = nullptr; // LSTM weights then head weights (params.h: MPPIB_BLOB_LSTM_WEIGHTS)
+  int lstm_hidden = 0;               // H
+  int lstm_head = 0;                 // L1 (head layers {H+4, L1, 1})
+};
+
+// models without recurrent state carry nothing from step to step
+struct NoCarry
+{
 };
 
 struct Cartpole
 {
+  typedef NoCarry Carry;
+  static void initCarry(const Aux&, Carry&)
+  {
+  }
   static constexpr int S = 4, C = 1, O = 4;
   typedef mppib_cartpole_dyn_params P;
   // dynamics/cartpole/cartpole_dynamics.cu:48-69 (host computeDynamics); kinematics empty
@@ -111,6 +124,10 @@ struct Cartpole
 
 struct DoubleIntegrator
 {
+  typedef NoCarry Carry;
+  static void initCarry(const Aux&, Carry&)
+  {
+  }
   static constexpr int S = 4, C = 2, O = 4;
   typedef mppib_di_dyn_params P;
   // dynamics/double_integrator/di_dynamics.cu:14-22
@@ -160,6 +177,10 @@ static void fnn_forward(const float* theta, const int* layers, int num_layers, c
 
 struct AutorallyNN
 {
+  typedef NoCarry Carry;
+  static void initCarry(const Aux&, Carry&)
+  {
+  }
   static constexpr int S = 7, C = 2, O = 8;
   static constexpr int DYNAMICS_DIM = 4;  // S_DIM - K_DIM (ar_nn_model.cuh)
   typedef mppib_ar_nn_dyn_params P;
@@ -181,18 +202,306 @@ struct AutorallyNN
   }
 };
 
+// utils/nn_helpers/lstm_helper.cu:267-323 (host forward: Eigen W_*m * h + W_*i * x + b, sigmoid = 1/(1+expf(-x)),
+// activation_functions.cuh:49-59 host branch) followed by the FNN head on [h_next; x] (:325-339).
+// Weight layout: lstm_helper.cu:72-88.
+static void lstm_forward(const float* w, int I, int H, const float* head_theta, const int* head_layers,
+                         int head_num_layers, const float* input, float* h, float* c, float* output)
+{
+  const int HH = H * H, IH = H * I;
+  const float *W_im = w, *W_fm = w + HH, *W_om = w + 2 * HH, *W_cm = w + 3 * HH;
+  const float *W_ii = w + 4 * HH, *W_fi = W_ii + IH, *W_oi = W_ii + 2 * IH, *W_ci = W_ii + 3 * IH;
+  const float *b_i = w + 4 * HH + 4 * IH, *b_f = b_i + H, *b_o = b_i + 2 * H, *b_c = b_i + 3 * H;
+  float c_next[128], h_next[128];
+  auto gate = [&](const float* Wm, const float* Wi, const float* b, int i) {
+    float hm = 0.0f, im = 0.0f;
+    for (int j = 0; j < H; j++)
+      hm += Wm[i * H + j] * h[j];
+    for (int j = 0; j < I; j++)
+      im += Wi[i * I + j] * input[j];
+    return (hm + im) + b[i];
+  };
+  for (int i = 0; i < H; i++)
+  {
+    const float g_i = 1.0f / (1.0f + expf(-gate(W_im, W_ii, b_i, i)));
+    const float g_f = 1.0f / (1.0f + expf(-gate(W_fm, W_fi, b_f, i)));
+    const float g_o = 1.0f / (1.0f + expf(-gate(W_om, W_oi, b_o, i)));
+    const float g_c = tanhf(gate(W_cm, W_ci, b_c, i));
+    c_next[i] = g_i * g_c + g_f * c[i];
+    h_next[i] = g_o * tanhf(c_next[i]);
+  }
+  for (int i = 0; i < H; i++)
+  {
+    h[i] = h_next[i];
+    c[i] = c_next[i];
+  }
+  float nn_input[192];
+  for (int i = 0; i < H; i++)
+    nn_input[i] = h[i];
+  for (int i = 0; i < I; i++)
+    nn_input[H + i] = input[i];
+  fnn_forward(head_theta, head_layers, head_num_layers, nn_input, output);
+}
+
+// RacerDubinsElevationLSTMSteering, host path: dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cu:66-118
+// (computeLSTMSteering + step), racer_dubins.cu:306-319 (computeParametricDelayDeriv), racer_dubins_elevation.cu:32-67
+// (computeParametricAccelDeriv, host), :336-515 (uncertainty Jacobian and Q), :662-741 (propagation),
+// lstm_steering.cu:267-285 (updateState, host), racer_dubins.cu:359-434 (static settling, no texture => flat),
+// racer_dubins_elevation.cu:69-227 (setOutputs).
+struct RacerLSTM
+{
+  static constexpr int S = 19, C = 2, O = 28;
+  static constexpr bool CUSTOM_STEP = true;
+  typedef mppib_racer_lstm_dyn_params P;
+  struct Carry
+  {
+    float h[128], c[128];
+  };
+  enum
+  {
+    VEL_X = 0, YAW, POS_X, POS_Y, STEER_ANGLE, BRAKE_STATE, ROLL, PITCH, STEER_ANGLE_RATE, UNC_POS_X, UNC_POS_Y, UNC_YAW,
+    UNC_VEL_X, UNC_POS_X_Y, UNC_POS_X_YAW, UNC_POS_X_VEL_X, UNC_POS_Y_YAW, UNC_POS_Y_VEL_X, UNC_YAW_VEL_X
+  };
+  enum
+  {
+    O_VEL_B_X = 0, O_VEL_B_Y, O_POS_I_X, O_POS_I_Y, O_POS_I_Z, O_YAW, O_ROLL, O_PITCH, O_STEER_ANGLE, O_STEER_ANGLE_RATE,
+    O_WF_UP, O_WF_FWD, O_WF_SIDE, O_ACCEL_X, O_ACCEL_Y, O_OMEGA_Z, O_TOTAL_VELOCITY, O_UNC_POS_X, O_UNC_POS_Y, O_UNC_YAW,
+    O_UNC_VEL_X, O_UNC_POS_X_Y, O_UNC_POS_X_YAW, O_UNC_POS_X_VEL_X, O_UNC_POS_Y_YAW, O_UNC_POS_Y_VEL_X, O_UNC_YAW_VEL_X
+  };
+  enum
+  {
+    U_VEL_X = 0, U_YAW, U_POS_X, U_POS_Y
+  };
+  static constexpr int cm(int row, int col)
+  {
+    return col * 4 + row;  // mm::columnMajorIndex
+  }
+  // LSTMHelper::resetHiddenCellCPU (lstm_helper.cu:465-473): h, c <- initial_hidden_, initial_cell_
+  static void initCarry(const Aux& aux, Carry& k)
+  {
+    const int H = aux.lstm_hidden, I = MPPIB_RACER_LSTM_INPUT_DIM;
+    const float* init = aux.lstm_theta + 4 * H * H + 4 * H * I + 4 * H;
+    for (int i = 0; i < H; i++)
+    {
+      k.h[i] = init[i];
+      k.c[i] = init[H + i];
+    }
+  }
+  static int velIndex(float vx)
+  {
+    const float linear_brake_slope = 0.2f;
+    return (fabsf(vx) > linear_brake_slope && fabsf(vx) <= 3.0f) + (fabsf(vx) > 3.0f) * 2;
+  }
+  static void step(const P& p, const Aux& aux, Carry& k, const float* state, float* next_state, float* state_der,
+                   const float* control, float* output, float dt)
+  {
+    // --- computeParametricDelayDeriv, racer_dubins.cu:306-319
+    const bool enable_brake = control[0] < 0.0f;
+    const float brake_error = (enable_brake * -control[0] - state[BRAKE_STATE]);
+    state_der[BRAKE_STATE] = fminf(fmaxf((brake_error > 0) * brake_error * p.brake_delay_constant +
+                                             (brake_error < 0) * brake_error * p.brake_delay_constant_neg,
+                                         -p.max_brake_rate_neg),
+                                   p.max_brake_rate_pos);
+    // --- computeParametricAccelDeriv (host), racer_dubins_elevation.cu:32-67
+    {
+      const float linear_brake_slope = 0.2f;
+      const int index = velIndex(state[VEL_X]);
+      const float brake_state = fminf(fmaxf(state[BRAKE_STATE], 0.0f), 0.25f);
+      float throttle = p.c_t[index] * control[0];
+      float brake = p.c_b[index] * brake_state * (state[VEL_X] >= 0.0f ? -1.0f : 1.0f);
+      if (fabsf(state[VEL_X]) <= linear_brake_slope)
+      {
+        throttle = p.c_t[index] * fmaxf(control[0] - p.low_min_throttle, 0.0f);
+        brake = p.c_b[index] * brake_state * -state[VEL_X];
+      }
+      state_der[VEL_X] = (!enable_brake) * throttle * p.gear_sign + brake - p.c_v[index] * state[VEL_X] + p.c_0;
+      state_der[VEL_X] = fminf(fmaxf(state_der[VEL_X], -p.clamp_ax), p.clamp_ax);
+      if (fabsf(state[PITCH]) < 1.57079632679489661923f)
+        state_der[VEL_X] -= p.gravity * sinf(state[PITCH]);
+      state_der[YAW] = (state[VEL_X] / p.wheel_base) * tanf(state[STEER_ANGLE] / p.steer_angle_scale);
+      float sin_yaw, cos_yaw;
+      sincosf(state[YAW], &sin_yaw, &cos_yaw);
+      state_der[POS_X] = state[VEL_X] * cos_yaw;
+      state_der[POS_Y] = state[VEL_X] * sin_yaw;
+    }
+    // --- computeLSTMSteering (host), lstm_steering.cu:66-88
+    {
+      const float parametric_accel =
+          (control[1] * p.steer_command_angle_scale - state[STEER_ANGLE]) * p.steering_constant;
+      state_der[STEER_ANGLE_RATE] =
+          fmaxf(fminf((parametric_accel - state[STEER_ANGLE_RATE]) * p.steer_accel_constant -
+                          state[STEER_ANGLE_RATE] * p.steer_accel_drag_constant,
+                      p.max_steer_rate),
+                -p.max_steer_rate);
+      float input[4], nn_output[1];
+      input[0] = state[STEER_ANGLE] * 0.2f;
+      input[1] = state[STEER_ANGLE_RATE] * 0.2f;
+      input[2] = control[1];
+      input[3] = state_der[STEER_ANGLE_RATE] * 0.2f;
+      const int H = aux.lstm_hidden, I = MPPIB_RACER_LSTM_INPUT_DIM;
+      const int head_layers[3] = { H + I, aux.lstm_head, 1 };
+      lstm_forward(aux.lstm_theta, I, H, aux.lstm_theta + 4 * H * H + 4 * H * I + 6 * H, head_layers, 3, input, k.h,
+                   k.c, nn_output);
+      state_der[STEER_ANGLE_RATE] += nn_output[0] * 5.0f;
+      state_der[STEER_ANGLE] = state[STEER_ANGLE_RATE];
+    }
+    // --- updateState (host), lstm_steering.cu:267-285
+    for (int i = 0; i < 6; i++)
+      next_state[i] = state[i] + state_der[i] * dt;
+    next_state[YAW] = normalizeAngle(next_state[YAW]);
+    next_state[STEER_ANGLE] = fmaxf(fminf(next_state[STEER_ANGLE], p.max_steer_angle), -p.max_steer_angle);
+    next_state[STEER_ANGLE_RATE] = state[STEER_ANGLE_RATE] + state_der[STEER_ANGLE_RATE] * dt;
+    next_state[BRAKE_STATE] = fminf(fmaxf(next_state[BRAKE_STATE], 0.0f), -p.lim.rng_lo[0]);
+    // --- computeUncertaintyPropagation, racer_dubins_elevation.cu:662-741
+    {
+      float A[16], Sa[16], Sb[16];
+      // computeUncertaintyJacobian (host trig), :336-425
+      float sin_yaw, cos_yaw;
+      sincosf(state[YAW], &sin_yaw, &cos_yaw);
+      const float delta = state[STEER_ANGLE] / p.steer_angle_scale;
+      const float tan_steer_angle = tanf(delta);
+      const float cos_2_delta = SQ(cosf(delta));
+      const int index = velIndex(state[VEL_X]);
+      const float brake_state = fminf(fmaxf(state[BRAKE_STATE], 0.0f), 0.25f);
+      A[cm(U_VEL_X, U_VEL_X)] = -p.c_v[index] - p.K_vel_x - (index == 0 ? 1.0f : 0.0f) * p.c_b[0] * brake_state;
+      A[cm(U_VEL_X, U_YAW)] = 0.0f;
+      A[cm(U_VEL_X, U_POS_X)] = -p.K_x * cos_yaw;
+      A[cm(U_VEL_X, U_POS_Y)] = -p.K_x * sin_yaw;
+      A[cm(U_YAW, U_VEL_X)] = tan_steer_angle / (p.wheel_base);
+      A[cm(U_YAW, U_YAW)] = -fabsf(state[VEL_X]) * p.K_yaw / (p.wheel_base * cos_2_delta);
+      A[cm(U_YAW, U_POS_X)] = state[VEL_X] * p.K_y * sin_yaw / (p.wheel_base * cos_2_delta);
+      A[cm(U_YAW, U_POS_Y)] = -state[VEL_X] * p.K_y * cos_yaw / (p.wheel_base * cos_2_delta);
+      A[cm(U_POS_X, U_VEL_X)] = cos_yaw;
+      A[cm(U_POS_X, U_YAW)] = -sin_yaw * state[VEL_X];
+      A[cm(U_POS_X, U_POS_X)] = 0.0f;
+      A[cm(U_POS_X, U_POS_Y)] = 0.0f;
+      A[cm(U_POS_Y, U_VEL_X)] = sin_yaw;
+      A[cm(U_POS_Y, U_YAW)] = cos_yaw * state[VEL_X];
+      A[cm(U_POS_Y, U_POS_Y)] = 0.0f;
+      A[cm(U_POS_Y, U_POS_X)] = 0.0f;
+      // uncertaintyStateToMatrix, :517-577
+      Sa[cm(U_VEL_X, U_VEL_X)] = state[UNC_VEL_X];
+      Sa[cm(U_YAW, U_VEL_X)] = Sa[cm(U_VEL_X, U_YAW)] = state[UNC_YAW_VEL_X];
+      Sa[cm(U_POS_X, U_VEL_X)] = Sa[cm(U_VEL_X, U_POS_X)] = state[UNC_POS_X_VEL_X];
+      Sa[cm(U_POS_Y, U_VEL_X)] = Sa[cm(U_VEL_X, U_POS_Y)] = state[UNC_POS_Y_VEL_X];
+      Sa[cm(U_YAW, U_YAW)] = state[UNC_YAW];
+      Sa[cm(U_POS_X, U_YAW)] = Sa[cm(U_YAW, U_POS_X)] = state[UNC_POS_X_YAW];
+      Sa[cm(U_POS_Y, U_YAW)] = Sa[cm(U_YAW, U_POS_Y)] = state[UNC_POS_Y_YAW];
+      Sa[cm(U_POS_X, U_POS_X)] = state[UNC_POS_X];
+      Sa[cm(U_POS_Y, U_POS_X)] = Sa[cm(U_POS_X, U_POS_Y)] = state[UNC_POS_X_Y];
+      Sa[cm(U_POS_Y, U_POS_Y)] = state[UNC_POS_Y];
+      // A <- I + A dt
+      for (int i = 0; i < 16; i++)
+        A[i] = (i % 5 == 0) + A[i] * dt;
+      // Sigma_a <- A Sigma_a A^T (Eigen: (A * Sigma) * A^T, inner index ascending)
+      for (int col = 0; col < 4; col++)
+        for (int row = 0; row < 4; row++)
+        {
+          float acc = 0.0f;
+          for (int q = 0; q < 4; q++)
+            acc += A[cm(row, q)] * Sa[cm(q, col)];
+          Sb[cm(row, col)] = acc;
+        }
+      for (int col = 0; col < 4; col++)
+        for (int row = 0; row < 4; row++)
+        {
+          float acc = 0.0f;
+          for (int q = 0; q < 4; q++)
+            acc += Sb[cm(row, q)] * A[cm(col, q)];
+          Sa[cm(row, col)] = acc;
+        }
+      // computeQ, :427-515. The host branch leaves sin_roll unset (only the device branch assigns it, :441); the
+      // device value sin(roll) is used here.
+      const float abs_vx = fabsf(state[VEL_X]);
+      const float abs_acc_x = fabsf(state_der[VEL_X]);
+      const float sin_roll = sinf(state[ROLL]);
+      const float side_force = SQ(abs_vx) * tan_steer_angle / p.wheel_base + p.gravity * sin_roll;
+      const float Q_11 = fabsf(p.Q_y_f * fabsf(side_force) * fmaxf(abs_vx - 2, 0.0f));
+      for (int i = 0; i < 16; i++)
+        Sb[i] = 0.0f;
+      Sb[cm(U_VEL_X, U_VEL_X)] = p.Q_x_acc * abs_acc_x + p.Q_x_v[index] * abs_vx;
+      Sb[cm(U_YAW, U_YAW)] = abs_vx * (p.Q_omega_steering * fabsf(delta) + p.Q_omega_v);
+      Sb[cm(U_POS_X, U_POS_X)] = Q_11 * sin_yaw * sin_yaw;
+      Sb[cm(U_POS_X, U_POS_Y)] = -Q_11 * sin_yaw * cos_yaw;
+      Sb[cm(U_POS_Y, U_POS_Y)] = Q_11 * cos_yaw * cos_yaw;
+      Sb[cm(U_POS_Y, U_POS_X)] = -Q_11 * sin_yaw * cos_yaw;
+      for (int i = 0; i < 16; i++)
+        Sa[i] += Sb[i] * dt;
+      // uncertaintyMatrixToState, :579-621
+      next_state[UNC_VEL_X] = Sa[cm(U_VEL_X, U_VEL_X)];
+      next_state[UNC_YAW_VEL_X] = Sa[cm(U_YAW, U_VEL_X)];
+      next_state[UNC_POS_X_VEL_X] = Sa[cm(U_POS_X, U_VEL_X)];
+      next_state[UNC_POS_Y_VEL_X] = Sa[cm(U_POS_Y, U_VEL_X)];
+      next_state[UNC_YAW] = Sa[cm(U_YAW, U_YAW)];
+      next_state[UNC_POS_X_YAW] = Sa[cm(U_POS_X, U_YAW)];
+      next_state[UNC_POS_Y_YAW] = Sa[cm(U_POS_Y, U_YAW)];
+      next_state[UNC_POS_X] = Sa[cm(U_POS_X, U_POS_X)];
+      next_state[UNC_POS_X_Y] = Sa[cm(U_POS_Y, U_POS_X)];
+      next_state[UNC_POS_Y] = Sa[cm(U_POS_Y, U_POS_Y)];
+    }
+    // --- static settling without an elevation map (racer_dubins.cu:427-432): roll = pitch = height = 0
+    output[O_POS_I_Z] = 0.0f;
+    next_state[PITCH] = 0.0f;
+    next_state[ROLL] = 0.0f;
+    // --- setOutputs, racer_dubins_elevation.cu:69-227
+    output[O_VEL_B_X] = next_state[VEL_X];
+    output[O_VEL_B_Y] = 0.0f;
+    output[O_POS_I_X] = next_state[POS_X];
+    output[O_POS_I_Y] = next_state[POS_Y];
+    output[O_PITCH] = next_state[PITCH];
+    output[O_ROLL] = next_state[ROLL];
+    output[O_YAW] = next_state[YAW];
+    output[O_STEER_ANGLE] = next_state[STEER_ANGLE];
+    output[O_STEER_ANGLE_RATE] = next_state[STEER_ANGLE_RATE];
+    output[O_WF_UP] = NAN;
+    output[O_WF_FWD] = NAN;
+    output[O_WF_SIDE] = NAN;
+    output[O_ACCEL_X] = state_der[VEL_X];
+    output[O_ACCEL_Y] = 0.0f;
+    output[O_OMEGA_Z] = state_der[YAW];
+    output[O_UNC_VEL_X] = next_state[UNC_VEL_X];
+    output[O_UNC_YAW_VEL_X] = next_state[UNC_YAW_VEL_X];
+    output[O_UNC_POS_X_VEL_X] = next_state[UNC_POS_X_VEL_X];
+    output[O_UNC_POS_Y_VEL_X] = next_state[UNC_POS_Y_VEL_X];
+    output[O_UNC_YAW] = next_state[UNC_YAW];
+    output[O_UNC_POS_X_YAW] = next_state[UNC_POS_X_YAW];
+    output[O_UNC_POS_Y_YAW] = next_state[UNC_POS_Y_YAW];
+    output[O_UNC_POS_X] = next_state[UNC_POS_X];
+    output[O_UNC_POS_X_Y] = next_state[UNC_POS_X_Y];
+    output[O_UNC_POS_Y] = next_state[UNC_POS_Y];
+    output[O_TOTAL_VELOCITY] = fabsf(next_state[VEL_X]);
+  }
+};
+
+template <class T, class = void>
+struct has_custom_step : std::false_type
+{
+};
+template <class T>
+struct has_custom_step<T, std::enable_if_t<T::CUSTOM_STEP>> : std::true_type
+{
+};
+
 // dynamics/dynamics.cuh:277-300
 template <class DYN>
 static inline void dyn_step(const typename DYN::P& p, const Aux& aux, const float* state, float* next_state,
-                            float* state_der, const float* control, float* output, float dt)
+                            float* state_der, const float* control, float* output, float dt,
+                            typename DYN::Carry* carry = nullptr)
 {
   for (int i = 0; i < DYN::S; i++)
     state_der[i] = 0.0f;  // Eigen state_array locals are written fully by every model used here
-  DYN::computeStateDeriv(p, aux, state, control, state_der);
-  for (int i = 0; i < DYN::S; i++)
-    next_state[i] = state[i] + state_der[i] * dt;
-  for (int i = 0; i < DYN::O && i < DYN::S; i++)
-    output[i] = next_state[i];
+  if constexpr (has_custom_step<DYN>::value)
+  {
+    DYN::step(p, aux, *carry, state, next_state, state_der, control, output, dt);
+  }
+  else
+  {
+    DYN::computeStateDeriv(p, aux, state, control, state_der);
+    for (int i = 0; i < DYN::S; i++)
+      next_state[i] = state[i] + state_der[i] * dt;
+    for (int i = 0; i < DYN::O && i < DYN::S; i++)
+      output[i] = next_state[i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -336,6 +645,27 @@ struct ARStandardCost
   }
 };
 
+// Ours (params.h: mppib_racer_quadratic_cost_params) — the RACER cost classes are not in the reference tree; this is
+// the specification the GPU twin is checked against, not a restatement.
+struct RacerQuadraticCost
+{
+  typedef mppib_racer_quadratic_cost_params P;
+  static float computeStateCost(const P& p, const Aux&, const float* y, int t, int*)
+  {
+    const float dv = y[RacerLSTM::O_VEL_B_X] - p.desired_speed;
+    const float dyaw = normalizeAngle(y[RacerLSTM::O_YAW] - p.desired_yaw);
+    const float dy = y[RacerLSTM::O_POS_I_Y] - p.desired_y;
+    const float st = y[RacerLSTM::O_STEER_ANGLE];
+    const float cost = p.speed_coeff * dv * dv + p.yaw_coeff * dyaw * dyaw + p.lateral_coeff * dy * dy +
+                       p.steer_coeff * st * st;
+    return cost * powf(p.discount, (float)t);
+  }
+  static float terminalCost(const P&, const Aux&, const float*)
+  {
+    return 0.0f;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Sampler semantics.
 // sampling_distributions/gaussian/gaussian.cu:17-277 (setGaussianControls), applied in place on raw eps.
@@ -397,6 +727,8 @@ static void rollout_range(const typename DYN::P& dp, const typename COST::P& cp,
         y[i] = 0.0f;
       int crash_status = 0;
       float running_cost = 0.0f;
+      typename DYN::Carry carry;
+      DYN::initCarry(aux, carry);
       for (int t = 0; t < T; t++)
       {
         float* us = &samples[(((size_t)d * N + n) * T + t) * C];
@@ -405,7 +737,7 @@ static void rollout_range(const typename DYN::P& dp, const typename COST::P& cp,
         enforceConstraints<C>(dp.lim, u);
         for (int i = 0; i < C; i++)
           us[i] = u[i];
-        dyn_step<DYN>(dp, aux, curr_x, next_x, x_der, u, y, dt);
+        dyn_step<DYN>(dp, aux, curr_x, next_x, x_der, u, y, dt, &carry);
         running_cost += COST::computeStateCost(cp, aux, y, t, &crash_status);
         running_cost += likelihoodRatioCost(sp, &means[((size_t)d * T + t) * C], u, C, d, n, N, lambda, alpha);
         for (int i = 0; i < S; i++)
@@ -453,6 +785,8 @@ static rollout_fn pick_rollout(int dyn_id, int cost_id)
     return &rollout<DoubleIntegrator, DICircleCost>;
   if (dyn_id == MPPIB_DYN_AUTORALLY_NN && cost_id == MPPIB_COST_AR_STANDARD)
     return &rollout<AutorallyNN, ARStandardCost>;
+  if (dyn_id == MPPIB_DYN_RACER_LSTM && cost_id == MPPIB_COST_RACER_QUADRATIC)
+    return &rollout<RacerLSTM, RacerQuadraticCost>;
   return nullptr;
 }
 
@@ -469,9 +803,105 @@ static void dims(int dyn_id, int* S, int* C, int* O)
     case MPPIB_DYN_AUTORALLY_NN:
       *S = 7, *C = 2, *O = 8;
       break;
+    case MPPIB_DYN_RACER_LSTM:
+      *S = 19, *C = 2, *O = 28;
+      break;
     default:
       *S = *C = *O = 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ColoredNoiseDistribution::generateSamples up to (not including) setGaussianControls,
+// sampling_distributions/colored_noise/colored_noise.cu:286-372 with its kernels :12-56; the algorithm is
+// scripts/colored_noise.py:12-104 (Timmer & Koenig). `normals` is what curandGenerateNormal wrote into
+// samples_in_freq_complex_d_: [n][c][freq] complex = 2 * N * C * (T + 1) floats. cuFFT's C2R (unnormalised inverse real
+// DFT of length 2T, libcufft — third party) is restated as the defining sum in double precision.
+static void coloredNoiseTables(const mppib_gaussian_params& sp, int C, int T, std::vector<float>& sample_freqs /*[c][f]*/,
+                               float* sigma)
+{
+  const int sample_num_timesteps = 2 * T;
+  const int freq_size = sample_num_timesteps / 2 + 1;  // fftfreq, colored_noise.cuh:24-34
+  std::vector<float> sample_freq(freq_size);
+  for (int i = 0; i < freq_size; i++)
+    sample_freq[i] = i / (1.0f * sample_num_timesteps);
+  const float cutoff_freq = fmaxf(sp.fmin, 1.0f / sample_num_timesteps);
+  int smaller_index = 0;
+  sample_freqs.assign((size_t)freq_size * C, 0.0f);  // Eigen MatrixXf(freq_size, C), column-major => [c][f]
+  auto at = [&](int f, int c) -> float& { return sample_freqs[(size_t)c * freq_size + f]; };
+  for (int i = 0; i < freq_size; i++)  // colored_noise.cu:305-326
+  {
+    if (sample_freq[i] < cutoff_freq)
+    {
+      smaller_index++;
+    }
+    else if (smaller_index < freq_size)
+    {
+      for (int j = 0; j < smaller_index; j++)
+      {
+        sample_freq[j] = sample_freq[smaller_index];
+        for (int k = 0; k < C; k++)
+          at(j, k) = powf(sample_freq[smaller_index], -sp.exponents[k] / 2.0f);
+      }
+    }
+    for (int j = 0; j < C; j++)
+      at(i, j) = powf(sample_freq[i], -sp.exponents[j] / 2.0f);
+  }
+  for (int i = 0; i < C; i++)  // :329-338
+  {
+    sigma[i] = 0.0f;
+    for (int j = 1; j < freq_size - 1; j++)
+      sigma[i] += SQ(at(j, i));
+    sigma[i] += SQ(at(freq_size - 1, i) * ((1.0f + (sample_num_timesteps % 2)) / 2.0f));
+    sigma[i] = 2.0f * sqrtf(sigma[i]) / sample_num_timesteps;
+  }
+}
+
+static void coloredNoise(const float* normals, const mppib_gaussian_params& sp, int N, int C, int T, int offset_t,
+                         float* eps /*[N][T][C]*/, int n_begin, int n_end)
+{
+  const int n2 = 2 * T, F = T + 1;
+  std::vector<float> coeff;
+  float sigma[MPPIB_MAX_CONTROL_DIM];
+  coloredNoiseTables(sp, C, T, coeff, sigma);
+  std::vector<double> cs(n2), sn(n2);
+  for (int i = 0; i < n2; i++)
+  {
+    cs[i] = cos(2.0 * M_PI * i / n2);
+    sn[i] = sin(2.0 * M_PI * i / n2);
+  }
+  std::vector<float> re(F), im(F), time(T);
+  for (int n = n_begin; n < n_end; n++)
+    for (int c = 0; c < C; c++)
+    {
+      const float* row = normals + ((size_t)n * C + c) * F * 2;
+      for (int f = 0; f < F; f++)  // configureFrequencyNoise, :12-37
+      {
+        const float v = coeff[(size_t)c * F + f];
+        re[f] = row[2 * f] * v;
+        if (f == 0)
+          im[f] = 0.0f;
+        else if (F % 2 == 1 && f == F - 1)
+          im[f] = 0.0f;
+        else
+          im[f] = row[2 * f + 1] * v;
+      }
+      for (int t = 0; t < T; t++)  // cufftExecC2R, first T of the 2T outputs; imaginary parts of DC / Nyquist ignored
+      {
+        double acc = (double)re[0] + ((t & 1) ? -(double)re[T] : (double)re[T]);
+        for (int k = 1; k < T; k++)
+        {
+          const int a = (int)(((long long)k * t) % n2);
+          acc += 2.0 * ((double)re[k] * cs[a] - (double)im[k] * sn[a]);
+        }
+        time[t] = (float)acc;
+      }
+      for (int t = 0; t < T; t++)  // rearrangeNoise, :39-56
+      {
+        const float decayed_offset = sp.offset_decay_rate == 0 ? 0 : powf(sp.offset_decay_rate, t);
+        eps[((size_t)n * T + t) * C + c] = (time[t] - time[offset_t] * decayed_offset) / (sigma[c] * 2 * T);
+      }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -605,6 +1035,8 @@ static void outputTrajectory(const void* dpv, const Aux& aux, const float* x0, c
     output[i] = x0[i];
   for (int i = 0; i < O; i++)
     outputs[i] = output[i];
+  typename DYN::Carry carry;
+  DYN::initCarry(aux, carry);
   for (int t = 0; t < T - 1; ++t)
   {
     for (int i = 0; i < S; i++)
@@ -612,7 +1044,7 @@ static void outputTrajectory(const void* dpv, const Aux& aux, const float* x0, c
     for (int i = 0; i < C; i++)
       ui[i] = u[(size_t)t * C + i];
     enforceConstraints<C>(dp.lim, ui);
-    dyn_step<DYN>(dp, aux, state, next_state, xdot, ui, output, dt);
+    dyn_step<DYN>(dp, aux, state, next_state, xdot, ui, output, dt, &carry);
     for (int i = 0; i < S; i++)
       states[(size_t)(t + 1) * S + i] = next_state[i];
     for (int i = 0; i < O; i++)
@@ -625,6 +1057,72 @@ static void outputTrajectory(const void* dpv, const Aux& aux, const float* x0, c
 // C interface for ctypes (tests/, bench.py cpu_baseline)
 // =================================================================================================================
 extern "C" {
+
+// LSTM weights / architecture for MPPIB_DYN_RACER_LSTM: set once, used by every later call (kept by pointer).
+static orc::Aux g_lstm;
+void orc_set_lstm(const float* theta, int hidden_dim, int head_hidden)
+{
+  g_lstm.lstm_theta = theta;
+  g_lstm.lstm_hidden = hidden_dim;
+  g_lstm.lstm_head = head_hidden;
+}
+static void fill_lstm(orc::Aux& aux)
+{
+  aux.lstm_theta = g_lstm.lstm_theta;
+  aux.lstm_hidden = g_lstm.lstm_hidden;
+  aux.lstm_head = g_lstm.lstm_head;
+}
+
+// LSTMHelper::forward(input, output) host path; h and c are updated in place. head_layers as in FNNHelper.
+void orc_lstm_forward(const float* lstm_w, int input_dim, int hidden_dim, const float* head_theta,
+                      const int* head_layers, int head_num_layers, const float* input, float* h, float* c,
+                      float* output)
+{
+  orc::lstm_forward(lstm_w, input_dim, hidden_dim, head_theta, head_layers, head_num_layers, input, h, c, output);
+}
+
+// One host step of RacerDubinsElevationLSTMSteering with explicit hidden/cell state (updated in place).
+int orc_racer_step(const mppib_racer_lstm_dyn_params* p, const float* x, const float* u, float dt, float* h, float* c,
+                   float* x_next, float* xdot, float* y)
+{
+  orc::Aux aux;
+  fill_lstm(aux);
+  if (!aux.lstm_theta)
+    return -1;
+  orc::RacerLSTM::Carry k;
+  memcpy(k.h, h, sizeof(float) * aux.lstm_hidden);
+  memcpy(k.c, c, sizeof(float) * aux.lstm_hidden);
+  orc::dyn_step<orc::RacerLSTM>(*p, aux, x, x_next, xdot, u, y, dt, &k);
+  memcpy(h, k.h, sizeof(float) * aux.lstm_hidden);
+  memcpy(c, k.c, sizeof(float) * aux.lstm_hidden);
+  return 0;
+}
+
+// ColoredNoiseDistribution noise block (before setGaussianControls) from the raw normals of one generateSamples call.
+void orc_colored_noise(const float* normals, const mppib_gaussian_params* sp, int N, int C, int T, int offset_t,
+                       float* eps, int nthreads)
+{
+  if (nthreads <= 1)
+  {
+    orc::coloredNoise(normals, *sp, N, C, T, offset_t, eps, 0, N);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int i = 0; i < nthreads; i++)
+  {
+    int b = (int)((long long)N * i / nthreads), e = (int)((long long)N * (i + 1) / nthreads);
+    th.emplace_back([=]() { orc::coloredNoise(normals, *sp, N, C, T, offset_t, eps, b, e); });
+  }
+  for (auto& t : th)
+    t.join();
+}
+
+void orc_colored_tables(const mppib_gaussian_params* sp, int C, int T, float* coeffs /*[C][T+1]*/, float* sigma)
+{
+  std::vector<float> c;
+  orc::coloredNoiseTables(*sp, C, T, c, sigma);
+  memcpy(coeffs, c.data(), c.size() * sizeof(float));
+}
 
 int orc_dims(int dyn_id, int* S, int* C, int* O)
 {
@@ -670,6 +1168,7 @@ int orc_rollout(int dyn_id, int cost_id, const void* dyn_params, const void* cos
   orc::Aux aux;
   aux.nn_theta = nn_theta;
   aux.costmap = costmap;
+  fill_lstm(aux);
   f(dyn_params, cost_params, *sp, aux, N, T, D, dt, lambda, alpha, x0, means, samples, costs, nthreads);
   return 0;
 }
@@ -766,6 +1265,11 @@ int orc_state_cost(int cost_id, const void* cost_params, const float* costmap, c
           orc::ARStandardCost::computeStateCost(*(const mppib_ar_standard_cost_params*)cost_params, aux, y, t, crash);
       *terminal_out = 0;
       return 0;
+    case MPPIB_COST_RACER_QUADRATIC:
+      *cost_out = orc::RacerQuadraticCost::computeStateCost(*(const mppib_racer_quadratic_cost_params*)cost_params,
+                                                            aux, y, t, crash);
+      *terminal_out = 0;
+      return 0;
   }
   return -1;
 }
@@ -810,6 +1314,10 @@ int orc_output_trajectory(int dyn_id, const void* dyn_params, const float* nn_th
       return 0;
     case MPPIB_DYN_AUTORALLY_NN:
       orc::outputTrajectory<orc::AutorallyNN>(dyn_params, aux, x0, u, T, dt, states, outputs);
+      return 0;
+    case MPPIB_DYN_RACER_LSTM:
+      fill_lstm(aux);
+      orc::outputTrajectory<orc::RacerLSTM>(dyn_params, aux, x0, u, T, dt, states, outputs);
       return 0;
   }
   return -1;

@@ -280,3 +280,100 @@ def test_output_trajectory_host_twin_matches_oracle():
         assert rc == 0
         np.testing.assert_allclose(st2, st, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(out2, out, rtol=1e-5, atol=1e-6)
+
+
+# ---- LSTM / RACER model / ColoredNoise -------------------------------------------------
+def test_lstm_forward_all_ones_known_answers():
+    # tests/nn_helpers/lstm_helper_test.cu:677-718 (forwardCPU): LSTMHelper(8, 20, {28, 3}), every weight, bias and the
+    # initial hidden / cell state = 1, input = 1  =>  28.28055, 28.901096, 28.986588, 28.998184, 28.999756
+    I, Hd = 8, 20
+    w = np.ones(4 * Hd * Hd + 4 * Hd * I + 4 * Hd, np.float32)
+    head = np.ones(28 * 3 + 3, np.float32)
+    h, c = np.ones(Hd, np.float32), np.ones(Hd, np.float32)
+    for expect in (28.28055, 28.901096, 28.986588, 28.998184, 28.999756):
+        out, h, c = oracle.lstm_forward(w, I, Hd, head, [28, 3], np.ones(I, np.float32), h, c)
+        np.testing.assert_allclose(out, expect, rtol=4e-7)  # EXPECT_FLOAT_EQ
+
+
+def test_racer_lstm_host_twin_matches_oracle():
+    """The product's host twin (host_twins.cpp, used by the controller tail) and the oracle restate the same host path
+    (racer_dubins_elevation_lstm_steering.cu:90-118) independently: they must agree to the last bit over a trajectory."""
+    w = W.racer_lstm(N=64, T=10)
+    dyn = w.dyn
+    oracle.set_lstm(dyn.lstm_theta, dyn.hidden_dim, dyn.head_hidden)
+    rng = np.random.RandomState(0)
+    x = w.x0[0].copy()
+    x[1], x[4] = 0.3, 0.1
+    x[9:19] = rng.uniform(0, 0.01, 10)
+    h, c = dyn.initial_hidden_cell()
+    xo, ho, co = x.copy(), h.copy(), c.copy()
+    for t in range(60):
+        u = rng.uniform(-1, 1, 2).astype(np.float32)
+        xn, xd, y, h, c = dyn.step(x, u, 0.02, h, c)
+        xn2, xd2, y2, ho, co = oracle.racer_step(dyn.params, xo, u, 0.02, ho, co)
+        np.testing.assert_array_equal(xn, xn2)
+        np.testing.assert_array_equal(xd, xd2)
+        np.testing.assert_array_equal(y, y2)  # NaN == NaN under assert_array_equal (WHEEL_FORCE_* outputs)
+        x, xo = xn, xn2
+    assert np.all(np.isfinite(x))
+    # known structure of one step (racer_dubins_elevation.cu:69-227, racer_dubins.cu:427-432): flat terrain, outputs
+    assert y[4] == 0.0 and y[6] == 0.0 and y[7] == 0.0 and np.isnan(y[10:13]).all()
+    assert y[0] == xn[0] and y[2] == xn[2] and y[3] == xn[3] and y[16] == abs(xn[0])
+
+
+def test_racer_parametric_known_answers():
+    """Hand-evaluated values of the parametric part (racer_dubins.cu:306-319, racer_dubins_elevation.cu:32-67) with the
+    LSTM silenced (all weights zero => head output 0)."""
+    dyn = H.RacerDubinsElevationLSTMSteering()
+    dyn.setControlRanges([(-1.0, 1.0), (-1.0, 1.0)])
+    oracle.set_lstm(dyn.lstm_theta, dyn.hidden_dim, dyn.head_hidden)
+    x = np.zeros(19, np.float32)
+    h, c = dyn.initial_hidden_cell()
+    # at rest, full throttle: index 0, |vx| <= 0.2 => throttle = c_t[0] * (1 - 0.13); xdot_vx = that + c_0, clamped to 5.5
+    xn, xd, y, _, _ = oracle.racer_step(dyn.params, x, np.array([1.0, 0.0], np.float32), 0.1, h, c)
+    assert xd[0] == pytest.approx(min(1.3 * (1.0 - 0.13) + 4.9, 5.5), rel=1e-6)
+    assert xn[0] == pytest.approx(xd[0] * 0.1, rel=1e-6)
+    assert xd[5] == 0.0 and xd[1] == 0.0
+    # moving at 4 m/s (index 2), braking: brake state rises at min(1 * 6.6, 0.33); drag c_v[2] * 4
+    x[0] = 4.0
+    xn, xd, y, _, _ = oracle.racer_step(dyn.params, x, np.array([-1.0, 0.5], np.float32), 0.1, h, c)
+    assert xd[5] == pytest.approx(0.33)
+    assert xd[0] == pytest.approx(max(-5.7 * 4.0 + 4.9, -5.5))
+    # steering: rate derivative = clamp(((0.5*5 - 0) * 0.6 - 0) * 12.1 - 0, +-5) = 5, angle derivative = current rate = 0
+    assert xd[8] == pytest.approx(5.0) and xd[4] == 0.0
+    assert xn[8] == pytest.approx(0.5)
+    assert xd[2] == pytest.approx(4.0) and xd[3] == pytest.approx(0.0)
+
+
+def test_colored_noise_matches_the_numpy_algorithm():
+    """colored_noise.cu:286-372 mirrors scripts/colored_noise.py:12-104 (Timmer & Koenig via numpy irfft) plus the offset
+    subtraction of rearrangeNoise (:39-56); the oracle's restatement must reproduce that algorithm."""
+    N, Cd, T = 64, 2, 50
+    betas = [1.0, 2.0]
+    s = H.ColoredNoiseDistribution(Cd, [0.3, 0.3], betas)
+    normals = oracle.curand_normal(42, 0, 2 * N * Cd * (T + 1))
+    for offset_t in (1, 4):
+        eps = oracle.colored_noise(normals, s.params, N, Cd, T, offset_t=offset_t)
+        z = normals.reshape(N, Cd, T + 1, 2).astype(np.float64)
+        ref = np.zeros((N, T, Cd))
+        for c, beta in enumerate(betas):
+            samples = 2 * T
+            f = np.fft.rfftfreq(samples)
+            fmin = max(0.0, 1.0 / samples)
+            ix = int(np.sum(f < fmin))
+            sc = f.copy()
+            if ix and ix < len(sc):
+                sc[:ix] = sc[ix]
+            sc = sc ** (-beta / 2.0)
+            wv = sc[1:].copy()
+            wv[-1] *= (1 + (samples % 2)) / 2.0
+            sigma = 2 * np.sqrt(np.sum(wv ** 2)) / samples
+            sr, si = z[:, c, :, 0] * sc, z[:, c, :, 1] * sc
+            si[:, -1] = 0
+            si[:, 0] = 0
+            yv = np.fft.irfft(sr + 1j * si, n=samples, axis=-1)[:, :T] / sigma
+            ref[:, :, c] = yv - yv[:, offset_t:offset_t + 1] * (0.97 ** np.arange(T))
+        np.testing.assert_allclose(eps, ref, atol=5e-6)
+        # unit variance before the offset is subtracted (Timmer & Koenig normalisation); pooled over N*T samples
+    tab, sigma = oracle.colored_tables(s.params, Cd, T)
+    assert tab.shape == (Cd, T + 1) and np.all(sigma > 0)
