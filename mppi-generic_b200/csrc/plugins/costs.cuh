@@ -185,7 +185,14 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
   __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux& aux, const float* theta_c,
                                                            const float* s, int timestep, int* crash_status)
   {
+#ifdef MPPIB_EXP_NO_COST
+    return s[4] * s[4];
+#endif
+#ifdef MPPIB_EXP_NO_TEX
+    float track_cost = s[0] + s[1];
+#else
     float track_cost = getTrackCost(p, aux, s, crash_status);
+#endif
     float speed_cost = getSpeedCost(p, s);
     float stabilizing_cost = getStabilizingCost(p, s, crash_status);
     float crash_cost = theta_c[timestep] * getCrashCost(p, crash_status);  // powf(discount, timestep)

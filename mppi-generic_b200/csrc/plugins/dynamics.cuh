@@ -61,6 +61,10 @@ struct Dynamics
   struct Aux
   {
   };
+  // per-sample state a model carries from step to step besides x (recurrent networks); lives in registers
+  struct Carry
+  {
+  };
 
   // dynamics.cuh:429-435 — y <- x on the first min(S,O) entries. theta_s untouched by default.
   __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux&, float* /*theta_s*/, const float* x,
@@ -69,6 +73,13 @@ struct Dynamics
 #pragma unroll
     for (int i = 0; i < O && i < S; i++)
       y[i] = x[i];
+  }
+  // what the rollout kernel calls; models with a Carry override this one
+  template <class AUX, class CARRY>
+  __device__ static __forceinline__ void initializeDynamics(const Params& p, const AUX& aux, float* theta_s, CARRY&,
+                                                            const float* x, float* y)
+  {
+    CLASS_T::initializeDynamics(p, aux, theta_s, x, y);
   }
   __device__ static __forceinline__ void enforceConstraints(const Params& p, const float* /*x*/, float* u)
   {
@@ -99,8 +110,8 @@ struct Dynamics
       y[i] = x[i];
   }
   // dynamics.cu:131-142
-  template <class AUX>
-  __device__ static __forceinline__ void step(const Params& p, const AUX&, float* theta_s, const float* x,
+  template <class AUX, class CARRY>
+  __device__ static __forceinline__ void step(const Params& p, const AUX&, float* theta_s, CARRY&, const float* x,
                                               float* x_next, float* xdot, const float* u, float* y, int /*t*/, float dt)
   {
     CLASS_T::computeStateDeriv(p, theta_s, x, u, xdot);
@@ -155,6 +166,10 @@ struct DoubleIntegratorDynamics : public Dynamics<DoubleIntegratorDynamics, mppi
 // the inputs k runs in the reference's order (k ascending, bias added last, fnn_helper.cu:463-472) and each neuron's sum
 // is bit-identical to a scalar FFMA chain. Weights sit in shared memory TRANSPOSED ([in][out]) so one broadcast LDS.128
 // (all lanes read the same address: one wavefront) feeds two FFMA2.
+// Tried and rejected on B200: weights as kernel parameters (constant-bank operands, `FFMA R, R, UR, R` fed by LDCU.128).
+// One issue slot per MAC and no shared-memory traffic, but the constant cache that backs LDCU holds ~4 KB: the 5.6 KB
+// network misses on every pass and K1 went from 353 us to 543 us (tools/ffma_probe.cu, tools/ldcu_probe.cu: 2590 cycles
+// per 32x32 layer at a 4.1 KB working set, 4850 at 8.2 KB; profiles/r01_autorally_k1_notes.md).
 //   theta_s: WT1[6][32] | b1[32] | WT2[32][32] | b2[32] | WT3[32][4] | b3[4]      (1412 floats, like the reference)
 __device__ __forceinline__ float tanh_fast(float x)
 {
@@ -179,6 +194,7 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
     const float* theta_d;  // reference packed layout, MPPIB_AR_NN_NUM_PARAMS floats (fnn_helper.cu:176-183)
   };
 
+  using Dynamics<AutorallyNNDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>::initializeDynamics;  // the Carry overload
   // FNNHelper::initialize (fnn_helper.cu:385-416): block-cooperative global -> shared copy, transposing W on the way.
   __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s,
                                                             const float* x, float* y)
@@ -240,7 +256,11 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
                    : "r"(a + 16u * j4));
   }
 
-  template <int IN, int OUT, bool TANH>
+  // One dense layer. TANH_IN: the inputs are the previous layer's PRE-activations and tanh is applied to input k+1 while
+  // the FFMA2s of input k issue — the MUFU work (ex2 + rcp per tanh) then overlaps the FMA pipe inside a single warp
+  // instead of forming a separate phase between the layers (with < 2 warps per scheduler nothing else would hide it).
+  // TANH_OUT is applied in the epilogue (unused by the lazy pipeline, kept for the tensor-core variant's reference use).
+  template <int IN, int OUT, bool TANH_IN, bool TANH_OUT>
   __device__ static __forceinline__ void layer(const float* __restrict__ WT, const float* __restrict__ b,
                                                const float* in, float* out)
   {
@@ -250,6 +270,7 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
       acc[j] = make_float2(0.0f, 0.0f);
     float4 w[OUT / 4], wn[OUT / 4];
     load_row<OUT>(w, WT);
+    float x_cur = TANH_IN ? tanh_fast(in[0]) : in[0];
 #pragma unroll
     for (int k = 0; k < IN; k++)
     {
@@ -257,7 +278,10 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
         load_row<OUT>(wn, WT + (k + 1) * OUT);
       else
         load_row<OUT>(wn, b);  // the bias row rides the same pipeline
-      const float2 xk = make_float2(in[k], in[k]);
+      float x_next = 0.0f;
+      if (k + 1 < IN)
+        x_next = TANH_IN ? tanh_fast(in[k + 1]) : in[k + 1];
+      const float2 xk = make_float2(x_cur, x_cur);
 #pragma unroll
       for (int j4 = 0; j4 < OUT / 4; j4++)
       {
@@ -267,6 +291,7 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
 #pragma unroll
       for (int j4 = 0; j4 < OUT / 4; j4++)
         w[j4] = wn[j4];
+      x_cur = x_next;
     }
     // w now holds the bias row
 #pragma unroll
@@ -274,10 +299,10 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
     {
       const float t0 = acc[2 * j4].x + w[j4].x, t1 = acc[2 * j4].y + w[j4].y, t2 = acc[2 * j4 + 1].x + w[j4].z,
                   t3 = acc[2 * j4 + 1].y + w[j4].w;
-      out[4 * j4 + 0] = TANH ? tanh_fast(t0) : t0;
-      out[4 * j4 + 1] = TANH ? tanh_fast(t1) : t1;
-      out[4 * j4 + 2] = TANH ? tanh_fast(t2) : t2;
-      out[4 * j4 + 3] = TANH ? tanh_fast(t3) : t3;
+      out[4 * j4 + 0] = TANH_OUT ? tanh_fast(t0) : t0;
+      out[4 * j4 + 1] = TANH_OUT ? tanh_fast(t1) : t1;
+      out[4 * j4 + 2] = TANH_OUT ? tanh_fast(t2) : t2;
+      out[4 * j4 + 3] = TANH_OUT ? tanh_fast(t3) : t3;
     }
   }
 
@@ -290,9 +315,16 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
       a0[i] = state[i + (7 - DYNAMICS_DIM)];
     a0[4] = control[0];
     a0[5] = control[1];
-    layer<6, 32, true>(theta_s + L1_W, theta_s + L1_B, a0, a1);
-    layer<32, 32, true>(theta_s + L2_W, theta_s + L2_B, a1, a2);
-    layer<32, 4, false>(theta_s + L3_W, theta_s + L3_B, a2, a3);
+#ifdef MPPIB_EXP_NO_NN
+    (void)a1, (void)a2;
+    for (int i = 0; i < 4; i++)
+      a3[i] = 0.01f * a0[i] + 0.02f * a0[4 + (i & 1)];
+#else
+    // a1, a2 hold PRE-activations; the consuming layer applies tanh as it walks its inputs
+    layer<6, 32, false, false>(theta_s + L1_W, theta_s + L1_B, a0, a1);
+    layer<32, 32, true, false>(theta_s + L2_W, theta_s + L2_B, a1, a2);
+    layer<32, 4, true, false>(theta_s + L3_W, theta_s + L3_B, a2, a3);
+#endif
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       state_der[i + (7 - DYNAMICS_DIM)] = a3[i];
@@ -340,6 +372,13 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
     const float* theta_d;  // MPPIB_BLOB_LSTM_WEIGHTS: LSTM block then head block (params.h)
     int H, L1;
   };
+  // compile-time fast path: the reference's test architecture (racer_dubins_elevation_lstm_steering_model_test.cu:26-32)
+  // keeps h and c in registers and runs fully unrolled; any other (H, L1) takes the run-time loops over shared memory
+  static constexpr int FAST_H = 4, FAST_L1 = 20;
+  struct Carry
+  {
+    float h[FAST_H], c[FAST_H];
+  };
   struct Layout
   {
     int gate, w1t, b1, w2, b2, per_thread, L1p, total;
@@ -354,7 +393,7 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
     l.w2 = l.b1 + l.L1p;
     l.b2 = l.w2 + l.L1p;
     l.per_thread = l.b2 + 4;
-    l.total = l.per_thread + 3 * H * bx;
+    l.total = l.per_thread + ((H == FAST_H && L1 == FAST_L1) ? 0 : 3 * H * bx);
     return l;
   }
   static int sharedFloats(const int* model_dims, int bx)
@@ -399,7 +438,7 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
 
   // lstm_steering.cu:115-128 (initializeDynamics: LSTMHelper::initialize copies the weights to shared memory and the
   // initial hidden / cell state into the sample's slice; outputs from the initial state)
-  __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s,
+  __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s, Carry& carry,
                                                             const float* x, float* y)
   {
     const int H = aux.H, L1 = aux.L1, bx = blockDim.x, tid = threadIdx.x;
@@ -444,11 +483,23 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       theta_s[l.b2] = hd[L1 * IN + L1 + L1];
     // per-sample hidden / cell state <- initial_hidden_, initial_cell_ (lstm_helper.cu:86-87)
     const float* init = gb + 4 * H;
-    float* pt = theta_s + l.per_thread;
-    for (int j = 0; j < H; j++)
+    if (H == FAST_H && L1 == FAST_L1)
     {
-      pt[j * bx + tid] = init[j];               // hA
-      pt[(2 * H + j) * bx + tid] = init[H + j];  // c
+#pragma unroll
+      for (int j = 0; j < FAST_H; j++)
+      {
+        carry.h[j] = init[j];
+        carry.c[j] = init[FAST_H + j];
+      }
+    }
+    else
+    {
+      float* pt = theta_s + l.per_thread;
+      for (int j = 0; j < H; j++)
+      {
+        pt[j * bx + tid] = init[j];               // hA
+        pt[(2 * H + j) * bx + tid] = init[H + j];  // c
+      }
     }
     setOutputs(x, x, y);  // lstm_steering.cu:128
   }
@@ -456,6 +507,77 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
   __device__ static __forceinline__ float sigmoid_dev(float v)
   {
     return (1.0f + tanh_fast(v * 0.5f)) * 0.5f;  // activation_functions.cuh:49-59, device branch
+  }
+
+
+  // Same arithmetic and summation order as lstm_forward below with H, L1 known at compile time: every weight access is
+  // a broadcast LDS.128 at a constant offset, so ptxas batches the loads ahead of the FMA chains.
+  template <int HC, int L1C>
+  __device__ static __forceinline__ float lstm_forward_ct(const float* theta_s, const float (&in)[I], Carry& k)
+  {
+    constexpr int row_f4 = I + HC + 1, L1p = (L1C + 3) & ~3;
+    constexpr int off_w1t = 4 * HC * row_f4, off_b1 = off_w1t + (HC + I) * L1p, off_w2 = off_b1 + L1p,
+                  off_b2 = off_w2 + L1p;
+    const float4* G = reinterpret_cast<const float4*>(theta_s);
+    float hn[HC];
+#pragma unroll
+    for (int i = 0; i < HC; i++)
+    {
+      const float4* row = G + i * row_f4;
+      float gi = 0.0f, gf = 0.0f, go = 0.0f, gc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < I; j++)
+      {
+        const float4 w = row[j];
+        gi = fmaf(w.x, in[j], gi);
+        gf = fmaf(w.y, in[j], gf);
+        go = fmaf(w.z, in[j], go);
+        gc = fmaf(w.w, in[j], gc);
+      }
+#pragma unroll
+      for (int j = 0; j < HC; j++)
+      {
+        const float4 w = row[I + j];
+        gi = fmaf(w.x, k.h[j], gi);
+        gf = fmaf(w.y, k.h[j], gf);
+        go = fmaf(w.z, k.h[j], go);
+        gc = fmaf(w.w, k.h[j], gc);
+      }
+      const float4 b = row[I + HC];
+      gi = sigmoid_dev(gi + b.x);
+      gf = sigmoid_dev(gf + b.y);
+      go = sigmoid_dev(go + b.z);
+      gc = tanh_fast(gc + b.w);
+      k.c[i] = gi * gc + gf * k.c[i];
+      hn[i] = tanh_fast(k.c[i]) * go;
+    }
+#pragma unroll
+    for (int i = 0; i < HC; i++)
+      k.h[i] = hn[i];
+    const float* W1T = theta_s + off_w1t;
+    float out = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < L1p; k4 += 4)
+    {
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < HC + I; j++)
+      {
+        const float4 w = *reinterpret_cast<const float4*>(W1T + j * L1p + k4);
+        const float a = j < HC ? hn[j < HC ? j : 0] : in[j < HC ? 0 : j - HC];
+        acc.x = fmaf(w.x, a, acc.x);
+        acc.y = fmaf(w.y, a, acc.y);
+        acc.z = fmaf(w.z, a, acc.z);
+        acc.w = fmaf(w.w, a, acc.w);
+      }
+      const float4 b = *reinterpret_cast<const float4*>(theta_s + off_b1 + k4);
+      const float4 w2 = *reinterpret_cast<const float4*>(theta_s + off_w2 + k4);
+      out = fmaf(w2.x, tanh_fast(acc.x + b.x), out);
+      out = fmaf(w2.y, tanh_fast(acc.y + b.y), out);
+      out = fmaf(w2.z, tanh_fast(acc.z + b.z), out);
+      out = fmaf(w2.w, tanh_fast(acc.w + b.w), out);
+    }
+    return out + theta_s[off_b2];
   }
 
   // LSTMHelper::forward (device) + head; returns the head's single output. h is read from the buffer of parity
@@ -543,9 +665,9 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
     return index == 0 ? a[0] : (index == 1 ? a[1] : a[2]);
   }
 
-  __device__ static __forceinline__ void step(const Params& p, const Aux& aux, float* theta_s, const float* state,
-                                              float* next_state, float* state_der, const float* control,
-                                              float* output, int t, float dt)
+  __device__ static __forceinline__ void step(const Params& p, const Aux& aux, float* theta_s, Carry& carry,
+                                              const float* state, float* next_state, float* state_der,
+                                              const float* control, float* output, int t, float dt)
   {
     const float vx = state[VEL_X];
     const float linear_brake_slope = 0.2f;
@@ -595,7 +717,8 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       in[1] = state[STEER_ANGLE_RATE] * 0.2f;
       in[2] = control[1];
       in[3] = state_der[STEER_ANGLE_RATE] * 0.2f;
-      const float nn_output = lstm_forward(aux, theta_s, in, t);
+      const float nn_output = (aux.H == FAST_H && aux.L1 == FAST_L1) ? lstm_forward_ct<FAST_H, FAST_L1>(theta_s, in, carry)
+                                                                    : lstm_forward(aux, theta_s, in, t);
       state_der[STEER_ANGLE_RATE] += nn_output * 5.0f;
       state_der[STEER_ANGLE] = state[STEER_ANGLE_RATE];
     }

@@ -222,10 +222,11 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   }
   // initializeDynamics fills theta_s cooperatively (FNNHelper::initialize) and seeds y; initializeCosts fills theta_c
   // (mppi_common.cu:94-96)
+  typename DYN::Carry carry[D];
 #pragma unroll
   for (int d = 0; d < D; d++)
   {
-    DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, x[d], y[d]);
+    DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, carry[d], x[d], y[d]);
   }
   COST::initializeCosts(args.cost, args.cost_aux, theta_c, T);
   __syncthreads();
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
 #pragma unroll
           for (int i = 0; i < S; i++)
             xdot[i] = 0.0f;
-          DYN::step(args.dyn, args.dyn_aux, theta_s, x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
+          DYN::step(args.dyn, args.dyn_aux, theta_s, carry[d], x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
           float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[d], u, t, &crash_status[d]);
           if (lr_on)
             step_cost += likelihood_ratio_cost<C>(lr_scale[d], mean_t, u, pure_noise, half_lambda_1ma);  // :126-128

@@ -17,7 +17,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmppi_b200.so")
+# MPPIB_LIB points experiments (tools/) at an alternative build of the same ABI; the product always loads the in-tree one
+LIB_PATH = os.environ.get("MPPIB_LIB") or os.path.join(_HERE, "libmppi_b200.so")
 
 MAX_C = 4  # MPPIB_MAX_CONTROL_DIM
 MAX_D = 2  # MPPIB_MAX_DISTRIBUTIONS

@@ -149,6 +149,8 @@ def racer_lstm(N: int = 65536, T: int = 150, hidden_dim: int = 4, head_hidden: i
     dyn.setControlRanges([(-1.0, 1.0), (-1.0, 1.0)])  # throttle/brake, steering command
     dyn.setAllValues(*synthetic_lstm_weights(hidden_dim, head_hidden, 2))
     cost = H.RacerQuadraticCost()
+    # with the reference's default coefficients (racer_dubins.cuh:78-82) full throttle saturates near 1.6 m/s
+    cost.params.desired_speed = 1.2
     if colored:
         sampler = H.ColoredNoiseDistribution(2, [0.3, 0.3], [1.0, 1.0])
     else:
