@@ -53,40 +53,99 @@ const mppib_control_limits* limits_of(int dyn_id, const void* p)
   return nullptr;
 }
 
-// FNNHelper::forward host twin (utils/nn_helpers/fnn_helper.cu:354-382) for the fixed 6-32-32-4 net
-void fnn_6_32_32_4(const float* theta, const float* in6, float* out4)
+// FNNHelper::forward host twin (utils/nn_helpers/fnn_helper.cu:354-382) for the fixed 6-32-32-4 net.
+// The controller calls it T times per computeControl for the nominal trajectory (controller.cuh:643-663), which next to a
+// GPU solve of a few hundred microseconds is a visible share of the call (112 us of ~480 us at T = 100 with the plain
+// scalar loops + tanhf). So: weights transposed once per trajectory ([in][out], the inner loop runs over the OUT
+// neurons and vectorises without reassociating any neuron's k-ascending sum), a branch-free tanh (below), and AVX2+FMA /
+// baseline clones selected at load time.
+struct FnnT
 {
-  float a1[32], a2[32];
-  const float* W1 = theta;
-  const float* b1 = theta + 192;
-  const float* W2 = theta + 224;
-  const float* b2 = theta + 1248;
-  const float* W3 = theta + 1280;
-  const float* b3 = theta + 1408;
+  float WT1[6 * 32], b1[32], WT2[32 * 32], b2[32], WT3[32 * 4], b3[4];
+};
+void fnn_transpose(const float* theta, FnnT& t)
+{
   for (int j = 0; j < 32; j++)
-  {
-    float s = 0.0f;
     for (int k = 0; k < 6; k++)
-      s += W1[j * 6 + k] * in6[k];
-    a1[j] = tanhf(s + b1[j]);
-  }
+      t.WT1[k * 32 + j] = theta[j * 6 + k];
+  memcpy(t.b1, theta + 192, sizeof(t.b1));
   for (int j = 0; j < 32; j++)
-  {
-    float s = 0.0f;
     for (int k = 0; k < 32; k++)
-      s += W2[j * 32 + k] * a1[k];
-    a2[j] = tanhf(s + b2[j]);
-  }
+      t.WT2[k * 32 + j] = theta[224 + j * 32 + k];
+  memcpy(t.b2, theta + 1248, sizeof(t.b2));
   for (int j = 0; j < 4; j++)
-  {
-    float s = 0.0f;
     for (int k = 0; k < 32; k++)
-      s += W3[j * 32 + k] * a2[k];
-    out4[j] = s + b3[j];
-  }
+      t.WT3[k * 4 + j] = theta[1280 + j * 32 + k];
+  memcpy(t.b3, theta + 1408, sizeof(t.b3));
 }
 
-int state_deriv(int dyn_id, const void* p, const float* nn_theta, const float* x, const float* u, float* xdot)
+// tanh(x) = 1 - 2 / (exp(2x) + 1), exp by Cody-Waite reduction + degree-7 polynomial: |abs error| < 2e-7 over the whole
+// range (the same bound as the device kernels' tanh_fast; the reference calls tanhf, activation_functions.cuh:15-26).
+// Straight-line code so the loops over neurons vectorise.
+static inline float exp_host(float z)
+{
+  z = z > 30.0f ? 30.0f : (z < -30.0f ? -30.0f : z);
+  const float nf = (z * 1.44269504088896341f + 12582912.0f) - 12582912.0f;  // round to nearest integer
+  float r = z - nf * 0.693145751953125f;                                    // ln2 high part
+  r = r - nf * 1.42860682030941723212e-6f;                                  // ln2 low part
+  float p = 1.0f / 5040.0f;
+  p = p * r + 1.0f / 720.0f;
+  p = p * r + 1.0f / 120.0f;
+  p = p * r + 1.0f / 24.0f;
+  p = p * r + 1.0f / 6.0f;
+  p = p * r + 0.5f;
+  p = p * r + 1.0f;
+  p = p * r + 1.0f;
+  int bits = ((int)nf + 127) << 23;
+  float scale;
+  memcpy(&scale, &bits, sizeof(scale));
+  return p * scale;
+}
+static inline float tanh_host(float x)
+{
+  return 1.0f - 2.0f / (exp_host(2.0f * x) + 1.0f);
+}
+static inline float sigmoid_host(float x)  // activation_functions.cuh:49-59 (host branch: 1 / (1 + expf(-x)))
+{
+  return 1.0f / (1.0f + exp_host(-x));
+}
+
+__attribute__((target_clones("arch=x86-64-v3", "default"))) void fnn_6_32_32_4(const FnnT& t, const float* in6,
+                                                                              float* out4)
+{
+  float a1[32], a2[32], acc[32];
+  for (int j = 0; j < 32; j++)
+    acc[j] = 0.0f;
+  for (int k = 0; k < 6; k++)
+  {
+    const float xk = in6[k];
+    for (int j = 0; j < 32; j++)
+      acc[j] += t.WT1[k * 32 + j] * xk;
+  }
+  for (int j = 0; j < 32; j++)
+    a1[j] = tanh_host(acc[j] + t.b1[j]);
+  for (int j = 0; j < 32; j++)
+    acc[j] = 0.0f;
+  for (int k = 0; k < 32; k++)
+  {
+    const float xk = a1[k];
+    for (int j = 0; j < 32; j++)
+      acc[j] += t.WT2[k * 32 + j] * xk;
+  }
+  for (int j = 0; j < 32; j++)
+    a2[j] = tanh_host(acc[j] + t.b2[j]);
+  float o[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+  for (int k = 0; k < 32; k++)
+  {
+    const float xk = a2[k];
+    for (int j = 0; j < 4; j++)
+      o[j] += t.WT3[k * 4 + j] * xk;
+  }
+  for (int j = 0; j < 4; j++)
+    out4[j] = o[j] + t.b3[j];
+}
+
+int state_deriv(int dyn_id, const void* p, const FnnT* nn, const float* x, const float* u, float* xdot)
 {
   switch (dyn_id)
   {
@@ -110,13 +169,14 @@ int state_deriv(int dyn_id, const void* p, const float* nn_theta, const float* x
       return 0;
     case MPPIB_DYN_AUTORALLY_NN:
     {  // dynamics/autorally/ar_nn_model.cu:90-119
-      if (!nn_theta)
+      if (!nn)
         return MPPIB_ERR_INVALID_ARG;
-      xdot[0] = cosf(x[2]) * x[4] - sinf(x[2]) * x[5];
-      xdot[1] = sinf(x[2]) * x[4] + cosf(x[2]) * x[5];
+      const float cs = cosf(x[2]), sn = sinf(x[2]);
+      xdot[0] = cs * x[4] - sn * x[5];
+      xdot[1] = sn * x[4] + cs * x[5];
       xdot[2] = -x[6];
       const float in6[6] = { x[3], x[4], x[5], x[6], u[0], u[1] };
-      fnn_6_32_32_4(nn_theta, in6, xdot + 3);
+      fnn_6_32_32_4(*nn, in6, xdot + 3);
       return 0;
     }
   }
@@ -143,7 +203,7 @@ float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
   const int HH = H * H, IH = H * I;
   const float* w = net->theta;
   const float* bias = w + 4 * HH + 4 * IH;
-  std::vector<float> hn(H), cn(H);
+  float hn[64], cn[64];  // H <= 64 (engine limit)
   for (int i = 0; i < H; i++)
   {
     float g[4];
@@ -158,12 +218,13 @@ float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
         im += Wi[j] * in4[j];
       g[k] = (hm + im) + bias[k * H + i];
     }
-    const float gi = 1.0f / (1.0f + expf(-g[0])), gf = 1.0f / (1.0f + expf(-g[1])), go = 1.0f / (1.0f + expf(-g[2]));
-    cn[i] = gi * tanhf(g[3]) + gf * net->cell[i];
-    hn[i] = go * tanhf(cn[i]);
+    // exp-based activations without libm calls (exp_host above; |abs error| < 2e-7 against expf / tanhf)
+    const float gi = sigmoid_host(g[0]), gf = sigmoid_host(g[1]), go = sigmoid_host(g[2]);
+    cn[i] = gi * tanh_host(g[3]) + gf * net->cell[i];
+    hn[i] = go * tanh_host(cn[i]);
   }
-  memcpy(net->hidden, hn.data(), sizeof(float) * H);
-  memcpy(net->cell, cn.data(), sizeof(float) * H);
+  memcpy(net->hidden, hn, sizeof(float) * H);
+  memcpy(net->cell, cn, sizeof(float) * H);
   const float* hd = w + 4 * HH + 4 * IH + 6 * H;  // head {H+I, L1, 1}: W1 | b1 | W2 | b2 (fnn_helper.cu:176-183)
   const int IN = H + I;
   float out = 0.0f;
@@ -174,7 +235,7 @@ float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
       a += hd[k * IN + j] * hn[j];
     for (int j = 0; j < I; j++)
       a += hd[k * IN + H + j] * in4[j];
-    out += hd[L1 * IN + L1 + k] * tanhf(a + hd[L1 * IN + k]);
+    out += hd[L1 * IN + L1 + k] * tanh_host(a + hd[L1 * IN + k]);
   }
   return out + hd[L1 * IN + 2 * L1];
 }
@@ -335,15 +396,15 @@ int mppib_host_enforce_constraints(int dyn_id, const void* dyn_params, float* u)
   return MPPIB_OK;
 }
 
-int mppib_host_step(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x, const float* u,
-                    float dt, float* x_next, float* xdot, float* y)
+static int host_step_impl(int dyn_id, const void* dyn_params, const FnnT* nn, const float* x, const float* u, float dt,
+                          float* x_next, float* xdot, float* y)
 {
   int S, C, O;
   if (mppib_host_dims(dyn_id, &S, &C, &O) || !dyn_params || !x || !u || !x_next || !xdot || !y)
     return MPPIB_ERR_INVALID_ARG;
   for (int i = 0; i < S; i++)
     xdot[i] = 0.0f;
-  int rc = state_deriv(dyn_id, dyn_params, nn_theta, x, u, xdot);
+  int rc = state_deriv(dyn_id, dyn_params, nn, x, u, xdot);
   if (rc)
     return rc;
   for (int i = 0; i < S; i++)
@@ -351,6 +412,16 @@ int mppib_host_step(int dyn_id, const void* dyn_params, const float* nn_theta, c
   for (int i = 0; i < O && i < S; i++)
     y[i] = x_next[i];  // dynamics.cuh:292-300
   return MPPIB_OK;
+}
+
+int mppib_host_step(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x, const float* u,
+                    float dt, float* x_next, float* xdot, float* y)
+{
+  FnnT nn;
+  if (dyn_id == MPPIB_DYN_AUTORALLY_NN && nn_theta)
+    fnn_transpose(nn_theta, nn);
+  return host_step_impl(dyn_id, dyn_params, (dyn_id == MPPIB_DYN_AUTORALLY_NN && nn_theta) ? &nn : nullptr, x, u, dt,
+                        x_next, xdot, y);
 }
 
 void mppib_host_smooth_controls(float* u, const float* history, int T, int C)
@@ -401,6 +472,13 @@ int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float
   if (mppib_host_dims(dyn_id, &S, &C, &O) || !dyn_params || !x0 || !u || !states || !outputs || T <= 0)
     return MPPIB_ERR_INVALID_ARG;
   std::vector<float> xn(S), xd(S), y(O, 0.0f), ui(C);
+  FnnT nn;
+  const FnnT* nnp = nullptr;
+  if (dyn_id == MPPIB_DYN_AUTORALLY_NN && nn_theta)
+  {
+    fnn_transpose(nn_theta, nn);
+    nnp = &nn;
+  }
   memcpy(states, x0, sizeof(float) * S);
   for (int i = 0; i < O && i < S; i++)
     y[i] = x0[i];  // initializeDynamics (dynamics.cuh:416-423)
@@ -409,8 +487,8 @@ int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float
   {
     memcpy(ui.data(), u + (size_t)t * C, sizeof(float) * C);
     enforce(*limits_of(dyn_id, dyn_params), ui.data(), C);
-    int rc = mppib_host_step(dyn_id, dyn_params, nn_theta, states + (size_t)t * S, ui.data(), dt, xn.data(), xd.data(),
-                             y.data());
+    int rc = host_step_impl(dyn_id, dyn_params, nnp, states + (size_t)t * S, ui.data(), dt, xn.data(), xd.data(),
+                            y.data());
     if (rc)
       return rc;
     memcpy(states + (size_t)(t + 1) * S, xn.data(), sizeof(float) * S);
