@@ -242,9 +242,7 @@ public:
     MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_COST_PARAMS, &cb, sizeof(cb)));
     auto sb = sampler_->blob();
     MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_SAMPLER_PARAMS, &sb, sizeof(sb)));
-    if (model_->nnWeights())
-      MPPIB_HANDLE(mppib_set_blob(engine_, MPPIB_BLOB_NN_WEIGHTS, model_->nnWeights(),
-                                  MPPIB_AR_NN_NUM_PARAMS * sizeof(float)));
+    MPPIB_HANDLE(model_->pushModelBlobs(engine_));  // NN / LSTM weights
     pushCostmap(cost_);
     MPPIB_HANDLE(mppib_set_solver(engine_, params_.dt_, params_.lambda_, params_.alpha_));
   }
@@ -304,9 +302,7 @@ public:
     control_trajectory uu = u;
     state_trajectory st = state_trajectory::Zero();
     output_trajectory out = output_trajectory::Zero();
-    auto db = model_->blob();
-    MPPIB_HANDLE(mppib_host_output_trajectory(DYN_T::DYN_ID, &db, model_->nnWeights(), x.data(), uu.data(),
-                                              getNumTimesteps(), getDt(), st.data(), out.data()));
+    MPPIB_HANDLE(model_->hostOutputTrajectory(x.data(), uu.data(), getNumTimesteps(), getDt(), st.data(), out.data()));
     state_result = st;
     output_result = out;
   }
@@ -338,6 +334,7 @@ protected:
     d.stream = (void*)stream_;
     d.rank = 0;
     d.world_size = 1;
+    model_->fillModelDims(d.model_dims);
     MPPIB_HANDLE(mppib_create(&engine_, &d));
     pushParams();
     MPPIB_HANDLE(mppib_seed(engine_, params_.seed_, 0ULL));  // createAndSeedCUDARandomNumberGen (controller.cu:192-198)

@@ -96,6 +96,22 @@ public:
   {
     return nullptr;
   }
+  // ---- engine hooks used by Controller (controller.hpp); models with constructor-time architecture or extra weight
+  // blobs (the LSTM vehicle model) shadow them ---------------------------------------------------------------------
+  void fillModelDims(int* /*dims[8]*/) const
+  {
+  }
+  int pushModelBlobs(mppib_engine* e) const
+  {
+    const float* w = static_cast<const CLASS_T*>(this)->nnWeights();
+    return w ? mppib_set_blob(e, MPPIB_BLOB_NN_WEIGHTS, w, MPPIB_AR_NN_NUM_PARAMS * sizeof(float)) : MPPIB_OK;
+  }
+  int hostOutputTrajectory(const float* x0, const float* u, int T, float dt, float* states, float* outputs) const
+  {
+    BLOB_T b = blob();
+    return mppib_host_output_trajectory(DYN_ID_V, &b, static_cast<const CLASS_T*>(this)->nnWeights(), x0, u, T, dt,
+                                        states, outputs);
+  }
 
   // ---- host methods (dynamics.cuh:250-300) -----------------------------------------------------------------------
   void enforceConstraints(Eigen::Ref<state_array> /*state*/, Eigen::Ref<control_array> control)

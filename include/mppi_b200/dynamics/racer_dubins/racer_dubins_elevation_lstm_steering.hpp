@@ -1,0 +1,222 @@
+/*
+ * RacerDubinsElevationLSTMSteering — host class of
+ * include/mppi/dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cuh:20-119 (parameters: racer_dubins.cuh:13-104,
+ * racer_dubins_elevation.cuh:16-59). S19 C2 O28. Same constructor as the reference:
+ *   RacerDubinsElevationLSTMSteering(init_input_dim, init_hidden_dim, init_output_layers,
+ *                                    input_dim, hidden_dim, output_layers, init_len, stream)
+ * The prediction LSTM (input_dim 4, head {hidden_dim + 4, L1, 1}) runs inside the rollout kernel; the init network
+ * (LSTMLSTMHelper) only turns a history buffer into the initial hidden / cell state on the host (updateFromBuffer,
+ * lstm_steering.cu:215-232) and is represented by that state (setInitialHiddenCell). No elevation map: flat terrain.
+ */
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <vector>
+
+#include "../dynamics.hpp"
+
+struct RacerDubinsElevationParams
+{
+  enum class StateIndex : int
+  {
+    VEL_X = 0, YAW, POS_X, POS_Y, STEER_ANGLE, BRAKE_STATE, ROLL, PITCH, STEER_ANGLE_RATE, UNCERTAINTY_POS_X,
+    UNCERTAINTY_POS_Y, UNCERTAINTY_YAW, UNCERTAINTY_VEL_X, UNCERTAINTY_POS_X_Y, UNCERTAINTY_POS_X_YAW,
+    UNCERTAINTY_POS_X_VEL_X, UNCERTAINTY_POS_Y_YAW, UNCERTAINTY_POS_Y_VEL_X, UNCERTAINTY_YAW_VEL_X, NUM_STATES
+  };
+  enum class ControlIndex : int { THROTTLE_BRAKE = 0, STEER_CMD, NUM_CONTROLS };
+  enum class OutputIndex : int
+  {
+    BASELINK_VEL_B_X = 0, BASELINK_VEL_B_Y, BASELINK_POS_I_X, BASELINK_POS_I_Y, BASELINK_POS_I_Z, YAW, ROLL, PITCH,
+    STEER_ANGLE, STEER_ANGLE_RATE, WHEEL_FORCE_UP_MAX, WHEEL_FORCE_FWD_MAX, WHEEL_FORCE_SIDE_MAX, ACCEL_X, ACCEL_Y,
+    OMEGA_Z, TOTAL_VELOCITY, UNCERTAINTY_POS_X, UNCERTAINTY_POS_Y, UNCERTAINTY_YAW, UNCERTAINTY_VEL_X,
+    UNCERTAINTY_POS_X_Y, UNCERTAINTY_POS_X_YAW, UNCERTAINTY_POS_X_VEL_X, UNCERTAINTY_POS_Y_YAW, UNCERTAINTY_POS_Y_VEL_X,
+    UNCERTAINTY_YAW_VEL_X, FILLER_1, NUM_OUTPUTS
+  };
+  // racer_dubins.cuh:78-104
+  float c_t[3] = { 1.3f, 2.6f, 3.9f };
+  float c_b[3] = { 2.5f, 3.5f, 4.5f };
+  float c_v[3] = { 3.7f, 4.7f, 5.7f };
+  float c_0 = 4.9f;
+  float steering_constant = .6f;
+  float steer_command_angle_scale = 5;
+  float steer_angle_scale = -9.1f;
+  float max_steer_angle = 0.5f;
+  float max_steer_rate = 5;
+  float steer_accel_constant = 12.1f;
+  float steer_accel_drag_constant = 1.0f;
+  float brake_delay_constant = 6.6f;
+  float brake_delay_constant_neg = 8.2f;
+  float max_brake_rate_neg = 0.9f;
+  float max_brake_rate_pos = 0.33f;
+  float wheel_base = 0.3f;
+  float low_min_throttle = 0.13f;
+  float gravity = -9.81f;
+  int gear_sign = 1;
+  // racer_dubins_elevation.cuh:47-59
+  float clamp_ax = 5.5f;
+  float K_x = 1.0f, K_y = 1.0f, K_yaw = 1.0f, K_vel_x = 1.0f;
+  float Q_x_acc = 1.0f;
+  float Q_x_v[3] = { 41.74219f, -0.8187027f, -2.2131343f };
+  float Q_y_f = 0.1f;
+  float Q_omega_v = 0.001f;
+  float Q_omega_steering = 0.0f;
+};
+
+class RacerDubinsElevationLSTMSteering
+  : public MPPI_internal::Dynamics<RacerDubinsElevationLSTMSteering, mppib_racer_lstm_dyn_params, MPPIB_DYN_RACER_LSTM, 19,
+                                   2, 28>
+{
+public:
+  typedef RacerDubinsElevationParams DYN_PARAMS_T;
+  using PARENT = MPPI_internal::Dynamics<RacerDubinsElevationLSTMSteering, mppib_racer_lstm_dyn_params,
+                                         MPPIB_DYN_RACER_LSTM, 19, 2, 28>;
+
+  RacerDubinsElevationLSTMSteering(int init_input_dim, int init_hidden_dim, std::vector<int>& init_output_layers,
+                                   int input_dim, int hidden_dim, std::vector<int>& output_layers, int init_len,
+                                   cudaStream_t stream = 0)
+    : hidden_dim_(hidden_dim)
+  {
+    if (input_dim != MPPIB_RACER_LSTM_INPUT_DIM)
+      throw std::invalid_argument("the steering LSTM takes 4 inputs (lstm_steering.cu:148-151)");
+    if (output_layers.size() != 3 || output_layers[0] != hidden_dim + input_dim || output_layers[2] != 1)
+      throw std::invalid_argument("output_layers must be {hidden_dim + 4, L1, 1}");
+    if (init_output_layers.empty() || init_output_layers.back() != 2 * hidden_dim)
+      throw std::invalid_argument("init network must output 2 * hidden_dim values (lstm_lstm_helper.cu:11)");
+    head_hidden_ = output_layers[1];
+    theta_.assign((size_t)MPPIB_RACER_LSTM_NUM_PARAMS(hidden_dim_, head_hidden_), 0.0f);
+    (void)init_input_dim, (void)init_hidden_dim, (void)init_len;
+  }
+  void setParams(const DYN_PARAMS_T& p)
+  {
+    params_ = p;
+  }
+  DYN_PARAMS_T getParams() const
+  {
+    return params_;
+  }
+  bool checkRequiresBuffer() const
+  {
+    return true;  // lstm_steering.cu:15
+  }
+  int lstmBlock() const
+  {
+    return 4 * hidden_dim_ * hidden_dim_ + 4 * hidden_dim_ * MPPIB_RACER_LSTM_INPUT_DIM + 6 * hidden_dim_;
+  }
+  // LSTMHelper::setAllValues(lstm, output) (lstm_helper.cuh:65-72)
+  void setAllValues(const std::vector<float>& lstm, const std::vector<float>& output)
+  {
+    if ((int)lstm.size() != lstmBlock() || lstm.size() + output.size() != theta_.size())
+      throw std::invalid_argument("wrong number of LSTM / head parameters");
+    for (float v : lstm)
+      if (!std::isfinite(v))
+        throw std::invalid_argument("LSTM parameters must be finite");
+    for (float v : output)
+      if (!std::isfinite(v))
+        throw std::invalid_argument("LSTM parameters must be finite");
+    std::copy(lstm.begin(), lstm.end(), theta_.begin());
+    std::copy(output.begin(), output.end(), theta_.begin() + lstm.size());
+  }
+  // LSTMHelper::updateLSTMInitialStates (lstm_helper.cu:98-110)
+  void setInitialHiddenCell(const std::vector<float>& hidden, const std::vector<float>& cell)
+  {
+    const int base = lstmBlock() - 2 * hidden_dim_;
+    for (int i = 0; i < hidden_dim_; i++)
+    {
+      theta_[base + i] = hidden[i];
+      theta_[base + hidden_dim_ + i] = cell[i];
+    }
+  }
+  std::string getDynamicsModelName() const override
+  {
+    return "RACER Dubins LSTM Steering Model";
+  }
+  mppib_racer_lstm_dyn_params modelBlob() const
+  {
+    mppib_racer_lstm_dyn_params b{};
+    for (int i = 0; i < 3; i++)
+    {
+      b.c_t[i] = params_.c_t[i];
+      b.c_b[i] = params_.c_b[i];
+      b.c_v[i] = params_.c_v[i];
+      b.Q_x_v[i] = params_.Q_x_v[i];
+    }
+    b.c_0 = params_.c_0;
+    b.steering_constant = params_.steering_constant;
+    b.steer_command_angle_scale = params_.steer_command_angle_scale;
+    b.steer_angle_scale = params_.steer_angle_scale;
+    b.max_steer_angle = params_.max_steer_angle;
+    b.max_steer_rate = params_.max_steer_rate;
+    b.steer_accel_constant = params_.steer_accel_constant;
+    b.steer_accel_drag_constant = params_.steer_accel_drag_constant;
+    b.brake_delay_constant = params_.brake_delay_constant;
+    b.brake_delay_constant_neg = params_.brake_delay_constant_neg;
+    b.max_brake_rate_neg = params_.max_brake_rate_neg;
+    b.max_brake_rate_pos = params_.max_brake_rate_pos;
+    b.wheel_base = params_.wheel_base;
+    b.low_min_throttle = params_.low_min_throttle;
+    b.gravity = params_.gravity;
+    b.gear_sign = params_.gear_sign;
+    b.clamp_ax = params_.clamp_ax;
+    b.K_x = params_.K_x, b.K_y = params_.K_y, b.K_yaw = params_.K_yaw, b.K_vel_x = params_.K_vel_x;
+    b.Q_x_acc = params_.Q_x_acc;
+    b.Q_y_f = params_.Q_y_f;
+    b.Q_omega_v = params_.Q_omega_v;
+    b.Q_omega_steering = params_.Q_omega_steering;
+    return b;
+  }
+  // ---- engine hooks (controller.hpp) -------------------------------------------------------------------------------
+  void fillModelDims(int* dims) const
+  {
+    dims[0] = hidden_dim_;
+    dims[1] = head_hidden_;
+  }
+  int pushModelBlobs(mppib_engine* e) const
+  {
+    return mppib_set_blob(e, MPPIB_BLOB_LSTM_WEIGHTS, theta_.data(), theta_.size() * sizeof(float));
+  }
+  int hostOutputTrajectory(const float* x0, const float* u, int T, float dt, float* states, float* outputs) const
+  {
+    auto b = this->blob();
+    std::vector<float> h(hidden_dim_), c(hidden_dim_);
+    mppib_host_lstm net{ theta_.data(), hidden_dim_, head_hidden_, h.data(), c.data() };
+    return mppib_host_output_trajectory_lstm(&b, &net, x0, u, T, dt, states, outputs);
+  }
+  // host step with the LSTM state kept inside the object, like the reference's host twin
+  // (lstm_steering.cu:90-118; reset by initializeDynamics :230-237)
+  void initializeDynamics(const Eigen::Ref<const state_array>&, const Eigen::Ref<const control_array>&,
+                          Eigen::Ref<output_array>, float, float)
+  {
+    const int base = lstmBlock() - 2 * hidden_dim_;
+    hidden_.assign(theta_.begin() + base, theta_.begin() + base + hidden_dim_);
+    cell_.assign(theta_.begin() + base + hidden_dim_, theta_.begin() + base + 2 * hidden_dim_);
+  }
+  void step(Eigen::Ref<state_array> state, Eigen::Ref<state_array> next_state, Eigen::Ref<state_array> state_der,
+            const Eigen::Ref<const control_array>& control, Eigen::Ref<output_array> output, const float /*t*/,
+            const float dt)
+  {
+    if ((int)hidden_.size() != hidden_dim_)
+    {
+      output_array tmp;
+      initializeDynamics(state, control, tmp, 0.0f, dt);
+    }
+    float x[19], u[2], xn[19], xd[19], y[28];
+    for (int i = 0; i < 19; i++)
+      x[i] = state(i);
+    u[0] = control(0), u[1] = control(1);
+    auto b = this->blob();
+    mppib_host_lstm net{ theta_.data(), hidden_dim_, head_hidden_, hidden_.data(), cell_.data() };
+    MPPIB_HANDLE(mppib_host_step_lstm(&b, &net, x, u, dt, xn, xd, y));
+    for (int i = 0; i < 19; i++)
+    {
+      next_state(i) = xn[i];
+      state_der(i) = xd[i];
+    }
+    for (int i = 0; i < 28; i++)
+      output(i) = y[i];
+  }
+
+private:
+  DYN_PARAMS_T params_;
+  int hidden_dim_ = 4, head_hidden_ = 20;
+  std::vector<float> theta_, hidden_, cell_;
+};

@@ -119,7 +119,8 @@ struct mppib_engine
   int N = 0, T = 0, TC = 0;
   int n_local = 0, n_offset = 0;
   int pstride = 0, nchunks = 0;
-  int bx = 64, grid = 0;
+  int bx = 64, grid = 0;  // bx = samples (noise-tile rows) per CTA
+  int spt = 1;  // samples per thread (rollout_kernel.cuh); threads per CTA = bx / spt
   uint32_t smem_bytes = 0;
   bool use_tma = false;
   bool use_pdl = true;
@@ -283,10 +284,10 @@ struct Pair
     return COST::sharedFloats(T);
   }
 
-  template <int DD, bool WB>
+  template <int DD, bool WB, int SPT = 1>
   static int prepare_one(mppib_engine& e)
   {
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, DD, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, DD, WB, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)e.smem_bytes));
     return MPPIB_OK;
   }
@@ -306,6 +307,12 @@ struct Pair
                                         (int)e.smem_bytes));
         return MPPIB_OK;
       }
+    }
+    if (e.D == 1 && e.spt == 2)
+    {
+      if constexpr (DYN::MAX_SPT >= 2)
+        return e.writeback ? prepare_one<1, true, 2>(e) : prepare_one<1, false, 2>(e);
+      return fail(MPPIB_ERR_UNSUPPORTED, "this dynamics model is built for one sample per thread only");
     }
     if (e.D == 1)
       return e.writeback ? prepare_one<1, true>(e) : prepare_one<1, false>(e);
@@ -364,22 +371,33 @@ struct Pair
         launched = true;
       }
     }
+    const int threads = e.bx / e.spt;
     if (launched)
     {
+    }
+    else if (e.D == 1 && e.spt == 2)
+    {
+      if constexpr (DYN::MAX_SPT >= 2)
+      {
+        if (e.writeback)
+          rollout_kernel<DYN, COST, 1, true, 2><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+        else
+          rollout_kernel<DYN, COST, 1, false, 2><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+      }
     }
     else if (e.D == 1)
     {
       if (e.writeback)
-        rollout_kernel<DYN, COST, 1, true><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+        rollout_kernel<DYN, COST, 1, true, 1><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
       else
-        rollout_kernel<DYN, COST, 1, false><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+        rollout_kernel<DYN, COST, 1, false, 1><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
     }
     else if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
     {
       if (e.writeback)
-        rollout_kernel<DYN, COST, 2, true><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+        rollout_kernel<DYN, COST, 2, true, 1><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
       else
-        rollout_kernel<DYN, COST, 2, false><<<e.grid, e.bx, e.smem_bytes, e.stream>>>(a, e.tmap);
+        rollout_kernel<DYN, COST, 2, false, 1><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
     }
     CUDA_TRY(cudaGetLastError());
     return MPPIB_OK;
@@ -393,6 +411,7 @@ struct PairEntry
   size_t dyn_bytes, cost_bytes;
   int (*dyn_shared_floats)(const int*, int);
   int max_block_threads;
+  int max_spt;
   int (*cost_shared_floats)(int);
   int (*launch)(mppib_engine&, const float*, const float*, int, int);
   int (*prepare)(mppib_engine&);
@@ -409,6 +428,7 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     sizeof(typename COST::Params),
                     &DYN::sharedFloats,
                     DYN::MAX_BLOCK_THREADS,
+                    DYN::MAX_SPT,
                     &Pair<DYN, COST>::cost_shared,
                     &Pair<DYN, COST>::launch,
                     &Pair<DYN, COST>::prepare };
@@ -835,24 +855,35 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
                                     e->cost_shared_floats(e->T))
         .total;
   };
+  // samples per thread: 2 for models that re-read block-shared weights every step (DYN::MAX_SPT) once there are enough
+  // rollouts to keep a warp on every scheduler with half the threads (148 SMs x 4 schedulers x 32 lanes x 2 samples =
+  // 37888; measured cross-over in profiles/r01_autorally_k1_notes.md); MPPIB_SPT overrides
+  int spt = (entry->max_spt >= 2 && e->D == 1 && e->n_local >= 24576) ? 2 : 1;
+  if (const char* s = getenv("MPPIB_SPT"))
+  {
+    const int v = atoi(s);
+    if (v >= 1 && v <= entry->max_spt && (v == 1 || e->D == 1))
+      spt = v;
+  }
+  e->spt = spt;
   int bx = 0;
   if (const char* s = getenv("MPPIB_BX"))
   {
     bx = atoi(s);
-    if (bx < 32 || bx > 256 || (bx % 32) != 0)
+    if (bx < 32 || bx > 512 || (bx % (32 * spt)) != 0)
       bx = 0;
   }
   if (bx == 0)
   {
     int best = 0;
     long best_waves = 1L << 40;
-    for (int cand = 64; cand <= entry->max_block_threads; cand += 32)
+    for (int cand = 64; cand <= entry->max_block_threads * spt; cand += 32 * spt)
     {
       const int sm = smem_for(cand);
       if (sm > max_smem)
         break;
       // +1 KB per CTA is what the hardware reserves out of the SM's shared memory
-      const int per_sm = std::min(std::min(smem_per_sm / (sm + 1024), 2048 / cand), 32);
+      const int per_sm = std::min(std::min(smem_per_sm / (sm + 1024), 2048 / (cand / spt)), 32);
       if (per_sm < 1)
         break;
       const long blocks = (e->n_local + cand - 1) / cand;
@@ -865,8 +896,11 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     }
     bx = best ? best : 32;
   }
-  if (bx > entry->max_block_threads)
-    bx = entry->max_block_threads;
+  if (bx > entry->max_block_threads * spt)
+    bx = entry->max_block_threads * spt;
+  bx = (bx / (32 * spt)) * (32 * spt);  // whole warps of threads
+  if (bx < 32 * spt)
+    bx = 32 * spt;
   while (smem_for(bx) > max_smem && bx > 32)
     bx -= 32;
   e->smem_bytes = (uint32_t)smem_for(bx);
@@ -1667,7 +1701,7 @@ int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_byte
   if (grid)
     *grid = e->grid;
   if (block)
-    *block = e->bx;
+    *block = e->nn_tc ? e->bx : e->bx / e->spt;
   if (smem_bytes)
     *smem_bytes = (int)e->smem_bytes;
   if (uses_tma)

@@ -56,6 +56,7 @@ struct Dynamics
     return CLASS_T::SHARED_FLOATS;
   }
   static constexpr int MAX_DISTRIBUTIONS = 2;  // systems one thread may roll out side by side (Tube / RMPPI)
+  static constexpr int MAX_SPT = 1;  // samples one thread may roll out side by side (rollout_kernel.cuh: SPT)
   static constexpr int MAX_BLOCK_THREADS = 256;  // __launch_bounds__ of the rollout kernel for this model
   static constexpr bool UNROLL_STEPS = true;     // unroll the 4/C steps that share one 16-byte noise group
   struct Aux
@@ -110,6 +111,17 @@ struct Dynamics
       y[i] = x[i];
   }
   // dynamics.cu:131-142
+  // M systems of one thread advanced together (Tube's actual + nominal, or SPT samples); models that can share work
+  // between them (weight loads) override this
+  template <int M, class AUX, class CARRY>
+  __device__ static __forceinline__ void stepBatch(const Params& p, const AUX& aux, float* theta_s, CARRY (&carry)[M],
+                                                   const float (&x)[M][S], float (&x_next)[M][S], float (&xdot)[M][S],
+                                                   const float (&u)[M][C], float (&y)[M][O], int t, float dt)
+  {
+#pragma unroll
+    for (int m = 0; m < M; m++)
+      CLASS_T::step(p, aux, theta_s, carry[m], x[m], x_next[m], xdot[m], u[m], y[m], t, dt);
+  }
   template <class AUX, class CARRY>
   __device__ static __forceinline__ void step(const Params& p, const AUX&, float* theta_s, CARRY&, const float* x,
                                               float* x_next, float* xdot, const float* u, float* y, int /*t*/, float dt)
@@ -187,7 +199,14 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
   static constexpr int L1_W = 0, L1_B = L1_W + 6 * 32, L2_W = L1_B + 32, L2_B = L2_W + 32 * 32, L3_W = L2_B + 32,
                        L3_B = L3_W + 32 * 4;
   static constexpr int SHARED_FLOATS = L3_B + 4;  // 1412
-  static constexpr int MAX_BLOCK_THREADS = 256;   // 86 registers/thread: up to 7 warps of samples share one SM's tile
+  // Tried and rejected: splitting every layer's neurons over two adjacent lanes of a warp (SHFL.BFLY exchange, 2048
+  // warps instead of 1024 at N = 32768) — parity-green but 486 us against 353 us: the weight rows are then no longer warp-
+  // uniform addresses, every LDS.128 costs twice the shared-memory wavefronts per sample, and that data pipe is already
+  // the busiest unit (74 M wavefronts in 353 us = 72 % of one per cycle per SM, profiles/r01_autorally_v4_kernels.csv).
+  // What follows from the same measurement is the opposite move: TWO SAMPLES PER THREAD (stepBatch below), so that
+  // every weight row loaded from shared memory feeds twice the FFMA2s.
+  static constexpr int MAX_SPT = 2;
+  static constexpr int MAX_BLOCK_THREADS = 256;   // 99 registers/thread: up to 7 warps of samples share one SM's tile
   static constexpr bool UNROLL_STEPS = false;     // one copy of the 1344-FMA step body
   struct Aux
   {
@@ -315,22 +334,112 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
       a0[i] = state[i + (7 - DYNAMICS_DIM)];
     a0[4] = control[0];
     a0[5] = control[1];
-#ifdef MPPIB_EXP_NO_NN
-    (void)a1, (void)a2;
-    for (int i = 0; i < 4; i++)
-      a3[i] = 0.01f * a0[i] + 0.02f * a0[4 + (i & 1)];
-#else
     // a1, a2 hold PRE-activations; the consuming layer applies tanh as it walks its inputs
     layer<6, 32, false, false>(theta_s + L1_W, theta_s + L1_B, a0, a1);
     layer<32, 32, true, false>(theta_s + L2_W, theta_s + L2_B, a1, a2);
     layer<32, 4, true, false>(theta_s + L3_W, theta_s + L3_B, a2, a3);
-#endif
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       state_der[i + (7 - DYNAMICS_DIM)] = a3[i];
   }
-};
+  // The same dense layer for M samples of one thread: one weight row (LDS.128 quads, broadcast) feeds M * OUT/2 FFMA2s.
+  // Per-neuron accumulation order unchanged (k ascending, bias last), so every sample's values are those of layer<>.
+  template <int IN, int OUT, bool TANH_IN, int M>
+  __device__ static __forceinline__ void layerBatch(const float* __restrict__ WT, const float* __restrict__ b,
+                                                    const float (&in)[M][IN], float (&out)[M][OUT])
+  {
+    float2 acc[M][OUT / 2];
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+      for (int j = 0; j < OUT / 2; j++)
+        acc[m][j] = make_float2(0.0f, 0.0f);
+    // software pipeline as in layer<>: row k+1 (or the bias row) and the tanh of input k+1 are requested before the
+    // FFMA2s of row k, so their latencies sit under arithmetic even when the thread's warp is alone on its scheduler
+    float4 w[OUT / 4], wn[OUT / 4];
+    load_row<OUT>(w, WT);
+    float x_cur[M], x_next[M];
+#pragma unroll
+    for (int m = 0; m < M; m++)
+      x_cur[m] = TANH_IN ? tanh_fast(in[m][0]) : in[m][0];
+#pragma unroll
+    for (int k = 0; k < IN; k++)
+    {
+      if (k + 1 < IN)
+        load_row<OUT>(wn, WT + (k + 1) * OUT);
+      else
+        load_row<OUT>(wn, b);
+#pragma unroll
+      for (int m = 0; m < M; m++)
+        x_next[m] = (k + 1 < IN) ? (TANH_IN ? tanh_fast(in[m][k + 1]) : in[m][k + 1]) : 0.0f;
+#pragma unroll
+      for (int m = 0; m < M; m++)
+      {
+        const float2 xk = make_float2(x_cur[m], x_cur[m]);
+#pragma unroll
+        for (int j4 = 0; j4 < OUT / 4; j4++)
+        {
+          acc[m][2 * j4] = __ffma2_rn(make_float2(w[j4].x, w[j4].y), xk, acc[m][2 * j4]);
+          acc[m][2 * j4 + 1] = __ffma2_rn(make_float2(w[j4].z, w[j4].w), xk, acc[m][2 * j4 + 1]);
+        }
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < OUT / 4; j4++)
+        w[j4] = wn[j4];
+#pragma unroll
+      for (int m = 0; m < M; m++)
+        x_cur[m] = x_next[m];
+    }
+    // w now holds the bias row
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+      for (int j4 = 0; j4 < OUT / 4; j4++)
+      {
+        out[m][4 * j4 + 0] = acc[m][2 * j4].x + w[j4].x;
+        out[m][4 * j4 + 1] = acc[m][2 * j4].y + w[j4].y;
+        out[m][4 * j4 + 2] = acc[m][2 * j4 + 1].x + w[j4].z;
+        out[m][4 * j4 + 3] = acc[m][2 * j4 + 1].y + w[j4].w;
+      }
+  }
 
+  template <int M, class AUX, class CARRY>
+  __device__ static __forceinline__ void stepBatch(const Params& p, const AUX& aux, float* theta_s, CARRY (&carry)[M],
+                                                   const float (&x)[M][7], float (&x_next)[M][7], float (&xdot)[M][7],
+                                                   const float (&u)[M][2], float (&y)[M][8], int t, float dt)
+  {
+    if constexpr (M == 1)
+    {
+      step(p, aux, theta_s, carry[0], x[0], x_next[0], xdot[0], u[0], y[0], t, dt);
+    }
+    else
+    {
+      float a0[M][6], a1[M][32], a2[M][32], a3[M][4];
+#pragma unroll
+      for (int m = 0; m < M; m++)
+      {
+        computeKinematics(p, x[m], xdot[m]);
+#pragma unroll
+        for (int i = 0; i < DYNAMICS_DIM; i++)
+          a0[m][i] = x[m][i + (7 - DYNAMICS_DIM)];
+        a0[m][4] = u[m][0];
+        a0[m][5] = u[m][1];
+      }
+      layerBatch<6, 32, false, M>(theta_s + L1_W, theta_s + L1_B, a0, a1);
+      layerBatch<32, 32, true, M>(theta_s + L2_W, theta_s + L2_B, a1, a2);
+      layerBatch<32, 4, true, M>(theta_s + L3_W, theta_s + L3_B, a2, a3);
+#pragma unroll
+      for (int m = 0; m < M; m++)
+      {
+#pragma unroll
+        for (int i = 0; i < DYNAMICS_DIM; i++)
+          xdot[m][i + (7 - DYNAMICS_DIM)] = a3[m][i];
+        updateState(x[m], x_next[m], xdot[m], dt);
+        stateToOutput(x_next[m], y[m]);
+      }
+    }
+  }
+};
 
 // ---- RacerDubinsElevationLSTMSteering: dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cu:131-213,240-262
 //      (device step / computeLSTMSteering / updateState), racer_dubins.cu:281-293 (brake delay),

@@ -130,20 +130,27 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, 
   return s;
 }
 
-template <class DYN, class COST, int D, bool WRITEBACK>
+// SPT = samples per thread. 1 everywhere except for models whose step re-reads block-shared weights (the NN): there a
+// second sample in the same thread reuses every weight row it loads, which halves the shared-memory wavefronts per
+// sample — the busiest unit of that kernel (profiles/r01_autorally_k1_notes.md) — and gives the in-order
+// issue two independent dependency chains to interleave. Thread `thr` owns tile rows thr + sp * blockDim.x.
+template <class DYN, class COST, int D, bool WRITEBACK, int SPT>
 __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
                                                       const __grid_constant__ CUtensorMap tmap)
 {
   constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
   static_assert(C == 1 || C == 2 || C == 4, "CONTROL_DIM must divide a 16-byte group");
   static_assert(D <= MPPIB_MAX_DISTRIBUTIONS, "too many distributions");
+  static_assert(SPT == 1 || D == 1, "several samples per thread are built for one distribution");
   constexpr int STEPS_PER_GROUP = 4 / C;
+  constexpr int M = SPT * D;  // systems rolled out by one thread: member m = sp * D + d
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  const int bx = blockDim.x;
-  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  const int bx = nthr * SPT;  // samples (tile rows) per block
+  const int thr = threadIdx.x;
   const int T = args.T;
   const int TC = T * C;
   const int nchunks = args.nchunks;
@@ -158,14 +165,23 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
 
   pdl_launch_dependents();           // K2 may be scheduled now; it waits for this grid to finish before reading
   const int row0 = blockIdx.x * bx;  // first local rollout of this block
-  const int n_loc = row0 + tid;
-  const bool valid = n_loc < args.n_local;
-  const int n_glob = args.n_offset + n_loc;
+  int row[SPT], n_loc[SPT];
+  bool valid[SPT], pure_noise[SPT], zero_noise_sample[SPT];
+#pragma unroll
+  for (int sp = 0; sp < SPT; sp++)
+  {
+    row[sp] = thr + sp * nthr;
+    n_loc[sp] = row0 + row[sp];
+    valid[sp] = n_loc[sp] < args.n_local;
+    const int n_glob = args.n_offset + n_loc[sp];
+    pure_noise[sp] = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
+    zero_noise_sample[sp] = (n_glob == 0);                             // gaussian.cu:101
+  }
 
   // ---- stage the block's noise rows -------------------------------------------------------------------------------
   if (args.use_tma)
   {
-    if (tid == 0)
+    if (thr == 0)
     {
       tma_prefetch_desc(&tmap);
       for (int k = 0; k < nchunks; k++)
@@ -173,7 +189,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
       fence_barrier_init();
     }
     __syncthreads();
-    if (tid == 0)
+    if (thr == 0)
     {
       for (int k = 0; k < nchunks; k++)
       {
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     const float* src = args.eps + (size_t)row0 * TC;
     const int rows_here = min(bx, args.n_local - row0);
     const int total = bx * nchunks * kChunkFloats;
-    for (int i = tid; i < total; i += bx)
+    for (int i = thr; i < total; i += nthr)
     {
       const int r = i / (nchunks * kChunkFloats);
       const int col = i - r * (nchunks * kChunkFloats);
@@ -202,37 +218,34 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   }
 
   // ---- block-shared read-only data --------------------------------------------------------------------------------
-  for (int i = tid; i < D * TC; i += bx)
+  for (int i = thr; i < D * TC; i += nthr)
     means_s[i] = args.means[i];
 
   // ---- per-sample state in registers ------------------------------------------------------------------------------
-  float x[D][S], y[D][O], running_cost[D];
-  int crash_status[D];
+  float x[M][S], y[M][O], running_cost[M];
+  int crash_status[M];
 #pragma unroll
-  for (int d = 0; d < D; d++)
+  for (int m = 0; m < M; m++)
   {
 #pragma unroll
     for (int i = 0; i < S; i++)
-      x[d][i] = args.x0[d * S + i];
+      x[m][i] = args.x0[(m % D) * S + i];
 #pragma unroll
     for (int i = 0; i < O; i++)
-      y[d][i] = 0.0f;
-    running_cost[d] = 0.0f;
-    crash_status[d] = 0;
+      y[m][i] = 0.0f;
+    running_cost[m] = 0.0f;
+    crash_status[m] = 0;
   }
   // initializeDynamics fills theta_s cooperatively (FNNHelper::initialize) and seeds y; initializeCosts fills theta_c
   // (mppi_common.cu:94-96)
-  typename DYN::Carry carry[D];
+  typename DYN::Carry carry[M];
 #pragma unroll
-  for (int d = 0; d < D; d++)
+  for (int m = 0; m < M; m++)
   {
-    DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, carry[d], x[d], y[d]);
+    DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, carry[m], x[m], y[m]);
   }
   COST::initializeCosts(args.cost, args.cost_aux, theta_c, T);
   __syncthreads();
-
-  const bool pure_noise = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
-  const bool zero_noise_sample = (n_glob == 0);                             // gaussian.cu:101
 
   // likelihood-ratio term: skipped altogether when every control_cost_coeff is zero (the sampler's default)
   float lr_scale[D][C];
@@ -258,8 +271,14 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
       const int col0 = k * kChunkFloats + g * 4;
       if (col0 >= TC)
         break;
-      unsigned char* gp = tile + tile_offset_bytes(bx, k, tid, g);
-      const float4 e4 = *reinterpret_cast<const float4*>(gp);
+      unsigned char* gp[SPT];
+      float4 e4[SPT];
+#pragma unroll
+      for (int sp = 0; sp < SPT; sp++)
+      {
+        gp[sp] = tile + tile_offset_bytes(bx, k, row[sp], g);
+        e4[sp] = *reinterpret_cast<const float4*>(gp[sp]);
+      }
       // light models: the 4/C steps of a 16-byte group are unrolled; heavy ones (NN) keep one copy of the step body
 #pragma unroll(DYN::UNROLL_STEPS ? STEPS_PER_GROUP : 1)
       for (int s = 0; s < STEPS_PER_GROUP; s++)
@@ -267,68 +286,80 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         const int t = col0 / C + s;
         if (t >= T)
           break;
-        const bool use_mean = zero_noise_sample || (t < args.opt_stride);
+        float u[M][C], x_next[M][S], xdot[M][S];
 #pragma unroll
-        for (int d = 0; d < D; d++)
+        for (int m = 0; m < M; m++)
         {
-          float u[C], x_next[S], xdot[S];
+          const int sp = m / D, d = m % D;
+          const bool use_mean = zero_noise_sample[sp] || (t < args.opt_stride);
           const float* mean_t = means_s + (d * T + t) * C;
 #pragma unroll
           for (int c = 0; c < C; c++)
-            u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], group_elem(e4, s * C + c), use_mean,
-                                  pure_noise);
-          DYN::enforceConstraints(args.dyn, x[d], u);  // mppi_common.cu:108-111
+            u[m][c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], group_elem(e4[sp], s * C + c), use_mean,
+                                     pure_noise[sp]);
+          DYN::enforceConstraints(args.dyn, x[m], u[m]);  // mppi_common.cu:108-111
           if (D == 1)
           {
             // single system: the constrained control replaces the noise in the shared tile (what writeControlSample does
             // in HBM, mppi_common.cu:117), so the epilogue's weighted sum reads it back instead of recomputing it
 #pragma unroll
             for (int c = 0; c < C; c++)
-              reinterpret_cast<float*>(gp)[s * C + c] = u[c];
+              reinterpret_cast<float*>(gp[sp])[s * C + c] = u[m][c];
           }
           if (WRITEBACK)
           {  // compat / debug path: keep the constrained samples in HBM like the reference
-            if (valid)
+            if (valid[sp])
             {
-              float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc) * T + t) * C;
+              float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc[sp]) * T + t) * C;
 #pragma unroll
               for (int c = 0; c < C; c++)
-                dst[c] = u[c];
+                dst[c] = u[m][c];
             }
           }
 #pragma unroll
           for (int i = 0; i < S; i++)
-            xdot[i] = 0.0f;
-          DYN::step(args.dyn, args.dyn_aux, theta_s, carry[d], x[d], x_next, xdot, u, y[d], t, args.dt);  // mppi_common.cu:120
-          float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[d], u, t, &crash_status[d]);
+            xdot[m][i] = 0.0f;
+        }
+        DYN::template stepBatch<M>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);  // mppi_common.cu:120
+#pragma unroll
+        for (int m = 0; m < M; m++)
+        {
+          const int sp = m / D, d = m % D;
+          float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[m], u[m], t, &crash_status[m]);
           if (lr_on)
-            step_cost += likelihood_ratio_cost<C>(lr_scale[d], mean_t, u, pure_noise, half_lambda_1ma);  // :126-128
-          running_cost[d] += step_cost;
+            step_cost += likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t) * C, u[m], pure_noise[sp],
+                                                  half_lambda_1ma);  // :126-128
+          running_cost[m] += step_cost;
 #pragma unroll
           for (int i = 0; i < S; i++)
-            x[d][i] = x_next[i];
+            x[m][i] = x_next[m][i];
         }
       }
     }
   }
 
   // ---- per-sample cost (computeAndSaveCost, mppi_common.cu:843-853) ------------------------------------------------
-  float cost[D];
+  float cost[M];
 #pragma unroll
-  for (int d = 0; d < D; d++)
+  for (int m = 0; m < M; m++)
   {
-    cost[d] = running_cost[d] / (float)T + COST::terminalCost(args.cost, args.cost_aux, y[d]) / (float)T;
-    if (valid)
-      args.costs[(size_t)d * args.n_local + n_loc] = cost[d];
+    const int sp = m / D, d = m % D;
+    cost[m] = running_cost[m] / (float)T + COST::terminalCost(args.cost, args.cost_aux, y[m]) / (float)T;
+    if (valid[sp])
+      args.costs[(size_t)d * args.n_local + n_loc[sp]] = cost[m];
   }
 
   // ---- block partial of the softmin-weighted control average ------------------------------------------------------
-  const int lane = tid & 31, warp = tid >> 5, nwarps = (bx + 31) >> 5;
+  const int lane = thr & 31, warp = thr >> 5, nwarps = (nthr + 31) >> 5;
 #pragma unroll
   for (int d = 0; d < D; d++)
   {
     // block baseline
-    float m = warp_min(valid ? cost[d] : INFINITY);
+    float mn = INFINITY;
+#pragma unroll
+    for (int sp = 0; sp < SPT; sp++)
+      mn = fminf(mn, valid[sp] ? cost[sp * D + d] : INFINITY);
+    float m = warp_min(mn);
     if (lane == 0)
       red_s[warp] = m;
     __syncthreads();
@@ -336,16 +367,23 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     for (int i = 1; i < nwarps; i++)
       beta_b = fminf(beta_b, red_s[i]);
     // normExpTransform (mppi_common.cu:958-966) against the block baseline
-    const float w = valid ? expf(-args.lambda_inv * (cost[d] - beta_b)) : 0.0f;
-    w_s[d * bx + tid] = w;
-    const float sw = warp_sum(w), sw2 = warp_sum(w * w);
+    float wsum = 0.0f, w2sum = 0.0f;
+#pragma unroll
+    for (int sp = 0; sp < SPT; sp++)
+    {
+      const float w = valid[sp] ? expf(-args.lambda_inv * (cost[sp * D + d] - beta_b)) : 0.0f;
+      w_s[d * bx + row[sp]] = w;
+      wsum += w;
+      w2sum += w * w;
+    }
+    const float sw = warp_sum(wsum), sw2 = warp_sum(w2sum);
     if (lane == 0)
     {
       red_s[32 + warp] = sw;
       red_s[64 + warp] = sw2;
     }
     __syncthreads();
-    if (tid == 0)
+    if (thr == 0)
     {
       float eta_b = 0.0f, w2_b = 0.0f;
       for (int i = 0; i < nwarps; i++)
@@ -367,7 +405,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   for (int d = 0; d < D; d++)
   {
     float* out = args.partials + ((size_t)blockIdx.x * D + d) * args.pstride + kPartialHeader;
-    for (int t = tid; t < T; t += bx)
+    for (int t = thr; t < T; t += nthr)
     {
       float acc[C];
 #pragma unroll

@@ -32,3 +32,31 @@ def test_host_layer_cartpole_example_swings_up_on_the_gpu():
     p = subprocess.run([EXE], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "final pole angle error" in p.stdout
+
+
+RACER_EXE = os.path.join(ROOT, "tests", "cpp", "racer_colored_example.bin")
+
+
+def _build_racer():
+    lib_dir = os.path.join(ROOT, "mppi-generic_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-variable", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "racer_colored_example.cpp"), "-o", RACER_EXE, "-L", lib_dir,
+                           "-lmppi_b200", "-Wl,-rpath," + lib_dir])
+
+
+def test_racer_colored_example_compiles_against_reference_include_paths():
+    """C5 through the C++ layer via the reference's own include paths (include/mppi/**.cuh forwarders)."""
+    _build_racer()
+    p = subprocess.run([RACER_EXE], capture_output=True, text=True, timeout=600)
+    if p.returncode == 5:
+        assert "no CUDA device" in p.stdout
+    else:
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_racer_colored_example_tracks_speed_on_the_gpu():
+    _build_racer()
+    p = subprocess.run([RACER_EXE], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "speed after 80 steps" in p.stdout

@@ -161,6 +161,118 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32));
 }
 
+
+// Round-trip latency of one layer's MMAs: thread 0 issues them + commit, every thread then waits on the mbarrier
+// (WAIT = 0: mbarrier.try_wait loop, 1: mbarrier.test_wait spin) and reads 32 accumulator columns back from TMEM.
+template <int N, int K, int WAIT>
+__global__ void __launch_bounds__(128) latency(float* out, long long* cycles, int reps)
+{
+  constexpr int KC = K / 4;
+  __shared__ __align__(128) float4 a_hi[KC][128];
+  __shared__ __align__(128) float4 a_lo[KC][128];
+  __shared__ __align__(128) float4 w_hi[KC][N];
+  __shared__ __align__(128) float4 w_lo[KC][N];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0)
+  {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int kc = 0; kc < KC; kc++)
+  {
+    a_hi[kc][tid] = make_float4(0.5f, 0.25f, 0.125f, 1.0f);
+    a_lo[kc][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = tid; i < KC * N; i += 128)
+  {
+    w_hi[i / N][i % N] = make_float4(0.01f, 0.02f, 0.03f, 0.04f);
+    w_lo[i / N][i % N] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = make_idesc_tf32(128, N);
+  uint32_t phase = 0;
+  float sum = 0.0f;
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; r++)
+  {
+    if (tid == 0)
+    {
+      uint32_t acc = 0;
+      for (int kb = 0; kb < K / 8; kb++)
+      {
+        const uint64_t dah = make_desc(smem_u32(&a_hi[kb * 2][0]), 2048, 128);
+        const uint64_t dal = make_desc(smem_u32(&a_lo[kb * 2][0]), 2048, 128);
+        const uint64_t dwh = make_desc(smem_u32(&w_hi[kb * 2][0]), N * 16, 128);
+        const uint64_t dwl = make_desc(smem_u32(&w_lo[kb * 2][0]), N * 16, 128);
+        mma_tf32(tmem_base, dah, dwh, idesc, acc);
+        mma_tf32(tmem_base, dal, dwh, idesc, 1);
+        mma_tf32(tmem_base, dah, dwl, idesc, 1);
+        acc = 1;
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok)
+    {
+      if (WAIT == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+      else
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(phase) : "memory");
+    }
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t v[4];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    sum += __uint_as_float(v[0]) + __uint_as_float(v[3]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // the kernel's per-layer barrier: operands of the next layer are written by all threads
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * 128 + tid] = sum;
+  if (tid == 0 && blockIdx.x == 0)
+    *cycles = t1 - t0;
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32));
+}
+
+template <int N, int K, int WAIT>
+static void run_latency(const char* name, int ctas)
+{
+  float* out;
+  long long* cyc;
+  cudaMalloc(&out, ctas * 128 * sizeof(float));
+  cudaMalloc(&cyc, sizeof(long long));
+  const int reps = 300;
+  latency<N, K, WAIT><<<ctas, 128>>>(out, cyc, reps);
+  cudaDeviceSynchronize();
+  latency<N, K, WAIT><<<ctas, 128>>>(out, cyc, reps);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c = 0;
+  cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
+  printf("%s N=%d K=%d (%d MMAs) wait=%s ctas=%d: %.0f cycles per issue->commit->wait->tmem-ld->barrier round trip (%s)\n", name, N,
+         K, 3 * K / 8, WAIT ? "test_wait" : "try_wait", ctas, (double)c / reps, cudaGetErrorString(e));
+  cudaFree(out);
+  cudaFree(cyc);
+}
+
 template <int N, int K, bool SPLIT3>
 static void run(const char* name)
 {
@@ -196,5 +308,11 @@ int main()
   run<32, 32, true>("L2 3xtf32 ");
   run<32, 8, true>("L1 3xtf32 ");
   run<8, 32, true>("L3 3xtf32 ");
+  run_latency<32, 32, 0>("L2", 148);
+  run_latency<32, 32, 1>("L2", 148);
+  run_latency<32, 8, 0>("L1", 148);
+  run_latency<32, 8, 1>("L1", 148);
+  run_latency<32, 32, 0>("L2", 296);
+  run_latency<32, 32, 1>("L2", 296);
   return 0;
 }
