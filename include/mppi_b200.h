@@ -61,6 +61,8 @@ enum mppib_blob
                                             (mppi_common.cu:117); needed by mppib_get_samples */
 #define MPPIB_FLAG_NO_TMA 2u             /* stage noise tiles with plain loads instead of cp.async.bulk.tensor */
 #define MPPIB_FLAG_NO_PREFETCH 8u         /* draw each solve's noise inline instead of one solve ahead on a side stream */
+#define MPPIB_FLAG_RMPPI 32u             /* RobustMPPI rollout semantics (core/rmppi_kernels.cu:665-866): requires                \
+                                            num_distributions == 2 with distribution 0 = nominal, 1 = real system */
 #define MPPIB_FLAG_NN_TENSOR 16u         /* Autorally NN: forward pass on tcgen05 tensor cores (3xTF32) instead of FP32 FFMA2 */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
@@ -186,6 +188,17 @@ enum mppib_option
   MPPIB_OPT_COLORED_OFFSET_T = 2
 };
 int mppib_set_option(mppib_engine* e, int option, long long value);
+
+/* ---- RMPPI (engines created with MPPIB_FLAG_RMPPI) ------------------------------------------------------------- */
+/* RobustMPPIController::setValueFunctionThreshold + fb_controller_->copyToDevice (robust_mppi_controller.cu:630-633):
+ * feedback_gains = the DDP gain trajectory, T matrices C x S column-major ([t][s][c]), or NULL for no feedback. */
+int mppib_set_rmppi(mppib_engine* e, float value_func_threshold, const float* feedback_gains);
+/* computeNominalStateAndStride's device part (robust_mppi_controller.cu:581-617): draws one noise block with
+ * `optimization_stride` (generateSamples) and evaluates num_candidates nominal-state candidates x samples_per_candidate
+ * rollouts of the nominal control U_nominal [T][C], candidate k replaying the controls shifted by strides[k]
+ * (launchInitEvalKernel, core/rmppi_kernels.cu:230-356). costs_out [num_candidates * samples_per_candidate]. */
+int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides, int num_candidates,
+                    int samples_per_candidate, const float* U_nominal, int optimization_stride, float* costs_out);
 
 const char* mppib_strerror(int status);
 const char* mppib_last_error(void); /* thread-local text of the last failure */

@@ -40,6 +40,14 @@ int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, con
                          float* x_next, float* xdot, float* y);
 int mppib_host_output_trajectory_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x0,
                                       const float* u, int T, float dt, float* states, float* outputs);
+/* RobustMPPI host logic (controllers/R-MPPI/robust_mppi_controller.cu:351-362,472-537): line-search weights [3][K],
+ * nominal-state candidates [K][S] + importance-sampler strides [K], best candidate (returns previous_best if none
+ * is under the value-function threshold). */
+void mppib_host_rmppi_line_search_weights(int num_candidates, float* out);
+void mppib_host_rmppi_candidates(int num_candidates, int S, const float* nominal_x_k, const float* nominal_x_kp1,
+                                 const float* real_x_kp1, int stride, float* candidates, int* strides);
+int mppib_host_rmppi_best_index(const float* costs, int num_candidates, int samples_per_candidate, float lambda,
+                                float value_func_threshold, int previous_best, float* free_energy);
 void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float lambda, float* out3);
 /* CPU twin of the K2 merge (csrc/combine_kernel.cuh): records [nrec][D][pstride] = (beta, eta, sum w^2, -, V[TC]). */
 int mppib_host_merge_records(const float* records, int nrec, int D, int TC, int pstride, float lambda, int normalize,

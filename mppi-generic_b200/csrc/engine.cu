@@ -132,6 +132,14 @@ struct mppib_engine
   unsigned* done_flag_dev = nullptr;
   unsigned solve_seq = 0;
   bool writeback = false;
+  bool rmppi = false;  // MPPIB_FLAG_RMPPI
+  float value_func_threshold = 1000.0f;  // robust_mppi_controller.cuh default
+  float* fb_gains_d = nullptr;           // [T][S][C] or null
+  float* eval_states_d = nullptr;        // init-eval scratch: candidates, strides, costs
+  int* eval_strides_d = nullptr;
+  float* eval_costs_d = nullptr;
+  int eval_capacity = 0;
+  int (*init_eval)(mppib_engine&, const float*, const int*, int, int, const float*, int) = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
 
@@ -308,6 +316,16 @@ struct Pair
         return MPPIB_OK;
       }
     }
+    if (e.rmppi)
+    {
+      if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
+      {
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2, true, 1, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
+        return MPPIB_OK;
+      }
+      return fail(MPPIB_ERR_UNSUPPORTED, "this dynamics model is built for num_distributions == 1 only");
+    }
     if (e.D == 1 && e.spt == 2)
     {
       if constexpr (DYN::MAX_SPT >= 2)
@@ -353,6 +371,8 @@ struct Pair
     a.opt_stride = opt_stride;
     a.use_tma = e.use_tma ? 1 : 0;
     a.dyn_shared_floats = e.dyn_shared_floats;
+    a.fb_gains = e.fb_gains_d;
+    a.value_func_threshold = e.value_func_threshold;
     a.dt = e.dt;
     a.lambda = e.lambda;
     a.alpha = e.alpha;
@@ -374,6 +394,11 @@ struct Pair
     const int threads = e.bx / e.spt;
     if (launched)
     {
+    }
+    else if (e.rmppi)
+    {
+      if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
+        rollout_kernel<DYN, COST, 2, true, 1, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
     }
     else if (e.D == 1 && e.spt == 2)
     {
@@ -404,6 +429,50 @@ struct Pair
   }
 };
 
+// launchInitEvalKernel (core/rmppi_kernels.cu:912-937) for this pair
+template <class DYN, class COST>
+static int init_eval_launch(mppib_engine& e, const float* candidates_d, const int* strides_d, int num_candidates, int samples,
+                            const float* U_nominal, int opt_stride)
+{
+  using Args = InitEvalArgs<DYN, COST>;
+  static_assert(sizeof(Args) < 30000, "kernel parameter block too large");
+  Args a;
+  memcpy(&a.dyn, e.dyn_blob.data(), sizeof(a.dyn));
+  memcpy(&a.cost, e.cost_blob.data(), sizeof(a.cost));
+  AuxFill<typename DYN::Aux>::fill(a.dyn_aux, e);
+  AuxFill<typename COST::Aux>::fill(a.cost_aux, e);
+  for (int d = 0; d < MPPIB_MAX_DISTRIBUTIONS; d++)
+    for (int c = 0; c < MPPIB_MAX_CONTROL_DIM; c++)
+    {
+      const float sd = (c < e.C) ? e.sampler.std_dev[d * e.C + c] : 1.0f;
+      a.samp.std_dev[d][c] = sd;
+      a.samp.std_dev_decayed[d][c] = sd;  // generateSamples(stride, 0, ...): iteration 0, decay^0 = 1
+    }
+  for (int c = 0; c < MPPIB_MAX_CONTROL_DIM; c++)
+    a.samp.control_cost_coeff[c] = e.sampler.control_cost_coeff[c];
+  a.samp.pure_noise_threshold = (1.0f - e.sampler.pure_noise_trajectories_percentage) * e.N;
+  a.eps = e.eps_d;
+  a.candidates = candidates_d;
+  a.strides = strides_d;
+  a.costs = e.eval_costs_d;
+  a.num_candidates = num_candidates;
+  a.samples = samples;
+  a.T = e.T;
+  a.opt_stride = opt_stride;
+  const int threads = 64;
+  a.dyn_shared_floats = DYN::sharedFloats(e.desc.model_dims, threads);
+  a.dt = e.dt;
+  a.lambda = e.lambda;
+  a.alpha = e.alpha;
+  memcpy(a.means, U_nominal, sizeof(float) * e.TC);
+  const int total = num_candidates * samples;
+  const size_t smem = (size_t)(((a.dyn_shared_floats + 3) / 4) * 4 + COST::sharedFloats(e.T)) * sizeof(float) + 16;
+  CUDA_TRY(cudaFuncSetAttribute(init_eval_kernel<DYN, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  init_eval_kernel<DYN, COST><<<(total + threads - 1) / threads, threads, smem, e.stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return MPPIB_OK;
+}
+
 struct PairEntry
 {
   int dyn_id, cost_id;
@@ -415,6 +484,7 @@ struct PairEntry
   int (*cost_shared_floats)(int);
   int (*launch)(mppib_engine&, const float*, const float*, int, int);
   int (*prepare)(mppib_engine&);
+  int (*init_eval)(mppib_engine&, const float*, const int*, int, int, const float*, int);
 };
 template <class DYN, class COST>
 constexpr PairEntry make_entry(int dyn_id, int cost_id)
@@ -431,7 +501,8 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     DYN::MAX_SPT,
                     &Pair<DYN, COST>::cost_shared,
                     &Pair<DYN, COST>::launch,
-                    &Pair<DYN, COST>::prepare };
+                    &Pair<DYN, COST>::prepare,
+                    &init_eval_launch<DYN, COST> };
 }
 static const PairEntry kPairs[] = {
   make_entry<plugins::CartpoleDynamics, plugins::CartpoleQuadraticCost>(MPPIB_DYN_CARTPOLE,
@@ -813,11 +884,18 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->TC = e->T * e->C;
   e->launch_rollout = entry->launch;
   e->prepare = entry->prepare;
+  e->init_eval = entry->init_eval;
   e->dyn_param_bytes = entry->dyn_bytes;
   e->cost_param_bytes = entry->cost_bytes;
   e->dyn_shared_floats_fn = entry->dyn_shared_floats;
   e->cost_shared_floats = entry->cost_shared_floats;
-  e->writeback = (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
+  e->rmppi = (desc->flags & MPPIB_FLAG_RMPPI) != 0;
+  if (e->rmppi && desc->num_distributions != 2)
+  {
+    delete e;
+    return fail(MPPIB_ERR_INVALID_ARG, "MPPIB_FLAG_RMPPI needs num_distributions == 2 (nominal, real)");
+  }
+  e->writeback = e->rmppi || (desc->flags & MPPIB_FLAG_WRITEBACK_CONTROLS) != 0;
   e->use_pdl = !getenv("MPPIB_NO_PDL");
   e->mapped_result = !getenv("MPPIB_NO_MAPPED_RESULT");
   // measured on B200: polling a mapped flag is not faster than cudaStreamSynchronize (39.99 vs 40.33 us per cartpole
@@ -1105,6 +1183,10 @@ int mppib_destroy(mppib_engine* e)
     cudaFreeArray(e->costmap_array);
   cudaFree(e->nn_theta_d);
   cudaFree(e->lstm_theta_d);
+  cudaFree(e->fb_gains_d);
+  cudaFree(e->eval_states_d);
+  cudaFree(e->eval_strides_d);
+  cudaFree(e->eval_costs_d);
   cudaFree(e->noise_alloc);
   cudaFree(e->noise_alloc2);
   cudaFree(e->costs_d);
@@ -1578,6 +1660,82 @@ int mppib_solve_wait(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
     return fail(MPPIB_ERR_STATE, "no solve in flight");
   CUDA_TRY(cudaSetDevice(e->desc.device));
   return wait_solve(e, U_out, stats);
+}
+
+int mppib_set_rmppi(mppib_engine* e, float value_func_threshold, const float* feedback_gains)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (!e->rmppi)
+    return fail(MPPIB_ERR_STATE, "engine was not created with MPPIB_FLAG_RMPPI");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  e->value_func_threshold = value_func_threshold;
+  const size_t n = (size_t)e->T * e->S * e->C;
+  if (feedback_gains)
+  {
+    for (size_t i = 0; i < n; i++)
+      if (!std::isfinite(feedback_gains[i]))
+        return fail(MPPIB_ERR_INVALID_ARG, "feedback gain %zu is not finite", i);
+    if (!e->fb_gains_d)
+      CUDA_TRY(cudaMalloc(&e->fb_gains_d, n * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(e->fb_gains_d, feedback_gains, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
+  else if (e->fb_gains_d)
+  {
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    cudaFree(e->fb_gains_d);
+    e->fb_gains_d = nullptr;
+  }
+  return MPPIB_OK;
+}
+
+int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides, int num_candidates,
+                    int samples_per_candidate, const float* U_nominal, int optimization_stride, float* costs_out)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!candidates || !strides || !U_nominal || !costs_out || num_candidates <= 0 || samples_per_candidate <= 0)
+    return fail(MPPIB_ERR_INVALID_ARG, "bad argument");
+  if (e->desc.world_size != 1)
+    return fail(MPPIB_ERR_UNSUPPORTED, "init-eval runs on one rank (a few hundred rollouts)");
+  if (samples_per_candidate > e->n_local || (long)num_candidates * samples_per_candidate > e->N)
+    return fail(MPPIB_ERR_INVALID_ARG, "(number of candidates) * (samples per candidate) cannot exceed NUM_ROLLOUTS");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  const int total = num_candidates * samples_per_candidate;
+  if (total > e->eval_capacity || !e->eval_states_d)
+  {
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    cudaFree(e->eval_states_d);
+    cudaFree(e->eval_strides_d);
+    cudaFree(e->eval_costs_d);
+    e->eval_states_d = nullptr;
+    e->eval_capacity = 0;
+    CUDA_TRY(cudaMalloc(&e->eval_states_d, (size_t)total * e->S * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&e->eval_strides_d, (size_t)total * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&e->eval_costs_d, (size_t)total * sizeof(float)));
+    e->eval_capacity = total;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->eval_states_d, candidates, (size_t)num_candidates * e->S * sizeof(float),
+                           cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->eval_strides_d, strides, (size_t)num_candidates * sizeof(int), cudaMemcpyHostToDevice,
+                           e->stream));
+  rc = draw_noise(*e, optimization_stride);  // sampler_->generateSamples(stride, 0, gen_) (:595)
+  if (rc != MPPIB_OK)
+    return rc;
+  rc = e->init_eval(*e, e->eval_states_d, e->eval_strides_d, num_candidates, samples_per_candidate, U_nominal,
+                    optimization_stride);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (e->prefetch_enabled)
+  {  // the kernel above read eps_buf[cur_buf]: later draws into that buffer must wait for it
+    CUDA_TRY(cudaEventRecord(e->ev_k1_done[e->cur_buf], e->stream));
+    e->k1_recorded[e->cur_buf] = true;
+  }
+  CUDA_TRY(cudaMemcpyAsync(costs_out, e->eval_costs_d, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
 }
 
 int mppib_set_option(mppib_engine* e, int option, long long value)

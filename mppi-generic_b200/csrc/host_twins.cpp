@@ -541,6 +541,65 @@ int mppib_host_output_trajectory_lstm(const void* dyn_params, const mppib_host_l
   return MPPIB_OK;
 }
 
+// ---- RobustMPPI host logic (controllers/R-MPPI/robust_mppi_controller.cu) --------------------------------------------
+void mppib_host_rmppi_line_search_weights(int num_candidates, float* out /*[3][K]*/)
+{  // computeLineSearchWeights, :472-491
+  const int K = num_candidates, h = K / 2;
+  for (int i = 0; i < 3 * K; i++)
+    out[i] = 0.0f;
+  for (int i = 0; i < h + 1; i++)
+  {
+    out[0 * K + i] = 1 - i / float(h);
+    out[1 * K + i] = i / float(h);
+    out[2 * K + i] = 0.0;
+  }
+  for (int i = 1; i < h + 1; i++)
+  {
+    out[0 * K + h + i] = 0.0;
+    out[1 * K + h + i] = 1 - i / float(h);
+    out[2 * K + h + i] = i / float(h);
+  }
+}
+
+void mppib_host_rmppi_candidates(int num_candidates, int S, const float* nominal_x_k, const float* nominal_x_kp1,
+                                 const float* real_x_kp1, int stride, float* candidates /*[K][S]*/, int* strides /*[K]*/)
+{  // getInitNominalStateCandidates :351-362 (points * line_search_weights) and computeImportanceSamplerStride :493-503
+  std::vector<float> w(3 * (size_t)num_candidates);
+  mppib_host_rmppi_line_search_weights(num_candidates, w.data());
+  const int K = num_candidates;
+  for (int k = 0; k < K; k++)
+  {
+    for (int i = 0; i < S; i++)
+      candidates[(size_t)k * S + i] = nominal_x_k[i] * w[k] + nominal_x_kp1[i] * w[K + k] + real_x_kp1[i] * w[2 * K + k];
+    strides[k] = (int)roundf(0.0f * w[k] + (float)stride * w[K + k] + (float)stride * w[2 * K + k]);
+  }
+}
+
+int mppib_host_rmppi_best_index(const float* costs, int num_candidates, int samples_per_candidate, float lambda,
+                                float value_func_threshold, int previous_best, float* free_energy /*[K] or NULL*/)
+{  // computeCandidateBaseline + computeBestIndex, :505-537 (the LAST candidate under the threshold wins; if none does
+   // best_index_ keeps its previous value)
+  const int n = num_candidates * samples_per_candidate;
+  float baseline = costs[0];
+  for (int i = 1; i < n; i++)
+    if (costs[i] < baseline)
+      baseline = costs[i];
+  int best = previous_best;
+  for (int i = 0; i < num_candidates; i++)
+  {
+    float fe = 0.0f;
+    for (int j = 0; j < samples_per_candidate; j++)
+      fe += expf(-1.0 / lambda * (costs[i * samples_per_candidate + j] - baseline));
+    fe /= (1.0 * samples_per_candidate);
+    fe = -lambda * logf(fe) + baseline;
+    if (free_energy)
+      free_energy[i] = fe;
+    if (fe < value_func_threshold)
+      best = i;
+  }
+  return best;
+}
+
 void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float lambda, float* out3)
 {
   // core/mppi_common.cu:1065-1081 from (eta, sum w^2): norm = eta/N, var = sum w^2

@@ -65,6 +65,9 @@ struct RolloutArgs
   int opt_stride;
   int use_tma;
   int dyn_shared_floats;  // DYN::sharedFloats(model_dims, blockDim.x): theta_s size (run-time for the LSTM model)
+  // RMPPI (rollout_kernel<..., RMPPI = true>): distribution 0 = nominal system, 1 = real system
+  const float* fb_gains;       // DDP feedback gains [T][S][C] (column-major C x S per step) or nullptr (no feedback)
+  float value_func_threshold;  // robust_mppi_controller.cuh: value_function_threshold_
   float dt, lambda, alpha, lambda_inv;
   float x0[MPPIB_MAX_DISTRIBUTIONS * kMaxStateDim];  // [D][S]
   float means[kMaxMeanFloats];                       // [D][T][C] importance-sampler mean == nominal control
@@ -134,7 +137,13 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, 
 // second sample in the same thread reuses every weight row it loads, which halves the shared-memory wavefronts per
 // sample — the busiest unit of that kernel (profiles/r01_autorally_k1_notes.md) — and gives the in-order
 // issue two independent dependency chains to interleave. Thread `thr` owns tile rows thr + sp * blockDim.x.
-template <class DYN, class COST, int D, bool WRITEBACK, int SPT>
+//
+// RMPPI = true (D == 2, WRITEBACK): the fused form of rolloutRMPPIKernel, core/rmppi_kernels.cu:665-866 — the real system
+// (d = 1) adds the feedback K_t (x_real - x_nominal) to its sampled control before the constraints; the real cost takes
+// running + likelihood-ratio cost, its tracking cost running + feedback cost (gaussian.cu:572-629); the nominal cost is
+// 0.5 c_nom + 0.5 max(min(tracking_real, value_func_threshold), c_nom) + its likelihood-ratio cost. The real system's
+// applied control depends on the state, so the block's weighted average reads it back from the write-back buffer.
+template <class DYN, class COST, int D, bool WRITEBACK, int SPT, bool RMPPI = false>
 __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
                                                       const __grid_constant__ CUtensorMap tmap)
 {
@@ -142,6 +151,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   static_assert(C == 1 || C == 2 || C == 4, "CONTROL_DIM must divide a 16-byte group");
   static_assert(D <= MPPIB_MAX_DISTRIBUTIONS, "too many distributions");
   static_assert(SPT == 1 || D == 1, "several samples per thread are built for one distribution");
+  static_assert(!RMPPI || (D == 2 && WRITEBACK && SPT == 1), "RMPPI: two systems, controls kept in HBM");
   constexpr int STEPS_PER_GROUP = 4 / C;
   constexpr int M = SPT * D;  // systems rolled out by one thread: member m = sp * D + d
 
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     means_s[i] = args.means[i];
 
   // ---- per-sample state in registers ------------------------------------------------------------------------------
-  float x[M][S], y[M][O], running_cost[M];
+  float x[M][S], y[M][O], running_cost[M], extra_cost[M];
   int crash_status[M];
 #pragma unroll
   for (int m = 0; m < M; m++)
@@ -234,6 +244,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     for (int i = 0; i < O; i++)
       y[m][i] = 0.0f;
     running_cost[m] = 0.0f;
+    extra_cost[m] = 0.0f;
     crash_status[m] = 0;
   }
   // initializeDynamics fills theta_s cooperatively (FNNHelper::initialize) and seeds y; initializeCosts fills theta_c
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         const int t = col0 / C + s;
         if (t >= T)
           break;
-        float u[M][C], x_next[M][S], xdot[M][S];
+        float u[M][C], x_next[M][S], xdot[M][S], ufb[C];
 #pragma unroll
         for (int m = 0; m < M; m++)
         {
@@ -297,6 +308,27 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
           for (int c = 0; c < C; c++)
             u[m][c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], group_elem(e4[sp], s * C + c), use_mean,
                                      pure_noise[sp]);
+          if (RMPPI && m == 1)
+          {  // fb_controller->k(x, x_nom, t) (rmppi_kernels.cu:770-784; DDP: K_t e, ddp.cu:11-45 in its host form)
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              ufb[c] = 0.0f;
+            if (args.fb_gains != nullptr)
+            {
+              const float* Kt = args.fb_gains + (size_t)t * S * C;
+#pragma unroll
+              for (int i = 0; i < S; i++)
+              {
+                const float e = x[1][i] - x[0][i];
+#pragma unroll
+                for (int c = 0; c < C; c++)
+                  ufb[c] = fmaf(__ldg(Kt + i * C + c), e, ufb[c]);
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              u[m][c] += ufb[c];
+          }
           DYN::enforceConstraints(args.dyn, x[m], u[m]);  // mppi_common.cu:108-111
           if (D == 1)
           {
@@ -326,10 +358,26 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         {
           const int sp = m / D, d = m % D;
           float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[m], u[m], t, &crash_status[m]);
+          float lr_cost = 0.0f;
           if (lr_on)
-            step_cost += likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t) * C, u[m], pure_noise[sp],
-                                                  half_lambda_1ma);  // :126-128
-          running_cost[m] += step_cost;
+            lr_cost = likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t) * C, u[m], pure_noise[sp],
+                                               half_lambda_1ma);  // :126-128
+          if (!RMPPI)
+            running_cost[m] += step_cost + lr_cost;
+          else if (m == 0)
+          {  // nominal system: rmppi_kernels.cu:806-811
+            running_cost[m] += step_cost;
+            extra_cost[m] += lr_cost;
+          }
+          else
+          {  // real system: :813-819; computeFeedbackCost = 0.5 lambda (1 - alpha) sum_i k_i u_fb,i^2 / sigma_i^2
+            running_cost[m] += step_cost + lr_cost;
+            float fb_cost = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              fb_cost += lr_scale[d][c] * (ufb[c] * ufb[c]);
+            extra_cost[m] += step_cost + half_lambda_1ma * fb_cost;
+          }
 #pragma unroll
           for (int i = 0; i < S; i++)
             x[m][i] = x_next[m][i];
@@ -345,9 +393,29 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   {
     const int sp = m / D, d = m % D;
     cost[m] = running_cost[m] / (float)T + COST::terminalCost(args.cost, args.cost_aux, y[m]) / (float)T;
+  }
+  if (RMPPI)
+  {  // rmppi_kernels.cu:836-858
+    const float term_nom = COST::terminalCost(args.cost, args.cost_aux, y[0]);
+    const float term_real = COST::terminalCost(args.cost, args.cost_aux, y[M - 1]);
+    const float c_real = (running_cost[M - 1] + term_real) / (float)T;
+    const float tracking_real = (extra_cost[M - 1] + term_real) / (float)T;
+    float c_nom = (running_cost[0] + term_nom) / (float)T;
+    const float tracking_nom = extra_cost[0] / (float)T;
+    c_nom = 0.5f * c_nom + 0.5f * fmaxf(fminf(tracking_real, args.value_func_threshold), c_nom);
+    c_nom += tracking_nom;
+    cost[0] = c_nom;
+    cost[M - 1] = c_real;
+  }
+#pragma unroll
+  for (int m = 0; m < M; m++)
+  {
+    const int sp = m / D, d = m % D;
     if (valid[sp])
       args.costs[(size_t)d * args.n_local + n_loc[sp]] = cost[m];
   }
+  if (RMPPI)
+    __threadfence_block();  // the epilogue reads other threads' written-back controls
 
   // ---- block partial of the softmin-weighted control average ------------------------------------------------------
   const int lane = thr & 31, warp = thr >> 5, nwarps = (nthr + 31) >> 5;
@@ -399,7 +467,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   // exp-weighted sum of the CONSTRAINED sampled controls (weightedReductionKernel, mppi_common.cu:710-737), taken
   // from the shared tile: thread j owns time step j (all C components so enforceConstraints sees the full u).
   // D == 1: the tile already holds the constrained controls. D == 2: the tile still holds the shared noise and each
-  // system's control is recomputed from it.
+  // system's control is recomputed from it (RMPPI's real system: read back, see above).
   const int rows_here = min(bx, args.n_local - row0);
 #pragma unroll
   for (int d = 0; d < D; d++)
@@ -434,6 +502,13 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
               for (int c = 0; c < C; c++)
                 u[c] = p[c];
             }
+            else if (RMPPI && d == 1)
+            {  // the real system's applied control (sample + feedback, constrained) as K1 wrote it back
+              const float* q = args.controls_out + (((size_t)d * args.n_local + row0 + r) * T + t) * C;
+#pragma unroll
+              for (int c = 0; c < C; c++)
+                u[c] = q[c];
+            }
             else
             {
               const int ng = args.n_offset + row0 + r;
@@ -456,6 +531,90 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         out[col + c] = acc[c];
     }
   }
+}
+
+// initEvalKernel, core/rmppi_kernels.cu:230-356: K candidate nominal states x `samples` noise rows; candidate k replays
+// the sampled controls shifted by its stride (control at step t = sample at min(t + stride_k, T - 1)) and only the
+// trajectory cost is kept. One thread per (candidate, sample); the noise rows are the first `samples` rows of the block
+// the sampler just drew (readControlSample(candidate_sample_idx, ...), :292-294), read straight from HBM/L2.
+template <class DYN, class COST>
+struct InitEvalArgs
+{
+  typename DYN::Params dyn;
+  typename COST::Params cost;
+  typename DYN::Aux dyn_aux;
+  typename COST::Aux cost_aux;
+  SamplerArgs samp;
+  const float* eps;         // [n_local][T][C]
+  const float* candidates;  // [K][S]
+  const int* strides;       // [K]
+  float* costs;             // [K * samples]
+  int num_candidates, samples, T, opt_stride, dyn_shared_floats;
+  float dt, lambda, alpha;
+  float means[kMaxMeanFloats];  // [T][C] nominal control (distribution 0)
+};
+
+template <class DYN, class COST>
+__global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) init_eval_kernel(const __grid_constant__ InitEvalArgs<DYN, COST> args)
+{
+  constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
+  extern __shared__ unsigned char smem_raw[];
+  float* theta_s = reinterpret_cast<float*>(smem_raw);
+  float* theta_c = theta_s + ((args.dyn_shared_floats + 3) / 4) * 4;
+  const int T = args.T;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = args.num_candidates * args.samples;
+  const bool valid = gid < total;
+  const int k = valid ? gid / args.samples : 0, j = valid ? gid % args.samples : 0;
+  float x[1][S], y[1][O], x_next[1][S], xdot[1][S], u[1][C];
+#pragma unroll
+  for (int i = 0; i < S; i++)
+    x[0][i] = args.candidates[k * S + i];
+#pragma unroll
+  for (int i = 0; i < O; i++)
+    y[0][i] = 0.0f;
+  typename DYN::Carry carry[1];
+  DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, carry[0], x[0], y[0]);
+  COST::initializeCosts(args.cost, args.cost_aux, theta_c, T);
+  __syncthreads();
+  const int stride = args.strides[k];
+  const bool pure_noise_row = (float)j >= args.samp.pure_noise_threshold;    // the row's own flags: setGaussianControls
+  const bool pure_noise_lr = (float)gid >= args.samp.pure_noise_threshold;   // LR cost is called with global_idx (:331-333)
+  float lr_scale[C];
+  bool lr_on = false;
+#pragma unroll
+  for (int c = 0; c < C; c++)
+  {
+    lr_scale[c] = args.samp.control_cost_coeff[c] / (args.samp.std_dev[0][c] * args.samp.std_dev[0][c]);
+    lr_on = lr_on || (args.samp.control_cost_coeff[c] != 0.0f);
+  }
+  const float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
+  float running = 0.0f;
+  int crash = 0;
+  for (int t = 0; t < T; t++)
+  {
+    const int ct = min(t + stride, T - 1);
+    const bool use_mean = (j == 0) || (ct < args.opt_stride);
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      u[0][c] = sample_control(args.means[ct * C + c], args.samp.std_dev_decayed[0][c],
+                               __ldg(args.eps + ((size_t)j * T + ct) * C + c), use_mean, pure_noise_row);
+    DYN::enforceConstraints(args.dyn, x[0], u[0]);
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      xdot[0][i] = 0.0f;
+    DYN::template stepBatch<1>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);
+    running += COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[0], u[0], t, &crash);
+    if (lr_on)
+      running += likelihood_ratio_cost<C>(lr_scale, args.means + t * C, u[0], pure_noise_lr, half_lambda_1ma);
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      x[0][i] = x_next[0][i];
+  }
+  running += COST::terminalCost(args.cost, args.cost_aux, y[0]);
+  running /= (float)T;
+  if (valid)
+    args.costs[gid] = running;
 }
 
 }  // namespace mppib

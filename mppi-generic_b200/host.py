@@ -29,7 +29,7 @@ DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM = 0, 1, 2,
 COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC = 0, 1, 2, 3
 SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
 BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
-FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR = 1, 2, 4, 8, 16
+FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR, FLAG_RMPPI = 1, 2, 4, 8, 16, 32
 OPT_L2_FLUSH_BYTES = 1
 OPT_COLORED_OFFSET_T = 2
 RACER_LSTM_INPUT_DIM = 4
@@ -164,6 +164,8 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_host_rmppi_best_index",
 ]
 
 _lib = None
@@ -216,6 +218,13 @@ def lib() -> C.CDLL:
     L.mppib_host_output_trajectory.argtypes = [C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp]
     L.mppib_host_step_lstm.argtypes = [vp, C.POINTER(HostLSTM), vp, vp, C.c_float, vp, vp, vp]
     L.mppib_host_output_trajectory_lstm.argtypes = [vp, C.POINTER(HostLSTM), vp, vp, C.c_int, C.c_float, vp, vp]
+    L.mppib_set_rmppi.argtypes = [vp, C.c_float, vp]
+    L.mppib_init_eval.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.mppib_host_rmppi_line_search_weights.argtypes = [C.c_int, vp]
+    L.mppib_host_rmppi_line_search_weights.restype = None
+    L.mppib_host_rmppi_candidates.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp]
+    L.mppib_host_rmppi_candidates.restype = None
+    L.mppib_host_rmppi_best_index.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp]
     L.mppib_host_free_energy.argtypes = [C.POINTER(SolveStats), C.c_int, C.c_float, vp]
     L.mppib_host_free_energy.restype = None
     L.mppib_host_merge_records.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]
@@ -700,6 +709,20 @@ class Engine:
     def set_option(self, option: int, value: int) -> None:
         _check(lib().mppib_set_option(self._h, option, value))
 
+    def set_rmppi(self, value_func_threshold: float, feedback_gains=None) -> None:
+        """feedback_gains: [T][S][C] (C x S column-major per step) or None."""
+        g = None if feedback_gains is None else _f32(feedback_gains)
+        _check(lib().mppib_set_rmppi(self._h, C.c_float(value_func_threshold), _ptr(g)))
+
+    def init_eval(self, candidates, strides, samples_per_candidate: int, U_nominal, optimization_stride: int = 1):
+        cand = _f32(candidates)
+        st = np.ascontiguousarray(strides, dtype=np.int32)
+        K = cand.shape[0]
+        costs = np.empty(K * samples_per_candidate, np.float32)
+        _check(lib().mppib_init_eval(self._h, _ptr(cand), st.ctypes.data_as(C.c_void_p), K, samples_per_candidate,
+                                     _ptr(_f32(U_nominal)), optimization_stride, _ptr(costs)))
+        return costs
+
     def set_noise(self, eps) -> None:
         eps = _f32(eps)
         _check(lib().mppib_set_noise(self._h, _ptr(eps), eps.size))
@@ -981,3 +1004,141 @@ class TubeMPPIController(_Controller):
         self._save_control_history(steps, self.nominal_control_trajectory_)
         self._slide(self.nominal_control_trajectory_, steps)
         self._slide(self.control_, steps)
+
+
+class RobustMPPIController(_Controller):
+    """controllers/R-MPPI/robust_mppi_controller.cuh — RobustMPPIController(model, cost, fb_controller, sampler, dt, max_iter,
+    lambda, alpha, value_function_threshold, num_timesteps, init_control_traj, num_candidate_nominal_states,
+    optimization_stride). Distribution 0 = nominal system, 1 = real system (robust_mppi_controller.cu:637-640). The DDP
+    feedback controller is out of scope: its product, the gain trajectory, is an input (``setFeedbackGains``; zero = no
+    feedback)."""
+    NUM_DISTRIBUTIONS = 2
+
+    def __init__(self, model, cost, fb_controller, sampler, dt: float, max_iter: int, lambda_: float, alpha: float,
+                 value_function_threshold: float, num_timesteps: int, num_rollouts: int, init_control_traj=None,
+                 num_candidate_nominal_states: int = 9, optimization_stride: int = 1,
+                 eval_samples_per_candidate: int = 64, **kw):
+        kw["flags"] = kw.get("flags", 0) | FLAG_RMPPI
+        super().__init__(model, cost, fb_controller, sampler, dt, max_iter, lambda_, alpha, num_timesteps, num_rollouts,
+                         init_control_traj, **kw)
+        self.value_function_threshold_ = value_function_threshold
+        self.optimization_stride_ = optimization_stride
+        self.eval_samples_per_candidate_ = eval_samples_per_candidate
+        self.nominal_control_trajectory_ = self.control_.copy()
+        self.nominal_control_history_ = np.zeros_like(self.control_history_)
+        self.nominal_state_trajectory_ = np.zeros_like(self.state_)
+        self.nominal_state_ = np.zeros(model.STATE_DIM, np.float32)
+        self.nominal_state_init_ = False
+        self.nominal_stride_, self.real_stride_, self.best_index_ = 0, 0, 0
+        self.feedback_gains_ = None  # [T][S][C]
+        self.candidate_free_energy_ = None
+        self.updateNumCandidates(num_candidate_nominal_states)
+        self.engine.set_rmppi(value_function_threshold, None)
+
+    # robust_mppi_controller.cu:430-467
+    def updateNumCandidates(self, n: int) -> None:
+        if n * self.eval_samples_per_candidate_ > self.num_rollouts_:
+            raise ValueError("(number of candidates) * (SAMPLES_PER_CANDIDATE) cannot exceed NUM_ROLLOUTS")
+        if n < 3:
+            raise ValueError("number of candidates must be greater or equal to 3")
+        if n % 2 == 0:
+            raise ValueError("number of candidates must be odd")
+        self.num_candidate_nominal_states_ = n
+        self.line_search_weights_ = np.zeros((3, n), np.float32)
+        lib().mppib_host_rmppi_line_search_weights(n, _ptr(self.line_search_weights_))
+
+    def getNumCandidates(self) -> int:
+        return self.num_candidate_nominal_states_
+
+    def setValueFunctionThreshold(self, v: float) -> None:
+        self.value_function_threshold_ = v
+        self.engine.set_rmppi(v, self.feedback_gains_)
+
+    def getValueFunctionThreshold(self) -> float:
+        return self.value_function_threshold_
+
+    def setFeedbackGains(self, gains_cxs_per_step) -> None:
+        """gains [T][C][S] (K_t as a C x S matrix) -> device layout [T][S][C] (Eigen column-major, ddp.cu:16)."""
+        g = _f32(gains_cxs_per_step)
+        T, Cd, S = self.num_timesteps_, self.model_.CONTROL_DIM, self.model_.STATE_DIM
+        assert g.shape == (T, Cd, S)
+        self.feedback_gains_ = np.ascontiguousarray(g.transpose(0, 2, 1))
+        self.engine.set_rmppi(self.value_function_threshold_, self.feedback_gains_)
+
+    def getNominalControlSeq(self) -> np.ndarray:
+        return self.nominal_control_trajectory_
+
+    def getNominalStateSeq(self) -> np.ndarray:
+        return self.nominal_state_trajectory_
+
+    # robust_mppi_controller.cu:571-617
+    def computeNominalStateAndStride(self, state, stride: int) -> None:
+        state = _f32(state)
+        if not self.nominal_state_init_:
+            self.nominal_state_ = state.copy()
+            self.nominal_state_init_ = True
+            self.nominal_stride_ = 0
+            return
+        K, S = self.num_candidate_nominal_states_, self.model_.STATE_DIM
+        cand = np.zeros((K, S), np.float32)
+        strides = np.zeros(K, np.int32)
+        lib().mppib_host_rmppi_candidates(K, S, _ptr(_f32(self.nominal_state_trajectory_[0])),
+                                          _ptr(_f32(self.nominal_state_trajectory_[1])), _ptr(state), stride, _ptr(cand),
+                                          strides.ctypes.data_as(C.c_void_p))
+        costs = self.engine.init_eval(cand, strides, self.eval_samples_per_candidate_,
+                                      self.nominal_control_trajectory_, stride)
+        fe = np.zeros(K, np.float32)
+        self.best_index_ = lib().mppib_host_rmppi_best_index(_ptr(costs), K, self.eval_samples_per_candidate_,
+                                                             C.c_float(self.lambda_),
+                                                             C.c_float(self.value_function_threshold_), self.best_index_,
+                                                             _ptr(fe))
+        self.candidate_free_energy_, self.candidate_nominal_states_, self.importance_sampler_strides_ = fe, cand, strides
+        self.nominal_stride_ = int(strides[self.best_index_])
+        self.nominal_state_ = cand[self.best_index_].copy()
+
+    # robust_mppi_controller.cu:539-563
+    def updateImportanceSamplingControl(self, state, stride: int) -> None:
+        self.real_stride_ = stride
+        self.computeNominalStateAndStride(state, stride)
+        self._save_history(self.nominal_stride_, self.nominal_control_trajectory_, self.nominal_control_history_)
+        self._save_history(self.real_stride_, self.control_, self.control_history_)
+        self._slide(self.nominal_control_trajectory_, self.nominal_stride_)
+        self._output_trajectory(self.nominal_state_, self.nominal_control_trajectory_, self.nominal_state_trajectory_,
+                                np.zeros_like(self.output_))
+
+    def _save_history(self, steps: int, u: np.ndarray, hist: np.ndarray) -> None:  # controller.cuh:602-616
+        if steps == 1:
+            hist[0] = hist[1]
+            hist[1] = u[0]
+        elif steps >= 2:
+            hist[0] = u[steps - 2]
+            hist[1] = u[steps - 1]
+
+    # robust_mppi_controller.cu:625-755
+    def computeControl(self, state, optimization_stride: int = 1) -> None:
+        state = _f32(state)
+        if not self.nominal_state_init_:
+            self.nominal_state_ = state.copy()
+            self.nominal_state_init_ = True
+        x0 = np.stack([self.nominal_state_, state]).astype(np.float32)
+        for it in range(self.num_iters_):
+            U_in = np.stack([self.nominal_control_trajectory_, self.nominal_control_trajectory_]).astype(np.float32)
+            U, stats = self.engine.solve(x0, U_in, optimization_stride, it)
+            self.nominal_control_trajectory_ = U[0].copy()
+            self.control_ = U[1].copy()
+            for d in range(2):
+                self.baseline_[d], self.normalizer_[d] = stats[d][0], stats[d][1]
+        self.free_energy_statistics_ = {"nominal_sys": self._free_energy(stats[0]), "real_sys": self._free_energy(stats[1]),
+                                        "nominal_state_used": self.best_index_}
+        self._smooth_with(self.control_, self.control_history_)
+        self._smooth_with(self.nominal_control_trajectory_, self.nominal_control_history_)
+        self._output_trajectory(self.nominal_state_, self.nominal_control_trajectory_, self.nominal_state_trajectory_,
+                                self.output_)
+        self.state_ = self.nominal_state_trajectory_
+
+    def _smooth_with(self, u: np.ndarray, hist: np.ndarray) -> None:
+        lib().mppib_host_smooth_controls(_ptr(u), _ptr(hist), self.num_timesteps_, self.model_.CONTROL_DIM)
+
+    def slideControlSequence(self, steps: int) -> None:
+        """robust_mppi_controller.cuh:186-190: a no-op — the nominal control slides by its own stride inside
+        updateImportanceSamplingControl, which the plant calls before each optimisation."""

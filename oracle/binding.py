@@ -230,3 +230,52 @@ def colored_tables(sp, C_, T):
     sigma = np.empty(C_, np.float32)
     lib().orc_colored_tables(C.byref(sp), C_, T, _p(coeffs), _p(sigma))
     return coeffs, sigma
+
+
+def rmppi_rollout(dyn_id, cost_id, dyn_params, cost_params, sp, nn_theta, costmap, N, T, dt, lam, alpha,
+                  value_func_threshold, x0, means, gains, samples, nominal_idx=0, nthreads=1):
+    """launchCPURMPPIRolloutKernel: samples [2][N][T][C] sampled controls (constrained in place, feedback added to the
+    real system's). gains [T][S][C] or None. Returns costs [2][N]."""
+    costs = np.empty((2, N), np.float32)
+    g = None if gains is None else _f32(gains)
+    rc = lib().orc_rmppi_rollout(dyn_id, cost_id, C.byref(dyn_params), C.byref(cost_params), C.byref(sp), _p(nn_theta),
+                                 _p(costmap), N, T, C.c_float(dt), C.c_float(lam), C.c_float(alpha),
+                                 C.c_float(value_func_threshold), nominal_idx, _p(_f32(x0)), _p(_f32(means)), _p(g),
+                                 _p(samples), _p(costs), nthreads)
+    if rc:
+        raise RuntimeError(f"orc_rmppi_rollout failed: {rc}")
+    return costs
+
+
+def init_eval(dyn_id, cost_id, dyn_params, cost_params, sp, nn_theta, costmap, N_sampler, T, dt, lam, alpha, candidates,
+              strides, samples_per_candidate, means, controls):
+    """launchCPUInitEvalKernel: controls [num_samples][T][C] = the sampler's buffer (distribution 0). costs [K * spc]."""
+    cand = _f32(candidates)
+    st = np.ascontiguousarray(strides, dtype=np.int32)
+    K = cand.shape[0]
+    costs = np.zeros(K * samples_per_candidate, np.float32)
+    rc = lib().orc_init_eval(dyn_id, cost_id, C.byref(dyn_params), C.byref(cost_params), C.byref(sp), _p(nn_theta),
+                             _p(costmap), N_sampler, T, C.c_float(dt), C.c_float(lam), C.c_float(alpha), K,
+                             samples_per_candidate, _p(cand), st.ctypes.data_as(C.c_void_p), _p(_f32(means)),
+                             _p(_f32(controls)), _p(costs))
+    if rc:
+        raise RuntimeError(f"orc_init_eval failed: {rc}")
+    return costs
+
+
+def rmppi_line_search_weights(K) -> np.ndarray:
+    out = np.zeros((3, K), np.float32)
+    lib().orc_rmppi_line_search_weights(K, _p(out))
+    return out
+
+
+def rmppi_strides(K, stride) -> np.ndarray:
+    out = np.zeros(K, np.int32)
+    lib().orc_rmppi_strides(K, stride, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def rmppi_best_index(costs, K, spc, lam, threshold):
+    fe = np.zeros(K, np.float32)
+    best = lib().orc_rmppi_best_index(_p(_f32(costs)), K, spc, C.c_float(lam), C.c_float(threshold), _p(fe))
+    return best, fe

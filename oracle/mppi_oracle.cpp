@@ -905,6 +905,149 @@ static void coloredNoise(const float* normals, const mppib_gaussian_params& sp, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// RMPPI. tests/include/kernel_tests/core/rmppi_kernel_test.cu:7-77 (launchCPURMPPIRolloutKernel) and :79-127
+// (launchCPUInitEvalKernel); computeFeedbackCost gaussian.cu:572-629; DDP feedback k(x, x*, t) = K_t (x - x*) with K_t
+// column-major C x S (feedback_controllers/DDP/ddp.cu:11-45 — the HOST form: the device code overwrites instead of
+// accumulating when CONTROL_DIM is even, which keeps only the last state's column; the intended product is restated).
+static inline float feedbackCost(const mppib_gaussian_params& sp, const float* u_fb, int C, int d, float lambda,
+                                 float alpha)
+{
+  float cost = 0.0f;
+  for (int i = 0; i < C; i++)
+  {
+    const float sd = sp.std_dev[d * C + i];
+    cost += sp.control_cost_coeff[i] * (u_fb[i] * u_fb[i]) / (sd * sd);
+  }
+  return 0.5f * lambda * (1.0f - alpha) * cost;
+}
+
+// samples [2][N][T][C]: sampled controls of both distributions (index nominal_idx / real_idx), constrained in place.
+template <class DYN, class COST>
+static void rmppiRollout(const void* dpv, const void* cpv, const mppib_gaussian_params& sp, const Aux& aux, int N, int T,
+                         float dt, float lambda, float alpha, float value_func_threshold, int nominal_idx,
+                         const float* x0 /*[2][S]*/, const float* means /*[2][T][C]*/,
+                         const float* gains /*[T][S][C] == column-major C x S per t, may be null*/, float* samples,
+                         float* costs /*[2][N]*/, int n_begin, int n_end)
+{
+  const auto& dp = *(const typename DYN::P*)dpv;
+  const auto& cp = *(const typename COST::P*)cpv;
+  constexpr int S = DYN::S, C = DYN::C, O = DYN::O;
+  const int real_idx = 1 - nominal_idx;
+  for (int n = n_begin; n < n_end; n++)
+  {
+    float xr[S], xn[S], xr_next[S], xn_next[S], dr[S], dn[S], yr[O], yn[O], ur[C], un[C], ufb[C];
+    for (int i = 0; i < S; i++)
+    {
+      xr[i] = x0[real_idx * S + i];
+      xn[i] = x0[nominal_idx * S + i];
+    }
+    for (int i = 0; i < O; i++)
+      yr[i] = yn[i] = 0.0f;
+    int crash_r = 0, crash_n = 0;
+    float running_real = 0, running_nom = 0, tracking_nom = 0, tracking_real = 0;
+    typename DYN::Carry kr, kn;
+    DYN::initCarry(aux, kr);
+    DYN::initCarry(aux, kn);
+    for (int t = 0; t < T; t++)
+    {
+      float* sr = &samples[(((size_t)real_idx * N + n) * T + t) * C];
+      float* sn = &samples[(((size_t)nominal_idx * N + n) * T + t) * C];
+      for (int i = 0; i < C; i++)
+      {
+        ur[i] = sr[i];
+        un[i] = sn[i];
+        ufb[i] = 0.0f;
+      }
+      if (gains)
+        for (int i = 0; i < S; i++)
+        {
+          const float e = xr[i] - xn[i];
+          for (int j = 0; j < C; j++)
+            ufb[j] += gains[((size_t)t * S + i) * C + j] * e;
+        }
+      for (int i = 0; i < C; i++)
+        ur[i] += ufb[i];
+      enforceConstraints<C>(dp.lim, ur);
+      enforceConstraints<C>(dp.lim, un);
+      for (int i = 0; i < C; i++)
+      {
+        sr[i] = ur[i];
+        sn[i] = un[i];
+      }
+      dyn_step<DYN>(dp, aux, xr, xr_next, dr, ur, yr, dt, &kr);
+      dyn_step<DYN>(dp, aux, xn, xn_next, dn, un, yn, dt, &kn);
+      const float real_cost = COST::computeStateCost(cp, aux, yr, t, &crash_r);
+      const float nom_cost = COST::computeStateCost(cp, aux, yn, t, &crash_n);
+      tracking_real += real_cost + feedbackCost(sp, ufb, C, real_idx, lambda, alpha);
+      running_real += real_cost + likelihoodRatioCost(sp, &means[((size_t)real_idx * T + t) * C], ur, C, real_idx, n, N,
+                                                      lambda, alpha);
+      running_nom += nom_cost;
+      tracking_nom += likelihoodRatioCost(sp, &means[((size_t)nominal_idx * T + t) * C], un, C, nominal_idx, n, N,
+                                          lambda, alpha);
+      for (int i = 0; i < S; i++)
+      {
+        xr[i] = xr_next[i];
+        xn[i] = xn_next[i];
+      }
+    }
+    running_real += COST::terminalCost(cp, aux, yr);
+    tracking_real += COST::terminalCost(cp, aux, yr);
+    running_nom += COST::terminalCost(cp, aux, yn);
+    tracking_nom /= T;
+    tracking_real /= T;
+    running_nom /= T;
+    running_real /= T;
+    running_nom = 0.5f * running_nom + 0.5f * fmaxf(fminf(tracking_real, value_func_threshold), running_nom);
+    running_nom += tracking_nom;
+    costs[(size_t)nominal_idx * N + n] = running_nom;
+    costs[(size_t)real_idx * N + n] = running_real;
+  }
+}
+
+// controls [num_samples][T][C]: the sampler's buffer after setGaussianControls (distribution 0); constrained copies are
+// not written back (the reference's CPU oracle does not either).
+template <class DYN, class COST>
+static void initEval(const void* dpv, const void* cpv, const mppib_gaussian_params& sp, const Aux& aux, int N_sampler,
+                     int T, float dt, float lambda, float alpha, int num_candidates, int num_samples,
+                     const float* candidates /*[K][S]*/, const int* strides, const float* means /*[T][C]*/,
+                     const float* controls, float* costs /*[K * num_samples]*/)
+{
+  const auto& dp = *(const typename DYN::P*)dpv;
+  const auto& cp = *(const typename COST::P*)cpv;
+  constexpr int S = DYN::S, C = DYN::C, O = DYN::O;
+  for (int k = 0; k < num_candidates; k++)
+    for (int j = 0; j < num_samples; j++)
+    {
+      const int global_idx = k * num_samples + j;
+      float x[S], xn[S], xd[S], y[O], u[C];
+      for (int i = 0; i < S; i++)
+        x[i] = candidates[k * S + i];
+      for (int i = 0; i < O; i++)
+        y[i] = 0.0f;
+      int crash = 0;
+      float running = 0.0f;
+      typename DYN::Carry carry;
+      DYN::initCarry(aux, carry);
+      for (int t = 0; t < T; t++)
+      {
+        const int ct = std::min(t + strides[k], T - 1);
+        for (int i = 0; i < C; i++)
+          u[i] = controls[((size_t)j * T + ct) * C + i];
+        enforceConstraints<C>(dp.lim, u);
+        dyn_step<DYN>(dp, aux, x, xn, xd, u, y, dt, &carry);
+        running += COST::computeStateCost(cp, aux, y, t, &crash);
+        // device call: computeLikelihoodRatioCost(u, theta_d, global_idx, t, 0, lambda, alpha) (rmppi_kernels.cu:331-333)
+        running += likelihoodRatioCost(sp, &means[(size_t)t * C], u, C, 0, global_idx, N_sampler, lambda, alpha);
+        for (int i = 0; i < S; i++)
+          x[i] = xn[i];
+      }
+      running += COST::terminalCost(cp, aux, y);
+      running /= T;
+      costs[global_idx] = running;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Weights. core/mppi_common.cu:858-900 (first minimum wins), :958-966 (expf), :1055-1063 (double sum),
 // :1065-1081 (free energy)
 static float computeBaselineCost(const float* c, int n)
@@ -1122,6 +1265,124 @@ void orc_colored_tables(const mppib_gaussian_params* sp, int C, int T, float* co
   std::vector<float> c;
   orc::coloredNoiseTables(*sp, C, T, c, sigma);
   memcpy(coeffs, c.data(), c.size() * sizeof(float));
+}
+
+// RMPPI rollout (both systems) on already-sampled controls [2][N][T][C]; costs [2][N]. Returns 0 / -1 (unknown pair).
+int orc_rmppi_rollout(int dyn_id, int cost_id, const void* dyn_params, const void* cost_params,
+                      const mppib_gaussian_params* sp, const float* nn_theta, const float* costmap, int N, int T,
+                      float dt, float lambda, float alpha, float value_func_threshold, int nominal_idx, const float* x0,
+                      const float* means, const float* gains, float* samples, float* costs, int nthreads)
+{
+  orc::Aux aux;
+  aux.nn_theta = nn_theta;
+  aux.costmap = costmap;
+  fill_lstm(aux);
+  typedef void (*fn_t)(const void*, const void*, const mppib_gaussian_params&, const orc::Aux&, int, int, float, float,
+                       float, float, int, const float*, const float*, const float*, float*, float*, int, int);
+  fn_t f = nullptr;
+  if (dyn_id == MPPIB_DYN_CARTPOLE && cost_id == MPPIB_COST_CARTPOLE_QUADRATIC)
+    f = &orc::rmppiRollout<orc::Cartpole, orc::CartpoleQuadraticCost>;
+  else if (dyn_id == MPPIB_DYN_DOUBLE_INTEGRATOR && cost_id == MPPIB_COST_DI_CIRCLE)
+    f = &orc::rmppiRollout<orc::DoubleIntegrator, orc::DICircleCost>;
+  else if (dyn_id == MPPIB_DYN_AUTORALLY_NN && cost_id == MPPIB_COST_AR_STANDARD)
+    f = &orc::rmppiRollout<orc::AutorallyNN, orc::ARStandardCost>;
+  if (!f)
+    return -1;
+  if (nthreads <= 1)
+  {
+    f(dyn_params, cost_params, *sp, aux, N, T, dt, lambda, alpha, value_func_threshold, nominal_idx, x0, means, gains,
+      samples, costs, 0, N);
+    return 0;
+  }
+  std::vector<std::thread> th;
+  for (int i = 0; i < nthreads; i++)
+  {
+    int b = (int)((long long)N * i / nthreads), e = (int)((long long)N * (i + 1) / nthreads);
+    th.emplace_back([=, &aux]() {
+      f(dyn_params, cost_params, *sp, aux, N, T, dt, lambda, alpha, value_func_threshold, nominal_idx, x0, means, gains,
+        samples, costs, b, e);
+    });
+  }
+  for (auto& t : th)
+    t.join();
+  return 0;
+}
+
+int orc_init_eval(int dyn_id, int cost_id, const void* dyn_params, const void* cost_params,
+                  const mppib_gaussian_params* sp, const float* nn_theta, const float* costmap, int N_sampler, int T,
+                  float dt, float lambda, float alpha, int num_candidates, int num_samples, const float* candidates,
+                  const int* strides, const float* means, const float* controls, float* costs)
+{
+  orc::Aux aux;
+  aux.nn_theta = nn_theta;
+  aux.costmap = costmap;
+  fill_lstm(aux);
+  if (dyn_id == MPPIB_DYN_CARTPOLE && cost_id == MPPIB_COST_CARTPOLE_QUADRATIC)
+    orc::initEval<orc::Cartpole, orc::CartpoleQuadraticCost>(dyn_params, cost_params, *sp, aux, N_sampler, T, dt, lambda,
+                                                             alpha, num_candidates, num_samples, candidates, strides,
+                                                             means, controls, costs);
+  else if (dyn_id == MPPIB_DYN_DOUBLE_INTEGRATOR && cost_id == MPPIB_COST_DI_CIRCLE)
+    orc::initEval<orc::DoubleIntegrator, orc::DICircleCost>(dyn_params, cost_params, *sp, aux, N_sampler, T, dt, lambda,
+                                                            alpha, num_candidates, num_samples, candidates, strides,
+                                                            means, controls, costs);
+  else if (dyn_id == MPPIB_DYN_AUTORALLY_NN && cost_id == MPPIB_COST_AR_STANDARD)
+    orc::initEval<orc::AutorallyNN, orc::ARStandardCost>(dyn_params, cost_params, *sp, aux, N_sampler, T, dt, lambda, alpha,
+                                                         num_candidates, num_samples, candidates, strides, means,
+                                                         controls, costs);
+  else
+    return -1;
+  return 0;
+}
+
+// RobustMPPI host helpers: computeLineSearchWeights (robust_mppi_controller.cu:472-491, out [3][K] row-major),
+// computeImportanceSamplerStride (:493-503), computeBestIndex (:519-537; returns -1 if no candidate passes, i.e. the
+// reference leaves best_index_ unchanged)
+void orc_rmppi_line_search_weights(int num_candidates, float* out)
+{
+  const int h = num_candidates / 2, K = num_candidates;
+  for (int i = 0; i < 3 * K; i++)
+    out[i] = 0.0f;
+  for (int i = 0; i < h + 1; i++)
+  {
+    out[0 * K + i] = 1 - i / float(h);
+    out[1 * K + i] = i / float(h);
+    out[2 * K + i] = 0.0;
+  }
+  for (int i = 1; i < h + 1; i++)
+  {
+    out[0 * K + h + i] = 0.0;
+    out[1 * K + h + i] = 1 - i / float(h);
+    out[2 * K + h + i] = i / float(h);
+  }
+}
+void orc_rmppi_strides(int num_candidates, int stride, int* out)
+{
+  std::vector<float> w(3 * num_candidates);
+  orc_rmppi_line_search_weights(num_candidates, w.data());
+  for (int i = 0; i < num_candidates; i++)
+    out[i] = (int)roundf(0.0f * w[i] + stride * w[num_candidates + i] + stride * w[2 * num_candidates + i]);
+}
+int orc_rmppi_best_index(const float* costs, int num_candidates, int samples_per_candidate, float lambda,
+                         float value_func_threshold, float* free_energy)
+{
+  const int n = num_candidates * samples_per_candidate;
+  float baseline = costs[0];
+  for (int i = 1; i < n; i++)
+    if (costs[i] < baseline)
+      baseline = costs[i];
+  int best = -1;
+  for (int i = 0; i < num_candidates; i++)
+  {
+    float fe = 0.0f;
+    for (int j = 0; j < samples_per_candidate; j++)
+      fe += expf(-1.0 / lambda * (costs[i * samples_per_candidate + j] - baseline));
+    fe /= (1.0 * samples_per_candidate);
+    fe = -lambda * logf(fe) + baseline;
+    free_energy[i] = fe;
+    if (fe < value_func_threshold)
+      best = i;
+  }
+  return best;
 }
 
 int orc_dims(int dyn_id, int* S, int* C, int* O)

@@ -664,3 +664,105 @@ def test_racer_lstm_controller_runs_and_tracks_speed():
     assert abs(x[0] - w.cost.params.desired_speed) < 0.3
     assert ctrl.getTargetStateSeq().shape == (w.T, 19) and np.all(np.isfinite(ctrl.getTargetStateSeq()))
     assert ctrl.getTargetOutputSeq().shape == (w.T, 28)
+
+
+# ---- RMPPI: rollout semantics, init-eval kernel, controller -------------------------------------------
+def _rmppi_setup(N=2048, T=60, with_gains=True, seed=11):
+    w = W.double_integrator_tube(N, T)
+    w.dyn.setControlRanges([(-2.0, 2.0), (-2.0, 2.0)])
+    w.sampler.setControlCostCoeff([0.5, 0.25])
+    e = H.Engine(w.dyn, w.cost, w.sampler, N, T, 2, flags=H.FLAG_RMPPI)
+    e.set_solver(w.dt, w.lambda_, 0.1)
+    e.seed(seed, 0)
+    rng = np.random.RandomState(1)
+    gains = None
+    if with_gains:
+        gains = (rng.randn(T, 4, 2) * 0.3).astype(np.float32)  # [t][s][c]
+    return w, e, gains
+
+
+@pytest.mark.parametrize("with_gains", [False, True])
+def test_rmppi_rollout_matches_oracle(with_gains):
+    """rolloutRMPPIKernel (core/rmppi_kernels.cu:665-866) against the restatement of the reference's CPU oracle
+    launchCPURMPPIRolloutKernel (tests/include/kernel_tests/core/rmppi_kernel_test.cu:7-77): same 1e-4 relative bound as
+    the reference's own comparison (tests/mppi_core/rmppi_kernel_tests.cu)."""
+    w, e, gains = _rmppi_setup(with_gains=with_gains)
+    thr = 6.0
+    e.set_rmppi(thr, gains)
+    N, T, Cd = w.N, w.T, 2
+    x0 = np.array([[2.0, 0.0, 0.0, 1.0], [2.08, -0.05, 0.05, 0.9]], np.float32)  # [nominal, real]
+    U_nom = np.zeros((T, Cd), np.float32)
+    U_nom[:, 0] = 0.2 * np.sin(np.arange(T) * 0.1)
+    U_in = np.stack([U_nom, U_nom])
+    U, stats = e.solve(x0, U_in, 1, 0)
+    eps = e.get_noise()
+    samples = np.stack([eps, eps]).copy()
+    oracle.set_gaussian_controls(U_in, w.sampler.params, samples, Cd, T, N, 2, 1, 0)
+    ref = oracle.rmppi_rollout(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, None, None,
+                               N, T, w.dt, w.lambda_, 0.1, thr, x0, U_in, gains, samples, nthreads=8)
+    costs = e.get_costs()
+    np.testing.assert_allclose(costs, ref, rtol=1e-4, atol=1e-5)
+    # the applied controls (feedback included, constrained) are what the weighted average uses
+    applied = e.get_samples()
+    np.testing.assert_allclose(applied, samples, rtol=1e-5, atol=2e-6)
+    lam_inv = np.float32(1.0 / w.lambda_)
+    for d in range(2):
+        c = costs[d].astype(np.float64)
+        wts = np.exp(-float(lam_inv) * (c - c.min()))
+        Uref = np.einsum("n,ntc->tc", wts / wts.sum(), applied[d].astype(np.float64))
+        np.testing.assert_allclose(U[d], Uref, atol=1e-5, rtol=1e-5)
+        assert stats[d][0] == np.float32(c.min())
+    if with_gains:
+        assert np.abs(applied[1] - applied[0]).max() > 1e-3  # the feedback term really acted on the real system
+    e.close()
+
+
+def test_rmppi_init_eval_matches_oracle():
+    """initEvalKernel (core/rmppi_kernels.cu:230-356) against launchCPUInitEvalKernel (rmppi_kernel_test.cu:79-127)."""
+    w, e, _ = _rmppi_setup(N=1024, T=50)
+    K, spc, stride = 9, 64, 3
+    rng = np.random.RandomState(2)
+    xk, xk1, xr = (np.array([2.0, 0.0, 0.0, 1.0], np.float32) + 0.05 * rng.randn(3, 4)).astype(np.float32)
+    cand = np.zeros((K, 4), np.float32)
+    strides = np.zeros(K, np.int32)
+    H.lib().mppib_host_rmppi_candidates(K, 4, xk.ctypes.data, xk1.ctypes.data, xr.ctypes.data, stride, cand.ctypes.data,
+                                        strides.ctypes.data)
+    U_nom = np.zeros((w.T, 2), np.float32)
+    U_nom[:, 1] = 0.1
+    before = e.rng_offset()
+    costs = e.init_eval(cand, strides, spc, U_nom, stride)
+    assert e.rng_offset() - before == w.N * w.T * 2  # one generateSamples draw (robust_mppi_controller.cu:595)
+    eps = e.get_noise()
+    samples = eps[None].copy()
+    oracle.set_gaussian_controls(U_nom[None], w.sampler.params, samples, 2, w.T, w.N, 1, stride, 0)
+    ref = oracle.init_eval(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, None, None, w.N,
+                           w.T, w.dt, w.lambda_, 0.1, cand, strides, spc, U_nom, samples[0, :spc])
+    np.testing.assert_allclose(costs, ref, rtol=1e-4, atol=1e-5)
+    e.close()
+
+
+def test_rmppi_controller_tracks_the_circle_under_disturbance():
+    """RobustMPPIController through the mirrored API on the CORL-2020 double integrator: with a stabilising feedback gain
+    the real system stays on the track while the nominal state is re-selected by the init-eval line search."""
+    w = W.double_integrator_tube(2048, 50)
+    ctrl = H.RobustMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, 20.0, w.T, w.N, seed=3,
+                                  num_candidate_nominal_states=9, eval_samples_per_candidate=64)
+    K = np.zeros((w.T, 2, 4), np.float32)  # u_fb = K (x - x*): PD on position / velocity error
+    K[:, 0, 0] = K[:, 1, 1] = -4.0
+    K[:, 0, 2] = K[:, 1, 3] = -2.0
+    ctrl.setFeedbackGains(K)
+    x = np.array([2.0, 0.0, 0.0, 1.0], np.float32)
+    rng = np.random.RandomState(0)
+    radii = []
+    for it in range(120):
+        ctrl.updateImportanceSamplingControl(x, 1)
+        ctrl.computeControl(x, 1)
+        xn = ctrl.getNominalStateSeq()[0]
+        u = ctrl.getNominalControlSeq()[0] + K[0] @ (x - xn)
+        xnext, _, _ = w.dyn.step(x, u, w.dt)
+        xnext[2:] += 0.2 * np.sqrt(w.dt) * rng.randn(2).astype(np.float32)
+        x = xnext
+        radii.append(float(np.hypot(x[0], x[1])))
+    assert 1.6 < min(radii[20:]) and max(radii[20:]) < 2.4
+    assert 0 <= ctrl.best_index_ < 9 and ctrl.candidate_free_energy_ is not None
+    assert np.isfinite(ctrl.getBaselineCost(0)) and np.isfinite(ctrl.getBaselineCost(1))

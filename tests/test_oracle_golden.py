@@ -378,3 +378,81 @@ def test_colored_noise_matches_the_numpy_algorithm():
         # unit variance before the offset is subtracted (Timmer & Koenig normalisation); pooled over N*T samples
     tab, sigma = oracle.colored_tables(s.params, Cd, T)
     assert tab.shape == (Cd, T + 1) and np.all(sigma > 0)
+
+
+# ---- RMPPI host logic ----------------------------------------------------------------------------------
+def test_rmppi_line_search_weights_strides_and_best_index():
+    """controllers/R-MPPI/robust_mppi_controller.cu:472-537 — hand-evaluated values + product host twin == oracle."""
+    K = 9
+    w = oracle.rmppi_line_search_weights(K)
+    # first half interpolates nominal_x_k -> nominal_x_kp1, second half nominal_x_kp1 -> real_x_kp1 (:476-490)
+    np.testing.assert_allclose(w[0], [1, .75, .5, .25, 0, 0, 0, 0, 0])
+    np.testing.assert_allclose(w[1], [0, .25, .5, .75, 1, .75, .5, .25, 0])
+    np.testing.assert_allclose(w[2], [0, 0, 0, 0, 0, .25, .5, .75, 1])
+    np.testing.assert_allclose(w.sum(axis=0), 1.0)
+    w2 = np.zeros((3, K), np.float32)
+    H.lib().mppib_host_rmppi_line_search_weights(K, w2.ctypes.data)
+    np.testing.assert_array_equal(w, w2)
+    # strides = round([0, s, s] . w) (:493-503)
+    np.testing.assert_array_equal(oracle.rmppi_strides(K, 1), [0, 0, 1, 1, 1, 1, 1, 1, 1])  # .25 -> 0, .5 -> 1 (Eigen round: half away from zero)
+    np.testing.assert_array_equal(oracle.rmppi_strides(K, 4), [0, 1, 2, 3, 4, 4, 4, 4, 4])
+    rng = np.random.RandomState(3)
+    xk, xk1, xr = rng.randn(3, 4).astype(np.float32)
+    cand = np.zeros((K, 4), np.float32)
+    st = np.zeros(K, np.int32)
+    H.lib().mppib_host_rmppi_candidates(K, 4, xk.ctypes.data, xk1.ctypes.data, xr.ctypes.data, 4, cand.ctypes.data,
+                                        st.ctypes.data)
+    np.testing.assert_array_equal(st, oracle.rmppi_strides(K, 4))
+    np.testing.assert_allclose(cand, (np.stack([xk, xk1, xr], 1) @ w).T, rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(cand[0], xk)
+    np.testing.assert_array_equal(cand[K // 2], xk1)
+    np.testing.assert_array_equal(cand[-1], xr)
+    # best index: the LAST candidate whose free energy is under the threshold; none => previous value kept
+    spc = 16
+    costs = (10.0 + rng.rand(K * spc)).astype(np.float32)
+    costs[2 * spc:3 * spc] -= 5.0
+    costs[6 * spc:7 * spc] -= 4.0
+    best, fe = oracle.rmppi_best_index(costs, K, spc, 1.0, 8.0)
+    assert best == 6 and fe[2] < 8.0 and fe[6] < 8.0 and fe[0] > 8.0
+    fe2 = np.zeros(K, np.float32)
+    assert H.lib().mppib_host_rmppi_best_index(costs.ctypes.data, K, spc, C.c_float(1.0), C.c_float(8.0), 3,
+                                               fe2.ctypes.data) == 6
+    np.testing.assert_allclose(fe2, fe, rtol=1e-6)
+    assert H.lib().mppib_host_rmppi_best_index(costs.ctypes.data, K, spc, C.c_float(1.0), C.c_float(1.0), 3,
+                                               fe2.ctypes.data) == 3
+    assert oracle.rmppi_best_index(costs, K, spc, 1.0, 1.0)[0] == -1
+    # free energy formula: -lambda log(mean exp(-(c - b)/lambda)) + b
+    b = costs.min()
+    ref = -1.0 * np.log(np.mean(np.exp(-(costs[:spc].astype(np.float64) - b)))) + b
+    assert fe[0] == pytest.approx(ref, rel=1e-5)
+
+
+def test_rmppi_oracle_reduces_to_plain_rollout_without_feedback():
+    """With zero gains, an infinite value-function threshold floor... the real system's RMPPI cost is the plain rollout
+    cost (running + LR + terminal)/T, and the nominal cost is 0.5 c + 0.5 max(min(tracking_real, thr), c) + LR."""
+    w = W.double_integrator_tube(256, 40)
+    sp = w.sampler.params
+    sp.control_cost_coeff[0] = sp.control_cost_coeff[1] = 0.5
+    N, T, Cd = w.N, w.T, 2
+    eps = oracle.curand_normal(5, 0, N * T * Cd).reshape(N, T, Cd)
+    U = np.zeros((2, T, Cd), np.float32)
+    U[:, :, 0] = 0.3
+    x0 = np.array([[2.0, 0.0, 0.0, 1.0], [2.05, 0.02, 0.0, 1.0]], np.float32)  # [nominal, real]
+    samples = np.stack([eps, eps]).copy()
+    oracle.set_gaussian_controls(U, sp, samples, Cd, T, N, 2, 1, 0)
+    plain = samples.copy()
+    c_plain = oracle.rollout(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, sp, None, None, N, T, 2, w.dt,
+                             w.lambda_, w.alpha, x0, U, plain)
+    thr = 10.0
+    c = oracle.rmppi_rollout(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, sp, None, None, N, T, w.dt,
+                             w.lambda_, w.alpha, thr, x0, U, None, samples)
+    np.testing.assert_allclose(c[1], c_plain[1], rtol=2e-6)
+    # nominal: plain cost = (state + LR)/T; split it with a run without LR
+    sp0 = type(sp).from_buffer_copy(bytes(sp))
+    sp0.control_cost_coeff[0] = sp0.control_cost_coeff[1] = 0.0
+    c_state = oracle.rollout(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, sp0, None, None, N, T, 2, w.dt,
+                             w.lambda_, w.alpha, x0, U, plain.copy())
+    lr_nom = c_plain[0] - c_state[0]
+    tracking_real = c_state[1]  # zero gains: tracking cost = state cost + 0 feedback cost
+    expect = 0.5 * c_state[0] + 0.5 * np.maximum(np.minimum(tracking_real, thr), c_state[0]) + lr_nom
+    np.testing.assert_allclose(c[0], expect, rtol=2e-5, atol=1e-5)
