@@ -61,7 +61,8 @@ struct ControllerParams
 };
 
 template <class DYN_T, class COST_T, class FB_T, class SAMPLING_T, int MAX_TIMESTEPS, int NUM_ROLLOUTS,
-          class PARAMS_T = ControllerParams<DYN_T::STATE_DIM, DYN_T::CONTROL_DIM, MAX_TIMESTEPS>, int NUM_DISTRIBUTIONS = 1>
+          class PARAMS_T = ControllerParams<DYN_T::STATE_DIM, DYN_T::CONTROL_DIM, MAX_TIMESTEPS>, int NUM_DISTRIBUTIONS = 1,
+          unsigned ENGINE_FLAGS = 0u>
 class Controller
 {
 public:
@@ -330,7 +331,7 @@ protected:
     d.num_timesteps = params_.num_timesteps_;
     d.num_distributions = NUM_DISTRIBUTIONS;
     d.device = 0;  // mppi_controller.cu:48
-    d.flags = 0;
+    d.flags = ENGINE_FLAGS;  // e.g. MPPIB_FLAG_RMPPI for RobustMPPIController
     d.stream = (void*)stream_;
     d.rank = 0;
     d.world_size = 1;

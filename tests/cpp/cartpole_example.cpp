@@ -3,6 +3,7 @@
 // Exit codes: 0 = swing-up cost below threshold, 5 = no CUDA device (expected on the CPU-only box), other = failure.
 #include <mppi_b200/controllers/MPPI/mppi_controller.hpp>
 #include <mppi_b200/controllers/Tube-MPPI/tube_mppi_controller.hpp>
+#include <mppi/controllers/R-MPPI/robust_mppi_controller.cuh>
 #include <mppi_b200/cost_functions/cartpole/cartpole_quadratic_cost.hpp>
 #include <mppi_b200/cost_functions/double_integrator/double_integrator_circle_cost.hpp>
 #include <mppi_b200/dynamics/cartpole/cartpole_dynamics.hpp>
@@ -134,6 +135,43 @@ int main(int argc, char** argv)
     printf("tube: radius after 50 steps %f, baselines %f / %f\n", r, tube.getBaselineCost(0), tube.getBaselineCost(1));
     if (!(r > 1.675f && r < 2.325f))
       rc = 3;
+  }
+  // Robust MPPI on the same system: init-eval line search + feedback in the rollout, through the reference's include path
+  {
+    using DI = DoubleIntegratorDynamics;
+    DI di_model(1.0f);
+    DoubleIntegratorCircleCost di_cost;
+    using DS = mppi::sampling_distributions::GaussianDistribution<DI::DYN_PARAMS_T>;
+    DS di_sampler;
+    using RMPPI = RobustMPPIController<DI, DoubleIntegratorCircleCost, NoFeedback, 50, 2048>;
+    RMPPI rmppi(&di_model, &di_cost, nullptr, &di_sampler, 0.02f, 1, 2.0f, 0.0f, 20.0f);
+    RMPPI::feedback_gain_matrix K = RMPPI::feedback_gain_matrix::Zero();
+    K(0, 0) = K(1, 1) = -4.0f;
+    K(0, 2) = K(1, 3) = -2.0f;
+    rmppi.setFeedbackGains(std::vector<RMPPI::feedback_gain_matrix>(50, K));
+    DI::state_array x;
+    x << 2, 0, 0, 1;
+    for (int t = 0; t < 80; t++)
+    {
+      rmppi.updateImportanceSamplingControl(x, 1);
+      rmppi.computeControl(x, 1);
+      DI::state_array xnom = rmppi.getNominalStateSeq().col(0), e = x;
+      for (int i = 0; i < 4; i++)
+        e(i) = x(i) - xnom(i);
+      DI::control_array u = rmppi.getNominalControlSeq().col(0);
+      for (int c = 0; c < 2; c++)
+        for (int i = 0; i < 4; i++)
+          u(c) += K(c, i) * e(i);
+      DI::state_array xn, xd;
+      DI::output_array y;
+      di_model.step(x, xn, xd, u, y, t, 0.02f);
+      x = xn;
+    }
+    const float r = sqrtf(x(0) * x(0) + x(1) * x(1));
+    printf("rmppi: radius after 80 steps %f, baselines nominal %f / real %f, candidate used %d\n", r,
+           rmppi.getBaselineCost(0), rmppi.getBaselineCost(1), rmppi.getBestIndex());
+    if (!(r > 1.675f && r < 2.325f))
+      rc = 4;
   }
   delete CartpoleController;
   return rc;
