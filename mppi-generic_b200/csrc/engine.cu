@@ -933,10 +933,11 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
                                     e->cost_shared_floats(e->T))
         .total;
   };
-  // samples per thread: 2 for models that re-read block-shared weights every step (DYN::MAX_SPT) once there are enough
-  // rollouts to keep a warp on every scheduler with half the threads (148 SMs x 4 schedulers x 32 lanes x 2 samples =
-  // 37888; measured cross-over in profiles/r01_autorally_k1_notes.md); MPPIB_SPT overrides
-  int spt = (entry->max_spt >= 2 && e->D == 1 && e->n_local >= 24576) ? 2 : 1;
+  // samples per thread (rollout_kernel.cuh): 1. SPT = 2 halves the shared-memory wavefronts per sample of the NN model
+  // (38 M instead of 74 M, ncu) but a lone warp per scheduler cannot overlap its own FFMA2 / MUFU / latency phases the
+  // way two warps do: measured 636 us against 352 us at N = 32768 and 1854 us against 685 us at N = 65536 on B200
+  // (profiles/r01_autorally_k1_notes.md). Kept selectable for experiments through MPPIB_SPT.
+  int spt = 1;
   if (const char* s = getenv("MPPIB_SPT"))
   {
     const int v = atoi(s);

@@ -203,8 +203,9 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
   // warps instead of 1024 at N = 32768) — parity-green but 486 us against 353 us: the weight rows are then no longer warp-
   // uniform addresses, every LDS.128 costs twice the shared-memory wavefronts per sample, and that data pipe is already
   // the busiest unit (74 M wavefronts in 353 us = 72 % of one per cycle per SM, profiles/r01_autorally_v4_kernels.csv).
-  // What follows from the same measurement is the opposite move: TWO SAMPLES PER THREAD (stepBatch below), so that
-  // every weight row loaded from shared memory feeds twice the FFMA2s.
+  // The opposite move — TWO SAMPLES PER THREAD (stepBatch below), every weight row feeding twice the FFMA2s — halves the
+  // wavefronts (38 M) and is slower as well (636 us): one warp per scheduler cannot overlap its own phases. It stays
+  // selectable (MPPIB_SPT=2) and serves Tube-MPPI's two systems, which share the weight rows through the same code.
   static constexpr int MAX_SPT = 2;
   static constexpr int MAX_BLOCK_THREADS = 256;   // 99 registers/thread: up to 7 warps of samples share one SM's tile
   static constexpr bool UNROLL_STEPS = false;     // one copy of the 1344-FMA step body
