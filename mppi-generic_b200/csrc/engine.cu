@@ -121,6 +121,8 @@ struct mppib_engine
   int pstride = 0, nchunks = 0;
   int bx = 64, grid = 0;  // bx = samples (noise-tile rows) per CTA
   int spt = 1;  // samples per thread (rollout_kernel.cuh); threads per CTA = bx / spt
+  bool stream_k1 = false;  // streaming K1: noise slabs through a ring, controls kept in HBM (rollout_kernel.cuh: STREAM)
+  int ring = 2;
   uint32_t smem_bytes = 0;
   bool use_tma = false;
   bool use_pdl = true;
@@ -197,6 +199,7 @@ struct mppib_engine
   float* time_d = nullptr;       // [n_local*C][2T] cuFFT output, kept until the next draw
   float* coeffs_d = nullptr;     // [C][F]
   float* sigma_d = nullptr;      // [C]
+  float* decay_pow_d = nullptr;  // [T] powf(offset_decay_rate, t)
   cufftHandle fft_plan = 0;
   bool have_plan = false;
   int colored_offset_t = 1;      // optimization_stride assumed by draws issued before a solve names its own
@@ -299,6 +302,32 @@ struct Pair
                                   (int)e.smem_bytes));
     return MPPIB_OK;
   }
+  // resident CTAs per SM of the streaming variant (registers, threads and shared memory all count)
+  static int stream_blocks_per_sm(int D, int threads, size_t smem)
+  {
+    int n = 0;
+    cudaError_t rc = cudaErrorInvalidValue;
+    if (D == 1)
+    {
+      cudaFuncSetAttribute(rollout_kernel<DYN, COST, 1, true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+      rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rollout_kernel<DYN, COST, 1, true, 1, false, true>, threads,
+                                                         smem);
+    }
+    else if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
+    {
+      cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2, true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+      rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rollout_kernel<DYN, COST, 2, true, 1, false, true>, threads,
+                                                         smem);
+    }
+    if (rc != cudaSuccess)
+    {
+      cudaGetLastError();
+      return 0;
+    }
+    return n;
+  }
   static constexpr bool kHasTensorCoreVariant = std::is_same<DYN, plugins::AutorallyNNDynamics>::value &&
                                                 std::is_same<COST, plugins::ARStandardCost>::value;
   static int prepare(mppib_engine& e)
@@ -315,6 +344,22 @@ struct Pair
                                         (int)e.smem_bytes));
         return MPPIB_OK;
       }
+    }
+    if (e.stream_k1)
+    {
+      if (e.D == 1)
+      {
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 1, true, 1, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
+        return MPPIB_OK;
+      }
+      if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
+      {
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2, true, 1, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
+        return MPPIB_OK;
+      }
+      return fail(MPPIB_ERR_UNSUPPORTED, "this dynamics model is built for num_distributions == 1 only");
     }
     if (e.rmppi)
     {
@@ -371,6 +416,7 @@ struct Pair
     a.opt_stride = opt_stride;
     a.use_tma = e.use_tma ? 1 : 0;
     a.dyn_shared_floats = e.dyn_shared_floats;
+    a.ring = e.stream_k1 ? e.ring : 0;
     a.fb_gains = e.fb_gains_d;
     a.value_func_threshold = e.value_func_threshold;
     a.dt = e.dt;
@@ -394,6 +440,13 @@ struct Pair
     const int threads = e.bx / e.spt;
     if (launched)
     {
+    }
+    else if (e.stream_k1)
+    {
+      if (e.D == 1)
+        rollout_kernel<DYN, COST, 1, true, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+      else if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
+        rollout_kernel<DYN, COST, 2, true, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
     }
     else if (e.rmppi)
     {
@@ -485,6 +538,7 @@ struct PairEntry
   int (*launch)(mppib_engine&, const float*, const float*, int, int);
   int (*prepare)(mppib_engine&);
   int (*init_eval)(mppib_engine&, const float*, const int*, int, int, const float*, int);
+  int (*stream_blocks_per_sm)(int, int, size_t);
 };
 template <class DYN, class COST>
 constexpr PairEntry make_entry(int dyn_id, int cost_id)
@@ -502,7 +556,8 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     &Pair<DYN, COST>::cost_shared,
                     &Pair<DYN, COST>::launch,
                     &Pair<DYN, COST>::prepare,
-                    &init_eval_launch<DYN, COST> };
+                    &init_eval_launch<DYN, COST>,
+                    &Pair<DYN, COST>::stream_blocks_per_sm };
 }
 static const PairEntry kPairs[] = {
   make_entry<plugins::CartpoleDynamics, plugins::CartpoleQuadraticCost>(MPPIB_DYN_CARTPOLE,
@@ -543,19 +598,19 @@ static int colored_rearrange(mppib_engine& e, int buf, cudaStream_t st, int offs
   if (offset_t < 0 || offset_t >= 2 * e.T)
     return fail(MPPIB_ERR_INVALID_ARG, "optimization_stride %d outside the 2T = %d colored-noise samples", offset_t,
                 2 * e.T);
-  const dim3 block(128), grid((unsigned)e.n_local, (unsigned)((e.T + 127) / 128));
+  const size_t total = (size_t)e.n_local * e.T;
+  const dim3 block(256), grid((unsigned)((total + 255) / 256));
   float* dst = e.eps_buf[buf];
-  const float decay = e.sampler.offset_decay_rate;
   switch (e.C)
   {
     case 1:
-      colored_rearrange_kernel<1><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.n_local, e.T, offset_t, decay);
+      colored_rearrange_kernel<1><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.decay_pow_d, e.n_local, e.T, offset_t);
       break;
     case 2:
-      colored_rearrange_kernel<2><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.n_local, e.T, offset_t, decay);
+      colored_rearrange_kernel<2><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.decay_pow_d, e.n_local, e.T, offset_t);
       break;
     case 4:
-      colored_rearrange_kernel<4><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.n_local, e.T, offset_t, decay);
+      colored_rearrange_kernel<4><<<grid, block, 0, st>>>(e.time_d, dst, e.sigma_d, e.decay_pow_d, e.n_local, e.T, offset_t);
       break;
     default:
       return fail(MPPIB_ERR_UNSUPPORTED, "ColoredNoise: CONTROL_DIM %d", e.C);
@@ -575,6 +630,7 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
   const unsigned long long start = pos + e.draw_start;
   const size_t count = e.draw_local;
   float* dst = e.colored ? reinterpret_cast<float*>(e.spec_d) : e.eps_buf[buf];
+  bool scaled_in_draw = false;  // the engine's own generator applies configureFrequencyNoise on the way out
   if (e.any_gen)
     CUDA_TRY(cudaStreamWaitEvent(st, e.ev_last_gen, 0));
   if (e.colored && e.rearr_recorded)
@@ -588,11 +644,17 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
                                                              e.xw_chunks, e.xw_states_d);
       CUDA_TRY(cudaGetLastError());
     }
-    xorwow_normal_kernel<<<(nstates + 255) / 256, 256, 0, st>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
-                                                               e.xw_rounds_per_chunk, e.xw_chunks,
-                                                               reinterpret_cast<float2*>(dst));
+    if (e.colored)
+      xorwow_normal_kernel<true><<<(nstates + 255) / 256, 256, 0, st>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
+                                                                       e.xw_rounds_per_chunk, e.xw_chunks,
+                                                                       reinterpret_cast<float2*>(dst), e.coeffs_d, e.C, e.F);
+    else
+      xorwow_normal_kernel<false><<<(nstates + 255) / 256, 256, 0, st>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
+                                                                        e.xw_rounds_per_chunk, e.xw_chunks,
+                                                                        reinterpret_cast<float2*>(dst));
     CUDA_TRY(cudaGetLastError());
     e.xw_pos = pos + global_count;
+    scaled_in_draw = e.colored;
   }
   else
   {
@@ -617,10 +679,13 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
   }
   if (e.colored)
   {
-    const size_t ncomplex = count / 2;
-    const int blocks = (int)std::min<size_t>((ncomplex + 255) / 256, 148 * 16);
-    colored_scale_kernel<<<blocks, 256, 0, st>>>(e.spec_d, e.coeffs_d, ncomplex, e.C, e.F);
-    CUDA_TRY(cudaGetLastError());
+    if (!scaled_in_draw)
+    {
+      const size_t ncomplex = count / 2;
+      const int blocks = (int)std::min<size_t>((ncomplex + 255) / 256, 148 * 16);
+      colored_scale_kernel<<<blocks, 256, 0, st>>>(e.spec_d, e.coeffs_d, ncomplex, e.C, e.F);
+      CUDA_TRY(cudaGetLastError());
+    }
     if (cufftSetStream(e.fft_plan, st) != CUFFT_SUCCESS)
       return fail(MPPIB_ERR_CUDA, "cufftSetStream failed");
     const cufftResult fr = cufftExecC2R(e.fft_plan, reinterpret_cast<cufftComplex*>(e.spec_d), e.time_d);
@@ -1000,6 +1065,45 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
       return bail(fail(MPPIB_ERR_SMEM, "tensor-core rollout needs %u B of shared memory, device allows %d",
                        e->smem_bytes, max_smem));
   }
+  // streaming K1 (rollout_kernel.cuh: STREAM): chosen when the resident whole-horizon tile forces several waves and the
+  // ring variant needs fewer; MPPIB_STREAM=0/1 overrides
+  {
+    const bool tma_ok = !(desc->flags & MPPIB_FLAG_NO_TMA) && (e->TC % 4 == 0) && !getenv("MPPIB_NO_TMA");
+    const int sm_res = smem_for(bx);
+    const int per_sm_res = std::max(1, std::min(std::min(smem_per_sm / (sm_res + 1024), 2048 / (bx / spt)), 32));
+    const long blocks_res = (e->n_local + bx - 1) / bx;
+    const long waves_res = (blocks_res + (long)per_sm_res * num_sms - 1) / ((long)per_sm_res * num_sms);
+    int sbx = 64;
+    if (const char* sb = getenv("MPPIB_BX"))
+    {
+      const int v = atoi(sb);
+      if (v >= 32 && v <= entry->max_block_threads && (v % 32) == 0)
+        sbx = v;
+    }
+    const int sm_str = (int)rollout_smem_layout(sbx, e->ring, e->D, e->TC, e->dyn_shared_floats_fn(e->desc.model_dims, sbx),
+                                                e->cost_shared_floats(e->T))
+                           .total;
+    bool want = false;
+    if (tma_ok && !e->rmppi && !e->nn_tc && spt == 1 && e->nchunks > e->ring && sm_str <= max_smem)
+    {
+      const int per_sm_str = entry->stream_blocks_per_sm(e->D, sbx, (size_t)sm_str);
+      if (per_sm_str > 0)
+      {
+        const long blocks_str = (e->n_local + sbx - 1) / sbx;
+        const long waves_str = (blocks_str + (long)per_sm_str * num_sms - 1) / ((long)per_sm_str * num_sms);
+        want = waves_res > 1 && waves_str < waves_res;
+        if (const char* sv = getenv("MPPIB_STREAM"))
+          want = atoi(sv) != 0;
+      }
+    }
+    if (want)
+    {
+      e->stream_k1 = true;
+      e->writeback = true;
+      bx = sbx;
+      e->smem_bytes = (uint32_t)sm_str;
+    }
+  }
   e->bx = bx;
   e->dyn_shared_floats = e->dyn_shared_floats_fn(e->desc.model_dims, bx);
   e->grid = (e->n_local + bx - 1) / bx;
@@ -1013,7 +1117,9 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     e->stream = (cudaStream_t)desc->stream;
   else
   {
-    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess)
       return bail(fail(MPPIB_ERR_CUDA, "cudaStreamCreate failed"));
     e->own_stream = true;
   }
@@ -1052,7 +1158,12 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     CUDA_TRY_B(cudaMalloc(&e->noise_alloc2, (lead_floats + noise_floats + 8) * sizeof(float)));
     CUDA_TRY_B(cudaMemsetAsync(e->noise_alloc2, 0, (lead_floats + noise_floats + 8) * sizeof(float), e->stream));
     e->eps_buf[1] = e->noise_alloc2 + lead_floats;
-    CUDA_TRY_B(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    {
+      // the prefetch (next solve's noise) yields to the solve in flight: lowest priority for the side stream
+      int prio_lo = 0, prio_hi = 0;
+      CUDA_TRY_B(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CUDA_TRY_B(cudaStreamCreateWithPriority(&e->side_stream, cudaStreamNonBlocking, prio_lo));
+    }
     for (int i = 0; i < 2; i++)
     {
       CUDA_TRY_B(cudaEventCreateWithFlags(&e->ev_k1_done[i], cudaEventDisableTiming));
@@ -1096,6 +1207,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     CUDA_TRY_B(cudaMalloc(&e->time_d, batch * 2 * e->T * sizeof(float)));
     CUDA_TRY_B(cudaMalloc(&e->coeffs_d, (size_t)e->C * e->F * sizeof(float)));
     CUDA_TRY_B(cudaMalloc(&e->sigma_d, (size_t)e->C * sizeof(float)));
+    CUDA_TRY_B(cudaMalloc(&e->decay_pow_d, (size_t)e->T * sizeof(float)));
     CUDA_TRY_B(cudaEventCreateWithFlags(&e->ev_rearr, cudaEventDisableTiming));
     const cufftResult fr = cufftPlan1d(&e->fft_plan, 2 * e->T, CUFFT_C2R, (int)batch);
     if (fr != CUFFT_SUCCESS)
@@ -1208,6 +1320,7 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->time_d);
   cudaFree(e->coeffs_d);
   cudaFree(e->sigma_d);
+  cudaFree(e->decay_pow_d);
   if (e->ev_rearr)
     cudaEventDestroy(e->ev_rearr);
   if (e->result_h)
@@ -1311,6 +1424,9 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         CUDA_TRY(cudaMemcpy(e->coeffs_d, coeffs.data(), coeffs.size() * sizeof(float), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->sigma_d, sigma, Cn * sizeof(float), cudaMemcpyHostToDevice));
+        colored_decay_table_kernel<<<(e->T + 127) / 128, 128, 0, e->stream>>>(e->decay_pow_d, e->T, sp.offset_decay_rate);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
         e->prefetch_valid = false;  // a prefetched block was shaped with the old table
       }
       e->sampler = sp;

@@ -44,17 +44,28 @@ __global__ void colored_scale_kernel(float2* __restrict__ spec, const float* __r
   }
 }
 
-// rearrangeNoise: one thread per (n, t), all C components (reads C rows coalesced along t, writes C contiguous floats).
+// powf(decay_rate, t) for t < T, evaluated once per parameter change by the same device powf the reference calls per
+// element (colored_noise.cu:45)
+__global__ void colored_decay_table_kernel(float* __restrict__ table, int T, float decay_rate)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T)
+    table[t] = decay_rate == 0 ? 0 : powf(decay_rate, t);
+}
+
+// rearrangeNoise: one thread per (n, t) pair of the flattened [n][t] index, all C components: reads C rows coalesced
+// along t, writes C contiguous floats.
 template <int C>
 __global__ void colored_rearrange_kernel(const float* __restrict__ time /*[n][c][2T]*/, float* __restrict__ eps /*[n][t][c]*/,
-                                         const float* __restrict__ sigma /*[C]*/, int n_local, int T, int offset_t,
-                                         float decay_rate)
+                                         const float* __restrict__ sigma /*[C]*/, const float* __restrict__ decay_pow /*[T]*/,
+                                         int n_local, int T, int offset_t)
 {
-  const int t = blockIdx.y * blockDim.x + threadIdx.x;
-  const int n = blockIdx.x;  // grid.x carries the rollouts (up to 2^31-1), grid.y the time chunks
-  if (t >= T || n >= n_local)
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_local * T)
     return;
-  const float decayed_offset = decay_rate == 0 ? 0 : powf(decay_rate, t);  // colored_noise.cu:45
+  const int n = (int)(idx / (size_t)T);
+  const int t = (int)(idx - (size_t)n * T);
+  const float decayed_offset = decay_pow[t];
   float out[C];
 #pragma unroll
   for (int c = 0; c < C; c++)
@@ -62,7 +73,7 @@ __global__ void colored_rearrange_kernel(const float* __restrict__ time /*[n][c]
     const float* row = time + ((size_t)n * C + c) * 2 * T;
     out[c] = (row[t] - row[offset_t] * decayed_offset) / (sigma[c] * 2 * T);
   }
-  float* dst = eps + ((size_t)n * T + t) * C;
+  float* dst = eps + idx * C;
 #pragma unroll
   for (int c = 0; c < C; c++)
     dst[c] = out[c];

@@ -129,9 +129,14 @@ __global__ void xorwow_init_kernel(unsigned long long seed, unsigned long long f
   states[(size_t)5 * nstates + idx] = st.d;
 }
 
+// SPECTRUM = true: the draw is the ColoredNoise sampler's complex spectrum [row][F] (row = sample * C + c) and
+// configureFrequencyNoise (colored_noise.cu:12-37: scale by coeffs[c][f], zero the imaginary part of DC / Nyquist) is
+// applied on the way out — the separate read-modify-write pass over the 2*N*C*(T+1) floats disappears.
+template <bool SPECTRUM>
 __global__ void __launch_bounds__(256)
     xorwow_normal_kernel(uint32_t* __restrict__ states, const uint32_t* __restrict__ jump_tables, uint32_t jump_d,
-                         int rounds_per_chunk, int nchunks, float2* __restrict__ out /* pairs of this rank's slice */)
+                         int rounds_per_chunk, int nchunks, float2* __restrict__ out /* pairs of this rank's slice */,
+                         const float* __restrict__ coeffs = nullptr, int C = 1, int F = 1)
 {
   __shared__ uint32_t tab[kXorwowNibbles * 16 * 5];
   for (int i = threadIdx.x; i < kXorwowNibbles * 16 * 5; i += blockDim.x)
@@ -150,6 +155,19 @@ __global__ void __launch_bounds__(256)
     v4 = states[(size_t)4 * nstates + idx];
     d = states[(size_t)5 * nstates + idx];
     float2* dst = out + ((size_t)j * rounds_per_chunk) * kXorwowStreams + k;
+    // position of this thread's first complex number inside the spectrum: (row, f), c = row % C; one round later the
+    // index has advanced by 4096
+    int f = 0, c = 0;
+    int df = 0, dc = 0;
+    if (SPECTRUM)
+    {
+      const size_t p0 = ((size_t)j * rounds_per_chunk) * kXorwowStreams + k;
+      const size_t row0 = p0 / (size_t)F;
+      f = (int)(p0 - row0 * (size_t)F);
+      c = (int)(row0 % (size_t)C);
+      df = kXorwowStreams % F;
+      dc = (kXorwowStreams / F) % C;
+    }
     for (int r = 0; r < rounds_per_chunk; r++)
     {
       // two draws of curand(curandStateXORWOW_t*) (curand_kernel.h:863-874)
@@ -163,7 +181,23 @@ __global__ void __launch_bounds__(256)
       v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
       d += kXorwowWeyl;
       const uint32_t y = v4 + d;
-      dst[(size_t)r * kXorwowStreams] = _curand_box_muller(x, y);  // cuRAND's own device arithmetic
+      float2 z = _curand_box_muller(x, y);  // cuRAND's own device arithmetic
+      if (SPECTRUM)
+      {
+        const float v = __ldg(coeffs + c * F + f);
+        z.x *= v;
+        z.y = (f == 0 || ((F & 1) && f == F - 1)) ? 0.0f : z.y * v;
+        f += df;
+        c += dc;
+        if (f >= F)
+        {
+          f -= F;
+          c += 1;
+        }
+        if (c >= C)
+          c -= C;
+      }
+      dst[(size_t)r * kXorwowStreams] = z;
     }
   }
   __syncthreads();

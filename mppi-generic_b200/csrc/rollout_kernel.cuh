@@ -65,6 +65,7 @@ struct RolloutArgs
   int opt_stride;
   int use_tma;
   int dyn_shared_floats;  // DYN::sharedFloats(model_dims, blockDim.x): theta_s size (run-time for the LSTM model)
+  int ring;               // > 0: streaming variant, noise slabs cycle through `ring` shared-memory buffers
   // RMPPI (rollout_kernel<..., RMPPI = true>): distribution 0 = nominal system, 1 = real system
   const float* fb_gains;       // DDP feedback gains [T][S][C] (column-major C x S per step) or nullptr (no feedback)
   float value_func_threshold;  // robust_mppi_controller.cuh: value_function_threshold_
@@ -110,13 +111,14 @@ struct RolloutSmem
 {
   uint32_t tile, means, theta, theta_c, weights, scratch, bars, total;
 };
-__host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, int D, int TC, int dyn_shared_floats,
+// tile_chunks = nchunks for the resident whole-horizon tile, = the ring depth for the streaming variant
+__host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int tile_chunks, int D, int TC, int dyn_shared_floats,
                                                            int cost_shared_floats)
 {
   RolloutSmem s;
   uint32_t off = 0;
   s.tile = off;
-  off += (uint32_t)nchunks * bx * kChunkBytes;
+  off += (uint32_t)tile_chunks * bx * kChunkBytes;
   s.means = off;
   off += ((uint32_t)(D * TC + 3) / 4) * 16;
   s.theta = off;
@@ -143,7 +145,14 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int nchunks, 
 // running + likelihood-ratio cost, its tracking cost running + feedback cost (gaussian.cu:572-629); the nominal cost is
 // 0.5 c_nom + 0.5 max(min(tracking_real, value_func_threshold), c_nom) + its likelihood-ratio cost. The real system's
 // applied control depends on the state, so the block's weighted average reads it back from the write-back buffer.
-template <class DYN, class COST, int D, bool WRITEBACK, int SPT, bool RMPPI = false>
+//
+// STREAM = true (WRITEBACK, TMA): the noise does not stay resident. Its 32-column slabs cycle through a small ring of
+// shared-memory buffers (TMA refills a buffer as soon as every thread is done with it), the constrained controls go to
+// HBM as they are produced and the block's weighted average reads them back from there (L2). Shared memory per sample
+// drops from T*C*4 bytes to ring*128, so long horizons no longer cap the block count per SM — the resident tile of
+// C5 (T*C = 300) allows 4 warps per SM and 3.5 waves, the ring 12+ warps and one wave — at the price of 3x the
+// algorithmic HBM traffic (read eps, write u, read u), which this latency-bound kernel has to spare.
+template <class DYN, class COST, int D, bool WRITEBACK, int SPT, bool RMPPI = false, bool STREAM = false>
 __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
                                                       const __grid_constant__ CUtensorMap tmap)
 {
@@ -152,6 +161,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   static_assert(D <= MPPIB_MAX_DISTRIBUTIONS, "too many distributions");
   static_assert(SPT == 1 || D == 1, "several samples per thread are built for one distribution");
   static_assert(!RMPPI || (D == 2 && WRITEBACK && SPT == 1), "RMPPI: two systems, controls kept in HBM");
+  static_assert(!STREAM || (WRITEBACK && SPT == 1 && !RMPPI), "streaming variant: controls kept in HBM");
   constexpr int STEPS_PER_GROUP = 4 / C;
   constexpr int M = SPT * D;  // systems rolled out by one thread: member m = sp * D + d
 
@@ -164,7 +174,8 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   const int T = args.T;
   const int TC = T * C;
   const int nchunks = args.nchunks;
-  const RolloutSmem L = rollout_smem_layout(bx, nchunks, D, TC, args.dyn_shared_floats, COST::sharedFloats(T));
+  const int ring = STREAM ? args.ring : nchunks;
+  const RolloutSmem L = rollout_smem_layout(bx, ring, D, TC, args.dyn_shared_floats, COST::sharedFloats(T));
   unsigned char* tile = smem + L.tile;
   float* means_s = reinterpret_cast<float*>(smem + L.means);
   float* theta_s = reinterpret_cast<float*>(smem + L.theta);
@@ -194,14 +205,14 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     if (thr == 0)
     {
       tma_prefetch_desc(&tmap);
-      for (int k = 0; k < nchunks; k++)
+      for (int k = 0; k < nchunks && k < ring; k++)
         mbar_init(&bars[k], 1);
       fence_barrier_init();
     }
     __syncthreads();
     if (thr == 0)
     {
-      for (int k = 0; k < nchunks; k++)
+      for (int k = 0; k < nchunks && k < ring; k++)
       {
         mbar_arrive_expect_tx(&bars[k], (uint32_t)bx * kChunkBytes);
         tma_load_2d(tile + (size_t)k * bx * kChunkBytes, &tmap, k * kChunkFloats, row0, &bars[k]);
@@ -274,8 +285,9 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   // ---- the horizon ----------------------------------------------------------------------------------------------
   for (int k = 0; k < nchunks; k++)
   {
+    const int slot = STREAM ? (k % ring) : k;  // buffer that holds slab k
     if (args.use_tma)
-      mbar_wait(&bars[k], 0);
+      mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
 #pragma unroll 1
     for (int g = 0; g < 8; g++)
     {
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
 #pragma unroll
       for (int sp = 0; sp < SPT; sp++)
       {
-        gp[sp] = tile + tile_offset_bytes(bx, k, row[sp], g);
+        gp[sp] = tile + tile_offset_bytes(bx, slot, row[sp], g);
         e4[sp] = *reinterpret_cast<const float4*>(gp[sp]);
       }
       // light models: the 4/C steps of a 16-byte group are unrolled; heavy ones (NN) keep one copy of the step body
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
               u[m][c] += ufb[c];
           }
           DYN::enforceConstraints(args.dyn, x[m], u[m]);  // mppi_common.cu:108-111
-          if (D == 1)
+          if (D == 1 && !STREAM)
           {
             // single system: the constrained control replaces the noise in the shared tile (what writeControlSample does
             // in HBM, mppi_common.cu:117), so the epilogue's weighted sum reads it back instead of recomputing it
@@ -384,6 +396,15 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         }
       }
     }
+    if (STREAM)
+    {
+      __syncthreads();  // every thread is done with this slab's buffer
+      if (thr == 0 && k + ring < nchunks)
+      {
+        mbar_arrive_expect_tx(&bars[slot], (uint32_t)bx * kChunkBytes);
+        tma_load_2d(tile + (size_t)slot * bx * kChunkBytes, &tmap, (k + ring) * kChunkFloats, row0, &bars[slot]);
+      }
+    }
   }
 
   // ---- per-sample cost (computeAndSaveCost, mppi_common.cu:843-853) ------------------------------------------------
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     if (valid[sp])
       args.costs[(size_t)d * args.n_local + n_loc[sp]] = cost[m];
   }
-  if (RMPPI)
+  if (RMPPI || STREAM)
     __threadfence_block();  // the epilogue reads other threads' written-back controls
 
   // ---- block partial of the softmin-weighted control average ------------------------------------------------------
@@ -496,13 +517,13 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
           {
             const float* p = reinterpret_cast<const float*>(slab + r * kChunkBytes + ((grp ^ i) << 4));
             float u[C];
-            if (D == 1)
+            if (D == 1 && !STREAM)
             {
 #pragma unroll
               for (int c = 0; c < C; c++)
                 u[c] = p[c];
             }
-            else if (RMPPI && d == 1)
+            else if (STREAM || (RMPPI && d == 1))
             {  // the real system's applied control (sample + feedback, constrained) as K1 wrote it back
               const float* q = args.controls_out + (((size_t)d * args.n_local + row0 + r) * T + t) * C;
 #pragma unroll

@@ -30,9 +30,11 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         e.comm_init(ids[0])
         outs = []
-        U = w.U0.copy()
+        # open loop: the same three nominal sequences go to the sharded and to the single-GPU engine, so the comparison
+        # sees one solve's reduction-order differences and not their closed-loop amplification
+        U_ins = [w.U0.copy(), (0.5 * w.U0 + 0.05).astype(np.float32), (-0.7 * w.U0).astype(np.float32)]
         for it in range(3):
-            U, stats = e.solve(w.x0, U)
+            U, stats = e.solve(w.x0, U_ins[it])
             outs.append((U.copy(), stats))
         # every rank must hold the same result
         t = torch.from_numpy(outs[-1][0].copy()).cuda()
@@ -43,9 +45,8 @@ def main():
             s = H.Engine(w.dyn, w.cost, w.sampler, w.N, w.T, w.D, device=local)
             s.set_solver(w.dt, w.lambda_, w.alpha)
             s.seed(w.seed, 0)
-            Us = w.U0.copy()
             for it in range(3):
-                Us, sstats = s.solve(w.x0, Us)
+                Us, sstats = s.solve(w.x0, U_ins[it])
                 scale = max(1.0, float(np.abs(Us).max()))
                 good = np.allclose(outs[it][0], Us, atol=2e-5 * scale, rtol=1e-4)
                 for d in range(w.D):
