@@ -130,6 +130,13 @@ int mppib_comm_init(mppib_engine* e, const void* unique_id_128);
  *   setHostOptimalControlSequence                                      gaussian.cu:460-478
  * x0 [D][S], U_in [D][T][C], U_out [D][T][C], stats [D] are host arrays. iteration_num scales std_dev by
  * std_dev_decay^iteration_num (gaussian.cu:423). Blocks until U_out is valid. */
+/* Optional peer-memory exchange (world_size <= 8, one node): every rank exports the handle of its gather buffer
+ * (64 bytes, a cudaIpcMemHandle_t), the launcher distributes all of them and every rank opens them. From then on a solve
+ * merges the ranks' records with ONE kernel that stores to / polls NVLink peer memory instead of ncclAllGather + two
+ * launches. Call after mppib_comm_init (NCCL stays the fallback if peer access is not possible). */
+int mppib_comm_p2p_handle(mppib_engine* e, void* handle_64);
+int mppib_comm_p2p_open(mppib_engine* e, const void* handles_world_x_64);
+
 int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num,
                 float* U_out, mppib_solve_stats* stats);
 

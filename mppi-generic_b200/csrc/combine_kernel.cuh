@@ -183,6 +183,97 @@ __global__ void __launch_bounds__(kCombineCols* kCombineGroups)
   }
 }
 
+// KX — cross-GPU exchange + merge in ONE kernel over NVLink peer memory (world_size > 1, after K2 has produced this
+// rank's un-normalised record). Replaces ncclAllGather + record_headers_kernel + a second K2 (three launches and the
+// collective's launch latency): every rank stores its record straight into slot [rank] of every peer's gather buffer
+// (P2P stores through NVSwitch), publishes a per-slot sequence flag with release semantics at system scope, spins
+// (acquire) until all world_size flags of its own buffer carry this solve's sequence number, and merges the records
+// in rank order — the same log-sum-exp arithmetic as K2's merge, so every rank computes the identical result.
+// Slots are double-buffered by the parity of the sequence number: a peer can only push solve s+2 after it has seen this
+// rank's push of s+1, which this rank issues after it finished merging s.
+struct PeerTable
+{
+  float* gather[8];     // peer r's gather buffer  [2][world][D][pstride]
+  unsigned* flags[8];   // peer r's flag words     [2][world]
+};
+
+__global__ void __launch_bounds__(512)
+    exchange_merge_kernel(const float* __restrict__ rank_rec, const __grid_constant__ PeerTable peers, int world, int rank,
+                          int D, int TC, int pstride, float lambda_inv, unsigned seq, float* __restrict__ out,
+                          float* __restrict__ out2)
+{
+  __shared__ float scale_sh[2][8];
+  __shared__ float eta_sh[2];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int par = (int)(seq & 1u);
+  const int rec = D * pstride;
+  pdl_wait_prerequisites();  // K2 (this rank's record) is complete from here on
+  // ---- push --------------------------------------------------------------------------------------------------------
+  for (int p = 0; p < world; p++)
+  {
+    float* dst = peers.gather[p] + ((size_t)par * world + rank) * rec;
+    for (int i = tid; i < rec; i += nthr)
+      dst[i] = rank_rec[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world)
+  {
+    unsigned* f = peers.flags[tid] + par * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+  }
+  // ---- wait for every rank's record of this solve --------------------------------------------------------------------
+  if (tid < world)
+  {
+    const unsigned* f = peers.flags[rank] + par * world + tid;
+    unsigned v;
+    do
+    {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while (v != seq);
+  }
+  __syncthreads();
+  // ---- merge (rank order) --------------------------------------------------------------------------------------------
+  const float* g = peers.gather[rank] + (size_t)par * world * rec;
+  if (tid < D)
+  {
+    const int d = tid;
+    float beta = INFINITY;
+    for (int r = 0; r < world; r++)
+      beta = fminf(beta, g[(size_t)r * rec + d * pstride]);
+    double eta = 0.0, w2 = 0.0;
+    for (int r = 0; r < world; r++)
+    {
+      const float* h = g + (size_t)r * rec + d * pstride;
+      const float s = expf(-lambda_inv * (h[0] - beta));
+      scale_sh[d][r] = s;
+      eta += (double)s * (double)h[1];
+      w2 += (double)s * (double)s * (double)h[2];
+    }
+    const float eta_f = (float)eta;
+    eta_sh[d] = eta_f;
+    float* o = out + (size_t)d * pstride;
+    o[0] = beta, o[1] = eta_f, o[2] = (float)w2, o[3] = 0.0f;
+    if (out2)
+    {
+      float* o2 = out2 + (size_t)d * pstride;
+      o2[0] = beta, o2[1] = eta_f, o2[2] = (float)w2, o2[3] = 0.0f;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < D * TC; i += nthr)
+  {
+    const int d = i / TC, col = i - d * TC;
+    float a = 0.0f;
+    for (int r = 0; r < world; r++)
+      a = fmaf(scale_sh[d][r], g[(size_t)r * rec + d * pstride + kPartialHeader + col], a);
+    const float v = a / eta_sh[d];
+    out[(size_t)d * pstride + kPartialHeader + col] = v;
+    if (out2)
+      out2[(size_t)d * pstride + kPartialHeader + col] = v;
+  }
+}
+
 // rank record (output of a non-normalising combine) -> compact header, for the cross-rank merge after the all-gather
 __global__ void record_headers_kernel(const float* __restrict__ records, int nrec, int D, int pstride,
                                       float4* __restrict__ headers)

@@ -234,6 +234,12 @@ struct mppib_engine
 
   // comm
   ncclComm_t comm = nullptr;
+  // peer-memory exchange (combine_kernel.cuh: exchange_merge_kernel)
+  bool p2p = false;
+  float* p2p_gather_d = nullptr;   // [2][world][D][pstride] followed by the flag words [2][world]
+  PeerTable peers{};
+  void* peer_opened[8] = { nullptr };
+  unsigned p2p_seq = 0;
 
   // timing
   bool timing = false;
@@ -800,6 +806,27 @@ static int launch_combine(mppib_engine& e, bool after_k1)
   int rc = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 0, e.rank_rec_d, nullptr, pdl);
   if (rc != MPPIB_OK)
     return rc;
+  if (e.p2p)
+  {  // KX: push to peers over NVLink, wait for theirs, merge — one launch
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(1, 1, 1);
+    cfg.blockDim = dim3(512, 1, 1);
+    cfg.stream = e.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = e.use_pdl ? 1 : 0;
+    const unsigned seq = ++e.p2p_seq;
+    const float lambda_inv = (float)(1.0 / e.lambda);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, exchange_merge_kernel, (const float*)e.rank_rec_d, e.peers, e.desc.world_size,
+                                e.desc.rank, e.D, e.TC, e.pstride, lambda_inv, seq, e.result_d, host_copy));
+    if (!e.mapped_result)
+      CUDA_TRY(cudaMemcpyAsync(e.result_h, e.result_d, (size_t)e.D * e.pstride * sizeof(float), cudaMemcpyDeviceToHost,
+                               e.stream));
+    return MPPIB_OK;
+  }
   const size_t rec_floats = (size_t)e.D * e.pstride;
   rc = g_nccl.AllGather(e.rank_rec_d, e.gather_d, rec_floats, kNcclFloat, e.comm, e.stream);
   if (rc != 0)
@@ -1288,6 +1315,10 @@ int mppib_destroy(mppib_engine* e)
     cudaStreamSynchronize(e->stream);
   if (e->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(e->comm);
+  for (int r = 0; r < 8; r++)
+    if (e->peer_opened[r])
+      cudaIpcCloseMemHandle(e->peer_opened[r]);
+  cudaFree(e->p2p_gather_d);
   if (e->gen)
     curandDestroyGenerator(e->gen);
   if (e->costmap_tex)
@@ -1593,6 +1624,63 @@ int mppib_comm_init(mppib_engine* e, const void* unique_id_128)
   int rc = g_nccl.CommInitRank(&e->comm, e->desc.world_size, id, e->desc.rank);
   if (rc != 0)
     return fail(MPPIB_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return MPPIB_OK;
+}
+
+int mppib_comm_p2p_handle(mppib_engine* e, void* handle_64)
+{
+  if (!e || !handle_64)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  const int world = e->desc.world_size;
+  if (world < 2 || world > 8)
+    return fail(MPPIB_ERR_UNSUPPORTED, "peer-memory exchange is built for 2..8 ranks");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  if (!e->p2p_gather_d)
+  {
+    const size_t floats = (size_t)2 * world * e->D * e->pstride + 2 * world + 16;
+    CUDA_TRY(cudaMalloc(&e->p2p_gather_d, floats * sizeof(float)));
+    CUDA_TRY(cudaMemset(e->p2p_gather_d, 0, floats * sizeof(float)));
+  }
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, e->p2p_gather_d));
+  memcpy(handle_64, &h, 64);
+  return MPPIB_OK;
+}
+
+int mppib_comm_p2p_open(mppib_engine* e, const void* handles)
+{
+  if (!e || !handles)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (!e->p2p_gather_d)
+    return fail(MPPIB_ERR_STATE, "call mppib_comm_p2p_handle first");
+  const int world = e->desc.world_size;
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  const size_t gather_floats = (size_t)2 * world * e->D * e->pstride;
+  for (int r = 0; r < world; r++)
+  {
+    float* base = nullptr;
+    if (r == e->desc.rank)
+      base = e->p2p_gather_d;
+    else
+    {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+      void* p = nullptr;
+      cudaError_t rc = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+      if (rc != cudaSuccess)
+      {
+        cudaGetLastError();
+        return fail(MPPIB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s — keep the NCCL path", r,
+                    cudaGetErrorString(rc));
+      }
+      e->peer_opened[r] = p;
+      base = (float*)p;
+    }
+    e->peers.gather[r] = base;
+    e->peers.flags[r] = reinterpret_cast<unsigned*>(base + gather_floats);
+  }
+  e->p2p = true;
   return MPPIB_OK;
 }
 

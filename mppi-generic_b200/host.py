@@ -164,7 +164,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
-    "mppib_set_rmppi", "mppib_init_eval", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
 
@@ -190,6 +190,8 @@ def lib() -> C.CDLL:
     L.mppib_get_rng_offset.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.mppib_comm_unique_id.argtypes = [vp]
     L.mppib_comm_init.argtypes = [vp, vp]
+    L.mppib_comm_p2p_handle.argtypes = [vp, vp]
+    L.mppib_comm_p2p_open.argtypes = [vp, vp]
     L.mppib_solve.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(SolveStats)]
     L.mppib_solve_async.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     L.mppib_solve_wait.argtypes = [vp, vp, C.POINTER(SolveStats)]
@@ -675,6 +677,16 @@ class Engine:
     def comm_init(self, unique_id: bytes) -> None:
         buf = C.create_string_buffer(unique_id, 128)
         _check(lib().mppib_comm_init(self._h, buf))
+
+    def p2p_handle(self) -> bytes:
+        """64-byte handle of this rank's gather buffer (mppib_comm_p2p_handle); all-gather them, then p2p_open."""
+        buf = C.create_string_buffer(64)
+        _check(lib().mppib_comm_p2p_handle(self._h, buf))
+        return buf.raw
+
+    def p2p_open(self, handles: Sequence[bytes]) -> None:
+        blob = b"".join(handles)
+        _check(lib().mppib_comm_p2p_open(self._h, blob))
 
     @staticmethod
     def comm_unique_id() -> bytes:
