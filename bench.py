@@ -101,6 +101,21 @@ def _workload(args):
     return W.by_name(args.workload, args.rollouts, args.timesteps)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch from the `ncu --set full` captures summarised under
+# profiles/ (r01_final_autorally_k1_kernels.csv, r01_final_racer_kernels.csv, r01_cartpole_v4_kernels.csv,
+# r01_double_integrator_tube_v4_kernels.csv) — only valid for the exact single-GPU configuration that was captured.
+_NCU_K1_TRAFFIC_BYTES = {
+    "autorally_nn_N32768_T100": 26_291_200,                      # algorithmic 26_214_400: the noise is read once
+    "cartpole_vanilla_N8192_T100": 3_308_544,                    # algorithmic 3_276_800
+    "double_integrator_tube_N16384_T150": 19_710_208,            # algorithmic 19_660_800
+    "racer_lstm_H4_colored_N65536_T150": 128_668_928 + 54_798_592,  # streaming K1: eps read + controls written + re-read
+}
+
+
+def _ncu_traffic(w, world):
+    return _NCU_K1_TRAFFIC_BYTES.get(w.name) if world == 1 else None
+
+
 def _oracle_prepare(w):
     """The LSTM model's weights / architecture are handed to the oracle once (oracle/binding.py: set_lstm)."""
     import oracle
@@ -306,7 +321,7 @@ def run_engine(args):
     achieved = bytes_per_launch / (t_cold["rollout_ms"] * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "rollout_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": _ncu_traffic(w, world), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_l2_flushed": t_cold["rollout_ms"],
         "kernel_ms_l2_warm": t_warm["rollout_ms"],
         "stage_ms_l2_warm": {k: t_warm[k] for k in ("noise_ms", "rollout_ms", "reduce_ms", "total_ms")},
