@@ -192,7 +192,10 @@ enum mppib_option
   MPPIB_OPT_L2_FLUSH_BYTES = 1,
   /* ColoredNoise: the optimization_stride (rearrangeNoise's offset_t, colored_noise.cu:39-56) assumed by draws that
    * are issued before a solve names its own: mppib_draw_noise and the one-solve-ahead prefetch. Default 1. */
-  MPPIB_OPT_COLORED_OFFSET_T = 2
+  MPPIB_OPT_COLORED_OFFSET_T = 2,
+  /* 0 = go back to the NCCL all-gather after mppib_comm_p2p_open (a launcher sets it on EVERY rank when any rank failed
+   * to open its peers' buffers: the two exchange paths cannot be mixed), 1 = use the peer-memory exchange again. */
+  MPPIB_OPT_P2P_ENABLE = 3
 };
 int mppib_set_option(mppib_engine* e, int option, long long value);
 

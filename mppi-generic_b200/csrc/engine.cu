@@ -236,6 +236,7 @@ struct mppib_engine
   ncclComm_t comm = nullptr;
   // peer-memory exchange (combine_kernel.cuh: exchange_merge_kernel)
   bool p2p = false;
+  bool p2p_opened = false;
   float* p2p_gather_d = nullptr;   // [2][world][D][pstride] followed by the flag words [2][world]
   PeerTable peers{};
   void* peer_opened[8] = { nullptr };
@@ -1681,6 +1682,7 @@ int mppib_comm_p2p_open(mppib_engine* e, const void* handles)
     e->peers.flags[r] = reinterpret_cast<unsigned*>(base + gather_floats);
   }
   e->p2p = true;
+  e->p2p_opened = true;
   return MPPIB_OK;
 }
 
@@ -1945,6 +1947,15 @@ int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides
 
 int mppib_set_option(mppib_engine* e, int option, long long value)
 {
+  if (e && option == MPPIB_OPT_P2P_ENABLE)
+  {
+    if (value != 0 && !e->p2p_opened)
+      return fail(MPPIB_ERR_STATE, "mppib_comm_p2p_open has not succeeded on this rank");
+    if (value == 0 && !e->comm)
+      return fail(MPPIB_ERR_STATE, "no NCCL communicator to fall back to (mppib_comm_init)");
+    e->p2p = value != 0;
+    return MPPIB_OK;
+  }
   if (e && option == MPPIB_OPT_COLORED_OFFSET_T)
   {
     if (value < 0 || value >= 2 * e->T)

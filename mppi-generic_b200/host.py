@@ -32,6 +32,7 @@ BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIG
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR, FLAG_RMPPI = 1, 2, 4, 8, 16, 32
 OPT_L2_FLUSH_BYTES = 1
 OPT_COLORED_OFFSET_T = 2
+OPT_P2P_ENABLE = 3
 RACER_LSTM_INPUT_DIM = 4
 
 
@@ -687,6 +688,31 @@ class Engine:
     def p2p_open(self, handles: Sequence[bytes]) -> None:
         blob = b"".join(handles)
         _check(lib().mppib_comm_p2p_open(self._h, blob))
+
+    def p2p_setup(self, dist) -> bool:
+        """Collective: exchange the gather-buffer handles through ``torch.distributed`` and switch every rank to the
+        peer-memory exchange — or leave every rank on NCCL if any rank could not open its peers' buffers."""
+        import torch
+        world = dist.get_world_size()
+        ok = 1
+        try:
+            mine = self.p2p_handle()
+        except MppibError:
+            mine, ok = b"\0" * 64, 0
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        if ok:
+            try:
+                self.p2p_open(handles)
+            except MppibError:
+                ok = 0
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = int(flag.item()) == 1
+        if ok and not all_ok:
+            self.set_option(OPT_P2P_ENABLE, 0)
+        return all_ok
 
     @staticmethod
     def comm_unique_id() -> bytes:

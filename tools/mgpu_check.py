@@ -30,10 +30,7 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         e.comm_init(ids[0])
         if os.environ.get("MPPIB_NO_P2P") is None:
-            # peer-memory exchange: all-gather the 64-byte IPC handles of the ranks' gather buffers, open them
-            handles = [None] * world
-            dist.all_gather_object(handles, e.p2p_handle())
-            e.p2p_open(handles)
+            e.p2p_setup(dist)  # peer-memory exchange on every rank, or NCCL on every rank
         outs = []
         # open loop: the same three nominal sequences go to the sharded and to the single-GPU engine, so the comparison
         # sees one solve's reduction-order differences and not their closed-loop amplification
