@@ -261,11 +261,30 @@ def run_engine(args):
     outputs = np.zeros((w.D, w.T, O_), np.float32)
     L = H.lib()
 
+    # the host-tail calls with their ctypes arguments bound once (the C++ controller pays no marshalling at all; this
+    # keeps the Python mirror's per-call overhead out of the number as far as ctypes allows)
+    import ctypes as C
+    tail_calls = []
+    keep = []
+    for d in range(w.D):
+        up, sp_, op_ = U_out[d].ctypes.data, states[d].ctypes.data, outputs[d].ctypes.data
+        tail_calls.append((L.mppib_host_smooth_controls, (up, hist.ctypes.data, w.T, Cd)))
+        x0p = x0[d].ctypes.data
+        if w.dyn.DYN_ID == H.DYN_RACER_LSTM:
+            h0, c0 = w.dyn.initial_hidden_cell()
+            net = w.dyn._host_net(h0, c0)
+            keep += [h0, c0, net]
+            tail_calls.append((L.mppib_host_output_trajectory_lstm,
+                               (C.byref(w.dyn.params), C.byref(net), x0p, up, w.T, C.c_float(w.dt), sp_, op_)))
+        else:
+            nn = None if w.dyn.nn_theta is None else w.dyn.nn_theta.ctypes.data
+            tail_calls.append((L.mppib_host_output_trajectory,
+                               (w.dyn.DYN_ID, C.byref(w.dyn.params), nn, x0p, up, w.T, C.c_float(w.dt), sp_, op_)))
+
     def compute_control():
         e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
-        for d in range(w.D):
-            L.mppib_host_smooth_controls(U_out[d].ctypes.data, hist.ctypes.data, w.T, Cd)
-            w.dyn.output_trajectory(x0[d], U_out[d], w.T, w.dt, states[d], outputs[d])
+        for fn, a in tail_calls:
+            fn(*a)
         U[...] = U_out
 
     for _ in range(3):

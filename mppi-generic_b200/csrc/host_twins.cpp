@@ -145,7 +145,7 @@ __attribute__((target_clones("arch=x86-64-v3", "default"))) void fnn_6_32_32_4(c
     out4[j] = o[j] + t.b3[j];
 }
 
-int state_deriv(int dyn_id, const void* p, const FnnT* nn, const float* x, const float* u, float* xdot)
+static inline int state_deriv(int dyn_id, const void* p, const FnnT* nn, const float* x, const float* u, float* xdot)
 {
   switch (dyn_id)
   {
@@ -354,6 +354,39 @@ void racer_step(const mppib_racer_lstm_dyn_params& p, const mppib_host_lstm* net
     y[17 + i] = xn[R_UNC0 + i];
   y[27] = 0.0f;
 }
+// controller.cuh:643-663 (computeOutputTrajectoryHelper) with the model's dimensions and its derivative known at compile
+// time: the T-step loop is part of every computeControl, so the per-step switch / allocation overhead of the generic
+// entry points is kept out of it
+template <int DYN_ID, int S, int C, int O>
+static int output_trajectory_impl(const void* dyn_params, const FnnT* nn, const mppib_control_limits& lim, const float* x0,
+                                  const float* u, int T, float dt, float* states, float* outputs)
+{
+  float xn[S], xd[S], y[O], ui[C];
+  memcpy(states, x0, sizeof(float) * S);
+  for (int i = 0; i < O; i++)
+    y[i] = (i < S) ? x0[i] : 0.0f;  // initializeDynamics (dynamics.cuh:416-423)
+  memcpy(outputs, y, sizeof(float) * O);
+  for (int t = 0; t < T - 1; t++)
+  {
+    const float* x = states + (size_t)t * S;
+    for (int i = 0; i < C; i++)
+      ui[i] = u[(size_t)t * C + i];
+    enforce(lim, ui, C);
+    for (int i = 0; i < S; i++)
+      xd[i] = 0.0f;
+    const int rc = state_deriv(DYN_ID, dyn_params, nn, x, ui, xd);  // constant id: the switch folds away
+    if (rc)
+      return rc;
+    for (int i = 0; i < S; i++)
+      xn[i] = x[i] + xd[i] * dt;  // dynamics.cuh:277-281
+    for (int i = 0; i < O && i < S; i++)
+      y[i] = xn[i];  // dynamics.cuh:292-300
+    memcpy(states + (size_t)(t + 1) * S, xn, sizeof(float) * S);
+    memcpy(outputs + (size_t)(t + 1) * O, y, sizeof(float) * O);
+  }
+  return MPPIB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -467,34 +500,28 @@ void mppib_host_slide_controls(float* u, int steps, int T, int C, const float* z
 int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float* nn_theta, const float* x0,
                                  const float* u, int T, float dt, float* states, float* outputs)
 {
-  // controller.cuh:643-663 (computeOutputTrajectoryHelper)
-  int S, C, O;
-  if (mppib_host_dims(dyn_id, &S, &C, &O) || !dyn_params || !x0 || !u || !states || !outputs || T <= 0)
+  if (!dyn_params || !x0 || !u || !states || !outputs || T <= 0)
     return MPPIB_ERR_INVALID_ARG;
-  std::vector<float> xn(S), xd(S), y(O, 0.0f), ui(C);
-  FnnT nn;
-  const FnnT* nnp = nullptr;
-  if (dyn_id == MPPIB_DYN_AUTORALLY_NN && nn_theta)
+  switch (dyn_id)
   {
-    fnn_transpose(nn_theta, nn);
-    nnp = &nn;
+    case MPPIB_DYN_CARTPOLE:
+      return output_trajectory_impl<MPPIB_DYN_CARTPOLE, 4, 1, 4>(dyn_params, nullptr, *limits_of(dyn_id, dyn_params), x0, u,
+                                                                T, dt, states, outputs);
+    case MPPIB_DYN_DOUBLE_INTEGRATOR:
+      return output_trajectory_impl<MPPIB_DYN_DOUBLE_INTEGRATOR, 4, 2, 4>(dyn_params, nullptr,
+                                                                         *limits_of(dyn_id, dyn_params), x0, u, T, dt,
+                                                                         states, outputs);
+    case MPPIB_DYN_AUTORALLY_NN:
+    {
+      if (!nn_theta)
+        return MPPIB_ERR_INVALID_ARG;
+      FnnT nn;
+      fnn_transpose(nn_theta, nn);
+      return output_trajectory_impl<MPPIB_DYN_AUTORALLY_NN, 7, 2, 8>(dyn_params, &nn, *limits_of(dyn_id, dyn_params), x0,
+                                                                    u, T, dt, states, outputs);
+    }
   }
-  memcpy(states, x0, sizeof(float) * S);
-  for (int i = 0; i < O && i < S; i++)
-    y[i] = x0[i];  // initializeDynamics (dynamics.cuh:416-423)
-  memcpy(outputs, y.data(), sizeof(float) * O);
-  for (int t = 0; t < T - 1; t++)
-  {
-    memcpy(ui.data(), u + (size_t)t * C, sizeof(float) * C);
-    enforce(*limits_of(dyn_id, dyn_params), ui.data(), C);
-    int rc = host_step_impl(dyn_id, dyn_params, nnp, states + (size_t)t * S, ui.data(), dt, xn.data(), xd.data(),
-                            y.data());
-    if (rc)
-      return rc;
-    memcpy(states + (size_t)(t + 1) * S, xn.data(), sizeof(float) * S);
-    memcpy(outputs + (size_t)(t + 1) * O, y.data(), sizeof(float) * O);
-  }
-  return MPPIB_OK;
+  return MPPIB_ERR_UNSUPPORTED;
 }
 
 int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x, const float* u, float dt,
