@@ -28,6 +28,25 @@
 
 namespace mppib
 {
+// MMA completion wait: MPPIB_TC_WAIT_NS > 0 parks the thread between polls (device_utils.cuh)
+#ifndef MPPIB_TC_WAIT_NS
+#define MPPIB_TC_WAIT_NS 0
+#endif
+// MPPIB_TC_WAIT_WARP0: only warp 0 polls the mbarrier, the other warps park at the CTA barrier (no issue slots)
+#if defined(MPPIB_TC_WAIT_WARP0)
+#define MMA_WAIT(bar, phase)                                                                                           \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if ((threadIdx.x >> 5) == 0)                                                                                       \
+      mbar_wait(bar, phase);                                                                                           \
+    __syncthreads();                                                                                                   \
+  } while (0)
+#elif MPPIB_TC_WAIT_NS > 0
+#define MMA_WAIT(bar, phase) mbar_wait_parked(bar, phase, MPPIB_TC_WAIT_NS)
+#else
+#define MMA_WAIT(bar, phase) mbar_wait(bar, phase)
+#endif
+
 namespace nn_tc
 {
 constexpr int kRows = 128;          // samples per CTA == UMMA M
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(nn_tc::kRows, 2)
             tma_load_2d(slabs + buf * kSlabBytes, &tmap, (k + 2) * kChunkFloats, row0, &bars[buf]);
           }
         }
-        mbar_wait(&bars[2], mma_phase);
+        MMA_WAIT(&bars[2], mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
         float act[32];
@@ -425,7 +444,7 @@ __global__ void __launch_bounds__(nn_tc::kRows, 2)
           tc_fence_after();
           issue_layer(w2h, w2l, 32, 4, true, idesc32);
         }
-        mbar_wait(&bars[2], mma_phase);
+        MMA_WAIT(&bars[2], mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
         tmem_ld32(tmem_row, act);
@@ -443,7 +462,7 @@ __global__ void __launch_bounds__(nn_tc::kRows, 2)
           tc_fence_after();
           issue_layer(w3h, w3l, 8, 4, true, idesc8);
         }
-        mbar_wait(&bars[2], mma_phase);
+        MMA_WAIT(&bars[2], mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
         float out4[4];
