@@ -28,24 +28,12 @@
 
 namespace mppib
 {
-// MMA completion wait: MPPIB_TC_WAIT_NS > 0 parks the thread between polls (device_utils.cuh)
-#ifndef MPPIB_TC_WAIT_NS
-#define MPPIB_TC_WAIT_NS 0
-#endif
-// MPPIB_TC_WAIT_WARP0: only warp 0 polls the mbarrier, the other warps park at the CTA barrier (no issue slots)
-#if defined(MPPIB_TC_WAIT_WARP0)
-#define MMA_WAIT(bar, phase)                                                                                           \
-  do                                                                                                                   \
-  {                                                                                                                    \
-    if ((threadIdx.x >> 5) == 0)                                                                                       \
-      mbar_wait(bar, phase);                                                                                           \
-    __syncthreads();                                                                                                   \
-  } while (0)
-#elif MPPIB_TC_WAIT_NS > 0
-#define MMA_WAIT(bar, phase) mbar_wait_parked(bar, phase, MPPIB_TC_WAIT_NS)
-#else
+// MMA completion wait. Measured on B200: parking the thread between polls (mbarrier.try_wait with a suspend-time hint),
+// or letting only warp 0 poll while the others sit at the CTA barrier, changes nothing (379-383 us); neither does starting
+// the two CTAs of an SM half a step apart. One CTA per SM alone takes 320 us: the per-step chain of a tile (stage -> sync ->
+// MMA round trip -> tcgen05.ld -> 32 tanh at 2 MUFU each on one warp per scheduler -> split -> store -> fence, three times)
+// is ~6300 cycles, longer than the FFMA2 kernel's ~4500 for a lone warp (profiles/r01_autorally_k1_notes.md).
 #define MMA_WAIT(bar, phase) mbar_wait(bar, phase)
-#endif
 
 namespace nn_tc
 {
