@@ -199,6 +199,11 @@ enum mppib_option
 };
 int mppib_set_option(mppib_engine* e, int option, long long value);
 
+/* ColoredMPPIController's alternative weighting (ColoredMPPI/colored_mppi_controller.cu:199-209): when gamma and r are
+ * both non-zero the exp weights are replaced by TsallisTransform (core/mppi_common.cu:968-985). Needs an engine created
+ * with MPPIB_FLAG_WRITEBACK_CONTROLS on one rank; gamma = 0 or r = 0 switches back to the exponential weights. */
+int mppib_set_tsallis(mppib_engine* e, float gamma, float r);
+
 /* ---- RMPPI (engines created with MPPIB_FLAG_RMPPI) ------------------------------------------------------------- */
 /* RobustMPPIController::setValueFunctionThreshold + fb_controller_->copyToDevice (robust_mppi_controller.cu:630-633):
  * feedback_gains = the DDP gain trajectory, T matrices C x S column-major ([t][s][c]), or NULL for no feedback. */

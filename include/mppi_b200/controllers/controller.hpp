@@ -309,6 +309,7 @@ public:
   }
 
 protected:
+  unsigned extra_flags_ = 0u;  // engine flags a derived controller turns on at run time (re-creates the engine)
   void construct(cudaStream_t stream)
   {
     stream_ = stream;
@@ -331,7 +332,7 @@ protected:
     d.num_timesteps = params_.num_timesteps_;
     d.num_distributions = NUM_DISTRIBUTIONS;
     d.device = 0;  // mppi_controller.cu:48
-    d.flags = ENGINE_FLAGS;  // e.g. MPPIB_FLAG_RMPPI for RobustMPPIController
+    d.flags = ENGINE_FLAGS | extra_flags_;  // e.g. MPPIB_FLAG_RMPPI for RobustMPPIController
     d.stream = (void*)stream_;
     d.rank = 0;
     d.world_size = 1;

@@ -274,6 +274,76 @@ __global__ void __launch_bounds__(512)
   }
 }
 
+// Tsallis weighting (TsallisTransform core/mppi_common.cu:968-985 + computeNormalizer + weightedReductionKernel), used by
+// ColoredMPPIController when gamma and r are non-zero (ColoredMPPI/colored_mppi_controller.cu:199-217). These weights
+// are not a function of (c - beta) that factors over block baselines, so the block partials of K1 cannot be rescaled:
+// K2 supplies the global baseline (record[0]) and this kernel reduces the written-back controls with the Tsallis
+// weights. grid (ceil(T*C / 32), D), block 16 warps x 32 columns; every block recomputes the normaliser (N floats).
+__global__ void __launch_bounds__(512)
+    tsallis_reduce_kernel(const float* __restrict__ costs,     // [D][n]
+                          const float* __restrict__ controls,  // [D][n][TC] constrained sampled controls
+                          int n, int D, int TC, int pstride, float gamma, float r,
+                          float* __restrict__ out,   // [D][pstride]: in = K2's record (beta at [0]); out = Tsallis result
+                          float* __restrict__ out2)  // optional mapped host copy
+{
+  __shared__ float acc_sh[16][32];
+  __shared__ double eta_sh[16];
+  const int d = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const float beta = out[(size_t)d * pstride];
+  const float* c = costs + (size_t)d * n;
+  const float* u = controls + (size_t)d * n * TC;
+  const float inv_rm1 = 1.0f / (r - 1.0f);
+  float a = 0.0f;
+  double eta = 0.0;
+  for (int i = warp; i < n; i += 16)
+  {
+    const float cost_dif = c[i] - beta;
+    float w = 0.0f;
+    if (cost_dif < gamma)
+      w = expf(logf(1.0f - cost_dif / gamma) * inv_rm1);
+    eta += (double)w;
+    if (col < TC)
+      a = fmaf(w, u[(size_t)i * TC + col], a);
+  }
+  acc_sh[warp][lane] = a;
+  if (lane == 0)
+    eta_sh[warp] = eta;
+  __syncthreads();
+  if (warp == 0)
+  {
+    double e = 0.0;
+    float s = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 16; g++)
+    {
+      e += eta_sh[g];
+      s += acc_sh[g][lane];
+    }
+    const float eta_f = (float)e;
+    float* o = out + (size_t)d * pstride;
+    float* o2 = out2 ? out2 + (size_t)d * pstride : nullptr;
+    __syncwarp();
+    if (col < TC)
+    {
+      const float v = s / eta_f;
+      o[kPartialHeader + col] = v;
+      if (o2)
+        o2[kPartialHeader + col] = v;
+    }
+    if (blockIdx.x == 0 && lane == 0)
+    {  // baseline stays; normaliser and sum of squares describe the Tsallis weights
+      o[1] = eta_f;
+      if (o2)
+      {
+        o2[0] = beta;
+        o2[1] = eta_f;
+      }
+    }
+  }
+}
+
 // rank record (output of a non-normalising combine) -> compact header, for the cross-rank merge after the all-gather
 __global__ void record_headers_kernel(const float* __restrict__ records, int nrec, int D, int pstride,
                                       float4* __restrict__ headers)

@@ -135,6 +135,7 @@ struct mppib_engine
   unsigned solve_seq = 0;
   bool writeback = false;
   bool rmppi = false;  // MPPIB_FLAG_RMPPI
+  float tsallis_gamma = 0.0f, tsallis_r = 0.0f;  // both non-zero: Tsallis weights (mppib_set_tsallis)
   float value_func_threshold = 1000.0f;  // robust_mppi_controller.cuh default
   float* fb_gains_d = nullptr;           // [T][S][C] or null
   float* eval_states_d = nullptr;        // init-eval scratch: candidates, strides, costs
@@ -795,6 +796,21 @@ static int launch_combine(mppib_engine& e, bool after_k1)
 {
   const bool pdl = after_k1 && e.use_pdl;
   float* host_copy = e.mapped_result ? e.result_h_dev : nullptr;
+  if (e.tsallis_gamma != 0.0f && e.tsallis_r != 0.0f)
+  {
+    // K2 for the global baseline (device copy only), then the Tsallis-weighted reduction of the written-back controls
+    int rc1 = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, nullptr, pdl, false);
+    if (rc1 != MPPIB_OK)
+      return rc1;
+    const dim3 grid((e.TC + 31) / 32, e.D, 1);
+    tsallis_reduce_kernel<<<grid, 512, 0, e.stream>>>(e.costs_d, e.controls_d, e.n_local, e.D, e.TC, e.pstride,
+                                                      e.tsallis_gamma, e.tsallis_r, e.result_d, host_copy);
+    CUDA_TRY(cudaGetLastError());
+    if (!e.mapped_result)
+      CUDA_TRY(cudaMemcpyAsync(e.result_h, e.result_d, (size_t)e.D * e.pstride * sizeof(float), cudaMemcpyDeviceToHost,
+                               e.stream));
+    return MPPIB_OK;
+  }
   if (e.desc.world_size == 1 || !e.comm)
   {
     int rc1 = launch_combine_one(e, e.partials_d, e.headers_d, e.grid, 1, e.result_d, host_copy, pdl, true);
@@ -1867,6 +1883,25 @@ int mppib_solve_wait(mppib_engine* e, float* U_out, mppib_solve_stats* stats)
     return fail(MPPIB_ERR_STATE, "no solve in flight");
   CUDA_TRY(cudaSetDevice(e->desc.device));
   return wait_solve(e, U_out, stats);
+}
+
+int mppib_set_tsallis(mppib_engine* e, float gamma, float r)
+{
+  if (!e)
+    return fail(MPPIB_ERR_INVALID_ARG, "null engine");
+  if (gamma != 0.0f && r != 0.0f)
+  {
+    if (!e->controls_d)
+      return fail(MPPIB_ERR_STATE, "Tsallis weights reduce the written-back controls: create the engine with "
+                                   "MPPIB_FLAG_WRITEBACK_CONTROLS");
+    if (e->desc.world_size != 1)
+      return fail(MPPIB_ERR_UNSUPPORTED, "Tsallis weights are built for one rank");
+    if (r == 1.0f || !(gamma > 0.0f))
+      return fail(MPPIB_ERR_INVALID_ARG, "Tsallis weights need gamma > 0 and r != 1");
+  }
+  e->tsallis_gamma = gamma;
+  e->tsallis_r = r;
+  return MPPIB_OK;
 }
 
 int mppib_set_rmppi(mppib_engine* e, float value_func_threshold, const float* feedback_gains)

@@ -165,7 +165,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
-    "mppib_set_rmppi", "mppib_init_eval", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
 
@@ -222,6 +222,7 @@ def lib() -> C.CDLL:
     L.mppib_host_step_lstm.argtypes = [vp, C.POINTER(HostLSTM), vp, vp, C.c_float, vp, vp, vp]
     L.mppib_host_output_trajectory_lstm.argtypes = [vp, C.POINTER(HostLSTM), vp, vp, C.c_int, C.c_float, vp, vp]
     L.mppib_set_rmppi.argtypes = [vp, C.c_float, vp]
+    L.mppib_set_tsallis.argtypes = [vp, C.c_float, C.c_float]
     L.mppib_init_eval.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
     L.mppib_host_rmppi_line_search_weights.argtypes = [C.c_int, vp]
     L.mppib_host_rmppi_line_search_weights.restype = None
@@ -747,6 +748,9 @@ class Engine:
     def set_option(self, option: int, value: int) -> None:
         _check(lib().mppib_set_option(self._h, option, value))
 
+    def set_tsallis(self, gamma: float, r: float) -> None:
+        _check(lib().mppib_set_tsallis(self._h, C.c_float(gamma), C.c_float(r)))
+
     def set_rmppi(self, value_func_threshold: float, feedback_gains=None) -> None:
         """feedback_gains: [T][S][C] (C x S column-major per step) or None."""
         g = None if feedback_gains is None else _f32(feedback_gains)
@@ -956,6 +960,55 @@ class VanillaMPPIController(_Controller):
         """controllers/MPPI/mppi_controller.cu (slideControlSequence): save history, then slide."""
         self._save_control_history(steps, self.control_)
         self._slide(self.control_, steps)
+
+
+class ColoredMPPIController(VanillaMPPIController):
+    """controllers/ColoredMPPI/colored_mppi_controller.cuh — VanillaMPPI's flow with the ColoredNoise sampler, an optional
+    state leash (colored_mppi_controller.cu:150-153), Tsallis weights when gamma and r are both non-zero (:199-209) and
+    the clamp of control 1 (:232-238). ``tsallis=True`` creates the engine with the control write-back buffer the
+    Tsallis reduction needs."""
+
+    def __init__(self, *args, tsallis: bool = False, **kw):
+        if tsallis:
+            kw["flags"] = kw.get("flags", 0) | FLAG_WRITEBACK_CONTROLS
+        super().__init__(*args, **kw)
+        self.gamma_, self.r_ = 0.0, 0.0
+        self.leash_active_, self.leash_jump_ = False, 1
+        self.state_leash_dist_ = np.zeros(self.model_.STATE_DIM, np.float32)
+
+    def setGamma(self, gamma: float) -> None:
+        self.gamma_ = gamma
+        self._push_weighting()
+
+    def setRExp(self, r: float) -> None:
+        self.r_ = r
+        self._push_weighting()
+
+    def _push_weighting(self) -> None:
+        on = self.gamma_ != 0 and self.r_ != 0
+        self.engine.set_tsallis(self.gamma_ if on else 0.0, self.r_ if on else 0.0)
+
+    def setLeashActive(self, v: bool) -> None:
+        self.leash_active_ = v
+
+    def setStateLeashLength(self, v: float, index: int = 0) -> None:
+        self.state_leash_dist_[index] = v
+
+    def computeControl(self, state, optimization_stride: int = 1) -> None:
+        state = _f32(state).copy()
+        if self.leash_active_:  # Dynamics::enforceLeash, dynamics.cuh:448-466
+            nominal = self.state_[self.leash_jump_]
+            diff = np.abs(nominal - state)
+            leashed = state + np.clip(nominal - state, -self.state_leash_dist_, self.state_leash_dist_)
+            state = np.where(self.state_leash_dist_ < diff, leashed, nominal).astype(np.float32)
+        super().computeControl(state, optimization_stride)
+        if self.model_.CONTROL_DIM > 1:  # colored_mppi_controller.cu:232-238
+            lo, hi = self.model_.params.lim.rng_lo[1], self.model_.params.lim.rng_hi[1]
+            self.control_[:, 1] = np.clip(self.control_[:, 1], lo, hi)
+
+    def slideControlSequence(self, steps: int) -> None:
+        self.leash_jump_ = steps
+        super().slideControlSequence(steps)
 
 
 class TubeMPPIController(_Controller):

@@ -279,3 +279,10 @@ def rmppi_best_index(costs, K, spc, lam, threshold):
     fe = np.zeros(K, np.float32)
     best = lib().orc_rmppi_best_index(_p(_f32(costs)), K, spc, C.c_float(lam), C.c_float(threshold), _p(fe))
     return best, fe
+
+
+def tsallis(costs, gamma, r, base) -> np.ndarray:
+    """TsallisTransform (core/mppi_common.cu:968-985): weights (1 - (c - beta)/gamma)^(1/(r-1)) below gamma, else 0."""
+    c = _f32(costs).copy()
+    lib().orc_tsallis(_p(c), c.size, C.c_float(gamma), C.c_float(r), C.c_float(base))
+    return c

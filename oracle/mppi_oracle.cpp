@@ -1066,6 +1066,20 @@ static void normExpTransform(float* c, int n, float lambda_inv, float baseline)
     c[i] = expf(-lambda_inv * cost_dif);
   }
 }
+// core/mppi_common.cu:968-985 (TsallisTransform), the weighting ColoredMPPIController uses when gamma and r are both
+// non-zero (ColoredMPPI/colored_mppi_controller.cu:199-209)
+static void tsallisTransform(float* c, int n, float gamma, float r, float baseline)
+{
+  for (int i = 0; i < n; i++)
+  {
+    float cost_dif = c[i] - baseline;
+    if (cost_dif < gamma)
+      c[i] = expf(logf(1.0 - cost_dif / gamma) / (r - 1));
+    else
+      c[i] = 0;
+  }
+}
+
 static float computeNormalizer(const float* w, int n)
 {
   double normalizer = 0.0;
@@ -1441,6 +1455,10 @@ float orc_baseline(const float* costs, int n)
 void orc_norm_exp(float* costs, int n, float lambda_inv, float baseline)
 {
   orc::normExpTransform(costs, n, lambda_inv, baseline);
+}
+void orc_tsallis(float* costs, int n, float gamma, float r, float baseline)
+{
+  orc::tsallisTransform(costs, n, gamma, r, baseline);
 }
 float orc_normalizer(const float* w, int n)
 {

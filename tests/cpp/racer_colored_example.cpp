@@ -1,7 +1,7 @@
 // Host-layer check for config C5: RacerDubinsElevationLSTMSteering + ColoredNoiseDistribution + VanillaMPPIController
 // written against the reference's include paths (include/mppi/...cuh forwarders), compiled with plain g++.
 // Exit codes: 0 = closed loop reaches the speed set-point, 5 = no CUDA device (expected on the CPU-only box).
-#include <mppi/controllers/MPPI/mppi_controller.cuh>
+#include <mppi/controllers/ColoredMPPI/colored_mppi_controller.cuh>
 #include <mppi/dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cuh>
 #include <mppi/sampling_distributions/colored_noise/colored_noise.cuh>
 #include <mppi_b200/cost_functions/racer/racer_quadratic_cost.hpp>
@@ -71,7 +71,7 @@ int main()
   const float dt = 0.02f;
   try
   {
-    VanillaMPPIController<DYN, RacerQuadraticCost, NoFeedback, T, 4096, SAMPLER_T> ctrl(&model, &cost, nullptr, &sampler, dt,
+    ColoredMPPIController<DYN, RacerQuadraticCost, NoFeedback, T, 4096> ctrl(&model, &cost, nullptr, &sampler, dt,
                                                                                      1, 1.0f, 0.0f);
     DYN::state_array x = DYN::state_array::Zero(), xn, xd;
     DYN::output_array y;
@@ -89,7 +89,23 @@ int main()
       ctrl.slideControlSequence(1);
     }
     printf("speed after 80 steps %f (set-point %f), baseline %f\n", x(0), cp.desired_speed, ctrl.getBaselineCost());
-    return fabsf(x(0) - cp.desired_speed) < 0.3f ? 0 : 2;
+    int rc = fabsf(x(0) - cp.desired_speed) < 0.3f ? 0 : 2;
+    // Tsallis weights (colored_mppi_controller.cu:199-209): the engine is re-created with the control write-back buffer
+    ctrl.setGamma(50.0f);
+    ctrl.setRExp(2.0f);
+    for (int it = 0; it < 40; it++)
+    {
+      ctrl.computeControl(x, 1);
+      DYN::control_array u = ctrl.getControlSeq().col(0);
+      model.step(x, xn, xd, u, y, it, dt);
+      x = xn;
+      ctrl.slideControlSequence(1);
+    }
+    printf("with Tsallis weights: speed %f, baseline %f, normalizer %f\n", x(0), ctrl.getBaselineCost(),
+           ctrl.getNormalizerCost());
+    if (!(fabsf(x(0) - cp.desired_speed) < 0.4f) || !(ctrl.getNormalizerCost() > 0.0f))
+      rc = 3;
+    return rc;
   }
   catch (const std::exception& e)
   {

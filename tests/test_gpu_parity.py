@@ -766,3 +766,42 @@ def test_rmppi_controller_tracks_the_circle_under_disturbance():
     assert 1.6 < min(radii[20:]) and max(radii[20:]) < 2.4
     assert 0 <= ctrl.best_index_ < 9 and ctrl.candidate_free_energy_ is not None
     assert np.isfinite(ctrl.getBaselineCost(0)) and np.isfinite(ctrl.getBaselineCost(1))
+
+
+# ---- ColoredMPPIController's Tsallis weighting (core/mppi_common.cu:968-985) -------------------------------------------
+@pytest.mark.parametrize("name", ["cartpole", "racer_lstm"])
+def test_tsallis_weights_match_oracle(name):
+    w = W.by_name(name, 2048, 64)
+    w.U0[0, :, 0] = 0.1
+    e = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    U_exp, st_exp = e.solve(w.x0, w.U0, 1, 0)
+    costs = e.get_costs()[0]
+    spread = float(np.percentile(costs, 60) - costs.min())
+    gamma, r = max(spread, 1e-3), 2.0
+    e.set_tsallis(gamma, r)
+    e.seed(w.seed, 0)
+    U, st = e.solve(w.x0, w.U0, 1, 0)
+    np.testing.assert_array_equal(e.get_costs()[0], costs)  # same noise block, same rollouts
+    wts = oracle.tsallis(costs, gamma, r, costs.min()).astype(np.float64)
+    assert 0 < np.count_nonzero(wts) < wts.size  # the cut-off at gamma is exercised
+    samples = e.get_samples()[0].astype(np.float64)
+    Uref = np.einsum("n,ntc->tc", wts / wts.sum(), samples)
+    scale = max(1.0, float(np.abs(Uref).max()))
+    np.testing.assert_allclose(U[0], Uref, atol=2e-5 * scale, rtol=2e-5)
+    assert st[0][0] == np.float32(costs.min())
+    assert st[0][1] == pytest.approx(wts.sum(), rel=1e-5)
+    assert np.abs(U[0] - U_exp[0]).max() > 1e-6  # really a different weighting
+    # gamma = 0 switches back to the exponential weights
+    e.set_tsallis(0.0, 0.0)
+    e.seed(w.seed, 0)
+    U2, _ = e.solve(w.x0, w.U0, 1, 0)
+    np.testing.assert_array_equal(U2, U_exp)
+    e.close()
+
+
+def test_tsallis_needs_the_writeback_buffer():
+    w = W.cartpole(1024, 32)
+    e = w.make_engine()
+    with pytest.raises(H.MppibError):
+        e.set_tsallis(1.0, 2.0)
+    e.close()
