@@ -24,6 +24,7 @@ enum mppib_dynamics_id
   MPPIB_DYN_DOUBLE_INTEGRATOR = 1, /* dynamics/double_integrator/di_dynamics.cuh         S4 C2 O4 */
   MPPIB_DYN_AUTORALLY_NN = 2,      /* dynamics/autorally/ar_nn_model.cuh NeuralNetModel<7,2,3>  S7 C2 O8 */
   MPPIB_DYN_RACER_LSTM = 3,        /* dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cuh S19 C2 O28 */
+  MPPIB_DYN_QUADROTOR = 4,         /* dynamics/quadrotor/quadrotor_dynamics.cuh          S13 C4 O13 */
   MPPIB_DYN_COUNT
 };
 
@@ -33,6 +34,7 @@ enum mppib_cost_id
   MPPIB_COST_DI_CIRCLE = 1,          /* cost_functions/double_integrator/double_integrator_circle_cost.cuh */
   MPPIB_COST_AR_STANDARD = 2,        /* cost_functions/autorally/ar_standard_cost.cuh */
   MPPIB_COST_RACER_QUADRATIC = 3,    /* ours: quadratic on speed / yaw, documented in DESIGN.md */
+  MPPIB_COST_QUADROTOR_QUADRATIC = 4, /* cost_functions/quadrotor/quadrotor_quadratic_cost.cuh */
   MPPIB_COST_COUNT
 };
 
@@ -118,6 +120,20 @@ typedef struct mppib_racer_lstm_dyn_params
   float Q_omega_v;                 /* 0.001 */
   float Q_omega_steering;          /* 0 */
 } mppib_racer_lstm_dyn_params;
+
+/* QuadrotorDynamics (dynamics/quadrotor/quadrotor_dynamics.cuh:9-63). State POS(3) VEL(3) QUAT_W..Z(4) ANG_VEL(3);
+ * controls ANG_RATE_X/Y/Z, THRUST. The default constructor's thrust range [0, 36] and zero_control[3] = GRAVITY
+ * (quadrotor_dynamics.cu:11-19) are set by the host-side mirror, they are not part of the params struct. */
+#define MPPIB_GRAVITY 9.81f /* utils/math_utils.h:45 */
+typedef struct mppib_quadrotor_dyn_params
+{
+  mppib_control_limits lim;
+  float tau_roll;  /* 0.25 */
+  float tau_pitch; /* 0.25 */
+  float tau_yaw;   /* 0.25 */
+  float mass;      /* 1 kg */
+} mppib_quadrotor_dyn_params;
+
 /* ---- Cost parameter blobs ----------------------------------------------------------------------- */
 typedef struct mppib_cartpole_cost_params /* cost_functions/cartpole/cartpole_quadratic_cost.cuh:10-23 */
 {
@@ -182,6 +198,23 @@ typedef struct mppib_racer_quadratic_cost_params
   float lateral_coeff; /* 2.0 */
   float steer_coeff;   /* 1.0 */
 } mppib_racer_quadratic_cost_params;
+
+/* QuadrotorQuadraticCost (cost_functions/quadrotor/quadrotor_quadratic_cost.cuh:9-66) */
+typedef struct mppib_quadrotor_cost_params
+{
+  float control_cost_coeff[MPPIB_MAX_CONTROL_DIM]; /* 2, 2, 2, 2; unused on device (cost.cuh:205-208) */
+  float discount;                                  /* CostParams default 1.0 (unused by this cost) */
+  float s_goal[13];                                /* x(3) v(3) q(4: 1,0,0,0) w(3) */
+  float x_coeff;                                   /* 1 */
+  float v_coeff;                                   /* 1 */
+  int use_euler;                                   /* true */
+  float q_coeff;                                   /* 1 */
+  float roll_coeff;                                /* 1 */
+  float pitch_coeff;                               /* 1 */
+  float yaw_coeff;                                 /* 1 */
+  float w_coeff;                                   /* 1 */
+  float terminal_cost_coeff;                       /* 0 */
+} mppib_quadrotor_cost_params;
 /* ---- Sampler parameter blob (sampling_distribution.cuh:14-29, gaussian.cuh:21-61) --------------- */
 typedef struct mppib_gaussian_params
 {

@@ -574,6 +574,8 @@ static const PairEntry kPairs[] = {
                                                                                      MPPIB_COST_DI_CIRCLE),
   make_entry<plugins::AutorallyNNDynamics, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
   make_entry<plugins::RacerLSTMDynamics, plugins::RacerQuadraticCost>(MPPIB_DYN_RACER_LSTM, MPPIB_COST_RACER_QUADRATIC),
+  make_entry<plugins::QuadrotorDynamics, plugins::QuadrotorQuadraticCost>(MPPIB_DYN_QUADROTOR,
+                                                                          MPPIB_COST_QUADROTOR_QUADRATIC),
 };
 
 // ---- helpers ----------------------------------------------------------------------------------------------------

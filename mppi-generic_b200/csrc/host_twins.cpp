@@ -49,6 +49,8 @@ const mppib_control_limits* limits_of(int dyn_id, const void* p)
       return &((const mppib_ar_nn_dyn_params*)p)->lim;
     case MPPIB_DYN_RACER_LSTM:
       return &((const mppib_racer_lstm_dyn_params*)p)->lim;
+    case MPPIB_DYN_QUADROTOR:
+      return &((const mppib_quadrotor_dyn_params*)p)->lim;
   }
   return nullptr;
 }
@@ -167,6 +169,27 @@ static inline int state_deriv(int dyn_id, const void* p, const FnnT* nn, const f
       xdot[2] = u[0];
       xdot[3] = u[1];
       return 0;
+    case MPPIB_DYN_QUADROTOR:
+    {  // dynamics/quadrotor/quadrotor_dynamics.cu:70-112; DCM column 2 as Eigen's toRotationMatrix evaluates it
+      const auto& q = *(const mppib_quadrotor_dyn_params*)p;
+      const float qw = x[6], qx = x[7], qy = x[8], qz = x[9];
+      const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+      const float col2[3] = { tz * qx + ty * qw, tz * qy - tx * qw, 1.0f - (tx * qx + ty * qy) };
+      const float tau_inv[3] = { 1 / q.tau_roll, 1 / q.tau_pitch, 1 / q.tau_yaw };
+      for (int i = 0; i < 3; i++)
+      {
+        xdot[i] = x[3 + i];
+        xdot[3 + i] = (u[3] / q.mass) * col2[i];
+        xdot[10 + i] = tau_inv[i] * (u[i] - x[10 + i]);
+      }
+      xdot[5] -= MPPIB_GRAVITY;
+      const float pp = x[10], qq = x[11], rr = x[12];
+      xdot[6] = 0.5f * (-pp * qx - qq * qy - rr * qz);
+      xdot[7] = 0.5f * (pp * qw - qq * qz + rr * qy);
+      xdot[8] = 0.5f * (pp * qz + qq * qw - rr * qx);
+      xdot[9] = 0.5f * (-pp * qy + qq * qx + rr * qw);
+      return 0;
+    }
     case MPPIB_DYN_AUTORALLY_NN:
     {  // dynamics/autorally/ar_nn_model.cu:90-119
       if (!nn)
@@ -357,6 +380,22 @@ void racer_step(const mppib_racer_lstm_dyn_params& p, const mppib_host_lstm* net
 // controller.cuh:643-663 (computeOutputTrajectoryHelper) with the model's dimensions and its derivative known at compile
 // time: the T-step loop is part of every computeControl, so the per-step switch / allocation overhead of the generic
 // entry points is kept out of it
+// Dynamics::updateState (dynamics.cuh:277-281) and the one override in tree: QuadrotorDynamics renormalises the
+// quaternion after the Euler step (quadrotor_dynamics.cu:114-122)
+static inline void update_state(int dyn_id, int S, const float* x, const float* xd, float dt, float* xn)
+{
+  for (int i = 0; i < S; i++)
+    xn[i] = x[i] + xd[i] * dt;
+  if (dyn_id == MPPIB_DYN_QUADROTOR)
+  {
+    float* q = xn + 6;
+    const float norm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float div = (float)((double)norm * copysign(1.0, (double)q[0]));
+    for (int i = 0; i < 4; i++)
+      q[i] /= div;
+  }
+}
+
 template <int DYN_ID, int S, int C, int O>
 static int output_trajectory_impl(const void* dyn_params, const FnnT* nn, const mppib_control_limits& lim, const float* x0,
                                   const float* u, int T, float dt, float* states, float* outputs)
@@ -377,8 +416,7 @@ static int output_trajectory_impl(const void* dyn_params, const FnnT* nn, const 
     const int rc = state_deriv(DYN_ID, dyn_params, nn, x, ui, xd);  // constant id: the switch folds away
     if (rc)
       return rc;
-    for (int i = 0; i < S; i++)
-      xn[i] = x[i] + xd[i] * dt;  // dynamics.cuh:277-281
+    update_state(DYN_ID, S, x, xd, dt, xn);
     for (int i = 0; i < O && i < S; i++)
       y[i] = xn[i];  // dynamics.cuh:292-300
     memcpy(states + (size_t)(t + 1) * S, xn, sizeof(float) * S);
@@ -407,6 +445,9 @@ int mppib_host_dims(int dyn_id, int* S, int* C, int* O)
       break;
     case MPPIB_DYN_RACER_LSTM:
       s = 19, c = 2, o = 28;
+      break;
+    case MPPIB_DYN_QUADROTOR:
+      s = 13, c = 4, o = 13;
       break;
     default:
       return MPPIB_ERR_UNSUPPORTED;
@@ -440,8 +481,7 @@ static int host_step_impl(int dyn_id, const void* dyn_params, const FnnT* nn, co
   int rc = state_deriv(dyn_id, dyn_params, nn, x, u, xdot);
   if (rc)
     return rc;
-  for (int i = 0; i < S; i++)
-    x_next[i] = x[i] + xdot[i] * dt;  // dynamics.cuh:277-281
+  update_state(dyn_id, S, x, xdot, dt, x_next);
   for (int i = 0; i < O && i < S; i++)
     y[i] = x_next[i];  // dynamics.cuh:292-300
   return MPPIB_OK;
@@ -520,6 +560,9 @@ int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float
       return output_trajectory_impl<MPPIB_DYN_AUTORALLY_NN, 7, 2, 8>(dyn_params, &nn, *limits_of(dyn_id, dyn_params), x0,
                                                                     u, T, dt, states, outputs);
     }
+    case MPPIB_DYN_QUADROTOR:
+      return output_trajectory_impl<MPPIB_DYN_QUADROTOR, 13, 4, 13>(dyn_params, nullptr, *limits_of(dyn_id, dyn_params), x0,
+                                                                   u, T, dt, states, outputs);
   }
   return MPPIB_ERR_UNSUPPORTED;
 }

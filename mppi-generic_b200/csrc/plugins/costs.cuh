@@ -236,5 +236,77 @@ struct RacerQuadraticCost : public Cost<RacerQuadraticCost, mppib_racer_quadrati
   }
 };
 
+// cost_functions/quadrotor/quadrotor_quadratic_cost.cu:70-132 (device body) with the float-array quaternion helpers of
+// utils/math_utils.h:166-211 (QuatInv / QuatMultiply normalised with rsqrtf) and :263-270 (Quat2EulerNWU).
+// The reference's NaN guard `sum * (1 - isnan(sum)) + isnan(sum) * MAX_COST_VALUE` evaluates to NaN for a NaN sum
+// (NaN * 0), exactly like the unguarded host body, so it is not restated: a NaN cost stays NaN on both sides.
+struct QuadrotorQuadraticCost : public Cost<QuadrotorQuadraticCost, mppib_quadrotor_cost_params>
+{
+  __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux&, const float*, const float* s, int,
+                                                           int*)
+  {
+    float s_diff[13];
+#pragma unroll
+    for (int i = 0; i < 13; i++)
+    {
+      const float d = s[i] - p.s_goal[i];
+      s_diff[i] = d * d;  // powf(x, 2)
+    }
+    // QuatSubtract(s + 6, s_goal + 6): q_goal * inverse(q), normalised
+    const float* q = s + 6;
+    const float* g = p.s_goal + 6;
+    const float inv_norm = rsqrtf(MPPIB_SQ(q[0]) + MPPIB_SQ(q[1]) + MPPIB_SQ(q[2]) + MPPIB_SQ(q[3]));
+    const float a0 = q[0] * inv_norm, a1 = -q[1] * inv_norm, a2 = -q[2] * inv_norm, a3 = -q[3] * inv_norm;
+    float d[4];
+    d[0] = g[0] * a0 - g[1] * a1 - g[2] * a2 - g[3] * a3;
+    d[1] = g[1] * a0 + g[0] * a1 - g[3] * a2 + g[2] * a3;
+    d[2] = g[2] * a0 + g[3] * a1 + g[0] * a2 - g[1] * a3;
+    d[3] = g[3] * a0 - g[2] * a1 + g[1] * a2 + g[0] * a3;
+    const float dn = rsqrtf(MPPIB_SQ(d[0]) + MPPIB_SQ(d[1]) + MPPIB_SQ(d[2]) + MPPIB_SQ(d[3]));
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      d[i] *= dn;
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      s_diff[i] *= p.x_coeff;
+#pragma unroll
+    for (int i = 3; i < 6; i++)
+      s_diff[i] *= p.v_coeff;
+    if (!p.use_euler)
+    {
+#pragma unroll
+      for (int i = 6; i < 10; i++)
+        s_diff[i] = p.q_coeff * d[i - 6];
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 6; i < 10; i++)
+        s_diff[i] = 0.0f;
+      const float r_diff = atan2f(2.0f * d[3] * d[2] + 2.0f * d[0] * d[1],
+                                  d[0] * d[0] + d[3] * d[3] - d[2] * d[2] - d[1] * d[1]);
+      const float temp = -2.0f * d[0] * d[2] + 2.0f * d[1] * d[3];
+      const float p_diff = -asinf(fmaxf(fminf(1.0f, temp), -1.0f));
+      const float y_diff = atan2f(2.0f * d[2] * d[1] + 2.0f * d[3] * d[0],
+                                  d[0] * d[0] + d[1] * d[1] - d[2] * d[2] - d[3] * d[3]);
+      sum += p.roll_coeff * MPPIB_SQ(r_diff);
+      sum += p.pitch_coeff * MPPIB_SQ(p_diff);
+      sum += p.yaw_coeff * MPPIB_SQ(y_diff);
+    }
+#pragma unroll
+    for (int i = 10; i < 13; i++)
+      s_diff[i] *= p.w_coeff;
+#pragma unroll
+    for (int i = 0; i < 13; i++)
+      sum += s_diff[i];
+    return sum;
+  }
+  __device__ static __forceinline__ float terminalCost(const Params& p, const Aux& a, const float* s)
+  {
+    return p.terminal_cost_coeff * computeStateCost(p, a, nullptr, s, 0, nullptr);
+  }
+};
+
 }  // namespace plugins
 }  // namespace mppib

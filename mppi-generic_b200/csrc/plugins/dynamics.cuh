@@ -932,5 +932,51 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
   }
 };
 
+// ---- Quadrotor: dynamics/quadrotor/quadrotor_dynamics.cu:124-179 (device computeDynamics + updateState) with
+//      Quat2DCM / omega2edot of utils/math_utils.h:272-283,534-540 ------------------------------------------------------
+// The only in-tree model with CONTROL_DIM = 4: one 16-byte noise group is one time step (rollout_kernel.cuh).
+struct QuadrotorDynamics : public Dynamics<QuadrotorDynamics, mppib_quadrotor_dyn_params, 13, 4, 13>
+{
+  __device__ static __forceinline__ void computeDynamics(const Params& p, const float*, const float* state,
+                                                         const float* control, float* state_der)
+  {
+    const float* v = state + 3;
+    const float* q = state + 6;
+    const float* w = state + 10;
+    const float u_thrust = control[3];
+    // third column of Quat2DCM
+    const float dcm02 = 2 * (q[1] * q[3] + q[0] * q[2]);
+    const float dcm12 = 2 * (q[2] * q[3] - q[0] * q[1]);
+    const float dcm22 = MPPIB_SQ(q[0]) - MPPIB_SQ(q[1]) - MPPIB_SQ(q[2]) + MPPIB_SQ(q[3]);
+    const float accel = u_thrust * rcp_nr(p.mass);  // u_thrust / mass
+    state_der[0] = v[0];
+    state_der[1] = v[1];
+    state_der[2] = v[2];
+    state_der[3] = accel * dcm02;
+    state_der[4] = accel * dcm12;
+    state_der[5] = accel * dcm22 - MPPIB_GRAVITY;
+    state_der[6] = 0.5f * (-w[0] * q[1] - w[1] * q[2] - w[2] * q[3]);
+    state_der[7] = 0.5f * (w[0] * q[0] - w[1] * q[3] + w[2] * q[2]);
+    state_der[8] = 0.5f * (w[0] * q[3] + w[1] * q[0] - w[2] * q[1]);
+    state_der[9] = 0.5f * (-w[0] * q[2] + w[1] * q[1] + w[2] * q[0]);
+    state_der[10] = (control[0] - w[0]) * rcp_nr(p.tau_roll);
+    state_der[11] = (control[1] - w[1]) * rcp_nr(p.tau_pitch);
+    state_der[12] = (control[2] - w[2]) * rcp_nr(p.tau_yaw);
+  }
+  // quadrotor_dynamics.cu:168-179: Euler step, then q /= |q| * copysignf(1, q_w)
+  __device__ static __forceinline__ void updateState(const float* x, float* x_next, const float* xdot, float dt)
+  {
+#pragma unroll
+    for (int i = 0; i < 13; i++)
+      x_next[i] = x[i] + xdot[i] * dt;
+    float* q = x_next + 6;
+    const float q_norm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float inv = rcp_nr(q_norm * copysignf(1.0f, q[0]));
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      q[i] *= inv;
+  }
+};
+
 }  // namespace plugins
 }  // namespace mppib

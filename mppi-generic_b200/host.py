@@ -25,8 +25,8 @@ MAX_D = 2  # MPPIB_MAX_DISTRIBUTIONS
 FLT_MAX = 3.4028234663852886e38
 
 # plugin ids (include/mppi_b200/params.h)
-DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM = 0, 1, 2, 3
-COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC = 0, 1, 2, 3
+DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM, DYN_QUADROTOR = 0, 1, 2, 3, 4
+COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC, COST_QUADROTOR_QUADRATIC = 0, 1, 2, 3, 4
 SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
 BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR, FLAG_RMPPI = 1, 2, 4, 8, 16, 32
@@ -82,6 +82,18 @@ class DIDynParams(C.Structure):
 
 class ARNNDynParams(C.Structure):
     _fields_ = [("lim", ControlLimits)]
+
+
+class QuadrotorDynParams(C.Structure):
+    _fields_ = [("lim", ControlLimits), ("tau_roll", C.c_float), ("tau_pitch", C.c_float), ("tau_yaw", C.c_float),
+                ("mass", C.c_float)]
+
+
+class QuadrotorCostParams(C.Structure):
+    _fields_ = [("control_cost_coeff", C.c_float * MAX_C), ("discount", C.c_float), ("s_goal", C.c_float * 13),
+                ("x_coeff", C.c_float), ("v_coeff", C.c_float), ("use_euler", C.c_int), ("q_coeff", C.c_float),
+                ("roll_coeff", C.c_float), ("pitch_coeff", C.c_float), ("yaw_coeff", C.c_float),
+                ("w_coeff", C.c_float), ("terminal_cost_coeff", C.c_float)]
 
 
 class RacerLSTMDynParams(C.Structure):
@@ -332,6 +344,30 @@ class DoubleIntegratorDynamics(_Dynamics):
         self.params.system_noise = system_noise
 
 
+class QuadrotorDynamics(_Dynamics):
+    """dynamics/quadrotor/quadrotor_dynamics.cuh:69-… — QuadrotorDynamics() / QuadrotorDynamics(control_rngs).
+    State POS(3) VEL(3) QUAT_W..Z ANG_VEL(3); controls ANG_RATE_X/Y/Z, THRUST."""
+    DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_QUADROTOR, 13, 4, 13
+    GRAVITY = 9.81  # utils/math_utils.h:45
+
+    def __init__(self, control_rngs: Optional[Sequence[Sequence[float]]] = None, mass: float = 1.0):
+        super().__init__()
+        self.params = QuadrotorDynParams()
+        self.params.lim.set_defaults()
+        self.params.tau_roll = self.params.tau_pitch = self.params.tau_yaw = 0.25
+        self.params.mass = mass
+        if control_rngs is not None:  # quadrotor_dynamics.cu:4-9
+            self.setControlRanges(control_rngs)
+        else:  # quadrotor_dynamics.cu:11-19: thrust in [0, 36]
+            self.params.lim.rng_lo[3], self.params.lim.rng_hi[3] = 0.0, 36.0
+        self.params.lim.zero_control[3] = self.GRAVITY
+
+    def getZeroState(self) -> np.ndarray:  # quadrotor_dynamics.cu:200-205
+        z = np.zeros(self.STATE_DIM, dtype=np.float32)
+        z[6] = 1.0
+        return z
+
+
 class NeuralNetModel(_Dynamics):
     """dynamics/autorally/ar_nn_model.cuh — NeuralNetModel<7,2,3>(control_rngs); 6-32-32-4 tanh network."""
     DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_AUTORALLY_NN, 7, 2, 8
@@ -541,6 +577,26 @@ class ARStandardCost(_Cost):
         R[2, 2] = 1.0
         trs = [-x_min / (x_max - x_min), -y_min / (y_max - y_min), 1.0]
         self.updateTransform(R, trs)
+
+
+class QuadrotorQuadraticCost(_Cost):
+    """cost_functions/quadrotor/quadrotor_quadratic_cost.cuh:9-66 (defaults reproduced)."""
+    COST_ID = COST_QUADROTOR_QUADRATIC
+
+    def __init__(self):
+        super().__init__()
+        p = QuadrotorCostParams()
+        for i in range(MAX_C):
+            p.control_cost_coeff[i] = 2.0
+        p.discount = 1.0
+        p.s_goal[:] = [0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+        p.x_coeff = p.v_coeff = p.q_coeff = p.roll_coeff = p.pitch_coeff = p.yaw_coeff = p.w_coeff = 1.0
+        p.use_euler = 1
+        p.terminal_cost_coeff = 0.0
+        self.params = p
+
+    def getDesiredState(self) -> np.ndarray:
+        return np.array(list(self.params.s_goal), dtype=np.float32)
 
 
 class RacerQuadraticCost(_Cost):

@@ -168,6 +168,24 @@ def racer_lstm_gaussian(N: int = 4096, T: int = 100) -> Workload:
     return racer_lstm(N, T, colored=False)
 
 
+def quadrotor(N: int = 8192, T: int = 100) -> Workload:
+    """Quadrotor + quadratic cost, VanillaMPPI (instantiations/quadrotor_mppi/quadrotor_mppi.cuh): fly from the origin
+    to a goal 4 m away and 2 m up, hovering there. The only CONTROL_DIM = 4 pair (one 16-byte noise group per step)."""
+    dyn = H.QuadrotorDynamics()
+    dyn.setControlRanges([(-3.0, 3.0), (-3.0, 3.0), (-3.0, 3.0), (0.0, 36.0)])
+    cost = H.QuadrotorQuadraticCost()
+    p = cost.params
+    p.s_goal[0], p.s_goal[1], p.s_goal[2] = 4.0, 1.0, 2.0
+    p.x_coeff, p.v_coeff, p.w_coeff = 10.0, 1.0, 0.5
+    p.roll_coeff = p.pitch_coeff = p.yaw_coeff = 5.0
+    sampler = H.GaussianDistribution(4, [0.5, 0.5, 0.5, 2.0])
+    sampler.setControlCostCoeff([0.1, 0.1, 0.1, 0.01])
+    x0 = dyn.getZeroState()[None, :].copy()
+    U0 = np.zeros((1, T, 4), np.float32)
+    U0[..., 3] = dyn.GRAVITY  # hover thrust (zero_control_[3])
+    return Workload(f"quadrotor_vanilla_N{N}_T{T}", "vanilla", dyn, cost, sampler, N, T, 1, 0.02, 1.0, 0.0, x0, U0)
+
+
 BUILDERS = {
     "racer_lstm": racer_lstm,
     "racer_lstm_gaussian": racer_lstm_gaussian,
@@ -175,6 +193,7 @@ BUILDERS = {
     "double_integrator_tube": double_integrator_tube,
     "double_integrator_vanilla": double_integrator_vanilla,
     "autorally": autorally,
+    "quadrotor": quadrotor,
 }
 
 

@@ -473,6 +473,60 @@ struct RacerLSTM
   }
 };
 
+// QuadrotorDynamics, host path: dynamics/quadrotor/quadrotor_dynamics.cu:70-112 (computeDynamics, Eigen) and :114-122
+// (updateState: Euler step, then the quaternion divided by norm * copysign(1, q.w)). Quat2DCM(Eigen) is
+// Eigen::Quaternionf::toRotationMatrix (utils/math_utils.h:529-532); Eigen is a system dependency of the reference
+// (CMakeLists.txt find_package(Eigen3)), absent from /root/reference, so its published column-2 formulas
+// (Eigen/src/Geometry/Quaternion.h, QuaternionBase::toRotationMatrix) are restated here.
+struct Quadrotor
+{
+  static constexpr int S = 13, C = 4, O = 13;
+  static constexpr bool CUSTOM_STEP = true;
+  typedef mppib_quadrotor_dyn_params P;
+  typedef NoCarry Carry;
+  static void initCarry(const Aux&, Carry&)
+  {
+  }
+  static void computeStateDeriv(const P& p, const Aux&, const float* state, const float* control, float* state_der)
+  {
+    const float u_thrust = control[3];
+    const float qw = state[6], qx = state[7], qy = state[8], qz = state[9];
+    // toRotationMatrix, column 2
+    const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+    const float twx = tx * qw, twy = ty * qw;
+    const float txx = tx * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy;
+    const float col2[3] = { txz + twy, tyz - twx, 1.0f - (txx + tyy) };
+    const float tau_inv[3] = { 1 / p.tau_roll, 1 / p.tau_pitch, 1 / p.tau_yaw };
+    for (int i = 0; i < 3; i++)
+      state_der[i] = state[3 + i];
+    for (int i = 0; i < 3; i++)
+      state_der[3 + i] = (u_thrust / p.mass) * col2[i];
+    state_der[5] -= MPPIB_GRAVITY;
+    // omega2edot (utils/math_utils.h:543-549)
+    const float pp = state[10], qq = state[11], rr = state[12];
+    state_der[6] = 0.5f * (-pp * qx - qq * qy - rr * qz);
+    state_der[7] = 0.5f * (pp * qw - qq * qz + rr * qy);
+    state_der[8] = 0.5f * (pp * qz + qq * qw - rr * qx);
+    state_der[9] = 0.5f * (-pp * qy + qq * qx + rr * qw);
+    for (int i = 0; i < 3; i++)
+      state_der[10 + i] = tau_inv[i] * (control[i] - state[10 + i]);
+  }
+  static void step(const P& p, const Aux& aux, Carry&, const float* state, float* next_state, float* state_der,
+                   const float* control, float* output, float dt)
+  {
+    computeStateDeriv(p, aux, state, control, state_der);
+    for (int i = 0; i < S; i++)
+      next_state[i] = state[i] + state_der[i] * dt;
+    const float* q = next_state + 6;
+    const float norm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float div = (float)((double)norm * copysign(1.0, (double)q[0]));  // Eigen `/=` takes a float Scalar
+    for (int i = 6; i < 10; i++)
+      next_state[i] /= div;
+    for (int i = 0; i < O; i++)
+      output[i] = next_state[i];
+  }
+};
+
 template <class T, class = void>
 struct has_custom_step : std::false_type
 {
@@ -666,6 +720,62 @@ struct RacerQuadraticCost
   }
 };
 
+// QuadrotorQuadraticCost, host path: cost_functions/quadrotor/quadrotor_quadratic_cost.cu:11-65. QuatSubtract(Eigen) is
+// q_2 * q_1.inverse() (utils/math_utils.h:285-289): Eigen's inverse = conjugate / squaredNorm and its Hamilton product,
+// not normalised. The !use_euler branch of the host code assigns a 4-vector to a Vector3f (ill-formed at run time), so for
+// that branch this oracle follows the DEVICE body (:70-126: q_coeff * q_diff[i], unsquared, with the device QuatSubtract of
+// math_utils.h:166-211); tests use the default use_euler = true.
+struct QuadrotorQuadraticCost
+{
+  typedef mppib_quadrotor_cost_params P;
+  static float computeStateCost(const P& p, const Aux&, const float* s, int, int*)
+  {
+    float x_cost = 0, v_cost = 0, w_cost = 0, q_cost = 0;
+    for (int i = 0; i < 3; i++)
+    {
+      x_cost += p.x_coeff * ((s[i] - p.s_goal[i]) * (s[i] - p.s_goal[i]));
+      v_cost += p.v_coeff * ((s[3 + i] - p.s_goal[3 + i]) * (s[3 + i] - p.s_goal[3 + i]));
+      w_cost += p.w_coeff * ((s[10 + i] - p.s_goal[10 + i]) * (s[10 + i] - p.s_goal[10 + i]));
+    }
+    const float* q = s + 6;
+    const float* g = p.s_goal + 6;
+    if (p.use_euler)
+    {
+      const float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+      const float iw = q[0] / n2, ix = -q[1] / n2, iy = -q[2] / n2, iz = -q[3] / n2;
+      // q_diff = q_g * q^-1
+      const float dw = g[0] * iw - g[1] * ix - g[2] * iy - g[3] * iz;
+      const float dx = g[0] * ix + g[1] * iw + g[2] * iz - g[3] * iy;
+      const float dy = g[0] * iy + g[2] * iw + g[3] * ix - g[1] * iz;
+      const float dz = g[0] * iz + g[3] * iw + g[1] * iy - g[2] * ix;
+      // Quat2EulerNWU (utils/math_utils.h:519-527)
+      const float r = atan2f(2.0f * dz * dy + 2.0f * dw * dx, dw * dw + dz * dz - dy * dy - dx * dx);
+      const float temp = -2.0f * dw * dy + 2.0f * dx * dz;
+      const float pi = -asinf(fmaxf(-1.0f, fminf(temp, 1.0f)));
+      const float y = atan2f(2.0f * dy * dx + 2.0f * dz * dw, dw * dw + dx * dx - dy * dy - dz * dz);
+      q_cost = p.roll_coeff * (r * r) + p.pitch_coeff * (pi * pi) + p.yaw_coeff * (y * y);
+    }
+    else
+    {
+      const float inv_norm = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      const float a[4] = { q[0] * inv_norm, -q[1] * inv_norm, -q[2] * inv_norm, -q[3] * inv_norm };
+      float d[4];
+      d[0] = g[0] * a[0] - g[1] * a[1] - g[2] * a[2] - g[3] * a[3];
+      d[1] = g[1] * a[0] + g[0] * a[1] - g[3] * a[2] + g[2] * a[3];
+      d[2] = g[2] * a[0] + g[3] * a[1] + g[0] * a[2] - g[1] * a[3];
+      d[3] = g[3] * a[0] - g[2] * a[1] + g[1] * a[2] + g[0] * a[3];
+      const float dn = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+      for (int i = 0; i < 4; i++)
+        q_cost += p.q_coeff * (d[i] * dn);
+    }
+    return x_cost + v_cost + q_cost + w_cost;
+  }
+  static float terminalCost(const P& p, const Aux& a, const float* s)
+  {
+    return p.terminal_cost_coeff * computeStateCost(p, a, s, 0, nullptr);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Sampler semantics.
 // sampling_distributions/gaussian/gaussian.cu:17-277 (setGaussianControls), applied in place on raw eps.
@@ -787,6 +897,8 @@ static rollout_fn pick_rollout(int dyn_id, int cost_id)
     return &rollout<AutorallyNN, ARStandardCost>;
   if (dyn_id == MPPIB_DYN_RACER_LSTM && cost_id == MPPIB_COST_RACER_QUADRATIC)
     return &rollout<RacerLSTM, RacerQuadraticCost>;
+  if (dyn_id == MPPIB_DYN_QUADROTOR && cost_id == MPPIB_COST_QUADROTOR_QUADRATIC)
+    return &rollout<Quadrotor, QuadrotorQuadraticCost>;
   return nullptr;
 }
 
@@ -805,6 +917,9 @@ static void dims(int dyn_id, int* S, int* C, int* O)
       break;
     case MPPIB_DYN_RACER_LSTM:
       *S = 19, *C = 2, *O = 28;
+      break;
+    case MPPIB_DYN_QUADROTOR:
+      *S = 13, *C = 4, *O = 13;
       break;
     default:
       *S = *C = *O = 0;
@@ -1300,6 +1415,8 @@ int orc_rmppi_rollout(int dyn_id, int cost_id, const void* dyn_params, const voi
     f = &orc::rmppiRollout<orc::DoubleIntegrator, orc::DICircleCost>;
   else if (dyn_id == MPPIB_DYN_AUTORALLY_NN && cost_id == MPPIB_COST_AR_STANDARD)
     f = &orc::rmppiRollout<orc::AutorallyNN, orc::ARStandardCost>;
+  else if (dyn_id == MPPIB_DYN_QUADROTOR && cost_id == MPPIB_COST_QUADROTOR_QUADRATIC)
+    f = &orc::rmppiRollout<orc::Quadrotor, orc::QuadrotorQuadraticCost>;
   if (!f)
     return -1;
   if (nthreads <= 1)
@@ -1343,6 +1460,10 @@ int orc_init_eval(int dyn_id, int cost_id, const void* dyn_params, const void* c
     orc::initEval<orc::AutorallyNN, orc::ARStandardCost>(dyn_params, cost_params, *sp, aux, N_sampler, T, dt, lambda, alpha,
                                                          num_candidates, num_samples, candidates, strides, means,
                                                          controls, costs);
+  else if (dyn_id == MPPIB_DYN_QUADROTOR && cost_id == MPPIB_COST_QUADROTOR_QUADRATIC)
+    orc::initEval<orc::Quadrotor, orc::QuadrotorQuadraticCost>(dyn_params, cost_params, *sp, aux, N_sampler, T, dt, lambda,
+                                                               alpha, num_candidates, num_samples, candidates, strides,
+                                                               means, controls, costs);
   else
     return -1;
   return 0;
@@ -1518,6 +1639,12 @@ int orc_dyn_step(int dyn_id, const void* dyn_params, const float* nn_theta, cons
     case MPPIB_DYN_AUTORALLY_NN:
       orc::dyn_step<orc::AutorallyNN>(*(const mppib_ar_nn_dyn_params*)dyn_params, aux, x, x_next, xdot, u, y, dt);
       return 0;
+    case MPPIB_DYN_QUADROTOR:
+    {
+      orc::NoCarry k;
+      orc::dyn_step<orc::Quadrotor>(*(const mppib_quadrotor_dyn_params*)dyn_params, aux, x, x_next, xdot, u, y, dt, &k);
+      return 0;
+    }
   }
   return -1;
 }
@@ -1548,6 +1675,11 @@ int orc_state_cost(int cost_id, const void* cost_params, const float* costmap, c
       *cost_out = orc::RacerQuadraticCost::computeStateCost(*(const mppib_racer_quadratic_cost_params*)cost_params,
                                                             aux, y, t, crash);
       *terminal_out = 0;
+      return 0;
+    case MPPIB_COST_QUADROTOR_QUADRATIC:
+      *cost_out = orc::QuadrotorQuadraticCost::computeStateCost(*(const mppib_quadrotor_cost_params*)cost_params, aux, y, t,
+                                                                crash);
+      *terminal_out = orc::QuadrotorQuadraticCost::terminalCost(*(const mppib_quadrotor_cost_params*)cost_params, aux, y);
       return 0;
   }
   return -1;
@@ -1597,6 +1729,9 @@ int orc_output_trajectory(int dyn_id, const void* dyn_params, const float* nn_th
     case MPPIB_DYN_RACER_LSTM:
       fill_lstm(aux);
       orc::outputTrajectory<orc::RacerLSTM>(dyn_params, aux, x0, u, T, dt, states, outputs);
+      return 0;
+    case MPPIB_DYN_QUADROTOR:
+      orc::outputTrajectory<orc::Quadrotor>(dyn_params, aux, x0, u, T, dt, states, outputs);
       return 0;
   }
   return -1;

@@ -60,3 +60,31 @@ def test_racer_colored_example_tracks_speed_on_the_gpu():
     p = subprocess.run([RACER_EXE], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "speed after 80 steps" in p.stdout
+
+
+QUAD_EXE = os.path.join(ROOT, "tests", "cpp", "quadrotor_example.bin")
+
+
+def _build_quad():
+    lib_dir = os.path.join(ROOT, "mppi-generic_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-variable", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "quadrotor_example.cpp"), "-o", QUAD_EXE, "-L", lib_dir,
+                           "-lmppi_b200", "-Wl,-rpath," + lib_dir])
+
+
+def test_quadrotor_example_compiles_against_reference_include_paths():
+    """Quadrotor pair through the C++ layer via instantiations/quadrotor_mppi/quadrotor_mppi.cuh."""
+    _build_quad()
+    p = subprocess.run([QUAD_EXE], capture_output=True, text=True, timeout=600)
+    if p.returncode == 5:
+        assert "no CUDA device" in p.stdout
+    else:
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_quadrotor_example_flies_to_the_goal_on_the_gpu():
+    _build_quad()
+    p = subprocess.run([QUAD_EXE], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "distance to goal after 250 steps" in p.stdout

@@ -805,3 +805,96 @@ def test_tsallis_needs_the_writeback_buffer():
     with pytest.raises(H.MppibError):
         e.set_tsallis(1.0, 2.0)
     e.close()
+
+
+# ---- Quadrotor: CONTROL_DIM = 4 -> one 16-byte noise group per time step --------------------------------
+def _quadrotor_case(N, T, D=1, seed=5):
+    w = W.quadrotor(N, T)
+    rng = np.random.RandomState(seed)
+    x0 = np.tile(w.x0, (D, 1))
+    for d in range(D):
+        x0[d, :6] += 0.3 * rng.randn(6)
+        q = np.array([1.0, 0, 0, 0]) + 0.2 * rng.randn(4)
+        x0[d, 6:10] = q / np.linalg.norm(q)
+        x0[d, 10:] = 0.2 * rng.randn(3)
+    w.x0 = x0.astype(np.float32)
+    U0 = np.tile(w.U0, (D, 1, 1))
+    U0[..., :3] += 0.3 * rng.randn(D, T, 3)
+    U0[..., 3] += rng.randn(D, T)
+    w.U0 = U0.astype(np.float32)
+    w.D = D
+    w.alpha = 0.2
+    if D == 2:
+        w.controller = "tube"
+        w.sampler.setStdDev([0.4, 0.6, 0.5, 1.5], 1)
+    return w
+
+
+@pytest.mark.parametrize("flags", [0, H.FLAG_NO_TMA])
+@pytest.mark.parametrize("N,T", [(2048, 64), (1000, 37), (129, 16)])
+def test_quadrotor_solve_parity(N, T, flags):
+    """QuadrotorDynamics + QuadrotorQuadraticCost (dynamics/quadrotor/quadrotor_dynamics.cu:124-179,
+    cost_functions/quadrotor/quadrotor_quadratic_cost.cu:70-132). Device quaternion helpers use rsqrtf and the device
+    atan2f / asinf; the reference compares its own CPU and GPU bodies with eigen_assert_float_eq per step
+    (tests/dynamics/quadrotor_dynamics_tests.cu:25-137); trajectory costs are held to the usual 1e-4 relative."""
+    w = _quadrotor_case(N, T)
+    e = w.make_engine(flags=flags)
+    assert e.launch_info()["uses_tma"] == (flags == 0)
+    _check_solve(w, e)
+    _check_solve(w, e, stride=3)
+    e.close()
+
+
+def test_quadrotor_two_systems_and_thrust_limits():
+    """Tube-style D = 2 launch of the C = 4 pair, with the thrust range biting: controls outside [0, 36] are clamped
+    before the dynamics, the cost and the weighted average."""
+    w = _quadrotor_case(2048, 48, D=2)
+    w.dyn.setControlRanges([(-1.0, 1.0), (-1.0, 1.0), (-1.0, 1.0), (8.0, 11.0)])
+    e = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    U, _, _ = _check_solve(w, e)
+    s = e.get_samples()
+    assert s[..., 3].min() >= 8.0 and s[..., 3].max() <= 11.0 and np.abs(s[..., :3]).max() <= 1.0
+    assert (s[..., 3] == 8.0).any() and (s[..., 3] == 11.0).any()
+    e.close()
+
+
+def test_quadrotor_rmppi_rollout_matches_oracle():
+    """RMPPI mode of the C = 4 pair: feedback gains [t][13][4] act on the real system."""
+    N, T = 1024, 40
+    w = _quadrotor_case(N, T, D=2)
+    w.sampler.setStdDev([0.5, 0.5, 0.5, 2.0], 1)
+    e = H.Engine(w.dyn, w.cost, w.sampler, N, T, 2, flags=H.FLAG_RMPPI)
+    e.set_solver(w.dt, w.lambda_, 0.1)
+    e.seed(9, 0)
+    gains = (np.random.RandomState(1).randn(T, 13, 4) * 0.05).astype(np.float32)
+    thr = 50.0
+    e.set_rmppi(thr, gains)
+    U_in = np.stack([w.U0[0], w.U0[0]])
+    U, stats = e.solve(w.x0, U_in, 1, 0)
+    eps = e.get_noise()
+    samples = np.stack([eps, eps]).copy()
+    oracle.set_gaussian_controls(U_in, w.sampler.params, samples, 4, T, N, 2, 1, 0)
+    ref = oracle.rmppi_rollout(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, None, None,
+                               N, T, w.dt, w.lambda_, 0.1, thr, w.x0, U_in, gains, samples, nthreads=8)
+    np.testing.assert_allclose(e.get_costs(), ref, rtol=1e-4, atol=1e-5)
+    applied = e.get_samples()
+    np.testing.assert_allclose(applied, samples, rtol=1e-5, atol=4e-6)
+    assert np.abs(applied[1] - applied[0]).max() > 1e-3
+    e.close()
+
+
+def test_quadrotor_controller_flies_to_the_goal():
+    """Closed loop through the mirrored VanillaMPPIController: from rest at the origin to hover near (4, 1, 2)."""
+    w = W.quadrotor(4096, 75)
+    ctrl = H.VanillaMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N,
+                                   init_control_traj=w.U0[0], seed=3)
+    x = w.x0[0].copy()
+    goal = np.array(list(w.cost.params.s_goal[:3]), np.float32)
+    for it in range(250):
+        ctrl.computeControl(x, 1)
+        u = ctrl.getControlSeq()[0].copy()
+        x, _, _ = w.dyn.step(x, u, w.dt)
+        ctrl.slideControlSequence(1)
+    assert np.linalg.norm(x[:3] - goal) < 0.5
+    assert abs(np.linalg.norm(x[6:10]) - 1) < 1e-5
+    assert ctrl.getTargetStateSeq().shape == (w.T, 13)

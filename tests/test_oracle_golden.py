@@ -456,3 +456,117 @@ def test_rmppi_oracle_reduces_to_plain_rollout_without_feedback():
     tracking_real = c_state[1]  # zero gains: tracking cost = state cost + 0 feedback cost
     expect = 0.5 * c_state[0] + 0.5 * np.maximum(np.minimum(tracking_real, thr), c_state[0]) + lr_nom
     np.testing.assert_allclose(c[0], expect, rtol=2e-5, atol=1e-5)
+
+
+# ---- Quadrotor (the CONTROL_DIM = 4 pair) -----------------------------------------------------------
+def _rand_quad_state(rng):
+    s = rng.randn(13).astype(np.float32)
+    s[6:10] /= np.linalg.norm(s[6:10])
+    return s
+
+
+def test_quadrotor_dynamics_known_answers_and_independent_formula():
+    from scipy.spatial.transform import Rotation
+    dyn = m.QuadrotorDynamics()
+    # hover: identity attitude, thrust = m g -> no acceleration; quaternion stays (1, 0, 0, 0)
+    x = dyn.getZeroState()
+    xn, xd, y = oracle.dyn_step(H.DYN_QUADROTOR, dyn.params, None, x, [0, 0, 0, 9.81], 0.01)
+    np.testing.assert_array_equal(xd, np.zeros(13, np.float32))
+    np.testing.assert_array_equal(xn, x)
+    np.testing.assert_array_equal(y, x)
+    # free fall
+    xn, xd, _ = oracle.dyn_step(H.DYN_QUADROTOR, dyn.params, None, x, [0, 0, 0, 0], 0.01)
+    assert xd[5] == np.float32(-9.81) and xn[5] == np.float32(-9.81) * np.float32(0.01)
+    # body-rate lag: w_dot = (u - w) / tau
+    xn, xd, _ = oracle.dyn_step(H.DYN_QUADROTOR, dyn.params, None, x, [1, -2, 0.5, 9.81], 0.01)
+    np.testing.assert_allclose(xd[10:], [4.0, -8.0, 2.0], rtol=1e-6)
+    # random states against an independent float64 formulation (scipy rotation matrix, quaternion kinematics
+    # q_dot = 0.5 q (x) (0, w)), quadrotor_dynamics_tests.cu:25-75 compares the same quantities CPU vs GPU
+    rng = np.random.RandomState(0)
+    dyn2 = m.QuadrotorDynamics(mass=2.5)
+    dt = 0.01
+    for _ in range(20):
+        s, u = _rand_quad_state(rng), rng.randn(4).astype(np.float32)
+        xn, xd, y = oracle.dyn_step(H.DYN_QUADROTOR, dyn2.params, None, s, u, dt)
+        w, xq, yq, zq = s[6:10].astype(np.float64)
+        R = Rotation.from_quat([xq, yq, zq, w]).as_matrix()
+        ref = np.zeros(13)
+        ref[0:3] = s[3:6]
+        ref[3:6] = (u[3] / 2.5) * R[:, 2] - np.array([0, 0, 9.81])
+        om = s[10:13].astype(np.float64)
+        ref[6] = -0.5 * np.dot([xq, yq, zq], om)
+        ref[7:10] = 0.5 * (w * om + np.cross([xq, yq, zq], om))
+        ref[10:13] = (u[:3] - s[10:13]) / 0.25
+        np.testing.assert_allclose(xd, ref, rtol=2e-5, atol=2e-6)
+        nx = s.astype(np.float64) + ref * dt
+        nx[6:10] /= np.linalg.norm(nx[6:10]) * np.copysign(1.0, nx[6])
+        np.testing.assert_allclose(xn, nx, rtol=2e-5, atol=2e-6)
+        assert xn[6] >= 0 and abs(np.linalg.norm(xn[6:10]) - 1) < 1e-6  # updateState: unit norm, w >= 0
+        np.testing.assert_array_equal(y, xn)
+    # the default constructor's thrust range and zero control (quadrotor_dynamics.cu:11-19)
+    assert (dyn.params.lim.rng_lo[3], dyn.params.lim.rng_hi[3]) == (0.0, 36.0)
+    assert dyn.zero_control_[3] == np.float32(9.81)
+
+
+def test_quadrotor_cost_known_answers():
+    from scipy.spatial.transform import Rotation
+    cost = m.QuadrotorQuadraticCost()
+    p = cost.params
+    goal = np.array(list(p.s_goal), np.float32)
+    c, term, _ = oracle.state_cost(H.COST_QUADROTOR_QUADRATIC, p, None, goal)
+    assert c == 0.0 and term == 0.0
+    # position / velocity / body-rate terms are coefficient * squared error
+    p.x_coeff, p.v_coeff, p.w_coeff = 3.0, 5.0, 7.0
+    s = goal.copy()
+    s[0], s[4], s[12] = 2.0, -1.0, 0.5
+    c, _, _ = oracle.state_cost(H.COST_QUADROTOR_QUADRATIC, p, None, s)
+    assert c == pytest.approx(3.0 * 4.0 + 5.0 * 1.0 + 7.0 * 0.25, rel=1e-6)
+    # attitude term: Euler angles of q_goal * q^-1 (quadrotor_quadratic_cost.cu:27-41); a pure yaw of +0.3 rad away from
+    # the identity goal gives yaw_coeff * 0.3^2, and roll / pitch likewise
+    p.roll_coeff, p.pitch_coeff, p.yaw_coeff = 2.0, 3.0, 4.0
+    for axis, coeff in (("x", 2.0), ("y", 3.0), ("z", 4.0)):
+        xq, yq, zq, w = Rotation.from_euler(axis, 0.3).as_quat()
+        s = goal.copy()
+        s[6:10] = [w, xq, yq, zq]
+        c, _, _ = oracle.state_cost(H.COST_QUADROTOR_QUADRATIC, p, None, s)
+        assert c == pytest.approx(coeff * 0.09, rel=1e-5)
+    p.terminal_cost_coeff = 0.5
+    c, term, _ = oracle.state_cost(H.COST_QUADROTOR_QUADRATIC, p, None, s)
+    assert term == pytest.approx(0.5 * c, rel=1e-6)
+    assert list(cost.getDesiredState()) == list(goal)
+
+
+def test_quadrotor_host_twin_matches_oracle():
+    w = W.quadrotor(64, 40)
+    rng = np.random.RandomState(3)
+    u = (rng.randn(w.T, 4) * [1, 1, 1, 3] + [0, 0, 0, 9.81]).astype(np.float32)
+    st, out = oracle.output_trajectory(w.dyn.DYN_ID, w.dyn.params, None, w.x0[0], u, w.dt)
+    st2, out2 = np.zeros_like(st), np.zeros_like(out)
+    w.dyn.output_trajectory(w.x0[0], u, w.T, w.dt, st2, out2)
+    np.testing.assert_array_equal(st2, st)
+    np.testing.assert_array_equal(out2, out)
+    assert np.all(np.abs(np.linalg.norm(st[:, 6:10], axis=1) - 1) < 1e-5)
+    xn, xd, y = w.dyn.step(st[5], u[5], w.dt)
+    u5 = oracle.enforce_constraints(w.dyn.params.lim, u[5])
+    xn2, xd2, y2 = oracle.dyn_step(w.dyn.DYN_ID, w.dyn.params, None, st[5], u[5], w.dt)
+    np.testing.assert_array_equal(xn, xn2)
+    np.testing.assert_array_equal(xd, xd2)
+    del u5
+
+
+def test_quadrotor_oracle_solve_flies_towards_the_goal():
+    # closed loop on the oracle alone: a few MPPI iterations must cut the distance to the goal
+    w = W.quadrotor(512, 50)
+    x = w.x0.copy()
+    U = w.U0.copy()
+    goal = np.array(list(w.cost.params.s_goal[:3]), np.float32)
+    d0 = np.linalg.norm(x[0, :3] - goal)
+    for it in range(40):
+        eps = oracle.curand_normal(42, it * 512 * 50 * 4, 512 * 50 * 4).reshape(512, 50, 4)
+        r = oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, None, None, 512, 50,
+                         1, 4, w.dt, w.lambda_, w.alpha, x, U, eps)
+        U = r["U"]
+        u0 = oracle.enforce_constraints(w.dyn.params.lim, U[0, 0])
+        x[0], _, _ = oracle.dyn_step(w.dyn.DYN_ID, w.dyn.params, None, x[0], u0, w.dt)
+        U[0, :-1] = U[0, 1:]
+    assert np.linalg.norm(x[0, :3] - goal) < 0.85 * d0  # 0.8 s of flight: 4.58 m -> 3.67 m, climbing and pitching over
