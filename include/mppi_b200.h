@@ -215,6 +215,22 @@ int mppib_set_rmppi(mppib_engine* e, float value_func_threshold, const float* fe
 int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides, int num_candidates,
                     int samples_per_candidate, const float* U_nominal, int optimization_stride, float* costs_out);
 
+/* ---- sampled (visualisation) trajectories ---------------------------------------------------------------------- */
+/* VanillaMPPIController::calculateSampledStateTrajectories (controllers/MPPI/mppi_controller.cu:262-298) /
+ * launchVisualizeKernel (core/mppi_common.cu:364-520, 1376-1420): after a solve, re-rolls the rollouts the host picked
+ * (controllers/controller.cu:55-179: the optimised sequence, a random subset, the top-n by weight) and returns every
+ * step's output, cost and crash flag. Needs MPPIB_FLAG_WRITEBACK_CONTROLS (the constrained controls of the last solve
+ * are the input) and no solve in flight; not available on RMPPI engines.
+ *   x0 [S], U_nominal [T][C]   what that solve was called with, for system `distribution`
+ *   sample_idx [n]             rank-local rollout indices in [0, n_local), or -1 = roll out U_opt [T][C]
+ *                              (the optimised sequence; control constraints are applied to it)
+ *   outputs [n][T][O]          y after step t (the reference keeps the first T - 1 rows)
+ *   costs   [n][T + 1]         [t] = (state cost + likelihood-ratio cost of step t) / T, [T] = terminal cost / T: a row
+ *                              of a stored rollout sums to its trajectory cost (mppib_get_costs)
+ *   crash   [n][T]             the sticky crash flag after step t */
+int mppib_sample_trajectories(mppib_engine* e, const float* x0, const float* U_nominal, int distribution,
+                              const int* sample_idx, int n, const float* U_opt, float* outputs, float* costs, int* crash);
+
 const char* mppib_strerror(int status);
 const char* mppib_last_error(void); /* thread-local text of the last failure */
 int mppib_version(void);

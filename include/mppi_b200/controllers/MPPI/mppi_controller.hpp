@@ -49,12 +49,16 @@ public:
   {
     this->free_energy_statistics_.real_sys.previousBaseline = this->getBaselineCost();
     state_array x0 = state;
+    control_trajectory u_nominal = this->control_;
     for (int opt_iter = 0; opt_iter < this->getNumIters(); opt_iter++)
     {
       control_trajectory u_out = control_trajectory::Zero();
+      u_nominal = this->control_;
       this->solve(x0.data(), this->control_.data(), optimization_stride, opt_iter, u_out.data());
       this->control_ = u_out;
     }
+    if (this->getTotalSampledTrajectories() > 0)  // mppi_controller.cu:232-240
+      this->pickSampledControls(x0, u_nominal, this->control_);
     this->free_energy_statistics_.real_sys.normalizerPercent = this->getNormalizerCost() / NUM_ROLLOUTS;
     this->free_energy_statistics_.real_sys.increase =
         this->getBaselineCost() - this->free_energy_statistics_.real_sys.previousBaseline;

@@ -10,7 +10,11 @@
  * (chooseAppropriateKernel keeps its RNG side effect only: one burnt noise draw, mppi_controller.cu:95).
  */
 #pragma once
+#include <algorithm>
+#include <array>
 #include <chrono>
+#include <cmath>
+#include <random>
 #include <memory>
 #include <vector>
 
@@ -79,6 +83,12 @@ public:
   typedef Eigen::Matrix<float, DYN_T::STATE_DIM, MAX_TIMESTEPS> state_trajectory;
   typedef Eigen::Matrix<float, DYN_T::OUTPUT_DIM, MAX_TIMESTEPS> output_trajectory;
   typedef Eigen::Matrix<float, NUM_ROLLOUTS, 1> sampled_cost_traj;
+  typedef Eigen::Matrix<float, MAX_TIMESTEPS + 1, 1> cost_trajectory;  // +1 for terminal cost (controller.cuh:107)
+#ifdef MPPIB_USING_EIGEN_SHIM
+  typedef std::array<int, MAX_TIMESTEPS> crash_status_trajectory;  // the shim only carries float matrices
+#else
+  typedef Eigen::Matrix<int, MAX_TIMESTEPS, 1> crash_status_trajectory;  // controller.cuh:109
+#endif
 
   Controller(DYN_T* model, COST_T* cost, FB_T* fb_controller, SAMPLING_T* sampler, float dt, int max_iter, float lambda,
              float alpha, int num_timesteps = MAX_TIMESTEPS,
@@ -115,6 +125,86 @@ public:
   virtual std::string getControllerName()
   {
     return "name not set";
+  }
+
+  // ---- sampled (visualisation) trajectories: controller.cuh:232,279-297,724-763, controller.cu:55-179 ----------------
+  // The engine re-rolls the written-back controls of the last solve (mppib_sample_trajectories), so asking for sampled
+  // trajectories turns MPPIB_FLAG_WRITEBACK_CONTROLS on (the engine is re-created once, like resizeSampledControlTrajectories
+  // re-allocates the reference's buffers).
+  void setPercentageSampledControlTrajectories(float new_perc)
+  {
+    perc_sampled_control_trajectories_ = new_perc;
+    needWriteback();
+  }
+  void setTopNSampledControlTrajectories(int new_top_num_samples)
+  {
+    num_top_control_trajectories_ = new_top_num_samples;
+    needWriteback();
+  }
+  float getPercentageSampledControlTrajectories() const
+  {
+    return perc_sampled_control_trajectories_;
+  }
+  int getNumberSampledTrajectories() const
+  {
+    return perc_sampled_control_trajectories_ * NUM_ROLLOUTS;
+  }
+  int getNumberTopControlTrajectories() const
+  {
+    return num_top_control_trajectories_;
+  }
+  int getTotalSampledTrajectories() const
+  {
+    return getNumberSampledTrajectories() + getNumberTopControlTrajectories();
+  }
+  virtual std::vector<output_trajectory> getSampledOutputTrajectories() const
+  {
+    return sampled_trajectories_;
+  }
+  virtual std::vector<cost_trajectory> getSampledCostTrajectories() const
+  {
+    return sampled_costs_;
+  }
+  virtual std::vector<crash_status_trajectory> getSampledCrashStatusTrajectories() const
+  {
+    return sampled_crash_status_;
+  }
+  std::vector<float> getTopNCosts() const
+  {
+    return top_n_costs_;
+  }
+  // rollout index behind every sampled trajectory (-1 = the optimised control sequence)
+  std::vector<int> getSampledIndices() const
+  {
+    return sampled_indices_;
+  }
+  // controllers/MPPI/mppi_controller.cu:262-298: launchVisualizeKernel + copies, here one C-ABI call
+  virtual void calculateSampledStateTrajectories()
+  {
+    const int n = (int)sampled_indices_.size();
+    if (n == 0 || !vis_inputs_valid_)
+      return;
+    const int T = getNumTimesteps();
+    std::vector<float> out((size_t)n * T * DYN_T::OUTPUT_DIM), costs((size_t)n * (T + 1));
+    std::vector<int> crash((size_t)n * T);
+    MPPIB_HANDLE(mppib_sample_trajectories(engine_, vis_x0_.data(), vis_nominal_.data(), 0, sampled_indices_.data(), n,
+                                           vis_opt_.data(), out.data(), costs.data(), crash.data()));
+    sampled_trajectories_.assign(n, output_trajectory::Zero());
+    sampled_costs_.assign(n, cost_trajectory::Zero());
+    sampled_crash_status_.assign(n, crash_status_trajectory());
+    for (int i = 0; i < n; i++)
+    {
+      for (int k = 0; k < T * DYN_T::OUTPUT_DIM; k++)
+        sampled_trajectories_[i].data()[k] = out[(size_t)i * T * DYN_T::OUTPUT_DIM + k];
+      for (int t = 0; t < T; t++)
+      {
+        sampled_costs_[i](t) = costs[(size_t)i * (T + 1) + t];
+        sampled_crash_status_[i][t] = crash[(size_t)i * T + t];
+      }
+      for (int t = T; t < MAX_TIMESTEPS; t++)
+        sampled_crash_status_[i][t] = 0;
+      sampled_costs_[i](MAX_TIMESTEPS) = costs[(size_t)i * (T + 1) + T];  // terminal cost in the last slot
+    }
   }
 
   // ---- getters (controller.cuh:409-436,510-517,773-776) ----------------------------------------------------------
@@ -310,6 +400,80 @@ public:
 
 protected:
   unsigned extra_flags_ = 0u;  // engine flags a derived controller turns on at run time (re-creates the engine)
+  float perc_sampled_control_trajectories_ = 0;  // controller.cuh:948-950
+  int num_top_control_trajectories_ = 0;
+  std::vector<float> top_n_costs_;
+  std::vector<int> sampled_indices_;
+  std::vector<output_trajectory> sampled_trajectories_;
+  std::vector<cost_trajectory> sampled_costs_;
+  std::vector<crash_status_trajectory> sampled_crash_status_;
+  state_array vis_x0_ = state_array::Zero();
+  control_trajectory vis_nominal_ = control_trajectory::Zero(), vis_opt_ = control_trajectory::Zero();
+  bool vis_inputs_valid_ = false;
+  std::mt19937 vis_gen_{ 0 };
+  void needWriteback()
+  {
+    if (getTotalSampledTrajectories() > 0 && !(extra_flags_ & MPPIB_FLAG_WRITEBACK_CONTROLS))
+    {
+      extra_flags_ |= MPPIB_FLAG_WRITEBACK_CONTROLS;
+      createEngine();
+      vis_inputs_valid_ = false;
+    }
+  }
+  // copySampledControlFromDevice + copyTopControlFromDevice (controller.cu:55-179), on rollout indices: slot 0 is the
+  // optimised sequence, then distinct random rollouts from the first 98 % (the tail holds the pure-noise samples; all of
+  // them in order above 98 %), then the top-n by weight = the n lowest trajectory costs
+  void pickSampledControls(const Eigen::Ref<const state_array>& x0, const control_trajectory& u_nominal,
+                           const control_trajectory& u_opt)
+  {
+    sampled_indices_.clear();
+    top_n_costs_.clear();
+    const int num_sampled = getNumberSampledTrajectories();
+    if (num_sampled + num_top_control_trajectories_ <= 0)
+      return;
+    std::vector<float> c((size_t)NUM_DISTRIBUTIONS * NUM_ROLLOUTS);
+    MPPIB_HANDLE(mppib_get_costs(engine_, c.data()));
+    if (num_sampled > 0)
+    {
+      sampled_indices_.push_back(-1);
+      if (perc_sampled_control_trajectories_ > 0.98f)
+      {
+        for (int i = 1; i < num_sampled; i++)
+          sampled_indices_.push_back(i);
+      }
+      else
+      {  // partial Fisher-Yates over [0, 0.98 N)
+        std::vector<int> pool((size_t)(NUM_ROLLOUTS * 0.98));
+        for (size_t i = 0; i < pool.size(); i++)
+          pool[i] = (int)i;
+        for (int i = 1; i < num_sampled && i <= (int)pool.size(); i++)
+        {
+          std::uniform_int_distribution<size_t> pick(i - 1, pool.size() - 1);
+          std::swap(pool[i - 1], pool[pick(vis_gen_)]);
+          sampled_indices_.push_back(pool[i - 1]);
+        }
+      }
+    }
+    if (num_top_control_trajectories_ > 0)
+    {
+      std::vector<int> order(NUM_ROLLOUTS);
+      for (int i = 0; i < NUM_ROLLOUTS; i++)
+        order[i] = i;
+      const int k = std::min(num_top_control_trajectories_, NUM_ROLLOUTS);
+      std::partial_sort(order.begin(), order.begin() + k, order.end(),
+                        [&](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
+      for (int i = 0; i < k; i++)
+      {
+        sampled_indices_.push_back(order[i]);
+        // trajectory_costs_[i] / normalizer (controller.cu:160): the normalised weight
+        top_n_costs_.push_back(expf(-(c[order[i]] - baseline_[0]) / params_.lambda_) / normalizer_[0]);
+      }
+    }
+    vis_x0_ = x0;
+    vis_nominal_ = u_nominal;
+    vis_opt_ = u_opt;
+    vis_inputs_valid_ = true;
+  }
   void construct(cudaStream_t stream)
   {
     stream_ = stream;

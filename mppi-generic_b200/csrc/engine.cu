@@ -143,6 +143,14 @@ struct mppib_engine
   float* eval_costs_d = nullptr;
   int eval_capacity = 0;
   int (*init_eval)(mppib_engine&, const float*, const int*, int, int, const float*, int) = nullptr;
+  // sampled (visualisation) trajectories scratch: picked indices, optimised sequence, outputs / costs / crash flags
+  int* vis_idx_d = nullptr;
+  float* vis_opt_d = nullptr;
+  float* vis_outputs_d = nullptr;
+  float* vis_costs_d = nullptr;
+  int* vis_crash_d = nullptr;
+  int vis_capacity = 0;
+  int (*sampled_traj)(mppib_engine&, const float*, const float*, int, int, bool) = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
 
@@ -534,6 +542,52 @@ static int init_eval_launch(mppib_engine& e, const float* candidates_d, const in
   return MPPIB_OK;
 }
 
+// launchVisualizeKernel (core/mppi_common.cu:1376-1420) for this pair: see sampled_traj_kernel
+template <class DYN, class COST>
+static int sampled_traj_launch(mppib_engine& e, const float* x0, const float* U_nominal, int distribution, int n,
+                               bool have_opt)
+{
+  using Args = SampledTrajArgs<DYN, COST>;
+  static_assert(sizeof(Args) < 30000, "kernel parameter block too large");
+  Args a;
+  memcpy(&a.dyn, e.dyn_blob.data(), sizeof(a.dyn));
+  memcpy(&a.cost, e.cost_blob.data(), sizeof(a.cost));
+  AuxFill<typename DYN::Aux>::fill(a.dyn_aux, e);
+  AuxFill<typename COST::Aux>::fill(a.cost_aux, e);
+  for (int d = 0; d < MPPIB_MAX_DISTRIBUTIONS; d++)
+    for (int c = 0; c < MPPIB_MAX_CONTROL_DIM; c++)
+    {
+      const float sd = (c < e.C) ? e.sampler.std_dev[d * e.C + c] : 1.0f;
+      a.samp.std_dev[d][c] = sd;
+      a.samp.std_dev_decayed[d][c] = sd;
+    }
+  for (int c = 0; c < MPPIB_MAX_CONTROL_DIM; c++)
+    a.samp.control_cost_coeff[c] = e.sampler.control_cost_coeff[c];
+  a.samp.pure_noise_threshold = (1.0f - e.sampler.pure_noise_trajectories_percentage) * e.N;
+  a.controls = e.controls_d + (size_t)distribution * e.n_local * e.TC;
+  a.opt = have_opt ? e.vis_opt_d : nullptr;
+  a.sample_idx = e.vis_idx_d;
+  a.outputs = e.vis_outputs_d;
+  a.costs = e.vis_costs_d;
+  a.crash = e.vis_crash_d;
+  a.n = n;
+  a.T = e.T;
+  a.n_offset = e.n_offset;
+  a.distribution = distribution;
+  const int threads = 64;
+  a.dyn_shared_floats = DYN::sharedFloats(e.desc.model_dims, threads);
+  a.dt = e.dt;
+  a.lambda = e.lambda;
+  a.alpha = e.alpha;
+  memcpy(a.x0, x0, sizeof(float) * e.S);
+  memcpy(a.means, U_nominal, sizeof(float) * e.TC);
+  const size_t smem = (size_t)(((a.dyn_shared_floats + 3) / 4) * 4 + COST::sharedFloats(e.T)) * sizeof(float) + 16;
+  CUDA_TRY(cudaFuncSetAttribute(sampled_traj_kernel<DYN, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sampled_traj_kernel<DYN, COST><<<(n + threads - 1) / threads, threads, smem, e.stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return MPPIB_OK;
+}
+
 struct PairEntry
 {
   int dyn_id, cost_id;
@@ -547,6 +601,7 @@ struct PairEntry
   int (*prepare)(mppib_engine&);
   int (*init_eval)(mppib_engine&, const float*, const int*, int, int, const float*, int);
   int (*stream_blocks_per_sm)(int, int, size_t);
+  int (*sampled_traj)(mppib_engine&, const float*, const float*, int, int, bool);
 };
 template <class DYN, class COST>
 constexpr PairEntry make_entry(int dyn_id, int cost_id)
@@ -565,7 +620,8 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     &Pair<DYN, COST>::launch,
                     &Pair<DYN, COST>::prepare,
                     &init_eval_launch<DYN, COST>,
-                    &Pair<DYN, COST>::stream_blocks_per_sm };
+                    &Pair<DYN, COST>::stream_blocks_per_sm,
+                    &sampled_traj_launch<DYN, COST> };
 }
 static const PairEntry kPairs[] = {
   make_entry<plugins::CartpoleDynamics, plugins::CartpoleQuadraticCost>(MPPIB_DYN_CARTPOLE,
@@ -996,6 +1052,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->launch_rollout = entry->launch;
   e->prepare = entry->prepare;
   e->init_eval = entry->init_eval;
+  e->sampled_traj = entry->sampled_traj;
   e->dyn_param_bytes = entry->dyn_bytes;
   e->cost_param_bytes = entry->cost_bytes;
   e->dyn_shared_floats_fn = entry->dyn_shared_floats;
@@ -1350,6 +1407,11 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->eval_states_d);
   cudaFree(e->eval_strides_d);
   cudaFree(e->eval_costs_d);
+  cudaFree(e->vis_idx_d);
+  cudaFree(e->vis_opt_d);
+  cudaFree(e->vis_outputs_d);
+  cudaFree(e->vis_costs_d);
+  cudaFree(e->vis_crash_d);
   cudaFree(e->noise_alloc);
   cudaFree(e->noise_alloc2);
   cudaFree(e->costs_d);
@@ -1978,6 +2040,72 @@ int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides
     e->k1_recorded[e->cur_buf] = true;
   }
   CUDA_TRY(cudaMemcpyAsync(costs_out, e->eval_costs_d, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+int mppib_sample_trajectories(mppib_engine* e, const float* x0, const float* U_nominal, int distribution,
+                              const int* sample_idx, int n, const float* U_opt, float* outputs, float* costs, int* crash)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !U_nominal || !sample_idx || n <= 0 || !outputs || !costs || !crash)
+    return fail(MPPIB_ERR_INVALID_ARG, "bad argument");
+  if (distribution < 0 || distribution >= e->D)
+    return fail(MPPIB_ERR_INVALID_ARG, "distribution %d out of range [0, %d)", distribution, e->D);
+  if (!e->writeback || !e->controls_d)
+    return fail(MPPIB_ERR_STATE, "sampled trajectories re-roll the written-back controls: create the engine with "
+                                 "MPPIB_FLAG_WRITEBACK_CONTROLS");
+  if (e->rmppi)
+    return fail(MPPIB_ERR_UNSUPPORTED, "sampled trajectories are built for the Vanilla / Tube / Colored rollouts");
+  if (!e->solved_once)
+    return fail(MPPIB_ERR_STATE, "no solve has been run yet");
+  if (e->pending)
+    return fail(MPPIB_ERR_STATE, "a solve is in flight (mppib_solve_wait first)");
+  bool have_opt = false;
+  for (int i = 0; i < n; i++)
+  {
+    if (sample_idx[i] < -1 || sample_idx[i] >= e->n_local)
+      return fail(MPPIB_ERR_INVALID_ARG, "sample index %d (entry %d) outside [-1, %d)", sample_idx[i], i, e->n_local);
+    have_opt = have_opt || sample_idx[i] < 0;
+  }
+  if (have_opt && !U_opt)
+    return fail(MPPIB_ERR_INVALID_ARG, "index -1 needs U_opt");
+  for (int i = 0; i < e->S; i++)
+    if (!std::isfinite(x0[i]))
+      return fail(MPPIB_ERR_INVALID_ARG, "x0[%d] is not finite", i);
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  if (n > e->vis_capacity)
+  {
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    cudaFree(e->vis_idx_d);
+    cudaFree(e->vis_outputs_d);
+    cudaFree(e->vis_costs_d);
+    cudaFree(e->vis_crash_d);
+    e->vis_idx_d = nullptr;
+    e->vis_outputs_d = e->vis_costs_d = nullptr;
+    e->vis_crash_d = nullptr;
+    e->vis_capacity = 0;
+    CUDA_TRY(cudaMalloc(&e->vis_idx_d, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&e->vis_outputs_d, (size_t)n * e->T * e->O * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&e->vis_costs_d, (size_t)n * (e->T + 1) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&e->vis_crash_d, (size_t)n * e->T * sizeof(int)));
+    e->vis_capacity = n;
+  }
+  if (have_opt && !e->vis_opt_d)
+    CUDA_TRY(cudaMalloc(&e->vis_opt_d, (size_t)e->TC * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(e->vis_idx_d, sample_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  if (have_opt)
+    CUDA_TRY(cudaMemcpyAsync(e->vis_opt_d, U_opt, (size_t)e->TC * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  rc = e->sampled_traj(*e, x0, U_nominal, distribution, n, have_opt);
+  if (rc != MPPIB_OK)
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(outputs, e->vis_outputs_d, (size_t)n * e->T * e->O * sizeof(float), cudaMemcpyDeviceToHost,
+                           e->stream));
+  CUDA_TRY(cudaMemcpyAsync(costs, e->vis_costs_d, (size_t)n * (e->T + 1) * sizeof(float), cudaMemcpyDeviceToHost,
+                           e->stream));
+  CUDA_TRY(cudaMemcpyAsync(crash, e->vis_crash_d, (size_t)n * e->T * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return MPPIB_OK;
 }

@@ -638,4 +638,102 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) init_eval_kernel(const
     args.costs[gid] = running;
 }
 
+// ---- sampled (visualisation) trajectories -----------------------------------------------------------------
+// The reference's visualizeKernel (core/mppi_common.cu:364-520) re-rolls the control samples the host picked after a
+// solve (controller.cu:55-179: the optimised sequence, a random subset, the top-n by weight) and dumps every step's
+// output, running cost and crash flag. Here: one thread per picked rollout, controls read back from the written-back
+// control buffer of the last solve (already constrained, so enforceConstraints is not applied a second time: deadbands
+// are not idempotent), index -1 = the optimised sequence `opt` (constraints applied). Row layout of `costs`: [t] = (state
+// cost + likelihood-ratio cost of step t) / T exactly as K1 accumulates them, [T] = terminal cost / T, so that a row sums
+// to the rollout's trajectory cost (the reference's kernel mixes strides T and T + 1 between its running and terminal
+// writes, :482-520, which scrambles every row but the first; that is not reproduced).
+template <class DYN, class COST>
+struct SampledTrajArgs
+{
+  typename DYN::Params dyn;
+  typename COST::Params cost;
+  typename DYN::Aux dyn_aux;
+  typename COST::Aux cost_aux;
+  SamplerArgs samp;
+  const float* controls;  // [n_local][T][C] of the chosen distribution
+  const float* opt;       // [T][C] or nullptr
+  const int* sample_idx;  // [n]
+  float* outputs;         // [n][T][O]
+  float* costs;           // [n][T + 1]
+  int* crash;             // [n][T]
+  int n, T, n_offset, distribution, dyn_shared_floats;
+  float dt, lambda, alpha;
+  float x0[32];
+  float means[kMaxMeanFloats];  // [T][C] nominal control of the chosen distribution
+};
+
+template <class DYN, class COST>
+__global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS)
+    sampled_traj_kernel(const __grid_constant__ SampledTrajArgs<DYN, COST> args)
+{
+  constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
+  static_assert(S <= 32, "x0 travels in the parameter block");
+  extern __shared__ unsigned char smem_raw[];
+  float* theta_s = reinterpret_cast<float*>(smem_raw);
+  float* theta_c = theta_s + ((args.dyn_shared_floats + 3) / 4) * 4;
+  const int T = args.T;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = gid < args.n;
+  const int idx = valid ? args.sample_idx[gid] : 0;
+  const bool from_opt = idx < 0;
+  const float* useq = from_opt ? args.opt : args.controls + (size_t)idx * T * C;
+  float x[1][S], y[1][O], x_next[1][S], xdot[1][S], u[1][C];
+#pragma unroll
+  for (int i = 0; i < S; i++)
+    x[0][i] = args.x0[i];
+#pragma unroll
+  for (int i = 0; i < O; i++)
+    y[0][i] = 0.0f;
+  typename DYN::Carry carry[1];
+  DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, carry[0], x[0], y[0]);
+  COST::initializeCosts(args.cost, args.cost_aux, theta_c, T);
+  __syncthreads();
+  const int d = args.distribution;
+  const bool pure_noise = !from_opt && (float)(args.n_offset + idx) >= args.samp.pure_noise_threshold;
+  float lr_scale[C];
+  bool lr_on = false;
+#pragma unroll
+  for (int c = 0; c < C; c++)
+  {
+    lr_scale[c] = args.samp.control_cost_coeff[c] / (args.samp.std_dev[d][c] * args.samp.std_dev[d][c]);
+    lr_on = lr_on || (args.samp.control_cost_coeff[c] != 0.0f);
+  }
+  const float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
+  const float inv_T = 1.0f / (float)T;
+  int crash = 0;
+  for (int t = 0; t < T; t++)
+  {
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      u[0][c] = __ldg(useq + (size_t)t * C + c);
+    if (from_opt)
+      DYN::enforceConstraints(args.dyn, x[0], u[0]);
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      xdot[0][i] = 0.0f;
+    DYN::template stepBatch<1>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);
+    float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[0], u[0], t, &crash);
+    if (lr_on)
+      step_cost += likelihood_ratio_cost<C>(lr_scale, args.means + t * C, u[0], pure_noise, half_lambda_1ma);
+    if (valid)
+    {
+#pragma unroll
+      for (int i = 0; i < O; i++)
+        args.outputs[((size_t)gid * T + t) * O + i] = y[0][i];
+      args.costs[(size_t)gid * (T + 1) + t] = step_cost * inv_T;
+      args.crash[(size_t)gid * T + t] = crash;
+    }
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      x[0][i] = x_next[0][i];
+  }
+  if (valid)
+    args.costs[(size_t)gid * (T + 1) + T] = COST::terminalCost(args.cost, args.cost_aux, y[0]) * inv_T;
+}
+
 }  // namespace mppib

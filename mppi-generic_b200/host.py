@@ -177,7 +177,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
-    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
 
@@ -676,6 +676,7 @@ class Engine:
         self.dyn, self.cost, self.sampler = dyn, cost, sampler
         self.N, self.T, self.D = num_rollouts, num_timesteps, num_distributions
         self.S, self.Cdim, self.O = dyn.STATE_DIM, dyn.CONTROL_DIM, dyn.OUTPUT_DIM
+        self.flags = flags
         d = Desc(dyn.DYN_ID, cost.COST_ID, sampler.SAMPLER_ID, num_rollouts, num_timesteps, num_distributions, device,
                  flags, stream, rank, world_size)
         for i, v in enumerate(dyn.model_dims()):
@@ -821,6 +822,20 @@ class Engine:
                                      _ptr(_f32(U_nominal)), optimization_stride, _ptr(costs)))
         return costs
 
+    def sample_trajectories(self, x0, U_nominal, sample_idx, U_opt=None, distribution: int = 0):
+        """mppib_sample_trajectories: re-roll picked rollouts of the last solve. sample_idx: rank-local indices, -1 = U_opt.
+        Returns (outputs [n][T][O], costs [n][T + 1], crash [n][T])."""
+        idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        n = idx.size
+        outputs = np.empty((n, self.T, self.dyn.OUTPUT_DIM), np.float32)
+        costs = np.empty((n, self.T + 1), np.float32)
+        crash = np.empty((n, self.T), np.int32)
+        _check(lib().mppib_sample_trajectories(self._h, _ptr(_f32(x0)), _ptr(_f32(U_nominal)), distribution,
+                                               idx.ctypes.data_as(C.c_void_p), n,
+                                               None if U_opt is None else _ptr(_f32(U_opt)), _ptr(outputs), _ptr(costs),
+                                               crash.ctypes.data_as(C.c_void_p)))
+        return outputs, costs, crash
+
     def set_noise(self, eps) -> None:
         eps = _f32(eps)
         _check(lib().mppib_set_noise(self._h, _ptr(eps), eps.size))
@@ -904,6 +919,13 @@ class _Controller:
         self.baseline_ = [0.0] * self.NUM_DISTRIBUTIONS
         self.normalizer_ = [0.0] * self.NUM_DISTRIBUTIONS
         self.free_energy_statistics_ = {}
+        self.perc_sampled_control_trajectories_ = 0.0  # controller.cuh:948-950
+        self.num_top_control_trajectories_ = 0
+        self.top_n_costs_ = np.zeros(0, np.float32)
+        self.sampled_indices_ = np.zeros(0, np.int32)
+        self.sampled_trajectories_ = self.sampled_costs_ = self.sampled_crash_status_ = None
+        self._vis_inputs = None
+        self._vis_rng = np.random.RandomState(0 if seed is None else seed)
         self.engine = Engine(model, cost, sampler, num_rollouts, num_timesteps, self.NUM_DISTRIBUTIONS, device, flags,
                              stream, rank, world_size)
         self.engine.set_solver(dt, lambda_, alpha)
@@ -935,6 +957,72 @@ class _Controller:
 
     def getSampledCostSeq(self) -> np.ndarray:
         return self.engine.get_costs()
+
+    # ---- sampled (visualisation) trajectories: controller.cuh:279-297,724-763, controller.cu:55-179 --------------------
+    def setPercentageSampledControlTrajectories(self, new_perc: float) -> None:
+        self._need_writeback()
+        self.perc_sampled_control_trajectories_ = float(new_perc)
+
+    def setTopNSampledControlTrajectories(self, new_top_num_samples: int) -> None:
+        self._need_writeback()
+        self.num_top_control_trajectories_ = int(new_top_num_samples)
+
+    def getPercentageSampledControlTrajectories(self) -> float:
+        return self.perc_sampled_control_trajectories_
+
+    def getNumberSampledTrajectories(self) -> int:
+        return int(self.perc_sampled_control_trajectories_ * self.num_rollouts_)
+
+    def getNumberTopControlTrajectories(self) -> int:
+        return self.num_top_control_trajectories_
+
+    def getTotalSampledTrajectories(self) -> int:
+        return self.getNumberSampledTrajectories() + self.getNumberTopControlTrajectories()
+
+    def getSampledOutputTrajectories(self) -> np.ndarray:
+        return self.sampled_trajectories_
+
+    def getSampledCostTrajectories(self) -> np.ndarray:
+        return self.sampled_costs_
+
+    def getSampledCrashStatusTrajectories(self) -> np.ndarray:
+        return self.sampled_crash_status_
+
+    def getTopNCosts(self) -> np.ndarray:
+        return self.top_n_costs_
+
+    def getSampledIndices(self) -> np.ndarray:
+        """Rank-local rollout index behind every sampled trajectory (-1 = the optimised control sequence)."""
+        return self.sampled_indices_
+
+    def _need_writeback(self) -> None:
+        if not (self.engine.flags & FLAG_WRITEBACK_CONTROLS):
+            raise MppibError(-9, "sampled trajectories need the stored controls: construct the controller with "
+                                        "flags=FLAG_WRITEBACK_CONTROLS")
+
+    def _pick_sampled_controls(self, state: np.ndarray, U_nominal: np.ndarray, U_opt: np.ndarray, costs: np.ndarray,
+                               normalizer: float) -> None:
+        """copySampledControlFromDevice + copyTopControlFromDevice (controller.cu:55-179): slot 0 is the optimised
+        sequence, then a random subset drawn without replacement from the first 98 % of the rollouts (the tail holds the
+        pure-noise samples), then the top-n by weight (= the n lowest costs)."""
+        self.sampled_indices_ = pick_sampled_indices(self.getNumberSampledTrajectories(),
+                                                     self.num_top_control_trajectories_, costs,
+                                                     self.perc_sampled_control_trajectories_, self._vis_rng)
+        self._vis_inputs = (state.copy(), U_nominal.copy(), U_opt.copy())
+        n_top = self.num_top_control_trajectories_
+        if n_top > 0:
+            c = costs[self.sampled_indices_[-n_top:]].astype(np.float64)
+            self.top_n_costs_ = (np.exp(-(c - float(costs.min())) / self.lambda_) / normalizer).astype(np.float32)
+        else:
+            self.top_n_costs_ = np.zeros(0, np.float32)
+
+    def calculateSampledStateTrajectories(self) -> None:
+        """controllers/MPPI/mppi_controller.cu:262-298 (launchVisualizeKernel + copies)."""
+        if self.getTotalSampledTrajectories() <= 0 or self._vis_inputs is None:
+            return
+        x0, U_nominal, U_opt = self._vis_inputs
+        out, costs, crash = self.engine.sample_trajectories(x0, U_nominal, self.sampled_indices_, U_opt)
+        self.sampled_trajectories_, self.sampled_costs_, self.sampled_crash_status_ = out, costs, crash
 
     def getNumTimesteps(self) -> int:
         return self.num_timesteps_
@@ -980,6 +1068,25 @@ class _Controller:
                 "freeEnergyModifiedVariance": float(out[2])}
 
 
+def pick_sampled_indices(num_sampled: int, num_top: int, costs: np.ndarray, perc: float,
+                         rng: np.random.RandomState) -> np.ndarray:
+    """Sample selection of controller.cu:55-179 on rank-local rollout indices. Entry 0 of the sampled block stands for
+    the optimised sequence (-1); entries 1.. are distinct rollouts from the first 98 % (all of them in order if
+    perc > 0.98); the last num_top entries are the rollouts with the largest weights, i.e. the lowest costs."""
+    N = costs.shape[0]
+    idx = []
+    if num_sampled > 0:
+        if perc > 0.98:
+            pool = np.arange(num_sampled)
+        else:
+            pool = rng.choice(int(N * 0.98), size=num_sampled, replace=False)
+        idx = [-1] + [int(v) for v in pool[1:]]
+    if num_top > 0:
+        top = np.argpartition(costs, min(num_top, N) - 1)[:num_top]
+        idx += [int(v) for v in top[np.argsort(costs[top], kind="stable")]]
+    return np.asarray(idx, dtype=np.int32)
+
+
 def merge_records(records: np.ndarray, lambda_: float, normalize: bool = True) -> np.ndarray:
     """records [nrec][D][pstride] -> merged [D][pstride] with the engine's K2 arithmetic (CPU twin, host_twins.h)."""
     r = _f32(records)
@@ -999,10 +1106,13 @@ class VanillaMPPIController(_Controller):
         state = _f32(state)
         prev_baseline = self.baseline_[0]
         for opt_iter in range(self.num_iters_):
+            U_nominal = self.control_
             U, stats = self.engine.solve(state, self.control_, optimization_stride, opt_iter)
             self.control_ = U[0].copy()
             self.baseline_[0], self.normalizer_[0] = stats[0][0], stats[0][1]
             fe = self._free_energy(stats[0])
+        if self.getTotalSampledTrajectories() > 0:  # mppi_controller.cu:232-240
+            self._pick_sampled_controls(state, U_nominal, self.control_, self.engine.get_costs()[0], self.normalizer_[0])
         fe["normalizerPercent"] = self.normalizer_[0] / self.num_rollouts_
         fe["increase"] = self.baseline_[0] - prev_baseline
         fe["previousBaseline"] = prev_baseline

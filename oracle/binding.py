@@ -286,3 +286,20 @@ def tsallis(costs, gamma, r, base) -> np.ndarray:
     c = _f32(costs).copy()
     lib().orc_tsallis(_p(c), c.size, C.c_float(gamma), C.c_float(r), C.c_float(base))
     return c
+
+
+def sampled_trajectory(dyn_id, cost_id, dyn_params, cost_params, sp, nn_theta, costmap, N, T, d, sample_index,
+                       apply_constraints, dt, lam, alpha, x0, means, controls):
+    """One rollout with every step dumped (the visualisation pass): returns outputs [T][O], costs [T + 1], crash [T]."""
+    S, C_, O = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_dims(dyn_id, C.byref(S), C.byref(C_), C.byref(O))
+    outputs = np.zeros((T, O.value), np.float32)
+    costs = np.zeros(T + 1, np.float32)
+    crash = np.zeros(T, np.int32)
+    rc = lib().orc_sampled_trajectory(dyn_id, cost_id, C.byref(dyn_params), C.byref(cost_params), C.byref(sp),
+                                      _p(nn_theta), _p(costmap), N, T, d, sample_index, int(apply_constraints),
+                                      C.c_float(dt), C.c_float(lam), C.c_float(alpha), _p(_f32(x0)), _p(_f32(means)),
+                                      _p(_f32(controls)), _p(outputs), _p(costs), crash.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"orc_sampled_trajectory failed: {rc}")
+    return outputs, costs, crash

@@ -860,6 +860,45 @@ static void rollout_range(const typename DYN::P& dp, const typename COST::P& cp,
   }
 }
 
+// One rollout with everything dumped: the per-step semantics of launchCPURolloutKernel above (and of visualizeKernel,
+// core/mppi_common.cu:364-520: step, then running cost + likelihood-ratio cost on the new output, crash flag sticky),
+// outputs [T][O] = y after step t, costs [T + 1] = per-step cost / T with the terminal cost / T last, crash [T].
+template <class DYN, class COST>
+static void sampledTrajectory(const void* dpv, const void* cpv, const mppib_gaussian_params& sp, const Aux& aux, int N, int T,
+                              int d, int sample_index, int apply_constraints, float dt, float lambda, float alpha,
+                              const float* x0, const float* means /*[T][C] of d*/, const float* controls /*[T][C]*/,
+                              float* outputs, float* costs, int* crash)
+{
+  constexpr int S = DYN::S, C = DYN::C, O = DYN::O;
+  const auto& dp = *(const typename DYN::P*)dpv;
+  const auto& cp = *(const typename COST::P*)cpv;
+  float curr_x[S], next_x[S], x_der[S], u[C], y[O];
+  for (int i = 0; i < S; i++)
+    curr_x[i] = x0[i];
+  for (int i = 0; i < O; i++)
+    y[i] = 0.0f;
+  int crash_status = 0;
+  typename DYN::Carry carry;
+  DYN::initCarry(aux, carry);
+  for (int t = 0; t < T; t++)
+  {
+    for (int i = 0; i < C; i++)
+      u[i] = controls[(size_t)t * C + i];
+    if (apply_constraints)
+      enforceConstraints<C>(dp.lim, u);
+    dyn_step<DYN>(dp, aux, curr_x, next_x, x_der, u, y, dt, &carry);
+    float c = COST::computeStateCost(cp, aux, y, t, &crash_status);
+    c += likelihoodRatioCost(sp, &means[(size_t)t * C], u, C, d, sample_index, N, lambda, alpha);
+    costs[t] = c / T;
+    crash[t] = crash_status;
+    for (int i = 0; i < O; i++)
+      outputs[(size_t)t * O + i] = y[i];
+    for (int i = 0; i < S; i++)
+      curr_x[i] = next_x[i];
+  }
+  costs[T] = COST::terminalCost(cp, aux, y) / T;
+}
+
 template <class DYN, class COST>
 static void rollout(const void* dp, const void* cp, const mppib_gaussian_params& sp, const Aux& aux, int N, int T,
                     int D, float dt, float lambda, float alpha, const float* x0, const float* means, float* samples,
@@ -1436,6 +1475,35 @@ int orc_rmppi_rollout(int dyn_id, int cost_id, const void* dyn_params, const voi
   }
   for (auto& t : th)
     t.join();
+  return 0;
+}
+
+int orc_sampled_trajectory(int dyn_id, int cost_id, const void* dyn_params, const void* cost_params,
+                           const mppib_gaussian_params* sp, const float* nn_theta, const float* costmap, int N, int T, int d,
+                           int sample_index, int apply_constraints, float dt, float lambda, float alpha, const float* x0,
+                           const float* means, const float* controls, float* outputs, float* costs, int* crash)
+{
+  orc::Aux aux;
+  aux.nn_theta = nn_theta;
+  aux.costmap = costmap;
+  fill_lstm(aux);
+  typedef void (*fn_t)(const void*, const void*, const mppib_gaussian_params&, const orc::Aux&, int, int, int, int, int, float,
+                       float, float, const float*, const float*, const float*, float*, float*, int*);
+  fn_t f = nullptr;
+  if (dyn_id == MPPIB_DYN_CARTPOLE && cost_id == MPPIB_COST_CARTPOLE_QUADRATIC)
+    f = &orc::sampledTrajectory<orc::Cartpole, orc::CartpoleQuadraticCost>;
+  else if (dyn_id == MPPIB_DYN_DOUBLE_INTEGRATOR && cost_id == MPPIB_COST_DI_CIRCLE)
+    f = &orc::sampledTrajectory<orc::DoubleIntegrator, orc::DICircleCost>;
+  else if (dyn_id == MPPIB_DYN_AUTORALLY_NN && cost_id == MPPIB_COST_AR_STANDARD)
+    f = &orc::sampledTrajectory<orc::AutorallyNN, orc::ARStandardCost>;
+  else if (dyn_id == MPPIB_DYN_RACER_LSTM && cost_id == MPPIB_COST_RACER_QUADRATIC)
+    f = &orc::sampledTrajectory<orc::RacerLSTM, orc::RacerQuadraticCost>;
+  else if (dyn_id == MPPIB_DYN_QUADROTOR && cost_id == MPPIB_COST_QUADROTOR_QUADRATIC)
+    f = &orc::sampledTrajectory<orc::Quadrotor, orc::QuadrotorQuadraticCost>;
+  if (!f)
+    return -1;
+  f(dyn_params, cost_params, *sp, aux, N, T, d, sample_index, apply_constraints, dt, lambda, alpha, x0, means, controls,
+    outputs, costs, crash);
   return 0;
 }
 

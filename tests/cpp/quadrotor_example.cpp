@@ -76,6 +76,29 @@ int main()
       x = xn;
       ctrl.slideControlSequence(1);
     }
+    // sampled (visualisation) trajectories of the last solve: 1 % random + the top 4 by weight
+    ctrl.setPercentageSampledControlTrajectories(0.01f);
+    ctrl.setTopNSampledControlTrajectories(4);
+    ctrl.computeControl(x, 1);
+    ctrl.calculateSampledStateTrajectories();
+    auto trajs = ctrl.getSampledOutputTrajectories();
+    auto ctrajs = ctrl.getSampledCostTrajectories();
+    auto crashes = ctrl.getSampledCrashStatusTrajectories();
+    auto top = ctrl.getTopNCosts();
+    auto idx = ctrl.getSampledIndices();
+    auto all_costs = ctrl.getSampledCostSeq();
+    bool vis_ok = (int)trajs.size() == ctrl.getTotalSampledTrajectories() && (int)trajs.size() == 40 + 4 && idx[0] == -1 &&
+                  top.size() == 4 && fabsf(top[0] * ctrl.getNormalizerCost() - 1.0f) < 1e-5f;
+    for (size_t i = trajs.size() - 4; i < trajs.size() && vis_ok; i++)
+    {  // a stored rollout's per-step costs sum to its trajectory cost
+      double sum = 0;
+      for (int t = 0; t <= T; t++)
+        sum += ctrajs[i](t);
+      vis_ok = fabs(sum - all_costs(idx[i])) <= 1e-4 * fmax(1.0, fabs(all_costs(idx[i]))) && crashes[i][T - 1] == 0;
+    }
+    printf("sampled trajectories: %zu (top weight %f), consistent %d\n", trajs.size(), top[0], (int)vis_ok);
+    if (!vis_ok)
+      return 3;
     const float dist = sqrtf((x(0) - 4) * (x(0) - 4) + (x(1) - 1) * (x(1) - 1) + (x(2) - 2) * (x(2) - 2));
     const float qn = sqrtf(x(6) * x(6) + x(7) * x(7) + x(8) * x(8) + x(9) * x(9));
     printf("distance to goal after 250 steps %f, |q| %f, baseline %f\n", dist, qn, ctrl.getBaselineCost());

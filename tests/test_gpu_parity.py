@@ -898,3 +898,81 @@ def test_quadrotor_controller_flies_to_the_goal():
     assert np.linalg.norm(x[:3] - goal) < 0.5
     assert abs(np.linalg.norm(x[6:10]) - 1) < 1e-5
     assert ctrl.getTargetStateSeq().shape == (w.T, 13)
+
+
+# ---- sampled (visualisation) trajectories ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cartpole", "autorally", "quadrotor", "racer_lstm_gaussian", "double_integrator_tube"])
+def test_sampled_trajectories_match_oracle(name):
+    """mppib_sample_trajectories (visualizeKernel, core/mppi_common.cu:364-520) against the oracle's per-step dump of the
+    same rollouts: outputs and per-step costs to the rollout tolerance, crash flags equal, every row summing to the
+    trajectory cost K1 produced for that sample."""
+    N, T = 2048, 48
+    w = W.by_name(name, N, T)
+    if name != "double_integrator_tube":
+        w.sampler.setControlCostCoeff([0.3] * w.dyn.CONTROL_DIM)
+        w.alpha = 0.1
+    if w.dyn.DYN_ID == H.DYN_RACER_LSTM:
+        oracle.set_lstm(w.dyn.lstm_theta, w.dyn.hidden_dim, w.dyn.head_hidden)
+    e = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    U, stats = e.solve(w.x0, w.U0)
+    costs = e.get_costs()
+    samples = e.get_samples()
+    for d in range(w.D):
+        idx = np.array([-1, 0, 5, N - 1, int(np.argmin(costs[d])), int(np.argmax(costs[d])), 777], np.int32)
+        out, ctraj, crash = e.sample_trajectories(w.x0[d], w.U0[d], idx, U_opt=U[d], distribution=d)
+        assert out.shape == (len(idx), T, w.dyn.OUTPUT_DIM) and ctraj.shape == (len(idx), T + 1)
+        for k, n in enumerate(idx):
+            ctrl = U[d] if n < 0 else samples[d, n]
+            ro, rc, rcr = oracle.sampled_trajectory(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params,
+                                                    w.sampler.params, w.dyn.nn_theta, getattr(w.cost, "costmap", None), N, T,
+                                                    d, max(int(n), 0) if n >= 0 else 0, n < 0, w.dt, w.lambda_, w.alpha,
+                                                    w.x0[d], w.U0[d], ctrl)
+            scale = np.maximum(np.abs(ro).max(axis=0), 1.0)
+            np.testing.assert_allclose(out[k] / scale, ro / scale, rtol=2e-4, atol=2e-4)
+            np.testing.assert_allclose(ctraj[k], rc, rtol=2e-4, atol=1e-6 + 2e-4 * float(np.abs(rc).max()))
+            np.testing.assert_array_equal(crash[k], rcr)
+            if n >= 0:
+                assert float(ctraj[k].astype(np.float64).sum()) == pytest.approx(float(costs[d, n]), rel=2e-5)
+    # argument checking: fails loudly, never silently clamps
+    with pytest.raises(m.MppibError):
+        e.sample_trajectories(w.x0[0], w.U0[0], [N], U_opt=U[0])
+    with pytest.raises(m.MppibError):
+        e.sample_trajectories(w.x0[0], w.U0[0], [-1])  # -1 without U_opt
+    with pytest.raises(m.MppibError):
+        e.sample_trajectories(w.x0[0], w.U0[0], [0], distribution=w.D)
+    e.close()
+    e2 = w.make_engine()
+    e2.solve(w.x0, w.U0)
+    with pytest.raises(m.MppibError):  # needs the written-back controls
+        e2.sample_trajectories(w.x0[0], w.U0[0], [0])
+    e2.close()
+
+
+def test_controller_sampled_state_trajectories():
+    """setPercentageSampledControlTrajectories / setTopNSampledControlTrajectories / calculateSampledStateTrajectories
+    through the mirrored controller (controller.cuh:279-297,724-763; mppi_controller.cu:232-298)."""
+    w = W.autorally(4096, 60)
+    ctrl = H.VanillaMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N,
+                                   init_control_traj=w.U0[0], seed=5, flags=H.FLAG_WRITEBACK_CONTROLS)
+    ctrl.setPercentageSampledControlTrajectories(0.01)
+    ctrl.setTopNSampledControlTrajectories(6)
+    assert ctrl.getNumberSampledTrajectories() == 40 and ctrl.getTotalSampledTrajectories() == 46
+    ctrl.computeControl(w.x0[0], 1)
+    ctrl.calculateSampledStateTrajectories()
+    out, ctraj, crash = (ctrl.getSampledOutputTrajectories(), ctrl.getSampledCostTrajectories(),
+                         ctrl.getSampledCrashStatusTrajectories())
+    assert out.shape == (46, w.T, 8) and ctraj.shape == (46, w.T + 1) and crash.shape == (46, w.T)
+    costs = ctrl.getSampledCostSeq()[0]
+    idx = ctrl.getSampledIndices()
+    assert idx[0] == -1 and len(set(idx[1:40].tolist())) == 39
+    order = np.argsort(costs, kind="stable")[:6]
+    np.testing.assert_array_equal(idx[-6:], order)
+    np.testing.assert_allclose(ctraj[-6:].astype(np.float64).sum(axis=1), costs[order], rtol=2e-5)
+    wts = np.exp(-(costs[order].astype(np.float64) - float(costs.min())) / w.lambda_) / ctrl.getNormalizerCost()
+    np.testing.assert_allclose(ctrl.getTopNCosts(), wts, rtol=1e-5)
+    assert ctrl.getTopNCosts()[0] == pytest.approx(1.0 / ctrl.getNormalizerCost(), rel=1e-6)
+    assert np.isfinite(out).all()
+    # a controller without the flag refuses instead of returning stale data
+    plain = H.VanillaMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N, seed=5)
+    with pytest.raises(m.MppibError):
+        plain.setTopNSampledControlTrajectories(3)

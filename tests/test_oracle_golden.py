@@ -570,3 +570,39 @@ def test_quadrotor_oracle_solve_flies_towards_the_goal():
         x[0], _, _ = oracle.dyn_step(w.dyn.DYN_ID, w.dyn.params, None, x[0], u0, w.dt)
         U[0, :-1] = U[0, 1:]
     assert np.linalg.norm(x[0, :3] - goal) < 0.85 * d0  # 0.8 s of flight: 4.58 m -> 3.67 m, climbing and pitching over
+
+
+# ---- sampled (visualisation) trajectories ---------------------------------------------------------------
+def test_pick_sampled_indices_semantics():
+    # controller.cu:55-179: slot 0 = optimised sequence, distinct random picks from the first 98 %, then top-n by weight
+    rng = np.random.RandomState(0)
+    costs = rng.rand(1000).astype(np.float32)
+    idx = H.pick_sampled_indices(50, 5, costs, 0.05, np.random.RandomState(1))
+    assert len(idx) == 55 and idx[0] == -1
+    body = idx[1:50]
+    assert len(set(body.tolist())) == 49 and body.min() >= 0 and body.max() < 980
+    np.testing.assert_array_equal(idx[-5:], np.argsort(costs, kind="stable")[:5])
+    # above 98 %: everything in order (controller.cu:66-70)
+    idx = H.pick_sampled_indices(990, 0, costs, 0.99, np.random.RandomState(1))
+    np.testing.assert_array_equal(idx, np.concatenate([[-1], np.arange(1, 990)]))
+    assert H.pick_sampled_indices(0, 0, costs, 0.0, rng).size == 0
+    np.testing.assert_array_equal(H.pick_sampled_indices(0, 2, costs, 0.0, rng), np.argsort(costs, kind="stable")[:2])
+
+
+def test_oracle_sampled_trajectory_rows_sum_to_the_rollout_cost():
+    w = W.cartpole(128, 40)
+    w.sampler.setControlCostCoeff([0.7])
+    w.alpha = 0.2
+    eps = oracle.curand_normal(3, 0, w.N * w.T).reshape(w.N, w.T, 1)
+    r = oracle.solve(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params, w.sampler.params, None, None, w.N, w.T, 1,
+                     1, w.dt, w.lambda_, w.alpha, w.x0, w.U0, eps, want_samples=True)
+    for n in (0, 17, 127):  # 127: pure-noise sample (likelihood-ratio term with mean 0)
+        out, costs, crash = oracle.sampled_trajectory(w.dyn.DYN_ID, w.cost.COST_ID, w.dyn.params, w.cost.params,
+                                                      w.sampler.params, None, None, w.N, w.T, 0, n, False, w.dt,
+                                                      w.lambda_, w.alpha, w.x0[0], w.U0[0], r["samples"][0, n])
+        assert costs.astype(np.float64).sum() == pytest.approx(float(r["costs"][0, n]), rel=1e-5)
+        assert out.shape == (w.T, 4) and not crash.any()
+        # outputs are the states after each step of the host twin driven by the same controls
+        st, _ = oracle.output_trajectory(w.dyn.DYN_ID, w.dyn.params, None, w.x0[0],
+                                         np.vstack([r["samples"][0, n], np.zeros((1, 1), np.float32)]), w.dt)
+        np.testing.assert_allclose(out, st[1:], rtol=1e-6, atol=1e-6)
