@@ -1,0 +1,3 @@
+#!/bin/bash
+# GPU-box script: sampled-trajectory tests + the C++ examples.
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_cpp_host_layer.py -m gpu -x -q -k "sampled or quadrotor_example or cartpole_example" 2>&1 | tail -25
