@@ -41,7 +41,8 @@ enum mppib_cost_id
 enum mppib_sampler_id
 {
   MPPIB_SAMPLER_GAUSSIAN = 0,     /* sampling_distributions/gaussian/gaussian.cuh */
-  MPPIB_SAMPLER_COLORED_NOISE = 1 /* sampling_distributions/colored_noise/colored_noise.cuh */
+  MPPIB_SAMPLER_COLORED_NOISE = 1, /* sampling_distributions/colored_noise/colored_noise.cuh */
+  MPPIB_SAMPLER_NLN = 2            /* sampling_distributions/nln/nln.cuh: normal x log-normal noise, GaussianParams */
 };
 
 /* ---- Dynamics base: control limits (dynamics/dynamics.cuh:133,511-512) ------------------------- */

@@ -202,6 +202,8 @@ struct mppib_engine
   size_t draw_local = 0;               // this rank's normals
   // ColoredNoise sampler (noise_colored.cuh)
   bool colored = false;
+  bool nln = false;              // NLN sampler: C log-normal planes + one normal block per draw (nln.cu:114-128)
+  float* nln_d = nullptr;        // [C][N][T]
   int F = 0;                     // T + 1 frequencies
   float2* spec_d = nullptr;      // [n_local*C][F] complex spectrum == the raw draw
   float* spec_alloc = nullptr;   // allocation incl. the offset-alignment lead-in
@@ -701,7 +703,43 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
     CUDA_TRY(cudaStreamWaitEvent(st, e.ev_last_gen, 0));
   if (e.colored && e.rearr_recorded)
     CUDA_TRY(cudaStreamWaitEvent(st, e.ev_rearr, 0));  // a re-rearrange may still be reading time_d
-  if (e.xw_enabled && (pos % 8192ULL) == 0)
+  if (e.nln)
+  {
+    // NLNDistribution::generateSamples (nln.cu:114-128): C curandGenerateLogNormal calls of N*T values (mean 0, std dev
+    // sigma_c) into plane c, one curandGenerateNormal of N*T*C, then createNLNNoise. Library generator, call after call like
+    // the reference; re-positioning (seed / burn) is exact only where cuRAND honours absolute offsets (multiples of 8192,
+    // tools/curand_probe.cu) and every call then stays on such a boundary.
+    const size_t plane = (size_t)e.n_local * e.T;
+    if (plane & 1)
+      return fail(MPPIB_ERR_UNSUPPORTED, "cuRAND draws need an even count (N * T = %zu)", plane);
+    CURAND_TRY(curandSetStream(e.gen, st));
+    if (e.curand_pos != pos)
+    {
+      if ((pos % 8192ULL) != 0 || (plane % 8192) != 0)
+        return fail(MPPIB_ERR_UNSUPPORTED, "NLN draws continue the generator call after call; re-positioning it to "
+                                           "offset %llu needs N * T (= %zu) to be a multiple of 8192", pos, plane);
+      CURAND_TRY(curandSetGeneratorOffset(e.gen, pos));
+    }
+    for (int c = 0; c < e.C; c++)
+      CURAND_TRY(curandGenerateLogNormal(e.gen, e.nln_d + (size_t)c * plane, plane, 0.0f, e.sampler.std_dev[c]));
+    CURAND_TRY(curandGenerateNormal(e.gen, dst, plane * e.C, 0.0f, 1.0f));
+    const int blocks = (int)std::min<size_t>((plane + 255) / 256, 148 * 16);
+    switch (e.C)
+    {
+      case 1:
+        nln_combine_kernel<1><<<blocks, 256, 0, st>>>(dst, e.nln_d, e.n_local, e.T);
+        break;
+      case 2:
+        nln_combine_kernel<2><<<blocks, 256, 0, st>>>(dst, e.nln_d, e.n_local, e.T);
+        break;
+      default:
+        nln_combine_kernel<4><<<blocks, 256, 0, st>>>(dst, e.nln_d, e.n_local, e.T);
+        break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    e.curand_pos = pos + global_count;
+  }
+  else if (e.xw_enabled && (pos % 8192ULL) == 0)
   {
     const int nstates = e.xw_chunks * kXorwowStreams;
     if (e.xw_pos != pos)
@@ -1004,7 +1042,10 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   const int world = desc->world_size <= 0 ? 1 : desc->world_size;
   if (desc->rank < 0 || desc->rank >= world)
     return fail(MPPIB_ERR_INVALID_ARG, "rank out of range");
-  if (desc->sampler_id != MPPIB_SAMPLER_GAUSSIAN && desc->sampler_id != MPPIB_SAMPLER_COLORED_NOISE)
+  if (desc->sampler_id == MPPIB_SAMPLER_NLN && (desc->world_size != 1 || desc->num_distributions != 1))
+    return fail(MPPIB_ERR_UNSUPPORTED, "the NLN sampler is built for one rank and one distribution");
+  if (desc->sampler_id != MPPIB_SAMPLER_GAUSSIAN && desc->sampler_id != MPPIB_SAMPLER_COLORED_NOISE &&
+      desc->sampler_id != MPPIB_SAMPLER_NLN)
     return fail(MPPIB_ERR_UNSUPPORTED, "sampler %d is not built into this library", desc->sampler_id);
   if (desc->sampler_id == MPPIB_SAMPLER_COLORED_NOISE && desc->num_distributions != 1)
     return fail(MPPIB_ERR_UNSUPPORTED,
@@ -1241,11 +1282,13 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   const size_t noise_floats = (size_t)e->n_local * e->TC;
   const size_t lead_floats = 8192;  // room for the offset-alignment lead-in (see draw_noise)
   e->colored = desc->sampler_id == MPPIB_SAMPLER_COLORED_NOISE;
+  e->nln = desc->sampler_id == MPPIB_SAMPLER_NLN;
   e->F = e->T + 1;
   {
     // normals per generateSamples call and this rank's slice of them
+    // colored_noise.cu:341-343 / gaussian.cu:380 / nln.cu:114-122 (C log-normal planes of N*T, then N*T*C normals)
     const unsigned long long per_rollout =
-        e->colored ? 2ULL * e->C * e->F : (unsigned long long)e->TC;  // colored_noise.cu:341-343 / gaussian.cu:380
+        e->colored ? 2ULL * e->C * e->F : (e->nln ? 2ULL * e->TC : (unsigned long long)e->TC);
     e->draw_global = per_rollout * (unsigned long long)e->N;
     e->draw_start = per_rollout * (unsigned long long)e->n_offset;
     e->draw_local = (size_t)(per_rollout * (unsigned long long)e->n_local);
@@ -1300,6 +1343,8 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   for (int i = 0; i < 4; i++)
     CUDA_TRY_B(cudaEventCreate(&e->ev[i]));
 
+  if (e->nln)
+    CUDA_TRY_B(cudaMalloc(&e->nln_d, noise_floats * sizeof(float)));
   if (e->colored)
   {
     // spectrum (the raw draw), time-domain buffer, tables and the reference's plan (colored_noise.cu:236-282)
@@ -1319,7 +1364,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   }
 
   // own XORWOW draw: possible when this rank's slice is a whole number of 8192-normal rounds
-  if (!(desc->flags & MPPIB_FLAG_CURAND_HOST_API) && !getenv("MPPIB_CURAND_HOST_API") &&
+  if (!e->nln && !(desc->flags & MPPIB_FLAG_CURAND_HOST_API) && !getenv("MPPIB_CURAND_HOST_API") &&
       (e->draw_local % 8192) == 0 && (e->draw_start % 8192ULL) == 0 && (e->draw_global % 8192ULL) == 0)
   {
     const int rounds_local = (int)(e->draw_local / 8192);
@@ -1407,6 +1452,7 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->eval_states_d);
   cudaFree(e->eval_strides_d);
   cudaFree(e->eval_costs_d);
+  cudaFree(e->nln_d);
   cudaFree(e->vis_idx_d);
   cudaFree(e->vis_opt_d);
   cudaFree(e->vis_outputs_d);
@@ -1541,6 +1587,8 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         e->prefetch_valid = false;  // a prefetched block was shaped with the old table
       }
+      if (e->nln && e->have_sampler && memcmp(sp.std_dev, e->sampler.std_dev, sizeof(sp.std_dev)) != 0)
+        e->prefetch_valid = false;  // a prefetched block drew its log-normal planes with the old std dev
       e->sampler = sp;
       e->have_sampler = true;
       return MPPIB_OK;

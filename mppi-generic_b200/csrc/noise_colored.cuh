@@ -79,4 +79,18 @@ __global__ void colored_rearrange_kernel(const float* __restrict__ time /*[n][c]
     dst[c] = out[c];
 }
 
+// ---- NLN sampler (sampling_distributions/nln/nln.cu:14-27, createNLNNoise) --------------------------------------------------
+// normal[n][t][c] *= log_normal[c][n][t]; one thread per (n, t), the C factors of a step read from the C planes.
+template <int C>
+__global__ void nln_combine_kernel(float* __restrict__ normal, const float* __restrict__ log_normal, int n_rollouts, int T)
+{
+  const size_t plane = (size_t)n_rollouts * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
+  {
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      normal[i * C + c] *= log_normal[c * plane + i];
+  }
+}
+
 }  // namespace mppib

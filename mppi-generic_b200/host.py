@@ -27,7 +27,7 @@ FLT_MAX = 3.4028234663852886e38
 # plugin ids (include/mppi_b200/params.h)
 DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM, DYN_QUADROTOR = 0, 1, 2, 3, 4
 COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC, COST_QUADROTOR_QUADRATIC = 0, 1, 2, 3, 4
-SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE = 0, 1
+SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE, SAMPLER_NLN = 0, 1, 2
 BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR, FLAG_RMPPI = 1, 2, 4, 8, 16, 32
 OPT_L2_FLUSH_BYTES = 1
@@ -663,6 +663,18 @@ class ColoredNoiseDistribution(GaussianDistribution):
 
     def setOffsetDecayRate(self, v: float) -> None:  # colored_noise.cuh setOffsetDecayRate
         self.params.offset_decay_rate = v
+
+
+class NLNDistribution(GaussianDistribution):
+    """sampling_distributions/nln/nln.cuh:20-74 — normal x log-normal noise (log-MPPI) with the Gaussian parameters, the
+    Gaussian control rewrite and likelihood-ratio cost. One rank, one distribution."""
+    SAMPLER_ID = SAMPLER_NLN
+
+    def log_noise_mean_and_std_dev(self):
+        """calculateLogMeanAndVariance (nln.cu:93-105), per control."""
+        sd = np.array([self.params.std_dev[c] for c in range(self.control_dim)], np.float32)
+        var = sd * sd
+        return np.exp(np.float32(0.5) * var), np.sqrt(np.exp(var) * np.exp(var - np.float32(1.0)))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -303,3 +303,13 @@ def sampled_trajectory(dyn_id, cost_id, dyn_params, cost_params, sp, nn_theta, c
     if rc:
         raise RuntimeError(f"orc_sampled_trajectory failed: {rc}")
     return outputs, costs, crash
+
+
+def nln_noise(seed: int, draws: int, N: int, T: int, C_: int, std_dev) -> np.ndarray:
+    """Raw noise of the `draws`-th NLNDistribution::generateSamples call since seeding (host cuRAND, the reference's call
+    sequence): normal * log-normal, [N][T][C]."""
+    out = np.empty((N, T, C_), np.float32)
+    rc = lib().orc_nln_noise(C.c_ulonglong(seed), draws, N, T, C_, _p(_f32(std_dev)), _p(out))
+    if rc:
+        raise RuntimeError(f"orc_nln_noise failed: {rc}")
+    return out

@@ -1612,6 +1612,39 @@ int orc_curand_normal(unsigned long long seed, unsigned long long offset, size_t
   return rc;
 }
 
+// NLNDistribution::generateSamples' raw noise (sampling_distributions/nln/nln.cu:14-27,114-128) with the HOST XORWOW generator:
+// `draws` whole generateSamples calls are made call after call from offset 0 like the reference (C log-normal planes of
+// N*T with mean 0 / std dev sigma_c, then N*T*C normals); the last one's product normal[n][t][c] * log_normal[c][n][t] is
+// returned in out [N][T][C].
+int orc_nln_noise(unsigned long long seed, int draws, int N, int T, int C, const float* std_dev, float* out)
+{
+  curandGenerator_t g;
+  if (curandCreateGeneratorHost(&g, CURAND_RNG_PSEUDO_DEFAULT))
+    return -1;
+  int rc = 0;
+  if (curandSetPseudoRandomGeneratorSeed(g, seed))
+    rc = -2;
+  if (!rc && curandSetGeneratorOffset(g, 0ULL))
+    rc = -3;
+  const size_t plane = (size_t)N * T;
+  std::vector<float> ln(plane * C);
+  for (int k = 0; k < draws && !rc; k++)
+  {
+    for (int c = 0; c < C && !rc; c++)
+      if (curandGenerateLogNormal(g, ln.data() + (size_t)c * plane, plane, 0.0f, std_dev[c]))
+        rc = -4;
+    if (!rc && curandGenerateNormal(g, out, plane * C, 0.0f, 1.0f))
+      rc = -5;
+  }
+  curandDestroyGenerator(g);
+  if (rc)
+    return rc;
+  for (size_t i = 0; i < plane; i++)
+    for (int c = 0; c < C; c++)
+      out[i * C + c] = out[i * C + c] * ln[(size_t)c * plane + i];
+  return 0;
+}
+
 void orc_set_gaussian_controls(const float* means, const mppib_gaussian_params* sp, float* samples, int C, int T,
                                int N, int D, int optimization_stride, int iteration_num)
 {

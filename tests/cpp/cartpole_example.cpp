@@ -4,6 +4,7 @@
 #include <mppi_b200/controllers/MPPI/mppi_controller.hpp>
 #include <mppi_b200/controllers/Tube-MPPI/tube_mppi_controller.hpp>
 #include <mppi/controllers/R-MPPI/robust_mppi_controller.cuh>
+#include <mppi/sampling_distributions/nln/nln.cuh>
 #include <mppi_b200/cost_functions/cartpole/cartpole_quadratic_cost.hpp>
 #include <mppi_b200/cost_functions/double_integrator/double_integrator_circle_cost.hpp>
 #include <mppi_b200/dynamics/cartpole/cartpole_dynamics.hpp>
@@ -172,6 +173,35 @@ int main(int argc, char** argv)
            rmppi.getBaselineCost(0), rmppi.getBaselineCost(1), rmppi.getBestIndex());
     if (!(r > 1.675f && r < 2.325f))
       rc = 4;
+  }
+  // NLN (log-MPPI) sampler behind VanillaMPPI on the double integrator, through the reference's include path
+  {
+    using DI = DoubleIntegratorDynamics;
+    DI di_model(1.0f);
+    DoubleIntegratorCircleCost di_cost;
+    using NS = mppi::sampling_distributions::NLNDistribution<DI::DYN_PARAMS_T>;
+    auto np = NS::SAMPLING_PARAMS_T();
+    np.std_dev[0] = np.std_dev[1] = 0.8f;
+    NS nln_sampler(np);
+    VanillaMPPIController<DI, DoubleIntegratorCircleCost, NoFeedback, 64, 2048, NS> nln(&di_model, &di_cost, nullptr,
+                                                                                      &nln_sampler, 0.02f, 1, 2.0f, 0.0f);
+    DI::state_array x;
+    x << 2, 0, 0, 1;
+    for (int t = 0; t < 100; t++)
+    {
+      nln.computeControl(x, 1);
+      DI::control_array u = nln.getControlSeq().col(0);
+      DI::state_array xn, xd;
+      DI::output_array y;
+      di_model.step(x, xn, xd, u, y, t, 0.02f);
+      x = xn;
+      nln.slideControlSequence(1);
+    }
+    const float r = sqrtf(x(0) * x(0) + x(1) * x(1));
+    printf("nln: radius after 100 steps %f, baseline %f (log-noise mean %f)\n", r, nln.getBaselineCost(),
+           nln_sampler.getLogNoiseMean()[0]);
+    if (!(r > 1.675f && r < 2.325f))
+      rc = 6;
   }
   delete CartpoleController;
   return rc;

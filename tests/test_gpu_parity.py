@@ -981,3 +981,62 @@ def test_controller_sampled_state_trajectories():
     plain = H.VanillaMPPIController(w.dyn, w.cost, None, w.sampler, w.dt, 1, w.lambda_, w.alpha, w.T, w.N, seed=5)
     with pytest.raises(m.MppibError):
         plain.setTopNSampledControlTrajectories(3)
+
+
+# ---- NLN sampler ------------------------------------------------------------------------------------------
+def _nln_workload(name, N, T, sd):
+    w = W.by_name(name, N, T)
+    s = m.NLNDistribution(w.dyn.CONTROL_DIM, sd)
+    s.setControlCostCoeff([0.2] * w.dyn.CONTROL_DIM)
+    w.sampler = s
+    w.alpha = 0.1
+    return w
+
+
+def test_nln_noise_matches_the_reference_call_sequence():
+    """NLNDistribution::generateSamples (nln.cu:107-165) on the device generator vs the same cuRAND call sequence on the
+    host generator (oracle.nln_noise): first draw, the prefetched second draw, and a draw after re-positioning (burn).
+    Host and device cuRAND agree to ~1e-6 on normals (test_device_noise_stream_matches_host_curand_indexing); the
+    log-normal factor exp(sigma z) carries that through."""
+    N, T, sd = 2048, 64, [0.6, 0.4]  # N*T = 16 * 8192
+    w = _nln_workload("double_integrator_vanilla", N, T, sd)
+    e = w.make_engine()
+    per = 2 * N * T * 2
+    e.solve(w.x0, w.U0)
+    np.testing.assert_allclose(e.get_noise(), oracle.nln_noise(w.seed, 1, N, T, 2, sd), rtol=3e-5, atol=1e-5)
+    assert e.rng_offset() == per  # C log-normal planes + the normal block (nln.cu:114-122)
+    e.solve(w.x0, w.U0)
+    ref2 = oracle.nln_noise(w.seed, 2, N, T, 2, sd)
+    np.testing.assert_allclose(e.get_noise(), ref2, rtol=3e-5, atol=1e-5)
+    e.seed(w.seed, 0)
+    e.burn_draws(1)
+    e.solve(w.x0, w.U0)
+    np.testing.assert_allclose(e.get_noise(), ref2, rtol=3e-5, atol=1e-5)
+    e.close()
+    # sizes cuRAND cannot be re-positioned for: continuation works, a burn fails loudly
+    w = _nln_workload("cartpole", 1000, 50, [0.7])
+    e = w.make_engine()
+    e.solve(w.x0, w.U0)
+    e.solve(w.x0, w.U0)
+    np.testing.assert_allclose(e.get_noise(), oracle.nln_noise(w.seed, 2, 1000, 50, 1, [0.7]), rtol=3e-5, atol=1e-5)
+    e.seed(w.seed, 0)
+    e.burn_draws(1)
+    with pytest.raises(m.MppibError):
+        e.solve(w.x0, w.U0)
+    e.close()
+    wt = W.double_integrator_tube(1024, 32)
+    wt.sampler = m.NLNDistribution(2, [1.0, 1.0])
+    with pytest.raises(m.MppibError):  # one distribution only
+        wt.make_engine()
+
+
+@pytest.mark.parametrize("name,sd", [("cartpole", [1.5]), ("double_integrator_vanilla", [0.8, 0.8]),
+                                     ("quadrotor", [0.4, 0.4, 0.4, 0.9])])
+def test_nln_solve_parity(name, sd):
+    """Everything after the draw is the Gaussian path (NLNDistributionImpl derives from GaussianDistributionImpl): the
+    whole solve against the oracle on the device's noise, C = 1 / 2 / 4."""
+    w = _nln_workload(name, 2048, 64, sd)
+    e = w.make_engine()
+    _check_solve(w, e)
+    _check_solve(w, e, stride=2)
+    e.close()

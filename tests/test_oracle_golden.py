@@ -606,3 +606,27 @@ def test_oracle_sampled_trajectory_rows_sum_to_the_rollout_cost():
         st, _ = oracle.output_trajectory(w.dyn.DYN_ID, w.dyn.params, None, w.x0[0],
                                          np.vstack([r["samples"][0, n], np.zeros((1, 1), np.float32)]), w.dt)
         np.testing.assert_allclose(out, st[1:], rtol=1e-6, atol=1e-6)
+
+
+# ---- NLN sampler ------------------------------------------------------------------------------------------
+def test_nln_noise_oracle_follows_the_reference_call_sequence():
+    """nln.cu:114-128: C log-normal planes of N*T (mean 0, std dev sigma_c), then N*T*C normals, multiplied element-wise
+    with plane index [c][n][t]. The normals of the k-th draw therefore sit at stream offset (2k - 1) * N*T*C, and the
+    quotient noise / normal is log-normal(0, sigma_c): mean exp(sigma^2 / 2) (log_noise_mean_, nln.cu:100)."""
+    N, T, Cd, sd = 1024, 64, 2, [0.5, 0.3]  # N*T = 8 * 8192: cuRAND honours these absolute offsets
+    for k in (1, 2):
+        a = oracle.nln_noise(42, k, N, T, Cd, sd)
+        n = oracle.curand_normal(42, (2 * k - 1) * N * T * Cd, N * T * Cd).reshape(N, T, Cd)
+        ratio = (a / n).astype(np.float64)
+        assert (ratio > 0).all()
+        np.testing.assert_allclose(np.log(ratio).std(axis=(0, 1)), sd, rtol=0.01)
+        np.testing.assert_allclose(np.log(ratio).mean(axis=(0, 1)), 0.0, atol=0.005)
+        np.testing.assert_allclose(ratio.mean(axis=(0, 1)), np.exp(0.5 * np.square(sd)), rtol=0.01)
+        # plane c of the log-normal factors is its own cuRAND call: exp(sigma_c * z) of the normals at offset (2k-2)NTC + c NT
+        z = oracle.curand_normal(42, (2 * k - 2) * N * T * Cd, N * T * Cd).reshape(Cd, N, T)
+        for c in range(Cd):
+            np.testing.assert_allclose(ratio[..., c], np.exp(np.float64(sd[c]) * z[c]), rtol=2e-5)
+    s = m.NLNDistribution(2, sd)
+    mean, std = s.log_noise_mean_and_std_dev()
+    np.testing.assert_allclose(mean, np.exp(0.5 * np.square(sd)), rtol=1e-6)
+    assert s.SAMPLER_ID == 2
