@@ -64,6 +64,7 @@ enum mppib_blob
 #define MPPIB_FLAG_RMPPI 32u             /* RobustMPPI rollout semantics (core/rmppi_kernels.cu:665-866): requires                \
                                             num_distributions == 2 with distribution 0 = nominal, 1 = real system */
 #define MPPIB_FLAG_NN_TENSOR 16u         /* Autorally NN: forward pass on tcgen05 tensor cores (3xTF32) instead of FP32 FFMA2 */
+#define MPPIB_FLAG_NN_MMA 64u            /* Autorally NN: forward pass with register-level mma.sync (FP16 hi/lo split, 3 products) */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
 

@@ -636,6 +636,10 @@ static const PairEntry kPairs[] = {
                                                                           MPPIB_COST_QUADROTOR_QUADRATIC),
 };
 
+static const PairEntry kPairsMma[] = {
+  make_entry<plugins::AutorallyNNMmaDynamics, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
+};
+
 // ---- helpers ----------------------------------------------------------------------------------------------------
 static int make_tensor_map(mppib_engine& e, float* base, CUtensorMap* out)
 {
@@ -1066,6 +1070,10 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   for (const auto& p : kPairs)
     if (p.dyn_id == desc->dynamics_id && p.cost_id == desc->cost_id)
       entry = &p;
+  if (entry && desc->dynamics_id == MPPIB_DYN_AUTORALLY_NN && ((desc->flags & MPPIB_FLAG_NN_MMA) || getenv("MPPIB_NN_MMA")))
+    for (const auto& p : kPairsMma)  // same pair, network on the legacy tensor path (plugins/nn_mma.cuh)
+      if (p.cost_id == desc->cost_id)
+        entry = &p;
   if (!entry)
     return fail(MPPIB_ERR_UNSUPPORTED, "no kernel registered for dynamics %d + cost %d", desc->dynamics_id,
                 desc->cost_id);

@@ -16,6 +16,7 @@
 #pragma once
 #include "../device_utils.cuh"
 #include "../../../include/mppi_b200/params.h"
+#include "nn_mma.cuh"
 
 namespace mppib
 {
@@ -439,6 +440,52 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
         stateToOutput(x_next[m], y[m]);
       }
     }
+  }
+};
+
+// ---- Autorally NeuralNetModel<7,2,3> with the network on the legacy tensor path (plugins/nn_mma.cuh): a warp evaluates
+//      its 32 samples with mma.sync (FP16 hi / lo split, three products, FP32 accumulate). Everything around the network
+//      is AutorallyNNDynamics'. Selected by MPPIB_FLAG_NN_MMA (engine.cu). -------------------------------------------------
+struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>
+{
+  static constexpr int DYNAMICS_DIM = 4;
+  static constexpr int MAX_SPT = 1;
+  static constexpr int MAX_BLOCK_THREADS = 256;
+  static constexpr bool UNROLL_STEPS = false;
+  using Aux = AutorallyNNDynamics::Aux;
+  // fragment-ordered weights + 1 KB of transposition scratch per warp
+  static int sharedFloats(const int* /*model_dims*/, int bx)
+  {
+    return nn_mma::sharedFloats(bx);
+  }
+  using Dynamics<AutorallyNNMmaDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>::initializeDynamics;  // the Carry overload
+  __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s,
+                                                            const float* x, float* y)
+  {
+    nn_mma::load_weights(aux.theta_d, theta_s);
+#pragma unroll
+    for (int i = 0; i < 7; i++)
+      y[i] = x[i];
+  }
+  __device__ static __forceinline__ void computeKinematics(const Params& p, const float* state, float* state_der)
+  {
+    AutorallyNNDynamics::computeKinematics(p, state, state_der);
+  }
+  // warp-collective: every lane of the warp calls it (the rollout kernels keep out-of-range rows running)
+  __device__ static __forceinline__ void computeDynamics(const Params&, const float* theta_s, const float* state,
+                                                         const float* control, float* state_der)
+  {
+    float in[6], out[4];
+#pragma unroll
+    for (int i = 0; i < DYNAMICS_DIM; i++)
+      in[i] = state[i + (7 - DYNAMICS_DIM)];
+    in[4] = control[0];
+    in[5] = control[1];
+    float* scratch = const_cast<float*>(theta_s) + nn_mma::kFixedFloats + (threadIdx.x >> 5) * nn_mma::kScratchPerWarp;
+    nn_mma::forward<false>(theta_s, scratch, in, out);
+#pragma unroll
+    for (int i = 0; i < DYNAMICS_DIM; i++)
+      state_der[i + (7 - DYNAMICS_DIM)] = out[i];
   }
 };
 
