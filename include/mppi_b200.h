@@ -63,8 +63,10 @@ enum mppib_blob
 #define MPPIB_FLAG_NO_PREFETCH 8u         /* draw each solve's noise inline instead of one solve ahead on a side stream */
 #define MPPIB_FLAG_RMPPI 32u             /* RobustMPPI rollout semantics (core/rmppi_kernels.cu:665-866): requires                \
                                             num_distributions == 2 with distribution 0 = nominal, 1 = real system */
-#define MPPIB_FLAG_NN_TENSOR 16u         /* Autorally NN: forward pass on tcgen05 tensor cores (3xTF32) instead of FP32 FFMA2 */
-#define MPPIB_FLAG_NN_MMA 64u            /* Autorally NN: forward pass with register-level mma.sync (FP16 hi/lo split, 3 products) */
+#define MPPIB_FLAG_NN_TENSOR 16u         /* Autorally NN: forward pass on tcgen05 tensor cores (3xTF32) */
+#define MPPIB_FLAG_NN_MMA 64u            /* Autorally NN: forward pass with register-level mma.sync (FP16 hi/lo split, 3      \
+                                            products, FP32 accumulate) — the default for that model */
+#define MPPIB_FLAG_NN_FFMA2 128u         /* Autorally NN: forward pass as FP32 FFMA2s fed from shared memory (the round-1 form) */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
 

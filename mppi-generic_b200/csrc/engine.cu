@@ -1070,8 +1070,13 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   for (const auto& p : kPairs)
     if (p.dyn_id == desc->dynamics_id && p.cost_id == desc->cost_id)
       entry = &p;
-  if (entry && desc->dynamics_id == MPPIB_DYN_AUTORALLY_NN && ((desc->flags & MPPIB_FLAG_NN_MMA) || getenv("MPPIB_NN_MMA")))
-    for (const auto& p : kPairsMma)  // same pair, network on the legacy tensor path (plugins/nn_mma.cuh)
+  // Autorally pair: the network runs on register-level mma.sync by default (plugins/nn_mma.cuh; K1 257 us against 350 us
+  // for the FP32 FFMA2 form at N = 32768, T = 100). MPPIB_FLAG_NN_FFMA2 / MPPIB_NN_FFMA2 keep the FFMA2 form,
+  // MPPIB_FLAG_NN_TENSOR / MPPIB_NN_TENSOR select the tcgen05 kernel (which is built on the FFMA2 entry).
+  const bool nn_other = (desc->flags & (MPPIB_FLAG_NN_FFMA2 | MPPIB_FLAG_NN_TENSOR)) || getenv("MPPIB_NN_FFMA2") ||
+                        getenv("MPPIB_NN_TENSOR");
+  if (entry && desc->dynamics_id == MPPIB_DYN_AUTORALLY_NN && (!nn_other || (desc->flags & MPPIB_FLAG_NN_MMA)))
+    for (const auto& p : kPairsMma)
       if (p.cost_id == desc->cost_id)
         entry = &p;
   if (!entry)

@@ -335,7 +335,7 @@ def test_double_integrator_vanilla():
 
 
 # ---- Autorally: NN dynamics + texture cost --------------------------------------------------------------------------
-@pytest.mark.parametrize("nn_flags", [H.FLAG_NN_TENSOR, 0, H.FLAG_NN_MMA], ids=["tcgen05", "ffma2", "mma"])
+@pytest.mark.parametrize("nn_flags", [H.FLAG_NN_TENSOR, H.FLAG_NN_FFMA2, 0], ids=["tcgen05", "ffma2", "mma"])
 def test_autorally_nn_all_ones_known_answer_on_device(nn_flags):
     """tests/dynamics/ar_dynamics_nn_test.cu:483-529 (computeDynamicsGPU): theta = 1, s = 0, u = (1,-1) => s_der[3..6] = 33.
     Observed through the rollout: one step of dt from x0 = 0 gives y = (0,0,0,33dt,33dt,33dt,33dt); the speed cost
@@ -357,7 +357,7 @@ def test_autorally_nn_all_ones_known_answer_on_device(nn_flags):
     e.close()
 
 
-@pytest.mark.parametrize("nn_flags", [H.FLAG_NN_TENSOR, 0, H.FLAG_NN_MMA], ids=["tcgen05", "ffma2", "mma"])
+@pytest.mark.parametrize("nn_flags", [H.FLAG_NN_TENSOR, H.FLAG_NN_FFMA2, 0], ids=["tcgen05", "ffma2", "mma"])
 def test_autorally_cost_golden_values_on_device(nn_flags):
     """tests/cost_functions/autorally_standard_cost_test.cu:897-982 — the reference's DEVICE known answers on
     track_map_standard: speed 68.0, slip 10*atan(0.5)^2, track 1116.3333, crash 9000 at t=1 (discount 0.9).
@@ -389,7 +389,7 @@ def test_autorally_cost_golden_values_on_device(nn_flags):
     e.close()
 
 
-@pytest.mark.parametrize("nn_flags", [H.FLAG_NN_TENSOR, 0, H.FLAG_NN_MMA], ids=["tcgen05", "ffma2", "mma"])
+@pytest.mark.parametrize("nn_flags", [H.FLAG_NN_TENSOR, H.FLAG_NN_FFMA2, 0], ids=["tcgen05", "ffma2", "mma"])
 @pytest.mark.parametrize("N,T", [(2048, 100), (1000, 37), (129, 16)])
 def test_autorally_rollout_matches_cpu_oracle(nn_flags, N, T):
     w = W.autorally(N, T)
@@ -415,7 +415,7 @@ def test_autorally_tensor_core_and_ffma2_paths_agree():
     99.9 % of the samples (the rest are map-texel flips at cell boundaries), identical baselines to 1e-4, U to 2e-3."""
     w = W.autorally(4096, 100)
     a = w.make_engine(flags=H.FLAG_NN_TENSOR)
-    b = w.make_engine()
+    b = w.make_engine(flags=H.FLAG_NN_FFMA2)
     assert a.launch_info()["block"] == 128
     Ua, sa = a.solve(w.x0, w.U0)
     Ub, sb = b.solve(w.x0, w.U0)
@@ -434,8 +434,8 @@ def test_autorally_mma_and_ffma2_paths_agree():
     as the tcgen05 comparison above; also through Tube-style D = 2 and the sampled-trajectory kernel (both instantiate the
     warp-collective network)."""
     w = W.autorally(4096, 100)
-    a = w.make_engine(flags=H.FLAG_NN_MMA | H.FLAG_WRITEBACK_CONTROLS)
-    b = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    a = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)  # the default: mma.sync
+    b = w.make_engine(flags=H.FLAG_NN_FFMA2 | H.FLAG_WRITEBACK_CONTROLS)
     Ua, sa = a.solve(w.x0, w.U0)
     Ub, sb = b.solve(w.x0, w.U0)
     np.testing.assert_array_equal(a.get_noise(), b.get_noise())
@@ -455,7 +455,7 @@ def test_autorally_mma_and_ffma2_paths_agree():
     w2.x0 = np.tile(w2.x0, (2, 1))
     w2.x0[1, :2] += 0.05
     w2.U0 = np.tile(w2.U0, (2, 1, 1))
-    e = w2.make_engine(flags=H.FLAG_NN_MMA)
+    e = w2.make_engine()
     _check_solve(w2, e)
     e.close()
 
