@@ -102,10 +102,10 @@ def _workload(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch from the `ncu --set full` captures summarised under
-# profiles/ (r01_final_autorally_k1_kernels.csv, r01_final_racer_kernels.csv, r01_cartpole_v4_kernels.csv,
+# profiles/ (r01_final_autorally_k1_mma_kernels.csv, r01_final_racer_kernels.csv, r01_cartpole_v4_kernels.csv,
 # r01_double_integrator_tube_v4_kernels.csv) — only valid for the exact single-GPU configuration that was captured.
 _NCU_K1_TRAFFIC_BYTES = {
-    "autorally_nn_N32768_T100": 26_291_200,                      # algorithmic 26_214_400: the noise is read once
+    "autorally_nn_N32768_T100": 26_280_960,                      # mma.sync K1 (r01_final_autorally_k1_mma_kernels.csv); algorithmic 26_214_400
     "cartpole_vanilla_N8192_T100": 3_308_544,                    # algorithmic 3_276_800
     "double_integrator_tube_N16384_T150": 19_710_208,            # algorithmic 19_660_800
     "racer_lstm_H4_colored_N65536_T150": 128_668_928 + 54_798_592,  # streaming K1: eps read + controls written + re-read
@@ -341,7 +341,7 @@ def run_engine(args):
         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_l2_flushed": t_cold["rollout_ms"],
         "kernel_ms_l2_warm": t_warm["rollout_ms"],
         "stage_ms_l2_warm": {k: t_warm[k] for k in ("noise_ms", "rollout_ms", "reduce_ms", "total_ms")},
-        "note": "K1 is bound by the T-step dependency chain (and FP32/MUFU work for NN dynamics), not by HBM: see DESIGN.md",
+        "note": "K1 is bound by the T-step dependency chain (and MUFU / tensor-pipe work for NN dynamics), not by HBM: see DESIGN.md",
     }
 
     if rank == 0:

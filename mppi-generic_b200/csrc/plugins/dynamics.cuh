@@ -469,7 +469,15 @@ struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar
   }
   __device__ static __forceinline__ void computeKinematics(const Params& p, const float* state, float* state_der)
   {
+#ifdef MPPIB_EXP_FAST_SINCOS  // ablation only (tools/run_mma_exp.sh): the reference's device code uses cosf / sinf
+    float sn, cs;
+    __sincosf(state[2], &sn, &cs);
+    state_der[0] = cs * state[4] - sn * state[5];
+    state_der[1] = sn * state[4] + cs * state[5];
+    state_der[2] = -state[6];
+#else
     AutorallyNNDynamics::computeKinematics(p, state, state_der);
+#endif
   }
   // warp-collective: every lane of the warp calls it (the rollout kernels keep out-of-range rows running)
   __device__ static __forceinline__ void computeDynamics(const Params&, const float* theta_s, const float* state,
@@ -482,7 +490,11 @@ struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar
     in[4] = control[0];
     in[5] = control[1];
     float* scratch = const_cast<float*>(theta_s) + nn_mma::kFixedFloats + (threadIdx.x >> 5) * nn_mma::kScratchPerWarp;
+#ifdef MPPIB_EXP_NEWTON  // ablation only: reciprocal of the tanh on the FP32 pipe instead of MUFU
+    nn_mma::forward<true>(theta_s, scratch, in, out);
+#else
     nn_mma::forward<false>(theta_s, scratch, in, out);
+#endif
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       state_der[i + (7 - DYNAMICS_DIM)] = out[i];
