@@ -3,6 +3,10 @@
 #pragma once
 #include <vector>
 
+#include <cstdio>
+#include <string>
+#include <vector>
+
 #include "../cost.hpp"
 
 #if !defined(__VECTOR_TYPES_H__) && !defined(__CUDACC__)
@@ -82,6 +86,41 @@ public:
     params_.r_c1 = float3{ 1.0f / (x_max - x_min), 0, 0 };
     params_.r_c2 = float3{ 0, 1.0f / (y_max - y_min), 0 };
     params_.trs = float3{ -x_min / (x_max - x_min), -y_min / (y_max - y_min), 1 };
+  }
+  // ARStandardCostImpl::loadTrackData (ar_standard_cost.cu:85-142): npz with "xBounds", "yBounds", "pixelsPerMeter" and
+  // "channel0".."channel3" (float32, row-major [height][width]); returns the CPU copy like the reference (empty on error)
+  std::vector<float4> loadTrackData(std::string map_path)
+  {
+    float xb[2], yb[2], ppm[1];
+    if (mppib_host_npz_read(map_path.c_str(), "xBounds", xb, 2, nullptr, nullptr, nullptr) != MPPIB_OK ||
+        mppib_host_npz_read(map_path.c_str(), "yBounds", yb, 2, nullptr, nullptr, nullptr) != MPPIB_OK ||
+        mppib_host_npz_read(map_path.c_str(), "pixelsPerMeter", ppm, 1, nullptr, nullptr, nullptr) != MPPIB_OK)
+    {
+      fprintf(stderr, "ERROR: map path invalid, %s (%s)\n", map_path.c_str(), mppib_last_error());
+      return std::vector<float4>();
+    }
+    const int width = int((xb[1] - xb[0]) * ppm[0]), height = int((yb[1] - yb[0]) * ppm[0]);
+    if (width <= 0 || height <= 0)
+    {
+      fprintf(stderr, "ERROR: load track has invalid sizes\n");
+      return std::vector<float4>();
+    }
+    std::vector<float> ch[4];
+    for (int c = 0; c < 4; c++)
+    {
+      ch[c].resize((size_t)width * height);
+      size_t n = 0;
+      const std::string key = "channel" + std::to_string(c);
+      if (mppib_host_npz_read(map_path.c_str(), key.c_str(), ch[c].data(), ch[c].size(), &n, nullptr, nullptr) != MPPIB_OK ||
+          n != ch[c].size())
+      {
+        fprintf(stderr, "ERROR: %s of %s does not hold %d x %d values (%s)\n", key.c_str(), map_path.c_str(), width, height,
+                mppib_last_error());
+        return std::vector<float4>();
+      }
+    }
+    setTrackData(ch[0].data(), ch[1].data(), ch[2].data(), ch[3].data(), xb[0], xb[1], yb[0], yb[1], ppm[0]);
+    return track_costs_;
   }
   void updateTransform(const Eigen::Matrix3f& m, const Eigen::Vector3f& trs)
   {  // ar_standard_cost.cu:188-204

@@ -3,6 +3,7 @@
 #pragma once
 #include <cmath>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "../dynamics.hpp"
@@ -48,6 +49,37 @@ public:
       if (!std::isfinite(v))
         throw std::invalid_argument("NN parameters must be finite");
     theta_ = data;
+  }
+  // ar_nn_model.cu:58-61 -> FNNHelper::loadParams (fnn_helper.cu:44-127): npz arrays "dynamics_W<i>" (out x in, row-major)
+  // and "dynamics_b<i>", i = 1.., float64 in the reference's files; the layer sizes are taken from the arrays
+  void loadParams(const std::string& model_path)
+  {
+    std::vector<int> layers;
+    std::vector<float> theta;
+    for (int i = 1;; i++)
+    {
+      const std::string wn = "dynamics_W" + std::to_string(i), bn = "dynamics_b" + std::to_string(i);
+      size_t nw = 0, nb = 0;
+      if (mppib_host_npz_read(model_path.c_str(), bn.c_str(), nullptr, 0, &nb, nullptr, nullptr) != MPPIB_OK)
+      {
+        if (i == 1)
+          throw std::runtime_error(std::string("Could not load neural net model: ") + mppib_last_error());
+        break;
+      }
+      if (mppib_host_npz_read(model_path.c_str(), wn.c_str(), nullptr, 0, &nw, nullptr, nullptr) != MPPIB_OK || nb == 0 ||
+          nw % nb != 0)
+        throw std::runtime_error(std::string("Could not load neural net model: ") + mppib_last_error());
+      if (i == 1)
+        layers.push_back((int)(nw / nb));
+      if ((size_t)layers.back() * nb != nw)
+        throw std::runtime_error("Could not load neural net model: " + wn + " does not match the previous layer");
+      layers.push_back((int)nb);
+      const size_t at = theta.size();
+      theta.resize(at + nw + nb);
+      MPPIB_HANDLE(mppib_host_npz_read(model_path.c_str(), wn.c_str(), theta.data() + at, nw, nullptr, nullptr, nullptr));
+      MPPIB_HANDLE(mppib_host_npz_read(model_path.c_str(), bn.c_str(), theta.data() + at + nw, nb, nullptr, nullptr, nullptr));
+    }
+    updateModel(layers, theta);
   }
   const float* nnWeights() const
   {

@@ -13,6 +13,8 @@
  */
 #ifndef MPPI_B200_HOST_TWINS_H_
 #define MPPI_B200_HOST_TWINS_H_
+#include <stddef.h>
+
 #include "../mppi_b200.h"
 #ifdef __cplusplus
 extern "C" {
@@ -52,6 +54,13 @@ void mppib_host_free_energy(const mppib_solve_stats* st, int num_rollouts, float
 /* CPU twin of the K2 merge (csrc/combine_kernel.cuh): records [nrec][D][pstride] = (beta, eta, sum w^2, -, V[TC]). */
 int mppib_host_merge_records(const float* records, int nrec, int D, int TC, int pstride, float lambda, int normalize,
                              float* out);
+/* One array of a NumPy .npz archive, converted to float — the input format of the reference's FNNHelper::loadParams
+ * (utils/nn_helpers/fnn_helper.cu:44-127: "dynamics_W<i>" / "dynamics_b<i>", float64) and ARStandardCostImpl::loadTrackData
+ * (cost_functions/autorally/ar_standard_cost.cu:85-142: "xBounds", "yBounds", "pixelsPerMeter", "channel0..3", float32),
+ * which go through cnpy::npz_load. `name` without ".npy". Stored and deflated members; little-endian f4 / f8 / i4 / i8; C
+ * order; up to 4 dimensions. out == NULL: only *count / shape4 / *ndim are filled. */
+int mppib_host_npz_read(const char* path, const char* name, float* out, size_t capacity, size_t* count, int* shape4,
+                        int* ndim);
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ OUT="$HERE/libmppi_b200.so"
   -Xcompiler -fPIC,-Wall,-Wno-unused-function -shared \
   -Xptxas -v \
   "$@" \
-  -o "$OUT" "$HERE/csrc/engine.cu" "$HERE/csrc/host_twins.cpp" \
+  -o "$OUT" "$HERE/csrc/engine.cu" "$HERE/csrc/host_twins.cpp" "$HERE/csrc/npz_reader.cpp" \
   -I"$HERE/../include" \
-  -L"$CUDA_HOME/lib64" -Xlinker -rpath -Xlinker "$CUDA_HOME/lib64" -lcurand -lcufft -ldl
+  -L"$CUDA_HOME/lib64" -Xlinker -rpath -Xlinker "$CUDA_HOME/lib64" -lcurand -lcufft -ldl -lz
 echo "built $OUT"

@@ -109,6 +109,18 @@ constexpr int kNcclFloat = 7;  // ncclFloat32
 
 }  // namespace
 
+
+// for the library's other translation units (npz_reader.cpp): same thread-local message, not part of the ABI
+extern "C" __attribute__((visibility("hidden"))) int mppib_set_last_error(int status, const char* fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return fail(status, "%s", buf);
+}
+
 using namespace mppib;
 
 // ---- engine state -----------------------------------------------------------------------------------------------

@@ -178,7 +178,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
-    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
 
@@ -245,6 +245,9 @@ def lib() -> C.CDLL:
     L.mppib_host_free_energy.argtypes = [C.POINTER(SolveStats), C.c_int, C.c_float, vp]
     L.mppib_host_free_energy.restype = None
     L.mppib_host_merge_records.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]
+    L.mppib_host_npz_read.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int * 4),
+                                      ip]
+    L.mppib_sample_trajectories.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -390,6 +393,35 @@ class NeuralNetModel(_Dynamics):
         if data.size != AR_NN_NUM_PARAMS or not np.all(np.isfinite(data)):
             raise ValueError("NN parameter vector must hold 1412 finite floats")
         self.nn_theta = data.copy()
+
+    def loadParams(self, model_path: str) -> None:
+        """ar_nn_model.cu:58-61 -> FNNHelper::loadParams (fnn_helper.cu:44-127): npz arrays "dynamics_W<i>" (out x in) and
+        "dynamics_b<i>", i = 1..; read through the library's own npz reader (mppib_host_npz_read) like the C++ mirror."""
+        layers, chunks, i = [], [], 1
+        while True:
+            try:
+                b = npz_read(model_path, f"dynamics_b{i}")
+            except MppibError:
+                if i == 1:
+                    raise
+                break
+            W_ = npz_read(model_path, f"dynamics_W{i}")
+            if i == 1:
+                layers.append(W_.size // b.size)
+            layers.append(b.size)
+            chunks += [W_.ravel(), b.ravel()]
+            i += 1
+        self.updateModel(layers, np.concatenate(chunks))
+
+
+def npz_read(path: str, name: str) -> np.ndarray:
+    """One array of a .npz archive through mppib_host_npz_read (float32, original shape)."""
+    count, ndim = C.c_size_t(), C.c_int()
+    shape = (C.c_int * 4)()
+    _check(lib().mppib_host_npz_read(path.encode(), name.encode(), None, 0, C.byref(count), C.byref(shape), C.byref(ndim)))
+    out = np.empty(count.value, np.float32)
+    _check(lib().mppib_host_npz_read(path.encode(), name.encode(), _ptr(out), out.size, None, None, None))
+    return out.reshape([shape[i] for i in range(ndim.value)])
 
 
 class RacerDubinsElevationLSTMSteering(_Dynamics):
@@ -562,6 +594,24 @@ class ARStandardCost(_Cost):
             self.params.r_c1[i] = float(m[i][0])
             self.params.r_c2[i] = float(m[i][1])
             self.params.trs[i] = float(trs[i])
+
+    def loadTrackDataFromFile(self, map_path: str) -> np.ndarray:
+        """ARStandardCostImpl::loadTrackData(map_path) (ar_standard_cost.cu:85-142): npz with xBounds, yBounds,
+        pixelsPerMeter, channel0..3 (row-major [height][width]). Returns the [height][width][4] texture."""
+        xb, yb = npz_read(map_path, "xBounds"), npz_read(map_path, "yBounds")
+        ppm = float(npz_read(map_path, "pixelsPerMeter").ravel()[0])
+        w, h = int((xb[1] - xb[0]) * ppm), int((yb[1] - yb[0]) * ppm)
+        if w <= 0 or h <= 0:
+            raise ValueError("load track has invalid sizes")
+        tex = np.zeros((h, w, 4), np.float32)
+        for c in range(4):
+            ch = npz_read(map_path, f"channel{c}")
+            if ch.size != w * h:
+                raise ValueError(f"channel{c} does not hold {w} x {h} values")
+            tex[..., c] = ch.reshape(h, w)
+        self.loadTrackData(tex[..., 0], float(xb[0]), float(xb[1]), float(yb[0]), float(yb[1]), ppm)
+        self.setCostmap(tex, w, h)
+        return tex
 
     def loadTrackData(self, channel0: np.ndarray, x_min: float, x_max: float, y_min: float, y_max: float,
                       ppm: float) -> None:
