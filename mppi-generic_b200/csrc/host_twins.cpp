@@ -63,7 +63,7 @@ const mppib_control_limits* limits_of(int dyn_id, const void* p)
 // baseline clones selected at load time.
 struct FnnT
 {
-  float WT1[6 * 32], b1[32], WT2[32 * 32], b2[32], WT3[32 * 4], b3[4];
+  float WT1[6 * 32], b1[32], WT2[32 * 32], b2[32], W3[4 * 32], b3[4];  // W3 keeps the reference's [out][in] order
 };
 void fnn_transpose(const float* theta, FnnT& t)
 {
@@ -75,9 +75,7 @@ void fnn_transpose(const float* theta, FnnT& t)
     for (int k = 0; k < 32; k++)
       t.WT2[k * 32 + j] = theta[224 + j * 32 + k];
   memcpy(t.b2, theta + 1248, sizeof(t.b2));
-  for (int j = 0; j < 4; j++)
-    for (int k = 0; k < 32; k++)
-      t.WT3[k * 4 + j] = theta[1280 + j * 32 + k];
+  memcpy(t.W3, theta + 1280, sizeof(t.W3));
   memcpy(t.b3, theta + 1408, sizeof(t.b3));
 }
 
@@ -112,39 +110,95 @@ static inline float sigmoid_host(float x)  // activation_functions.cuh:49-59 (ho
   return 1.0f / (1.0f + exp_host(-x));
 }
 
+// GCC / clang generic vectors: the same source lowers to 8-lane AVX2 + FMA in the x86-64-v3 clone and to SSE2 pairs in the
+// baseline clone. Written out by hand because the auto-vectoriser keeps tanh scalar (clamp branches, float -> int -> float
+// round trip): 64 scalar tanh with a vdivss each were 2/3 of the forward pass.
+typedef float v8f __attribute__((vector_size(32), aligned(4)));
+typedef int v8i __attribute__((vector_size(32), aligned(4)));
+static inline v8f splat8(float v)
+{
+  return v8f{ v, v, v, v, v, v, v, v };
+}
+static inline v8f load8(const float* p)
+{
+  v8f v;
+  memcpy(&v, p, sizeof(v));
+  return v;
+}
+static inline void store8(float* p, v8f v)
+{
+  memcpy(p, &v, sizeof(v));
+}
+// exp_host / tanh_host above, eight lanes at a time (same constants, same operation order)
+static inline v8f exp8(v8f z)
+{
+  const v8f hi = splat8(30.0f), lo = splat8(-30.0f);
+  z = z > hi ? hi : (z < lo ? lo : z);
+  const v8f magic = splat8(12582912.0f);
+  const v8f nf = (z * splat8(1.44269504088896341f) + magic) - magic;
+  v8f r = z - nf * splat8(0.693145751953125f);
+  r = r - nf * splat8(1.42860682030941723212e-6f);
+  v8f p = splat8(1.0f / 5040.0f);
+  p = p * r + splat8(1.0f / 720.0f);
+  p = p * r + splat8(1.0f / 120.0f);
+  p = p * r + splat8(1.0f / 24.0f);
+  p = p * r + splat8(1.0f / 6.0f);
+  p = p * r + splat8(0.5f);
+  p = p * r + splat8(1.0f);
+  p = p * r + splat8(1.0f);
+  const v8i bits = (__builtin_convertvector(nf, v8i) + 127) << 23;
+  v8f scale;
+  memcpy(&scale, &bits, sizeof(scale));
+  return p * scale;
+}
+static inline v8f tanh8(v8f x)
+{
+  return splat8(1.0f) - splat8(2.0f) / (exp8(splat8(2.0f) * x) + splat8(1.0f));
+}
+
 __attribute__((target_clones("arch=x86-64-v3", "default"))) void fnn_6_32_32_4(const FnnT& t, const float* in6,
                                                                               float* out4)
 {
-  float a1[32], a2[32], acc[32];
-  for (int j = 0; j < 32; j++)
-    acc[j] = 0.0f;
+  // layers 1 and 2: the 32 outputs are four 8-lane vectors, k ascending per neuron (fnn_helper.cu:354-382), bias last
+  v8f acc[4], a1[4], a2[4];
+  for (int v = 0; v < 4; v++)
+    acc[v] = splat8(0.0f);
   for (int k = 0; k < 6; k++)
   {
-    const float xk = in6[k];
-    for (int j = 0; j < 32; j++)
-      acc[j] += t.WT1[k * 32 + j] * xk;
+    const v8f xk = splat8(in6[k]);
+    for (int v = 0; v < 4; v++)
+      acc[v] += load8(t.WT1 + k * 32 + 8 * v) * xk;
   }
-  for (int j = 0; j < 32; j++)
-    a1[j] = tanh_host(acc[j] + t.b1[j]);
-  for (int j = 0; j < 32; j++)
-    acc[j] = 0.0f;
-  for (int k = 0; k < 32; k++)
+  for (int v = 0; v < 4; v++)
+    a1[v] = tanh8(acc[v] + load8(t.b1 + 8 * v));
+  float a1s[32];
+  for (int v = 0; v < 4; v++)
+    store8(a1s + 8 * v, a1[v]);
+  // layer 2: even and odd k accumulate separately (two FMA chains of 16 instead of one of 32 on the critical path) and
+  // are added at the end; like layer 3 below a reassociation of a few ulp
+  v8f acc_odd[4];
+  for (int v = 0; v < 4; v++)
+    acc[v] = acc_odd[v] = splat8(0.0f);
+  for (int k = 0; k < 32; k += 2)
   {
-    const float xk = a1[k];
-    for (int j = 0; j < 32; j++)
-      acc[j] += t.WT2[k * 32 + j] * xk;
+    const v8f xa = splat8(a1s[k]), xb = splat8(a1s[k + 1]);
+    for (int v = 0; v < 4; v++)
+    {
+      acc[v] += load8(t.WT2 + k * 32 + 8 * v) * xa;
+      acc_odd[v] += load8(t.WT2 + (k + 1) * 32 + 8 * v) * xb;
+    }
   }
-  for (int j = 0; j < 32; j++)
-    a2[j] = tanh_host(acc[j] + t.b2[j]);
-  float o[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-  for (int k = 0; k < 32; k++)
-  {
-    const float xk = a2[k];
-    for (int j = 0; j < 4; j++)
-      o[j] += t.WT3[k * 4 + j] * xk;
-  }
+  for (int v = 0; v < 4; v++)
+    a2[v] = tanh8((acc[v] + acc_odd[v]) + load8(t.b2 + 8 * v));
+  // layer 3: four 32-term dot products, eight interleaved partial sums each (one 8-lane FMA chain of length 4) — a
+  // reassociation of the kind Eigen's packet products in the reference's host code make as well
   for (int j = 0; j < 4; j++)
-    out4[j] = o[j] + t.b3[j];
+  {
+    v8f part = load8(t.W3 + j * 32) * a2[0];
+    for (int v = 1; v < 4; v++)
+      part += load8(t.W3 + j * 32 + 8 * v) * a2[v];
+    out4[j] = (((part[0] + part[4]) + (part[1] + part[5])) + ((part[2] + part[6]) + (part[3] + part[7]))) + t.b3[j];
+  }
 }
 
 static inline int state_deriv(int dyn_id, const void* p, const FnnT* nn, const float* x, const float* u, float* xdot)
