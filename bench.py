@@ -112,6 +112,18 @@ _NCU_K1_TRAFFIC_BYTES = {
 }
 
 
+def _k1_variant(w):
+    """Which form of the Autorally network K1 ran with (engine.cu: default mma.sync, env / flag overrides)."""
+    if type(w.dyn).__name__ != "NeuralNetModel":
+        return {}
+    if os.environ.get("MPPIB_NN_TENSOR"):
+        return {"nn_form": "tcgen05 3xTF32, FP32 accumulate"}
+    if os.environ.get("MPPIB_NN_FFMA2"):
+        return {"nn_form": "FP32 FFMA2 from shared memory"}
+    return {"nn_form": "mma.sync m16n8k16, FP16 hi/lo operands in three products, FP32 accumulate (FP32-equivalent: "
+                       "5.1e-7 max error against FP64, tools/mma_probe.cu); state, cost and reductions in FP32"}
+
+
 def _ncu_traffic(w, world):
     return _NCU_K1_TRAFFIC_BYTES.get(w.name) if world == 1 else None
 
@@ -361,6 +373,7 @@ def run_engine(args):
             "config": {"workload": w.name, "num_rollouts": w.N, "num_timesteps": w.T, "controller": w.controller,
                        "parallelism": f"rollout-sharded dp{world}", "rollouts_per_gpu": e.n_local,
                        "k1_launch": info,
+                       **_k1_variant(w),
                        "l2": "noise buffer is regenerated on the device every step (K0 -> K1 through L2/HBM); no data "
                              "is reused across steps; the roofline pass flushes L2 (256 MiB memset) between K0 and K1"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
