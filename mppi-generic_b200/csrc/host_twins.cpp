@@ -274,17 +274,32 @@ inline float normalize_angle(float a)  // utils/angle_utils.cuh
 }
 
 // LSTMHelper::forward (host), utils/nn_helpers/lstm_helper.cu:267-339: gates from W_*m h + W_*i x + b, FNN head on [h; x]
-float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
+// In-place activations of n values, eight lanes at a time through exp8 (the scalar exp_host per value — ~40 of them per
+// step at H = 4, L1 = 20 — was most of the roll-forward): kind 0 = sigmoid 1 / (1 + exp(-x)), kind 1 = tanh.
+static inline void activate_n(float* v, int n, int kind)
+{
+  for (int i = 0; i < n; i += 8)
+  {
+    float buf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    const int m = n - i < 8 ? n - i : 8;
+    memcpy(buf, v + i, sizeof(float) * m);
+    const v8f x = load8(buf);
+    const v8f r = kind ? tanh8(x) : splat8(1.0f) / (splat8(1.0f) + exp8(-x));
+    store8(buf, r);
+    memcpy(v + i, buf, sizeof(float) * m);
+  }
+}
+
+__attribute__((target_clones("arch=x86-64-v3", "default"))) float lstm_head_forward(const mppib_host_lstm* net,
+                                                                                   const float* in4)
 {
   const int H = net->hidden_dim, I = MPPIB_RACER_LSTM_INPUT_DIM, L1 = net->head_hidden;
   const int HH = H * H, IH = H * I;
   const float* w = net->theta;
   const float* bias = w + 4 * HH + 4 * IH;
-  float hn[64], cn[64];  // H <= 64 (engine limit)
-  for (int i = 0; i < H; i++)
-  {
-    float g[4];
-    for (int k = 0; k < 4; k++)  // k: input, forget, output, cell-update
+  float g[4][64];  // gate pre-activations [input, forget, output, cell-update][H], H <= 64 (engine limit)
+  for (int k = 0; k < 4; k++)
+    for (int i = 0; i < H; i++)
     {
       const float* Wm = w + k * HH + i * H;
       const float* Wi = w + 4 * HH + k * IH + i * I;
@@ -293,18 +308,24 @@ float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
         hm += Wm[j] * net->hidden[j];
       for (int j = 0; j < I; j++)
         im += Wi[j] * in4[j];
-      g[k] = (hm + im) + bias[k * H + i];
+      g[k][i] = (hm + im) + bias[k * H + i];
     }
-    // exp-based activations without libm calls (exp_host above; |abs error| < 2e-7 against expf / tanhf)
-    const float gi = sigmoid_host(g[0]), gf = sigmoid_host(g[1]), go = sigmoid_host(g[2]);
-    cn[i] = gi * tanh_host(g[3]) + gf * net->cell[i];
-    hn[i] = go * tanh_host(cn[i]);
-  }
+  // exp-based activations without libm calls (exp8 above; |abs error| < 2e-7 against expf / tanhf)
+  activate_n(g[0], H, 0);
+  activate_n(g[1], H, 0);
+  activate_n(g[2], H, 0);
+  activate_n(g[3], H, 1);
+  float hn[64], cn[64];
+  for (int i = 0; i < H; i++)
+    cn[i] = hn[i] = g[0][i] * g[3][i] + g[1][i] * net->cell[i];
+  activate_n(hn, H, 1);
+  for (int i = 0; i < H; i++)
+    hn[i] = g[2][i] * hn[i];
   memcpy(net->hidden, hn, sizeof(float) * H);
   memcpy(net->cell, cn, sizeof(float) * H);
   const float* hd = w + 4 * HH + 4 * IH + 6 * H;  // head {H+I, L1, 1}: W1 | b1 | W2 | b2 (fnn_helper.cu:176-183)
   const int IN = H + I;
-  float out = 0.0f;
+  float a1[64];
   for (int k = 0; k < L1; k++)
   {
     float a = 0.0f;
@@ -312,8 +333,12 @@ float lstm_head_forward(const mppib_host_lstm* net, const float* in4)
       a += hd[k * IN + j] * hn[j];
     for (int j = 0; j < I; j++)
       a += hd[k * IN + H + j] * in4[j];
-    out += hd[L1 * IN + L1 + k] * tanh_host(a + hd[L1 * IN + k]);
+    a1[k] = a + hd[L1 * IN + k];
   }
+  activate_n(a1, L1, 1);
+  float out = 0.0f;
+  for (int k = 0; k < L1; k++)
+    out += hd[L1 * IN + L1 + k] * a1[k];
   return out + hd[L1 * IN + 2 * L1];
 }
 
