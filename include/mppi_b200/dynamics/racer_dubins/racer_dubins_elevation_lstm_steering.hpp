@@ -11,6 +11,7 @@
 #pragma once
 #include <cmath>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "../dynamics.hpp"
@@ -101,6 +102,56 @@ public:
   int lstmBlock() const
   {
     return 4 * hidden_dim_ * hidden_dim_ + 4 * hidden_dim_ * MPPIB_RACER_LSTM_INPUT_DIM + 6 * hidden_dim_;
+  }
+  // LSTMHelper::loadParams (utils/nn_helpers/lstm_helper.cu:496-585) for the prediction network: npz arrays
+  // "<prefix>lstm/weight_hh_l0" [4H][H], "lstm/weight_ih_l0" [4H][4], "lstm/bias_hh_l0" + "lstm/bias_ih_l0" [4H] in PyTorch's
+  // gate order (input, forget, cell, output), head as "<prefix>output/dynamics_W<i>" / "_b<i>"; "model/" is tried first like
+  // the reference does (:520-523). Packed order: i, f, o, c (lstm_helper.cu:72-88). The initial hidden / cell state (the init
+  // network's output) is left untouched.
+  void loadParamsLSTM(const std::string& model_path, std::string prefix = "")
+  {
+    if (!prefix.empty() && prefix.back() != '/')
+      prefix += "/";
+    if (mppib_host_npz_read(model_path.c_str(), ("model/" + prefix + "lstm/weight_hh_l0").c_str(), nullptr, 0, nullptr,
+                            nullptr, nullptr) == MPPIB_OK)
+      prefix = "model/" + prefix;
+    const int H = hidden_dim_, I = MPPIB_RACER_LSTM_INPUT_DIM;
+    auto read = [&](const std::string& name, size_t expect) {
+      std::vector<float> v(expect);
+      size_t n = 0;
+      if (mppib_host_npz_read(model_path.c_str(), (prefix + name).c_str(), v.data(), v.size(), &n, nullptr, nullptr) !=
+              MPPIB_OK ||
+          n != expect)
+        throw std::runtime_error("Could not load LSTM model (" + prefix + name + "): " + mppib_last_error());
+      return v;
+    };
+    const std::vector<float> whh = read("lstm/weight_hh_l0", (size_t)4 * H * H), wih = read("lstm/weight_ih_l0", (size_t)4 * H * I),
+                             bhh = read("lstm/bias_hh_l0", (size_t)4 * H), bih = read("lstm/bias_ih_l0", (size_t)4 * H);
+    const int order[4] = { 0, 1, 3, 2 };  // file blocks i, f, c, o -> packed i, f, o, c
+    std::vector<float> lstm(theta_.begin(), theta_.begin() + lstmBlock());
+    size_t at = 0;
+    for (int k : order)
+      for (int i = 0; i < H * H; i++)
+        lstm[at++] = whh[(size_t)k * H * H + i];
+    for (int k : order)
+      for (int i = 0; i < H * I; i++)
+        lstm[at++] = wih[(size_t)k * H * I + i];
+    for (int k : order)
+      for (int i = 0; i < H; i++)
+        lstm[at++] = (float)((double)bhh[k * H + i] + (double)bih[k * H + i]);
+    const int IN = H + I, L1 = head_hidden_;
+    std::vector<float> head;
+    const std::vector<float> w1 = read("output/dynamics_W1", (size_t)L1 * IN), b1 = read("output/dynamics_b1", (size_t)L1),
+                             w2 = read("output/dynamics_W2", (size_t)L1), b2 = read("output/dynamics_b2", 1);
+    head.insert(head.end(), w1.begin(), w1.end());
+    head.insert(head.end(), b1.begin(), b1.end());
+    head.insert(head.end(), w2.begin(), w2.end());
+    head.insert(head.end(), b2.begin(), b2.end());
+    setAllValues(lstm, head);
+  }
+  const std::vector<float>& getTheta() const
+  {  // packed LSTM block (incl. initial hidden / cell) followed by the packed head
+    return theta_;
   }
   // LSTMHelper::setAllValues(lstm, output) (lstm_helper.cuh:65-72)
   void setAllValues(const std::vector<float>& lstm, const std::vector<float>& output)

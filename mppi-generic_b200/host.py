@@ -486,6 +486,43 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
             raise ValueError("LSTM parameters must be finite")
         self.lstm_theta = np.concatenate([lstm, output]).astype(np.float32)
 
+    def loadParamsLSTM(self, model_path: str, prefix: str = "") -> None:
+        """LSTMHelper::loadParams (utils/nn_helpers/lstm_helper.cu:496-585) for the prediction network: npz arrays
+        "<prefix>lstm/weight_hh_l0" [4H][H], "lstm/weight_ih_l0" [4H][4], "lstm/bias_hh_l0" + "lstm/bias_ih_l0" [4H] in
+        PyTorch's gate order (input, forget, cell, output) and the head as "<prefix>output/dynamics_W<i>" / "_b<i>"; a leading
+        "model/" is tried like the reference does (:520-523). The packed order here is the reference's i, f, o, c
+        (lstm_helper.cu:72-88). The initial hidden / cell state (the init network's output) is left untouched."""
+        if prefix and not prefix.endswith("/"):
+            prefix += "/"
+        try:
+            npz_read(model_path, "model/" + prefix + "lstm/weight_hh_l0")
+            prefix = "model/" + prefix
+        except MppibError:
+            pass
+        H, I = self.hidden_dim, 4
+        whh = npz_read(model_path, prefix + "lstm/weight_hh_l0").astype(np.float64)
+        wih = npz_read(model_path, prefix + "lstm/weight_ih_l0").astype(np.float64)
+        bias = (npz_read(model_path, prefix + "lstm/bias_hh_l0").astype(np.float64) +
+                npz_read(model_path, prefix + "lstm/bias_ih_l0").astype(np.float64))
+        if whh.shape != (4 * H, H) or wih.shape != (4 * H, I) or bias.shape != (4 * H,):
+            raise ValueError(f"LSTM arrays do not match hidden_dim = {H}, input_dim = {I}")
+        order = (0, 1, 3, 2)  # file blocks i, f, c(g), o -> packed i, f, o, c
+        lstm = np.concatenate([np.concatenate([whh[k * H:(k + 1) * H].ravel() for k in order]),
+                               np.concatenate([wih[k * H:(k + 1) * H].ravel() for k in order]),
+                               np.concatenate([bias[k * H:(k + 1) * H] for k in order]),
+                               self.lstm_theta[self._lstm_block() - 2 * H:self._lstm_block()]])
+        head, i = [], 1
+        while True:
+            try:
+                b = npz_read(model_path, f"{prefix}output/dynamics_b{i}")
+            except MppibError:
+                if i == 1:
+                    raise
+                break
+            head += [npz_read(model_path, f"{prefix}output/dynamics_W{i}").ravel(), b.ravel()]
+            i += 1
+        self.setAllValues(lstm, np.concatenate(head))
+
     def setInitialHiddenCell(self, hidden, cell) -> None:
         """LSTMHelper::updateLSTMInitialStates (lstm_helper.cu:98-110)."""
         H, base = self.hidden_dim, self._lstm_block() - 2 * self.hidden_dim

@@ -2,6 +2,7 @@
 // against the reference's include paths. Prints key=value pairs that tests/test_npz_io.py compares with numpy.
 #include <mppi/cost_functions/autorally/ar_standard_cost.cuh>
 #include <mppi/dynamics/autorally/ar_nn_model.cuh>
+#include <mppi/dynamics/racer_dubins/racer_dubins_elevation_lstm_steering.cuh>
 
 #include <cmath>
 #include <cstdio>
@@ -33,5 +34,15 @@ int main(int argc, char** argv)
     rc = 1;
   }
   printf("missing_rc=%d\n", rc);
+  if (argc >= 4)
+  {  // prediction LSTM of the RACER model (H = 4, head {8, 20, 1}) from a PyTorch-layout npz
+    std::vector<int> init_layers = { 23, 100, 8 }, out_layers = { 8, 20, 1 };
+    RacerDubinsElevationLSTMSteering racer(3, 20, init_layers, 4, 4, out_layers, 11);
+    racer.loadParamsLSTM(argv[3]);
+    double ls = 0, la = 0;
+    for (float v : racer.getTheta())
+      ls += v, la += std::fabs(v);
+    printf("lstm_sum=%.9g lstm_abs=%.9g\n", ls, la);
+  }
   return 0;
 }

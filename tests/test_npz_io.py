@@ -114,3 +114,57 @@ def test_cpp_host_layer_loads_the_same_files(tmp_path):
     assert float(vals["ch0_sum"]) == pytest.approx(float(ch0.astype(np.float64).sum()), rel=1e-6)
     assert float(vals["ch2_sum"]) == pytest.approx(float(h * w), rel=1e-6)
     assert int(vals["missing_rc"]) != 0
+
+
+def test_racer_lstm_load_params_from_pytorch_layout(tmp_path):
+    """LSTMHelper::loadParams (lstm_helper.cu:496-585): PyTorch gate order i, f, g (cell), o in the file, the reference's
+    packed i, f, o, c in memory; biases summed; head from output/dynamics_*; "model/" prefix tried first."""
+    H_, I, L1 = 4, 4, 20
+    lstm_w, head = W.synthetic_lstm_weights(H_, L1, seed=7)
+    HH, IH = H_ * H_, H_ * I
+    blocks_m = [lstm_w[k * HH:(k + 1) * HH].reshape(H_, H_) for k in range(4)]          # packed: i, f, o, c
+    blocks_i = [lstm_w[4 * HH + k * IH:4 * HH + (k + 1) * IH].reshape(H_, I) for k in range(4)]
+    bias = [lstm_w[4 * HH + 4 * IH + k * H_:4 * HH + 4 * IH + (k + 1) * H_] for k in range(4)]
+    to_file = (0, 1, 3, 2)  # file order i, f, c, o
+    rng = np.random.RandomState(0)
+    split = [rng.randn(H_).astype(np.float32) * 0.1 for _ in range(4)]
+    arrays = {
+        "model/lstm/weight_hh_l0": np.concatenate([blocks_m[k] for k in to_file]).astype(np.float64),
+        "model/lstm/weight_ih_l0": np.concatenate([blocks_i[k] for k in to_file]).astype(np.float64),
+        "model/lstm/bias_hh_l0": np.concatenate([bias[k] - split[i] for i, k in enumerate(to_file)]).astype(np.float64),
+        "model/lstm/bias_ih_l0": np.concatenate(split).astype(np.float64),
+        "model/output/dynamics_W1": head[:L1 * (H_ + I)].reshape(L1, H_ + I).astype(np.float64),
+        "model/output/dynamics_b1": head[L1 * (H_ + I):L1 * (H_ + I) + L1].astype(np.float64),
+        "model/output/dynamics_W2": head[L1 * (H_ + I) + L1:L1 * (H_ + I) + 2 * L1].reshape(1, L1).astype(np.float64),
+        "model/output/dynamics_b2": head[-1:].astype(np.float64),
+    }
+    path = str(tmp_path / "lstm.npz")
+    np.savez(path, **arrays)
+    # the C++ mirror reads the same file to the same packed vector (initial state zero there)
+    exe = os.path.join(ROOT, "tests", "cpp", "npz_load_test.bin")
+    if os.path.exists(exe):
+        model = str(tmp_path / "m.npz")
+        _write_model(model)
+        ch0, xb, yb, ppm = W.track_map_standard()
+        track = str(tmp_path / "t.npz")
+        np.savez(track, xBounds=np.array(xb, np.float32), yBounds=np.array(yb, np.float32),
+                 pixelsPerMeter=np.array([ppm], np.float32), **{f"channel{c}": ch0.astype(np.float32).ravel() for c in range(4)})
+        p = subprocess.run([exe, model, track, path], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, p.stdout + p.stderr
+        vals = dict(line.split("=") for line in p.stdout.split())
+        expect = np.concatenate([lstm_w, head]).astype(np.float64)
+        assert float(vals["lstm_sum"]) == pytest.approx(float(expect.sum()), rel=1e-5, abs=1e-5)
+        assert float(vals["lstm_abs"]) == pytest.approx(float(np.abs(expect).sum()), rel=1e-6)
+    dyn = m.RacerDubinsElevationLSTMSteering(hidden_dim=H_, output_layers=(H_ + I, L1, 1))
+    h0 = np.linspace(-0.2, 0.2, H_).astype(np.float32)
+    dyn.setInitialHiddenCell(h0, -h0)
+    dyn.loadParamsLSTM(path)
+    block = 4 * HH + 4 * IH + 4 * H_
+    np.testing.assert_array_equal(dyn.lstm_theta[:4 * HH + 4 * IH], lstm_w[:4 * HH + 4 * IH])
+    np.testing.assert_allclose(dyn.lstm_theta[4 * HH + 4 * IH:block], lstm_w[4 * HH + 4 * IH:block], rtol=0, atol=2e-8)
+    np.testing.assert_array_equal(dyn.lstm_theta[block + 2 * H_:], head)
+    hh, cc = dyn.initial_hidden_cell()
+    np.testing.assert_array_equal(hh, h0)  # the init network's state is not part of this file
+    np.testing.assert_array_equal(cc, -h0)
+    with pytest.raises(ValueError):
+        m.RacerDubinsElevationLSTMSteering(hidden_dim=8, output_layers=(12, L1, 1)).loadParamsLSTM(path)
