@@ -32,6 +32,24 @@ struct Cost
   {
     return 0.0f;  // cost.cuh:205-208
   }
+  // Deferred-cost protocol of the rollout kernel (DYN::DEFER_COST): prefetch() issues whatever long-latency loads the
+  // running cost of output y needs and returns their raw results; computeRunningCostPrefetched() is computeRunningCost
+  // with those results handed in. Default: nothing to prefetch.
+  struct Prefetch
+  {
+  };
+  template <class AUX>
+  __device__ static __forceinline__ auto prefetch(const Params&, const AUX&, const float* /*y*/)
+  {
+    return typename CLASS_T::Prefetch{};
+  }
+  template <class AUX, class PF>
+  __device__ static __forceinline__ float computeRunningCostPrefetched(const Params& p, const AUX& aux, const float* theta_c,
+                                                                       const float* y, const float* u, int t, int* crash,
+                                                                       const PF&)
+  {
+    return CLASS_T::computeRunningCost(p, aux, theta_c, y, u, t, crash);
+  }
   // cost.cu:40-53
   template <class AUX>
   __device__ static __forceinline__ float computeRunningCost(const Params& p, const AUX& aux, const float* theta_c,
@@ -181,6 +199,40 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
     if (track_cost_front >= p.boundary_threshold || track_cost_back >= p.boundary_threshold)
       crash[0] = 1;
     return track_cost;
+  }
+  // deferred-cost protocol: the two map lookups of getTrackCost are issued by prefetch() and finished here
+  struct Prefetch
+  {
+    float front, back;
+  };
+  __device__ static __forceinline__ Prefetch prefetch(const Params& p, const Aux& aux, const float* s)
+  {
+    float sn, cs;
+    __sincosf(s[2], &sn, &cs);
+    Prefetch pf;
+    pf.front = queryTextureTransformed(p, aux, s[0] + p.front_d * cs, s[1] + p.front_d * sn).x;
+    pf.back = queryTextureTransformed(p, aux, s[0] + p.back_d * cs, s[1] + p.back_d * sn).x;
+    return pf;
+  }
+  __device__ static __forceinline__ float computeRunningCostPrefetched(const Params& p, const Aux&, const float* theta_c,
+                                                                       const float* s, const float* /*u*/, int timestep,
+                                                                       int* crash_status, const Prefetch& pf)
+  {
+    // getTrackCost (above) from the prefetched texels, then computeStateCost's sum in its order
+    float track_cost = (fabsf(pf.front) + fabsf(pf.back)) / 2.0f;
+    if (fabsf(track_cost) < p.track_slop)
+      track_cost = 0;
+    else
+      track_cost = p.track_coeff * track_cost;
+    if (pf.front >= p.boundary_threshold || pf.back >= p.boundary_threshold)
+      crash_status[0] = 1;
+    float speed_cost = getSpeedCost(p, s);
+    float stabilizing_cost = getStabilizingCost(p, s, crash_status);
+    float crash_cost = theta_c[timestep] * getCrashCost(p, crash_status);
+    float cost = speed_cost + crash_cost + track_cost + stabilizing_cost;
+    if (cost > MAX_COST_VALUE || isnan(cost))
+      cost = MAX_COST_VALUE;
+    return cost;
   }
   __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux& aux, const float* theta_c,
                                                            const float* s, int timestep, int* crash_status)

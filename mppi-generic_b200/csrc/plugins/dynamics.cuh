@@ -60,6 +60,7 @@ struct Dynamics
   static constexpr int MAX_SPT = 1;  // samples one thread may roll out side by side (rollout_kernel.cuh: SPT)
   static constexpr int MAX_BLOCK_THREADS = 256;  // __launch_bounds__ of the rollout kernel for this model
   static constexpr bool UNROLL_STEPS = true;     // unroll the 4/C steps that share one 16-byte noise group
+  static constexpr bool DEFER_COST = false;      // rollout_kernel.cuh: issue a step's cost lookups a step ahead of their use
   struct Aux
   {
   };
@@ -449,6 +450,9 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
 struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>
 {
   static constexpr int DYNAMICS_DIM = 4;
+#ifdef MPPIB_EXP_DEFER_COST  // experimental (round 2): not yet run on a GPU
+  static constexpr bool DEFER_COST = true;
+#endif
   static constexpr int MAX_SPT = 1;
   static constexpr int MAX_BLOCK_THREADS = 256;
   static constexpr bool UNROLL_STEPS = false;

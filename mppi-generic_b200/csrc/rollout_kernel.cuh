@@ -282,6 +282,32 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     }
   const float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
 
+  // Deferred running cost (DYN::DEFER_COST, experimental, profiles/r01_autorally_k1_notes.md): the cost of step t needs
+  // texture data whose latency nothing overlaps when a scheduler holds one or two warps. With DEFER the lookups of step t
+  // are ISSUED right after its state is known (COST::prefetch) and CONSUMED after the dynamics of step t + 1
+  // (COST::computeRunningCostPrefetched on the kept copy of y / u), in step order, so the sticky crash flag and the sums see
+  // exactly the sequence they see without it.
+  constexpr bool DEFER = DYN::DEFER_COST && !RMPPI;
+  float y_prev[DEFER ? M : 1][O], u_prev[DEFER ? M : 1][C];
+  typename COST::Prefetch pf[DEFER ? M : 1];
+  int t_prev = -1;
+  auto consume_deferred = [&]() {
+    if constexpr (DEFER)
+    {
+#pragma unroll
+      for (int m = 0; m < M; m++)
+      {
+        const int sp = m / D, d = m % D;
+        float step_cost = COST::computeRunningCostPrefetched(args.cost, args.cost_aux, theta_c, y_prev[m], u_prev[m], t_prev,
+                                                             &crash_status[m], pf[m]);
+        if (lr_on)
+          step_cost += likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t_prev) * C, u_prev[m], pure_noise[sp],
+                                                half_lambda_1ma);
+        running_cost[m] += step_cost;
+      }
+    }
+  };
+
   // ---- the horizon ----------------------------------------------------------------------------------------------
   for (int k = 0; k < nchunks; k++)
   {
@@ -365,6 +391,27 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
             xdot[m][i] = 0.0f;
         }
         DYN::template stepBatch<M>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);  // mppi_common.cu:120
+        if constexpr (DEFER)
+        {
+          if (t_prev >= 0)
+            consume_deferred();  // cost of the previous step: its lookups were issued a whole step ago
+#pragma unroll
+          for (int m = 0; m < M; m++)
+          {
+            pf[m] = COST::prefetch(args.cost, args.cost_aux, y[m]);
+#pragma unroll
+            for (int i = 0; i < O; i++)
+              y_prev[m][i] = y[m][i];
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              u_prev[m][c] = u[m][c];
+#pragma unroll
+            for (int i = 0; i < S; i++)
+              x[m][i] = x_next[m][i];
+          }
+          t_prev = t;
+          continue;
+        }
 #pragma unroll
         for (int m = 0; m < M; m++)
         {
@@ -407,6 +454,11 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     }
   }
 
+  if constexpr (DEFER)
+  {
+    if (t_prev >= 0)
+      consume_deferred();  // the last step's cost
+  }
   // ---- per-sample cost (computeAndSaveCost, mppi_common.cu:843-853) ------------------------------------------------
   float cost[M];
 #pragma unroll
