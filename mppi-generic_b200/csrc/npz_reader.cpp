@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -87,6 +88,8 @@ int find_member(FILE* f, const std::string& member, Member& out)
     cd_size = rd64(r + 40);
     cd_off = rd64(r + 48);
   }
+  if (cd_size > fsize || cd_off > fsize)
+    return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: central directory outside the file");
   std::vector<unsigned char> cd(cd_size);
   if (cd_size == 0 || !read_at(f, cd_off, cd.data(), cd_size))
     return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: central directory unreadable");
@@ -137,6 +140,11 @@ int read_member(FILE* f, const Member& m, std::vector<unsigned char>& data)
   if (!read_at(f, m.local_off, lh, 30) || rd32(lh) != 0x04034b50u)
     return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: local file header unreadable");
   const uint64_t data_off = m.local_off + 30 + rd16(lh + 26) + rd16(lh + 28);
+  if (fseeko(f, 0, SEEK_END) != 0)
+    return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: cannot seek");
+  const uint64_t fsize = (uint64_t)ftello(f);
+  if (m.csize > fsize || data_off > fsize || m.usize > (1ull << 34))
+    return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: member sizes do not fit the file");
   std::vector<unsigned char> comp(m.csize);
   if (m.csize && !read_at(f, data_off, comp.data(), m.csize))
     return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: member data truncated");
@@ -194,8 +202,24 @@ bool dict_value(const std::string& hdr, const char* key, char open, char close, 
 }
 }  // namespace
 
+static int npz_read_impl(const char* path, const char* name, float* out, size_t capacity, size_t* count, int* shape4,
+                         int* ndim);
+
 extern "C" int mppib_host_npz_read(const char* path, const char* name, float* out, size_t capacity, size_t* count,
                                    int* shape4, int* ndim)
+{
+  try
+  {  // no exception may cross the C ABI (a corrupt archive can ask for absurd buffer sizes)
+    return npz_read_impl(path, name, out, capacity, count, shape4, ndim);
+  }
+  catch (const std::exception& e)
+  {
+    return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: %s", e.what());
+  }
+}
+
+static int npz_read_impl(const char* path, const char* name, float* out, size_t capacity, size_t* count, int* shape4,
+                         int* ndim)
 {
   if (!path || !name)
     return mppib_set_last_error(MPPIB_ERR_INVALID_ARG, "npz: null argument");
