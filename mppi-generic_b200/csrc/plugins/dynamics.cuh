@@ -494,10 +494,12 @@ struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar
     in[4] = control[0];
     in[5] = control[1];
     float* scratch = const_cast<float*>(theta_s) + nn_mma::kFixedFloats + (threadIdx.x >> 5) * nn_mma::kScratchPerWarp;
-#ifdef MPPIB_EXP_NEWTON  // ablation only: reciprocal of the tanh on the FP32 pipe instead of MUFU
-    nn_mma::forward<true>(theta_s, scratch, in, out);
+#if defined(MPPIB_EXP_NEWTON)  // ablation only: reciprocal of the tanh on the FP32 pipe instead of MUFU (measured slower)
+    nn_mma::forward<1>(theta_s, scratch, in, out);
+#elif defined(MPPIB_EXP_PAIR_RCP)  // experimental (round 2): one MUFU.RCP per pair of tanh
+    nn_mma::forward<2>(theta_s, scratch, in, out);
 #else
-    nn_mma::forward<false>(theta_s, scratch, in, out);
+    nn_mma::forward<0>(theta_s, scratch, in, out);
 #endif
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)

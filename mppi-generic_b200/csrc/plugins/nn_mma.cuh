@@ -103,16 +103,29 @@ __device__ __forceinline__ float2 tanh2_prescaled_newton(float z0, float z1)
   }
   return __ffma2_rn(make_float2(-2.0f, -2.0f), r, one);
 }
+// One reciprocal for two values (experimental, tools/mma_probe.cu): 1/d0 = d1 / (d0 d1), 1/d1 = d0 / (d0 d1) — three MUFU per
+// pair instead of four on the busiest pipe (XU 45 % in K1), two more FMULs on a short chain. z is clamped at 60 so that the
+// product (<= 2^120) stays finite; tanh is 1 to the last bit long before that.
+__device__ __forceinline__ float2 tanh2_prescaled_pair(float z0, float z1)
+{
+  float e0, e1, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(z0, 60.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(z1, 60.0f)));
+  const float d0 = e0 + 1.0f, d1 = e1 + 1.0f;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  return make_float2(fmaf(-2.0f, r * d1, 1.0f), fmaf(-2.0f, r * d0, 1.0f));
+}
 // Finished tile (hi*hi sum in c, cross terms in x) -> tanh -> the two half2 registers (rows g and g+8) of the next layer's
 // A fragment, hi and lo parts
-template <bool NEWTON_RCP>
+// TANH: 0 = ex2 + rcp on MUFU (shipped), 1 = Newton reciprocal on the FP32 pipe (measured slower), 2 = one rcp per pair
+template <int TANH>
 __device__ __forceinline__ void activate(const float (&c)[4], const float (&x)[4], uint32_t& top_hi, uint32_t& bot_hi,
                                          uint32_t& top_lo, uint32_t& bot_lo)
 {
   const float z0 = fmaf(x[0], kLoInv, c[0]), z1 = fmaf(x[1], kLoInv, c[1]), z2 = fmaf(x[2], kLoInv, c[2]),
               z3 = fmaf(x[3], kLoInv, c[3]);
-  const float2 u = NEWTON_RCP ? tanh2_prescaled_newton(z0, z1) : tanh2_prescaled(z0, z1);
-  const float2 v = NEWTON_RCP ? tanh2_prescaled_newton(z2, z3) : tanh2_prescaled(z2, z3);
+  const float2 u = TANH == 1 ? tanh2_prescaled_newton(z0, z1) : (TANH == 2 ? tanh2_prescaled_pair(z0, z1) : tanh2_prescaled(z0, z1));
+  const float2 v = TANH == 1 ? tanh2_prescaled_newton(z2, z3) : (TANH == 2 ? tanh2_prescaled_pair(z2, z3) : tanh2_prescaled(z2, z3));
   split2(u.x, u.y, top_hi, top_lo);
   split2(v.x, v.y, bot_hi, bot_lo);
 }
@@ -174,7 +187,7 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ g, float*
 }
 
 // Forward pass for the calling warp's 32 samples (all 32 lanes must call it): in[6] / out[4] are the lane's own sample.
-template <bool NEWTON_RCP = false>
+template <int TANH = 0>
 __device__ __forceinline__ void forward(const float* theta_s, float* scratch, const float (&in)[6], float (&out)[4])
 {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -214,7 +227,7 @@ __device__ __forceinline__ void forward(const float* theta_s, float* scratch, co
       mma8(x, a_lo[m], wf.x);
       mma8(x, a_hi[m], wf.y);
       mma8(c, a_hi[m], wf.x);
-      activate<NEWTON_RCP>(c, x, h_hi[m][i >> 1][(i & 1) * 2], h_hi[m][i >> 1][(i & 1) * 2 + 1], h_lo[m][i >> 1][(i & 1) * 2],
+      activate<TANH>(c, x, h_hi[m][i >> 1][(i & 1) * 2], h_hi[m][i >> 1][(i & 1) * 2 + 1], h_lo[m][i >> 1][(i & 1) * 2],
                            h_lo[m][i >> 1][(i & 1) * 2 + 1]);
     }
   }
@@ -245,7 +258,7 @@ __device__ __forceinline__ void forward(const float* theta_s, float* scratch, co
     }
 #pragma unroll
     for (int m = 0; m < 2; m++)
-      activate<NEWTON_RCP>(c[m], x[m], q_hi[m][i >> 1][(i & 1) * 2], q_hi[m][i >> 1][(i & 1) * 2 + 1],
+      activate<TANH>(c[m], x[m], q_hi[m][i >> 1][(i & 1) * 2], q_hi[m][i >> 1][(i & 1) * 2 + 1],
                            q_lo[m][i >> 1][(i & 1) * 2], q_lo[m][i >> 1][(i & 1) * 2 + 1]);
   }
   // ---- layer 3: 32 -> 8 (4)

@@ -65,9 +65,11 @@ __global__ void __launch_bounds__(256) probe(const float* __restrict__ gw, const
   for (int s = 0; s < steps; s++)
   {
     if (MMA == 1)
-      nn_mma::forward<false>(theta_s, scratch, in, out);
+      nn_mma::forward<0>(theta_s, scratch, in, out);
     else if (MMA == 2)
-      nn_mma::forward<true>(theta_s, scratch, in, out);
+      nn_mma::forward<1>(theta_s, scratch, in, out);
+    else if (MMA == 3)
+      nn_mma::forward<2>(theta_s, scratch, in, out);
     else
       forward_ffma(gw, in, out);
     if (s + 1 < steps)
@@ -143,20 +145,24 @@ int main()
   const size_t smem = nn_mma::sharedFloats(256) * sizeof(float);
   cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(probe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(probe<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
   // ---- accuracy: one evaluation
   std::vector<float> o_mma(max_threads * 4), o_ffma(max_threads * 4);
-  std::vector<float> o_mma2(max_threads * 4);
+  std::vector<float> o_mma2(max_threads * 4), o_mma3(max_threads * 4);
   probe<2><<<148, 224, smem>>>(gw, gin, 1, gout, cyc_d);
   cudaDeviceSynchronize();
   cudaMemcpy(o_mma2.data(), gout, 148 * 224 * 16, cudaMemcpyDeviceToHost);
+  probe<3><<<148, 224, smem>>>(gw, gin, 1, gout, cyc_d);
+  cudaDeviceSynchronize();
+  cudaMemcpy(o_mma3.data(), gout, 148 * 224 * 16, cudaMemcpyDeviceToHost);
   probe<1><<<148, 224, smem>>>(gw, gin, 1, gout, cyc_d);
   cudaError_t e1 = cudaDeviceSynchronize();
   cudaMemcpy(o_mma.data(), gout, 148 * 224 * 16, cudaMemcpyDeviceToHost);
   probe<0><<<148, 224, smem>>>(gw, gin, 1, gout, cyc_d);
   cudaError_t e2 = cudaDeviceSynchronize();
   cudaMemcpy(o_ffma.data(), gout, 148 * 224 * 16, cudaMemcpyDeviceToHost);
-  double err_mma = 0, err_mma2 = 0, err_ffma = 0, mag = 0;
+  double err_mma = 0, err_mma2 = 0, err_mma3 = 0, err_ffma = 0, mag = 0;
   for (int s = 0; s < 148 * 224; s++)
   {
     double di[6], dout[4];
@@ -167,18 +173,19 @@ int main()
     {
       err_mma = fmax(err_mma, fabs(o_mma[s * 4 + k] - dout[k]));
       err_mma2 = fmax(err_mma2, fabs(o_mma2[s * 4 + k] - dout[k]));
+      err_mma3 = fmax(err_mma3, fabs(o_mma3[s * 4 + k] - dout[k]));
       err_ffma = fmax(err_ffma, fabs(o_ffma[s * 4 + k] - dout[k]));
       mag = fmax(mag, fabs(dout[k]));
     }
   }
-  printf("accuracy vs FP64 over %d samples (|out| up to %.3f): mma f16 x3 max abs err %.3e (Newton rcp: %.3e), FFMA + tanh_fast %.3e  (%s / %s)\n",
-         148 * 224, mag, err_mma, err_mma2, err_ffma, cudaGetErrorString(e1), cudaGetErrorString(e2));
+  printf("accuracy vs FP64 over %d samples (|out| up to %.3f): mma f16 x3 max abs err %.3e (Newton rcp: %.3e, pair rcp: %.3e), FFMA + tanh_fast %.3e  (%s / %s)\n",
+         148 * 224, mag, err_mma, err_mma2, err_mma3, err_ffma, cudaGetErrorString(e1), cudaGetErrorString(e2));
 
   // ---- timing: dependent recurrence of 100 evaluations
   const int steps = 100;
   for (int threads : { 128, 224, 256 })
   {
-    for (int mode = 0; mode < 3; mode++)
+    for (int mode = 0; mode < 4; mode++)
     {
       cudaEvent_t a, b;
       cudaEventCreate(&a);
@@ -190,6 +197,8 @@ int main()
           probe<1><<<148, threads, smem>>>(gw, gin, steps, gout, cyc_d);
         else if (mode == 1)
           probe<2><<<148, threads, smem>>>(gw, gin, steps, gout, cyc_d);
+        else if (mode == 3)
+          probe<3><<<148, threads, smem>>>(gw, gin, steps, gout, cyc_d);
         else if (threads == 128)
           probe<0><<<148, threads, smem>>>(gw, gin, steps, gout, cyc_d);
         cudaEventRecord(b);
@@ -200,7 +209,7 @@ int main()
       long long cyc = 0;
       cudaMemcpy(&cyc, cyc_d, 8, cudaMemcpyDeviceToHost);
       printf("%-22s %3d threads/SM (%d warps): %8.1f cycles per evaluation (block 0), %7.1f us per %d steps\n",
-             mode == 0 ? "mma f16 x3, MUFU rcp" : (mode == 1 ? "mma f16 x3, Newton rcp" : "scalar FFMA (global w)"), threads, threads / 32, (double)cyc / steps,
+             mode == 0 ? "mma f16 x3, MUFU rcp" : (mode == 1 ? "mma f16 x3, Newton rcp" : (mode == 3 ? "mma f16 x3, pair rcp" : "scalar FFMA (global w)")), threads, threads / 32, (double)cyc / steps,
              ms * 1000.0, steps);
     }
   }
