@@ -60,7 +60,12 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
   const __half2 h = __floats2half2_rn(v0, v1);
   const float2 hf = __half22float2(h);
   hi = h2_bits(h);
+#ifdef MPPIB_EXP_PACKED  // experimental (round 2): the residual with packed FP32x2 instructions (same IEEE results per lane)
+  const float2 r = __fmul2_rn(__fadd2_rn(make_float2(v0, v1), make_float2(-hf.x, -hf.y)), make_float2(kLoScale, kLoScale));
+  lo = h2_bits(__floats2half2_rn(r.x, r.y));
+#else
   lo = h2_bits(__floats2half2_rn((v0 - hf.x) * kLoScale, (v1 - hf.y) * kLoScale));
+#endif
 }
 __device__ __forceinline__ void mma16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
@@ -122,8 +127,15 @@ template <int TANH>
 __device__ __forceinline__ void activate(const float (&c)[4], const float (&x)[4], uint32_t& top_hi, uint32_t& bot_hi,
                                          uint32_t& top_lo, uint32_t& bot_lo)
 {
+#ifdef MPPIB_EXP_PACKED
+  const float2 inv = make_float2(kLoInv, kLoInv);
+  const float2 za = __ffma2_rn(make_float2(x[0], x[1]), inv, make_float2(c[0], c[1]));
+  const float2 zb = __ffma2_rn(make_float2(x[2], x[3]), inv, make_float2(c[2], c[3]));
+  const float z0 = za.x, z1 = za.y, z2 = zb.x, z3 = zb.y;
+#else
   const float z0 = fmaf(x[0], kLoInv, c[0]), z1 = fmaf(x[1], kLoInv, c[1]), z2 = fmaf(x[2], kLoInv, c[2]),
               z3 = fmaf(x[3], kLoInv, c[3]);
+#endif
   const float2 u = TANH == 1 ? tanh2_prescaled_newton(z0, z1) : (TANH == 2 ? tanh2_prescaled_pair(z0, z1) : tanh2_prescaled(z0, z1));
   const float2 v = TANH == 1 ? tanh2_prescaled_newton(z2, z3) : (TANH == 2 ? tanh2_prescaled_pair(z2, z3) : tanh2_prescaled(z2, z3));
   split2(u.x, u.y, top_hi, top_lo);

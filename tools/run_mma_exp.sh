@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU-box script: ablations / experiments on the mma.sync K1. Build the variants first (CPU box): bash tools/build_exp.sh NAME.
 #   VARIANTS="DEFAULT DEFER_COST" PARITY=DEFER_COST bash tools/run_mma_exp.sh
-for v in ${VARIANTS:-DEFAULT NEWTON FAST_SINCOS NO_COST DEFER_COST PAIR_RCP}; do
+for v in ${VARIANTS:-DEFAULT NEWTON FAST_SINCOS NO_COST DEFER_COST PAIR_RCP PACKED}; do
   if [ "$v" = "DEFAULT" ]; then L=""; else L="/root/repo/tools/libexp_$v.so"; [ -f "$L" ] || { echo "[$v] not built"; continue; }; fi
   for n in 32768 8192; do
     MPPIB_LIB=$L timeout 200 python bench.py --rollouts $n --steps 100 --warmup 10 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('[$v]', $n, 'K1 us', round(d['roofline']['stage_ms_l2_warm']['rollout_ms']*1000,1), 'value', round(d['value'],1))"
