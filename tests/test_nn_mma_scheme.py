@@ -1,0 +1,114 @@
+"""CPU pin of the arithmetic scheme of csrc/plugins/nn_mma.cuh (the Autorally network on mma.sync): FP16 hi / lo operands,
+three products, FP32 accumulation — emulated with numpy float16 / float32, on the synthetic 6-32-32-4 network, against
+float64. Two things are pinned: (1) the fragment bookkeeping (which lane register holds which matrix element, how a C
+fragment becomes the next layer's A fragment, the weight-fragment order of load_weights) reproduces the plain matrix
+products exactly; (2) the split reaches FP32-class accuracy where a single FP16 product does not (the reason for it).
+The device numbers (5.1e-7 max error, tools/mma_probe.cu) are measured on the GPU; this file needs none."""
+import numpy as np
+
+from mppi_generic_b200 import workloads as W
+
+SC = 2.8853900817779268  # kTanhScale: tanh(x) = 1 - 2 / (exp2(SC x) + 1)
+LANES = np.arange(32)
+G, T = LANES >> 2, LANES & 3
+
+
+def _frag_a16(a):  # a[4][32][2] -> A[16][16]   (PTX m16n8k16 .f16 A layout)
+    A = np.zeros((16, 16))
+    for l in range(32):
+        g, t = G[l], T[l]
+        A[g, 2 * t:2 * t + 2], A[g + 8, 2 * t:2 * t + 2] = a[0][l], a[1][l]
+        A[g, 2 * t + 8:2 * t + 10], A[g + 8, 2 * t + 8:2 * t + 10] = a[2][l], a[3][l]
+    return A
+
+
+def _frag_b16(b0, b1):  # [32][2] each -> B[16][8]
+    B = np.zeros((16, 8))
+    for l in range(32):
+        g, t = G[l], T[l]
+        B[2 * t:2 * t + 2, g], B[2 * t + 8:2 * t + 10, g] = b0[l], b1[l]
+    return B
+
+
+def _c_frag(Cm):  # C[16][8] -> c[32][4]
+    return np.array([[Cm[G[l], 2 * T[l]], Cm[G[l], 2 * T[l] + 1], Cm[G[l] + 8, 2 * T[l]], Cm[G[l] + 8, 2 * T[l] + 1]]
+                     for l in range(32)])
+
+
+def _c_mat(c):
+    Cm = np.zeros((16, 8))
+    for l in range(32):
+        g, t = G[l], T[l]
+        Cm[g, 2 * t], Cm[g, 2 * t + 1], Cm[g + 8, 2 * t], Cm[g + 8, 2 * t + 1] = c[l]
+    return Cm
+
+
+def test_fragment_bookkeeping_reproduces_the_matrix_products():
+    """forward() / load_weights() of nn_mma.cuh restated lane by lane (exact arithmetic): layer 2 and 3 of the network."""
+    theta = W.synthetic_nn_weights(1).astype(np.float64)
+    W2, b2 = theta[224:1248].reshape(32, 32), theta[1248:1280]
+    W3, b3 = theta[1280:1408].reshape(4, 32), theta[1408:1412]
+    rng = np.random.RandomState(0)
+    h = np.tanh(rng.randn(16, 32))  # one m-tile of layer-1 activations, [row][neuron]
+    # layer-1 C fragments of n-tile i, re-used as layer 2's A fragments: k16-tile j <- n-tiles 2j, 2j+1
+    cf = [_c_frag(h[:, 8 * i:8 * i + 8]) for i in range(4)]
+    a2 = [[cf[2 * j][:, 0:2], cf[2 * j][:, 2:4], cf[2 * j + 1][:, 0:2], cf[2 * j + 1][:, 2:4]] for j in range(2)]
+    out2 = np.zeros((16, 32))
+    for i in range(4):  # n-tile
+        c = np.array([[b2[8 * i + 2 * T[l]], b2[8 * i + 2 * T[l] + 1]] * 2 for l in range(32)])
+        for j in range(2):
+            b0 = np.array([[W2[8 * i + G[l], 16 * j + 2 * T[l]], W2[8 * i + G[l], 16 * j + 2 * T[l] + 1]] for l in range(32)])
+            b1 = np.array([[W2[8 * i + G[l], 16 * j + 8 + 2 * T[l]], W2[8 * i + G[l], 16 * j + 9 + 2 * T[l]]] for l in range(32)])
+            c = _c_frag(_c_mat(c) + _frag_a16(a2[j]) @ _frag_b16(b0, b1))
+        out2[:, 8 * i:8 * i + 8] = _c_mat(c)
+    np.testing.assert_allclose(out2, h @ W2.T + b2, rtol=0, atol=1e-13)
+    q = np.tanh(out2)
+    cf = [_c_frag(q[:, 8 * i:8 * i + 8]) for i in range(4)]
+    a3 = [[cf[2 * j][:, 0:2], cf[2 * j][:, 2:4], cf[2 * j + 1][:, 0:2], cf[2 * j + 1][:, 2:4]] for j in range(2)]
+    b3p = np.concatenate([b3, np.zeros(4)])
+    c = np.array([[b3p[2 * T[l]], b3p[2 * T[l] + 1]] * 2 for l in range(32)])
+    for j in range(2):
+        w = lambda g, k: W3[g, k] if g < 4 else 0.0  # noqa: E731  (outputs 4..7 of the tile are padding)
+        b0 = np.array([[w(G[l], 16 * j + 2 * T[l]), w(G[l], 16 * j + 2 * T[l] + 1)] for l in range(32)])
+        b1 = np.array([[w(G[l], 16 * j + 8 + 2 * T[l]), w(G[l], 16 * j + 9 + 2 * T[l])] for l in range(32)])
+        c = _c_frag(_c_mat(c) + _frag_a16(a3[j]) @ _frag_b16(b0, b1))
+    np.testing.assert_allclose(_c_mat(c)[:, :4], q @ W3.T + b3, rtol=0, atol=1e-13)
+
+
+def _split(v):
+    hi = v.astype(np.float16)
+    lo = ((v - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+    return hi.astype(np.float32), lo.astype(np.float32)
+
+
+def _layer_split(a, Wm, b):
+    """hi*hi + (lo*hi + hi*lo) / 2048 with FP32 accumulators, bias in the hi*hi accumulator (activate() folds x in)."""
+    ah, al = _split(a.astype(np.float32))
+    wh, wl = _split(Wm.astype(np.float32))
+    c = (ah @ wh.T).astype(np.float32) + b.astype(np.float32)
+    x = (al @ wh.T).astype(np.float32) + (ah @ wl.T).astype(np.float32)
+    return x * np.float32(1.0 / 2048.0) + c
+
+
+def test_three_product_fp16_split_reaches_fp32_class_accuracy():
+    theta = W.synthetic_nn_weights(1).astype(np.float64)
+    W1, b1 = theta[:192].reshape(32, 6), theta[192:224]
+    W2, b2 = theta[224:1248].reshape(32, 32), theta[1248:1280]
+    W3, b3 = theta[1280:1408].reshape(4, 32), theta[1408:1412]
+    rng = np.random.RandomState(1)
+    x = (rng.randn(4096, 6) * [0.3, 3.0, 1.0, 1.0, 0.5, 0.5]).astype(np.float32)  # roll, vx, vy, yaw rate, steering, throttle
+    ref = np.tanh(np.tanh(x.astype(np.float64) @ W1.T + b1) @ W2.T + b2) @ W3.T + b3
+    tanh_pre = lambda z: np.float32(1.0) - np.float32(2.0) / (np.exp2(z).astype(np.float32) + np.float32(1.0))  # noqa: E731
+    h = tanh_pre(_layer_split(x, W1 * SC, b1 * SC))
+    q = tanh_pre(_layer_split(h, W2 * SC, b2 * SC))
+    out = _layer_split(q, W3, b3)
+    err_split = np.abs(out - ref).max()
+    # the same network with ONE FP16 product per term (what a plain FP16 / TF32 MMA would do)
+    f16 = lambda v: v.astype(np.float16).astype(np.float32)  # noqa: E731
+    h1 = np.tanh((f16(x) @ f16(W1.astype(np.float32)).T) + b1.astype(np.float32))
+    q1 = np.tanh((f16(h1) @ f16(W2.astype(np.float32)).T) + b2.astype(np.float32))
+    out1 = (f16(q1) @ f16(W3.astype(np.float32)).T) + b3.astype(np.float32)
+    err_single = np.abs(out1 - ref).max()
+    assert err_split < 1.5e-6, err_split      # FP32 class (device: 5.1e-7 on its own inputs)
+    assert err_single > 1e-4, err_single      # fails the 1e-4 parity bar of a 100-step recurrence on its own
+    assert err_single > 100 * err_split
