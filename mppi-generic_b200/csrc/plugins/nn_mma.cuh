@@ -5,7 +5,7 @@
  *
  * Why: the FFMA2 kernel (plugins/dynamics.cuh) is bound by shared-memory wavefronts — every 4 FMAs of a thread need one
  * broadcast LDS.128 of weights, 672 wavefronts per warp-step, 72 % of the data pipe (profiles/r01_autorally_k1_notes.md).
- * Here the weights are B fragments (one LDS.128 per lane per tile carrying the hi and lo parts, 52 per warp-step) and the
+ * Here the weights are B fragments (one LDS.128 per lane per tile carrying the hi and lo parts: 14 loads, ~50 wavefronts per warp-step) and the
  * activations never leave registers between layers: with 16-bit inputs the C fragment of n-tiles 2j, 2j+1 of layer l,
  * packed to half2, IS the A fragment of k-tile j of layer l+1.
  *
