@@ -695,6 +695,72 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
                   off_b2 = off_w2 + L1p;
     const float4* G = reinterpret_cast<const float4*>(theta_s);
     float hn[HC];
+#ifdef MPPIB_EXP_LSTM_FFMA2
+    // experimental (round 2, compiled but never run): the four gate sums of a row and the four neurons of a head group as
+    // two packed FFMA2 each. Every lane is the same IEEE fma in the same order as below, so the results are identical;
+    // the kernel is issue-bound (66 % issue active) and this removes ~140 of its ~1060 instructions per warp-step.
+    float2 in2[I], h2[HC];
+#pragma unroll
+    for (int j = 0; j < I; j++)
+      in2[j] = make_float2(in[j], in[j]);
+#pragma unroll
+    for (int j = 0; j < HC; j++)
+      h2[j] = make_float2(k.h[j], k.h[j]);
+#pragma unroll
+    for (int i = 0; i < HC; i++)
+    {
+      const float4* row = G + i * row_f4;
+      float2 g_if = make_float2(0.0f, 0.0f), g_oc = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < I; j++)
+      {
+        const float4 w = row[j];
+        g_if = __ffma2_rn(make_float2(w.x, w.y), in2[j], g_if);
+        g_oc = __ffma2_rn(make_float2(w.z, w.w), in2[j], g_oc);
+      }
+#pragma unroll
+      for (int j = 0; j < HC; j++)
+      {
+        const float4 w = row[I + j];
+        g_if = __ffma2_rn(make_float2(w.x, w.y), h2[j], g_if);
+        g_oc = __ffma2_rn(make_float2(w.z, w.w), h2[j], g_oc);
+      }
+      const float4 b = row[I + HC];
+      const float gi = sigmoid_dev(g_if.x + b.x), gf = sigmoid_dev(g_if.y + b.y), go = sigmoid_dev(g_oc.x + b.z),
+                  gc = tanh_fast(g_oc.y + b.w);
+      k.c[i] = gi * gc + gf * k.c[i];
+      hn[i] = tanh_fast(k.c[i]) * go;
+    }
+#pragma unroll
+    for (int i = 0; i < HC; i++)
+      k.h[i] = hn[i];
+    const float* W1T = theta_s + off_w1t;
+    float out = 0.0f;
+    float2 hn2[HC];
+#pragma unroll
+    for (int j = 0; j < HC; j++)
+      hn2[j] = make_float2(hn[j], hn[j]);
+#pragma unroll
+    for (int k4 = 0; k4 < L1p; k4 += 4)
+    {
+      float2 acc_xy = make_float2(0.0f, 0.0f), acc_zw = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < HC + I; j++)
+      {
+        const float4 w = *reinterpret_cast<const float4*>(W1T + j * L1p + k4);
+        const float2 a = j < HC ? hn2[j < HC ? j : 0] : in2[j < HC ? 0 : j - HC];
+        acc_xy = __ffma2_rn(make_float2(w.x, w.y), a, acc_xy);
+        acc_zw = __ffma2_rn(make_float2(w.z, w.w), a, acc_zw);
+      }
+      const float4 b = *reinterpret_cast<const float4*>(theta_s + off_b1 + k4);
+      const float4 w2 = *reinterpret_cast<const float4*>(theta_s + off_w2 + k4);
+      out = fmaf(w2.x, tanh_fast(acc_xy.x + b.x), out);
+      out = fmaf(w2.y, tanh_fast(acc_xy.y + b.y), out);
+      out = fmaf(w2.z, tanh_fast(acc_zw.x + b.z), out);
+      out = fmaf(w2.w, tanh_fast(acc_zw.y + b.w), out);
+    }
+    return out + theta_s[off_b2];
+#else
 #pragma unroll
     for (int i = 0; i < HC; i++)
     {
@@ -753,6 +819,7 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       out = fmaf(w2.w, tanh_fast(acc.w + b.w), out);
     }
     return out + theta_s[off_b2];
+#endif
   }
 
   // LSTMHelper::forward (device) + head; returns the head's single output. h is read from the buffer of parity
