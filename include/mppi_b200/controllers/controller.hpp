@@ -207,6 +207,82 @@ public:
     }
   }
 
+  // ---- names (controller.cuh:236-261) --------------------------------------------------------------------------------
+  virtual std::string getDynamicsModelName() const
+  {
+    return model_->getDynamicsModelName();
+  }
+  virtual std::string getCostFunctionName() const
+  {
+    return cost_->getCostFunctionName();
+  }
+  virtual std::string getSamplingDistributionName() const
+  {
+    return sampler_->getSamplingDistributionName();
+  }
+  virtual std::string getFullName()
+  {
+    return getControllerName() + "(" + getDynamicsModelName() + ", " + getCostFunctionName() + ", " +
+           getSamplingDistributionName() + ")";
+  }
+  // ---- host-only helpers of the base class (controller.cuh:317-393,530-533,620-622,765-768) --------------------------
+  virtual void updateImportanceSampler(const Eigen::Ref<const control_trajectory>& nominal_control)
+  {
+    control_ = nominal_control;
+  }
+  // linear interpolation of a control trajectory at rel_time seconds after it was computed (controller.cuh:363-378)
+  virtual control_array interpolateControls(double rel_time, control_trajectory& c_traj)
+  {
+    const int lower_idx = (int)(rel_time / getDt());
+    const int upper_idx = lower_idx + 1;
+    const double alpha = (rel_time - lower_idx * getDt()) / getDt();
+    control_array out;
+    for (int i = 0; i < DYN_T::CONTROL_DIM; i++)
+      out(i) = (float)((1 - alpha) * c_traj(i, lower_idx) + alpha * c_traj(i, upper_idx));
+    return out;
+  }
+  // feed-forward part of getCurrentControl (controller.cuh:329-346); the feedback term belongs to FB_T, which is the
+  // caller's (DDP is out of scope here), so it is added by the caller before the constraints if it has one
+  virtual control_array getCurrentControl(state_array& /*state*/, double rel_time, state_array& /*target_nominal_state*/,
+                                          control_trajectory& c_traj)
+  {
+    control_array result = interpolateControls(rel_time, c_traj);
+    state_array empty_state = model_->getZeroState();
+    model_->enforceConstraints(empty_state, result);
+    return result;
+  }
+  output_trajectory getActualOutputSeq() const
+  {
+    return output_;
+  }
+  virtual void resetControls()
+  {  // controller.cuh:620-622 ("TODO" in the reference: a no-op there as well)
+  }
+  void setSlideControlScale(const Eigen::Ref<const control_array>& slide_control_scale)
+  {
+    params_.slide_control_scale_ = slide_control_scale;
+  }
+  // Controller::getSampledNoise (controller.cu:274-283): the sampler's control buffer, [NUM_ROLLOUTS][T][C]
+  std::vector<float> getSampledNoise()
+  {
+    std::vector<float> v((size_t)NUM_DISTRIBUTIONS * NUM_ROLLOUTS * getNumTimesteps() * DYN_T::CONTROL_DIM);
+    MPPIB_HANDLE(mppib_get_samples(engine_, v.data()));  // needs MPPIB_FLAG_WRITEBACK_CONTROLS (fails loudly otherwise)
+    v.resize((size_t)NUM_ROLLOUTS * getNumTimesteps() * DYN_T::CONTROL_DIM);
+    return v;
+  }
+  void setDebug(bool debug)
+  {
+    debug_ = debug;
+  }
+  bool getDebug() const
+  {
+    return debug_;
+  }
+  int getKernelChoiceAsInt() const
+  {
+    return (int)getKernelChoiceAsEnum();
+  }
+
   // ---- getters (controller.cuh:409-436,510-517,773-776) ----------------------------------------------------------
   virtual control_trajectory getControlSeq() const
   {
@@ -399,6 +475,7 @@ public:
   }
 
 protected:
+  bool debug_ = false;
   unsigned extra_flags_ = 0u;  // engine flags a derived controller turns on at run time (re-creates the engine)
   float perc_sampled_control_trajectories_ = 0;  // controller.cuh:948-950
   int num_top_control_trajectories_ = 0;

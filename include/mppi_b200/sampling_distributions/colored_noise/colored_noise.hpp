@@ -46,6 +46,10 @@ public:
   {
     return params_;
   }
+  std::string getSamplingDistributionName() const
+  {
+    return "Colored Noise";
+  }
   float getOffsetDecayRate() const
   {
     return params_.offset_decay_rate;

@@ -4,6 +4,7 @@
  * (generateSamples / updateDistributionParamsFromDevice, gaussian.cu:375-457) live in the engine.
  */
 #pragma once
+#include <string>
 #include "../../utils/common.hpp"
 
 namespace mppi
@@ -58,6 +59,10 @@ public:
   SAMPLING_PARAMS_T getParams() const
   {
     return params_;
+  }
+  std::string getSamplingDistributionName() const
+  {  // gaussian.cuh
+    return "Gaussian";
   }
   void GPUSetup()
   {

@@ -1127,6 +1127,29 @@ class _Controller:
     def getNumTimesteps(self) -> int:
         return self.num_timesteps_
 
+    # host-only helpers of the base class (controller.cuh:317-393,765-768; controller.cu:274-283)
+    def updateImportanceSampler(self, nominal_control) -> None:
+        self.control_ = _f32(nominal_control).copy()
+
+    def interpolateControls(self, rel_time: float, c_traj: np.ndarray) -> np.ndarray:
+        lower = int(rel_time / self.dt_)
+        alpha = (rel_time - lower * self.dt_) / self.dt_
+        return ((1 - alpha) * c_traj[lower].astype(np.float64) + alpha * c_traj[lower + 1].astype(np.float64)).astype(np.float32)
+
+    def getCurrentControl(self, state, rel_time: float, target_nominal_state, c_traj: np.ndarray) -> np.ndarray:
+        """Feed-forward part of Controller::getCurrentControl (controller.cuh:329-346): interpolated control, constrained.
+        The feedback term belongs to the caller's FB_T (DDP is out of scope here)."""
+        u = self.interpolateControls(rel_time, c_traj)
+        self.model_.enforceConstraints(None, u)
+        return u
+
+    def setSlideControlScale(self, slide_control_scale) -> None:
+        self.slide_control_scale_[:] = _f32(slide_control_scale)
+
+    def getSampledNoise(self) -> np.ndarray:
+        """The sampler's control buffer [NUM_ROLLOUTS][T][C] of distribution 0 (needs FLAG_WRITEBACK_CONTROLS)."""
+        return self.engine.get_samples()[0]
+
     def getDt(self) -> float:
         return self.dt_
 

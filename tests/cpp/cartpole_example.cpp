@@ -107,6 +107,21 @@ int main(int argc, char** argv)
   }
   auto diff = std::chrono::duration<double, std::milli>(std::chrono::system_clock::now() - time_start);
   printf("The elapsed time is: %f milliseconds (%f solves/s)\n", diff.count(), 1000.0 * time_horizon / diff.count());
+  {  // host-only helpers of the Controller base (controller.cuh:236-261,317-378)
+    printf("controller: %s\n", CartpoleController->getFullName().c_str());
+    auto seq = CartpoleController->getControlSeq();
+    CartpoleDynamics::state_array target = CartpoleDynamics::state_array::Zero();
+    CartpoleDynamics::control_array u_mid = CartpoleController->getCurrentControl(current_state, 0.5 * dt, target, seq);
+    CartpoleDynamics::control_array lo = seq.col(0), hi = seq.col(1);
+    model->enforceConstraints(current_state, lo);
+    const float expect = 0.5f * (seq(0, 0) + seq(0, 1));
+    if (fabsf(u_mid(0) - expect) > 1e-5f * (1.0f + fabsf(expect)) ||
+        CartpoleController->getFullName() != "Vanilla MPPI(Cartpole, Cartpole quadratic cost, Gaussian)")
+    {
+      printf("getCurrentControl / getFullName mismatch: %f vs %f\n", u_mid(0), expect);
+      return 7;
+    }
+  }
   const float pole_err = fabsf(fabsf(current_state(2)) - (float)M_PI);
   printf("final pole angle error %f, baseline %f\n", pole_err, CartpoleController->getBaselineCost());
   int rc = (CartpoleController->getBaselineCost() < 1.0f && pole_err < 0.3f) ? 0 : 2;  // EXPECT_LT(baseline, 1.0)
