@@ -173,6 +173,10 @@ public:
   {
     return top_n_costs_;
   }
+  virtual std::vector<float> getTopTransformedCosts() const
+  {  // controller.cuh:294-297
+    return top_n_costs_;
+  }
   // rollout index behind every sampled trajectory (-1 = the optimised control sequence)
   std::vector<int> getSampledIndices() const
   {

@@ -1091,6 +1091,9 @@ class _Controller:
     def getTopNCosts(self) -> np.ndarray:
         return self.top_n_costs_
 
+    def getTopTransformedCosts(self) -> np.ndarray:  # controller.cuh:294-297
+        return self.top_n_costs_
+
     def getSampledIndices(self) -> np.ndarray:
         """Rank-local rollout index behind every sampled trajectory (-1 = the optimised control sequence)."""
         return self.sampled_indices_
