@@ -114,12 +114,16 @@ public:
         local_state(i) = (leash < diff) ? state(i) + fminf(fmaxf(nominal - state(i), -leash), leash) : nominal;
       }
     }
+    control_trajectory u_nominal = this->control_;
     for (int opt_iter = 0; opt_iter < this->getNumIters(); opt_iter++)
     {
       control_trajectory u_out = control_trajectory::Zero();
+      u_nominal = this->control_;
       this->solve(local_state.data(), this->control_.data(), optimization_stride, opt_iter, u_out.data());
       this->control_ = u_out;
     }
+    if (this->getTotalSampledTrajectories() > 0)  // colored_mppi_controller.cu:242-248
+      this->pickSampledControls(local_state, u_nominal, this->control_);
     this->free_energy_statistics_.real_sys.normalizerPercent = this->getNormalizerCost() / NUM_ROLLOUTS;
     this->free_energy_statistics_.real_sys.increase =
         this->getBaselineCost() - this->free_energy_statistics_.real_sys.previousBaseline;
