@@ -67,6 +67,8 @@ enum mppib_blob
 #define MPPIB_FLAG_NN_MMA 64u            /* Autorally NN: forward pass with register-level mma.sync (FP16 hi/lo split, 3      \
                                             products, FP32 accumulate) — the default for that model */
 #define MPPIB_FLAG_NN_FFMA2 128u         /* Autorally NN: forward pass as FP32 FFMA2s fed from shared memory (the round-1 form) */
+#define MPPIB_FLAG_NO_WARP_SPEC 256u     /* Autorally pair: keep the generic one-thread-per-sample K1 instead of the warp-   \
+                                            specialised producer / consumer kernel (rollout_kernel_ar_ws.cuh) */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
 

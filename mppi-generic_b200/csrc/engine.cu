@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -33,6 +34,7 @@
 #include "plugins/costs.cuh"
 #include "plugins/dynamics.cuh"
 #include "rollout_kernel.cuh"
+#include "rollout_kernel_ar_ws.cuh"
 #include "rollout_kernel_nn_tc.cuh"
 
 namespace
@@ -132,13 +134,16 @@ struct mppib_engine
   int n_local = 0, n_offset = 0;
   int pstride = 0, nchunks = 0;
   int bx = 64, grid = 0;  // bx = samples (noise-tile rows) per CTA
-  int spt = 1;  // samples per thread (rollout_kernel.cuh); threads per CTA = bx / spt
+  int spt = 1;  // samples per thread (rollout_kernel.cuh); threads per CTA = bx / spt * lps
+  int lps = 1;  // lanes per sample = 32 / DYN::SAMPLES_PER_WARP (rollout_kernel.cuh: SPW)
   bool stream_k1 = false;  // streaming K1: noise slabs through a ring, controls kept in HBM (rollout_kernel.cuh: STREAM)
   int ring = 2;
   uint32_t smem_bytes = 0;
   bool use_tma = false;
   bool use_pdl = true;
   bool nn_tc = false;  // Autorally pair: NN forward pass on tcgen05 tensor cores (rollout_kernel_nn_tc.cuh)
+  bool ar_ws = false;  // Autorally pair: warp-specialised K1 (rollout_kernel_ar_ws.cuh)
+  int ws_pspw = 16;    // its samples per producer warp: threads per CTA = bx * (32 / ws_pspw + 1)
   bool mapped_result = true;  // K2 writes the result record straight into mapped pinned host memory
   bool spin_wait = true;      // the host waits for the solve by polling a mapped flag K2's last block sets
   unsigned* k2_counter_d = nullptr;
@@ -360,6 +365,8 @@ struct Pair
   }
   static constexpr bool kHasTensorCoreVariant = std::is_same<DYN, plugins::AutorallyNNDynamics>::value &&
                                                 std::is_same<COST, plugins::ARStandardCost>::value;
+  static constexpr bool kHasWarpSpecVariant = std::is_same<DYN, plugins::AutorallyNNMmaDynamics<32>>::value &&
+                                              std::is_same<COST, plugins::ARStandardCost>::value;
   static int prepare(mppib_engine& e)
   {
     if constexpr (kHasTensorCoreVariant)
@@ -372,6 +379,21 @@ struct Pair
         else
           CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)e.smem_bytes));
+        return MPPIB_OK;
+      }
+    }
+    if constexpr (kHasWarpSpecVariant)
+    {
+      if (e.ar_ws)
+      {
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_ws<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)e.smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_ws<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)e.smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_ws<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)e.smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_ar_ws<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)e.smem_bytes));
         return MPPIB_OK;
       }
     }
@@ -467,7 +489,26 @@ struct Pair
         launched = true;
       }
     }
-    const int threads = e.bx / e.spt;
+    if constexpr (kHasWarpSpecVariant)
+    {
+      if (e.ar_ws)
+      {
+        const int ws_threads = e.bx * ar_ws::warpsPerGroup(e.ws_pspw);
+        if (e.ws_pspw == 16)
+        {
+          if (e.writeback)
+            rollout_kernel_ar_ws<true, 16><<<e.grid, ws_threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+          else
+            rollout_kernel_ar_ws<false, 16><<<e.grid, ws_threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+        }
+        else if (e.writeback)
+          rollout_kernel_ar_ws<true, 32><<<e.grid, ws_threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+        else
+          rollout_kernel_ar_ws<false, 32><<<e.grid, ws_threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+        launched = true;
+      }
+    }
+    const int threads = e.bx / e.spt * e.lps;
     if (launched)
     {
     }
@@ -610,6 +651,7 @@ struct PairEntry
   int (*dyn_shared_floats)(const int*, int);
   int max_block_threads;
   int max_spt;
+  int spw;  // DYN::SAMPLES_PER_WARP: 32 = one sample per lane; 16 / 8 = sub-warp sample groups (plugins/nn_mma.cuh)
   int (*cost_shared_floats)(int);
   int (*launch)(mppib_engine&, const float*, const float*, int, int);
   int (*prepare)(mppib_engine&);
@@ -630,12 +672,13 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     &DYN::sharedFloats,
                     DYN::MAX_BLOCK_THREADS,
                     DYN::MAX_SPT,
+                    DYN::SAMPLES_PER_WARP,
                     &Pair<DYN, COST>::cost_shared,
                     &Pair<DYN, COST>::launch,
                     &Pair<DYN, COST>::prepare,
-                    &init_eval_launch<DYN, COST>,
+                    &init_eval_launch<typename DYN::AuxDyn, COST>,
                     &Pair<DYN, COST>::stream_blocks_per_sm,
-                    &sampled_traj_launch<DYN, COST> };
+                    &sampled_traj_launch<typename DYN::AuxDyn, COST> };
 }
 static const PairEntry kPairs[] = {
   make_entry<plugins::CartpoleDynamics, plugins::CartpoleQuadraticCost>(MPPIB_DYN_CARTPOLE,
@@ -648,8 +691,11 @@ static const PairEntry kPairs[] = {
                                                                           MPPIB_COST_QUADROTOR_QUADRATIC),
 };
 
+// the Autorally pair's default form, one entry per samples-per-warp width (chosen at create time from n_local)
 static const PairEntry kPairsMma[] = {
-  make_entry<plugins::AutorallyNNMmaDynamics, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
+  make_entry<plugins::AutorallyNNMmaDynamics<32>, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
+  make_entry<plugins::AutorallyNNMmaDynamics<16>, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
+  make_entry<plugins::AutorallyNNMmaDynamics<8>, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
 };
 
 // ---- helpers ----------------------------------------------------------------------------------------------------
@@ -1088,9 +1134,22 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   const bool nn_other = (desc->flags & (MPPIB_FLAG_NN_FFMA2 | MPPIB_FLAG_NN_TENSOR)) || getenv("MPPIB_NN_FFMA2") ||
                         getenv("MPPIB_NN_TENSOR");
   if (entry && desc->dynamics_id == MPPIB_DYN_AUTORALLY_NN && (!nn_other || (desc->flags & MPPIB_FLAG_NN_MMA)))
+  {
+    // samples per warp of the generic kernel's network (plugins/nn_mma.cuh): 32. Narrower sample groups (MPPIB_SPW = 16 / 8)
+    // halve / quarter a warp's tensor work per step, but measured on B200 the step time of a lone warp barely moves
+    // (1.70 / 1.73 / 1.45 us per step at 4096 rollouts, profiles/r02_autorally_k1_notes.md): the chain, not the work, is
+    // the limit — which the warp-specialised kernel (rollout_kernel_ar_ws.cuh, the default for D == 1) removes instead.
+    int spw = 32;
+    if (const char* sv = getenv("MPPIB_SPW"))
+    {
+      const int v = atoi(sv);
+      if (v == 32 || v == 16 || v == 8)
+        spw = v;
+    }
     for (const auto& p : kPairsMma)
-      if (p.cost_id == desc->cost_id)
+      if (p.cost_id == desc->cost_id && p.spw == spw)
         entry = &p;
+  }
   if (!entry)
     return fail(MPPIB_ERR_UNSUPPORTED, "no kernel registered for dynamics %d + cost %d", desc->dynamics_id,
                 desc->cost_id);
@@ -1162,7 +1221,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
   CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, desc->device));
   CUDA_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, desc->device));
-  auto smem_for = [&](int b) {
+  std::function<int(int)> smem_for = [&](int b) {
     return (int)rollout_smem_layout(b, e->nchunks, e->D, e->TC, e->dyn_shared_floats_fn(e->desc.model_dims, b),
                                     e->cost_shared_floats(e->T))
         .total;
@@ -1179,24 +1238,65 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
       spt = v;
   }
   e->spt = spt;
+  const int lps = 32 / entry->spw;
+  e->lps = lps;
+  // Autorally pair, one system: the warp-specialised K1 (rollout_kernel_ar_ws.cuh) — a producer and a consumer warp per 32
+  // samples. MPPIB_NO_WS / MPPIB_SPW / MPPIB_SPT keep the generic kernel (A/B runs, tests of the generic form).
+  const bool is_mma32 = entry >= kPairsMma && entry < kPairsMma + sizeof(kPairsMma) / sizeof(kPairsMma[0]) && entry->spw == 32;
+  e->ar_ws = is_mma32 && e->D == 1 && !e->rmppi && spt == 1 && !getenv("MPPIB_NO_WS") && !getenv("MPPIB_SPW") &&
+             !(desc->flags & MPPIB_FLAG_NO_WARP_SPEC);
+  const bool ws = e->ar_ws;
+  if (const char* sv = getenv("MPPIB_WS_PSPW"))
+    if (atoi(sv) == 32 || atoi(sv) == 16)
+      e->ws_pspw = atoi(sv);
+  const int ws_wpg = ar_ws::warpsPerGroup(e->ws_pspw);
+  if (ws)
+    smem_for = [&](int b) {
+      return (int)rollout_smem_layout(b, e->nchunks, 1, e->TC, ar_ws::sharedFloats(b), e->cost_shared_floats(e->T)).total;
+    };
+  const int unit = ws ? 32 : entry->spw * spt;  // samples per warp of threads
+  const int max_bx = ws ? 256 : entry->max_block_threads / 32 * unit;  // samples per CTA (__launch_bounds__)
+  auto threads_for = [&](int b) { return ws ? ws_wpg * b : b / spt * lps; };
+  // resident CTAs per SM: shared memory (+1 KB the hardware reserves per CTA), threads, and for the warp-specialised kernel
+  // its 128-register budget
+  auto ctas_per_sm = [&](int b, int sm) {
+    int n = std::min(std::min(smem_per_sm / (sm + 1024), 2048 / threads_for(b)), 32);
+    if (ws)  // registers: __launch_bounds__(maxThreads, 1) lets ptxas use 65536 / maxThreads per thread
+      n = std::min(n, ar_ws::maxThreads(e->ws_pspw) / threads_for(b));
+    return n;
+  };
   int bx = 0;
   if (const char* s = getenv("MPPIB_BX"))
   {
     bx = atoi(s);
-    if (bx < 32 || bx > 512 || (bx % (32 * spt)) != 0)
+    if (bx < unit || bx > 512 || (bx % unit) != 0)
       bx = 0;
+  }
+  if (bx == 0 && ws)
+  {
+    // warp-specialised kernel: up to one warp per scheduler, one pair per CTA (no two producers ever share a scheduler);
+    // beyond that ONE CTA per SM, as narrow as covers n_local, so that every SM is busy and the kernel's alternating role
+    // table (P C C P C P P C) balances producers over the four schedulers. Wider than fits: the wave rule below.
+    const long pairs_total = (e->n_local + 31) / 32;
+    if (ws_wpg * pairs_total <= 4L * num_sms)
+      bx = 32;
+    else
+    {
+      const int need = (int)(((e->n_local + num_sms - 1) / num_sms + 31) / 32) * 32;
+      if (need <= max_bx && smem_for(need) <= max_smem)
+        bx = need;
+    }
   }
   if (bx == 0)
   {
     int best = 0;
     long best_waves = 1L << 40;
-    for (int cand = 64; cand <= entry->max_block_threads * spt; cand += 32 * spt)
+    for (int cand = ws ? unit : std::max(unit, 64 / lps); cand <= max_bx; cand += unit)
     {
       const int sm = smem_for(cand);
       if (sm > max_smem)
         break;
-      // +1 KB per CTA is what the hardware reserves out of the SM's shared memory
-      const int per_sm = std::min(std::min(smem_per_sm / (sm + 1024), 2048 / (cand / spt)), 32);
+      const int per_sm = ctas_per_sm(cand, sm);
       if (per_sm < 1)
         break;
       const long blocks = (e->n_local + cand - 1) / cand;
@@ -1207,15 +1307,15 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
         best = cand;
       }
     }
-    bx = best ? best : 32;
+    bx = best ? best : unit;
   }
-  if (bx > entry->max_block_threads * spt)
-    bx = entry->max_block_threads * spt;
-  bx = (bx / (32 * spt)) * (32 * spt);  // whole warps of threads
-  if (bx < 32 * spt)
-    bx = 32 * spt;
-  while (smem_for(bx) > max_smem && bx > 32)
-    bx -= 32;
+  if (bx > max_bx)
+    bx = max_bx;
+  bx = (bx / unit) * unit;  // whole warps of threads
+  if (bx < unit)
+    bx = unit;
+  while (smem_for(bx) > max_smem && bx > unit)
+    bx -= unit;
   e->smem_bytes = (uint32_t)smem_for(bx);
   if ((int)e->smem_bytes > max_smem)
     return bail(fail(MPPIB_ERR_SMEM, "noise tile needs %u B of shared memory, device allows %d", e->smem_bytes,
@@ -1239,7 +1339,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   {
     const bool tma_ok = !(desc->flags & MPPIB_FLAG_NO_TMA) && (e->TC % 4 == 0) && !getenv("MPPIB_NO_TMA");
     const int sm_res = smem_for(bx);
-    const int per_sm_res = std::max(1, std::min(std::min(smem_per_sm / (sm_res + 1024), 2048 / (bx / spt)), 32));
+    const int per_sm_res = std::max(1, ctas_per_sm(bx, sm_res));
     const long blocks_res = (e->n_local + bx - 1) / bx;
     const long waves_res = (blocks_res + (long)per_sm_res * num_sms - 1) / ((long)per_sm_res * num_sms);
     int sbx = 64;
@@ -1253,7 +1353,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
                                                 e->cost_shared_floats(e->T))
                            .total;
     bool want = false;
-    if (tma_ok && !e->rmppi && !e->nn_tc && spt == 1 && e->nchunks > e->ring && sm_str <= max_smem)
+    if (tma_ok && !e->rmppi && !e->nn_tc && !ws && spt == 1 && lps == 1 && e->nchunks > e->ring && sm_str <= max_smem)
     {
       const int per_sm_str = entry->stream_blocks_per_sm(e->D, sbx, (size_t)sm_str);
       if (per_sm_str > 0)
@@ -1274,7 +1374,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     }
   }
   e->bx = bx;
-  e->dyn_shared_floats = e->dyn_shared_floats_fn(e->desc.model_dims, bx);
+  e->dyn_shared_floats = ws ? ar_ws::sharedFloats(bx) : e->dyn_shared_floats_fn(e->desc.model_dims, bx);
   e->grid = (e->n_local + bx - 1) / bx;
   if (e->grid > kCombineMaxRecords)
     return bail(fail(MPPIB_ERR_UNSUPPORTED, "%d rollout blocks exceed the combine kernel's %d records; raise MPPIB_BX",
@@ -2313,7 +2413,7 @@ int mppib_get_launch_info(mppib_engine* e, int* grid, int* block, int* smem_byte
   if (grid)
     *grid = e->grid;
   if (block)
-    *block = e->nn_tc ? e->bx : e->bx / e->spt;
+    *block = e->nn_tc ? e->bx : (e->ar_ws ? ar_ws::warpsPerGroup(e->ws_pspw) * e->bx : e->bx / e->spt * e->lps);
   if (smem_bytes)
     *smem_bytes = (int)e->smem_bytes;
   if (uses_tma)

@@ -32,24 +32,6 @@ struct Cost
   {
     return 0.0f;  // cost.cuh:205-208
   }
-  // Deferred-cost protocol of the rollout kernel (DYN::DEFER_COST): prefetch() issues whatever long-latency loads the
-  // running cost of output y needs and returns their raw results; computeRunningCostPrefetched() is computeRunningCost
-  // with those results handed in. Default: nothing to prefetch.
-  struct Prefetch
-  {
-  };
-  template <class AUX>
-  __device__ static __forceinline__ auto prefetch(const Params&, const AUX&, const float* /*y*/)
-  {
-    return typename CLASS_T::Prefetch{};
-  }
-  template <class AUX, class PF>
-  __device__ static __forceinline__ float computeRunningCostPrefetched(const Params& p, const AUX& aux, const float* theta_c,
-                                                                       const float* y, const float* u, int t, int* crash,
-                                                                       const PF&)
-  {
-    return CLASS_T::computeRunningCost(p, aux, theta_c, y, u, t, crash);
-  }
   // cost.cu:40-53
   template <class AUX>
   __device__ static __forceinline__ float computeRunningCost(const Params& p, const AUX& aux, const float* theta_c,
@@ -142,6 +124,11 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
   {
     float u = p.r_c1[0] * x + p.r_c2[0] * y + p.trs[0];
     float v = p.r_c1[1] * x + p.r_c2[1] * y + p.trs[1];
+    // An affine map transform (third row 0 0 1: every track map the reference ships) has w == 1 exactly and u / 1 == u, so
+    // the four IEEE divisions of a step (66 SASS instructions) are skipped on a block-uniform test of the parameters;
+    // projective transforms keep them.
+    if (p.r_c1[2] == 0.0f && p.r_c2[2] == 0.0f && p.trs[2] == 1.0f)
+      return tex2D<float4>(aux.costmap_tex, u, v);
     float w = p.r_c1[2] * x + p.r_c2[2] * y + p.trs[2];
     return tex2D<float4>(aux.costmap_tex, u / w, v / w);
   }
@@ -199,40 +186,6 @@ struct ARStandardCost : public Cost<ARStandardCost, mppib_ar_standard_cost_param
     if (track_cost_front >= p.boundary_threshold || track_cost_back >= p.boundary_threshold)
       crash[0] = 1;
     return track_cost;
-  }
-  // deferred-cost protocol: the two map lookups of getTrackCost are issued by prefetch() and finished here
-  struct Prefetch
-  {
-    float front, back;
-  };
-  __device__ static __forceinline__ Prefetch prefetch(const Params& p, const Aux& aux, const float* s)
-  {
-    float sn, cs;
-    __sincosf(s[2], &sn, &cs);
-    Prefetch pf;
-    pf.front = queryTextureTransformed(p, aux, s[0] + p.front_d * cs, s[1] + p.front_d * sn).x;
-    pf.back = queryTextureTransformed(p, aux, s[0] + p.back_d * cs, s[1] + p.back_d * sn).x;
-    return pf;
-  }
-  __device__ static __forceinline__ float computeRunningCostPrefetched(const Params& p, const Aux&, const float* theta_c,
-                                                                       const float* s, const float* /*u*/, int timestep,
-                                                                       int* crash_status, const Prefetch& pf)
-  {
-    // getTrackCost (above) from the prefetched texels, then computeStateCost's sum in its order
-    float track_cost = (fabsf(pf.front) + fabsf(pf.back)) / 2.0f;
-    if (fabsf(track_cost) < p.track_slop)
-      track_cost = 0;
-    else
-      track_cost = p.track_coeff * track_cost;
-    if (pf.front >= p.boundary_threshold || pf.back >= p.boundary_threshold)
-      crash_status[0] = 1;
-    float speed_cost = getSpeedCost(p, s);
-    float stabilizing_cost = getStabilizingCost(p, s, crash_status);
-    float crash_cost = theta_c[timestep] * getCrashCost(p, crash_status);
-    float cost = speed_cost + crash_cost + track_cost + stabilizing_cost;
-    if (cost > MAX_COST_VALUE || isnan(cost))
-      cost = MAX_COST_VALUE;
-    return cost;
   }
   __device__ static __forceinline__ float computeStateCost(const Params& p, const Aux& aux, const float* theta_c,
                                                            const float* s, int timestep, int* crash_status)

@@ -60,7 +60,10 @@ struct Dynamics
   static constexpr int MAX_SPT = 1;  // samples one thread may roll out side by side (rollout_kernel.cuh: SPT)
   static constexpr int MAX_BLOCK_THREADS = 256;  // __launch_bounds__ of the rollout kernel for this model
   static constexpr bool UNROLL_STEPS = true;     // unroll the 4/C steps that share one 16-byte noise group
-  static constexpr bool DEFER_COST = false;      // rollout_kernel.cuh: issue a step's cost lookups a step ahead of their use
+  // rollout_kernel.cuh: samples a warp carries. 32 = one per lane; fewer = lanes l, l + SPW, ... share a sample (models whose
+  // step is warp-collective, plugins/nn_mma.cuh, shorten the per-warp chain this way when a GPU holds few rollouts)
+  static constexpr int SAMPLES_PER_WARP = 32;
+  using AuxDyn = CLASS_T;  // the form the one-thread-per-rollout auxiliary kernels (init-eval, sampled trajectories) instantiate
   struct Aux
   {
   };
@@ -253,11 +256,12 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
       y[i] = x[i];
   }
 
-  // ar_nn_model.cu:123-128 (cosf / sinf, not the fast intrinsics, in the reference's device code)
+  // ar_nn_model.cu:123-128 (cosf / sinf, not the fast intrinsics, in the reference's device code): full-precision sine and
+  // cosine from one shared range reduction (device_utils.cuh: sincos_cw, 1.5 ulp)
   __device__ static __forceinline__ void computeKinematics(const Params&, const float* state, float* state_der)
   {
     float sn, cs;
-    sincosf(state[2], &sn, &cs);
+    sincos_cw(state[2], &sn, &cs);
     state_der[0] = cs * state[4] - sn * state[5];
     state_der[1] = sn * state[4] + cs * state[5];
     state_der[2] = -state[6];
@@ -445,24 +449,28 @@ struct AutorallyNNDynamics : public Dynamics<AutorallyNNDynamics, mppib_ar_nn_dy
 };
 
 // ---- Autorally NeuralNetModel<7,2,3> with the network on the legacy tensor path (plugins/nn_mma.cuh): a warp evaluates
-//      its 32 samples with mma.sync (FP16 hi / lo split, three products, FP32 accumulate). Everything around the network
-//      is AutorallyNNDynamics'. Selected by MPPIB_FLAG_NN_MMA (engine.cu). -------------------------------------------------
-struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>
+//      SPW = 32 / 16 / 8 samples with mma.sync (FP16 hi / lo split, three products, FP32 accumulate). With SPW < 32 the
+//      lanes l, l + SPW, ... of a warp carry the same sample (rollout_kernel.cuh: SAMPLES_PER_WARP) and only the first
+//      owns its results: a shorter per-step chain per warp and more warps per scheduler when a GPU holds few rollouts.
+//      Everything around the network is AutorallyNNDynamics'. The default form of the pair (engine.cu). -------------------
+template <int SPW>
+struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics<SPW>, mppib_ar_nn_dyn_params, 7, 2, 8>
 {
+  using Base = Dynamics<AutorallyNNMmaDynamics<SPW>, mppib_ar_nn_dyn_params, 7, 2, 8>;
+  using Params = typename Base::Params;
   static constexpr int DYNAMICS_DIM = 4;
-#ifdef MPPIB_EXP_DEFER_COST  // experimental (round 2): not yet run on a GPU
-  static constexpr bool DEFER_COST = true;
-#endif
+  static constexpr int SAMPLES_PER_WARP = SPW;
+  using AuxDyn = AutorallyNNMmaDynamics<32>;  // the auxiliary kernels map one lane to one rollout
   static constexpr int MAX_SPT = 1;
-  static constexpr int MAX_BLOCK_THREADS = 256;
+  static constexpr int MAX_BLOCK_THREADS = SPW == 32 ? 256 : 512;  // <= 256 samples per block either way
   static constexpr bool UNROLL_STEPS = false;
   using Aux = AutorallyNNDynamics::Aux;
-  // fragment-ordered weights + 1 KB of transposition scratch per warp
+  // fragment-ordered weights + transposition scratch per warp; bx = samples per block
   static int sharedFloats(const int* /*model_dims*/, int bx)
   {
-    return nn_mma::sharedFloats(bx);
+    return nn_mma::sharedFloats(bx * (32 / SPW), SPW);
   }
-  using Dynamics<AutorallyNNMmaDynamics, mppib_ar_nn_dyn_params, 7, 2, 8>::initializeDynamics;  // the Carry overload
+  using Base::initializeDynamics;  // the Carry overload
   __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s,
                                                             const float* x, float* y)
   {
@@ -473,15 +481,7 @@ struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar
   }
   __device__ static __forceinline__ void computeKinematics(const Params& p, const float* state, float* state_der)
   {
-#ifdef MPPIB_EXP_FAST_SINCOS  // ablation only (tools/run_mma_exp.sh): the reference's device code uses cosf / sinf
-    float sn, cs;
-    __sincosf(state[2], &sn, &cs);
-    state_der[0] = cs * state[4] - sn * state[5];
-    state_der[1] = sn * state[4] + cs * state[5];
-    state_der[2] = -state[6];
-#else
     AutorallyNNDynamics::computeKinematics(p, state, state_der);
-#endif
   }
   // warp-collective: every lane of the warp calls it (the rollout kernels keep out-of-range rows running)
   __device__ static __forceinline__ void computeDynamics(const Params&, const float* theta_s, const float* state,
@@ -493,14 +493,8 @@ struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics, mppib_ar
       in[i] = state[i + (7 - DYNAMICS_DIM)];
     in[4] = control[0];
     in[5] = control[1];
-    float* scratch = const_cast<float*>(theta_s) + nn_mma::kFixedFloats + (threadIdx.x >> 5) * nn_mma::kScratchPerWarp;
-#if defined(MPPIB_EXP_NEWTON)  // ablation only: reciprocal of the tanh on the FP32 pipe instead of MUFU (measured slower)
-    nn_mma::forward<1>(theta_s, scratch, in, out);
-#elif defined(MPPIB_EXP_PAIR_RCP)  // experimental (round 2): one MUFU.RCP per pair of tanh
-    nn_mma::forward<2>(theta_s, scratch, in, out);
-#else
-    nn_mma::forward<0>(theta_s, scratch, in, out);
-#endif
+    float* scratch = const_cast<float*>(theta_s) + nn_mma::kFixedFloats + (threadIdx.x >> 5) * nn_mma::scratchPerWarp(SPW);
+    nn_mma::forward<SPW>(theta_s, scratch, in, out);
 #pragma unroll
     for (int i = 0; i < DYNAMICS_DIM; i++)
       state_der[i + (7 - DYNAMICS_DIM)] = out[i];
@@ -695,10 +689,9 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
                   off_b2 = off_w2 + L1p;
     const float4* G = reinterpret_cast<const float4*>(theta_s);
     float hn[HC];
-#ifdef MPPIB_EXP_LSTM_FFMA2
-    // experimental (round 2, compiled but never run): the four gate sums of a row and the four neurons of a head group as
-    // two packed FFMA2 each. Every lane is the same IEEE fma in the same order as below, so the results are identical;
-    // the kernel is issue-bound (66 % issue active) and this removes ~140 of its ~1060 instructions per warp-step.
+    // the four gate sums of a row and the four neurons of a head group as two packed FFMA2 each: every lane is the same
+    // IEEE fma in the same order as the scalar form (lstm_forward), so the results are identical; the kernel is issue-bound
+    // (66 % issue active) and this removes ~140 of its ~1060 instructions per warp-step (K1 at C5: 621 -> 610 us, B200).
     float2 in2[I], h2[HC];
 #pragma unroll
     for (int j = 0; j < I; j++)
@@ -760,66 +753,6 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       out = fmaf(w2.w, tanh_fast(acc_zw.y + b.w), out);
     }
     return out + theta_s[off_b2];
-#else
-#pragma unroll
-    for (int i = 0; i < HC; i++)
-    {
-      const float4* row = G + i * row_f4;
-      float gi = 0.0f, gf = 0.0f, go = 0.0f, gc = 0.0f;
-#pragma unroll
-      for (int j = 0; j < I; j++)
-      {
-        const float4 w = row[j];
-        gi = fmaf(w.x, in[j], gi);
-        gf = fmaf(w.y, in[j], gf);
-        go = fmaf(w.z, in[j], go);
-        gc = fmaf(w.w, in[j], gc);
-      }
-#pragma unroll
-      for (int j = 0; j < HC; j++)
-      {
-        const float4 w = row[I + j];
-        gi = fmaf(w.x, k.h[j], gi);
-        gf = fmaf(w.y, k.h[j], gf);
-        go = fmaf(w.z, k.h[j], go);
-        gc = fmaf(w.w, k.h[j], gc);
-      }
-      const float4 b = row[I + HC];
-      gi = sigmoid_dev(gi + b.x);
-      gf = sigmoid_dev(gf + b.y);
-      go = sigmoid_dev(go + b.z);
-      gc = tanh_fast(gc + b.w);
-      k.c[i] = gi * gc + gf * k.c[i];
-      hn[i] = tanh_fast(k.c[i]) * go;
-    }
-#pragma unroll
-    for (int i = 0; i < HC; i++)
-      k.h[i] = hn[i];
-    const float* W1T = theta_s + off_w1t;
-    float out = 0.0f;
-#pragma unroll
-    for (int k4 = 0; k4 < L1p; k4 += 4)
-    {
-      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-      for (int j = 0; j < HC + I; j++)
-      {
-        const float4 w = *reinterpret_cast<const float4*>(W1T + j * L1p + k4);
-        const float a = j < HC ? hn[j < HC ? j : 0] : in[j < HC ? 0 : j - HC];
-        acc.x = fmaf(w.x, a, acc.x);
-        acc.y = fmaf(w.y, a, acc.y);
-        acc.z = fmaf(w.z, a, acc.z);
-        acc.w = fmaf(w.w, a, acc.w);
-      }
-      const float4 b = *reinterpret_cast<const float4*>(theta_s + off_b1 + k4);
-      const float4 w2 = *reinterpret_cast<const float4*>(theta_s + off_w2 + k4);
-      out = fmaf(w2.x, tanh_fast(acc.x + b.x), out);
-      out = fmaf(w2.y, tanh_fast(acc.y + b.y), out);
-      out = fmaf(w2.z, tanh_fast(acc.z + b.z), out);
-      out = fmaf(w2.w, tanh_fast(acc.w + b.w), out);
-    }
-    return out + theta_s[off_b2];
-#endif
   }
 
   // LSTMHelper::forward (device) + head; returns the head's single output. h is read from the buffer of parity

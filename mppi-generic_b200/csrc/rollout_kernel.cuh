@@ -168,9 +168,15 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
+  // SPW = samples per warp (DYN::SAMPLES_PER_WARP). 32: lane l owns tile row (warp * 32 + l). Fewer (models whose step is
+  // warp-collective, plugins/nn_mma.cuh): lanes l, l + SPW, ... carry the same row and compute the same values; the first
+  // of them (`owner`) alone stores the cost and contributes to the block's sums.
+  constexpr int SPW = DYN::SAMPLES_PER_WARP;
+  static_assert(SPW == 32 || SPT == 1, "sub-warp sample groups are built for one sample per thread");
   const int nthr = blockDim.x;
-  const int bx = nthr * SPT;  // samples (tile rows) per block
+  const int bx = (SPW == 32) ? nthr * SPT : (nthr >> 5) * SPW;  // samples (tile rows) per block
   const int thr = threadIdx.x;
+  const bool owner = (SPW == 32) || ((thr & 31) < SPW);
   const int T = args.T;
   const int TC = T * C;
   const int nchunks = args.nchunks;
@@ -191,12 +197,15 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
 #pragma unroll
   for (int sp = 0; sp < SPT; sp++)
   {
-    row[sp] = thr + sp * nthr;
+    row[sp] = (SPW == 32) ? thr + sp * nthr : (thr >> 5) * SPW + (thr & (SPW - 1));
     n_loc[sp] = row0 + row[sp];
-    valid[sp] = n_loc[sp] < args.n_local;
+    valid[sp] = owner && n_loc[sp] < args.n_local;
     const int n_glob = args.n_offset + n_loc[sp];
-    pure_noise[sp] = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
-    zero_noise_sample[sp] = (n_glob == 0);                             // gaussian.cu:101
+    int pn = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
+    int zn = (n_glob == 0);                                    // gaussian.cu:101
+    asm volatile("" : "+r"(pn), "+r"(zn));                     // kept as flags: no per-step re-read of the parameter bank
+    pure_noise[sp] = pn != 0;
+    zero_noise_sample[sp] = zn != 0;
   }
 
   // ---- stage the block's noise rows -------------------------------------------------------------------------------
@@ -280,170 +289,148 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
       lr_scale[d][c] = args.samp.control_cost_coeff[c] / (args.samp.std_dev[d][c] * args.samp.std_dev[d][c]);
       lr_on = lr_on || (args.samp.control_cost_coeff[c] != 0.0f);
     }
-  const float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
+  float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
+  asm volatile("" : "+f"(half_lambda_1ma));  // computed once, not once per step
 
-  // Deferred running cost (DYN::DEFER_COST, experimental, profiles/r01_autorally_k1_notes.md): the cost of step t needs
-  // texture data whose latency nothing overlaps when a scheduler holds one or two warps. With DEFER the lookups of step t
-  // are ISSUED right after its state is known (COST::prefetch) and CONSUMED after the dynamics of step t + 1
-  // (COST::computeRunningCostPrefetched on the kept copy of y / u), in step order, so the sticky crash flag and the sums see
-  // exactly the sequence they see without it.
-  constexpr bool DEFER = DYN::DEFER_COST && !RMPPI;
-  float y_prev[DEFER ? M : 1][O], u_prev[DEFER ? M : 1][C];
-  typename COST::Prefetch pf[DEFER ? M : 1];
-  int t_prev = -1;
-  auto consume_deferred = [&]() {
-    if constexpr (DEFER)
+  // ---- the horizon ----------------------------------------------------------------------------------------------
+  // One loop over the horizon's 16-byte noise groups (4 / C steps each); slab k = groups 8k .. 8k+7. Everything a step
+  // needs that does not change along the horizon — the row's byte offset and swizzle key, the decayed sigmas, the special
+  // sample flags — is computed here once and pinned in registers (the optimiser otherwise re-derives the shared-memory
+  // carve-up and re-reads the parameter bank every step: ~70 of the NN kernel's ~690 instructions per step).
+  uint32_t row_off[SPT], swz[SPT];
+#pragma unroll
+  for (int sp = 0; sp < SPT; sp++)
+  {
+    row_off[sp] = (uint32_t)row[sp] * kChunkBytes;
+    swz[sp] = (uint32_t)row[sp] & 7u;
+    asm volatile("" : "+r"(row_off[sp]), "+r"(swz[sp]));
+  }
+  float sd_dec[D][C];
+#pragma unroll
+  for (int d = 0; d < D; d++)
+#pragma unroll
+    for (int c = 0; c < C; c++)
     {
+      sd_dec[d][c] = args.samp.std_dev_decayed[d][c];
+      asm volatile("" : "+f"(sd_dec[d][c]));
+    }
+  const int opt_stride = args.opt_stride;
+  const int ngroups = (TC + 3) >> 2;
+  const uint32_t slab_bytes = (uint32_t)bx * kChunkBytes;
+  unsigned char* slab = tile;
+  int slot = 0;
+#pragma unroll 1
+  for (int gi = 0; gi < ngroups; gi++)
+  {
+    const int k = gi >> 3, g = gi & 7;
+    if (g == 0)
+    {
+      slot = STREAM ? (k % ring) : k;  // buffer that holds slab k
+      if (args.use_tma)
+        mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
+      slab = tile + (size_t)slot * slab_bytes;
+    }
+    unsigned char* gp[SPT];
+    float4 e4[SPT];
+#pragma unroll
+    for (int sp = 0; sp < SPT; sp++)
+    {
+      gp[sp] = slab + row_off[sp] + (((uint32_t)g ^ swz[sp]) << 4);
+      e4[sp] = *reinterpret_cast<const float4*>(gp[sp]);
+    }
+    // light models: the 4/C steps of a 16-byte group are unrolled; heavy ones (NN) keep one copy of the step body
+#pragma unroll(DYN::UNROLL_STEPS ? STEPS_PER_GROUP : 1)
+    for (int s = 0; s < STEPS_PER_GROUP; s++)
+    {
+      const int t = gi * STEPS_PER_GROUP + s;
+      if (t >= T)
+        break;
+      float u[M][C], x_next[M][S], xdot[M][S], ufb[C];
 #pragma unroll
       for (int m = 0; m < M; m++)
       {
         const int sp = m / D, d = m % D;
-        float step_cost = COST::computeRunningCostPrefetched(args.cost, args.cost_aux, theta_c, y_prev[m], u_prev[m], t_prev,
-                                                             &crash_status[m], pf[m]);
-        if (lr_on)
-          step_cost += likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t_prev) * C, u_prev[m], pure_noise[sp],
-                                                half_lambda_1ma);
-        running_cost[m] += step_cost;
-      }
-    }
-  };
-
-  // ---- the horizon ----------------------------------------------------------------------------------------------
-  for (int k = 0; k < nchunks; k++)
-  {
-    const int slot = STREAM ? (k % ring) : k;  // buffer that holds slab k
-    if (args.use_tma)
-      mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
-#pragma unroll 1
-    for (int g = 0; g < 8; g++)
-    {
-      const int col0 = k * kChunkFloats + g * 4;
-      if (col0 >= TC)
-        break;
-      unsigned char* gp[SPT];
-      float4 e4[SPT];
+        const bool use_mean = zero_noise_sample[sp] || (t < opt_stride);
+        const float* mean_t = means_s + (d * T + t) * C;
 #pragma unroll
-      for (int sp = 0; sp < SPT; sp++)
-      {
-        gp[sp] = tile + tile_offset_bytes(bx, slot, row[sp], g);
-        e4[sp] = *reinterpret_cast<const float4*>(gp[sp]);
-      }
-      // light models: the 4/C steps of a 16-byte group are unrolled; heavy ones (NN) keep one copy of the step body
-#pragma unroll(DYN::UNROLL_STEPS ? STEPS_PER_GROUP : 1)
-      for (int s = 0; s < STEPS_PER_GROUP; s++)
-      {
-        const int t = col0 / C + s;
-        if (t >= T)
-          break;
-        float u[M][C], x_next[M][S], xdot[M][S], ufb[C];
-#pragma unroll
-        for (int m = 0; m < M; m++)
-        {
-          const int sp = m / D, d = m % D;
-          const bool use_mean = zero_noise_sample[sp] || (t < args.opt_stride);
-          const float* mean_t = means_s + (d * T + t) * C;
+        for (int c = 0; c < C; c++)
+          u[m][c] = sample_control(mean_t[c], sd_dec[d][c], group_elem(e4[sp], s * C + c), use_mean, pure_noise[sp]);
+        if (RMPPI && m == 1)
+        {  // fb_controller->k(x, x_nom, t) (rmppi_kernels.cu:770-784; DDP: K_t e, ddp.cu:11-45 in its host form)
 #pragma unroll
           for (int c = 0; c < C; c++)
-            u[m][c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], group_elem(e4[sp], s * C + c), use_mean,
-                                     pure_noise[sp]);
-          if (RMPPI && m == 1)
-          {  // fb_controller->k(x, x_nom, t) (rmppi_kernels.cu:770-784; DDP: K_t e, ddp.cu:11-45 in its host form)
-#pragma unroll
-            for (int c = 0; c < C; c++)
-              ufb[c] = 0.0f;
-            if (args.fb_gains != nullptr)
-            {
-              const float* Kt = args.fb_gains + (size_t)t * S * C;
-#pragma unroll
-              for (int i = 0; i < S; i++)
-              {
-                const float e = x[1][i] - x[0][i];
-#pragma unroll
-                for (int c = 0; c < C; c++)
-                  ufb[c] = fmaf(__ldg(Kt + i * C + c), e, ufb[c]);
-              }
-            }
-#pragma unroll
-            for (int c = 0; c < C; c++)
-              u[m][c] += ufb[c];
-          }
-          DYN::enforceConstraints(args.dyn, x[m], u[m]);  // mppi_common.cu:108-111
-          if (D == 1 && !STREAM)
+            ufb[c] = 0.0f;
+          if (args.fb_gains != nullptr)
           {
-            // single system: the constrained control replaces the noise in the shared tile (what writeControlSample does
-            // in HBM, mppi_common.cu:117), so the epilogue's weighted sum reads it back instead of recomputing it
-#pragma unroll
-            for (int c = 0; c < C; c++)
-              reinterpret_cast<float*>(gp[sp])[s * C + c] = u[m][c];
-          }
-          if (WRITEBACK)
-          {  // compat / debug path: keep the constrained samples in HBM like the reference
-            if (valid[sp])
-            {
-              float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc[sp]) * T + t) * C;
-#pragma unroll
-              for (int c = 0; c < C; c++)
-                dst[c] = u[m][c];
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < S; i++)
-            xdot[m][i] = 0.0f;
-        }
-        DYN::template stepBatch<M>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);  // mppi_common.cu:120
-        if constexpr (DEFER)
-        {
-          if (t_prev >= 0)
-            consume_deferred();  // cost of the previous step: its lookups were issued a whole step ago
-#pragma unroll
-          for (int m = 0; m < M; m++)
-          {
-            pf[m] = COST::prefetch(args.cost, args.cost_aux, y[m]);
-#pragma unroll
-            for (int i = 0; i < O; i++)
-              y_prev[m][i] = y[m][i];
-#pragma unroll
-            for (int c = 0; c < C; c++)
-              u_prev[m][c] = u[m][c];
+            const float* Kt = args.fb_gains + (size_t)t * S * C;
 #pragma unroll
             for (int i = 0; i < S; i++)
-              x[m][i] = x_next[m][i];
-          }
-          t_prev = t;
-          continue;
-        }
+            {
+              const float e = x[1][i] - x[0][i];
 #pragma unroll
-        for (int m = 0; m < M; m++)
-        {
-          const int sp = m / D, d = m % D;
-          float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[m], u[m], t, &crash_status[m]);
-          float lr_cost = 0.0f;
-          if (lr_on)
-            lr_cost = likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t) * C, u[m], pure_noise[sp],
-                                               half_lambda_1ma);  // :126-128
-          if (!RMPPI)
-            running_cost[m] += step_cost + lr_cost;
-          else if (m == 0)
-          {  // nominal system: rmppi_kernels.cu:806-811
-            running_cost[m] += step_cost;
-            extra_cost[m] += lr_cost;
+              for (int c = 0; c < C; c++)
+                ufb[c] = fmaf(__ldg(Kt + i * C + c), e, ufb[c]);
+            }
           }
-          else
-          {  // real system: :813-819; computeFeedbackCost = 0.5 lambda (1 - alpha) sum_i k_i u_fb,i^2 / sigma_i^2
-            running_cost[m] += step_cost + lr_cost;
-            float fb_cost = 0.0f;
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            u[m][c] += ufb[c];
+        }
+        DYN::enforceConstraints(args.dyn, x[m], u[m]);  // mppi_common.cu:108-111
+        if (D == 1 && !STREAM)
+        {
+          // single system: the constrained control replaces the noise in the shared tile (what writeControlSample does
+          // in HBM, mppi_common.cu:117), so the epilogue's weighted sum reads it back instead of recomputing it
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            reinterpret_cast<float*>(gp[sp])[s * C + c] = u[m][c];
+        }
+        if (WRITEBACK)
+        {  // compat / debug path: keep the constrained samples in HBM like the reference
+          if (valid[sp])
+          {
+            float* dst = args.controls_out + (((size_t)d * args.n_local + n_loc[sp]) * T + t) * C;
 #pragma unroll
             for (int c = 0; c < C; c++)
-              fb_cost += lr_scale[d][c] * (ufb[c] * ufb[c]);
-            extra_cost[m] += step_cost + half_lambda_1ma * fb_cost;
+              dst[c] = u[m][c];
           }
-#pragma unroll
-          for (int i = 0; i < S; i++)
-            x[m][i] = x_next[m][i];
         }
+#pragma unroll
+        for (int i = 0; i < S; i++)
+          xdot[m][i] = 0.0f;
+      }
+      DYN::template stepBatch<M>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);  // mppi_common.cu:120
+#pragma unroll
+      for (int m = 0; m < M; m++)
+      {
+        const int sp = m / D, d = m % D;
+        float step_cost = COST::computeRunningCost(args.cost, args.cost_aux, theta_c, y[m], u[m], t, &crash_status[m]);
+        float lr_cost = 0.0f;
+        if (lr_on)
+          lr_cost = likelihood_ratio_cost<C>(lr_scale[d], means_s + (d * T + t) * C, u[m], pure_noise[sp],
+                                             half_lambda_1ma);  // :126-128
+        if (!RMPPI)
+          running_cost[m] += step_cost + lr_cost;
+        else if (m == 0)
+        {  // nominal system: rmppi_kernels.cu:806-811
+          running_cost[m] += step_cost;
+          extra_cost[m] += lr_cost;
+        }
+        else
+        {  // real system: :813-819; computeFeedbackCost = 0.5 lambda (1 - alpha) sum_i k_i u_fb,i^2 / sigma_i^2
+          running_cost[m] += step_cost + lr_cost;
+          float fb_cost = 0.0f;
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            fb_cost += lr_scale[d][c] * (ufb[c] * ufb[c]);
+          extra_cost[m] += step_cost + half_lambda_1ma * fb_cost;
+        }
+#pragma unroll
+        for (int i = 0; i < S; i++)
+          x[m][i] = x_next[m][i];
       }
     }
-    if (STREAM)
+    if (STREAM && (g == 7 || gi == ngroups - 1))
     {
       __syncthreads();  // every thread is done with this slab's buffer
       if (thr == 0 && k + ring < nchunks)
@@ -454,11 +441,6 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     }
   }
 
-  if constexpr (DEFER)
-  {
-    if (t_prev >= 0)
-      consume_deferred();  // the last step's cost
-  }
   // ---- per-sample cost (computeAndSaveCost, mppi_common.cu:843-853) ------------------------------------------------
   float cost[M];
 #pragma unroll
@@ -513,7 +495,8 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     for (int sp = 0; sp < SPT; sp++)
     {
       const float w = valid[sp] ? expf(-args.lambda_inv * (cost[sp * D + d] - beta_b)) : 0.0f;
-      w_s[d * bx + row[sp]] = w;
+      if (owner)
+        w_s[d * bx + row[sp]] = w;
       wsum += w;
       w2sum += w * w;
     }

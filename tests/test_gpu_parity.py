@@ -460,6 +460,35 @@ def test_autorally_mma_and_ffma2_paths_agree():
     e.close()
 
 
+@pytest.mark.parametrize("pspw", [16, 32])
+@pytest.mark.parametrize("N,T", [(4096, 100), (1000, 37), (224 * 3 + 5, 64)])
+def test_autorally_warp_specialised_equals_generic(N, T, pspw, monkeypatch):
+    """The default K1 of the Autorally pair (rollout_kernel_ar_ws.cuh: producer warps run the network recurrence in mma
+    fragment layout, consumer warps the kinematics and the cost) performs, per sample, the operations of the generic
+    one-thread-per-sample kernel in the same order: the written-back controls must agree bit for bit and the costs to the
+    last ulp or two (4 of 4096 costs differ by one ulp on B200), and with the same block width so must U. Ragged sizes and a T whose T*C is not a multiple of 4
+    (plain-load staging, a one-step last group) included."""
+    monkeypatch.setenv("MPPIB_BX", "64")
+    monkeypatch.setenv("MPPIB_WS_PSPW", str(pspw))  # samples per producer warp: 16 (default, two producers per group) or 32
+    w = W.autorally(N, T)
+    a = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    b = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS | H.FLAG_NO_WARP_SPEC)
+    # 32 / pspw producer warps and one consumer warp per 32 samples
+    assert a.launch_info()["block"] == (32 // pspw + 1) * b.launch_info()["block"] == (32 // pspw + 1) * 64
+    Ua, sa = a.solve(w.x0, w.U0)
+    Ub, sb = b.solve(w.x0, w.U0)
+    np.testing.assert_array_equal(a.get_noise(), b.get_noise())
+    np.testing.assert_array_equal(a.get_samples(), b.get_samples())  # constrained controls: identical bits
+    ca, cb = a.get_costs(), b.get_costs()
+    rel = np.abs(ca - cb) / np.maximum(np.abs(cb), 1.0)
+    # identical operations per sample; the two kernels' FMA contraction of the cost expressions may differ by an ulp
+    assert rel.max() < 1e-6 and np.mean(ca != cb) < 0.01, (rel.max(), np.mean(ca != cb))
+    np.testing.assert_allclose(Ua, Ub, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(np.asarray(sa), np.asarray(sb), rtol=1e-6)
+    a.close()
+    b.close()
+
+
 # ---- K2 + whole solve properties at BASELINE sizes -----------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cartpole", "double_integrator_tube", "autorally"])
 def test_full_size_size_independent_properties(name):
