@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload autorally|cartpole|double_integrator_tube]
     python bench.py --impl reference ...      # the reference's CPU step() loop (oracle port) on the host cores
+    python bench.py --all-configs             # one JSON line per BASELINE config C2..C5 (the last line is the headline C4)
 
 A "step" is one optimisation iteration of Controller::computeControl (noise draw -> N x T rollout -> baseline /
 exp-weights -> weighted control average) on synthetic inputs. Default workload = the configuration the
@@ -16,11 +17,19 @@ Reported numbers
             inputs -> device, result -> host every step (what Controller::computeControl does).
   roofline  K1 (fused rollout kernel): algorithmic bytes (N_local*T*C*4, one read of the noise buffer) / its average
             duration from CUDA events in a separate pass of the same process with L2 flushed between K0 and K1.
-  cpu_baseline  the oracle (CPU port of the reference's launchCPURolloutKernel + host weight code) on the host cores.
+  cpu_baseline  the oracle (CPU port of the reference's launchCPURolloutKernel + host weight code) on the host cores
+            (persistent worker pool, one pinned thread per core).
+  reference_gpu  the UNMODIFIED reference GPU build (oracle/_ref/libmppi_ref_gpu.so: the reference's VanillaMPPIController
+            and kernels compiled for sm_100 with an Eigen stand-in, "reference kernels, shimmed host") timed on the same
+            box for C2 / C4: computeControl Hz with steady_clock around the host call, best of a few rollout block shapes.
+  parity_ok (N > 1) the sharded solve against a single-GPU solve of the same seed, checked inside the warm-up.
+The timed regions always cover >= 100 ms of work: `steps` solves are repeated `inner_repeats` times back to back and the
+per-solve mean is reported (a 20-step run of a 0.2 ms solve would otherwise be a 4 ms measurement).
 """
 import argparse
 import ctypes
 import json
+import math
 import os
 import sys
 import threading
@@ -101,17 +110,6 @@ def _workload(args):
     return W.by_name(args.workload, args.rollouts, args.timesteps)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE K1 launch from the `ncu --set full` captures summarised under
-# profiles/ (r01_final_autorally_k1_mma_kernels.csv, r01_final_racer_kernels.csv, r01_cartpole_v4_kernels.csv,
-# r01_double_integrator_tube_v4_kernels.csv) — only valid for the exact single-GPU configuration that was captured.
-_NCU_K1_TRAFFIC_BYTES = {
-    "autorally_nn_N32768_T100": 26_280_960,                      # mma.sync K1 (r01_final_autorally_k1_mma_kernels.csv); algorithmic 26_214_400
-    "cartpole_vanilla_N8192_T100": 3_308_544,                    # algorithmic 3_276_800
-    "double_integrator_tube_N16384_T150": 19_710_208,            # algorithmic 19_660_800
-    "racer_lstm_H4_colored_N65536_T150": 128_668_928 + 54_798_592,  # streaming K1: eps read + controls written + re-read
-}
-
-
 def _k1_variant(w):
     """Which form of the Autorally network K1 ran with (engine.cu: default mma.sync, env / flag overrides)."""
     if type(w.dyn).__name__ != "NeuralNetModel":
@@ -121,11 +119,7 @@ def _k1_variant(w):
     if os.environ.get("MPPIB_NN_FFMA2"):
         return {"nn_form": "FP32 FFMA2 from shared memory"}
     return {"nn_form": "mma.sync m16n8k16, FP16 hi/lo operands in three products, FP32 accumulate (FP32-equivalent: "
-                       "5.1e-7 max error against FP64, tools/mma_probe.cu); state, cost and reductions in FP32"}
-
-
-def _ncu_traffic(w, world):
-    return _NCU_K1_TRAFFIC_BYTES.get(w.name) if world == 1 else None
+                       "4e-7 max error against FP64, tests/test_nn_mma_scheme.py); state, cost and reductions in FP32"}
 
 
 def _oracle_prepare(w):
@@ -192,7 +186,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "num_rollouts": w.N, "num_timesteps": w.T, "controller": w.controller},
+        "config": _base_config(w),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -200,23 +194,62 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_engine(args):
+def _base_config(w):
+    """The keys both arms (--impl ours / reference) print under `config`, so that the driver's same-config check passes."""
+    return {"workload": w.name, "num_rollouts": w.N, "num_timesteps": w.T, "controller": w.controller}
+
+
+_REF_GPU_CHILD = r'''
+import json, sys
+sys.path.insert(0, sys.argv[3])
+from mppi_generic_b200 import workloads as W
+from oracle import ref_gpu as RG
+name, b = sys.argv[1], tuple(int(v) for v in sys.argv[2].split(","))
+w = W.by_name(name)
+r = (RG.cartpole if name == "cartpole" else RG.autorally)(w, 42, block=b)
+s = r.time_compute_control(w.x0[0], 1, warmup=5, iters=int(sys.argv[4]))
+print("RESULT " + json.dumps({"block": list(b), "kernel": r.kernel_choice(), "ms": s * 1e3, "hz": 1.0 / s}))
+'''
+# rollout block shapes tried for the reference (dynamics x, y[, cost x, y]); the reference itself then picks its single or
+# split rollout kernel by timing both. Each shape runs in its own process: the reference exit()s on a shape it rejects.
+_REF_GPU_SHAPES = {"cartpole": ["64,4", "32,4", "64,1"], "autorally": ["64,8", "32,8", "64,4", "32,16"]}
+
+
+def _reference_gpu(w):
+    """computeControl Hz of the unmodified reference GPU build on this box (see the module docstring), or the reason it is
+    not reported."""
+    import subprocess
+    from mppi_generic_b200 import workloads as W
+    from oracle import ref_gpu as RG
+    name = {"cartpole_vanilla_N8192_T100": "cartpole", "autorally_nn_N32768_T100": "autorally"}.get(w.name)
+    if name is None:
+        return {"unavailable": "the harness instantiates the reference for C2 (cartpole 8192 x 100) and C4 (autorally 32768 x 100) only"}
+    if not RG.available():
+        return {"unavailable": "oracle/_ref/libmppi_ref_gpu.so not built (oracle/ref_build/build.sh needs /root/reference)"}
+    rows = []
+    for b in _REF_GPU_SHAPES[name]:
+        try:
+            p = subprocess.run([sys.executable, "-c", _REF_GPU_CHILD, name, b, ROOT, "200" if name == "cartpole" else "40"],
+                               capture_output=True, text=True, timeout=240)
+            res = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            rows.append(json.loads(res[0][7:]) if res else {"block": b, "error": (p.stdout + p.stderr)[-160:]})
+        except Exception as ex:  # noqa: BLE001
+            rows.append({"block": b, "error": str(ex)[:160]})
+    ok = [r for r in rows if "hz" in r]
+    if not ok:
+        return {"unavailable": "every block shape failed", "tried": rows}
+    best = max(ok, key=lambda r: r["hz"])
+    return {"value": best["hz"], "unit": UNIT, "ms_per_call": best["ms"], "block": best["block"], "kernel": best["kernel"],
+            "label": "reference kernels, shimmed host (unmodified /root/reference sources, Eigen stand-in, no-op feedback "
+                     "controller), computeControl timed with steady_clock around the host call",
+            "tried": rows}
+
+
+def run_engine(args, ctx):
     import torch
     import mppi_generic_b200 as m
     H = m.host
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist, world, rank, local_rank = ctx
 
     w = _workload(args)
     # a real (non-default) stream: the legacy default stream has handle 0, which the C-ABI reads as "engine-owned", and
@@ -245,19 +278,53 @@ def run_engine(args):
     U_out = np.empty_like(U)
     stats = (H.SolveStats * w.D)()
 
-    # ---- warm-up ---------------------------------------------------------------------------------------------------
+    # ---- multi-GPU parity, inside the warm-up: the sharded solve against a single-GPU solve of the same seed ------------
+    parity = None
+    if world > 1:
+        e1 = H.Engine(w.dyn, w.cost, w.sampler, w.N, w.T, w.D, device=local_rank, flags=0, stream=stream.cuda_stream)
+        e1.set_solver(w.dt, w.lambda_, w.alpha)
+        e1.seed(w.seed, 0)
+        U1, st1 = e1.solve(x0, U, w.optimization_stride, 0)
+        e1.close()
+        Us, sts = e.solve(x0, U, w.optimization_stride, 0)
+        scale = max(1.0, float(np.abs(U1).max()))
+        du = float(np.abs(Us - U1).max())
+        ok = du <= 2e-5 * scale
+        for d in range(w.D):
+            ok = ok and sts[d][0] == st1[d][0] and abs(sts[d][1] - st1[d][1]) <= 1e-5 * abs(st1[d][1])
+        t = torch.tensor([1.0 if ok else 0.0, du], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.MAX)
+        parity = {"parity_ok": bool(t[0].item() == 1.0), "max_abs_dU_vs_single_gpu": float(t[1].item()),
+                  "check": "sharded solve == single-GPU solve of the same seed: baseline identical, normaliser 1e-5, "
+                           "U 2e-5 of the control scale, on every rank"}
+        e.seed(w.seed, 0)
+
+    # ---- warm-up + per-solve estimate (sizes the timed regions to >= 100 ms) ------------------------------------------
     for _ in range(max(args.warmup, 3)):
         e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
     barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        e.solve_async(x0, U, w.optimization_stride, 0)
+    e.solve_wait()
+    torch.cuda.synchronize()
+    est = (time.perf_counter() - t0) / 10
+    inner = max(1, int(math.ceil(0.1 / max(args.steps * est, 1e-9))))
+    if dist is not None:
+        ti = torch.tensor([inner], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        inner = int(ti.item())
+    n_timed = args.steps * inner
 
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    # ---- value: K solves enqueued back to back, inputs resident (kernel parameter bank), device-timed -----------------
+    # ---- value: solves enqueued back to back, inputs resident (kernel parameter bank), device-timed ---------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(n_timed):
         e.solve_async(x0, U, w.optimization_stride, 0)
     ev1.record(stream)
     e.solve_wait()
@@ -305,7 +372,7 @@ def run_engine(args):
     barrier()
     ev0.record(stream)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_timed):
         compute_control()
     ev1.record(stream)
     torch.cuda.synchronize()
@@ -315,7 +382,7 @@ def run_engine(args):
     # the same loop without the host tail (C-ABI solve only), reported next to it
     U[...] = w.U0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(n_timed):
         e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
         U[...] = U_out
     torch.cuda.synchronize()
@@ -348,17 +415,22 @@ def run_engine(args):
     bytes_per_launch = e.n_local * w.T * w.dyn.CONTROL_DIM * 4
     achieved = bytes_per_launch / (t_cold["rollout_ms"] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "rollout_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": _ncu_traffic(w, world), "peak_source": peak_src,
+        "bound": "hbm", "kernel": "rollout kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None,
+        "traffic_note": "not measured in this run (no profiler attached); the ncu captures of this kernel are summarised "
+                        "under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_l2_flushed": t_cold["rollout_ms"],
         "kernel_ms_l2_warm": t_warm["rollout_ms"],
         "stage_ms_l2_warm": {k: t_warm[k] for k in ("noise_ms", "rollout_ms", "reduce_ms", "total_ms")},
         "note": "K1 is bound by the T-step dependency chain (and MUFU / tensor-pipe work for NN dynamics), not by HBM: see DESIGN.md",
     }
+    n_local = e.n_local
+    e.close()
 
     if rank == 0:
-        value = args.steps / (dev_ms * 1e-3)
-        e2e_value = args.steps / (e2e_ms * 1e-3)
+        value = n_timed / (dev_ms * 1e-3)
+        e2e_value = n_timed / (e2e_ms * 1e-3)
         h2d = (x0.nbytes + U.nbytes)
         d2h = w.D * (w.T * w.dyn.CONTROL_DIM + 4) * 4
         cpu = None
@@ -368,29 +440,52 @@ def run_engine(args):
             cpu = {"value": hz, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / n_timed, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "num_rollouts": w.N, "num_timesteps": w.T, "controller": w.controller,
-                       "parallelism": f"rollout-sharded dp{world}", "rollouts_per_gpu": e.n_local,
-                       "k1_launch": info,
+            "config": _base_config(w),
+            "engine": {"parallelism": f"rollout-sharded dp{world}", "rollouts_per_gpu": n_local, "k1_launch": info,
+                       "inner_repeats": inner, "timed_solves": n_timed, "timed_ms": dev_ms,
                        **_k1_variant(w),
-                       "l2": "noise buffer is regenerated on the device every step (K0 -> K1 through L2/HBM); no data "
-                             "is reused across steps; the roofline pass flushes L2 (256 MiB memset) between K0 and K1"},
+                       "l2": "noise buffer is regenerated on the device every solve (K0 -> K1 through L2/HBM); no data "
+                             "is reused across solves; the roofline pass flushes L2 (256 MiB memset) between K0 and K1"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step": e2e_ms / n_timed,
                     "includes": "blocking mppib_solve (host x0/U in, U/stats out) + host tail: SG smoothing and nominal "
                                 "state/output roll-forward (T host step() calls)",
-                    "solve_only_value": args.steps / (solve_only_ms * 1e-3)},
-            "gpu_launches": args.steps * info["kernels_per_solve"],
+                    "solve_only_value": n_timed / (solve_only_ms * 1e-3)},
+            "gpu_launches": n_timed * info["kernels_per_solve"],
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if parity is not None:
+            line.update(parity)
+        if world == 1 and not args.no_reference_gpu:
+            rg = _reference_gpu(w)
+            line["reference_gpu"] = rg
+            if "value" in rg:
+                line["vs_reference_gpu"] = {"e2e_ratio": e2e_value / rg["value"], "value_ratio": value / rg["value"],
+                                            "note": "north_star target: >= 10x the reference GPU build's computeControl Hz (C4)"}
         print(json.dumps(line), flush=True)
-    e.close()
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
+
+
+def _setup():
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return dist, world, rank, local_rank
 
 
 def main():
@@ -403,11 +498,23 @@ def main():
     ap.add_argument("--rollouts", type=int, default=None)
     ap.add_argument("--timesteps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--all-configs", action="store_true",
+                    help="one JSON line per BASELINE config: C2 cartpole, C3 double_integrator_tube, C5 racer_lstm, then C4 "
+                         "autorally (the headline, last)")
     args = ap.parse_args()
+    workloads = ["cartpole", "double_integrator_tube", "racer_lstm", "autorally"] if args.all_configs else [args.workload]
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_engine(args)
+        for wl in workloads:
+            args.workload = wl
+            run_reference(args)
+        return
+    ctx = _setup()
+    for wl in workloads:
+        args.workload = wl
+        run_engine(args, ctx)
+    if ctx[0] is not None:
+        ctx[0].destroy_process_group()
 
 
 if __name__ == "__main__":

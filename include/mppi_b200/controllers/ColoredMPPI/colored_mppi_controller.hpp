@@ -40,6 +40,19 @@ public:
   {
     this->chooseAppropriateKernel();
   }
+  // colored_mppi_controller.cuh: the PARAMS_T constructor (gamma, r and the leash travel in the parameter struct)
+  ColoredMPPIController(DYN_T* model, COST_T* cost, FB_T* fb_controller, SAMPLING_T* sampler, PARAMS_T& params,
+                        cudaStream_t stream = nullptr)
+    : PARENT_CLASS(model, cost, fb_controller, sampler, params, stream)
+  {
+    pushWeighting();
+    this->chooseAppropriateKernel();
+  }
+  void setParams(const PARAMS_T& p)
+  {
+    PARENT_CLASS::setParams(p);
+    pushWeighting();
+  }
   std::string getControllerName() override
   {
     return "Colored MPPI";
@@ -106,13 +119,11 @@ public:
     this->free_energy_statistics_.real_sys.previousBaseline = this->getBaselineCost();
     state_array local_state = state;
     if (getLeashActive())
-    {  // Dynamics::enforceLeash (dynamics.cuh:448-466) against the planned state leash_jump_ steps ahead
-      for (int i = 0; i < DYN_T::STATE_DIM; i++)
-      {
-        const float nominal = this->state_(i, leash_jump_), leash = this->params_.state_leash_dist_[i];
-        const float diff = fabsf(nominal - state(i));
-        local_state(i) = (leash < diff) ? state(i) + fminf(fmaxf(nominal - state(i), -leash), leash) : nominal;
-      }
+    {  // the model's own enforceLeash (dynamics.cuh:448-466, RacerDubins: racer_dubins.cu:177-230) against the planned state
+       // leash_jump_ steps ahead (colored_mppi_controller.cu:150-153)
+      state_array nominal = this->state_.col(leash_jump_);
+      state_array leash = this->params_.state_leash_dist_;
+      this->model_->enforceLeash(state, nominal, leash, local_state);
     }
     control_trajectory u_nominal = this->control_;
     for (int opt_iter = 0; opt_iter < this->getNumIters(); opt_iter++)
@@ -139,6 +150,15 @@ public:
     leash_jump_ = steps;
     this->saveControlHistoryHelper(steps, this->control_, this->control_history_);
     this->slideControlSequenceHelper(steps, this->control_);
+  }
+
+protected:
+  // a re-created engine (new horizon, stream or write-back flag) starts with the exponential weights: give it ours again
+  void onEngineCreated() override
+  {
+    const bool tsallis = this->params_.gamma != 0 && this->params_.r != 0;
+    if (tsallis && (this->extra_flags_ & MPPIB_FLAG_WRITEBACK_CONTROLS))
+      MPPIB_HANDLE(mppib_set_tsallis(this->engine_, this->params_.gamma, this->params_.r));
   }
 
 private:

@@ -212,6 +212,12 @@ public:
   {  // robust_mppi_controller.cuh:186-190: done inside updateImportanceSamplingControl
   }
 
+protected:
+  void onEngineCreated() override
+  {  // a re-created engine has lost the value-function threshold and the feedback gains
+    pushRMPPI();
+  }
+
 private:
   void pushRMPPI()
   {

@@ -562,10 +562,20 @@ protected:
       baseline_[d] = normalizer_[d] = 0.0f;
     createEngine();
   }
+  // engine state that lives outside the parameter blobs (Tsallis weights, RMPPI gains / threshold): derived controllers
+  // re-apply it here. Not reached from the base constructor (virtual dispatch), where they apply it themselves.
+  virtual void onEngineCreated()
+  {
+  }
   void createEngine()
   {
+    // a re-created engine must continue the noise stream where the old one stood (the reference keeps its generator across
+    // setNumTimesteps / setCUDAStream), not restart it at offset 0
+    unsigned long long rng_offset = 0ULL;
+    const bool recreated = engine_ != nullptr;
     if (engine_)
     {
+      MPPIB_HANDLE(mppib_get_rng_offset(engine_, &rng_offset));
       mppib_destroy(engine_);
       engine_ = nullptr;
     }
@@ -584,7 +594,10 @@ protected:
     model_->fillModelDims(d.model_dims);
     MPPIB_HANDLE(mppib_create(&engine_, &d));
     pushParams();
-    MPPIB_HANDLE(mppib_seed(engine_, params_.seed_, 0ULL));  // createAndSeedCUDARandomNumberGen (controller.cu:192-198)
+    // createAndSeedCUDARandomNumberGen (controller.cu:192-198) for a new controller; the old position for a re-creation
+    MPPIB_HANDLE(mppib_seed(engine_, params_.seed_, recreated ? rng_offset : 0ULL));
+    if (recreated)
+      onEngineCreated();
   }
   template <class C>
   auto pushCostmap(C* c) -> decltype(c->costmapBytes(), void())

@@ -6,6 +6,7 @@
  * blob blob(). Host methods call the exported CPU twins (host_twins.h) so the arithmetic exists once.
  */
 #pragma once
+#include <cmath>
 #include <array>
 #include <cfloat>
 #include <string>
@@ -158,6 +159,20 @@ public:
   virtual std::string getDynamicsModelName() const
   {
     return "Dynamics model name not set";
+  }
+  // dynamics.cuh:448-466: pull the planner's initial state towards the true one, component by component; models whose
+  // states are not all Euclidean override it (RacerDubins: racer_dubins.cu:177-230)
+  virtual void enforceLeash(const Eigen::Ref<const state_array>& state_true, const Eigen::Ref<const state_array>& state_nominal,
+                            const Eigen::Ref<const state_array>& leash_values, Eigen::Ref<state_array> state_output)
+  {
+    for (int i = 0; i < S_DIM; i++)
+    {
+      const float diff = fabsf(state_nominal(i) - state_true(i));
+      if (leash_values(i) < diff)
+        state_output(i) = state_true(i) + fminf(fmaxf(state_nominal(i) - state_true(i), -leash_values(i)), leash_values(i));
+      else
+        state_output(i) = state_nominal(i);
+    }
   }
 };
 }  // namespace MPPI_internal

@@ -99,6 +99,42 @@ public:
   {
     return true;  // lstm_steering.cu:15
   }
+  // RacerDubinsImpl::enforceLeash (racer_dubins.cu:177-230): positions are leashed in the body frame of the true state, yaw
+  // by its shortest angular distance (and re-normalised), every other state component-wise; starts from state_true
+  void enforceLeash(const Eigen::Ref<const state_array>& state_true, const Eigen::Ref<const state_array>& state_nominal,
+                    const Eigen::Ref<const state_array>& leash_values, Eigen::Ref<state_array> state_output) override
+  {
+    typedef RacerDubinsElevationParams::StateIndex SI;
+    const int PX = (int)SI::POS_X, PY = (int)SI::POS_Y, YW = (int)SI::YAW;
+    auto normalize = [](float a) {  // angle_utils.cuh:20-26
+      const float pi = 3.14159265358979323846f;
+      const float r = fmodf(a + pi, 2.0f * pi);
+      return r <= 0.0f ? r + pi : r - pi;
+    };
+    for (int i = 0; i < STATE_DIM; i++)
+      state_output(i) = state_true(i);
+    float dx = state_nominal(PX) - state_true(PX), dy = state_nominal(PY) - state_true(PY);
+    const float cy = cosf(state_true(YW)), sy = sinf(state_true(YW));
+    float dx_body = dx * cy + dy * sy, dy_body = -dx * sy + dy * cy;
+    dx_body = fminf(fmaxf(dx_body, -leash_values(PX)), leash_values(PX));
+    dy_body = fminf(fmaxf(dy_body, -leash_values(PY)), leash_values(PY));
+    state_output(PX) += dx_body * cy + -dy_body * sy;
+    state_output(PY) += dx_body * sy + dy_body * cy;
+    for (int i = 0; i < STATE_DIM; i++)
+    {
+      if (i == PX || i == PY)
+        continue;
+      const float diff = (i == YW) ? normalize(state_nominal(i) - state_true(i)) : state_nominal(i) - state_true(i);
+      if (leash_values(i) < fabsf(diff))
+      {
+        state_output(i) = state_true(i) + fminf(fmaxf(diff, -leash_values(i)), leash_values(i));
+        if (i == YW)
+          state_output(i) = normalize(state_output(i));
+      }
+      else
+        state_output(i) = state_nominal(i);
+    }
+  }
   int lstmBlock() const
   {
     return 4 * hidden_dim_ * hidden_dim_ + 4 * hidden_dim_ * MPPIB_RACER_LSTM_INPUT_DIM + 6 * hidden_dim_;

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(512)
                           float* __restrict__ out2)  // optional mapped host copy
 {
   __shared__ float acc_sh[16][32];
-  __shared__ double eta_sh[16];
+  __shared__ double eta_sh[16], w2_sh[16];
   const int d = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(512)
   const float* u = controls + (size_t)d * n * TC;
   const float inv_rm1 = 1.0f / (r - 1.0f);
   float a = 0.0f;
-  double eta = 0.0;
+  double eta = 0.0, w2 = 0.0;
   for (int i = warp; i < n; i += 16)
   {
     const float cost_dif = c[i] - beta;
@@ -304,21 +304,26 @@ __global__ void __launch_bounds__(512)
     if (cost_dif < gamma)
       w = expf(logf(1.0f - cost_dif / gamma) * inv_rm1);
     eta += (double)w;
+    w2 += (double)w * (double)w;
     if (col < TC)
       a = fmaf(w, u[(size_t)i * TC + col], a);
   }
   acc_sh[warp][lane] = a;
   if (lane == 0)
+  {
     eta_sh[warp] = eta;
+    w2_sh[warp] = w2;
+  }
   __syncthreads();
   if (warp == 0)
   {
-    double e = 0.0;
+    double e = 0.0, e2 = 0.0;
     float s = 0.0f;
 #pragma unroll
     for (int g = 0; g < 16; g++)
     {
       e += eta_sh[g];
+      e2 += w2_sh[g];
       s += acc_sh[g][lane];
     }
     const float eta_f = (float)e;
@@ -335,10 +340,14 @@ __global__ void __launch_bounds__(512)
     if (blockIdx.x == 0 && lane == 0)
     {  // baseline stays; normaliser and sum of squares describe the Tsallis weights
       o[1] = eta_f;
+      o[2] = (float)e2;  // the free-energy statistics are taken over the Tsallis weights (mppi_common.cu:1065-1081)
+      o[3] = 0.0f;
       if (o2)
       {
         o2[0] = beta;
         o2[1] = eta_f;
+        o2[2] = (float)e2;
+        o2[3] = 0.0f;
       }
     }
   }

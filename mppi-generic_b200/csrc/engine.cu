@@ -150,6 +150,7 @@ struct mppib_engine
   volatile unsigned* done_flag_h = nullptr;
   unsigned* done_flag_dev = nullptr;
   unsigned solve_seq = 0;
+  bool flag_armed = false;  // the LAST enqueued solve ends in a kernel that publishes done_flag == solve_seq
   bool writeback = false;
   bool rmppi = false;  // MPPIB_FLAG_RMPPI
   float tsallis_gamma = 0.0f, tsallis_r = 0.0f;  // both non-zero: Tsallis weights (mppib_set_tsallis)
@@ -932,6 +933,7 @@ static int launch_combine_one(mppib_engine& e, const float* records, const float
   {
     flag = e.done_flag_dev;
     seq = ++e.solve_seq;
+    e.flag_armed = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -952,6 +954,9 @@ static int launch_combine_one(mppib_engine& e, const float* records, const float
 
 static int launch_combine(mppib_engine& e, bool after_k1)
 {
+  // only a final-stage K2 publishes the completion flag; the Tsallis reduction and the peer-memory exchange kernel end the
+  // solve without it, and wait_for_stream then falls back to cudaStreamSynchronize instead of trusting a stale flag
+  e.flag_armed = false;
   const bool pdl = after_k1 && e.use_pdl;
   float* host_copy = e.mapped_result ? e.result_h_dev : nullptr;
   if (e.tsallis_gamma != 0.0f && e.tsallis_r != 0.0f)
@@ -1637,6 +1642,10 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
   if (!e || !host)
     return fail(MPPIB_ERR_INVALID_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(e->desc.device));
+  // weights, the costmap texture and the LSTM blob are read by kernels of a solve still in flight (mppib_solve_async):
+  // replacing them under it would be a use-after-free
+  if (e->pending != 0 && (which == MPPIB_BLOB_NN_WEIGHTS || which == MPPIB_BLOB_LSTM_WEIGHTS || which == MPPIB_BLOB_COSTMAP))
+    return fail(MPPIB_ERR_STATE, "mppib_set_blob(%d) while a solve is pending: call mppib_solve_wait first", which);
   switch (which)
   {
     case MPPIB_BLOB_DYN_PARAMS:
@@ -2034,7 +2043,7 @@ static int enqueue_solve(mppib_engine* e, const float* x0, const float* U_in, in
 // stream is queried so that a failed launch cannot spin forever, and timing mode uses a full synchronize (events).
 static int wait_for_stream(mppib_engine* e)
 {
-  if (e->spin_wait && !e->timing && e->solve_seq != 0)
+  if (e->spin_wait && !e->timing && e->flag_armed && e->solve_seq != 0)
   {
     const unsigned want = e->solve_seq;
     for (unsigned spins = 1;; spins++)

@@ -289,6 +289,13 @@ class _Dynamics:
                                                   _ptr(_f32(x0)), _ptr(u), T, C.c_float(dt), _ptr(states),
                                                   _ptr(outputs)))
 
+    def enforceLeash(self, state_true, state_nominal, leash_values) -> np.ndarray:
+        """Dynamics::enforceLeash (dynamics.cuh:448-466): component-wise pull of the planner's initial state towards the
+        true one. Models with non-Euclidean states override it (RacerDubins)."""
+        t, n, l = _f32(state_true), _f32(state_nominal), _f32(leash_values)
+        leashed = t + np.clip(n - t, -l, l)
+        return np.where(l < np.abs(n - t), leashed, n).astype(np.float32)
+
     # dynamics.cuh:163-175
     def setControlRanges(self, control_rngs: Sequence[Sequence[float]]):
         for i, (lo, hi) in enumerate(control_rngs):
@@ -433,6 +440,35 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
     buffer on the host (updateFromBuffer, :215-232) and is represented here by that state itself
     (``setInitialHiddenCell``). No elevation map: flat terrain."""
     DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_RACER_LSTM, 19, 2, 28
+
+    def enforceLeash(self, state_true, state_nominal, leash_values) -> np.ndarray:
+        """RacerDubinsImpl::enforceLeash (racer_dubins.cu:177-230): x / y leashed in the body frame of the true state, yaw by
+        its shortest angular distance (and re-normalised), the rest component-wise; starts from state_true."""
+        YAW, PX, PY = 1, 2, 3  # racer_dubins.cuh state indices: VEL_X, YAW, POS_X, POS_Y, ...
+        t, n, l = _f32(state_true), _f32(state_nominal), _f32(leash_values)
+        f32, pi = np.float32, np.float32(math.pi)
+
+        def normalize(a):  # angle_utils.cuh:20-26
+            r = np.fmod(f32(a + pi), f32(2.0) * pi)
+            return f32(r + pi) if r <= 0 else f32(r - pi)
+        out = t.copy()
+        dx, dy = n[PX] - t[PX], n[PY] - t[PY]
+        cy, sy = f32(math.cos(t[YAW])), f32(math.sin(t[YAW]))
+        dxb = np.clip(dx * cy + dy * sy, -l[PX], l[PX])
+        dyb = np.clip(-dx * sy + dy * cy, -l[PY], l[PY])
+        out[PX] += dxb * cy - dyb * sy
+        out[PY] += dxb * sy + dyb * cy
+        for i in range(self.STATE_DIM):
+            if i in (PX, PY):
+                continue
+            diff = normalize(n[i] - t[i]) if i == YAW else n[i] - t[i]
+            if l[i] < abs(diff):
+                out[i] = t[i] + np.clip(diff, -l[i], l[i])
+                if i == YAW:
+                    out[i] = normalize(out[i])
+            else:
+                out[i] = n[i]
+        return out.astype(np.float32)
 
     def __init__(self, init_input_dim: int = 3, init_hidden_dim: int = 20, init_output_layers: Sequence[int] = (23, 100, 8),
                  input_dim: int = 4, hidden_dim: int = 4, output_layers: Sequence[int] = (8, 20, 1), init_len: int = 11):
@@ -1289,11 +1325,8 @@ class ColoredMPPIController(VanillaMPPIController):
 
     def computeControl(self, state, optimization_stride: int = 1) -> None:
         state = _f32(state).copy()
-        if self.leash_active_:  # Dynamics::enforceLeash, dynamics.cuh:448-466
-            nominal = self.state_[self.leash_jump_]
-            diff = np.abs(nominal - state)
-            leashed = state + np.clip(nominal - state, -self.state_leash_dist_, self.state_leash_dist_)
-            state = np.where(self.state_leash_dist_ < diff, leashed, nominal).astype(np.float32)
+        if self.leash_active_:  # the model's own enforceLeash (colored_mppi_controller.cu:150-153)
+            state = self.model_.enforceLeash(state, self.state_[self.leash_jump_], self.state_leash_dist_)
         super().computeControl(state, optimization_stride)
         if self.model_.CONTROL_DIM > 1:  # colored_mppi_controller.cu:232-238
             lo, hi = self.model_.params.lim.rng_lo[1], self.model_.params.lim.rng_hi[1]

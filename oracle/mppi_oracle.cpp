@@ -18,6 +18,11 @@
  * Build: make -C oracle   (g++ -O2, no -ffast-math, -ffp-contract=off so products are rounded like the Eigen host
  * code compiled without FMA contraction).
  */
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <pthread.h>
+#include <sched.h>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -899,6 +904,100 @@ static void sampledTrajectory(const void* dpv, const void* cpv, const mppib_gaus
   costs[T] = COST::terminalCost(cp, aux, y) / T;
 }
 
+// ---- persistent worker pool -----------------------------------------------------------------------------------------
+// The CPU arm of the bench times back-to-back solves; spawning and joining ~128 std::threads per solve, unpinned, made that
+// number swing 4x between boxes (round-1 verdict). The workers below are created once, pinned one per core
+// (pthread_setaffinity_np), and woken per parallel region; chunk i of a region always runs on worker i.
+namespace
+{
+class WorkerPool
+{
+public:
+  explicit WorkerPool(int n) : n_(n), gen_(0), pending_(0), stop_(false)
+  {
+    const int ncpu = (int)std::max(1u, std::thread::hardware_concurrency());
+    for (int i = 0; i < n_; i++)
+    {
+      th_.emplace_back([this, i]() { loop(i); });
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      CPU_SET(i % ncpu, &set);
+      pthread_setaffinity_np(th_.back().native_handle(), sizeof(set), &set);
+    }
+  }
+  ~WorkerPool()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& t : th_)
+      t.join();
+  }
+  int size() const
+  {
+    return n_;
+  }
+  void run(const std::function<void(int)>& fn)
+  {
+    std::unique_lock<std::mutex> lk(m_);
+    fn_ = &fn;
+    pending_ = n_;
+    gen_++;
+    cv_.notify_all();
+    done_.wait(lk, [this]() { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+private:
+  void loop(int i)
+  {
+    unsigned long seen = 0;
+    for (;;)
+    {
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&]() { return gen_ != seen; });
+        seen = gen_;
+        if (stop_)
+          return;
+        fn = fn_;
+      }
+      (*fn)(i);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0)
+          done_.notify_one();
+      }
+    }
+  }
+  int n_;
+  unsigned long gen_;
+  int pending_;
+  bool stop_;
+  const std::function<void(int)>* fn_ = nullptr;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> th_;
+};
+// fn(chunk, nchunks) for chunk = 0 .. nthreads-1 on the pool (re-created when a different width is asked for)
+static void parallel_chunks(int nthreads, const std::function<void(int)>& fn)
+{
+  static std::mutex guard;
+  static WorkerPool* pool = nullptr;
+  std::lock_guard<std::mutex> lk(guard);
+  if (pool == nullptr || pool->size() != nthreads)
+  {
+    delete pool;
+    pool = new WorkerPool(nthreads);
+  }
+  pool->run(fn);
+}
+}  // namespace
+
 template <class DYN, class COST>
 static void rollout(const void* dp, const void* cp, const mppib_gaussian_params& sp, const Aux& aux, int N, int T,
                     int D, float dt, float lambda, float alpha, const float* x0, const float* means, float* samples,
@@ -911,16 +1010,10 @@ static void rollout(const void* dp, const void* cp, const mppib_gaussian_params&
     rollout_range<DYN, COST>(d, c, sp, aux, N, T, D, dt, lambda, alpha, x0, means, samples, costs, 0, N);
     return;
   }
-  std::vector<std::thread> th;
-  for (int i = 0; i < nthreads; i++)
-  {
+  parallel_chunks(nthreads, [=, &d, &c, &sp, &aux](int i) {
     int b = (int)((long long)N * i / nthreads), e = (int)((long long)N * (i + 1) / nthreads);
-    th.emplace_back([=, &d, &c, &sp, &aux]() {
-      rollout_range<DYN, COST>(d, c, sp, aux, N, T, D, dt, lambda, alpha, x0, means, samples, costs, b, e);
-    });
-  }
-  for (auto& t : th)
-    t.join();
+    rollout_range<DYN, COST>(d, c, sp, aux, N, T, D, dt, lambda, alpha, x0, means, samples, costs, b, e);
+  });
 }
 
 typedef void (*rollout_fn)(const void*, const void*, const mppib_gaussian_params&, const Aux&, int, int, int, float,

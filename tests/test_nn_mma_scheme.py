@@ -1,9 +1,10 @@
-"""CPU pin of the arithmetic scheme of csrc/plugins/nn_mma.cuh (the Autorally network on mma.sync): FP16 hi / lo operands,
-three products, FP32 accumulation — emulated with numpy float16 / float32, on the synthetic 6-32-32-4 network, against
-float64. Two things are pinned: (1) the fragment bookkeeping (which lane register holds which matrix element, how a C
+"""CPU pin of the arithmetic scheme of csrc/plugins/nn_mma.cuh (the Autorally network on mma.sync): FP16 hi / lo operands
+(unscaled residual), three products in one FP32 accumulator, activations handed on as r = 1 / (exp2(z) + 1) with the affine
+map of tanh folded into the consuming layer's weights — emulated with numpy float16 / float32, on the synthetic 6-32-32-4
+network, against float64. Two things are pinned: (1) the fragment bookkeeping (which lane register holds which matrix element, how a C
 fragment becomes the next layer's A fragment, the weight-fragment order of load_weights) reproduces the plain matrix
 products exactly; (2) the split reaches FP32-class accuracy where a single FP16 product does not (the reason for it).
-The device numbers (5.1e-7 max error, tools/mma_probe.cu) are measured on the GPU; this file needs none."""
+The device itself is checked against the oracle and the FFMA2 form in tests/test_gpu_parity.py; this file needs no GPU."""
 import numpy as np
 
 from mppi_generic_b200 import workloads as W
@@ -76,18 +77,37 @@ def test_fragment_bookkeeping_reproduces_the_matrix_products():
 
 
 def _split(v):
+    """split2 of nn_mma.cuh: hi = half(v), lo = half(v - hi) — the residual is NOT rescaled; below 2^-14 it is an FP16
+    subnormal (numpy's float16 keeps subnormals like the tensor cores do)."""
     hi = v.astype(np.float16)
-    lo = ((v - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float16)
     return hi.astype(np.float32), lo.astype(np.float32)
 
 
 def _layer_split(a, Wm, b):
-    """hi*hi + (lo*hi + hi*lo) / 2048 with FP32 accumulators, bias in the hi*hi accumulator (activate() folds x in)."""
+    """bias + hi*hi + lo*hi + hi*lo, all in ONE FP32 accumulator (forward_frag: the accumulator starts at the bias)."""
     ah, al = _split(a.astype(np.float32))
     wh, wl = _split(Wm.astype(np.float32))
-    c = (ah @ wh.T).astype(np.float32) + b.astype(np.float32)
-    x = (al @ wh.T).astype(np.float32) + (ah @ wl.T).astype(np.float32)
-    return x * np.float32(1.0 / 2048.0) + c
+    c = b.astype(np.float32) + (ah @ wh.T).astype(np.float32)
+    c = (c + (al @ wh.T).astype(np.float32)).astype(np.float32)
+    return (c + (ah @ wl.T).astype(np.float32)).astype(np.float32)
+
+
+def _sigmoid_pre(z):
+    """sigmoid2_prescaled: r = 1 / (exp2(z) + 1); tanh(x) = 1 - 2 r with z = 2 log2(e) x."""
+    return np.float32(1.0) / (np.exp2(z).astype(np.float32) + np.float32(1.0))
+
+
+def _folded(theta):
+    """load_weights: layers feeding a tanh carry kTanhScale; layers consuming r = (1 - tanh) / 2 carry W' = -2 W and
+    b' = b + row sum of W (taken in double, rounded once)."""
+    W1, b1 = theta[:192].reshape(32, 6), theta[192:224]
+    W2, b2 = theta[224:1248].reshape(32, 32), theta[1248:1280]
+    W3, b3 = theta[1280:1408].reshape(4, 32), theta[1408:1412]
+    f32 = np.float32
+    return ((W1 * SC).astype(f32), (b1 * SC).astype(f32),
+            (W2.astype(f32) * f32(-2.0 * SC)).astype(f32), ((b2 + W2.sum(1)).astype(f32) * f32(SC)).astype(f32),
+            (W3.astype(f32) * f32(-2.0)).astype(f32), (b3 + W3.sum(1)).astype(f32))
 
 
 def test_three_product_fp16_split_reaches_fp32_class_accuracy():
@@ -96,19 +116,45 @@ def test_three_product_fp16_split_reaches_fp32_class_accuracy():
     W2, b2 = theta[224:1248].reshape(32, 32), theta[1248:1280]
     W3, b3 = theta[1280:1408].reshape(4, 32), theta[1408:1412]
     rng = np.random.RandomState(1)
-    x = (rng.randn(4096, 6) * [0.3, 3.0, 1.0, 1.0, 0.5, 0.5]).astype(np.float32)  # roll, vx, vy, yaw rate, steering, throttle
+    x = (rng.randn(16384, 6) * [0.3, 3.0, 1.0, 1.0, 0.5, 0.5]).astype(np.float32)  # roll, vx, vy, yaw rate, steering, throttle
     ref = np.tanh(np.tanh(x.astype(np.float64) @ W1.T + b1) @ W2.T + b2) @ W3.T + b3
-    tanh_pre = lambda z: np.float32(1.0) - np.float32(2.0) / (np.exp2(z).astype(np.float32) + np.float32(1.0))  # noqa: E731
-    h = tanh_pre(_layer_split(x, W1 * SC, b1 * SC))
-    q = tanh_pre(_layer_split(h, W2 * SC, b2 * SC))
-    out = _layer_split(q, W3, b3)
+    w1, c1, w2, c2, w3, c3 = _folded(theta)
+    r1 = _sigmoid_pre(_layer_split(x, w1, c1))
+    r2 = _sigmoid_pre(_layer_split(r1, w2, c2))
+    out = _layer_split(r2, w3, c3)
     err_split = np.abs(out - ref).max()
-    # the same network with ONE FP16 product per term (what a plain FP16 / TF32 MMA would do)
+    # the same network as plain FP32 FMA chains (what the reference's FNNHelper::forward computes)
+    f32 = np.float32
+
+    def chain(a, Wm, b):
+        acc = np.zeros((a.shape[0], Wm.shape[0]), f32)
+        for k in range(Wm.shape[1]):
+            acc = (acc + a[:, k:k + 1].astype(f32) * Wm[:, k].astype(f32)[None, :]).astype(f32)
+        return acc + b.astype(f32)
+    err_fp32 = np.abs(chain(np.tanh(chain(np.tanh(chain(x, W1, b1)), W2, b2)), W3, b3) - ref).max()
+    # and with ONE FP16 product per term (what a plain FP16 / TF32 MMA would do)
     f16 = lambda v: v.astype(np.float16).astype(np.float32)  # noqa: E731
     h1 = np.tanh((f16(x) @ f16(W1.astype(np.float32)).T) + b1.astype(np.float32))
     q1 = np.tanh((f16(h1) @ f16(W2.astype(np.float32)).T) + b2.astype(np.float32))
     out1 = (f16(q1) @ f16(W3.astype(np.float32)).T) + b3.astype(np.float32)
     err_single = np.abs(out1 - ref).max()
-    assert err_split < 1.5e-6, err_split      # FP32 class (device: 5.1e-7 on its own inputs)
-    assert err_single > 1e-4, err_single      # fails the 1e-4 parity bar of a 100-step recurrence on its own
+    assert err_split < 1.0e-6, err_split          # FP32 class: ~4e-7 here, plain FP32 chains ~2e-7
+    assert err_split < 4 * err_fp32 + 2e-7, (err_split, err_fp32)
+    assert err_single > 1e-4, err_single          # fails the 1e-4 parity bar of a 100-step recurrence on its own
     assert err_single > 100 * err_split
+
+
+def test_layer1_k16_concatenation_and_sigmoid_fold_are_exact_identities():
+    """Two bookkeeping identities of forward_frag, in exact arithmetic: (1) layer 1 as [a_hi | a_lo] x [w_hi ; w_hi] (one k16
+    MMA) + a_hi x w_lo (one k8 MMA) is a_hi w_hi + a_lo w_hi + a_hi w_lo; (2) feeding r = (1 - tanh) / 2 into W' = -2 W,
+    b' = b + sum W reproduces W tanh + b."""
+    rng = np.random.RandomState(3)
+    a_hi, a_lo = rng.randn(16, 8), rng.randn(16, 8) * 1e-4
+    w_hi, w_lo = rng.randn(8, 8), rng.randn(8, 8) * 1e-4   # [n][k]
+    A16 = np.concatenate([a_hi, a_lo], axis=1)               # [16][16]
+    B16 = np.concatenate([w_hi, w_hi], axis=1)               # [n][16]: k 0..7 and k 8..15 both multiply w_hi
+    got = A16 @ B16.T + a_hi @ w_lo.T
+    np.testing.assert_allclose(got, a_hi @ w_hi.T + a_lo @ w_hi.T + a_hi @ w_lo.T, rtol=0, atol=1e-12)
+    Wm, b, t = rng.randn(32, 32), rng.randn(32), np.tanh(rng.randn(16, 32))
+    r = (1.0 - t) / 2.0
+    np.testing.assert_allclose(r @ (-2.0 * Wm).T + (b + Wm.sum(1)), t @ Wm.T + b, rtol=0, atol=1e-12)

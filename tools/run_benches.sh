@@ -1,4 +1,4 @@
 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
 for wl in autorally cartpole double_integrator_tube racer_lstm; do
-python bench.py --workload $wl --steps 200 --warmup 20 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'solve_only', round(d['e2e']['solve_only_value'],1), d['roofline']['stage_ms_l2_warm'], d['config']['k1_launch']['grid'], d['config']['k1_launch']['block'])"
+python bench.py --workload $wl --steps 200 --warmup 20 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'solve_only', round(d['e2e']['solve_only_value'],1), d['roofline']['stage_ms_l2_warm'], d['engine']['k1_launch']['grid'], d['engine']['k1_launch']['block'])"
 done

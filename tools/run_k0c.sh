@@ -12,4 +12,4 @@ for r in rows[1:]:
     except: pass
 for k,v in d.items(): print(k, len(v), 'avg us', round(sum(v)/len(v)/1000,1) if max(v)>1000 else round(sum(v)/len(v),1))
 PY
-python bench.py --workload racer_lstm --steps 100 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('auto', d['config']['workload'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['roofline']['stage_ms_l2_warm'], d['config']['k1_launch'])"
+python bench.py --workload racer_lstm --steps 100 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('auto', d['config']['workload'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['roofline']['stage_ms_l2_warm'], d['engine']['k1_launch'])"
