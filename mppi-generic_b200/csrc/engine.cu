@@ -404,11 +404,15 @@ struct Pair
       {
         CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 1, true, 1, false, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 1, false, 1, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
         return MPPIB_OK;
       }
       if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
       {
         CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2, true, 1, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<DYN, COST, 2, false, 1, false, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
         return MPPIB_OK;
       }
@@ -470,6 +474,7 @@ struct Pair
     a.use_tma = e.use_tma ? 1 : 0;
     a.dyn_shared_floats = e.dyn_shared_floats;
     a.ring = e.stream_k1 ? e.ring : 0;
+    a.stream_readback = (e.stream_k1 && e.writeback && getenv("MPPIB_STREAM_READBACK")) ? 1 : 0;
     a.fb_gains = e.fb_gains_d;
     a.value_func_threshold = e.value_func_threshold;
     a.dt = e.dt;
@@ -516,9 +521,19 @@ struct Pair
     else if (e.stream_k1)
     {
       if (e.D == 1)
-        rollout_kernel<DYN, COST, 1, true, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+      {
+        if (e.writeback)
+          rollout_kernel<DYN, COST, 1, true, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+        else
+          rollout_kernel<DYN, COST, 1, false, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+      }
       else if constexpr (DYN::MAX_DISTRIBUTIONS >= 2)
-        rollout_kernel<DYN, COST, 2, true, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+      {
+        if (e.writeback)
+          rollout_kernel<DYN, COST, 2, true, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+        else
+          rollout_kernel<DYN, COST, 2, false, 1, false, true><<<e.grid, threads, e.smem_bytes, e.stream>>>(a, e.tmap);
+      }
     }
     else if (e.rmppi)
     {
@@ -1373,7 +1388,8 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     if (want)
     {
       e->stream_k1 = true;
-      e->writeback = true;
+      if (getenv("MPPIB_STREAM_READBACK"))  // A/B: the round-1 form (controls written back and re-read by the epilogue)
+        e->writeback = true;
       bx = sbx;
       e->smem_bytes = (uint32_t)sm_str;
     }

@@ -89,9 +89,10 @@ struct DoubleIntegratorCircleCost : public Cost<DoubleIntegratorCircleCost, mppi
     float current_velocity = sqrtf(s[2] * s[2] + s[3] * s[3]);
     float current_angular_momentum = s[0] * s[3] - s[1] * s[2];
     float cost = 0;
+    const float crash = theta_c[timestep] * params_.crash_cost;  // powf(discount, timestep); loaded unconditionally, then selected
     if ((radial_position < params_.inner_path_radius2) || (radial_position > params_.outer_path_radius2))
     {
-      cost += theta_c[timestep] * params_.crash_cost;  // powf(discount, timestep)
+      cost += crash;
     }
     cost += params_.velocity_cost * fabsf(current_velocity - params_.velocity_desired);
     cost += params_.velocity_cost * fabsf(current_angular_momentum - params_.angular_momentum_desired);

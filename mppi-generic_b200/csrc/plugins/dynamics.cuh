@@ -29,15 +29,11 @@ __device__ __forceinline__ void enforceConstraintsDefault(const mppib_control_li
 #pragma unroll
   for (int i = 0; i < C; i++)
   {
-    if (fabsf(control[i]) < lim.deadband[i])
-    {
-      control[i] = lim.zero_control[i];
-    }
-    else
-    {
-      control[i] += lim.deadband[i] * -signf_ref(control[i]);
-    }
-    control[i] = fminf(fmaxf(lim.rng_lo[i], control[i]), lim.rng_hi[i]);
+    // both arms evaluated, one selected: no divergent-branch region in the step loop (same values as the if / else)
+    const float u = control[i];
+    const float shifted = u + lim.deadband[i] * -signf_ref(u);
+    const float v = (fabsf(u) < lim.deadband[i]) ? lim.zero_control[i] : shifted;
+    control[i] = fminf(fmaxf(lim.rng_lo[i], v), lim.rng_hi[i]);
   }
 }
 

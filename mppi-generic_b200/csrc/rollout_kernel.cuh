@@ -66,6 +66,7 @@ struct RolloutArgs
   int use_tma;
   int dyn_shared_floats;  // DYN::sharedFloats(model_dims, blockDim.x): theta_s size (run-time for the LSTM model)
   int ring;               // > 0: streaming variant, noise slabs cycle through `ring` shared-memory buffers
+  int stream_readback;    // streaming variant, A/B switch: 1 = weighted sum from the written-back controls (round-1 form)
   // RMPPI (rollout_kernel<..., RMPPI = true>): distribution 0 = nominal system, 1 = real system
   const float* fb_gains;       // DDP feedback gains [T][S][C] (column-major C x S per step) or nullptr (no feedback)
   float value_func_threshold;  // robust_mppi_controller.cuh: value_function_threshold_
@@ -75,13 +76,12 @@ struct RolloutArgs
 };
 
 // gaussian.cu:101-121: the three cases of setGaussianControls for one element
+// Branch-free: x + (-0.0f) == x for every float (including both zeros), so the pure-noise case sd * eps is the same FFMA with
+// the addend -0.0f, and the three cases become two selects instead of two divergent-branch regions per control and step.
 __device__ __forceinline__ float sample_control(float mean, float sd, float eps, bool use_mean, bool pure_noise)
 {
-  if (use_mean)
-    return mean;
-  if (pure_noise)
-    return sd * eps;
-  return fmaf(sd, eps, mean);  // nvcc contracts the reference's `mean + std_dev * eps` to the same FFMA
+  const float v = fmaf(sd, eps, pure_noise ? -0.0f : mean);  // nvcc contracts the reference's `mean + std_dev * eps` to this FFMA
+  return use_mean ? mean : v;
 }
 
 // element i (0..3) of a 16-byte group without forcing it into local memory when i is not a compile-time constant
@@ -146,12 +146,12 @@ __host__ __device__ inline RolloutSmem rollout_smem_layout(int bx, int tile_chun
 // 0.5 c_nom + 0.5 max(min(tracking_real, value_func_threshold), c_nom) + its likelihood-ratio cost. The real system's
 // applied control depends on the state, so the block's weighted average reads it back from the write-back buffer.
 //
-// STREAM = true (WRITEBACK, TMA): the noise does not stay resident. Its 32-column slabs cycle through a small ring of
-// shared-memory buffers (TMA refills a buffer as soon as every thread is done with it), the constrained controls go to
-// HBM as they are produced and the block's weighted average reads them back from there (L2). Shared memory per sample
-// drops from T*C*4 bytes to ring*128, so long horizons no longer cap the block count per SM — the resident tile of
-// C5 (T*C = 300) allows 4 warps per SM and 3.5 waves, the ring 12+ warps and one wave — at the price of 3x the
-// algorithmic HBM traffic (read eps, write u, read u), which this latency-bound kernel has to spare.
+// STREAM = true (TMA): the noise does not stay resident. Its 32-column slabs cycle through a small ring of shared-memory
+// buffers (TMA refills a buffer as soon as every thread is done with it) and the block's weighted average, which needs every
+// control of the horizon once the weights are known, recomputes them from a SECOND read of the block's noise rows (fresh in
+// L2: the 126 MB L2 holds C5's 78.6 MB buffer) instead of the write + read of u round 1 paid (ncu: 183 MB per launch against
+// 78.6 MB algorithmic). Shared memory per sample drops from T*C*4 bytes to ring*128, so long horizons no longer cap the
+// block count per SM — the resident tile of C5 (T*C = 300) allows 4 warps per SM and 3.5 waves, the ring 12+ warps and one.
 template <class DYN, class COST, int D, bool WRITEBACK, int SPT, bool RMPPI = false, bool STREAM = false>
 __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const __grid_constant__ RolloutArgs<DYN, COST> args,
                                                       const __grid_constant__ CUtensorMap tmap)
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   static_assert(D <= MPPIB_MAX_DISTRIBUTIONS, "too many distributions");
   static_assert(SPT == 1 || D == 1, "several samples per thread are built for one distribution");
   static_assert(!RMPPI || (D == 2 && WRITEBACK && SPT == 1), "RMPPI: two systems, controls kept in HBM");
-  static_assert(!STREAM || (WRITEBACK && SPT == 1 && !RMPPI), "streaming variant: controls kept in HBM");
+  static_assert(!STREAM || (SPT == 1 && !RMPPI), "streaming variant: one sample per thread, no feedback");
   constexpr int STEPS_PER_GROUP = 4 / C;
   constexpr int M = SPT * D;  // systems rolled out by one thread: member m = sp * D + d
 
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     if (valid[sp])
       args.costs[(size_t)d * args.n_local + n_loc[sp]] = cost[m];
   }
-  if (RMPPI || STREAM)
+  if (RMPPI || (STREAM && WRITEBACK))
     __threadfence_block();  // the epilogue reads other threads' written-back controls
 
   // ---- block partial of the softmin-weighted control average ------------------------------------------------------
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
               for (int c = 0; c < C; c++)
                 u[c] = p[c];
             }
-            else if (STREAM || (RMPPI && d == 1))
+            else if ((RMPPI && d == 1) || (STREAM && WRITEBACK && args.stream_readback))
             {  // the real system's applied control (sample + feedback, constrained) as K1 wrote it back
               const float* q = args.controls_out + (((size_t)d * args.n_local + row0 + r) * T + t) * C;
 #pragma unroll
@@ -566,13 +566,15 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
                 u[c] = q[c];
             }
             else
-            {
+            {  // recomputed from the noise: the shared tile (resident, D == 2) or — streaming variant, whose ring no longer
+               // holds it — the global buffer again (a second, L2-friendly read of eps instead of a write + read of u)
+              const float* src = STREAM ? args.eps + ((size_t)(row0 + r) * T + t) * C : p;
               const int ng = args.n_offset + row0 + r;
               const bool pn = (float)ng >= args.samp.pure_noise_threshold;
               const bool um = t_uses_mean || (ng == 0);
 #pragma unroll
               for (int c = 0; c < C; c++)
-                u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], p[c], um, pn);
+                u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], STREAM ? __ldg(src + c) : src[c], um, pn);
               DYN::enforceConstraints(args.dyn, nullptr, u);
             }
             const float w = wrow[r];

@@ -17,7 +17,7 @@ CUDA_HOME="${CUDA_HOME:-/usr/local/cuda}"
 [ -d "$REF/include/mppi" ] || { echo "reference tree not found at $REF (the GPU box uses the prebuilt oracle/_ref)"; exit 0; }
 mkdir -p "$OUT"
 # compute_100 (not 100a): the reference is architecture-generic CUDA; this is what its own CMake would emit for a B200
-"$CUDA_HOME/bin/nvcc" -std=c++17 -O3 -lineinfo -gencode arch=compute_100,code=sm_100 -Xcompiler -fPIC -shared \
+"$CUDA_HOME/bin/nvcc" -std=c++17 -O3 -g -lineinfo -gencode arch=compute_100,code=sm_100 -Xcompiler -fPIC -shared \
   -include "$HERE/shim/ref_prefix.h" -I"$HERE/shim" -I"$REF/include" -I"$REF/submodules/cnpy" \
   "$HERE/ref_gpu.cu" "$REF/submodules/cnpy/cnpy.cpp" -o "$OUT/libmppi_ref_gpu.so" \
   -L"$CUDA_HOME/lib64" -Xlinker -rpath -Xlinker "$CUDA_HOME/lib64" -lcurand -lcufft -lz

@@ -262,6 +262,7 @@ static RefHandleBase* make_autorally(const float* theta, int ntheta, const char*
   h->model = new ARModel(rng);
   h->model->updateModel({ 6, 32, 32, 4 }, std::vector<float>(theta, theta + ntheta));
   h->cost = new ARStandardCost();
+  h->cost->GPUSetup();  // costmapToTexture writes the texture handle into the device copy (ar_standard_cost.cu:179-183)
   if (h->cost->loadTrackData(map_path).empty())
   {
     g_err = std::string("loadTrackData failed for ") + map_path;

@@ -491,6 +491,27 @@ def test_autorally_warp_specialised_equals_generic(N, T, pspw, monkeypatch):
     b.close()
 
 
+@pytest.mark.parametrize("spw", [32, 16, 8])
+def test_autorally_generic_kernel_sample_groups_agree_with_default(spw, monkeypatch):
+    """The generic one-thread-per-sample K1 with 32 / 16 / 8 samples per warp (MPPIB_SPW, plugins/nn_mma.cuh: forward<SPW>;
+    kept for A/B runs) against the default warp-specialised kernel on the same noise: same per-sample operations, so the
+    constrained controls agree bit for bit and the costs to an ulp; ragged size so that partial groups are exercised."""
+    w = W.autorally(1000 + 37, 64)
+    a = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    monkeypatch.setenv("MPPIB_SPW", str(spw))
+    b = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
+    assert b.launch_info()["block"] % 32 == 0
+    Ua, sa = a.solve(w.x0, w.U0)
+    Ub, sb = b.solve(w.x0, w.U0)
+    np.testing.assert_array_equal(a.get_samples(), b.get_samples())
+    ca, cb = a.get_costs(), b.get_costs()
+    rel = np.abs(ca - cb) / np.maximum(np.abs(cb), 1.0)
+    assert rel.max() < 1e-6, rel.max()
+    np.testing.assert_allclose(Ua, Ub, rtol=0, atol=1e-5)
+    a.close()
+    b.close()
+
+
 # ---- oracle parity at BASELINE.json's exact sizes (the launch geometry the bench runs: 147 x 672 for C4) ----------------
 @pytest.mark.parametrize("name", ["cartpole", "double_integrator_tube", "autorally", "racer_lstm"])
 def test_full_size_oracle_parity(name):
