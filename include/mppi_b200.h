@@ -69,6 +69,8 @@ enum mppib_blob
 #define MPPIB_FLAG_NN_FFMA2 128u         /* Autorally NN: forward pass as FP32 FFMA2s fed from shared memory (the round-1 form) */
 #define MPPIB_FLAG_NO_WARP_SPEC 256u     /* Autorally pair: keep the generic one-thread-per-sample K1 instead of the warp-   \
                                             specialised producer / consumer kernel (rollout_kernel_ar_ws.cuh) */
+#define MPPIB_FLAG_LSTM_SIMT 512u         /* RacerDubinsElevationLSTMSteering at hidden_dim 32: keep the one-thread-per-sample    \
+                                            LSTM instead of the tensor-core form (plugins/lstm_mma.cuh) */
 #define MPPIB_FLAG_CURAND_HOST_API 4u    /* draw with curandGenerateNormal (library) instead of the engine's own     \
                                             bit-identical XORWOW kernel */
 

@@ -707,6 +707,10 @@ static const PairEntry kPairs[] = {
                                                                           MPPIB_COST_QUADROTOR_QUADRATIC),
 };
 
+// RacerDubinsElevationLSTMSteering with the steering LSTM on tensor cores (hidden_dim 32, head width <= 24)
+static const PairEntry kPairsLstmMma[] = {
+  make_entry<plugins::RacerLSTMMmaDynamics, plugins::RacerQuadraticCost>(MPPIB_DYN_RACER_LSTM, MPPIB_COST_RACER_QUADRATIC),
+};
 // the Autorally pair's default form, one entry per samples-per-warp width (chosen at create time from n_local)
 static const PairEntry kPairsMma[] = {
   make_entry<plugins::AutorallyNNMmaDynamics<32>, plugins::ARStandardCost>(MPPIB_DYN_AUTORALLY_NN, MPPIB_COST_AR_STANDARD),
@@ -1170,6 +1174,14 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
       if (p.cost_id == desc->cost_id && p.spw == spw)
         entry = &p;
   }
+  // steering LSTM at hidden_dim 32 (head width <= 24): gates and head as mma.sync products, hidden / cell state in fragment
+  // layout in registers (plugins/lstm_mma.cuh) — 11.2 ms -> see profiles/r02_racer_h32_* per C5-sized solve.
+  // MPPIB_FLAG_LSTM_SIMT / MPPIB_LSTM_SIMT keep the one-thread-per-sample network.
+  if (entry && desc->dynamics_id == MPPIB_DYN_RACER_LSTM && desc->model_dims[0] == lstm_mma::H &&
+      desc->model_dims[1] <= 8 * lstm_mma::kHeadTiles && !(desc->flags & MPPIB_FLAG_LSTM_SIMT) && !getenv("MPPIB_LSTM_SIMT"))
+    for (const auto& p : kPairsLstmMma)
+      if (p.cost_id == desc->cost_id)
+        entry = &p;
   if (!entry)
     return fail(MPPIB_ERR_UNSUPPORTED, "no kernel registered for dynamics %d + cost %d", desc->dynamics_id,
                 desc->cost_id);
@@ -1366,16 +1378,16 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     if (const char* sb = getenv("MPPIB_BX"))
     {
       const int v = atoi(sb);
-      if (v >= 32 && v <= entry->max_block_threads && (v % 32) == 0)
+      if (v >= unit && v <= max_bx && (v % unit) == 0)
         sbx = v;
     }
     const int sm_str = (int)rollout_smem_layout(sbx, e->ring, e->D, e->TC, e->dyn_shared_floats_fn(e->desc.model_dims, sbx),
                                                 e->cost_shared_floats(e->T))
                            .total;
     bool want = false;
-    if (tma_ok && !e->rmppi && !e->nn_tc && !ws && spt == 1 && lps == 1 && e->nchunks > e->ring && sm_str <= max_smem)
+    if (tma_ok && !e->rmppi && !e->nn_tc && !ws && spt == 1 && e->nchunks > e->ring && sm_str <= max_smem)
     {
-      const int per_sm_str = entry->stream_blocks_per_sm(e->D, sbx, (size_t)sm_str);
+      const int per_sm_str = entry->stream_blocks_per_sm(e->D, threads_for(sbx), (size_t)sm_str);
       if (per_sm_str > 0)
       {
         const long blocks_str = (e->n_local + sbx - 1) / sbx;

@@ -17,6 +17,7 @@
 #include "../device_utils.cuh"
 #include "../../../include/mppi_b200/params.h"
 #include "nn_mma.cuh"
+#include "lstm_mma.cuh"
 
 namespace mppib
 {
@@ -685,6 +686,7 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
                   off_b2 = off_w2 + L1p;
     const float4* G = reinterpret_cast<const float4*>(theta_s);
     float hn[HC];
+#ifndef MPPIB_EXP_LSTM_SCALAR
     // the four gate sums of a row and the four neurons of a head group as two packed FFMA2 each: every lane is the same
     // IEEE fma in the same order as the scalar form (lstm_forward), so the results are identical; the kernel is issue-bound
     // (66 % issue active) and this removes ~140 of its ~1060 instructions per warp-step (K1 at C5: 621 -> 610 us, B200).
@@ -749,6 +751,66 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       out = fmaf(w2.w, tanh_fast(acc_zw.y + b.w), out);
     }
     return out + theta_s[off_b2];
+#else
+#pragma unroll
+    for (int i = 0; i < HC; i++)
+    {
+      const float4* row = G + i * row_f4;
+      float gi = 0.0f, gf = 0.0f, go = 0.0f, gc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < I; j++)
+      {
+        const float4 w = row[j];
+        gi = fmaf(w.x, in[j], gi);
+        gf = fmaf(w.y, in[j], gf);
+        go = fmaf(w.z, in[j], go);
+        gc = fmaf(w.w, in[j], gc);
+      }
+#pragma unroll
+      for (int j = 0; j < HC; j++)
+      {
+        const float4 w = row[I + j];
+        gi = fmaf(w.x, k.h[j], gi);
+        gf = fmaf(w.y, k.h[j], gf);
+        go = fmaf(w.z, k.h[j], go);
+        gc = fmaf(w.w, k.h[j], gc);
+      }
+      const float4 b = row[I + HC];
+      gi = sigmoid_dev(gi + b.x);
+      gf = sigmoid_dev(gf + b.y);
+      go = sigmoid_dev(go + b.z);
+      gc = tanh_fast(gc + b.w);
+      k.c[i] = gi * gc + gf * k.c[i];
+      hn[i] = tanh_fast(k.c[i]) * go;
+    }
+#pragma unroll
+    for (int i = 0; i < HC; i++)
+      k.h[i] = hn[i];
+    const float* W1T = theta_s + off_w1t;
+    float out = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < L1p; k4 += 4)
+    {
+      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < HC + I; j++)
+      {
+        const float4 w = *reinterpret_cast<const float4*>(W1T + j * L1p + k4);
+        const float a = j < HC ? hn[j < HC ? j : 0] : in[j < HC ? 0 : j - HC];
+        acc.x = fmaf(w.x, a, acc.x);
+        acc.y = fmaf(w.y, a, acc.y);
+        acc.z = fmaf(w.z, a, acc.z);
+        acc.w = fmaf(w.w, a, acc.w);
+      }
+      const float4 b = *reinterpret_cast<const float4*>(theta_s + off_b1 + k4);
+      const float4 w2 = *reinterpret_cast<const float4*>(theta_s + off_w2 + k4);
+      out = fmaf(w2.x, tanh_fast(acc.x + b.x), out);
+      out = fmaf(w2.y, tanh_fast(acc.y + b.y), out);
+      out = fmaf(w2.z, tanh_fast(acc.z + b.z), out);
+      out = fmaf(w2.w, tanh_fast(acc.w + b.w), out);
+    }
+    return out + theta_s[off_b2];
+#endif
   }
 
   // LSTMHelper::forward (device) + head; returns the head's single output. h is read from the buffer of parity
@@ -840,6 +902,16 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
                                               const float* state, float* next_state, float* state_der,
                                               const float* control, float* output, int t, float dt)
   {
+    stepWith(p, state, next_state, state_der, control, output, dt, [&](const float(&in)[I]) {
+      return (aux.H == FAST_H && aux.L1 == FAST_L1) ? lstm_forward_ct<FAST_H, FAST_L1>(theta_s, in, carry) :
+                                                      lstm_forward(aux, theta_s, in, t);
+    });
+  }
+  // the step with the steering network's evaluation handed in (NET(in) -> head output): shared with the tensor-core form
+  template <class NET>
+  __device__ static __forceinline__ void stepWith(const Params& p, const float* state, float* next_state, float* state_der,
+                                                  const float* control, float* output, float dt, NET&& net)
+  {
     const float vx = state[VEL_X];
     const float linear_brake_slope = 0.2f;
     const int index = (fabsf(vx) > linear_brake_slope && fabsf(vx) <= 3.0f) + (fabsf(vx) > 3.0f) * 2;
@@ -888,8 +960,7 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       in[1] = state[STEER_ANGLE_RATE] * 0.2f;
       in[2] = control[1];
       in[3] = state_der[STEER_ANGLE_RATE] * 0.2f;
-      const float nn_output = (aux.H == FAST_H && aux.L1 == FAST_L1) ? lstm_forward_ct<FAST_H, FAST_L1>(theta_s, in, carry)
-                                                                    : lstm_forward(aux, theta_s, in, t);
+      const float nn_output = net(in);
       state_der[STEER_ANGLE_RATE] += nn_output * 5.0f;
       state_der[STEER_ANGLE] = state[STEER_ANGLE_RATE];
     }
@@ -990,6 +1061,43 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
     next_state[PITCH] = 0.0f;
     next_state[ROLL] = 0.0f;
     setOutputs(state_der, next_state, output);
+  }
+};
+
+// ---- RacerDubinsElevationLSTMSteering with the steering LSTM on tensor cores (plugins/lstm_mma.cuh): hidden_dim 32, head
+//      width <= 24. A warp carries 16 samples (lanes l and l + 16 the same one, rollout_kernel.cuh: SAMPLES_PER_WARP); the LSTM's
+//      hidden and cell state live in mma fragment layout in the warp's registers across the whole horizon. Everything around
+//      the network is RacerLSTMDynamics'. Chosen by engine.cu from mppib_desc.model_dims. ------------------------------------
+struct RacerLSTMMmaDynamics : public Dynamics<RacerLSTMMmaDynamics, mppib_racer_lstm_dyn_params, 19, 2, 28>
+{
+  using Base = RacerLSTMDynamics;
+  static constexpr int I = Base::I;
+  static constexpr int SAMPLES_PER_WARP = 16;
+  using AuxDyn = RacerLSTMDynamics;  // the one-thread-per-rollout auxiliary kernels keep the one-thread-per-sample network
+  static constexpr int MAX_BLOCK_THREADS = 256;
+  static constexpr int MAX_DISTRIBUTIONS = 1;
+  static constexpr bool UNROLL_STEPS = false;
+  using Aux = Base::Aux;
+  using Carry = lstm_mma::State;
+  static int sharedFloats(const int* /*model_dims*/, int bx)
+  {
+    return lstm_mma::sharedFloats(bx / SAMPLES_PER_WARP);
+  }
+  __device__ static __forceinline__ void initializeDynamics(const Params&, const Aux& aux, float* theta_s, Carry& carry,
+                                                            const float* x, float* y)
+  {
+    lstm_mma::load_weights(aux.theta_d, aux.L1, theta_s);
+    lstm_mma::init_state(aux.theta_d, carry);
+    Base::setOutputs(x, x, y);  // lstm_steering.cu:128
+  }
+  // warp-collective: every lane of the warp calls it (the rollout kernels keep out-of-range rows running)
+  __device__ static __forceinline__ void step(const Params& p, const Aux&, float* theta_s, Carry& carry, const float* state,
+                                              float* next_state, float* state_der, const float* control, float* output,
+                                              int /*t*/, float dt)
+  {
+    float* scratch = theta_s + lstm_mma::kFixedFloats + (threadIdx.x >> 5) * lstm_mma::kScratchPerWarp;
+    Base::stepWith(p, state, next_state, state_der, control, output, dt,
+                   [&](const float(&in)[I]) { return lstm_mma::forward(theta_s, scratch, in, carry); });
   }
 };
 

@@ -80,8 +80,16 @@ struct RolloutArgs
 // the addend -0.0f, and the three cases become two selects instead of two divergent-branch regions per control and step.
 __device__ __forceinline__ float sample_control(float mean, float sd, float eps, bool use_mean, bool pure_noise)
 {
+#ifdef MPPIB_EXP_BRANCHY
+  if (use_mean)
+    return mean;
+  if (pure_noise)
+    return sd * eps;
+  return fmaf(sd, eps, mean);
+#else
   const float v = fmaf(sd, eps, pure_noise ? -0.0f : mean);  // nvcc contracts the reference's `mean + std_dev * eps` to this FFMA
   return use_mean ? mean : v;
+#endif
 }
 
 // element i (0..3) of a 16-byte group without forcing it into local memory when i is not a compile-time constant
@@ -203,7 +211,9 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     const int n_glob = args.n_offset + n_loc[sp];
     int pn = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
     int zn = (n_glob == 0);                                    // gaussian.cu:101
+#ifdef MPPIB_EXP_PIN
     asm volatile("" : "+r"(pn), "+r"(zn));                     // kept as flags: no per-step re-read of the parameter bank
+#endif
     pure_noise[sp] = pn != 0;
     zero_noise_sample[sp] = zn != 0;
   }
@@ -290,7 +300,9 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
       lr_on = lr_on || (args.samp.control_cost_coeff[c] != 0.0f);
     }
   float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
+#ifdef MPPIB_EXP_PIN
   asm volatile("" : "+f"(half_lambda_1ma));  // computed once, not once per step
+#endif
 
   // ---- the horizon ----------------------------------------------------------------------------------------------
   // One loop over the horizon's 16-byte noise groups (4 / C steps each); slab k = groups 8k .. 8k+7. Everything a step
@@ -303,7 +315,9 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   {
     row_off[sp] = (uint32_t)row[sp] * kChunkBytes;
     swz[sp] = (uint32_t)row[sp] & 7u;
+#ifdef MPPIB_EXP_PIN
     asm volatile("" : "+r"(row_off[sp]), "+r"(swz[sp]));
+#endif
   }
   float sd_dec[D][C];
 #pragma unroll
@@ -312,13 +326,29 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     for (int c = 0; c < C; c++)
     {
       sd_dec[d][c] = args.samp.std_dev_decayed[d][c];
+#ifdef MPPIB_EXP_PIN
       asm volatile("" : "+f"(sd_dec[d][c]));
+#endif
     }
   const int opt_stride = args.opt_stride;
   const int ngroups = (TC + 3) >> 2;
   const uint32_t slab_bytes = (uint32_t)bx * kChunkBytes;
   unsigned char* slab = tile;
   int slot = 0;
+#ifdef MPPIB_EXP_NESTED
+  for (int k = 0; k < nchunks; k++)
+  {
+    slot = STREAM ? (k % ring) : k;
+    if (args.use_tma)
+      mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
+    slab = tile + (size_t)slot * slab_bytes;
+#pragma unroll 1
+  for (int g = 0; g < 8; g++)
+  {
+    const int gi = k * 8 + g;
+    if (gi >= ngroups)
+      break;
+#else
 #pragma unroll 1
   for (int gi = 0; gi < ngroups; gi++)
   {
@@ -330,6 +360,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
       slab = tile + (size_t)slot * slab_bytes;
     }
+#endif
     unsigned char* gp[SPT];
     float4 e4[SPT];
 #pragma unroll
@@ -430,7 +461,12 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
           x[m][i] = x_next[m][i];
       }
     }
+#ifdef MPPIB_EXP_NESTED
+  }
+    if (STREAM)
+#else
     if (STREAM && (g == 7 || gi == ngroups - 1))
+#endif
     {
       __syncthreads();  // every thread is done with this slab's buffer
       if (thr == 0 && k + ring < nchunks)
@@ -541,47 +577,58 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
       const bool t_uses_mean = t < args.opt_stride;
       const unsigned char* slab = tile + (size_t)chunk * bx * kChunkBytes + ((within & 3) << 2);
       const float* wrow = w_s + d * bx;
-      // rows in blocks of 8: the swizzle term (grp ^ (r & 7)) << 4 is then a per-lane constant of the unrolled body
+      // rows in blocks of 8: the swizzle term (grp ^ (r & 7)) << 4 is then a per-lane constant of the unrolled body. The
+      // loads of a block are issued first and unconditionally (rows past the end are clamped and get weight 0), so eight
+      // loads are in flight per thread instead of one load-use round trip per row — this loop reads L2 / HBM in the streaming
+      // and RMPPI forms, where the serialised version cost 13 % of C5's K1 (profiles/r02_racer_k1_stalls.txt).
+      const bool from_global = (RMPPI && d == 1) || STREAM;
+      const bool readback = (RMPPI && d == 1) || (STREAM && WRITEBACK && args.stream_readback);
+      const float* gsrc = readback ? args.controls_out + (size_t)d * args.n_local * T * C : args.eps;
       for (int r8 = 0; r8 < rows_here; r8 += 8)
       {
+        float v[8][C];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+          const int r = min(r8 + i, rows_here - 1);
+          if (from_global)
+          {
+            const float* q = gsrc + ((size_t)(row0 + r) * T + t) * C;
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              v[i][c] = __ldg(q + c);
+          }
+          else
+          {
+            const float* p = reinterpret_cast<const float*>(slab + r * kChunkBytes + ((grp ^ (r & 7)) << 4));
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              v[i][c] = p[c];
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++)
         {
           const int r = r8 + i;
-          if (r < rows_here)
-          {
-            const float* p = reinterpret_cast<const float*>(slab + r * kChunkBytes + ((grp ^ i) << 4));
-            float u[C];
-            if (D == 1 && !STREAM)
-            {
+          float u[C];
 #pragma unroll
-              for (int c = 0; c < C; c++)
-                u[c] = p[c];
-            }
-            else if ((RMPPI && d == 1) || (STREAM && WRITEBACK && args.stream_readback))
-            {  // the real system's applied control (sample + feedback, constrained) as K1 wrote it back
-              const float* q = args.controls_out + (((size_t)d * args.n_local + row0 + r) * T + t) * C;
-#pragma unroll
-              for (int c = 0; c < C; c++)
-                u[c] = q[c];
-            }
-            else
-            {  // recomputed from the noise: the shared tile (resident, D == 2) or — streaming variant, whose ring no longer
-               // holds it — the global buffer again (a second, L2-friendly read of eps instead of a write + read of u)
-              const float* src = STREAM ? args.eps + ((size_t)(row0 + r) * T + t) * C : p;
-              const int ng = args.n_offset + row0 + r;
-              const bool pn = (float)ng >= args.samp.pure_noise_threshold;
-              const bool um = t_uses_mean || (ng == 0);
-#pragma unroll
-              for (int c = 0; c < C; c++)
-                u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], STREAM ? __ldg(src + c) : src[c], um, pn);
-              DYN::enforceConstraints(args.dyn, nullptr, u);
-            }
-            const float w = wrow[r];
+          for (int c = 0; c < C; c++)
+            u[c] = v[i][c];
+          if (!(D == 1 && !STREAM) && !readback)
+          {  // the value is noise: recompute the constrained control (resident tile with D == 2, or the streaming variant, whose
+             // ring no longer holds it: a second, L2-friendly read of eps instead of round 1's write + read of u)
+            const int ng = args.n_offset + row0 + min(r, rows_here - 1);
+            const bool pn = (float)ng >= args.samp.pure_noise_threshold;
+            const bool um = t_uses_mean || (ng == 0);
 #pragma unroll
             for (int c = 0; c < C; c++)
-              acc[c] = fmaf(w, u[c], acc[c]);
+              u[c] = sample_control(mean_t[c], args.samp.std_dev_decayed[d][c], v[i][c], um, pn);
+            DYN::enforceConstraints(args.dyn, nullptr, u);
           }
+          const float w = (r < rows_here) ? wrow[r] : 0.0f;
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            acc[c] = fmaf(w, u[c], acc[c]);
         }
       }
 #pragma unroll

@@ -32,6 +32,7 @@ BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIG
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR, FLAG_RMPPI = 1, 2, 4, 8, 16, 32
 FLAG_NN_MMA, FLAG_NN_FFMA2 = 64, 128
 FLAG_NO_WARP_SPEC = 256
+FLAG_LSTM_SIMT = 512
 OPT_L2_FLUSH_BYTES = 1
 OPT_COLORED_OFFSET_T = 2
 OPT_P2P_ENABLE = 3

@@ -168,6 +168,11 @@ def racer_lstm_gaussian(N: int = 4096, T: int = 100) -> Workload:
     return racer_lstm(N, T, colored=False)
 
 
+def racer_lstm_h32(N: int = 65536, T: int = 150) -> Workload:
+    """C5 at the tensor-core-relevant size of SURVEY §8d: hidden_dim 32 (gate matrix [36 x 128] per step), head {36, 20, 1}."""
+    return racer_lstm(N, T, hidden_dim=32, head_hidden=20)
+
+
 def quadrotor(N: int = 8192, T: int = 100) -> Workload:
     """Quadrotor + quadratic cost, VanillaMPPI (instantiations/quadrotor_mppi/quadrotor_mppi.cuh): fly from the origin
     to a goal 4 m away and 2 m up, hovering there. The only CONTROL_DIM = 4 pair (one 16-byte noise group per step)."""
@@ -189,6 +194,7 @@ def quadrotor(N: int = 8192, T: int = 100) -> Workload:
 BUILDERS = {
     "racer_lstm": racer_lstm,
     "racer_lstm_gaussian": racer_lstm_gaussian,
+    "racer_lstm_h32": racer_lstm_h32,
     "cartpole": cartpole,
     "double_integrator_tube": double_integrator_tube,
     "double_integrator_vanilla": double_integrator_vanilla,

@@ -765,6 +765,31 @@ def test_racer_lstm_solve_parity(colored, hidden):
     e.close()
 
 
+def test_racer_lstm_tensor_core_form_agrees_with_one_thread_per_sample_form():
+    """hidden_dim 32: the steering LSTM on mma.sync (plugins/lstm_mma.cuh: FP16 hi / lo operands, three products, hidden and
+    cell state in fragment layout in registers; the default) against the one-thread-per-sample FP32 form
+    (MPPIB_FLAG_LSTM_SIMT) on the same noise, over a 150-step recurrence, with a non-zero initial hidden / cell state; ragged
+    rollout count and the streaming K1 (long horizon) included. Both are then held to the oracle by _check_solve."""
+    for N, T in ((2048, 150), (1000 + 13, 64)):
+        w = W.racer_lstm(N, T, hidden_dim=32, colored=False)
+        rng = np.random.RandomState(5)
+        w.dyn.setInitialHiddenCell(rng.uniform(-0.5, 0.5, 32).astype(np.float32), rng.uniform(-1, 1, 32).astype(np.float32))
+        w.U0[0, :, 1] = np.linspace(-0.4, 0.4, w.T)
+        a = w.make_engine()
+        b = w.make_engine(flags=H.FLAG_LSTM_SIMT)
+        Ua, sa = a.solve(w.x0, w.U0)
+        Ub, sb = b.solve(w.x0, w.U0)
+        np.testing.assert_array_equal(a.get_noise(), b.get_noise())
+        ca, cb = a.get_costs(), b.get_costs()
+        rel = np.abs(ca - cb) / np.maximum(np.abs(cb), 1.0)
+        assert rel.max() < 2e-5, (N, T, rel.max())
+        assert sa[0][0] == pytest.approx(sb[0][0], rel=2e-5)
+        np.testing.assert_allclose(Ua, Ub, atol=2e-4)
+        _check_solve(w, a, cost_rtol=2e-4)
+        a.close()
+        b.close()
+
+
 def test_racer_lstm_controller_runs_and_tracks_speed():
     """Closed loop through the mirrored controller API (VanillaMPPIController): the car accelerates to the desired speed
     and the state / output trajectories come from the LSTM host twin."""

@@ -158,3 +158,63 @@ def test_layer1_k16_concatenation_and_sigmoid_fold_are_exact_identities():
     Wm, b, t = rng.randn(32, 32), rng.randn(32), np.tanh(rng.randn(16, 32))
     r = (1.0 - t) / 2.0
     np.testing.assert_allclose(r @ (-2.0 * Wm).T + (b + Wm.sum(1)), t @ Wm.T + b, rtol=0, atol=1e-12)
+
+
+# ---- plugins/lstm_mma.cuh: the steering LSTM (hidden_dim 32) on the same scheme -----------------------------------------------
+def test_lstm_fragment_bookkeeping_keeps_the_recurrence_lane_local():
+    """Index identities lstm_mma.cuh rests on. Gate tile (q, k) = gate q, hidden units 8k .. 8k+7: lane (g, t) of its C
+    fragment holds units 8k+2t, 8k+2t+1 of rows g, g+8 — the same units for all four gates, so c' and h' are lane-local;
+    and those two units, packed, are register (k & 1) * 2 + {0: row g, 1: row g+8} of k16-tile k >> 1 of the next step's
+    A fragment (m16n8k16 A layout: a0 (g, 2t..), a1 (g+8, 2t..), a2 (g, 2t+8..), a3 (g+8, 2t+8..))."""
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        for k in range(4):
+            units_c = {8 * k + 2 * t, 8 * k + 2 * t + 1}                     # C fragment columns 2t, 2t+1 of tile (q, k), any q
+            j, reg = k >> 1, (k & 1) * 2                                      # where forward() stores h'
+            col0 = 2 * t + (8 if reg >= 2 else 0)                             # a0/a1 -> cols 2t.., a2/a3 -> cols 2t+8..
+            units_a = {16 * j + col0, 16 * j + col0 + 1}
+            assert units_c == units_a, (lane, k)
+
+
+def test_lstm_step_with_folded_scales_matches_float64():
+    """One LSTM step + head for a batch, emulated the way forward() computes it — gate weights pre-scaled by -log2(e)
+    (sigmoid gates) / 2 log2(e) (cell candidate), r = 1 / (1 + exp2(z)), tanh = 1 - 2 r, head tanh handed on as r with
+    W2' = -2 W2, b2' = b2 + sum W2, every product split hi / lo in FP16 — against the float64 LSTM of lstm_helper.cu:341-463."""
+    Hd, I, L1 = 32, 4, 20
+    lstm, head = W.synthetic_lstm_weights(Hd, L1, 2)
+    lstm, head = lstm.astype(np.float64), head.astype(np.float64)
+    HH, IH = Hd * Hd, Hd * I
+    Wm = [lstm[q * HH:(q + 1) * HH].reshape(Hd, Hd) for q in range(4)]           # W_im W_fm W_om W_cm
+    Wi = [lstm[4 * HH + q * IH:4 * HH + (q + 1) * IH].reshape(Hd, I) for q in range(4)]
+    b = [lstm[4 * HH + 4 * IH + q * Hd:4 * HH + 4 * IH + (q + 1) * Hd] for q in range(4)]
+    IN = Hd + I
+    W1, b1 = head[:L1 * IN].reshape(L1, IN), head[L1 * IN:L1 * IN + L1]
+    W2, b2 = head[L1 * IN + L1:L1 * IN + 2 * L1], head[L1 * IN + 2 * L1]
+    rng = np.random.RandomState(7)
+    n = 4096
+    h, c = rng.uniform(-0.9, 0.9, (n, Hd)), rng.uniform(-2, 2, (n, Hd))
+    x = rng.uniform(-0.3, 0.3, (n, I))
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))  # noqa: E731
+    gi, gf, go = (sig(h @ Wm[q].T + x @ Wi[q].T + b[q]) for q in range(3))
+    gc = np.tanh(h @ Wm[3].T + x @ Wi[3].T + b[3])
+    c_ref = gi * gc + gf * c
+    h_ref = np.tanh(c_ref) * go
+    out_ref = np.tanh(np.concatenate([h_ref, x], 1) @ W1.T + b1) @ W2 + b2
+    # emulation
+    f32, LOG2E = np.float32, 1.4426950408889634
+    a = np.concatenate([h, x], 1).astype(f32)
+    acts = []
+    for q in range(4):
+        sc = 2.0 * LOG2E if q == 3 else -LOG2E
+        Wq = (np.concatenate([Wm[q], Wi[q]], 1) * sc).astype(f32)
+        acts.append(_sigmoid_pre(_layer_split(a, Wq, (b[q] * sc).astype(f32))))
+    g_ = f32(1.0) - f32(2.0) * acts[3]
+    c_new = (acts[0] * g_ + acts[1] * c.astype(f32)).astype(f32)
+    rt = _sigmoid_pre((c_new * f32(2.0 * LOG2E)).astype(f32))
+    h_new = (acts[2] * (f32(1.0) - f32(2.0) * rt)).astype(f32)
+    a2 = np.concatenate([h_new, x.astype(f32)], 1)
+    r1 = _sigmoid_pre(_layer_split(a2, (W1 * 2.0 * LOG2E).astype(f32), (b1 * 2.0 * LOG2E).astype(f32)))
+    out = _layer_split(r1, (-2.0 * W2).astype(f32)[None, :], np.array([b2 + W2.sum()], f32))[:, 0]
+    assert np.abs(c_new - c_ref).max() < 2e-6 and np.abs(h_new - h_ref).max() < 1e-6, (np.abs(c_new - c_ref).max(),
+                                                                                       np.abs(h_new - h_ref).max())
+    assert np.abs(out - out_ref).max() < 2e-6, np.abs(out - out_ref).max()
