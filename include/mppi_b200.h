@@ -238,6 +238,17 @@ int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides
 int mppib_sample_trajectories(mppib_engine* e, const float* x0, const float* U_nominal, int distribution,
                               const int* sample_idx, int n, const float* U_opt, float* outputs, float* costs, int* crash);
 
+/* ---- user plugins ----------------------------------------------------------------------------------------------------
+ * The reference's plugin contract is "compile your Dynamics / Cost class against the templates" (dynamics.cuh:67-76,
+ * cost.cuh:34-35, utils/managed.cuh:109-135). Here a user pair is compiled into a SECOND shared library from
+ * mppi-generic_b200/csrc/engine_internal.cuh (device twins with the static methods of csrc/plugins/dynamics.cuh / costs.cuh;
+ * see plugins_example/ and INTEGRATION.md E) whose `int mppib_plugin_init(void)` registers it; engines are then created with
+ * its ids (>= MPPIB_USER_ID_BASE) and its POD parameter structs go through mppib_set_blob like the built-in ones.
+ * mppib_load_plugin = dlopen + mppib_plugin_init. mppib_register_pair is what the plugin calls (through register_pair<>). */
+#define MPPIB_USER_ID_BASE 1000
+int mppib_load_plugin(const char* path);
+int mppib_register_pair(const void* pair_entry, size_t entry_bytes, unsigned abi);
+
 const char* mppib_strerror(int status);
 const char* mppib_last_error(void); /* thread-local text of the last failure */
 int mppib_version(void);

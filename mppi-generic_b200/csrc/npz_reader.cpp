@@ -18,7 +18,7 @@
 
 #include "../../include/mppi_b200/host_twins.h"
 
-extern "C" __attribute__((visibility("hidden"))) int mppib_set_last_error(int status, const char* fmt, ...);  // engine.cu
+extern "C" int mppib_set_last_error(int status, const char* fmt, ...);  // engine.cu
 
 namespace
 {

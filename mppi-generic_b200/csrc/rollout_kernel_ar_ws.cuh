@@ -17,8 +17,8 @@
  *
  *   phase 0 (all warps)   noise tile -> constrained controls, in place in shared memory (what setGaussianControls +
  *                         enforceConstraints + writeControlSample do in HBM): no recurrence, fully parallel.
- *   producer warp         32 samples' network recurrence and nothing else, ENTIRELY in mma fragment layout: lane (g, t)
- *                         keeps states (3 + 2t, 4 + 2t) of rows g, g+8, g+16, g+24 (t < 2), reads those rows' controls
+ *   producer warp         32 / 16 / 8 samples' network recurrence and nothing else, ENTIRELY in mma fragment layout: lane (g, t)
+ *                         keeps states (3 + 2t, 4 + 2t) of its rows g, g+8, ... (t < 2), reads those rows' controls
  *                         from the tile (t == 2), and the C fragment it gets back from layer 3 is exactly the derivative
  *                         of its own slice (nn_mma.cuh: forward_frag) — no transposition through shared memory, no
  *                         __syncwarp inside the recurrence. Per 16-byte noise group (2 steps) it publishes states 3..6
@@ -48,13 +48,20 @@ constexpr int kSlotFloats = 2 * 32 * 4;  // [step in group][sample][states 3..6]
 // and 16-31 of the group, one m16 tile each) + one consumer — a producer's step is layer after layer of [MMAs -> ex2 / rcp ->
 // conversions] with no overlap between layers inside one in-order warp, so two half-size producers that the scheduler
 // interleaves finish a group's step in about half the time of one full-size producer (profiles/r02_autorally_k1_notes.md).
+// 8: four producers of 8 rows (rows 8..15 of their m16 tile are padding, activations skipped) + one consumer: the same tensor
+// work per producer as with 16 rows but half the ex2 / rcp, each producer on its own scheduler — for a GPU that holds so few
+// rollouts that a group's step time, not the chip's throughput, sets K1 (multi-GPU strong scaling).
 __host__ __device__ constexpr int warpsPerGroup(int pspw)
 {
   return 32 / pspw + 1;
 }
+__host__ __device__ constexpr int maxGroups(int pspw)
+{
+  return pspw == 8 ? 4 : 8;  // 32-sample groups per block: 256 samples, 128 for the 5-warp groups (register budget)
+}
 __host__ __device__ constexpr int maxThreads(int pspw)
 {
-  return warpsPerGroup(pspw) * 32 * 8;  // 8 groups = 256 samples per block
+  return warpsPerGroup(pspw) * 32 * maxGroups(pspw);
 }
 // floats of the block's `theta_s` region for bx samples: fragment-ordered weights, then the rings, then the barriers
 // (kRing full + kRing empty per pair, 8 bytes each)
@@ -75,11 +82,12 @@ template <bool WRITEBACK, int PSPW>
 __global__ void __launch_bounds__(ar_ws::maxThreads(PSPW), 1)
     rollout_kernel_ar_ws(const __grid_constant__ ArWsArgs args, const __grid_constant__ CUtensorMap tmap)
 {
-  static_assert(PSPW == 32 || PSPW == 16, "samples per producer warp");
-  constexpr int NP = 32 / PSPW;   // producer warps per 32-sample group
-  constexpr int WPG = NP + 1;     // warps per group
-  constexpr int MT = PSPW / 16;   // m16 tiles per producer
-  constexpr int NR = 2 * MT;      // rows a producer lane carries (g + 8 j)
+  static_assert(PSPW == 32 || PSPW == 16 || PSPW == 8, "samples per producer warp");
+  constexpr int NP = 32 / PSPW;                 // producer warps per 32-sample group
+  constexpr int WPG = NP + 1;                   // warps per group
+  constexpr int MT = PSPW == 32 ? 2 : 1;        // m16 tiles per producer
+  constexpr bool BOT = PSPW >= 16;              // rows g + 8 of the tile carry samples
+  constexpr int NR = PSPW / 8;                  // rows a producer lane carries (g + 8 j)
   using DYN = ArWsDyn;
   using COST = plugins::ARStandardCost;
   constexpr int S = 7, C = 2, O = 8;
@@ -213,11 +221,13 @@ __global__ void __launch_bounds__(ar_ws::maxThreads(PSPW), 1)
   //   PSPW 32: warps 2p, 2p+1 serve group p; roles with period 8:  P C C P  C P P C
   //   PSPW 16: warps 3p .. 3p+2 serve group p; the consumer is the first warp of even groups and the last of odd ones
   //            (period 12: C P P  P P C  C P P  P P C — one consumer and two producers per scheduler)
+  //   PSPW  8: warps 5p .. 5p+4 serve group p; the consumer is the first: warps 5p and 5p+4 land on the same scheduler, so
+  //            the light consumer shares with one producer and the other three producers have a scheduler each
   const int pair = warp / WPG;
   const int wi = warp - pair * WPG;
-  const int c_off = (pair & 1) ? 2 : 0;  // NP == 2: the consumer's position inside its group
+  const int c_off = (NP == 2) ? ((pair & 1) ? 2 : 0) : 0;  // the consumer's position inside its group (NP >= 2)
   const bool is_producer = (NP == 1) ? (((0x69u >> (warp & 7)) & 1u) != 0) : (wi != c_off);
-  const int half = (NP == 1) ? 0 : (wi > c_off ? wi - 1 : wi);  // which 16 rows of the group this producer owns
+  const int half = (NP == 1) ? 0 : (wi > c_off ? wi - 1 : wi);  // which PSPW rows of the group this producer owns
   if (is_producer)
   {
     // ---- producer: the network recurrence of PSPW samples in fragment layout ----------------------------------------
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(ar_ws::maxThreads(PSPW), 1)
     float* ring = rings + pair * kRing * kSlotFloats;
     uint64_t* full = ring_bars + pair * kRing * 2;
     uint64_t* empty = full + kRing;
-    const int rbase = half * 16;  // first row of this producer inside the group
+    const int rbase = half * PSPW;  // first row of this producer inside the group
     float2 st[NR];  // states (3 + 2t, 4 + 2t) of rows rbase + g + 8 j; lanes t >= 2 carry zeros (and stay zero: padded outputs)
 #pragma unroll
     for (int j = 0; j < NR; j++)
@@ -258,6 +268,8 @@ __global__ void __launch_bounds__(ar_ws::maxThreads(PSPW), 1)
         if (gi * 2 + s >= T)
           break;
         uint32_t a_hi[MT][2], a_lo[MT][2];
+        if (!BOT)
+          a_hi[0][1] = a_lo[0][1] = 0u;
 #pragma unroll
         for (int j = 0; j < NR; j++)
         {
@@ -266,14 +278,12 @@ __global__ void __launch_bounds__(ar_ws::maxThreads(PSPW), 1)
           nn_mma::split2(v.x, v.y, a_hi[j >> 1][j & 1], a_lo[j >> 1][j & 1]);
         }
         float o[MT][4];
-        nn_mma::forward_frag<MT, true>(theta_s, a_hi, a_lo, o);
+        nn_mma::forward_frag<MT, BOT>(theta_s, a_hi, a_lo, o);
 #pragma unroll
-        for (int m = 0; m < MT; m++)
-        {  // x_next = x + xdot * dt (dynamics.cu:118-129), on the lane's own slice
-          st[2 * m].x = fmaf(o[m][0], dt, st[2 * m].x);
-          st[2 * m].y = fmaf(o[m][1], dt, st[2 * m].y);
-          st[2 * m + 1].x = fmaf(o[m][2], dt, st[2 * m + 1].x);
-          st[2 * m + 1].y = fmaf(o[m][3], dt, st[2 * m + 1].y);
+        for (int j = 0; j < NR; j++)
+        {  // x_next = x + xdot * dt (dynamics.cu:118-129), on the lane's own slice: row g + 8 j is C-fragment pair (j & 1) of m-tile j >> 1
+          st[j].x = fmaf(o[j >> 1][2 * (j & 1)], dt, st[j].x);
+          st[j].y = fmaf(o[j >> 1][2 * (j & 1) + 1], dt, st[j].y);
         }
         if (t < 2)
         {

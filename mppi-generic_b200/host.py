@@ -170,7 +170,7 @@ class Timing(C.Structure):
 
 # every symbol include/mppi_b200.h and include/mppi_b200/host_twins.h declare (tests check the .so exports them all)
 ABI_SYMBOLS = [
-    "mppib_create", "mppib_destroy", "mppib_set_blob", "mppib_set_solver", "mppib_seed", "mppib_burn_draws",
+    "mppib_create", "mppib_destroy", "mppib_load_plugin", "mppib_register_pair", "mppib_set_blob", "mppib_set_solver", "mppib_seed", "mppib_burn_draws",
     "mppib_get_rng_offset", "mppib_comm_unique_id", "mppib_comm_init", "mppib_solve", "mppib_solve_async",
     "mppib_solve_wait", "mppib_set_option", "mppib_set_noise",
     "mppib_draw_noise", "mppib_rollout_only", "mppib_reduce_only", "mppib_get_costs", "mppib_get_noise",
@@ -603,6 +603,31 @@ class _Cost:
 
     def blob(self) -> bytes:
         return bytes(self.params)
+
+
+USER_ID_BASE = 1000  # MPPIB_USER_ID_BASE: dynamics / cost ids of out-of-tree pairs
+
+
+def load_plugin(path: str) -> None:
+    """mppib_load_plugin: dlopen an out-of-tree pair library (plugins_example/) and let it register its pairs."""
+    _check(lib().mppib_load_plugin(os.fsencode(path)))
+
+
+class UserDynamics(_Dynamics):
+    """Host handle of a user-registered dynamics (the device twin lives in the plugin library): ids, dimensions and the
+    POD parameter struct, which must start with a ControlLimits field named `lim` like every built-in dynamics blob."""
+
+    def __init__(self, dyn_id: int, state_dim: int, control_dim: int, output_dim: int, params: C.Structure):
+        super().__init__()
+        self.DYN_ID, self.STATE_DIM, self.CONTROL_DIM, self.OUTPUT_DIM = dyn_id, state_dim, control_dim, output_dim
+        self.params = params
+        self.params.lim.set_defaults()
+
+
+class UserCost(_Cost):
+    def __init__(self, cost_id: int, params: C.Structure):
+        super().__init__()
+        self.COST_ID, self.params = cost_id, params
 
 
 class CartpoleQuadraticCost(_Cost):

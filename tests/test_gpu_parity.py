@@ -462,7 +462,7 @@ def test_autorally_mma_and_ffma2_paths_agree():
     e.close()
 
 
-@pytest.mark.parametrize("pspw", [16, 32])
+@pytest.mark.parametrize("pspw", [16, 32, 8])
 @pytest.mark.parametrize("N,T", [(4096, 100), (1000, 37), (224 * 3 + 5, 64)])
 def test_autorally_warp_specialised_equals_generic(N, T, pspw, monkeypatch):
     """The default K1 of the Autorally pair (rollout_kernel_ar_ws.cuh: producer warps run the network recurrence in mma
@@ -471,7 +471,7 @@ def test_autorally_warp_specialised_equals_generic(N, T, pspw, monkeypatch):
     last ulp or two (4 of 4096 costs differ by one ulp on B200), and with the same block width so must U. Ragged sizes and a T whose T*C is not a multiple of 4
     (plain-load staging, a one-step last group) included."""
     monkeypatch.setenv("MPPIB_BX", "64")
-    monkeypatch.setenv("MPPIB_WS_PSPW", str(pspw))  # samples per producer warp: 16 (default, two producers per group) or 32
+    monkeypatch.setenv("MPPIB_WS_PSPW", str(pspw))  # samples per producer warp: 16 / 8 (chosen by rollout count) or 32
     w = W.autorally(N, T)
     a = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS)
     b = w.make_engine(flags=H.FLAG_WRITEBACK_CONTROLS | H.FLAG_NO_WARP_SPEC)
