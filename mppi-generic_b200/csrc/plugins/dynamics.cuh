@@ -686,7 +686,6 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
                   off_b2 = off_w2 + L1p;
     const float4* G = reinterpret_cast<const float4*>(theta_s);
     float hn[HC];
-#ifndef MPPIB_EXP_LSTM_SCALAR
     // the four gate sums of a row and the four neurons of a head group as two packed FFMA2 each: every lane is the same
     // IEEE fma in the same order as the scalar form (lstm_forward), so the results are identical; the kernel is issue-bound
     // (66 % issue active) and this removes ~140 of its ~1060 instructions per warp-step (K1 at C5: 621 -> 610 us, B200).
@@ -751,66 +750,6 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       out = fmaf(w2.w, tanh_fast(acc_zw.y + b.w), out);
     }
     return out + theta_s[off_b2];
-#else
-#pragma unroll
-    for (int i = 0; i < HC; i++)
-    {
-      const float4* row = G + i * row_f4;
-      float gi = 0.0f, gf = 0.0f, go = 0.0f, gc = 0.0f;
-#pragma unroll
-      for (int j = 0; j < I; j++)
-      {
-        const float4 w = row[j];
-        gi = fmaf(w.x, in[j], gi);
-        gf = fmaf(w.y, in[j], gf);
-        go = fmaf(w.z, in[j], go);
-        gc = fmaf(w.w, in[j], gc);
-      }
-#pragma unroll
-      for (int j = 0; j < HC; j++)
-      {
-        const float4 w = row[I + j];
-        gi = fmaf(w.x, k.h[j], gi);
-        gf = fmaf(w.y, k.h[j], gf);
-        go = fmaf(w.z, k.h[j], go);
-        gc = fmaf(w.w, k.h[j], gc);
-      }
-      const float4 b = row[I + HC];
-      gi = sigmoid_dev(gi + b.x);
-      gf = sigmoid_dev(gf + b.y);
-      go = sigmoid_dev(go + b.z);
-      gc = tanh_fast(gc + b.w);
-      k.c[i] = gi * gc + gf * k.c[i];
-      hn[i] = tanh_fast(k.c[i]) * go;
-    }
-#pragma unroll
-    for (int i = 0; i < HC; i++)
-      k.h[i] = hn[i];
-    const float* W1T = theta_s + off_w1t;
-    float out = 0.0f;
-#pragma unroll
-    for (int k4 = 0; k4 < L1p; k4 += 4)
-    {
-      float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll
-      for (int j = 0; j < HC + I; j++)
-      {
-        const float4 w = *reinterpret_cast<const float4*>(W1T + j * L1p + k4);
-        const float a = j < HC ? hn[j < HC ? j : 0] : in[j < HC ? 0 : j - HC];
-        acc.x = fmaf(w.x, a, acc.x);
-        acc.y = fmaf(w.y, a, acc.y);
-        acc.z = fmaf(w.z, a, acc.z);
-        acc.w = fmaf(w.w, a, acc.w);
-      }
-      const float4 b = *reinterpret_cast<const float4*>(theta_s + off_b1 + k4);
-      const float4 w2 = *reinterpret_cast<const float4*>(theta_s + off_w2 + k4);
-      out = fmaf(w2.x, tanh_fast(acc.x + b.x), out);
-      out = fmaf(w2.y, tanh_fast(acc.y + b.y), out);
-      out = fmaf(w2.z, tanh_fast(acc.z + b.z), out);
-      out = fmaf(w2.w, tanh_fast(acc.w + b.w), out);
-    }
-    return out + theta_s[off_b2];
-#endif
   }
 
   // LSTMHelper::forward (device) + head; returns the head's single output. h is read from the buffer of parity

@@ -80,16 +80,8 @@ struct RolloutArgs
 // the addend -0.0f, and the three cases become two selects instead of two divergent-branch regions per control and step.
 __device__ __forceinline__ float sample_control(float mean, float sd, float eps, bool use_mean, bool pure_noise)
 {
-#ifdef MPPIB_EXP_BRANCHY
-  if (use_mean)
-    return mean;
-  if (pure_noise)
-    return sd * eps;
-  return fmaf(sd, eps, mean);
-#else
   const float v = fmaf(sd, eps, pure_noise ? -0.0f : mean);  // nvcc contracts the reference's `mean + std_dev * eps` to this FFMA
   return use_mean ? mean : v;
-#endif
 }
 
 // element i (0..3) of a 16-byte group without forcing it into local memory when i is not a compile-time constant
@@ -211,9 +203,6 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     const int n_glob = args.n_offset + n_loc[sp];
     int pn = (float)n_glob >= args.samp.pure_noise_threshold;  // gaussian.cu:108, :505
     int zn = (n_glob == 0);                                    // gaussian.cu:101
-#ifdef MPPIB_EXP_PIN
-    asm volatile("" : "+r"(pn), "+r"(zn));                     // kept as flags: no per-step re-read of the parameter bank
-#endif
     pure_noise[sp] = pn != 0;
     zero_noise_sample[sp] = zn != 0;
   }
@@ -300,9 +289,6 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
       lr_on = lr_on || (args.samp.control_cost_coeff[c] != 0.0f);
     }
   float half_lambda_1ma = 0.5f * args.lambda * (1.0f - args.alpha);
-#ifdef MPPIB_EXP_PIN
-  asm volatile("" : "+f"(half_lambda_1ma));  // computed once, not once per step
-#endif
 
   // ---- the horizon ----------------------------------------------------------------------------------------------
   // One loop over the horizon's 16-byte noise groups (4 / C steps each); slab k = groups 8k .. 8k+7. Everything a step
@@ -315,9 +301,6 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   {
     row_off[sp] = (uint32_t)row[sp] * kChunkBytes;
     swz[sp] = (uint32_t)row[sp] & 7u;
-#ifdef MPPIB_EXP_PIN
-    asm volatile("" : "+r"(row_off[sp]), "+r"(swz[sp]));
-#endif
   }
   float sd_dec[D][C];
 #pragma unroll
@@ -326,29 +309,12 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
     for (int c = 0; c < C; c++)
     {
       sd_dec[d][c] = args.samp.std_dev_decayed[d][c];
-#ifdef MPPIB_EXP_PIN
-      asm volatile("" : "+f"(sd_dec[d][c]));
-#endif
     }
   const int opt_stride = args.opt_stride;
   const int ngroups = (TC + 3) >> 2;
   const uint32_t slab_bytes = (uint32_t)bx * kChunkBytes;
   unsigned char* slab = tile;
   int slot = 0;
-#ifdef MPPIB_EXP_NESTED
-  for (int k = 0; k < nchunks; k++)
-  {
-    slot = STREAM ? (k % ring) : k;
-    if (args.use_tma)
-      mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
-    slab = tile + (size_t)slot * slab_bytes;
-#pragma unroll 1
-  for (int g = 0; g < 8; g++)
-  {
-    const int gi = k * 8 + g;
-    if (gi >= ngroups)
-      break;
-#else
 #pragma unroll 1
   for (int gi = 0; gi < ngroups; gi++)
   {
@@ -360,7 +326,6 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
         mbar_wait(&bars[slot], STREAM ? ((k / ring) & 1) : 0);
       slab = tile + (size_t)slot * slab_bytes;
     }
-#endif
     unsigned char* gp[SPT];
     float4 e4[SPT];
 #pragma unroll
@@ -461,12 +426,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
           x[m][i] = x_next[m][i];
       }
     }
-#ifdef MPPIB_EXP_NESTED
-  }
-    if (STREAM)
-#else
     if (STREAM && (g == 7 || gi == ngroups - 1))
-#endif
     {
       __syncthreads();  // every thread is done with this slab's buffer
       if (thr == 0 && k + ring < nchunks)

@@ -79,12 +79,17 @@ def test_out_of_tree_pendulum_pair_matches_numpy_rollout(N, T):
     U, stats = e.solve(x0, U0)
     eps = e.get_noise()[:, :, 0]                                   # [N][T]
     f32 = np.float32
-    u = (U0[0, :, 0][None, :] + f32(1.5) * eps).astype(f32)      # mean + sigma eps
+    # the device evaluates mean + sigma eps as ONE fma (nvcc contracts the reference's expression the same way): the
+    # float64 product is exact, so rounding the float64 sum reproduces it up to (rare) double rounding
+    u = (U0[0, :, 0][None, :].astype(np.float64) + 1.5 * eps.astype(np.float64)).astype(f32)
     u[0] = U0[0, :, 0]                                             # sample 0 is noise-free (gaussian.cu:101)
     tail = np.arange(N) >= np.float32((1.0 - sampler.params.pure_noise_trajectories_percentage) * N)
     u[tail] = (f32(1.5) * eps[tail]).astype(f32)                   # pure-noise tail (gaussian.cu:108)
     u = np.clip(u, f32(-2.0), f32(2.0))
-    np.testing.assert_array_equal(e.get_samples()[0][:, :, 0], u)  # the engine's constrained controls
+    dev_u = e.get_samples()[0][:, :, 0]                            # the engine's constrained controls
+    np.testing.assert_allclose(dev_u, u, rtol=2e-7, atol=1e-7)
+    assert (dev_u != u).mean() < 1e-3
+    u = dev_u
     th, om = np.full(N, x0[0, 0], f32), np.full(N, x0[0, 1], f32)
     running = np.zeros(N, f32)
     for t in range(T):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Builds an experimental variant of the library next to the shipped one: tools/libexp_<NAME>.so with -DMPPIB_EXP_<NAME>
 # (plugins/dynamics.cuh, plugins/costs.cuh). Select it at run time with MPPIB_LIB=/root/repo/tools/libexp_<NAME>.so.
-#   bash tools/build_exp.sh DEFER_COST [MORE_MACROS...]
+#   bash tools/build_exp.sh NO_COST [MORE_MACROS...]   (macros left in the tree: NO_COST, NO_TEX — ablations of the Autorally cost)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 NAME=$1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU-box script: A/B of experimental library builds (tools/build_exp.sh NAME) on one workload.  WORKLOAD=racer_lstm VARIANTS="DEFAULT NOPIN" bash tools/run_ab.sh
+# GPU-box script: A/B of experimental library builds (tools/build_exp.sh NAME) on one workload.  WORKLOAD=racer_lstm VARIANTS="DEFAULT NO_TEX" bash tools/run_ab.sh
 for v in ${VARIANTS:-DEFAULT}; do
   if [ "$v" = "DEFAULT" ]; then L=""; else L="/root/repo/tools/libexp_$v.so"; fi
   for wl in ${WORKLOADS:-racer_lstm}; do
