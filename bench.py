@@ -245,7 +245,8 @@ def _reference_gpu(w):
             "tried": rows}
 
 
-def run_engine(args, ctx):
+def run_engine(args, ctx, emit=True, extra=None):
+    """One workload through the engine; rank 0 prints the JSON line (emit) and returns it, the other ranks return None."""
     import torch
     import mppi_generic_b200 as m
     H = m.host
@@ -388,6 +389,29 @@ def run_engine(args, ctx):
     torch.cuda.synchronize()
     solve_only_ms = (time.perf_counter() - t0) * 1e3
 
+    # the same computeControl with the tail ON THE DEVICE (mppib_nominal_trajectory chained behind the solve: one
+    # host wait per call). Reported next to e2e; the host-twin tail above stays the default because it is faster.
+    U[...] = w.U0
+    U_s = np.empty_like(U)
+    st_d = np.zeros((w.D, w.T, S_), np.float32)
+    out_d = np.zeros((w.D, w.T, O_), np.float32)
+    nt_args = (e._h, x0.ctypes.data, None, hist.ctypes.data, U_s.ctypes.data, st_d.ctypes.data, out_d.ctypes.data)
+    device_tail_ms = None
+    try:
+        for it in range(3 + n_timed):
+            if it == 3:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            e.solve_async(x0, U, w.optimization_stride, 0)
+            H._check(L.mppib_nominal_trajectory(*nt_args))
+            H._check(L.mppib_solve_wait(e._h, U_out.ctypes.data, stats))
+            U[...] = U_s
+        torch.cuda.synchronize()
+        device_tail_ms = (time.perf_counter() - t0) * 1e3
+    except H.MppibError as ex:  # a user pair without the call, Tsallis ...
+        device_tail_ms = None
+        print(f"[bench] device tail skipped: {ex}", file=sys.stderr)
+
     sampler.stop_flag = True
     sampler.join(timeout=2)
     clocks = sampler.result()
@@ -427,6 +451,7 @@ def run_engine(args, ctx):
     }
     n_local = e.n_local
     e.close()
+    line = None
 
     if rank == 0:
         value = n_timed / (dev_ms * 1e-3)
@@ -452,7 +477,10 @@ def run_engine(args, ctx):
                     "ms_per_step": e2e_ms / n_timed,
                     "includes": "blocking mppib_solve (host x0/U in, U/stats out) + host tail: SG smoothing and nominal "
                                 "state/output roll-forward (T host step() calls)",
-                    "solve_only_value": n_timed / (solve_only_ms * 1e-3)},
+                    "solve_only_value": n_timed / (solve_only_ms * 1e-3),
+                    "device_tail_value": None if device_tail_ms is None else n_timed / (device_tail_ms * 1e-3),
+                    "device_tail_note": "same computeControl with smoothing + roll-forward as one device kernel chained "
+                                        "behind the solve (mppib_nominal_trajectory); the host-twin tail is the default"},
             "gpu_launches": n_timed * info["kernels_per_solve"],
             "clocks": clocks,
             "roofline": roofline,
@@ -466,9 +494,13 @@ def run_engine(args, ctx):
             if "value" in rg:
                 line["vs_reference_gpu"] = {"e2e_ratio": e2e_value / rg["value"], "value_ratio": value / rg["value"],
                                             "note": "north_star target: >= 10x the reference GPU build's computeControl Hz (C4)"}
-        print(json.dumps(line), flush=True)
+        if extra:
+            line.update(extra)
+        if emit:
+            print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+    return line if rank == 0 else None
 
 
 def _setup():
@@ -499,6 +531,8 @@ def main():
     ap.add_argument("--timesteps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="default run only: skip the C2 / C3 / C5 summaries carried in the headline line (other_configs)")
     ap.add_argument("--all-configs", action="store_true",
                     help="one JSON line per BASELINE config: C2 cartpole, C3 double_integrator_tube, C5 racer_lstm, then C4 "
                          "autorally (the headline, last)")
@@ -510,9 +544,27 @@ def main():
             run_reference(args)
         return
     ctx = _setup()
+    extra = None
+    if (not args.all_configs and args.workload == "autorally" and args.rollouts is None and args.timesteps is None
+            and not args.no_other_configs):
+        # the other BASELINE configs (C2, C3, C5), measured the same way in the same process and carried inside the
+        # headline line as a summary, so that one default run shows every config at this GPU count
+        import copy
+        others = []
+        for wl in ("cartpole", "double_integrator_tube", "racer_lstm"):
+            sub = copy.copy(args)
+            sub.workload, sub.no_cpu_baseline, sub.no_reference_gpu = wl, True, True
+            ln = run_engine(sub, ctx, emit=False)
+            if ln is not None:
+                others.append({"workload": ln["config"]["workload"], "value": ln["value"], "unit": ln["unit"],
+                               "e2e": ln["e2e"]["value"], "ms_per_step": ln["ms_per_step"],
+                               "k1_ms_l2_flushed": ln["roofline"]["kernel_ms_l2_flushed"],
+                               "k1_hbm_frac": ln["roofline"]["frac"], "stage_ms": ln["roofline"]["stage_ms_l2_warm"],
+                               "timed_ms": ln["engine"]["timed_ms"], "parity_ok": ln.get("parity_ok")})
+        extra = {"other_configs": others}
     for wl in workloads:
         args.workload = wl
-        run_engine(args, ctx)
+        run_engine(args, ctx, extra=extra if wl == "autorally" else None)
     if ctx[0] is not None:
         ctx[0].destroy_process_group()
 

@@ -238,6 +238,20 @@ int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides
 int mppib_sample_trajectories(mppib_engine* e, const float* x0, const float* U_nominal, int distribution,
                               const int* sample_idx, int n, const float* U_opt, float* outputs, float* costs, int* crash);
 
+/* Device-side host tail: Controller::smoothControlTrajectoryHelper (controllers/controller.cuh:557-586) and
+ * computeOutputTrajectoryHelper (:643-663) as one kernel on the solve's stream — Savitzky-Golay smoothing of the control
+ * sequence and the nominal state / output roll-forward (T - 1 step() calls with the constrained controls).
+ *   x0 [D][S]
+ *   U  [D][T][C] host, or NULL = the optimised sequence of the last solve, read on the device from the result record
+ *                (may be called right after mppib_solve_async: the kernel is ordered behind the solve, and this call's
+ *                single wait then covers the whole computeControl; mppib_solve_wait afterwards returns at once)
+ *   control_history [2][C], or NULL = no smoothing (the controls are only copied)
+ *   U_smoothed [D][T][C] (may be NULL), states [D][T][S], outputs [D][T][O]   row 0 = x0 / the initial output
+ * A T-step dependent chain on ONE thread per system: slower than the library's vectorised host twins
+ * (mppib_host_output_trajectory), which stay the default of the controller mirrors; see DESIGN.md §9. */
+int mppib_nominal_trajectory(mppib_engine* e, const float* x0, const float* U, const float* control_history,
+                             float* U_smoothed, float* states, float* outputs);
+
 /* ---- user plugins ----------------------------------------------------------------------------------------------------
  * The reference's plugin contract is "compile your Dynamics / Cost class against the templates" (dynamics.cuh:67-76,
  * cost.cuh:34-35, utils/managed.cuh:109-135). Here a user pair is compiled into a SECOND shared library from

@@ -62,8 +62,13 @@ public:
     this->free_energy_statistics_.real_sys.normalizerPercent = this->getNormalizerCost() / NUM_ROLLOUTS;
     this->free_energy_statistics_.real_sys.increase =
         this->getBaselineCost() - this->free_energy_statistics_.real_sys.previousBaseline;
-    smoothControlTrajectory();
-    computeStateTrajectory(state);
+    if (this->device_side_tail_)
+      this->deviceSideTail(state, this->control_, this->control_history_, this->state_, this->output_);
+    else
+    {
+      smoothControlTrajectory();
+      computeStateTrajectory(state);
+    }
     state_array zero_state = this->model_->getZeroState();
     for (int i = 0; i < this->getNumTimesteps(); i++)
     {  // mppi_controller.cu:227-231

@@ -478,7 +478,34 @@ public:
     output_result = out;
   }
 
+  // Not in the reference: computeControl's host tail (smoothing + nominal roll-forward, controller.cuh:557-586, 643-663) as one
+  // device kernel behind the solve (mppib_nominal_trajectory) instead of the host twins. Off by default (the host twins are
+  // faster); VanillaMPPI / ColoredMPPI honour it.
+  void setDeviceSideTail(bool on)
+  {
+    device_side_tail_ = on;
+  }
+  bool getDeviceSideTail() const
+  {
+    return device_side_tail_;
+  }
+  void deviceSideTail(const Eigen::Ref<const state_array>& x0, Eigen::Ref<control_trajectory> u,
+                      const Eigen::Ref<const Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2>>& control_history,
+                      Eigen::Ref<state_trajectory> state_result, Eigen::Ref<output_trajectory> output_result)
+  {
+    state_array x = x0;
+    control_trajectory uu = u, us = control_trajectory::Zero();
+    Eigen::Matrix<float, DYN_T::CONTROL_DIM, 2> h = control_history;
+    state_trajectory st = state_trajectory::Zero();
+    output_trajectory out = output_trajectory::Zero();
+    MPPIB_HANDLE(mppib_nominal_trajectory(engine_, x.data(), uu.data(), h.data(), us.data(), st.data(), out.data()));
+    u = us;
+    state_result = st;
+    output_result = out;
+  }
+
 protected:
+  bool device_side_tail_ = false;
   bool debug_ = false;
   unsigned extra_flags_ = 0u;  // engine flags a derived controller turns on at run time (re-creates the engine)
   float perc_sampled_control_trajectories_ = 0;  // controller.cuh:948-950

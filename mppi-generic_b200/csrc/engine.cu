@@ -681,6 +681,7 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
   e->prepare = entry->prepare;
   e->init_eval = entry->init_eval;
   e->sampled_traj = entry->sampled_traj;
+  e->nominal_traj = entry->nominal_traj;
   e->dyn_param_bytes = entry->dyn_bytes;
   e->cost_param_bytes = entry->cost_bytes;
   e->dyn_shared_floats_fn = entry->dyn_shared_floats;
@@ -1087,6 +1088,10 @@ int mppib_destroy(mppib_engine* e)
   cudaFree(e->nln_d);
   cudaFree(e->vis_idx_d);
   cudaFree(e->vis_opt_d);
+  cudaFree(e->nom_d);
+  cudaFree(e->nom_u_d);
+  if (e->nom_h)
+    cudaFreeHost(e->nom_h);
   cudaFree(e->vis_outputs_d);
   cudaFree(e->vis_costs_d);
   cudaFree(e->vis_crash_d);
@@ -1791,6 +1796,51 @@ int mppib_sample_trajectories(mppib_engine* e, const float* x0, const float* U_n
                            e->stream));
   CUDA_TRY(cudaMemcpyAsync(crash, e->vis_crash_d, (size_t)n * e->T * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MPPIB_OK;
+}
+
+// Device-side host tail (controller.cuh:557-586, 643-663): see nominal_traj_kernel.
+int mppib_nominal_trajectory(mppib_engine* e, const float* x0, const float* U, const float* control_history,
+                             float* U_smoothed, float* states, float* outputs)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !states || !outputs)
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument");
+  if (!U && !e->solved_once && !e->pending)
+    return fail(MPPIB_ERR_STATE, "U == NULL rolls out the last solve's result, and no solve has been run yet");
+  if (e->T < 2)
+    return fail(MPPIB_ERR_INVALID_ARG, "needs at least two time steps");
+  for (int i = 0; i < e->D * e->S; i++)
+    if (!std::isfinite(x0[i]))
+      return fail(MPPIB_ERR_INVALID_ARG, "x0[%d] is not finite", i);
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  const size_t n_u = (size_t)e->D * e->TC, n_s = (size_t)e->D * e->T * e->S, n_o = (size_t)e->D * e->T * e->O;
+  if (!e->nom_d)
+  {
+    CUDA_TRY(cudaMalloc(&e->nom_d, (n_u + n_s + n_o) * sizeof(float)));
+    CUDA_TRY(cudaHostAlloc(&e->nom_h, (n_u + n_s + n_o) * sizeof(float), cudaHostAllocDefault));
+  }
+  const float* u_src = e->result_d + kPartialHeader;  // the optimised sequence where K2 / KX left it
+  int u_stride = e->pstride;
+  if (U)
+  {
+    if (!e->nom_u_d)
+      CUDA_TRY(cudaMalloc(&e->nom_u_d, n_u * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(e->nom_u_d, U, n_u * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    u_src = e->nom_u_d;
+    u_stride = e->TC;
+  }
+  rc = e->nominal_traj(*e, x0, u_src, u_stride, control_history);
+  if (rc != MPPIB_OK)
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(e->nom_h, e->nom_d, (n_u + n_s + n_o) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (U_smoothed)
+    memcpy(U_smoothed, e->nom_h, n_u * sizeof(float));
+  memcpy(states, e->nom_h + n_u, n_s * sizeof(float));
+  memcpy(outputs, e->nom_h + n_u + n_s, n_o * sizeof(float));
   return MPPIB_OK;
 }
 

@@ -100,6 +100,10 @@ struct mppib_engine
   // sampled (visualisation) trajectories scratch: picked indices, optimised sequence, outputs / costs / crash flags
   int* vis_idx_d = nullptr;
   float* vis_opt_d = nullptr;
+  float* nom_d = nullptr;      // device tail: [D][T][C] smoothed controls | [D][T][S] states | [D][T][O] outputs
+  float* nom_h = nullptr;      // pinned host copy of the same
+  float* nom_u_d = nullptr;    // uploaded [D][T][C] when the caller passes its own U
+  int (*nominal_traj)(mppib_engine&, const float*, const float*, int, const float*) = nullptr;
   float* vis_outputs_d = nullptr;
   float* vis_costs_d = nullptr;
   int* vis_crash_d = nullptr;
@@ -606,6 +610,40 @@ static int sampled_traj_launch(mppib_engine& e, const float* x0, const float* U_
   return MPPIB_OK;
 }
 
+// device-side host tail for this pair's dynamics: see nominal_traj_kernel
+template <class DYN>
+static int nominal_traj_launch(mppib_engine& e, const float* x0, const float* u_src, int u_stride, const float* history)
+{
+  using Args = NominalTrajArgs<DYN>;
+  static_assert(sizeof(Args) < 30000, "kernel parameter block too large");
+  Args a;
+  memcpy(&a.dyn, e.dyn_blob.data(), sizeof(a.dyn));
+  AuxFill<typename DYN::Aux>::fill(a.dyn_aux, e);
+  a.u_src = u_src;
+  a.u_stride = u_stride;
+  a.u_out = e.nom_d;
+  a.states = e.nom_d + (size_t)e.D * e.TC;
+  a.outputs = a.states + (size_t)e.D * e.T * e.S;
+  a.T = e.T;
+  a.D = e.D;
+  a.smooth = history != nullptr;
+  a.dt = e.dt;
+  const int threads = 64;
+  a.dyn_shared_floats = DYN::sharedFloats(e.desc.model_dims, threads);
+  memset(a.x0, 0, sizeof(a.x0));
+  memset(a.history, 0, sizeof(a.history));
+  for (int d = 0; d < e.D; d++)
+    memcpy(a.x0[d], x0 + (size_t)d * e.S, sizeof(float) * e.S);
+  if (history)
+    for (int k = 0; k < 2; k++)
+      memcpy(a.history[k], history + (size_t)k * e.C, sizeof(float) * e.C);
+  const size_t smem = (size_t)(((a.dyn_shared_floats + 3) / 4) * 4) * sizeof(float) + 16;
+  CUDA_TRY(cudaFuncSetAttribute(nominal_traj_kernel<DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nominal_traj_kernel<DYN><<<1, threads, smem, e.stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return MPPIB_OK;
+}
+
 struct PairEntry
 {
   int dyn_id, cost_id;
@@ -621,6 +659,7 @@ struct PairEntry
   int (*init_eval)(mppib_engine&, const float*, const int*, int, int, const float*, int);
   int (*stream_blocks_per_sm)(int, int, size_t);
   int (*sampled_traj)(mppib_engine&, const float*, const float*, int, int, bool);
+  int (*nominal_traj)(mppib_engine&, const float*, const float*, int, const float*);
 };
 template <class DYN, class COST>
 constexpr PairEntry make_entry(int dyn_id, int cost_id)
@@ -641,7 +680,8 @@ constexpr PairEntry make_entry(int dyn_id, int cost_id)
                     &Pair<DYN, COST>::prepare,
                     &init_eval_launch<typename DYN::AuxDyn, COST>,
                     &Pair<DYN, COST>::stream_blocks_per_sm,
-                    &sampled_traj_launch<typename DYN::AuxDyn, COST> };
+                    &sampled_traj_launch<typename DYN::AuxDyn, COST>,
+                    &nominal_traj_launch<typename DYN::AuxDyn> };
 }
 
 // ---- registration of out-of-tree pairs -------------------------------------------------------------------------------------

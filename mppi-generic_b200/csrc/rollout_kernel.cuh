@@ -780,4 +780,105 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS)
     args.costs[(size_t)gid * (T + 1) + T] = COST::terminalCost(args.cost, args.cost_aux, y[0]) * inv_T;
 }
 
+// =================================================================================================================
+// Device-side host tail: what Controller::computeControl runs on the HOST after the weighted update —
+// smoothControlTrajectoryHelper (controller.cuh:557-586: Savitzky-Golay (-3 12 17 12 -3)/35 over [history(2) | u(T) | u_last
+// u_last]) and computeOutputTrajectoryHelper (controller.cuh:643-663: state(0) = x0, output(0) from initializeDynamics, then
+// T - 1 step() calls with the constrained controls) — as ONE kernel chained behind K2 on the solve's stream: it reads the
+// optimised sequence straight from the result record, so a whole computeControl needs one host wait. One thread per system
+// (D <= 2); the other lanes of the warp run along (the mma.sync forms of the network need full warps) and store nothing.
+// It is a T-step dependent chain on one thread: slower than the vectorised host twins, hence opt-in.
+template <class DYN>
+struct NominalTrajArgs
+{
+  typename DYN::Params dyn;
+  typename DYN::Aux dyn_aux;
+  const float* u_src;   // system d's [T][C] at u_src + d * u_stride (the result record, or an uploaded copy)
+  float* u_out;         // [D][T][C]   smoothed (or copied) controls
+  float* states;        // [D][T][S]
+  float* outputs;       // [D][T][O]
+  int T, D, u_stride, smooth, dyn_shared_floats;
+  float dt;
+  float x0[MPPIB_MAX_DISTRIBUTIONS][32];
+  float history[2][MPPIB_MAX_CONTROL_DIM];
+};
+
+template <class DYN>
+__global__ void __launch_bounds__(64) nominal_traj_kernel(const __grid_constant__ NominalTrajArgs<DYN> args)
+{
+  constexpr int S = DYN::STATE_DIM, C = DYN::CONTROL_DIM, O = DYN::OUTPUT_DIM;
+  static_assert(S <= 32, "x0 travels in the parameter block");
+  extern __shared__ unsigned char smem_raw[];
+  float* theta_s = reinterpret_cast<float*>(smem_raw);
+  const int T = args.T, D = args.D;
+  // ---- smoothing: every element is independent, the block shares them out ----
+  for (int i = threadIdx.x; i < D * T * C; i += blockDim.x)
+  {
+    const int d = i / (T * C), t = (i / C) % T, c = i % C;
+    const float* u = args.u_src + (size_t)d * args.u_stride;
+    float v = u[t * C + c];
+    if (args.smooth)
+    {
+      const float coef[5] = { -3.0f / 35.0f, 12.0f / 35.0f, 17.0f / 35.0f, 12.0f / 35.0f, -3.0f / 35.0f };
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+      {
+        const int tt = t + k - 2;  // index into u; -2, -1 = the history, >= T = the last control held
+        const float b = tt < 0 ? args.history[tt + 2][c] : u[(tt < T ? tt : T - 1) * C + c];
+        acc += coef[k] * b;
+      }
+      v = acc;
+    }
+    args.u_out[i] = v;
+  }
+  const bool valid = threadIdx.x < D;
+  const int d = valid ? threadIdx.x : 0;
+  float x[1][S], y[1][O], x_next[1][S], xdot[1][S], u[1][C];
+#pragma unroll
+  for (int i = 0; i < S; i++)
+    x[0][i] = args.x0[d][i];
+#pragma unroll
+  for (int i = 0; i < O; i++)
+    y[0][i] = 0.0f;
+  typename DYN::Carry carry[1];
+  DYN::initializeDynamics(args.dyn, args.dyn_aux, theta_s, carry[0], x[0], y[0]);
+  __syncthreads();  // theta_s filled, u_out written
+  float* st = args.states + (size_t)d * T * S;
+  float* ot = args.outputs + (size_t)d * T * O;
+  const float* useq = args.u_out + (size_t)d * T * C;
+  if (valid)
+  {
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      st[i] = x[0][i];
+#pragma unroll
+    for (int i = 0; i < O; i++)
+      ot[i] = y[0][i];
+  }
+  for (int t = 0; t < T - 1; t++)
+  {
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      u[0][c] = useq[(size_t)t * C + c];
+    DYN::enforceConstraints(args.dyn, x[0], u[0]);
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      xdot[0][i] = 0.0f;
+    DYN::template stepBatch<1>(args.dyn, args.dyn_aux, theta_s, carry, x, x_next, xdot, u, y, t, args.dt);
+    if (valid)
+    {
+#pragma unroll
+      for (int i = 0; i < S; i++)
+        st[(size_t)(t + 1) * S + i] = x_next[0][i];
+#pragma unroll
+      for (int i = 0; i < O; i++)
+        ot[(size_t)(t + 1) * O + i] = y[0][i];
+    }
+#pragma unroll
+    for (int i = 0; i < S; i++)
+      x[0][i] = x_next[0][i];
+  }
+}
+
 }  // namespace mppib

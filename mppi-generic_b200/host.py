@@ -180,7 +180,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
-    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_nominal_trajectory", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
 
@@ -250,6 +250,8 @@ def lib() -> C.CDLL:
     L.mppib_host_npz_read.argtypes = [C.c_char_p, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int * 4),
                                       ip]
     L.mppib_sample_trajectories.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
+    L.mppib_nominal_trajectory.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.mppib_load_plugin.argtypes = [C.c_char_p]
     _lib = L
     return L
 
@@ -999,6 +1001,18 @@ class Engine:
                                                crash.ctypes.data_as(C.c_void_p)))
         return outputs, costs, crash
 
+    def nominal_trajectory(self, x0, U=None, control_history=None):
+        """mppib_nominal_trajectory: the host tail of computeControl on the device (controller.cuh:557-586, 643-663).
+        U None = the last solve's result, read on the device (may follow solve_async directly). control_history [2][C] or
+        None (no smoothing). Returns (U_smoothed [D][T][C], states [D][T][S], outputs [D][T][O])."""
+        Us = np.empty((self.D, self.T, self.Cdim), np.float32)
+        states = np.empty((self.D, self.T, self.dyn.STATE_DIM), np.float32)
+        outputs = np.empty((self.D, self.T, self.dyn.OUTPUT_DIM), np.float32)
+        _check(lib().mppib_nominal_trajectory(self._h, _ptr(_f32(x0)), None if U is None else _ptr(_f32(U)),
+                                              None if control_history is None else _ptr(_f32(control_history)),
+                                              _ptr(Us), _ptr(states), _ptr(outputs)))
+        return Us, states, outputs
+
     def set_noise(self, eps) -> None:
         eps = _f32(eps)
         _check(lib().mppib_set_noise(self._h, _ptr(eps), eps.size))
@@ -1228,6 +1242,12 @@ class _Controller:
         self.engine.push_params()
         self.engine.set_solver(self.dt_, self.lambda_, self.alpha_)
 
+    def setDeviceSideTail(self, on: bool = True) -> None:
+        """Not in the reference: run computeControl's host tail (controller.cuh:557-586, 643-663) as one device kernel
+        (mppib_nominal_trajectory) instead of the library's host twins. VanillaMPPI / ColoredMPPI. Off by default: the
+        host twins are faster."""
+        self.device_side_tail_ = bool(on)
+
     # host tail helpers — CPU, in the C library (controller.cuh:557-663)
     def _smooth(self, u: np.ndarray) -> None:
         lib().mppib_host_smooth_controls(_ptr(u), _ptr(self.control_history_), self.num_timesteps_,
@@ -1306,8 +1326,12 @@ class VanillaMPPIController(_Controller):
         fe["increase"] = self.baseline_[0] - prev_baseline
         fe["previousBaseline"] = prev_baseline
         self.free_energy_statistics_ = {"real_sys": fe}
-        self._smooth(self.control_)  # smoothControlTrajectory
-        self._output_trajectory(state, self.control_, self.state_, self.output_)  # computeStateTrajectory
+        if getattr(self, "device_side_tail_", False):  # smoothing + roll-forward as one device kernel
+            Us, st, out = self.engine.nominal_trajectory(state.reshape(1, -1), self.control_[None], self.control_history_)
+            self.control_, self.state_[...], self.output_[...] = Us[0].copy(), st[0], out[0]
+        else:
+            self._smooth(self.control_)  # smoothControlTrajectory
+            self._output_trajectory(state, self.control_, self.state_, self.output_)  # computeStateTrajectory
         for i in range(self.num_timesteps_):  # mppi_controller.cu:227-231
             self.model_.enforceConstraints(None, self.control_[i])
 

@@ -27,7 +27,8 @@ class PendulumCostParams(C.Structure):
 
 
 def _plugin():
-    if not os.path.exists(PLUGIN):
+    lib_so = os.path.join(ROOT, "mppi-generic_b200", "libmppi_b200.so")
+    if not os.path.exists(PLUGIN) or os.path.getmtime(PLUGIN) < os.path.getmtime(lib_so):  # stale: the layout fingerprint would refuse it
         subprocess.check_call(["bash", os.path.join(ROOT, "plugins_example", "build.sh")])
     H.load_plugin(PLUGIN)
 
