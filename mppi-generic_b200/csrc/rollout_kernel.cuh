@@ -852,9 +852,12 @@ __global__ void __launch_bounds__(64) nominal_traj_kernel(const __grid_constant_
 #pragma unroll
     for (int i = 0; i < S; i++)
       st[i] = x[0][i];
+    // row 0 follows the HOST initializeDynamics, which is what computeOutputTrajectoryHelper calls (dynamics.cuh:416-423:
+    // y <- x on the first min(S, O) entries); the reference's device initializeDynamics of the RACER model differs
+    // (setOutputs(state, state, output), lstm_steering.cu:128)
 #pragma unroll
     for (int i = 0; i < O; i++)
-      ot[i] = y[0][i];
+      ot[i] = i < S ? x[0][i < S ? i : 0] : 0.0f;
   }
   for (int t = 0; t < T - 1; t++)
   {

@@ -47,7 +47,9 @@ def test_device_tail_matches_host_twins(name):
         Us_d, st_d, out_d = e.nominal_trajectory(x0, U, h)
         np.testing.assert_allclose(Us_d, Us_h, rtol=0, atol=2e-6 * max(1.0, float(np.abs(U).max())))
         for a, b in ((st_d, st_h), (out_d, out_h)):
-            assert np.isfinite(a).all()
+            nan = np.isnan(b)  # the RACER model reports its wheel forces as NaN without an elevation map (both twins)
+            assert np.array_equal(np.isnan(a), nan) and np.isfinite(a[~nan]).all()
+            a, b = np.where(nan, 0.0, a), np.where(nan, 0.0, b)
             # per state component: 1e-4 of that component's range over the trajectory (the reference's CPU==GPU bar)
             scale = np.maximum(np.abs(b).max(axis=1, keepdims=True), 1.0)
             assert (np.abs(a - b) / scale).max() < 1e-4, (name, (np.abs(a - b) / scale).max())

@@ -86,6 +86,7 @@ def test_out_of_tree_pendulum_pair_matches_numpy_rollout(N, T):
     u[0] = U0[0, :, 0]                                             # sample 0 is noise-free (gaussian.cu:101)
     tail = np.arange(N) >= np.float32((1.0 - sampler.params.pure_noise_trajectories_percentage) * N)
     u[tail] = (f32(1.5) * eps[tail]).astype(f32)                   # pure-noise tail (gaussian.cu:108)
+    u[:, :1] = U0[0, :1, 0]                                        # t < optimization_stride (= 1) keeps the mean (gaussian.cu:101)
     u = np.clip(u, f32(-2.0), f32(2.0))
     dev_u = e.get_samples()[0][:, :, 0]                            # the engine's constrained controls
     np.testing.assert_allclose(dev_u, u, rtol=2e-7, atol=1e-7)
