@@ -311,7 +311,7 @@ def run_engine(args, ctx, emit=True, extra=None):
     e.solve_wait()
     torch.cuda.synchronize()
     est = (time.perf_counter() - t0) / 10
-    inner = max(1, int(math.ceil(0.1 / max(args.steps * est, 1e-9))))
+    inner = max(1, int(math.ceil(0.14 / max(args.steps * est, 1e-9))))  # >= 100 ms timed, with margin: est includes launch gaps
     if dist is not None:
         ti = torch.tensor([inner], device="cuda", dtype=torch.int64)
         dist.all_reduce(ti, op=dist.ReduceOp.MAX)
@@ -323,14 +323,24 @@ def run_engine(args, ctx, emit=True, extra=None):
 
     # ---- value: solves enqueued back to back, inputs resident (kernel parameter bank), device-timed ---------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(n_timed):
-        e.solve_async(x0, U, w.optimization_stride, 0)
-    ev1.record(stream)
-    e.solve_wait()
-    barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    for _attempt in range(3):
+        barrier()
+        ev0.record(stream)
+        for _ in range(n_timed):
+            e.solve_async(x0, U, w.optimization_stride, 0)
+        ev1.record(stream)
+        e.solve_wait()
+        barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+        lo_ms = dev_ms
+        if dist is not None:
+            tm = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MIN)
+            lo_ms = float(tm.item())
+        if lo_ms >= 100.0:
+            break
+        inner = int(math.ceil(inner * 125.0 / max(lo_ms, 1.0)))  # the estimate was short: enlarge and measure again
+        n_timed = args.steps * inner
 
     # ---- e2e: what Controller::computeControl does per call (mppi_controller.cu:151-241): one blocking C-ABI solve with
     # host buffers, then the host tail on the result — Savitzky-Golay smoothing and the nominal state/output roll-forward
