@@ -237,8 +237,8 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
     const int nstates = e.xw_chunks * kXorwowStreams;
     if (e.xw_pos != pos)
     {
-      xorwow_init_kernel<<<(nstates + 127) / 128, 128, 0, st>>>(e.seed, start / 8192ULL, e.xw_rounds_per_chunk,
-                                                             e.xw_chunks, e.xw_states_d);
+      xorwow_init_kernel<<<(nstates + 127) / 128, 128, 0, st>>>(e.seed, pos / 8192ULL + e.xw_first_round,
+                                                             e.xw_rounds_per_chunk, e.xw_chunks, e.xw_states_d);
       CUDA_TRY(cudaGetLastError());
     }
     if (e.colored)
@@ -246,9 +246,9 @@ static int gen_draw(mppib_engine& e, int buf, cudaStream_t st, unsigned long lon
                                                                        e.xw_rounds_per_chunk, e.xw_chunks,
                                                                        reinterpret_cast<float2*>(dst), e.coeffs_d, e.C, e.F);
     else
-      xorwow_normal_kernel<false><<<(nstates + 255) / 256, 256, 0, st>>>(e.xw_states_d, e.xw_tables_d, e.xw_jump_d,
-                                                                        e.xw_rounds_per_chunk, e.xw_chunks,
-                                                                        reinterpret_cast<float2*>(dst));
+      xorwow_normal_kernel<false><<<(nstates + 255) / 256, 256, 0, st>>>(
+          e.xw_states_d, e.xw_tables_d, e.xw_jump_d, e.xw_rounds_per_chunk, e.xw_chunks, reinterpret_cast<float2*>(dst),
+          nullptr, 1, 1, e.xw_lead, e.xw_window ? (unsigned long long)count : 0ULL);
     CUDA_TRY(cudaGetLastError());
     e.xw_pos = pos + global_count;
     scaled_in_draw = e.colored;
@@ -996,11 +996,19 @@ int mppib_create(mppib_engine** out, const mppib_desc* desc)
     e->have_plan = true;
   }
 
-  // own XORWOW draw: possible when this rank's slice is a whole number of 8192-normal rounds
+  // own XORWOW draw: possible when a solve's block is a whole number of 8192-normal rounds (the states then sit at the
+  // same place of every block and one fixed jump takes them from solve to solve). A rank slice that starts or ends
+  // inside a round (e.g. 1024 x 100 normals per rank at 8 GPUs) is drawn in WINDOW mode: whole rounds around it, stores
+  // predicated to the slice — the library fallback would re-seed 4096 subsequences on every solve (~200 us).
+  const bool xw_aligned = (e->draw_local % 8192) == 0 && (e->draw_start % 8192ULL) == 0;
   if (!e->nln && !(desc->flags & MPPIB_FLAG_CURAND_HOST_API) && !getenv("MPPIB_CURAND_HOST_API") &&
-      (e->draw_local % 8192) == 0 && (e->draw_start % 8192ULL) == 0 && (e->draw_global % 8192ULL) == 0)
+      (e->draw_global % 8192ULL) == 0 && e->draw_local > 0 && (xw_aligned || !e->colored))
   {
-    const int rounds_local = (int)(e->draw_local / 8192);
+    const unsigned long long w0 = e->draw_start / 8192ULL, w1 = (e->draw_start + e->draw_local + 8191ULL) / 8192ULL;
+    e->xw_window = !xw_aligned;
+    e->xw_first_round = w0;
+    e->xw_lead = (unsigned)(e->draw_start - w0 * 8192ULL);
+    const int rounds_local = (int)(w1 - w0);
     const unsigned long long rounds_global = e->draw_global / 8192ULL;
     int K = 1;
     for (int cand = 1; cand <= 64 && cand <= rounds_local; cand++)

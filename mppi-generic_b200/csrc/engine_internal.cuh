@@ -153,6 +153,9 @@ struct mppib_engine
   unsigned long long prefetch_pos = 0;
   int prefetch_buf = 0;
   int xw_chunks = 0, xw_rounds_per_chunk = 0;
+  unsigned xw_lead = 0;                     // window mode: floats of the first round before this rank's slice
+  unsigned long long xw_first_round = 0;    // first round of the window, relative to the block's position
+  bool xw_window = false;                   // the slice starts / ends inside an 8192-normal round
   uint32_t xw_jump_d = 0;
   // normals per generateSamples call: Gaussian N*T*C (gaussian.cu:380-381), ColoredNoise 2*N*C*(T+1) (colored_noise.cu:343)
   unsigned long long draw_global = 0;  // whole job

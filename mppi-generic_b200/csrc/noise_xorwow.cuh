@@ -136,7 +136,9 @@ template <bool SPECTRUM>
 __global__ void __launch_bounds__(256)
     xorwow_normal_kernel(uint32_t* __restrict__ states, const uint32_t* __restrict__ jump_tables, uint32_t jump_d,
                          int rounds_per_chunk, int nchunks, float2* __restrict__ out /* pairs of this rank's slice */,
-                         const float* __restrict__ coeffs = nullptr, int C = 1, int F = 1)
+                         const float* __restrict__ coeffs = nullptr, int C = 1, int F = 1,
+                         unsigned lead = 0u /* window mode: floats of the first round that precede the slice */,
+                         unsigned long long count = 0ULL /* window mode (count != 0): floats in the slice */)
 {
   __shared__ uint32_t tab[kXorwowNibbles * 16 * 5];
   for (int i = threadIdx.x; i < kXorwowNibbles * 16 * 5; i += blockDim.x)
@@ -197,7 +199,19 @@ __global__ void __launch_bounds__(256)
         if (c >= C)
           c -= C;
       }
-      dst[(size_t)r * kXorwowStreams] = z;
+      if (count == 0ULL)
+        dst[(size_t)r * kXorwowStreams] = z;
+      else
+      {
+        // window mode: the states cover WHOLE 8192-normal rounds around a rank slice that starts / ends inside a round
+        // (rank r of W keeps floats [lead, lead + count) of the window); `out` points at the slice, not at the window
+        const unsigned long long fi = 2ULL * (((unsigned long long)j * rounds_per_chunk + r) * kXorwowStreams + k);
+        float* of = reinterpret_cast<float*>(out);
+        if (fi >= lead && fi < lead + count)
+          of[fi - lead] = z.x;
+        if (fi + 1 >= lead && fi + 1 < lead + count)
+          of[fi + 1 - lead] = z.y;
+      }
     }
   }
   __syncthreads();

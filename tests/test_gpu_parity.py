@@ -158,6 +158,37 @@ def test_rank_slices_tile_the_global_stream():
     e.close()
 
 
+def test_own_draw_window_mode_for_rank_slices_inside_a_round():
+    """Cartpole 8192 x 100 on 8 ranks: a rank keeps 102400 normals = 12.5 rounds of 8192, so its slice starts or ends inside a
+    round. The engine's own generator draws whole rounds around it with predicated stores (window mode, engine.cu); over
+    several consecutive blocks (the states jump from solve to solve) every rank's slice must be bit-identical to the
+    corresponding part of the single-GPU stream, which is itself bit-identical to curandGenerateNormal."""
+    w = W.cartpole(8192, 100)
+    world = 8
+    def blocks(e):
+        out = []
+        for _ in range(3):  # consecutive blocks: the states JUMP from block to block
+            e.draw_noise()
+            out.append(e.get_noise().copy())
+        e.burn_draws(2)      # re-positioning: the states are re-initialised at a later block
+        e.draw_noise()
+        out.append(e.get_noise().copy())
+        return out
+
+    full = w.make_engine(flags=H.FLAG_NO_PREFETCH)
+    refs = blocks(full)
+    full.close()
+    assert not np.array_equal(refs[0], refs[1]) and not np.array_equal(refs[2], refs[3])
+    nl = w.N // world
+    for r in (0, 1, 4, 7):
+        e = H.Engine(w.dyn, w.cost, w.sampler, w.N, w.T, 1, rank=r, world_size=world, flags=H.FLAG_NO_PREFETCH)
+        e.seed(w.seed, 0)
+        assert e.rng_info()["own_kernel"], "the window mode keeps the engine's own generator on unaligned slices"
+        for k, (got, ref) in enumerate(zip(blocks(e), refs)):
+            np.testing.assert_array_equal(got, ref[r * nl:(r + 1) * nl], err_msg=f"rank {r} block {k}")
+        e.close()
+
+
 def test_noise_prefetch_is_transparent():
     """The draw for solve s+1 runs one solve ahead on a side stream; results must be bit-identical to drawing inline,
     through sequences of solves, async pipelines, re-seeding, burn_draws and interleaved hook calls."""
