@@ -548,6 +548,8 @@ int mppib_load_plugin(const char* path)
   const int rc = init();
   if (rc == MPPIB_OK)
     loaded.push_back(h);
+  else
+    dlclose(h);  // e.g. built against another revision: a rebuilt file at the same path must be mapped afresh
   return rc;
 }
 
