@@ -88,3 +88,48 @@ def test_quadrotor_example_flies_to_the_goal_on_the_gpu():
     p = subprocess.run([QUAD_EXE], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "distance to goal after 250 steps" in p.stdout
+
+
+# ---- the reference's instantiation libraries (src/controllers/*/: SURVEY §8 f4) ------------------------------------------
+INST_EXE = os.path.join(ROOT, "tests", "cpp", "instantiation_user.bin")
+
+
+def _build_instantiation_user():
+    lib_dir = os.path.join(ROOT, "mppi-generic_b200")
+    subprocess.check_call(["bash", os.path.join(ROOT, "src", "controllers", "build.sh")])
+    obj = INST_EXE + ".o"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-DMPPIB_USE_INSTANTIATION_LIBRARY", "-I", os.path.join(ROOT, "include"),
+                           "-c", os.path.join(ROOT, "tests", "cpp", "instantiation_user.cpp"), "-o", obj])
+    subprocess.check_call(["g++", obj, "-o", INST_EXE, "-L", lib_dir, "-l:libmppi_b200_controllers.so", "-l:libmppi_b200.so",
+                           "-Wl,-rpath," + lib_dir])
+    return obj
+
+
+def test_instantiation_library_provides_the_prebuilt_controllers():
+    """A translation unit that includes <mppi/instantiations/cartpole_mppi/cartpole_mppi.cuh> with
+    MPPIB_USE_INSTANTIATION_LIBRARY does not instantiate the controller: computeControl is an undefined symbol of the object
+    and a defined one of libmppi_b200_controllers.so, for every class the reference's src/controllers/*/ pre-build."""
+    obj = _build_instantiation_user()
+    und = subprocess.run(["nm", "-C", "--undefined-only", obj], capture_output=True, text=True, check=True).stdout
+    assert "VanillaMPPIController<CartpoleDynamics, CartpoleQuadraticCost, DDPFeedback<CartpoleDynamics, 100>, 100, 2048" in und
+    assert "::computeControl(" in und
+    lib = os.path.join(ROOT, "mppi-generic_b200", "libmppi_b200_controllers.so")
+    defined = subprocess.run(["nm", "-DC", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    for needle in ("VanillaMPPIController<CartpoleDynamics, CartpoleQuadraticCost, DDPFeedback<CartpoleDynamics, 100>, 100, 2048",
+                   "VanillaMPPIController<CartpoleDynamics, CartpoleQuadraticCost, DDPFeedback<CartpoleDynamics, 100>, 100, 256",
+                   "VanillaMPPIController<CartpoleDynamics, CartpoleQuadraticCost, DDPFeedback<CartpoleDynamics, 150>, 150, 512",
+                   "VanillaMPPIController<DoubleIntegratorDynamics, DoubleIntegratorCircleCost, DDPFeedback<DoubleIntegratorDynamics, 50>, 50, 1024",
+                   "TubeMPPIController<DoubleIntegratorDynamics, DoubleIntegratorCircleCost, DDPFeedback<DoubleIntegratorDynamics, 100>, 100, 1024",
+                   "VanillaMPPIController<QuadrotorDynamics, QuadrotorQuadraticCost, DDPFeedback<QuadrotorDynamics, 100>, 100, 512",
+                   "VanillaMPPIController<NeuralNetModel<7, 2, 3>, ARStandardCost, DDPFeedback<NeuralNetModel<7, 2, 3>, 150>, 150, 1920"):
+        assert any(needle in ln and "::computeControl(" in ln for ln in defined.splitlines()), needle
+    p = subprocess.run([INST_EXE], capture_output=True, text=True, timeout=600)
+    if p.returncode != 0:  # no GPU here: the host layer reports it like the reference's HANDLE_ERROR (message + exit)
+        assert "no CUDA device" in (p.stdout + p.stderr), p.stdout[-1000:] + p.stderr[-1000:]
+
+
+@pytest.mark.gpu
+def test_instantiation_library_user_runs_on_the_gpu():
+    _build_instantiation_user()
+    p = subprocess.run([INST_EXE], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
