@@ -9,16 +9,7 @@
 
 #include "../cost.hpp"
 
-#if !defined(__VECTOR_TYPES_H__) && !defined(__CUDACC__)
-struct float3
-{
-  float x, y, z;
-};
-struct float4
-{
-  float x, y, z, w;
-};
-#endif
+// float3 / float4 stand-ins: utils/common.hpp (included through cost.hpp)
 
 struct ARStandardCostParams : public CostParams<2>
 {

@@ -10,11 +10,13 @@
  */
 #pragma once
 #include <cmath>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../dynamics.hpp"
+#include "../../utils/texture_helpers/two_d_texture_helper.hpp"
 
 struct RacerDubinsElevationParams
 {
@@ -259,13 +261,22 @@ public:
   }
   int pushModelBlobs(mppib_engine* e) const
   {
-    return mppib_set_blob(e, MPPIB_BLOB_LSTM_WEIGHTS, theta_.data(), theta_.size() * sizeof(float));
+    const int rc = mppib_set_blob(e, MPPIB_BLOB_LSTM_WEIGHTS, theta_.data(), theta_.size() * sizeof(float));
+    if (rc != MPPIB_OK || !tex_helper_->hasData())
+      return rc;
+    const std::vector<unsigned char>& m = tex_helper_->blob();  // TwoDTextureHelper::copyToDevice
+    return mppib_set_blob(e, MPPIB_BLOB_ELEVATION_MAP, m.data(), m.size());
+  }
+  // racer_dubins_elevation.cuh: getTextureHelper() — map 0 is the elevation map computeStaticSettling samples
+  TwoDTextureHelper<float>* getTextureHelper()
+  {
+    return tex_helper_.get();
   }
   int hostOutputTrajectory(const float* x0, const float* u, int T, float dt, float* states, float* outputs) const
   {
     auto b = this->blob();
     std::vector<float> h(hidden_dim_), c(hidden_dim_);
-    mppib_host_lstm net{ theta_.data(), hidden_dim_, head_hidden_, h.data(), c.data() };
+    mppib_host_lstm net{ theta_.data(), hidden_dim_, head_hidden_, h.data(), c.data(), tex_helper_->header() };
     return mppib_host_output_trajectory_lstm(&b, &net, x0, u, T, dt, states, outputs);
   }
   // host step with the LSTM state kept inside the object, like the reference's host twin
@@ -291,7 +302,7 @@ public:
       x[i] = state(i);
     u[0] = control(0), u[1] = control(1);
     auto b = this->blob();
-    mppib_host_lstm net{ theta_.data(), hidden_dim_, head_hidden_, hidden_.data(), cell_.data() };
+    mppib_host_lstm net{ theta_.data(), hidden_dim_, head_hidden_, hidden_.data(), cell_.data(), tex_helper_->header() };
     MPPIB_HANDLE(mppib_host_step_lstm(&b, &net, x, u, dt, xn, xd, y));
     for (int i = 0; i < 19; i++)
     {
@@ -306,4 +317,5 @@ private:
   DYN_PARAMS_T params_;
   int hidden_dim_ = 4, head_hidden_ = 20;
   std::vector<float> theta_, hidden_, cell_;
+  std::shared_ptr<TwoDTextureHelper<float>> tex_helper_ = std::make_shared<TwoDTextureHelper<float>>(1);
 };

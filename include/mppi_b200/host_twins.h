@@ -37,7 +37,14 @@ typedef struct mppib_host_lstm
   int head_hidden;    /* L1 */
   float* hidden;      /* [H] */
   float* cell;        /* [H] */
+  const mppib_elevation_map_header* map; /* header + width * height floats (params.h), or NULL = flat ground */
 } mppib_host_lstm;
+/* TwoDTextureHelper<float>::queryTextureAtWorldPose on the host (texture_helper.cu:94-134,274-280 + two_d_texture_helper.cu:
+ * 151-243: clamp addressing, bilinear filter) — what the RACER models' computeStaticSettling samples. */
+float mppib_host_elevation_at_world_pose(const mppib_elevation_map_header* map, float x, float y, float z);
+/* RACER::computeStaticSettling (racer_dubins.cu:359-434): roll / pitch in: current, out: settled; returns the height. */
+float mppib_host_static_settling(const mppib_elevation_map_header* map, float yaw, float x, float y, float* roll,
+                                 float* pitch);
 int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x, const float* u, float dt,
                          float* x_next, float* xdot, float* y);
 int mppib_host_output_trajectory_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x0,

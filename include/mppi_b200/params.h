@@ -122,6 +122,20 @@ typedef struct mppib_racer_lstm_dyn_params
   float Q_omega_steering;          /* 0 */
 } mppib_racer_lstm_dyn_params;
 
+/* Elevation map of the RACER models (utils/texture_helpers/texture_helper.cuh:11-56 TextureParams + two_d_texture_helper.cu):
+ * MPPIB_BLOB_ELEVATION_MAP = this header followed by width * height floats, row-major (value at row i, column j =
+ * data[i * width + j]: TwoDTextureHelper's cpu_values_ layout). Clamp addressing, bilinear filtering, normalised
+ * coordinates (the TextureParams defaults). `use` is enableTexture / checkTextureUse (texture_helper.cu): with use == 0 the
+ * model settles on flat ground (racer_dubins.cu:427-432). */
+typedef struct mppib_elevation_map_header
+{
+  int width, height;   /* cudaExtent: width = x cells, height = y cells (both >= 2) */
+  float origin[3];     /* TextureParams::origin */
+  float rotations[9];  /* TextureParams::rotations[3], row-major: map = R (world - origin) */
+  float resolution[3]; /* metres per cell */
+  int use;
+} mppib_elevation_map_header;
+
 /* QuadrotorDynamics (dynamics/quadrotor/quadrotor_dynamics.cuh:9-63). State POS(3) VEL(3) QUAT_W..Z(4) ANG_VEL(3);
  * controls ANG_RATE_X/Y/Z, THRUST. The default constructor's thrust range [0, 36] and zero_control[3] = GRAVITY
  * (quadrotor_dynamics.cu:11-19) are set by the host-side mirror, they are not part of the params struct. */

@@ -4,6 +4,7 @@
  * include/mppi/utils/gpu_err_chk.cuh:32-40 (print, then exit) applied to C-ABI status codes.
  */
 #pragma once
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -26,6 +27,26 @@ struct dim3
   }
 };
 typedef struct CUstream_st* cudaStream_t;
+struct float3
+{
+  float x, y, z;
+};
+struct float4
+{
+  float x, y, z, w;
+};
+inline float3 make_float3(float x, float y, float z)
+{
+  return float3{ x, y, z };
+}
+struct cudaExtent
+{
+  size_t width, height, depth;
+};
+inline cudaExtent make_cudaExtent(size_t w, size_t h, size_t d)
+{
+  return cudaExtent{ w, h, d };
+}
 #endif
 
 namespace mppi_b200

@@ -1091,6 +1091,7 @@ int mppib_destroy(mppib_engine* e)
     cudaFreeArray(e->costmap_array);
   cudaFree(e->nn_theta_d);
   cudaFree(e->lstm_theta_d);
+  cudaFree(e->elev_d);
   cudaFree(e->fb_gains_d);
   cudaFree(e->eval_states_d);
   cudaFree(e->eval_strides_d);
@@ -1161,7 +1162,8 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
   CUDA_TRY(cudaSetDevice(e->desc.device));
   // weights, the costmap texture and the LSTM blob are read by kernels of a solve still in flight (mppib_solve_async):
   // replacing them under it would be a use-after-free
-  if (e->pending != 0 && (which == MPPIB_BLOB_NN_WEIGHTS || which == MPPIB_BLOB_LSTM_WEIGHTS || which == MPPIB_BLOB_COSTMAP))
+  if (e->pending != 0 && (which == MPPIB_BLOB_NN_WEIGHTS || which == MPPIB_BLOB_LSTM_WEIGHTS || which == MPPIB_BLOB_COSTMAP ||
+                          which == MPPIB_BLOB_ELEVATION_MAP))
     return fail(MPPIB_ERR_STATE, "mppib_set_blob(%d) while a solve is pending: call mppib_solve_wait first", which);
   switch (which)
   {
@@ -1279,6 +1281,44 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
       CUDA_TRY(cudaMemcpyAsync(e->lstm_theta_d, host, nbytes, cudaMemcpyHostToDevice, e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
       e->have_lstm = true;
+      return MPPIB_OK;
+    }
+    case MPPIB_BLOB_ELEVATION_MAP:
+    {
+      // TwoDTextureHelper<float>::updateTexture / updateOrigin / updateRotation / updateResolution / enableTexture +
+      // copyToDevice of the RACER models' map 0 (racer_dubins_elevation.cuh: tex_helper_), in one blob
+      if (e->desc.dynamics_id != MPPIB_DYN_RACER_LSTM)
+        return fail(MPPIB_ERR_INVALID_ARG, "elevation map given to a dynamics without one");
+      if (nbytes < sizeof(mppib_elevation_map_header))
+        return fail(MPPIB_ERR_INVALID_ARG, "elevation map: %zu bytes is smaller than its header", nbytes);
+      mppib_elevation_map_header h;
+      memcpy(&h, host, sizeof(h));
+      if (h.width < 2 || h.height < 2 || h.width > 16384 || h.height > 16384)
+        return fail(MPPIB_ERR_INVALID_ARG, "elevation map: extent %d x %d (need 2 .. 16384 cells per side)", h.width, h.height);
+      const size_t cells = (size_t)h.width * h.height;
+      if (nbytes != sizeof(h) + cells * sizeof(float))
+        return fail(MPPIB_ERR_INVALID_ARG, "elevation map: got %zu bytes, expected %zu (header + %d x %d floats)", nbytes,
+                    sizeof(h) + cells * sizeof(float), h.width, h.height);
+      for (int i = 0; i < 3; i++)
+        if (!std::isfinite(h.origin[i]) || !std::isfinite(h.resolution[i]) || h.resolution[i] == 0.0f)
+          return fail(MPPIB_ERR_INVALID_ARG, "elevation map: origin / resolution component %d is not usable", i);
+      for (int i = 0; i < 9; i++)
+        if (!std::isfinite(h.rotations[i]))
+          return fail(MPPIB_ERR_INVALID_ARG, "elevation map: rotation entry %d is not finite", i);
+      // the values themselves may be NaN (unobserved cells): the model's own isfinite guards handle that (racer_dubins.cu:414-425)
+      if (cells > e->elev_capacity)
+      {
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        cudaFree(e->elev_d);
+        e->elev_d = nullptr;
+        e->elev_capacity = 0;
+        CUDA_TRY(cudaMalloc(&e->elev_d, cells * sizeof(float)));
+        e->elev_capacity = cells;
+      }
+      CUDA_TRY(cudaMemcpyAsync(e->elev_d, (const char*)host + sizeof(h), cells * sizeof(float), cudaMemcpyHostToDevice,
+                               e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      e->elev_hdr = h;
       return MPPIB_OK;
     }
     case MPPIB_BLOB_COSTMAP:

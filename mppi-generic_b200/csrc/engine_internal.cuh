@@ -124,6 +124,9 @@ struct mppib_engine
   float* nn_theta_d = nullptr;
   float* lstm_theta_d = nullptr;  // MPPIB_BLOB_LSTM_WEIGHTS
   bool have_lstm = false;
+  float* elev_d = nullptr;               // MPPIB_BLOB_ELEVATION_MAP: width * height floats, row-major
+  size_t elev_capacity = 0;              // floats allocated
+  mppib_elevation_map_header elev_hdr{};  // use == 0 until a map is set
   cudaArray_t costmap_array = nullptr;
   cudaTextureObject_t costmap_tex = 0;
 
@@ -253,6 +256,10 @@ struct AuxFill<plugins::RacerLSTMDynamics::Aux>
     a.theta_d = e.lstm_theta_d;
     a.H = e.desc.model_dims[0];
     a.L1 = e.desc.model_dims[1];
+    a.elev.data = e.elev_d;
+    a.elev.hdr = e.elev_hdr;
+    if (!e.elev_d)
+      a.elev.hdr.use = 0;
   }
 };
 template <>

@@ -342,6 +342,72 @@ __attribute__((target_clones("arch=x86-64-v3", "default"))) float lstm_head_forw
   return out + hd[L1 * IN + 2 * L1];
 }
 
+// TextureHelper::worldPoseToTexCoord (texture_helper.cu:94-134) + TwoDTextureHelper::queryTextureCPU
+// (two_d_texture_helper.cu:151-243) for the TextureParams defaults: clamp addressing, bilinear filter
+float elevation_at_world_pose(const mppib_elevation_map_header* h, float wx, float wy, float wz)
+{
+  const float* data = reinterpret_cast<const float*>(h + 1);
+  const float dx = wx - h->origin[0], dy = wy - h->origin[1], dz = wz - h->origin[2];
+  const float mx = h->rotations[0] * dx + h->rotations[1] * dy + h->rotations[2] * dz;
+  const float my = h->rotations[3] * dx + h->rotations[4] * dy + h->rotations[5] * dz;
+  float qx = ((mx / h->resolution[0]) / (float)h->width) * (float)h->width - 0.5f;
+  float qy = ((my / h->resolution[1]) / (float)h->height) * (float)h->height - 0.5f;
+  if (qx > (float)(h->width - 1))
+    qx = (float)(h->width - 1);
+  else if (qx <= 0.0f)
+    qx = 0.0f;
+  if (qy > (float)(h->height - 1))
+    qy = (float)(h->height - 1);
+  else if (qy <= 0.0f)
+    qy = 0.0f;
+  if (std::isnan(qx) || std::isnan(qy))
+    return NAN;
+  const int x0 = std::min((int)std::floor(qx), h->width - 2), y0 = std::min((int)std::floor(qy), h->height - 2);
+  const int w = h->width;
+  const float q11 = data[(size_t)y0 * w + x0], q12 = data[(size_t)y0 * w + x0 + 1];
+  const float q21 = data[(size_t)(y0 + 1) * w + x0], q22 = data[(size_t)(y0 + 1) * w + x0 + 1];
+  const float lo = q11 * ((float)(x0 + 1) - qx) + q12 * (qx - (float)x0);
+  const float hi = q21 * ((float)(x0 + 1) - qx) + q22 * (qx - (float)x0);
+  return lo * ((float)(y0 + 1) - qy) + hi * (qy - (float)y0);
+}
+// RACER::computeStaticSettling, racer_dubins.cu:359-434 (host branch of math::Euler2DCM_NWU: sincosf without normalisation)
+float static_settling(const mppib_elevation_map_header* map, float yaw, float x, float y, float& roll, float& pitch)
+{
+  if (!map || !map->use)
+  {
+    roll = 0.0f;
+    pitch = 0.0f;
+    return 0.0f;
+  }
+  float sr, cr, sp, cp, sy, cy;
+  sincosf(roll, &sr, &cr);
+  sincosf(pitch, &sp, &cp);
+  sincosf(yaw, &sy, &cy);
+  const float M00 = cp * cy, M01 = sr * sp * cy - cr * sy, M10 = cp * sy, M11 = sr * sp * sy + cr * cy, M20 = -sp,
+              M21 = sr * cp;
+  float hgt[4];
+  for (int k = 0; k < 4; k++)
+  {  // front left, front right, rear left, rear right (:364-367)
+    const float ox = (k < 2) ? 2.981f : 0.0f, oy = (k & 1) ? -0.737f : 0.737f;
+    hgt[k] = elevation_at_world_pose(map, M00 * ox + M01 * oy + x, M10 * ox + M11 * oy + y, M20 * ox + M21 * oy + 0.0f);
+  }
+  const float fl = hgt[0], fr = hgt[1], rl = hgt[2], rr = hgt[3];
+  const float front_diff = fmaxf(fminf(fl - fr, 0.736f * 2.0f), -0.736f * 2.0f);
+  const float rear_diff = fmaxf(fminf(rl - rr, 0.736f * 2.0f), -0.736f * 2.0f);
+  roll = (asinf(front_diff / (0.737f * 2.0f)) + asinf(rear_diff / (0.737f * 2.0f))) / 2.0f;
+  const float left_diff = fmaxf(fminf(rl - fl, 2.98f), -2.98f);
+  const float right_diff = fmaxf(fminf(rr - fr, 2.98f), -2.98f);
+  pitch = (asinf(left_diff / 2.981f) + asinf(right_diff / 2.981f)) / 2.0f;
+  float height = (rl + rr) / 2.0f;
+  if (!std::isfinite(roll) || fabsf(roll) > (float)M_PI)
+    roll = 2.0f * (float)M_PI;
+  if (!std::isfinite(pitch) || fabsf(pitch) > (float)M_PI)
+    pitch = 2.0f * (float)M_PI;
+  if (!std::isfinite(height))
+    height = 0.0f;
+  return height;
+}
+
 // racer_dubins_elevation_lstm_steering.cu:90-118 (host step) and the host methods it calls
 void racer_step(const mppib_racer_lstm_dyn_params& p, const mppib_host_lstm* net, const float* x, const float* u,
                 float dt, float* xn, float* xd, float* y)
@@ -445,10 +511,13 @@ void racer_step(const mppib_racer_lstm_dyn_params& p, const mppib_host_lstm* net
     o[0] = Sg[2][2], o[1] = Sg[3][3], o[2] = Sg[1][1], o[3] = Sg[0][0], o[4] = Sg[3][2], o[5] = Sg[2][1], o[6] = Sg[2][0],
     o[7] = Sg[3][1], o[8] = Sg[3][0], o[9] = Sg[1][0];
   }
-  xn[R_ROLL] = 0.0f;  // computeStaticSettling without an elevation map, racer_dubins.cu:427-432
-  xn[R_PITCH] = 0.0f;
+  // computeStaticSettling (lstm_steering.cu:105-112): current roll / pitch, next yaw and position; flat without a map
+  float roll = x[R_ROLL], pitch = x[R_PITCH];
+  const float height = static_settling(net->map, xn[R_YAW], xn[R_POS_X], xn[R_POS_Y], roll, pitch);
+  xn[R_ROLL] = roll;
+  xn[R_PITCH] = pitch;
   // setOutputs, racer_dubins_elevation.cu:69-227 (output order racer_dubins.cuh:35-76)
-  y[0] = xn[R_VEL_X], y[1] = 0.0f, y[2] = xn[R_POS_X], y[3] = xn[R_POS_Y], y[4] = 0.0f, y[5] = xn[R_YAW];
+  y[0] = xn[R_VEL_X], y[1] = 0.0f, y[2] = xn[R_POS_X], y[3] = xn[R_POS_Y], y[4] = height, y[5] = xn[R_YAW];
   y[6] = xn[R_ROLL], y[7] = xn[R_PITCH], y[8] = xn[R_STEER_ANGLE], y[9] = xn[R_STEER_ANGLE_RATE];
   y[10] = y[11] = y[12] = NAN;
   y[13] = xd[R_VEL_X], y[14] = 0.0f, y[15] = xd[R_YAW], y[16] = fabsf(xn[R_VEL_X]);
@@ -644,6 +713,21 @@ int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float
                                                                    u, T, dt, states, outputs);
   }
   return MPPIB_ERR_UNSUPPORTED;
+}
+
+float mppib_host_elevation_at_world_pose(const mppib_elevation_map_header* map, float x, float y, float z)
+{
+  return map ? elevation_at_world_pose(map, x, y, z) : 0.0f;
+}
+float mppib_host_static_settling(const mppib_elevation_map_header* map, float yaw, float x, float y, float* roll, float* pitch)
+{
+  float r = roll ? *roll : 0.0f, p = pitch ? *pitch : 0.0f;
+  const float h = static_settling(map, yaw, x, y, r, p);
+  if (roll)
+    *roll = r;
+  if (pitch)
+    *pitch = p;
+  return h;
 }
 
 int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x, const float* u, float dt,

@@ -511,6 +511,82 @@ struct AutorallyNNMmaDynamics : public Dynamics<AutorallyNNMmaDynamics<SPW>, mpp
 // so one broadcast LDS.128 brings the four gate weights of a (row, input) pair and every accumulation runs in the
 // reference's order (inputs, then hidden, then bias; lstm_helper.cu:411-431). The elevation map is not built: flat
 // terrain (TwoDTextureHelper::checkTextureUse false => roll = pitch = height = 0, racer_dubins.cu:427-432).
+// The RACER models' elevation map: TwoDTextureHelper<float> map 0 (utils/texture_helpers/). The reference samples a CUDA
+// texture (clamp, bilinear, normalised coordinates) on the device and interpolates in software on the host
+// (two_d_texture_helper.cu:151-243 queryTextureCPU); the hardware filter carries 8-bit weights, so the two disagree by up to
+// 2^-9 of a cell's height step. Here the device evaluates the HOST formula in FP32 from four plain loads (read-only cache):
+// device, host twin and oracle then agree to rounding, and a step costs 16 cached loads instead of 4 texture fetches.
+struct ElevationMap
+{
+  const float* data;  // [height][width]
+  mppib_elevation_map_header hdr;
+};
+// TextureHelper::worldPoseToTexCoord (texture_helper.cu:94-134) + TwoDTextureHelper::queryTextureCPU (:151-243)
+__device__ __forceinline__ float elevation_at_world_pose(const ElevationMap& m, float wx, float wy, float wz)
+{
+  const mppib_elevation_map_header& h = m.hdr;
+  const float dx = wx - h.origin[0], dy = wy - h.origin[1], dz = wz - h.origin[2];
+  const float mx = h.rotations[0] * dx + h.rotations[1] * dy + h.rotations[2] * dz;
+  const float my = h.rotations[3] * dx + h.rotations[4] * dy + h.rotations[5] * dz;
+  // [m] -> [cells] -> normalised -> array index, minus half a cell (the value sits at the cell centre)
+  float qx = ((mx / h.resolution[0]) / (float)h.width) * (float)h.width - 0.5f;
+  float qy = ((my / h.resolution[1]) / (float)h.height) * (float)h.height - 0.5f;
+  const float xmax = (float)(h.width - 1), ymax = (float)(h.height - 1);
+  qx = qx > xmax ? xmax : (qx <= 0.0f ? 0.0f : qx);  // cudaAddressModeClamp (a NaN coordinate stays NaN -> NaN height)
+  qy = qy > ymax ? ymax : (qy <= 0.0f ? 0.0f : qy);
+  if (!(qx == qx) || !(qy == qy))
+    return __int_as_float(0x7fc00000);
+  const int x0 = min((int)floorf(qx), h.width - 2), y0 = min((int)floorf(qy), h.height - 2);
+  const float* r0 = m.data + (size_t)y0 * h.width + x0;
+  const float q11 = __ldg(r0), q12 = __ldg(r0 + 1), q21 = __ldg(r0 + h.width), q22 = __ldg(r0 + h.width + 1);
+  const float fx1 = (float)(x0 + 1) - qx, fx0 = qx - (float)x0;  // (x_max - x) / 1, (x - x_min) / 1
+  const float fy1 = (float)(y0 + 1) - qy, fy0 = qy - (float)y0;
+  const float lo = q11 * fx1 + q12 * fx0, hi = q21 * fx1 + q22 * fx0;
+  return lo * fy1 + hi * fy0;
+}
+// RACER::computeStaticSettling (racer_dubins.cu:359-434): wheel contact heights from the map -> roll, pitch, height
+__device__ __forceinline__ void racer_static_settling(const ElevationMap& m, float yaw, float x, float y, float& roll,
+                                                      float& pitch, float& height)
+{
+  height = 0.0f;
+  if (!m.hdr.use)
+  {
+    roll = 0.0f;
+    pitch = 0.0f;
+    return;
+  }
+  // math::Euler2DCM_NWU (math_utils.h:457-482, device branch) with the CURRENT roll / pitch and the NEXT yaw; offsets have z = 0
+  float sr, cr, sp, cp, sy, cy;
+  __sincosf(normalizeAngle(roll), &sr, &cr);
+  __sincosf(normalizeAngle(pitch), &sp, &cp);
+  __sincosf(normalizeAngle(yaw), &sy, &cy);
+  const float M00 = cp * cy, M01 = sr * sp * cy - cr * sy, M10 = cp * sy, M11 = sr * sp * sy + cr * cy, M20 = -sp,
+              M21 = sr * cp;
+  const float L = 2.981f, W = 0.737f;  // wheel base / half track of the vehicle (racer_dubins.cu:364-367)
+  float hgt[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+  {  // front left, front right, rear left, rear right
+    const float ox = (k < 2) ? L : 0.0f, oy = (k & 1) ? -W : W;
+    hgt[k] = elevation_at_world_pose(m, M00 * ox + M01 * oy + x, M10 * ox + M11 * oy + y, M20 * ox + M21 * oy + 0.0f);
+  }
+  const float fl = hgt[0], fr = hgt[1], rl = hgt[2], rr = hgt[3];
+  const float front_diff = fmaxf(fminf(fl - fr, 0.736f * 2.0f), -0.736f * 2.0f);
+  const float rear_diff = fmaxf(fminf(rl - rr, 0.736f * 2.0f), -0.736f * 2.0f);
+  roll = (asinf(front_diff / (0.737f * 2.0f)) + asinf(rear_diff / (0.737f * 2.0f))) / 2.0f;
+  const float left_diff = fmaxf(fminf(rl - fl, 2.98f), -2.98f);
+  const float right_diff = fmaxf(fminf(rr - fr, 2.98f), -2.98f);
+  pitch = (asinf(left_diff / 2.981f) + asinf(right_diff / 2.981f)) / 2.0f;
+  height = (rl + rr) / 2.0f;
+  const float pi = 3.14159265358979323846f;
+  if (!isfinite(roll) || fabsf(roll) > pi)
+    roll = 2.0f * pi;
+  if (!isfinite(pitch) || fabsf(pitch) > pi)
+    pitch = 2.0f * pi;
+  if (!isfinite(height))
+    height = 0.0f;
+}
+
 struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_dyn_params, 19, 2, 28>
 {
   static constexpr int I = MPPIB_RACER_LSTM_INPUT_DIM;
@@ -537,6 +613,7 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
   {
     const float* theta_d;  // MPPIB_BLOB_LSTM_WEIGHTS: LSTM block then head block (params.h)
     int H, L1;
+    ElevationMap elev;     // MPPIB_BLOB_ELEVATION_MAP (hdr.use == 0: flat ground)
   };
   // compile-time fast path: the reference's test architecture (racer_dubins_elevation_lstm_steering_model_test.cu:26-32)
   // keeps h and c in registers and runs fully unrolled; any other (H, L1) takes the run-time loops over shared memory
@@ -841,15 +918,16 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
                                               const float* state, float* next_state, float* state_der,
                                               const float* control, float* output, int t, float dt)
   {
-    stepWith(p, state, next_state, state_der, control, output, dt, [&](const float(&in)[I]) {
+    stepWith(p, aux.elev, state, next_state, state_der, control, output, dt, [&](const float(&in)[I]) {
       return (aux.H == FAST_H && aux.L1 == FAST_L1) ? lstm_forward_ct<FAST_H, FAST_L1>(theta_s, in, carry) :
                                                       lstm_forward(aux, theta_s, in, t);
     });
   }
   // the step with the steering network's evaluation handed in (NET(in) -> head output): shared with the tensor-core form
   template <class NET>
-  __device__ static __forceinline__ void stepWith(const Params& p, const float* state, float* next_state, float* state_der,
-                                                  const float* control, float* output, float dt, NET&& net)
+  __device__ static __forceinline__ void stepWith(const Params& p, const ElevationMap& elev, const float* state,
+                                                  float* next_state, float* state_der, const float* control,
+                                                  float* output, float dt, NET&& net)
   {
     const float vx = state[VEL_X];
     const float linear_brake_slope = 0.2f;
@@ -995,10 +1073,12 @@ struct RacerLSTMDynamics : public Dynamics<RacerLSTMDynamics, mppib_racer_lstm_d
       next_state[UNC_POS_X_Y] = Sa[cm(U_POS_Y, U_POS_X)];
       next_state[UNC_POS_Y] = Sa[cm(U_POS_Y, U_POS_Y)];
     }
-    // static settling without an elevation map (racer_dubins.cu:427-432)
-    output[O_POS_I_Z] = 0.0f;
-    next_state[PITCH] = 0.0f;
-    next_state[ROLL] = 0.0f;
+    // static settling (lstm_steering.cu:105-112 -> racer_dubins.cu:359-434); flat ground without a map (:427-432)
+    float roll = state[ROLL], pitch = state[PITCH], height;
+    racer_static_settling(elev, next_state[YAW], next_state[POS_X], next_state[POS_Y], roll, pitch, height);
+    output[O_POS_I_Z] = height;
+    next_state[PITCH] = pitch;
+    next_state[ROLL] = roll;
     setOutputs(state_der, next_state, output);
   }
 };
@@ -1030,12 +1110,12 @@ struct RacerLSTMMmaDynamics : public Dynamics<RacerLSTMMmaDynamics, mppib_racer_
     Base::setOutputs(x, x, y);  // lstm_steering.cu:128
   }
   // warp-collective: every lane of the warp calls it (the rollout kernels keep out-of-range rows running)
-  __device__ static __forceinline__ void step(const Params& p, const Aux&, float* theta_s, Carry& carry, const float* state,
-                                              float* next_state, float* state_der, const float* control, float* output,
-                                              int /*t*/, float dt)
+  __device__ static __forceinline__ void step(const Params& p, const Aux& aux, float* theta_s, Carry& carry,
+                                              const float* state, float* next_state, float* state_der,
+                                              const float* control, float* output, int /*t*/, float dt)
   {
     float* scratch = theta_s + lstm_mma::kFixedFloats + (threadIdx.x >> 5) * lstm_mma::kScratchPerWarp;
-    Base::stepWith(p, state, next_state, state_der, control, output, dt,
+    Base::stepWith(p, aux.elev, state, next_state, state_der, control, output, dt,
                    [&](const float(&in)[I]) { return lstm_mma::forward(theta_s, scratch, in, carry); });
   }
 };

@@ -28,7 +28,7 @@ FLT_MAX = 3.4028234663852886e38
 DYN_CARTPOLE, DYN_DOUBLE_INTEGRATOR, DYN_AUTORALLY_NN, DYN_RACER_LSTM, DYN_QUADROTOR = 0, 1, 2, 3, 4
 COST_CARTPOLE_QUADRATIC, COST_DI_CIRCLE, COST_AR_STANDARD, COST_RACER_QUADRATIC, COST_QUADROTOR_QUADRATIC = 0, 1, 2, 3, 4
 SAMPLER_GAUSSIAN, SAMPLER_COLORED_NOISE, SAMPLER_NLN = 0, 1, 2
-BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS = range(6)
+BLOB_DYN, BLOB_COST, BLOB_SAMPLER, BLOB_NN_WEIGHTS, BLOB_COSTMAP, BLOB_LSTM_WEIGHTS, BLOB_ELEVATION_MAP = range(7)
 FLAG_WRITEBACK_CONTROLS, FLAG_NO_TMA, FLAG_CURAND_HOST_API, FLAG_NO_PREFETCH, FLAG_NN_TENSOR, FLAG_RMPPI = 1, 2, 4, 8, 16, 32
 FLAG_NN_MMA, FLAG_NN_FFMA2 = 64, 128
 FLAG_NO_WARP_SPEC = 256
@@ -120,7 +120,86 @@ class RacerQuadraticCostParams(C.Structure):
 
 class HostLSTM(C.Structure):
     _fields_ = [("theta", C.c_void_p), ("hidden_dim", C.c_int), ("head_hidden", C.c_int), ("hidden", C.c_void_p),
-                ("cell", C.c_void_p)]
+                ("cell", C.c_void_p), ("map", C.c_void_p)]
+
+
+class ElevationMapHeader(C.Structure):
+    """mppib_elevation_map_header (params.h): TextureParams of the RACER models' map 0."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("origin", C.c_float * 3), ("rotations", C.c_float * 9),
+                ("resolution", C.c_float * 3), ("use", C.c_int)]
+
+
+class TwoDTextureHelper:
+    """Host handle of TwoDTextureHelper<float> (utils/texture_helpers/two_d_texture_helper.cuh) for ONE map, with the
+    reference's method names: setExtent / updateTexture / updateOrigin / updateRotation / updateResolution / enableTexture /
+    disableTexture / checkTextureUse / queryTextureAtWorldPose. The values are kept row-major ([height][width]); blob() is
+    what travels as MPPIB_BLOB_ELEVATION_MAP (copyToDevice happens when the owning model's parameters are pushed)."""
+
+    def __init__(self):
+        self.hdr = ElevationMapHeader()
+        self.hdr.width = self.hdr.height = 0
+        for i, v in enumerate((1, 0, 0, 0, 1, 0, 0, 0, 1)):
+            self.hdr.rotations[i] = v
+        for i in range(3):
+            self.hdr.origin[i], self.hdr.resolution[i] = 0.0, 1.0
+        self.hdr.use = 0
+        self.values: Optional[np.ndarray] = None
+        self._blob: Optional[np.ndarray] = None
+
+    def setExtent(self, index: int, width: int, height: int) -> None:
+        self.hdr.width, self.hdr.height = int(width), int(height)
+        self._blob = None
+
+    def updateTexture(self, index: int, values, column_major: bool = False) -> None:
+        v = _f32(values).reshape(-1)
+        w, h = self.hdr.width, self.hdr.height
+        if v.size != w * h:
+            raise ValueError(f"invalid size to updateTexture {v.size} != {w * h}")  # two_d_texture_helper.cu:27-32
+        self.values = (v.reshape(w, h).T if column_major else v.reshape(h, w)).copy()
+        self._blob = None
+
+    def updateOrigin(self, index: int, origin) -> None:
+        for i in range(3):
+            self.hdr.origin[i] = float(origin[i])
+        self._blob = None
+
+    def updateRotation(self, index: int, rows) -> None:
+        r = _f32(rows).reshape(9)
+        for i in range(9):
+            self.hdr.rotations[i] = float(r[i])
+        self._blob = None
+
+    def updateResolution(self, index: int, resolution) -> None:
+        res = np.broadcast_to(np.asarray(resolution, np.float32), (3,))
+        for i in range(3):
+            self.hdr.resolution[i] = float(res[i])
+        self._blob = None
+
+    def enableTexture(self, index: int = 0) -> None:
+        self.hdr.use = 1
+        self._blob = None
+
+    def disableTexture(self, index: int = 0) -> None:
+        self.hdr.use = 0
+        self._blob = None
+
+    def checkTextureUse(self, index: int = 0) -> bool:
+        return bool(self.hdr.use) and self.values is not None
+
+    def blob(self) -> Optional[np.ndarray]:
+        """Header + values as one byte array (None until a texture has been given)."""
+        if self.values is None:
+            return None
+        if self._blob is None:
+            self._blob = np.concatenate([np.frombuffer(bytes(self.hdr), np.uint8), self.values.reshape(-1).view(np.uint8)])
+        return self._blob
+
+    def queryTextureAtWorldPose(self, index: int, point) -> float:
+        b = self.blob()
+        L = lib()
+        L.mppib_host_elevation_at_world_pose.restype = C.c_float
+        L.mppib_host_elevation_at_world_pose.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+        return float(L.mppib_host_elevation_at_world_pose(b.ctypes.data, float(point[0]), float(point[1]), float(point[2])))
 
 
 class CartpoleCostParams(C.Structure):
@@ -180,6 +259,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
+    "mppib_host_elevation_at_world_pose", "mppib_host_static_settling",
     "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_nominal_trajectory", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
@@ -508,6 +588,33 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
         p.Q_y_f, p.Q_omega_v, p.Q_omega_steering = 0.1, 0.001, 0.0
         self.params = p
         self.lstm_theta = np.zeros(racer_lstm_num_params(self.hidden_dim, self.head_hidden), np.float32)
+        self.tex_helper_ = TwoDTextureHelper()  # racer_dubins_elevation.cuh: tex_helper_ (map 0 = elevation)
+
+    def getTextureHelper(self) -> "TwoDTextureHelper":
+        return self.tex_helper_
+
+    def setElevationMap(self, values, resolution, origin=(0.0, 0.0, 0.0), rotation=None, enable: bool = True) -> None:
+        """Convenience over the texture helper: values [height][width] (row i = y cell, column j = x cell)."""
+        v = _f32(values)
+        t = self.tex_helper_
+        t.setExtent(0, v.shape[1], v.shape[0])
+        t.updateTexture(0, v)
+        t.updateResolution(0, resolution)
+        t.updateOrigin(0, origin)
+        if rotation is not None:
+            t.updateRotation(0, rotation)
+        t.enableTexture(0) if enable else t.disableTexture(0)
+
+    def staticSettling(self, yaw: float, x: float, y: float, roll: float = 0.0, pitch: float = 0.0):
+        """RACER::computeStaticSettling on the host (racer_dubins.cu:359-434): returns (roll, pitch, height)."""
+        L = lib()
+        L.mppib_host_static_settling.restype = C.c_float
+        L.mppib_host_static_settling.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float),
+                                                 C.POINTER(C.c_float)]
+        b = self.tex_helper_.blob()
+        r, p_ = C.c_float(roll), C.c_float(pitch)
+        h = L.mppib_host_static_settling(None if b is None else b.ctypes.data, yaw, x, y, C.byref(r), C.byref(p_))
+        return r.value, p_.value, float(h)
 
     def model_dims(self) -> Sequence[int]:
         return (self.hidden_dim, self.head_hidden)
@@ -570,8 +677,9 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
         self.lstm_theta[base + H:base + 2 * H] = _f32(cell)
 
     def _host_net(self, hidden: np.ndarray, cell: np.ndarray) -> HostLSTM:
+        b = self.tex_helper_.blob()
         return HostLSTM(self.lstm_theta.ctypes.data, self.hidden_dim, self.head_hidden, hidden.ctypes.data,
-                        cell.ctypes.data)
+                        cell.ctypes.data, None if b is None else b.ctypes.data)
 
     def initial_hidden_cell(self):
         H, base = self.hidden_dim, self._lstm_block() - 2 * self.hidden_dim
@@ -866,6 +974,9 @@ class Engine:
         if self.dyn.DYN_ID == DYN_RACER_LSTM:
             w = _f32(self.dyn.lstm_theta)
             _check(L.mppib_set_blob(self._h, BLOB_LSTM_WEIGHTS, _ptr(w), w.nbytes))
+            m = self.dyn.tex_helper_.blob()
+            if m is not None:  # TwoDTextureHelper::copyToDevice
+                _check(L.mppib_set_blob(self._h, BLOB_ELEVATION_MAP, m.ctypes.data, m.nbytes))
         if self.cost.COST_ID == COST_AR_STANDARD:
             if self.cost.costmap is None:
                 raise MppibError(-9, "ARStandardCost has no costmap (call loadTrackData / setCostmap)")

@@ -195,6 +195,41 @@ def set_lstm(theta, hidden_dim: int, head_hidden: int) -> None:
     lib().orc_set_lstm(_p(_lstm_keepalive), hidden_dim, head_hidden)
 
 
+_elev_keepalive = None
+
+
+def set_elevation_map(blob) -> None:
+    """Elevation map of the RACER model: mppib_elevation_map_header + [height][width] floats as one byte array (what
+    host.TwoDTextureHelper.blob() returns), or None = flat ground. Kept by pointer inside the oracle."""
+    global _elev_keepalive
+    if blob is None:
+        _elev_keepalive = None
+        lib().orc_set_elevation_map(None)
+        return
+    _elev_keepalive = np.ascontiguousarray(blob, dtype=np.uint8).copy()
+    lib().orc_set_elevation_map(C.c_void_p(_elev_keepalive.ctypes.data))
+
+
+def elevation_at_world_pose(blob, x: float, y: float, z: float = 0.0) -> float:
+    """TwoDTextureHelper<float>::queryTextureAtWorldPose on the host (texture_helper.cu:94-134, two_d_texture_helper.cu:151-243)."""
+    b = np.ascontiguousarray(blob, dtype=np.uint8)
+    L = lib()
+    L.orc_elevation_at_world_pose.restype = C.c_float
+    L.orc_elevation_at_world_pose.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+    return float(L.orc_elevation_at_world_pose(b.ctypes.data, x, y, z))
+
+
+def static_settling(blob, yaw: float, x: float, y: float, roll: float = 0.0, pitch: float = 0.0):
+    """RACER::computeStaticSettling (racer_dubins.cu:359-434): returns (roll, pitch, height)."""
+    L = lib()
+    L.orc_static_settling.restype = C.c_float
+    L.orc_static_settling.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    b = None if blob is None else np.ascontiguousarray(blob, dtype=np.uint8)
+    r, p = C.c_float(roll), C.c_float(pitch)
+    h = L.orc_static_settling(None if b is None else b.ctypes.data, yaw, x, y, C.byref(r), C.byref(p))
+    return r.value, p.value, float(h)
+
+
 def lstm_forward(lstm_w, input_dim, hidden_dim, head_theta, head_layers, inp, h, c):
     """LSTMHelper::forward(input, output), host path. Returns (output, h_next, c_next)."""
     head_layers = np.ascontiguousarray(head_layers, dtype=np.int32)

@@ -90,7 +90,108 @@ struct Aux
   const float* lstm_theta = nullptr; // LSTM weights then head weights (params.h: MPPIB_BLOB_LSTM_WEIGHTS)
   int lstm_hidden = 0;               // H
   int lstm_head = 0;                 // L1 (head layers {H+4, L1, 1})
+  const mppib_elevation_map_header* elev = nullptr;  // header + [height][width] floats (params.h), or none = flat ground
 };
+
+// TwoDTextureHelper<float> on the host for the TextureParams defaults (texture_helper.cuh:31-55: clamp, linear, normalised):
+// worldPoseToMapPose (texture_helper.cu:94-103), mapPoseToTexCoord (:106-123), queryTextureCPU (two_d_texture_helper.cu:151-243)
+static float elevationAtWorldPose(const mppib_elevation_map_header* t, float wx, float wy, float wz)
+{
+  const float* values = reinterpret_cast<const float*>(t + 1);
+  // world -> map
+  const float diff[3] = { wx - t->origin[0], wy - t->origin[1], wz - t->origin[2] };
+  float map[3];
+  for (int r = 0; r < 3; r++)
+    map[r] = t->rotations[3 * r] * diff[0] + t->rotations[3 * r + 1] * diff[1] + t->rotations[3 * r + 2] * diff[2];
+  // map -> pixels -> normalised
+  float tx = map[0] / t->resolution[0];
+  float ty = map[1] / t->resolution[1];
+  tx /= t->width;
+  ty /= t->height;
+  // queryTextureCPU
+  float qx = tx * t->width, qy = ty * t->height;
+  qx = qx - 0.5f;
+  qy = qy - 0.5f;
+  if (qx > t->width - 1)
+    qx = t->width - 1;
+  else if (qx <= 0.0)
+    qx = 0.0;
+  if (qy > t->height - 1)
+    qy = t->height - 1;
+  else if (qy <= 0.0)
+    qy = 0.0;
+  if (std::isnan(qx) || std::isnan(qy))
+    return NAN;
+  const int w = t->width;
+  const int x_min = std::min((int)std::floor(qx), w - 2), x_max = x_min + 1;
+  const int y_min = std::min((int)std::floor(qy), t->height - 2), y_max = y_min + 1;
+  const float Q_11 = values[y_min * w + x_min], Q_12 = values[y_min * w + x_max];
+  const float Q_21 = values[y_max * w + x_min], Q_22 = values[y_max * w + x_max];
+  const float y_min_interp = Q_11 * ((x_max - qx) / (x_max - x_min)) + Q_12 * ((qx - x_min) / (x_max - x_min));
+  const float y_max_interp = Q_21 * ((x_max - qx) / (x_max - x_min)) + Q_22 * ((qx - x_min) / (x_max - x_min));
+  return y_min_interp * ((y_max - qy) / (y_max - y_min)) + y_max_interp * ((qy - y_min) / (y_max - y_min));
+}
+// RACER::computeStaticSettling, racer_dubins.cu:359-434, with math::bodyOffsetToWorldPoseEuler (math_utils.h:585-597) and the
+// host branch of Euler2DCM_NWU (:457-482)
+static float staticSettling(const mppib_elevation_map_header* t, float yaw, float x, float y, float& roll, float& pitch)
+{
+  float height = 0.0f;
+  if (t && t->use)
+  {
+    float sin_phi, cos_phi, sin_theta, cos_theta, sin_psi, cos_psi;
+    sincosf(roll, &sin_phi, &cos_phi);
+    sincosf(pitch, &sin_theta, &cos_theta);
+    sincosf(yaw, &sin_psi, &cos_psi);
+    float M[3][3];
+    M[0][0] = cos_theta * cos_psi;
+    M[0][1] = sin_phi * sin_theta * cos_psi - cos_phi * sin_psi;
+    M[0][2] = cos_phi * sin_theta * cos_psi + sin_phi * sin_psi;
+    M[1][0] = cos_theta * sin_psi;
+    M[1][1] = sin_phi * sin_theta * sin_psi + cos_phi * cos_psi;
+    M[1][2] = cos_phi * sin_theta * sin_psi - sin_phi * cos_psi;
+    M[2][0] = -sin_theta;
+    M[2][1] = sin_phi * cos_theta;
+    M[2][2] = cos_phi * cos_theta;
+    const float offsets[4][3] = { { 2.981f, 0.737f, 0.0f }, { 2.981f, -0.737f, 0.0f }, { 0.0f, 0.737f, 0.0f },
+                                  { 0.0f, -0.737f, 0.0f } };  // front left, front right, rear left, rear right
+    float h[4];
+    for (int k = 0; k < 4; k++)
+    {
+      float w[3];
+      for (int r = 0; r < 3; r++)
+        w[r] = M[r][0] * offsets[k][0] + M[r][1] * offsets[k][1] + M[r][2] * offsets[k][2];
+      h[k] = elevationAtWorldPose(t, w[0] + x, w[1] + y, w[2] + 0.0f);
+    }
+    float front_diff = h[0] - h[1];
+    front_diff = fmaxf(fminf(front_diff, 0.736f * 2.0f), -0.736f * 2.0f);
+    float rear_diff = h[2] - h[3];
+    rear_diff = fmaxf(fminf(rear_diff, 0.736f * 2.0f), -0.736f * 2.0f);
+    const float front_roll = asinf(front_diff / (0.737f * 2.0f));
+    const float rear_roll = asinf(rear_diff / (0.737f * 2.0f));
+    roll = (front_roll + rear_roll) / 2.0f;
+    float left_diff = h[2] - h[0];
+    left_diff = fmaxf(fminf(left_diff, 2.98f), -2.98f);
+    float right_diff = h[3] - h[1];
+    right_diff = fmaxf(fminf(right_diff, 2.98f), -2.98f);
+    const float left_pitch = asinf(left_diff / 2.981f);
+    const float right_pitch = asinf(right_diff / 2.981f);
+    pitch = (left_pitch + right_pitch) / 2.0f;
+    height = (h[2] + h[3]) / 2.0f;
+    if (!std::isfinite(roll) || fabsf(roll) > (float)M_PI)
+      roll = 2.0f * (float)M_PI;
+    if (!std::isfinite(pitch) || fabsf(pitch) > (float)M_PI)
+      pitch = 2.0f * (float)M_PI;
+    if (!std::isfinite(height))
+      height = 0.0f;
+  }
+  else
+  {
+    roll = 0.0f;
+    pitch = 0.0f;
+    height = 0.0f;
+  }
+  return height;
+}
 
 // models without recurrent state carry nothing from step to step
 struct NoCarry
@@ -444,10 +545,11 @@ struct RacerLSTM
       next_state[UNC_POS_X_Y] = Sa[cm(U_POS_Y, U_POS_X)];
       next_state[UNC_POS_Y] = Sa[cm(U_POS_Y, U_POS_Y)];
     }
-    // --- static settling without an elevation map (racer_dubins.cu:427-432): roll = pitch = height = 0
-    output[O_POS_I_Z] = 0.0f;
-    next_state[PITCH] = 0.0f;
-    next_state[ROLL] = 0.0f;
+    // --- static settling (lstm_steering.cu:105-112 -> racer_dubins.cu:359-434); without a map roll = pitch = height = 0
+    float roll = state[ROLL], pitch = state[PITCH];
+    output[O_POS_I_Z] = staticSettling(aux.elev, next_state[YAW], next_state[POS_X], next_state[POS_Y], roll, pitch);
+    next_state[PITCH] = pitch;
+    next_state[ROLL] = roll;
     // --- setOutputs, racer_dubins_elevation.cu:69-227
     output[O_VEL_B_X] = next_state[VEL_X];
     output[O_VEL_B_Y] = 0.0f;
@@ -1470,8 +1572,22 @@ void orc_set_lstm(const float* theta, int hidden_dim, int head_hidden)
   g_lstm.lstm_hidden = hidden_dim;
   g_lstm.lstm_head = head_hidden;
 }
+// elevation map of the RACER model (mppib_elevation_map_header + values, kept by pointer; nullptr = flat ground)
+void orc_set_elevation_map(const void* blob)
+{
+  g_lstm.elev = static_cast<const mppib_elevation_map_header*>(blob);
+}
+float orc_elevation_at_world_pose(const void* blob, float x, float y, float z)
+{
+  return orc::elevationAtWorldPose(static_cast<const mppib_elevation_map_header*>(blob), x, y, z);
+}
+float orc_static_settling(const void* blob, float yaw, float x, float y, float* roll, float* pitch)
+{
+  return orc::staticSettling(static_cast<const mppib_elevation_map_header*>(blob), yaw, x, y, *roll, *pitch);
+}
 static void fill_lstm(orc::Aux& aux)
 {
+  aux.elev = g_lstm.elev;
   aux.lstm_theta = g_lstm.lstm_theta;
   aux.lstm_hidden = g_lstm.lstm_hidden;
   aux.lstm_head = g_lstm.lstm_head;

@@ -133,3 +133,15 @@ def test_instantiation_library_user_runs_on_the_gpu():
     _build_instantiation_user()
     p = subprocess.run([INST_EXE], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_texture_helper_through_the_cpp_layer():
+    """TwoDTextureHelper<float> (include/mppi/utils/texture_helpers/two_d_texture_helper.cuh forwarder): the reference's own
+    world-pose known answers and a host step of the RACER model over a sloped elevation map (tests/cpp/texture_helper_test.cpp)."""
+    lib_dir = os.path.join(ROOT, "mppi-generic_b200")
+    exe = os.path.join(ROOT, "tests", "cpp", "texture_helper_test.bin")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unused-variable", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "texture_helper_test.cpp"), "-o", exe, "-L", lib_dir,
+                           "-l:libmppi_b200.so", "-Wl,-rpath," + lib_dir])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
