@@ -10,6 +10,7 @@
  */
 #pragma once
 #include <cmath>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -87,7 +88,68 @@ public:
       throw std::invalid_argument("init network must output 2 * hidden_dim values (lstm_lstm_helper.cu:11)");
     head_hidden_ = output_layers[1];
     theta_.assign((size_t)MPPIB_RACER_LSTM_NUM_PARAMS(hidden_dim_, head_hidden_), 0.0f);
-    (void)init_input_dim, (void)init_hidden_dim, (void)init_len;
+    // the init network (LSTMLSTMHelper::init_model_, lstm_lstm_helper.cu:4-12): host-only, zero-initialised
+    if (init_output_layers[0] != init_hidden_dim + init_input_dim)
+      throw std::invalid_argument("init_output_layers[0] must be init_hidden_dim + init_input_dim (lstm_helper.cu:41)");
+    init_input_dim_ = init_input_dim;
+    init_hidden_dim_ = init_hidden_dim;
+    init_len_ = init_len;
+    init_layers_ = init_output_layers;
+    init_lstm_.assign((size_t)4 * init_hidden_dim * init_hidden_dim + 4 * init_hidden_dim * init_input_dim + 6 * init_hidden_dim,
+                      0.0f);
+    size_t head = 0;
+    for (size_t l = 0; l + 1 < init_layers_.size(); l++)
+      head += (size_t)init_layers_[l] * init_layers_[l + 1] + init_layers_[l + 1];
+    init_head_.assign(head, 0.0f);
+  }
+  // ---- the init network (LSTMLSTMHelper) ---------------------------------------------------------------------------
+  // getInitModel()->setAllValues(lstm, output): LSTM block in lstm_helper.cu:72-88 order (with its own initial hidden / cell),
+  // head in fnn_helper.cu:176-183 order
+  void setAllValuesInit(const std::vector<float>& lstm, const std::vector<float>& output)
+  {
+    if (lstm.size() != init_lstm_.size() || output.size() != init_head_.size())
+      throw std::invalid_argument("init network: expected " + std::to_string(init_lstm_.size()) + " + " +
+                                  std::to_string(init_head_.size()) + " values");
+    init_lstm_ = lstm;
+    init_head_ = output;
+  }
+  int getInitLen() const
+  {
+    return init_len_;
+  }
+  // LSTMLSTMHelper::initializeLSTM (lstm_lstm_helper.cu:50-73). `buffer` is the reference's init_input_dim x cols matrix in
+  // Eigen's column-major order (one column per past time step), cols >= init_len. The new initial hidden / cell state reaches
+  // an existing engine with the next push of the model's blobs (Controller::setParams).
+  void initializeLSTM(const float* buffer, int rows, int cols)
+  {
+    if (rows != init_input_dim_ || cols < init_len_)
+      throw std::invalid_argument("initializeLSTM: buffer must be init_input_dim x (>= init_len)");
+    mppib_host_init_lstm net{ init_lstm_.data(), init_input_dim_, init_hidden_dim_, init_head_.data(), init_layers_.data(),
+                              (int)init_layers_.size(), init_len_ };
+    std::vector<float> out((size_t)2 * hidden_dim_);
+    MPPIB_HANDLE(mppib_host_lstm_initialize(&net, buffer, cols, out.data()));
+    setInitialHiddenCell(std::vector<float>(out.begin(), out.begin() + hidden_dim_),
+                         std::vector<float>(out.begin() + hidden_dim_, out.end()));
+  }
+  // racer_dubins_elevation_lstm_steering.cu:215-233 (buffer_trajectory = one vector of past values per key)
+  bool updateFromBuffer(const std::map<std::string, std::vector<float>>& buffer)
+  {
+    const char* keys[3] = { "STEER_ANGLE", "STEER_ANGLE_RATE", "CAN_STEER_CMD" };
+    for (const char* k : keys)
+      if (buffer.find(k) == buffer.end())
+        return false;
+    const size_t cols = buffer.at("STEER_ANGLE").size();
+    if (buffer.at("STEER_ANGLE_RATE").size() != cols || buffer.at("CAN_STEER_CMD").size() != cols || init_input_dim_ != 3)
+      return false;
+    std::vector<float> init_buffer(3 * cols);
+    for (size_t t = 0; t < cols; t++)
+    {
+      init_buffer[3 * t] = buffer.at("STEER_ANGLE")[t] * 0.2f;
+      init_buffer[3 * t + 1] = buffer.at("STEER_ANGLE_RATE")[t] * 0.2f;
+      init_buffer[3 * t + 2] = buffer.at("CAN_STEER_CMD")[t];
+    }
+    initializeLSTM(init_buffer.data(), 3, (int)cols);
+    return true;
   }
   void setParams(const DYN_PARAMS_T& p)
   {
@@ -317,5 +379,8 @@ private:
   DYN_PARAMS_T params_;
   int hidden_dim_ = 4, head_hidden_ = 20;
   std::vector<float> theta_, hidden_, cell_;
+  std::vector<float> init_lstm_, init_head_;  // the init network's weights (host only)
+  std::vector<int> init_layers_;
+  int init_input_dim_ = 0, init_hidden_dim_ = 0, init_len_ = 0;
   std::shared_ptr<TwoDTextureHelper<float>> tex_helper_ = std::make_shared<TwoDTextureHelper<float>>(1);
 };

@@ -49,6 +49,25 @@ int mppib_host_step_lstm(const void* dyn_params, const mppib_host_lstm* net, con
                          float* x_next, float* xdot, float* y);
 int mppib_host_output_trajectory_lstm(const void* dyn_params, const mppib_host_lstm* net, const float* x0,
                                       const float* u, int T, float dt, float* states, float* outputs);
+/* LSTMLSTMHelper::initializeLSTM (utils/nn_helpers/lstm_lstm_helper.cu:50-73): the INIT network — an LSTM (input_dim, hidden_dim)
+ * with an FNN head on [h; x] (layers {hidden_dim + input_dim, ..., 2 * H_prediction}) — runs over the last init_len columns
+ * of a buffer of past inputs, starting from its own initial hidden / cell state; the head's output after the last column is
+ * the prediction LSTM's initial hidden (first half) and cell (second half) state. Host-only in the reference too.
+ *   lstm_theta  W_im W_fm W_om W_cm [H x H each] | W_ii W_fi W_oi W_ci [H x I each] | b_i b_f b_o b_c [H each] |
+ *               initial hidden [H] | initial cell [H]                      (lstm_helper.cu:72-88)
+ *   head_theta  packed W (out x in, row-major) then b, layer after layer   (fnn_helper.cu:176-183); tanh between layers
+ *   buffer      [cols][input_dim]: element (t, r) = the reference's buffer(r, t); cols >= init_len
+ *   out         [head_layers[head_num_layers - 1]] */
+typedef struct mppib_host_init_lstm
+{
+  const float* lstm_theta;
+  int input_dim, hidden_dim;
+  const float* head_theta;
+  const int* head_layers;
+  int head_num_layers;
+  int init_len;
+} mppib_host_init_lstm;
+int mppib_host_lstm_initialize(const mppib_host_init_lstm* net, const float* buffer, int cols, float* out);
 /* RobustMPPI host logic (controllers/R-MPPI/robust_mppi_controller.cu:351-362,472-537): line-search weights [3][K],
  * nominal-state candidates [K][S] + importance-sampler strides [K], best candidate (returns previous_best if none
  * is under the value-function threshold). */

@@ -715,6 +715,79 @@ int mppib_host_output_trajectory(int dyn_id, const void* dyn_params, const float
   return MPPIB_ERR_UNSUPPORTED;
 }
 
+// LSTMLSTMHelper::initializeLSTM, lstm_lstm_helper.cu:50-73, with LSTMHelper::forward (host, lstm_helper.cu:267-339) and
+// FNNHelper::forward (host: tanh between layers, linear output) for arbitrary dimensions. Runs once per re-initialisation
+// (a few hundred microseconds of scalar code), not per solve.
+int mppib_host_lstm_initialize(const mppib_host_init_lstm* net, const float* buffer, int cols, float* out)
+{
+  if (!net || !net->lstm_theta || !net->head_theta || !net->head_layers || !buffer || !out)
+    return MPPIB_ERR_INVALID_ARG;
+  const int I = net->input_dim, H = net->hidden_dim, L = net->head_num_layers;
+  if (I <= 0 || H <= 0 || L < 2 || net->init_len <= 0 || cols < net->init_len || net->head_layers[0] != H + I)
+    return MPPIB_ERR_INVALID_ARG;
+  const int HH = H * H, IH = H * I;
+  const float* w = net->lstm_theta;
+  const float* bias = w + 4 * HH + 4 * IH;
+  std::vector<float> h(bias + 4 * H, bias + 5 * H), c(bias + 5 * H, bias + 6 * H);  // resetHiddenCellCPU
+  std::vector<float> hn(H), cn(H);
+  for (int t = cols - net->init_len; t < cols; t++)
+  {
+    const float* x = buffer + (size_t)t * I;
+    for (int i = 0; i < H; i++)
+    {
+      float g[4];
+      for (int k = 0; k < 4; k++)
+      {
+        const float* Wm = w + k * HH + i * H;
+        const float* Wi = w + 4 * HH + k * IH + i * I;
+        float hm = 0.0f, im = 0.0f;
+        for (int j = 0; j < H; j++)
+          hm += Wm[j] * h[j];
+        for (int j = 0; j < I; j++)
+          im += Wi[j] * x[j];
+        g[k] = (hm + im) + bias[k * H + i];
+      }
+      const float gi = 1.0f / (1.0f + expf(-g[0])), gf = 1.0f / (1.0f + expf(-g[1])), go = 1.0f / (1.0f + expf(-g[2]));
+      cn[i] = gi * tanhf(g[3]) + gf * c[i];
+      hn[i] = go * tanhf(cn[i]);
+    }
+    h = hn;
+    c = cn;
+  }
+  // head on [h; x_last]
+  int widest = 0;
+  for (int l = 0; l < L; l++)
+  {
+    if (net->head_layers[l] <= 0)
+      return MPPIB_ERR_INVALID_ARG;
+    widest = std::max(widest, net->head_layers[l]);
+  }
+  std::vector<float> a(widest), b(widest);
+  for (int i = 0; i < H; i++)
+    a[i] = h[i];
+  for (int i = 0; i < I; i++)
+    a[H + i] = buffer[(size_t)(cols - 1) * I + i];
+  const float* th = net->head_theta;
+  for (int l = 0; l + 1 < L; l++)
+  {
+    const int in = net->head_layers[l], on = net->head_layers[l + 1];
+    const float* W = th;
+    const float* bb = th + (size_t)in * on;
+    for (int o = 0; o < on; o++)
+    {
+      float acc = 0.0f;
+      for (int j = 0; j < in; j++)
+        acc += W[(size_t)o * in + j] * a[j];
+      acc += bb[o];
+      b[o] = (l + 2 < L) ? tanhf(acc) : acc;
+    }
+    std::swap(a, b);
+    th += (size_t)in * on + on;
+  }
+  memcpy(out, a.data(), sizeof(float) * net->head_layers[L - 1]);
+  return MPPIB_OK;
+}
+
 float mppib_host_elevation_at_world_pose(const mppib_elevation_map_header* map, float x, float y, float z)
 {
   return map ? elevation_at_world_pose(map, x, y, z) : 0.0f;

@@ -123,6 +123,12 @@ class HostLSTM(C.Structure):
                 ("cell", C.c_void_p), ("map", C.c_void_p)]
 
 
+class HostInitLSTM(C.Structure):
+    """mppib_host_init_lstm (host_twins.h)."""
+    _fields_ = [("lstm_theta", C.c_void_p), ("input_dim", C.c_int), ("hidden_dim", C.c_int), ("head_theta", C.c_void_p),
+                ("head_layers", C.c_void_p), ("head_num_layers", C.c_int), ("init_len", C.c_int)]
+
+
 class ElevationMapHeader(C.Structure):
     """mppib_elevation_map_header (params.h): TextureParams of the RACER models' map 0."""
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("origin", C.c_float * 3), ("rotations", C.c_float * 9),
@@ -259,7 +265,7 @@ ABI_SYMBOLS = [
     "mppib_host_dims", "mppib_host_enforce_constraints", "mppib_host_step", "mppib_host_smooth_controls",
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
-    "mppib_host_elevation_at_world_pose", "mppib_host_static_settling",
+    "mppib_host_elevation_at_world_pose", "mppib_host_static_settling", "mppib_host_lstm_initialize",
     "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_nominal_trajectory", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
@@ -521,7 +527,8 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
     output_layers, init_len). The prediction LSTM (input_dim must be 4, output_layers = [hidden_dim + 4, L1, 1]) runs
     inside the rollout; the init network (LSTMLSTMHelper) only produces the initial hidden / cell state from a history
     buffer on the host (updateFromBuffer, :215-232) and is represented here by that state itself
-    (``setInitialHiddenCell``). No elevation map: flat terrain."""
+    (``setInitialHiddenCell``), or computed by the init network itself (``setAllValuesInit`` / ``loadParamsInit`` +
+    ``initializeLSTM`` / ``updateFromBuffer``). Elevation map: ``getTextureHelper()`` / ``setElevationMap``."""
     DYN_ID, STATE_DIM, CONTROL_DIM, OUTPUT_DIM = DYN_RACER_LSTM, 19, 2, 28
 
     def enforceLeash(self, state_true, state_nominal, leash_values) -> np.ndarray:
@@ -564,6 +571,16 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
         if tuple(init_output_layers)[-1] != 2 * hidden_dim:
             raise ValueError("init network must output 2 * hidden_dim values (lstm_lstm_helper.cu:11)")
         self.hidden_dim, self.head_hidden = hidden_dim, output_layers[1]
+        # the init network (LSTMLSTMHelper::init_model_, lstm_lstm_helper.cu:4-12): host-only, zero-initialised like the
+        # reference's constructor leaves it
+        self.init_input_dim, self.init_hidden_dim, self.init_len = init_input_dim, init_hidden_dim, init_len
+        self.init_output_layers = tuple(int(v) for v in init_output_layers)
+        if self.init_output_layers[0] != init_hidden_dim + init_input_dim:
+            raise ValueError("init_output_layers[0] must be init_hidden_dim + init_input_dim (lstm_helper.cu:41)")
+        Hi, Ii = init_hidden_dim, init_input_dim
+        self.init_lstm_theta = np.zeros(4 * Hi * Hi + 4 * Hi * Ii + 6 * Hi, np.float32)
+        self.init_head_theta = np.zeros(sum(a * b + b for a, b in zip(self.init_output_layers[:-1],
+                                                                     self.init_output_layers[1:])), np.float32)
         p = RacerLSTMDynParams()
         p.lim.set_defaults()
         # racer_dubins.cuh:78-104, racer_dubins_elevation.cuh:47-59
@@ -669,6 +686,84 @@ class RacerDubinsElevationLSTMSteering(_Dynamics):
             head += [npz_read(model_path, f"{prefix}output/dynamics_W{i}").ravel(), b.ravel()]
             i += 1
         self.setAllValues(lstm, np.concatenate(head))
+
+    # ---- the init network (LSTMLSTMHelper) ---------------------------------------------------------------------------------
+    def setAllValuesInit(self, lstm, output) -> None:
+        """getInitModel()->setAllValues(lstm, output): the init LSTM block (lstm_helper.cu:72-88 order, with its own initial
+        hidden / cell) and its head (fnn_helper.cu:176-183)."""
+        lstm, output = _f32(lstm).ravel(), _f32(output).ravel()
+        if lstm.size != self.init_lstm_theta.size or output.size != self.init_head_theta.size:
+            raise ValueError(f"init network: expected {self.init_lstm_theta.size} + {self.init_head_theta.size} values")
+        self.init_lstm_theta, self.init_head_theta = lstm.copy(), output.copy()
+
+    def loadParamsInit(self, model_path: str, prefix: str = "") -> None:
+        """LSTMLSTMHelper::loadParams (lstm_lstm_helper.cu:101-118): the "<prefix>init_" arrays of the npz file — same
+        names and PyTorch gate order as the prediction network (loadParamsLSTM), head of any depth — and "init_length"
+        (+ 1, :33-38) when the file has it."""
+        if prefix and not prefix.endswith("/"):
+            prefix += "/"
+        try:
+            npz_read(model_path, "model/" + prefix + "init_lstm/weight_hh_l0")
+            prefix = "model/" + prefix
+        except MppibError:
+            pass
+        ip = prefix + "init_"
+        H, I = self.init_hidden_dim, self.init_input_dim
+        whh = npz_read(model_path, ip + "lstm/weight_hh_l0").astype(np.float64)
+        wih = npz_read(model_path, ip + "lstm/weight_ih_l0").astype(np.float64)
+        bias = (npz_read(model_path, ip + "lstm/bias_hh_l0").astype(np.float64) +
+                npz_read(model_path, ip + "lstm/bias_ih_l0").astype(np.float64))
+        if whh.shape != (4 * H, H) or wih.shape != (4 * H, I) or bias.shape != (4 * H,):
+            raise ValueError(f"init LSTM arrays do not match init_hidden_dim = {H}, init_input_dim = {I}")
+        order = (0, 1, 3, 2)  # file blocks i, f, c(g), o -> packed i, f, o, c
+        lstm = np.concatenate([np.concatenate([whh[k * H:(k + 1) * H].ravel() for k in order]),
+                               np.concatenate([wih[k * H:(k + 1) * H].ravel() for k in order]),
+                               np.concatenate([bias[k * H:(k + 1) * H] for k in order]),
+                               self.init_lstm_theta[-2 * H:]])
+        head, i = [], 1
+        while True:
+            try:
+                b = npz_read(model_path, f"{ip}output/dynamics_b{i}")
+            except MppibError:
+                if i == 1:
+                    raise
+                break
+            head += [npz_read(model_path, f"{ip}output/dynamics_W{i}").ravel(), b.ravel()]
+            i += 1
+        self.setAllValuesInit(lstm, np.concatenate(head))
+        try:
+            self.init_len = int(npz_read(model_path, "init_length").ravel()[0]) + 1
+        except MppibError:
+            pass
+
+    def initializeLSTM(self, buffer) -> None:
+        """LSTMLSTMHelper::initializeLSTM (lstm_lstm_helper.cu:50-73). buffer [init_input_dim][cols] like the reference's
+        matrix (one column per past time step, cols >= init_len): runs the init network over the last init_len columns and
+        installs its output as the prediction LSTM's initial hidden / cell state."""
+        b = _f32(buffer)
+        if b.ndim != 2 or b.shape[0] != self.init_input_dim or b.shape[1] < self.init_len:
+            raise ValueError(f"buffer must be [{self.init_input_dim}][>= {self.init_len}]")
+        cols = np.ascontiguousarray(b.T)  # [cols][input_dim]
+        layers = np.asarray(self.init_output_layers, np.int32)
+        net = HostInitLSTM(self.init_lstm_theta.ctypes.data, self.init_input_dim, self.init_hidden_dim,
+                           self.init_head_theta.ctypes.data, layers.ctypes.data, len(layers), self.init_len)
+        out = np.zeros(2 * self.hidden_dim, np.float32)
+        L = lib()
+        L.mppib_host_lstm_initialize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        _check(L.mppib_host_lstm_initialize(C.byref(net), cols.ctypes.data, cols.shape[0], out.ctypes.data))
+        self.setInitialHiddenCell(out[:self.hidden_dim], out[self.hidden_dim:])
+
+    def updateFromBuffer(self, buffer: dict) -> bool:
+        """racer_dubins_elevation_lstm_steering.cu:215-233: rows STEER_ANGLE * 0.2, STEER_ANGLE_RATE * 0.2, CAN_STEER_CMD of
+        the history buffer feed the init network. Returns False when a key is missing (like the reference). The new initial
+        state reaches an existing engine with the next push of the model's parameters (Controller::setParams)."""
+        keys = ("STEER_ANGLE", "STEER_ANGLE_RATE", "CAN_STEER_CMD")
+        if any(k not in buffer for k in keys):
+            return False
+        init_buffer = np.stack([_f32(buffer["STEER_ANGLE"]) * np.float32(0.2), _f32(buffer["STEER_ANGLE_RATE"]) * np.float32(0.2),
+                                _f32(buffer["CAN_STEER_CMD"])])
+        self.initializeLSTM(init_buffer)
+        return True
 
     def setInitialHiddenCell(self, hidden, cell) -> None:
         """LSTMHelper::updateLSTMInitialStates (lstm_helper.cu:98-110)."""

@@ -240,6 +240,17 @@ def lstm_forward(lstm_w, input_dim, hidden_dim, head_theta, head_layers, inp, h,
     return out, h, c
 
 
+def lstm_initialize(init_w, input_dim, hidden_dim, head_theta, head_layers, init_len, buffer):
+    """LSTMLSTMHelper::initializeLSTM (lstm_lstm_helper.cu:50-73). buffer [cols][input_dim]. Returns the head output
+    (first half = hidden, second half = cell of the prediction LSTM)."""
+    head_layers = np.ascontiguousarray(head_layers, dtype=np.int32)
+    buffer = _f32(buffer)
+    out = np.zeros(int(head_layers[-1]), np.float32)
+    lib().orc_lstm_initialize(_p(_f32(init_w)), input_dim, hidden_dim, _p(_f32(head_theta)), _p(head_layers), len(head_layers),
+                              init_len, _p(buffer), buffer.shape[0], _p(out))
+    return out
+
+
 def racer_step(dyn_params, x, u, dt, h, c):
     """One host step of RacerDubinsElevationLSTMSteering. Returns (x_next, xdot, y, h_next, c_next)."""
     h, c = _f32(h).copy(), _f32(c).copy()

@@ -249,7 +249,7 @@ struct DoubleIntegrator
 // utils/nn_helpers/fnn_helper.cu:354-382 (host forward), layout :176-183, tanh = tanhf (activation_functions.cuh:15-26)
 static void fnn_forward(const float* theta, const int* layers, int num_layers, const float* input, float* output)
 {
-  float acts[2][64];
+  float acts[2][512];  // widest layer in tree: the init network's 100 (lstm_lstm_helper_test.cu:29)
   int cur = 0;
   for (int i = 0; i < layers[0]; i++)
     acts[0][i] = input[i];
@@ -1599,6 +1599,28 @@ void orc_lstm_forward(const float* lstm_w, int input_dim, int hidden_dim, const 
                       float* output)
 {
   orc::lstm_forward(lstm_w, input_dim, hidden_dim, head_theta, head_layers, head_num_layers, input, h, c, output);
+}
+
+// LSTMLSTMHelper::initializeLSTM (lstm_lstm_helper.cu:50-73): reset the init model to its initial hidden / cell state, run it
+// over the last init_len columns of the buffer (forward without output, then forward with output on the last column), the
+// output's head / tail are the prediction LSTM's hidden / cell state. buffer [cols][input_dim] (column t of the reference's
+// matrix), out [2 * H_prediction].
+void orc_lstm_initialize(const float* init_w, int input_dim, int hidden_dim, const float* head_theta, const int* head_layers,
+                         int head_num_layers, int init_len, const float* buffer, int cols, float* out)
+{
+  const float* init = init_w + 4 * hidden_dim * hidden_dim + 4 * hidden_dim * input_dim + 4 * hidden_dim;
+  float h[128], c[128], scratch[512];
+  for (int i = 0; i < hidden_dim; i++)
+  {
+    h[i] = init[i];
+    c[i] = init[hidden_dim + i];
+  }
+  int t = cols - init_len;
+  for (; t < cols - 1; t++)
+    orc::lstm_forward(init_w, input_dim, hidden_dim, head_theta, head_layers, head_num_layers,
+                      buffer + (size_t)t * input_dim, h, c, scratch);
+  orc::lstm_forward(init_w, input_dim, hidden_dim, head_theta, head_layers, head_num_layers, buffer + (size_t)t * input_dim, h,
+                    c, out);
 }
 
 // One host step of RacerDubinsElevationLSTMSteering with explicit hidden/cell state (updated in place).

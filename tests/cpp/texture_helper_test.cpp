@@ -45,5 +45,18 @@ int main()
   model.step(x, xn, xd, u, y, 0.0f, 0.02f);
   const float expect_pitch = asinf(-0.1f * 2.981f / 2.981f);
   printf("pitch %f expect %f height %f\n", xn(7), expect_pitch, y(4));
-  return (fabsf(xn(7) - expect_pitch) < 1e-4f && fabsf(xn(6)) < 1e-5f) ? 0 : 2;
+  if (!(fabsf(xn(7) - expect_pitch) < 1e-4f && fabsf(xn(6)) < 1e-5f))
+    return 2;
+  // the init network: the reference's known answer (tests/nn_helpers/lstm_lstm_helper_test.cu:161-180): all weights 1, a
+  // buffer of ones -> hidden = cell = 101
+  std::vector<int> il = { 68, 100, 20 }, ol = { 14, 20, 1 };
+  RacerDubinsElevationLSTMSteering m2(8, 60, il, 4, 10, ol, 6);
+  m2.setAllValuesInit(std::vector<float>(4 * 60 * 60 + 4 * 60 * 8 + 6 * 60, 1.0f),
+                      std::vector<float>(68 * 100 + 100 + 100 * 20 + 20, 1.0f));
+  std::vector<float> ones(8 * 10, 1.0f);
+  m2.initializeLSTM(ones.data(), 8, 10);
+  const std::vector<float>& th = m2.getTheta();
+  const size_t base = 4 * 10 * 10 + 4 * 10 * 4 + 4 * 10;
+  printf("init hidden %f cell %f\n", th[base], th[base + 10]);
+  return (th[base] == 101.0f && th[base + 19] == 101.0f) ? 0 : 3;
 }
