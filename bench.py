@@ -105,6 +105,34 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _traffic_from_profile(workload_name: str, info: dict):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of K1 from the committed `ncu --set full` capture of this
+    command (profiles/r02_final_*_k1_kernels.csv, written by tools/run_final_r02.sh + tools/summarize_ncu.py) — used only when
+    that capture is of the SAME launch (grid and block of this run), otherwise None: a stale profile must not speak for a
+    changed kernel."""
+    import csv
+    tag = "autorally" if workload_name.startswith("autorally_nn_N32768_T100") else (
+        "racer" if workload_name.startswith("racer_lstm_H4_colored_N65536_T150") else None)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f"r02_final_{tag}_k1_kernels.csv")
+    if tag is None or not os.path.exists(path):
+        return None, None
+    try:
+        rows = list(csv.reader(open(path)))
+        rec = dict(zip(rows[0], rows[1]))
+
+        def mbytes(prefix):
+            for k, v in rec.items():
+                if k.startswith(prefix):
+                    unit = k[k.index("[") + 1:k.index("]")].lower()
+                    return float(v) * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+            raise KeyError(prefix)
+        if int(float(rec["launch__grid_size []"])) != info["grid"] or int(float(rec["launch__block_size []"])) != info["block"]:
+            return None, None
+        return mbytes("dram__bytes_read.sum") + mbytes("dram__bytes_write.sum"), os.path.relpath(path, os.path.dirname(path) + "/..")
+    except Exception:  # an unreadable summary is the same as no summary
+        return None, None
+
+
 def _workload(args):
     from mppi_generic_b200 import workloads as W
     return W.by_name(args.workload, args.rollouts, args.timesteps)
@@ -446,13 +474,16 @@ def run_engine(args, ctx, emit=True, extra=None):
     e.enable_timing(False)
     info = e.launch_info()
     peak, peak_src = _peaks()
+    traffic, traffic_src = _traffic_from_profile(_base_config(w)["workload"], info) if world == 1 else (None, None)
     bytes_per_launch = e.n_local * w.T * w.dyn.CONTROL_DIM * 4
     achieved = bytes_per_launch / (t_cold["rollout_ms"] * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "rollout kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None,
-        "traffic_note": "not measured in this run (no profiler attached); the ncu captures of this kernel are summarised "
-                        "under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of "
+                         f"this command with the same grid / block ({traffic_src})") if traffic is not None else
+                        "not measured in this run (no profiler attached) and no committed capture of this exact launch; the "
+                        "ncu captures of this kernel are summarised under profiles/",
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_l2_flushed": t_cold["rollout_ms"],
         "kernel_ms_l2_warm": t_warm["rollout_ms"],

@@ -5,7 +5,7 @@
  *
  * Why: the FFMA2 kernel (plugins/dynamics.cuh) is bound by shared-memory wavefronts — every 4 FMAs of a thread need one
  * broadcast LDS.128 of weights, 672 wavefronts per warp-step, 72 % of the data pipe (profiles/r01_autorally_k1_notes.md).
- * Here the weights are B fragments (one LDS.128 per lane per tile carrying the hi and lo parts: 14 loads, ~50 wavefronts per warp-step) and the
+ * Here the weights are B fragments (one LDS.128 per lane per tile carrying the hi and lo parts: 14 loads, ~50 wavefronts per warp-step; the biases as ready-made C fragments, 9 more) and the
  * activations never leave registers between layers: with 16-bit inputs the C fragment of n-tiles 2j, 2j+1 of layer l,
  * packed to half2, IS the A fragment of k-tile j of layer l+1.
  *
@@ -37,13 +37,16 @@ namespace mppib
 namespace nn_mma
 {
 // shared-memory layout in floats (block-wide part, then scratch per warp)
-constexpr int kW1F = 0;               // layer 1: 4 n-tiles x 32 lanes x (b_hi, b_lo)                                  uint2
-constexpr int kW2F = kW1F + 4 * 64;   // layer 2: 8 tiles (n-tile i major, k-tile j minor) x 32 x (b0_hi, b1_hi, b0_lo, b1_lo)
+constexpr int kW1F = 0;               // layer 1: 4 n-tiles x 32 lanes x (b_hi, b_hi, b_lo, 0): the k16 cross-term MMA takes the
+                                      // hi part in BOTH of its B registers, stored as a pair so that no MOV builds it  uint4
+constexpr int kW2F = kW1F + 4 * 128;  // layer 2: 8 tiles (n-tile i major, k-tile j minor) x 32 x (b0_hi, b1_hi, b0_lo, b1_lo)
 constexpr int kW3F = kW2F + 8 * 128;  // layer 3: 2 k-tiles x 32 x (b0_hi, b1_hi, b0_lo, b1_lo)
-constexpr int kB1 = kW3F + 2 * 128;   // 32 (pre-scaled like the weights)
-constexpr int kB2 = kB1 + 32;         // 32
-constexpr int kB3 = kB2 + 32;         // 8 (4 real)
-constexpr int kFixedFloats = kB3 + 8;  // 1608
+// biases as ready-made C fragments: [n-tile][t] x (b[2t], b[2t+1], b[2t], b[2t+1]) — one LDS.128 is the accumulator's start
+// (rows g and g + 8 share the bias; as a float2 the quad cost two MOVs per tile, 26 of the 314 instructions of a step)
+constexpr int kB1 = kW3F + 2 * 128;   // 4 x 4 x 4 (pre-scaled like the weights)
+constexpr int kB2 = kB1 + 64;         // 4 x 4 x 4
+constexpr int kB3 = kB2 + 64;         // 4 x 4 (columns 4..7 are padding)
+constexpr int kFixedFloats = kB3 + 16;  // 1936
 // per warp: [2][SPW][4] input halves, then [SPW][4] outputs (separate regions: two __syncwarp per evaluation, not four)
 __host__ __device__ constexpr int scratchPerWarp(int spw)
 {
@@ -134,8 +137,10 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ g, float*
       const float v1 = (2 * t + 1 < 6) ? g[n * 6 + 2 * t + 1] * kTanhScale : 0.0f;
       uint32_t hi, lo;
       split2(v0, v1, hi, lo);
-      w1f[idx * 2 + 0] = hi;
-      w1f[idx * 2 + 1] = lo;
+      w1f[idx * 4 + 0] = hi;
+      w1f[idx * 4 + 1] = hi;
+      w1f[idx * 4 + 2] = lo;
+      w1f[idx * 4 + 3] = 0u;
     }
     else
     {
@@ -181,7 +186,11 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ g, float*
     }
     else
       v = 0.0f;
-    theta_s[kB1 + i] = v;
+    // bias i of its layer (column 8 n + 2 t + e of n-tile n) -> elements e and e + 2 of quad (n, t)
+    const int layer = i < 32 ? 0 : (i < 64 ? 1 : 2), col = i - (layer == 0 ? 0 : (layer == 1 ? 32 : 64));
+    float* q = theta_s + (layer == 0 ? kB1 : (layer == 1 ? kB2 : kB3)) + ((col >> 3) * 4 + ((col & 7) >> 1)) * 4 + (col & 1);
+    q[0] = v;
+    q[2] = v;
   }
 }
 
@@ -195,7 +204,7 @@ __device__ __forceinline__ void forward_frag(const float* theta_s, const uint32_
                                              float (&o)[MT][4])
 {
   const int lane = threadIdx.x & 31, t = lane & 3;
-  const uint2* w1f = reinterpret_cast<const uint2*>(theta_s + kW1F);
+  const uint4* w1f = reinterpret_cast<const uint4*>(theta_s + kW1F);
   const uint4* w2f = reinterpret_cast<const uint4*>(theta_s + kW2F);
   const uint4* w3f = reinterpret_cast<const uint4*>(theta_s + kW3F);
   // ---- layer 1: 8 (6) -> 32. The k = 8 operands leave half of a k16 MMA free, so [a_hi | a_lo] x [w_hi ; w_hi] brings
@@ -205,14 +214,14 @@ __device__ __forceinline__ void forward_frag(const float* theta_s, const uint32_
 #pragma unroll
   for (int i = 0; i < 4; i++)
   {
-    const float2 b = *reinterpret_cast<const float2*>(theta_s + kB1 + 8 * i + 2 * t);
-    const uint2 wf = w1f[i * 32 + lane];  // (b_hi, b_lo)
+    const float4 b = *reinterpret_cast<const float4*>(theta_s + kB1 + (4 * i + t) * 4);
+    const uint4 wf = w1f[i * 32 + lane];  // (b_hi, b_hi, b_lo, -)
 #pragma unroll
     for (int m = 0; m < MT; m++)
     {
-      float c[4] = { b.x, b.y, b.x, b.y };
-      mma16(c, a_hi[m][0], a_hi[m][1], a_lo[m][0], a_lo[m][1], wf.x, wf.x);
-      mma8(c, a_hi[m][0], a_hi[m][1], wf.y);
+      float c[4] = { b.x, b.y, b.z, b.w };
+      mma16(c, a_hi[m][0], a_hi[m][1], a_lo[m][0], a_lo[m][1], wf.x, wf.y);
+      mma8(c, a_hi[m][0], a_hi[m][1], wf.z);
       activate<BOT>(c, h_hi[m][i >> 1][(i & 1) * 2], h_hi[m][i >> 1][(i & 1) * 2 + 1], h_lo[m][i >> 1][(i & 1) * 2],
                     h_lo[m][i >> 1][(i & 1) * 2 + 1]);
     }
@@ -222,11 +231,11 @@ __device__ __forceinline__ void forward_frag(const float* theta_s, const uint32_
 #pragma unroll
   for (int i = 0; i < 4; i++)
   {
-    const float2 b = *reinterpret_cast<const float2*>(theta_s + kB2 + 8 * i + 2 * t);
+    const float4 b = *reinterpret_cast<const float4*>(theta_s + kB2 + (4 * i + t) * 4);
     float c[MT][4];
 #pragma unroll
     for (int m = 0; m < MT; m++)
-      c[m][0] = b.x, c[m][1] = b.y, c[m][2] = b.x, c[m][3] = b.y;
+      c[m][0] = b.x, c[m][1] = b.y, c[m][2] = b.z, c[m][3] = b.w;
 #pragma unroll
     for (int j = 0; j < 2; j++)
     {
@@ -246,12 +255,12 @@ __device__ __forceinline__ void forward_frag(const float* theta_s, const uint32_
   }
   // ---- layer 3: 32 -> 8 (4); one accumulator per k-tile so that the two chains of three MMAs run side by side
   {
-    const float2 b = *reinterpret_cast<const float2*>(theta_s + kB3 + 2 * t);
+    const float4 b = *reinterpret_cast<const float4*>(theta_s + kB3 + t * 4);
     float o2[MT][4];
 #pragma unroll
     for (int m = 0; m < MT; m++)
     {
-      o[m][0] = b.x, o[m][1] = b.y, o[m][2] = b.x, o[m][3] = b.y;
+      o[m][0] = b.x, o[m][1] = b.y, o[m][2] = b.z, o[m][3] = b.w;
       o2[m][0] = o2[m][1] = o2[m][2] = o2[m][3] = 0.0f;
     }
     const uint4 wf0 = w3f[lane], wf1 = w3f[32 + lane];
