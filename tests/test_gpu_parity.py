@@ -20,6 +20,7 @@ H = m.host
 pytestmark = pytest.mark.gpu
 
 COST_RTOL = 1e-4
+U_ORACLE_TOL = 2e-3
 
 
 def _oracle_solve(w, eps, stride=1, it=0, want_samples=False):
@@ -41,10 +42,21 @@ def _check_solve(w, e, stride=1, cost_rtol=COST_RTOL, u_tol=1e-5):
         assert stats[d][0] == pytest.approx(float(ref["baseline"][d]), rel=cost_rtol)
         # the normaliser inherits the per-sample cost differences through exp(-(c-beta)/lambda)
         assert stats[d][1] == pytest.approx(float(ref["normalizer"][d]), rel=5e-3)
-    # U compared against the oracle run on the oracle's own costs: dominated by cost parity, so use a looser bound
-    np.testing.assert_allclose(U, ref["U"], atol=2e-3 * scale)
-    # tight check of the reduction itself: recompute the reference average from the DEVICE costs (float64)
+    # U against the oracle's U (computed from the ORACLE's costs). The two weight sets differ by exp(-(dc_n - dc_base) / lambda),
+    # so to first order |dU| <= 2 max|dc| / lambda * max_n |u_n - U|: the bound follows the measured cost differences instead of
+    # a fixed allowance (round 1 used 2e-3 of the control scale; measured on B200: 2e-7 .. 7e-4, the large ones being cartpole
+    # with costs ~1e3 / lambda = 0.25, i.e. a 5e-7 relative cost difference already moves the weights by 1e-3).
     samples = _oracle_solve(w, eps, stride, want_samples=True)["samples"]
+    for d in range(w.D):
+        dc = float(np.abs(costs[d].astype(np.float64) - ref["costs"][d].astype(np.float64)).max())
+        spread = float(np.abs(samples[d].astype(np.float64) - ref["U"][d][None].astype(np.float64)).max())
+        bound = 2.0 * dc / w.lambda_ * spread + 4e-6 * scale
+        u_err = float(np.abs(U[d] - ref["U"][d]).max())
+        if os.environ.get("MPPIB_U_REPORT"):
+            with open(os.environ["MPPIB_U_REPORT"], "a") as f:
+                f.write(f"{w.name} stride={stride} d={d} u_err={u_err:.3e} bound={bound:.3e} dc={dc:.3e}\n")
+        assert u_err <= min(bound, U_ORACLE_TOL * scale), (w.name, d, u_err, bound)
+    # tight check of the reduction itself: recompute the reference average from the DEVICE costs (float64)
     lam_inv = np.float32(1.0 / w.lambda_)
     for d in range(w.D):
         c = costs[d].astype(np.float64)
