@@ -441,10 +441,7 @@ __global__ void __launch_bounds__(DYN::MAX_BLOCK_THREADS) rollout_kernel(const _
   float cost[M];
 #pragma unroll
   for (int m = 0; m < M; m++)
-  {
-    const int sp = m / D, d = m % D;
     cost[m] = running_cost[m] / (float)T + COST::terminalCost(args.cost, args.cost_aux, y[m]) / (float)T;
-  }
   if (RMPPI)
   {  // rmppi_kernels.cu:836-858
     const float term_nom = COST::terminalCost(args.cost, args.cost_aux, y[0]);
