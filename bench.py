@@ -399,11 +399,20 @@ def run_engine(args, ctx, emit=True, extra=None):
             tail_calls.append((L.mppib_host_output_trajectory,
                                (w.dyn.DYN_ID, C.byref(w.dyn.params), nn, x0p, up, w.T, C.c_float(w.dt), sp_, op_)))
 
-    def compute_control():
+    def compute_control_separate():  # what the controller mirrors do: mppib_solve, then the host twins, call by call
         e.solve_into(x0, U, U_out, stats, w.optimization_stride, 0)
         for fn, a in tail_calls:
             fn(*a)
         U[...] = U_out
+
+    cc_args = (e._h, x0.ctypes.data, U.ctypes.data, w.optimization_stride, 0, hist.ctypes.data, states.ctypes.data,
+               outputs.ctypes.data, stats)
+    is_user_pair = w.dyn.DYN_ID >= getattr(H, "USER_ID_BASE", 1 << 30)
+
+    def compute_control():  # the same computeControl as ONE C-ABI call (mppib_compute_control), U updated in place
+        if is_user_pair:
+            return compute_control_separate()
+        H._check(L.mppib_compute_control(*cc_args))
 
     for _ in range(3):
         compute_control()
@@ -418,6 +427,13 @@ def run_engine(args, ctx, emit=True, extra=None):
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = max(e2e_wall_ms, ev0.elapsed_time(ev1))
+    # the same computeControl as separate calls (mppib_solve + host twins, what the header-only / Python controllers do)
+    U[...] = w.U0
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        compute_control_separate()
+    torch.cuda.synchronize()
+    separate_ms = (time.perf_counter() - t0) * 1e3
     # the same loop without the host tail (C-ABI solve only), reported next to it
     U[...] = w.U0
     t0 = time.perf_counter()
@@ -516,8 +532,9 @@ def run_engine(args, ctx, emit=True, extra=None):
                              "is reused across solves; the roofline pass flushes L2 (256 MiB memset) between K0 and K1"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / n_timed,
-                    "includes": "blocking mppib_solve (host x0/U in, U/stats out) + host tail: SG smoothing and nominal "
-                                "state/output roll-forward (T host step() calls)",
+                    "includes": "mppib_compute_control: blocking solve (host x0/U in, U/stats out) + host tail: SG smoothing and "
+                                "nominal state/output roll-forward (T host step() calls), one C-ABI call per computeControl",
+                    "separate_calls_value": n_timed / (separate_ms * 1e-3),
                     "solve_only_value": n_timed / (solve_only_ms * 1e-3),
                     "device_tail_value": None if device_tail_ms is None else n_timed / (device_tail_ms * 1e-3),
                     "device_tail_note": "same computeControl with smoothing + roll-forward as one device kernel chained "

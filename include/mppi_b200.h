@@ -240,6 +240,18 @@ int mppib_init_eval(mppib_engine* e, const float* candidates, const int* strides
 int mppib_sample_trajectories(mppib_engine* e, const float* x0, const float* U_nominal, int distribution,
                               const int* sample_idx, int n, const float* U_opt, float* outputs, float* costs, int* crash);
 
+/* One iteration of Controller::computeControl (controllers/MPPI/mppi_controller.cu:151-241) as ONE call: mppib_solve, then the
+ * host tail on the result with the parameter blobs the engine holds — smoothControlTrajectory (controllers/controller.cuh:
+ * 557-586) and computeStateTrajectory (:643-663) through the library's host twins (host_twins.h).
+ *   U_inout [D][T][C]          in: nominal control, out: the optimised (and, with a history, smoothed) control
+ *   control_history [2][C]     or NULL = no smoothing
+ *   states [D][T][S], outputs [D][T][O]   the nominal roll-forward; both NULL = skip it (user dynamics registered by a plugin
+ *                              have no host twin here: MPPIB_ERR_UNSUPPORTED unless both are NULL)
+ * The header-only controllers keep calling mppib_solve and the host twins separately (their virtual hooks sit in between);
+ * this entry point is for C callers and language bindings, where every call across the boundary costs. */
+int mppib_compute_control(mppib_engine* e, const float* x0, float* U_inout, int optimization_stride, int iteration_num,
+                          const float* control_history, float* states, float* outputs, mppib_solve_stats* stats);
+
 /* Device-side host tail: Controller::smoothControlTrajectoryHelper (controllers/controller.cuh:557-586) and
  * computeOutputTrajectoryHelper (:643-663) as one kernel on the solve's stream — Savitzky-Golay smoothing of the control
  * sequence and the nominal state / output roll-forward (T - 1 step() calls with the constrained controls).

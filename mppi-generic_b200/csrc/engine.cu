@@ -38,6 +38,7 @@
 #include "rollout_kernel_ar_ws.cuh"
 #include "rollout_kernel_nn_tc.cuh"
 #include "engine_internal.cuh"
+#include "../../include/mppi_b200/host_twins.h"
 
 namespace
 {
@@ -1261,6 +1262,7 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
         CUDA_TRY(cudaMalloc(&e->nn_theta_d, nbytes));
       CUDA_TRY(cudaMemcpyAsync(e->nn_theta_d, host, nbytes, cudaMemcpyHostToDevice, e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
+      e->nn_theta_h.assign(w, w + MPPIB_AR_NN_NUM_PARAMS);
       return MPPIB_OK;
     }
     case MPPIB_BLOB_LSTM_WEIGHTS:
@@ -1280,6 +1282,7 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
         CUDA_TRY(cudaMalloc(&e->lstm_theta_d, nbytes));
       CUDA_TRY(cudaMemcpyAsync(e->lstm_theta_d, host, nbytes, cudaMemcpyHostToDevice, e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
+      e->lstm_theta_h.assign(w, w + nbytes / sizeof(float));
       e->have_lstm = true;
       return MPPIB_OK;
     }
@@ -1319,6 +1322,7 @@ int mppib_set_blob(mppib_engine* e, int which, const void* host, size_t nbytes)
                                e->stream));
       CUDA_TRY(cudaStreamSynchronize(e->stream));
       e->elev_hdr = h;
+      e->elev_h.assign((const unsigned char*)host, (const unsigned char*)host + nbytes);
       return MPPIB_OK;
     }
     case MPPIB_BLOB_COSTMAP:
@@ -1665,6 +1669,51 @@ int mppib_solve(mppib_engine* e, const float* x0, const float* U_in, int optimiz
   if (rc != MPPIB_OK)
     return rc;
   return wait_solve(e, U_out, stats);
+}
+
+// One iteration of Controller::computeControl (controllers/MPPI/mppi_controller.cu:151-241) as ONE call: the solve, then the
+// host tail on its result with the parameter blobs the engine was given — smoothControlTrajectory (controller.cuh:557-586) and
+// computeStateTrajectory (:643-663) through the library's host twins.
+int mppib_compute_control(mppib_engine* e, const float* x0, float* U_inout, int optimization_stride, int iteration_num,
+                          const float* control_history, float* states, float* outputs, mppib_solve_stats* stats)
+{
+  int rc = check_ready(e);
+  if (rc != MPPIB_OK)
+    return rc;
+  if (!x0 || !U_inout || (states == nullptr) != (outputs == nullptr))
+    return fail(MPPIB_ERR_INVALID_ARG, "null argument (states and outputs go together)");
+  const int dyn = e->desc.dynamics_id;
+  if (states && dyn >= MPPIB_USER_ID_BASE)
+    return fail(MPPIB_ERR_UNSUPPORTED, "user dynamics have no host twin in the library: roll the state forward in the caller");
+  CUDA_TRY(cudaSetDevice(e->desc.device));
+  rc = enqueue_solve(e, x0, U_inout, optimization_stride, iteration_num);
+  if (rc != MPPIB_OK)
+    return rc;
+  rc = wait_solve(e, U_inout, stats);
+  if (rc != MPPIB_OK)
+    return rc;
+  for (int d = 0; d < e->D; d++)
+  {
+    float* u = U_inout + (size_t)d * e->TC;
+    if (control_history)
+      mppib_host_smooth_controls(u, control_history, e->T, e->C);
+    if (!states)
+      continue;
+    float* st = states + (size_t)d * e->T * e->S;
+    float* out = outputs + (size_t)d * e->T * e->O;
+    if (dyn == MPPIB_DYN_RACER_LSTM)
+    {
+      mppib_host_lstm net{ e->lstm_theta_h.data(), e->desc.model_dims[0], e->desc.model_dims[1], nullptr, nullptr,
+                           e->elev_h.empty() ? nullptr : reinterpret_cast<const mppib_elevation_map_header*>(e->elev_h.data()) };
+      rc = mppib_host_output_trajectory_lstm(e->dyn_blob.data(), &net, x0 + (size_t)d * e->S, u, e->T, e->dt, st, out);
+    }
+    else
+      rc = mppib_host_output_trajectory(dyn, e->dyn_blob.data(), e->nn_theta_h.empty() ? nullptr : e->nn_theta_h.data(),
+                                        x0 + (size_t)d * e->S, u, e->T, e->dt, st, out);
+    if (rc != MPPIB_OK)
+      return fail(rc, "host roll-forward failed for dynamics %d", dyn);
+  }
+  return MPPIB_OK;
 }
 
 int mppib_solve_async(mppib_engine* e, const float* x0, const float* U_in, int optimization_stride, int iteration_num)

@@ -125,6 +125,9 @@ struct mppib_engine
   float* lstm_theta_d = nullptr;  // MPPIB_BLOB_LSTM_WEIGHTS
   bool have_lstm = false;
   float* elev_d = nullptr;               // MPPIB_BLOB_ELEVATION_MAP: width * height floats, row-major
+  // host copies of the weight / map blobs for mppib_compute_control's host tail (the library's host twins)
+  std::vector<float> nn_theta_h, lstm_theta_h;
+  std::vector<unsigned char> elev_h;
   size_t elev_capacity = 0;              // floats allocated
   mppib_elevation_map_header elev_hdr{};  // use == 0 until a map is set
   cudaArray_t costmap_array = nullptr;

@@ -266,7 +266,7 @@ ABI_SYMBOLS = [
     "mppib_host_slide_controls", "mppib_host_output_trajectory", "mppib_host_free_energy",
     "mppib_host_merge_records", "mppib_host_step_lstm", "mppib_host_output_trajectory_lstm",
     "mppib_host_elevation_at_world_pose", "mppib_host_static_settling", "mppib_host_lstm_initialize",
-    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_nominal_trajectory", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
+    "mppib_set_rmppi", "mppib_init_eval", "mppib_set_tsallis", "mppib_sample_trajectories", "mppib_nominal_trajectory", "mppib_compute_control", "mppib_host_npz_read", "mppib_comm_p2p_handle", "mppib_comm_p2p_open", "mppib_host_rmppi_line_search_weights", "mppib_host_rmppi_candidates",
     "mppib_host_rmppi_best_index",
 ]
 
@@ -337,6 +337,7 @@ def lib() -> C.CDLL:
                                       ip]
     L.mppib_sample_trajectories.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]
     L.mppib_nominal_trajectory.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.mppib_compute_control.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(SolveStats)]
     L.mppib_load_plugin.argtypes = [C.c_char_p]
     _lib = L
     return L
@@ -1206,6 +1207,19 @@ class Engine:
                                                None if U_opt is None else _ptr(_f32(U_opt)), _ptr(outputs), _ptr(costs),
                                                crash.ctypes.data_as(C.c_void_p)))
         return outputs, costs, crash
+
+    def compute_control(self, x0, U, control_history=None, optimization_stride: int = 1, iteration_num: int = 0,
+                        roll_forward: bool = True):
+        """mppib_compute_control: the solve plus the host tail (smoothing, nominal roll-forward) in one C call. Returns
+        (U [D][T][C] optimised and smoothed, states [D][T][S] or None, outputs [D][T][O] or None, stats)."""
+        U = _f32(U).copy()
+        states = np.empty((self.D, self.T, self.dyn.STATE_DIM), np.float32) if roll_forward else None
+        outputs = np.empty((self.D, self.T, self.dyn.OUTPUT_DIM), np.float32) if roll_forward else None
+        stats = (SolveStats * self.D)()
+        _check(lib().mppib_compute_control(self._h, _ptr(_f32(x0)), _ptr(U), optimization_stride, iteration_num,
+                                           None if control_history is None else _ptr(_f32(control_history)),
+                                           _ptr(states), _ptr(outputs), stats))
+        return U, states, outputs, [(s.baseline, s.normalizer, s.sum_w2) for s in stats]
 
     def nominal_trajectory(self, x0, U=None, control_history=None):
         """mppib_nominal_trajectory: the host tail of computeControl on the device (controller.cuh:557-586, 643-663).

@@ -97,3 +97,30 @@ def test_controller_mirror_with_the_device_side_tail():
     u_d, s_d = run(True)
     np.testing.assert_allclose(u_d, u_h, atol=2e-4 * max(1.0, float(np.abs(u_h).max())))
     np.testing.assert_allclose(s_d, s_h, atol=2e-4 * max(1.0, float(np.abs(s_h).max())))
+
+
+@pytest.mark.parametrize("name", ["cartpole", "double_integrator_tube", "autorally", "racer_lstm", "quadrotor"])
+def test_compute_control_is_solve_plus_host_tail(name):
+    """mppib_compute_control = mppib_solve followed by the library's host twins on its result (SG smoothing, nominal
+    roll-forward): bit-identical to doing the three calls separately, two closed-loop rounds."""
+    w = CASES[name]()
+    if name == "racer_lstm":  # with an elevation map, so that the engine-held host copy of the map is exercised too
+        j, i = np.meshgrid(np.arange(64), np.arange(64))
+        w.dyn.setElevationMap((0.3 * np.sin(0.2 * j) * np.cos(0.15 * i)).astype(np.float32), 0.5, (-8.0, -16.0, 0.0))
+    a, b = w.make_engine(), w.make_engine()
+    x0 = np.ascontiguousarray(w.x0, np.float32)
+    hist = np.zeros((2, w.dyn.CONTROL_DIM), np.float32)
+    Ua = Ub = np.ascontiguousarray(w.U0, np.float32)
+    for it in range(2):
+        Ua, st_a, out_a, stats_a = a.compute_control(x0, Ua, hist)
+        Us, stats_b = b.solve(x0, Ub)
+        Ub, st_b, out_b = _host_tail(w, x0, Us, hist)
+        assert np.array_equal(Ua, Ub), it
+        assert np.array_equal(st_a, st_b) and np.array_equal(np.nan_to_num(out_a), np.nan_to_num(out_b)), it
+        assert stats_a == stats_b
+        hist = Ua[0, :2].copy()
+    # without the roll-forward / without smoothing
+    U2, st2, out2, _ = a.compute_control(x0, w.U0, None, roll_forward=False)
+    assert st2 is None and out2 is None and np.isfinite(U2).all()
+    a.close()
+    b.close()
