@@ -156,3 +156,29 @@ def test_device_tail_over_an_elevation_map_matches_the_host_twin():
     assert (np.abs(st_d[0] - st_h) / scale).max() < 1e-4
     np.testing.assert_allclose(np.nan_to_num(out_d[0][:, 4]), np.nan_to_num(out_h[:, 4]), atol=1e-4)  # BASELINK_POS_I_Z
     e.close()
+
+
+def test_texture_query_against_an_independent_interpolator():
+    """The oracle's (and the product host twin's) queryTextureAtWorldPose against scipy's order-1 `map_coordinates` with edge
+    extension (= clamp addressing) on a random map with a rotated, shifted frame: an independent formulation in float64."""
+    from scipy.ndimage import map_coordinates
+    rng = np.random.default_rng(11)
+    w, h, res = 37, 29, 0.4
+    vals = rng.standard_normal((h, w)).astype(np.float32)
+    c, s = np.cos(0.6), np.sin(0.6)
+    rot = np.array([[c, s, 0.0], [-s, c, 0.0], [0.0, 0.0, 1.0]])
+    origin = np.array([1.5, -2.0, 0.3])
+    t = H.TwoDTextureHelper()
+    t.setExtent(0, w, h)
+    t.updateTexture(0, vals)
+    t.updateRotation(0, rot)
+    t.updateOrigin(0, origin)
+    t.updateResolution(0, res)
+    t.enableTexture(0)
+    pts = rng.uniform(-6.0, 18.0, size=(400, 3))
+    m = (rot @ (pts - origin).T).T                         # world -> map frame
+    qx, qy = m[:, 0] / res - 0.5, m[:, 1] / res - 0.5       # cell-centre convention (two_d_texture_helper.cu:157-160)
+    ref = map_coordinates(vals.astype(np.float64), [np.clip(qy, 0, h - 1), np.clip(qx, 0, w - 1)], order=1, mode="nearest")
+    for p, r in zip(pts, ref):
+        assert oracle.elevation_at_world_pose(t.blob(), *p) == pytest.approx(r, abs=2e-5)
+        assert t.queryTextureAtWorldPose(0, p) == pytest.approx(r, abs=2e-5)
